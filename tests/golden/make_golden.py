@@ -1,0 +1,283 @@
+#!/usr/bin/env python
+"""Generate the committed golden fixtures by executing the UNMODIFIED reference sources.
+
+Runs only in the build container (needs /root/reference):   python tests/golden/make_golden.py
+
+  ppo_small.npz     core/common.py estimate_advantages, core/policy_gaussian.py, core/critic.py,
+                    agents/agent_ppo.py update_policy (3 epochs, torch Adam, grad-norm clip) on a seeded
+                    synthetic trajbatch with small layer sizes (fixture size), float64
+  math_helpers.npz  utils/math.py + utils/transformation.py helpers on random inputs
+  zfilter.npz       utils/zfilter.py sequential filtering
+  env_traj.npz      ego_pose/envs/humanoid_v1.py + ego_pose/core/reward_function.py stepped on the
+                    restated physics through oracle/mujoco_shim.py (pins env logic, NOT MuJoCo itself),
+                    and the gen_expert.py feature pipeline re-driven with the reference's own helpers
+"""
+import os
+import pickle
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+from oracle import cphys, mujoco_shim, refimport  # noqa: E402
+
+refimport.install()
+import torch  # noqa: E402
+
+torch.set_default_dtype(torch.float64)
+
+
+def gen_ppo():
+    from agents.agent_ppo import AgentPPO
+    from core.common import estimate_advantages
+    from core.critic import Value
+    from core.policy_gaussian import PolicyGaussian
+    from models.mlp import MLP
+
+    torch.manual_seed(1)
+    rng = np.random.RandomState(1)
+    N, D, A, H = 640, 24, 6, (32, 16)
+    policy = PolicyGaussian(MLP(D, H, 'relu'), A, log_std=-2.3, fix_std=True)
+    value = Value(MLP(D, H, 'relu'))
+    states = rng.randn(N, D)
+    masks = np.ones(N)
+    ends = np.sort(rng.choice(N - 1, size=24, replace=False))
+    masks[ends] = 0
+    masks[-1] = 0
+    rewards = rng.rand(N)
+    exps = (rng.rand(N) > 0.1).astype(np.float64)
+    with torch.no_grad():
+        mean = policy(torch.from_numpy(states)).loc.numpy()
+    actions = mean + np.exp(-2.3) * rng.randn(N, A) * 1.5
+    out = dict(states=states, actions=actions, masks=masks, rewards=rewards, exps=exps)
+    for k, v in policy.state_dict().items():
+        out['p0.' + k] = v.numpy().copy()
+    for k, v in value.state_dict().items():
+        out['v0.' + k] = v.numpy().copy()
+    st, ac = torch.from_numpy(states), torch.from_numpy(actions)
+    with torch.no_grad():
+        values = value(st)
+        out['values0'] = values.numpy().copy()
+    adv, ret = estimate_advantages(torch.from_numpy(rewards), torch.from_numpy(masks), values, 0.95, 0.95)
+    out['advantages'], out['returns'] = adv.numpy().copy(), ret.numpy().copy()
+    with torch.no_grad():
+        out['fixed_log_probs'] = policy.get_log_prob(st, ac).numpy().copy()
+
+    opt_p = torch.optim.Adam(policy.parameters(), lr=5e-3)
+    opt_v = torch.optim.Adam(value.parameters(), lr=3e-3)
+    pparams = list(policy.parameters())
+    agent = AgentPPO(env=None, dtype=torch.float64, device=torch.device('cpu'), policy_net=policy, value_net=value,
+                     optimizer_policy=opt_p, optimizer_value=opt_v, opt_num_epochs=3, gamma=0.95, tau=0.95,
+                     clip_epsilon=0.2, policy_grad_clip=[(pparams, 0.05)], use_mini_batch=False)
+    ex = torch.from_numpy(exps)
+    surr, vloss, gnorm = [], [], []
+    # wrap to record per-epoch losses (calls the reference's own ppo_loss / update_value unchanged)
+    orig_loss = agent.ppo_loss
+
+    def rec_loss(*a):
+        loss = orig_loss(*a)
+        surr.append(loss.item())
+        return loss
+    agent.ppo_loss = rec_loss
+    orig_clip = agent.clip_policy_grad
+
+    def rec_clip():
+        gnorm.append(float(torch.sqrt(sum((p.grad ** 2).sum() for p in pparams if p.grad is not None))))
+        orig_clip()
+    agent.clip_policy_grad = rec_clip
+    orig_uv = agent.update_value
+
+    def rec_uv(s_, r_):
+        with torch.no_grad():
+            vloss.append(float((value(s_) - r_).pow(2).mean()))
+        orig_uv(s_, r_)
+    agent.update_value = rec_uv
+    agent.update_policy(st, ac, ret, adv, ex)
+    out['surr_loss'], out['value_loss'], out['grad_norm'] = np.array(surr), np.array(vloss), np.array(gnorm)
+    for k, v in policy.state_dict().items():
+        out['p3.' + k] = v.numpy().copy()
+    for k, v in value.state_dict().items():
+        out['v3.' + k] = v.numpy().copy()
+    out['hyper'] = np.array([0.95, 0.95, 0.2, 5e-3, 3e-3, 0.05])   # gamma tau clip lr_p lr_v max_norm
+    np.savez_compressed(os.path.join(OUT, 'ppo_small.npz'), **out)
+    print('ppo_small: surr', surr, 'vloss', vloss, 'gnorm', gnorm)
+
+
+def gen_math():
+    from utils.math import (de_heading, get_angvel_fd, get_heading_q, get_qvel_fd, multi_quat_diff, multi_quat_norm,
+                            transform_vec)
+    from utils.transformation import (quaternion_from_euler, quaternion_inverse, quaternion_matrix,
+                                      quaternion_multiply, rotation_from_quaternion)
+    rng = np.random.RandomState(7)
+    n = 16
+    q = rng.randn(n, 4)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    q2 = rng.randn(n, 4)
+    q2 /= np.linalg.norm(q2, axis=1, keepdims=True)
+    v = rng.randn(n, 3)
+    eul = rng.uniform(-2, 2, size=(n, 3))
+    qa = np.concatenate([rng.randn(n, 3), q, rng.randn(n, 52)], axis=1)
+    dq = rng.randn(n, 3) * 0.05
+    qb = qa.copy()
+    qb[:, :3] += rng.randn(n, 3) * 0.02
+    qb[:, 7:] += rng.randn(n, 52) * 0.03
+    for i in range(n):   # small relative rotation
+        ang = np.linalg.norm(dq[i])
+        dqq = np.concatenate([[np.cos(ang / 2)], np.sin(ang / 2) * dq[i] / ang])
+        qb[i, 3:7] = quaternion_multiply(dqq, qa[i, 3:7])
+    qb[0, 3:7] = qa[0, 3:7]         # identical rotation -> 1 - w < 1e-8 branch
+    bq0 = rng.randn(n, 21, 4)
+    bq0 /= np.linalg.norm(bq0, axis=2, keepdims=True)
+    bq1 = bq0 + 0.05 * rng.randn(n, 21, 4)
+    bq1 /= np.linalg.norm(bq1, axis=2, keepdims=True)
+    out = dict(q=q, q2=q2, v=v, eul=eul, qa=qa, qb=qb, bq0=bq0.reshape(n, 84), bq1=bq1.reshape(n, 84))
+    out['mul'] = np.stack([quaternion_multiply(q[i], q2[i]) for i in range(n)])
+    out['inv'] = np.stack([quaternion_inverse(q[i] * (1 + 0.1 * i)) for i in range(n)])
+    out['inv_in'] = np.stack([q[i] * (1 + 0.1 * i) for i in range(n)])
+    out['from_euler'] = np.stack([quaternion_from_euler(*eul[i]) for i in range(n)])
+    out['matrix'] = np.stack([quaternion_matrix(q[i] * (1 + 0.1 * i))[:3, :3] for i in range(n)])
+    out['rot_from_quat'] = np.stack([rotation_from_quaternion(q[i]) for i in range(n)])
+    out['heading_q'] = np.stack([get_heading_q(q[i]) for i in range(n)])
+    out['de_heading'] = np.stack([de_heading(q[i]) for i in range(n)])
+    out['tv_root'] = np.stack([transform_vec(v[i], q[i], 'root') for i in range(n)])
+    out['tv_heading'] = np.stack([transform_vec(v[i], q[i], 'heading') for i in range(n)])
+    out['qvel_fd_none'] = np.stack([get_qvel_fd(qa[i], qb[i], 1 / 30.0) for i in range(n)])
+    out['qvel_fd_heading'] = np.stack([get_qvel_fd(qa[i], qb[i], 1 / 30.0, 'heading') for i in range(n)])
+    out['angvel_fd'] = np.stack([get_angvel_fd(out['bq0'][i], out['bq1'][i], 1 / 30.0) for i in range(n)])
+    diff = np.stack([multi_quat_diff(out['bq1'][i], out['bq0'][i]) for i in range(n)])
+    out['quat_diff'] = diff
+    out['quat_norm'] = np.stack([multi_quat_norm(diff[i]) for i in range(n)])
+    np.savez_compressed(os.path.join(OUT, 'math_helpers.npz'), **out)
+    print('math_helpers ok')
+
+
+def gen_zfilter():
+    from utils.zfilter import ZFilter
+    rng = np.random.RandomState(3)
+    xs = rng.randn(40, 9) * rng.uniform(0.1, 20, size=9) + rng.randn(9)
+    zf = ZFilter((9,), clip=5)
+    ys = np.stack([zf(x) for x in xs])
+    frozen = np.stack([zf(x, update=False) for x in xs[:5]])
+    np.savez_compressed(os.path.join(OUT, 'zfilter.npz'), xs=xs, ys=ys, frozen=frozen, n=zf.rs.n, mean=zf.rs.mean,
+                        std=zf.rs.std, S=zf.rs._S)
+    print('zfilter ok')
+
+
+def gen_env():
+    orc = cphys.Oracle()
+    mujoco_shim.install(orc)
+    work = tempfile.mkdtemp(prefix='egopose_golden_')
+    os.symlink(os.path.join(refimport.REF, 'config'), os.path.join(work, 'config'))
+    os.symlink(os.path.join(refimport.REF, 'assets'), os.path.join(work, 'assets'))
+    os.makedirs(os.path.join(work, 'datasets', 'meta'))
+    os.makedirs(os.path.join(work, 'datasets', 'features'))
+    take_names = ['take_a', 'take_b']
+    import yaml
+    yaml.safe_dump({'train': take_names, 'test': take_names},
+                   open(os.path.join(work, 'datasets', 'meta', 'meta_subject_03.yml'), 'w'))
+    os.chdir(work)
+
+    from ego_pose.core.reward_function import quat_space_reward_v3
+    from ego_pose.envs.humanoid_v1 import HumanoidEnv
+    from ego_pose.utils.egomimic_config import Config
+    from utils.math import de_heading, get_angvel_fd, get_qvel_fd, transform_vec
+
+    L, EPLEN = 48, 10
+    takes = cphys.synthetic_takes(orc.md, 2, L, seed=5)
+    cfg = Config('subject_03', create_dirs=False)
+    cfg.env_episode_len = EPLEN
+    env = HumanoidEnv(cfg)
+    env.seed(1)
+
+    # ---- gen_expert.py:28-83 re-driven with the reference's own env methods / helpers -----------
+    def get_expert(expert_qpos):
+        keys = ['qvel', 'rlinv', 'rlinv_local', 'rangv', 'rq_rmh', 'head_pos', 'ee_pos', 'bquat', 'bangvel']
+        ex = {k: [] for k in keys}
+        for i in range(expert_qpos.shape[0]):
+            qpos = expert_qpos[i]
+            env.data.qpos[:] = qpos
+            env.sim.forward()
+            ex['rq_rmh'].append(de_heading(qpos[3:7]))
+            ex['ee_pos'].append(env.get_ee_pos(cfg.obs_coord))
+            ex['bquat'].append(env.get_body_quat())
+            ex['head_pos'].append(env.get_body_com('Head').copy())
+            if i > 0:
+                qvel = get_qvel_fd(expert_qpos[i - 1], qpos, env.dt)
+                ex['qvel'].append(qvel)
+                ex['rlinv'].append(qvel[:3].copy())
+                ex['rlinv_local'].append(transform_vec(qvel[:3].copy(), qpos[3:7], cfg.obs_coord))
+                ex['rangv'].append(qvel[3:6].copy())
+        for k in ('qvel', 'rlinv', 'rlinv_local', 'rangv'):
+            ex[k].insert(0, ex[k][0].copy())
+        for i in range(1, expert_qpos.shape[0]):
+            ex['bangvel'].append(get_angvel_fd(ex['bquat'][i - 1], ex['bquat'][i], env.dt))
+        ex['bangvel'].insert(0, ex['bangvel'][0].copy())
+        out = {k: np.vstack(v) for k, v in ex.items()}
+        out['qpos'] = expert_qpos
+        out['len'] = expert_qpos.shape[0]
+        out['height_lb'] = expert_qpos[:, 2].min()
+        out['head_height_lb'] = out['head_pos'][:, 2].min()
+        return out
+
+    expert_dict = {n: get_expert(q) for n, q in zip(take_names, takes)}
+    cnn = {n: np.random.RandomState(11).randn(L, 128) for n in take_names}
+    pickle.dump(expert_dict, open(cfg.expert_feat_file, 'wb'))
+    pickle.dump((cnn, {}), open(cfg.cnn_feat_file, 'wb'))
+    env.load_experts(take_names, cfg.expert_feat_file, cfg.cnn_feat_file)
+
+    out = dict(takes_qpos=np.stack(takes), episode_len=EPLEN)
+    for k in ('qvel', 'rlinv_local', 'rangv', 'rq_rmh', 'ee_pos', 'bquat', 'bangvel'):
+        out['expert.' + k] = np.stack([expert_dict[n][k] for n in take_names])
+    out['expert.head_height_lb'] = np.array([expert_dict[n]['head_height_lb'] for n in take_names])
+
+    # ---- episodes --------------------------------------------------------------------------------
+    rng = np.random.RandomState(21)
+    episodes = [dict(take=0, start=12, head_lb=None, end_reward=0.0),       # natural fail rule
+                dict(take=1, start=15, head_lb=-10.0, end_reward=1.7)]      # runs to the time limit
+    for ei, ep in enumerate(episodes):
+        env.set_fix_sampling(expert_ind=ep['take'], start_ind=ep['start'])
+        env.set_fix_head_lb(ep['head_lb'])
+        env.end_reward = ep['end_reward']
+        obs0 = env.reset()
+        rec = dict(obs=[obs0], qpos=[env.data.qpos.copy()], qvel=[env.data.qvel.copy()], reward=[], c_info=[], fail=[],
+                   end=[], action=[], head_z=[], torque0=[], qM_diag=[], bias=[])
+        for t in range(EPLEN + 3):
+            action = 0.3 * rng.randn(env.model.nu)
+            rec['torque0'].append(env.compute_torque(cfg.a_ref + action * cfg.a_scale))   # PD torque at sub-step 0
+            obs, _r, done, info = env.step(action)
+            rew, c_info = quat_space_reward_v3(env, None, action, info)
+            rec['action'].append(action)
+            rec['obs'].append(obs)
+            rec['qpos'].append(env.data.qpos.copy())
+            rec['qvel'].append(env.data.qvel.copy())
+            rec['reward'].append(rew)
+            rec['c_info'].append(c_info)
+            rec['fail'].append(info['fail'])
+            rec['end'].append(info['end'])
+            rec['head_z'].append(env.get_body_com('Head')[2])
+            rec['bias'].append(env.data.qfrc_bias.copy())
+            if done:
+                break
+        for k, v in rec.items():
+            out['ep%d.%s' % (ei, k)] = np.array(v)
+        out['ep%d.meta' % ei] = np.array([ep['take'], ep['start'], np.nan if ep['head_lb'] is None else ep['head_lb'],
+                                          ep['end_reward']])
+        print('episode', ei, 'steps', len(rec['reward']), 'fail', rec['fail'][-1], 'end', rec['end'][-1],
+              'rewards', np.round(rec['reward'], 4))
+    np.savez_compressed(os.path.join(OUT, 'env_traj.npz'), **out)
+
+
+if __name__ == '__main__':
+    which = sys.argv[1:] or ['ppo', 'math', 'zfilter', 'env']
+    if 'ppo' in which:
+        gen_ppo()
+    if 'math' in which:
+        gen_math()
+    if 'zfilter' in which:
+        gen_zfilter()
+    if 'env' in which:
+        gen_env()
