@@ -1,0 +1,34 @@
+// Shared host/device helpers for the egopose_b200 C-ABI library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/egopose_b200.h"
+
+namespace egp {
+
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what);
+
+#define EGP_CUDA(call)                                             \
+    do {                                                           \
+        cudaError_t _e = (call);                                   \
+        if (_e != cudaSuccess) return egp::cuda_fail(_e, #call);   \
+    } while (0)
+
+#define EGP_CHECK_LAUNCH(name)                                     \
+    do {                                                           \
+        cudaError_t _e = cudaGetLastError();                       \
+        if (_e != cudaSuccess) return egp::cuda_fail(_e, name);    \
+    } while (0)
+
+int num_sms(int device = -1);
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace egp

@@ -1,0 +1,1152 @@
+// Fused humanoid rollout (K1 physics + K2 policy/sample + K3 reward/done/reset/trajbatch) - sm_100a, f64.
+//
+// Replaces Agent.sample / sample_worker (agents/agent.py:29-111) + HumanoidEnv.step/reset
+// (ego_pose/envs/humanoid_v1.py:130-231) + quat_space_reward_v3 (ego_pose/core/reward_function.py:4-60)
+// + the MuJoCo calls behind them (mj_forward / mj_step / mj_fullM) + the dense LAPACK solve of the
+// stable-PD controller.
+//
+// Dynamics formulation (same results as the reference's CRBA + dense Cholesky, O(n) instead of O(n^3)):
+//   * every spatial quantity is expressed in world axes about the point O = current root position
+//   * bias force C = RNE(q, v, 0) by one forward (velocities / bias accelerations) and one backward
+//     (force accumulation) sweep over the kinematic tree
+//   * both linear solves  qacc = M^-1 (tau - C)  and  q**  = (M + Kd h)^-1 rhs  are articulated-body
+//     sweeps (Featherstone): the diagonal terms (armature, Kd h) enter the joint-space pivots D_i
+//   * the stable-PD solve of sub-step k runs BEFORE the kinematics refresh, i.e. on the tree data of
+//     sub-step k-1 - exactly the one-sub-step staleness of data.qM / data.qfrc_bias in the reference
+//     (humanoid_v1.py:134-136); head / end-effector positions are taken from the
+//     last refresh (state before the last sub-step, appendix C.2)
+// Mapping (V1): one thread per environment, CTA = 32 environments; tree data in thread-local arrays,
+// policy activations staged in shared memory [feature][env] (bank-conflict free), model constants in
+// __constant__ memory (warp-uniform indices -> broadcast), policy weights pre-transposed/padded and read
+// through the uniform L1/L2 path.
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace egp {
+
+constexpr int MAXB = EGP_MAX_BODY;
+constexpr int MAXV = EGP_MAX_DOF;
+constexpr int MAXC = EGP_MAX_CHAIN;
+constexpr int ENVS_PER_CTA = 32;
+constexpr int JB = 8;                       // output neurons per register block in the policy MLP
+
+struct DevModel {
+    int nq, nv, nu, nbody, nchain, frame_skip, head_body, v_ord, decay;
+    int ee_body[EGP_NEE];
+    double h, grav[3];
+    int body_parent[MAXB], body_dofadr[MAXB], body_dofnum[MAXB], body_qposadr[MAXB], body_chain[MAXB];
+    double body_pos[MAXB][3], body_mass[MAXB], body_ipos[MAXB][3], body_inertia[MAXB][6], b_diffw[MAXB];
+    int dof_axis_id[MAXV];
+    double dof_arm[MAXV], dof_axis[MAXV][3], dof_anchor[MAXV][3];
+    double kp[MAXV], kd[MAXV], a_ref[MAXV], a_scale[MAXV], tlim[MAXV];        // indexed by dof (0 on the root)
+    int chain_lo[MAXC], chain_hi[MAXC], chain_parent[MAXC];                   // body ranges, inclusive
+    double w_p, w_v, w_e, w_rp, w_rv, k_p, k_v, k_e, k_rh, k_rq, k_rl, k_ra;
+};
+
+__constant__ DevModel c_m;
+
+}  // namespace egp
+
+struct EgpModel {
+    egp::DevModel host;
+    int device;
+    int n_takes, ctx_dim;
+    long long total_frames;
+    int32_t *d_take_off;
+    double *d_rows, *d_head_lb, *d_ctx;
+    // transposed / padded policy weights (scratch owned by the model)
+    double *d_wbuf;
+    size_t wbuf_elems;
+};
+
+namespace egp {
+
+static const EgpModel *g_bound_model[64] = {nullptr};
+
+static int bind_model(const EgpModel *m) {
+    int dev = m->device;
+    if (dev >= 0 && dev < 64 && g_bound_model[dev] == m) return EGP_OK;
+    EGP_CUDA(cudaMemcpyToSymbol(c_m, &m->host, sizeof(DevModel)));
+    if (dev >= 0 && dev < 64) g_bound_model[dev] = m;
+    return EGP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// small device math
+__device__ __forceinline__ void cross3(const double *a, const double *b, double *o) {
+    double x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+    o[0] = x; o[1] = y; o[2] = z;
+}
+__device__ __forceinline__ double dot3(const double *a, const double *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+__device__ __forceinline__ double dot6(const double *a, const double *b) {
+    return a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3] + a[4] * b[4] + a[5] * b[5];
+}
+// quaternion helpers (w, x, y, z), utils/transformation.py:1379-1421 conventions
+__device__ __forceinline__ void quat_mul(const double *q1, const double *q0, double *o) {
+    double w0 = q0[0], x0 = q0[1], y0 = q0[2], z0 = q0[3], w1 = q1[0], x1 = q1[1], y1 = q1[2], z1 = q1[3];
+    o[0] = -x1 * x0 - y1 * y0 - z1 * z0 + w1 * w0;
+    o[1] = x1 * w0 + y1 * z0 - z1 * y0 + w1 * x0;
+    o[2] = -x1 * z0 + y1 * w0 + z1 * x0 + w1 * y0;
+    o[3] = x1 * y0 - y1 * x0 + z1 * w0 + w1 * z0;
+}
+__device__ __forceinline__ void quat_inv(const double *q, double *o) {
+    double n = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+    o[0] = q[0] / n; o[1] = -q[1] / n; o[2] = -q[2] / n; o[3] = -q[3] / n;
+}
+__device__ __forceinline__ void quat_to_mat(const double *q, double *R) {      // unit quaternion
+    double w = q[0], x = q[1], y = q[2], z = q[3];
+    R[0] = w * w + x * x - y * y - z * z; R[1] = 2 * (x * y - w * z);           R[2] = 2 * (x * z + w * y);
+    R[3] = 2 * (x * y + w * z);           R[4] = w * w - x * x + y * y - z * z; R[5] = 2 * (y * z - w * x);
+    R[6] = 2 * (x * z - w * y);           R[7] = 2 * (y * z + w * x);           R[8] = w * w - x * x - y * y + z * z;
+}
+// utils/math.py:62-67,80-81: heading quaternion (w,0,0,z)/|.| and de_heading
+__device__ __forceinline__ void heading_cs(const double *q, double *hw, double *hz) {
+    double n = sqrt(q[0] * q[0] + q[3] * q[3]);
+    *hw = q[0] / n; *hz = q[3] / n;
+}
+__device__ __forceinline__ void de_heading(const double *q, double *o) {
+    double hw, hz;
+    heading_cs(q, &hw, &hz);
+    double hq[4] = {hw, 0.0, 0.0, hz}, ih[4];
+    quat_inv(hq, ih);
+    quat_mul(ih, q, o);
+}
+// utils/math.py:47-59 transform_vec(v, q, 'heading'): R(hq)^T v with quaternion_matrix's normalisation
+__device__ __forceinline__ void to_heading(const double *v, const double *q, double *o) {
+    double hw, hz;
+    heading_cs(q, &hw, &hz);
+    double n = hw * hw + hz * hz, s = 2.0 / n;
+    double czz = hz * hz * s, cwz = hw * hz * s;        // R = [[1-czz, -cwz, 0], [cwz, 1-czz, 0], [0, 0, 1]]
+    double x = (1.0 - czz) * v[0] + cwz * v[1];
+    double y = -cwz * v[0] + (1.0 - czz) * v[1];
+    o[0] = x; o[1] = y; o[2] = v[2];
+}
+// utils/math.py:47-59 transform_vec(v, q, 'root')
+__device__ __forceinline__ void to_root(const double *v, const double *quat, double *o) {
+    double n = quat[0] * quat[0] + quat[1] * quat[1] + quat[2] * quat[2] + quat[3] * quat[3];
+    double s = sqrt(2.0 / n);
+    double q0 = quat[0] * s, q1 = quat[1] * s, q2 = quat[2] * s, q3 = quat[3] * s;
+    double R0 = 1.0 - q2 * q2 - q3 * q3, R1 = q1 * q2 - q3 * q0, R2 = q1 * q3 + q2 * q0;
+    double R3 = q1 * q2 + q3 * q0, R4 = 1.0 - q1 * q1 - q3 * q3, R5 = q2 * q3 - q1 * q0;
+    double R6 = q1 * q3 - q2 * q0, R7 = q2 * q3 + q1 * q0, R8 = 1.0 - q1 * q1 - q2 * q2;
+    double x = R0 * v[0] + R3 * v[1] + R6 * v[2], y = R1 * v[0] + R4 * v[1] + R7 * v[2], z = R2 * v[0] + R5 * v[1] + R8 * v[2];
+    o[0] = x; o[1] = y; o[2] = z;
+}
+// utils/transformation.py:348-356 rotation_from_quaternion -> axis * angle
+__device__ __forceinline__ void rot_from_quat(const double *q, double *o, double *angle_out) {
+    if (1.0 - q[0] < 1e-8) { o[0] = o[1] = o[2] = 0.0; *angle_out = 0.0; return; }
+    double s = sqrt(1.0 - q[0] * q[0]), ang = 2.0 * acos(q[0]);
+    o[0] = q[1] / s; o[1] = q[2] / s; o[2] = q[3] / s;
+    *angle_out = ang;
+}
+// utils/transformation.py:1194-1248 quaternion_from_euler(.., 'sxyz')
+__device__ __forceinline__ void quat_from_euler(double ai, double aj, double ak, double *q) {
+    double si, ci, sj, cj, sk, ck;
+    sincos(0.5 * ai, &si, &ci);
+    sincos(0.5 * aj, &sj, &cj);
+    sincos(0.5 * ak, &sk, &ck);
+    double cc = ci * ck, cs = ci * sk, sc = si * ck, ss = si * sk;
+    q[0] = cj * cc + sj * ss; q[1] = cj * sc - sj * cs; q[2] = cj * ss + sj * cc; q[3] = cj * cs - sj * sc;
+}
+
+// symmetric 6x6 in packed upper storage
+__device__ __forceinline__ constexpr int sx(int r, int c) { return r <= c ? r * 6 - r * (r - 1) / 2 + (c - r) : c * 6 - c * (c - 1) / 2 + (r - c); }
+
+// spatial inertia (m, h = m c, I_O) applied to a motion vector [w; v]
+__device__ __forceinline__ void spi_mul(const double *ci /*10*/, const double *x, double *f) {
+    const double m = ci[0], *hh = ci + 1, *I = ci + 4;
+    double hxl[3], hxw[3];
+    cross3(hh, x + 3, hxl);
+    cross3(hh, x, hxw);
+    f[0] = I[0] * x[0] + I[3] * x[1] + I[4] * x[2] + hxl[0];
+    f[1] = I[3] * x[0] + I[1] * x[1] + I[5] * x[2] + hxl[1];
+    f[2] = I[4] * x[0] + I[5] * x[1] + I[2] * x[2] + hxl[2];
+    f[3] = m * x[3] - hxw[0];
+    f[4] = m * x[4] - hxw[1];
+    f[5] = m * x[5] - hxw[2];
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-environment scratch (thread-local)
+struct Fwd {            // forward carry along a chain: body frame (relative to O), spatial velocity, bias accel
+    double p[3], R[9], v[6], a[6];
+};
+struct Bwd {            // backward carry: articulated inertia, bias force of the pure solve, RNE force
+    double IA[21], pA[6], F[6];
+};
+
+struct EnvData {
+    double q[MAXV + 1], v[MAXV];
+    double S[MAXV][6], U[MAXV][6], Dinv[MAXV], u[MAXV];
+    double C[MAXV], tau[MAXV], qacc[MAXV];
+    double cin[MAXB][10], fb[MAXB][6];
+    double xp[MAXB][3];                 // body positions (world) from the last kinematics refresh
+    Fwd jf[MAXC];
+    Bwd jb[MAXC];
+    double ja[MAXC][6];
+};
+
+// F1: kinematics + velocities + bias accelerations + body inertias/forces at (q, v); refreshes S, cin, fb, xp.
+__device__ void pass_kinematics(EnvData &e) {
+    const int nchain = c_m.nchain;
+    for (int c = 0; c < nchain; c++) {
+        Fwd f;
+        const int pc = c_m.chain_parent[c];
+        if (pc >= 0) f = e.jf[pc];
+        for (int b = c_m.chain_lo[c]; b <= c_m.chain_hi[c]; b++) {
+            const int da = c_m.body_dofadr[b], nd = c_m.body_dofnum[b], qa = c_m.body_qposadr[b];
+            if (nd == 6) {
+                // free joint; O = root position, so the frame origin is 0 and rotational cdofs have no linear part
+                double qn[4], n = sqrt(e.q[qa + 3] * e.q[qa + 3] + e.q[qa + 4] * e.q[qa + 4] + e.q[qa + 5] * e.q[qa + 5] +
+                                       e.q[qa + 6] * e.q[qa + 6]);
+                for (int k = 0; k < 4; k++) qn[k] = e.q[qa + 3 + k] / n;
+                quat_to_mat(qn, f.R);
+                f.p[0] = f.p[1] = f.p[2] = 0.0;
+                double wl[3] = {e.v[da + 3], e.v[da + 4], e.v[da + 5]}, ww[3];
+                for (int r = 0; r < 3; r++) ww[r] = f.R[3 * r] * wl[0] + f.R[3 * r + 1] * wl[1] + f.R[3 * r + 2] * wl[2];
+                for (int k = 0; k < 3; k++) {
+                    for (int r = 0; r < 6; r++) { e.S[da + k][r] = 0.0; e.S[da + 3 + k][r] = 0.0; }
+                    e.S[da + k][3 + k] = 1.0;
+                    for (int r = 0; r < 3; r++) e.S[da + 3 + k][r] = f.R[3 * r + k];
+                }
+                double vl[3] = {e.v[da], e.v[da + 1], e.v[da + 2]}, vxw[3];
+                cross3(vl, ww, vxw);            // sum_k ([0;v] x [R e_k;0]) w_k = [0; v x (R w)]
+                for (int k = 0; k < 3; k++) {
+                    f.v[k] = ww[k]; f.v[3 + k] = vl[k];
+                    f.a[k] = 0.0; f.a[3 + k] = -c_m.grav[k] + vxw[k];
+                }
+            } else {
+                // frame before the joints: parent frame shifted by body_pos
+                double off[3];
+                for (int r = 0; r < 3; r++)
+                    off[r] = f.R[3 * r] * c_m.body_pos[b][0] + f.R[3 * r + 1] * c_m.body_pos[b][1] + f.R[3 * r + 2] * c_m.body_pos[b][2];
+                for (int r = 0; r < 3; r++) f.p[r] += off[r];
+                for (int j = 0; j < nd; j++) {
+                    const int i = da + j;
+                    double anc[3], ax[3];
+                    for (int r = 0; r < 3; r++) {
+                        anc[r] = f.p[r] + f.R[3 * r] * c_m.dof_anchor[i][0] + f.R[3 * r + 1] * c_m.dof_anchor[i][1] +
+                                 f.R[3 * r + 2] * c_m.dof_anchor[i][2];
+                    }
+                    const int aid = c_m.dof_axis_id[i];
+                    if (aid >= 0) { ax[0] = f.R[aid]; ax[1] = f.R[3 + aid]; ax[2] = f.R[6 + aid]; }
+                    else for (int r = 0; r < 3; r++)
+                        ax[r] = f.R[3 * r] * c_m.dof_axis[i][0] + f.R[3 * r + 1] * c_m.dof_axis[i][1] + f.R[3 * r + 2] * c_m.dof_axis[i][2];
+                    double S[6];
+                    S[0] = ax[0]; S[1] = ax[1]; S[2] = ax[2];
+                    cross3(anc, ax, S + 3);
+                    for (int r = 0; r < 6; r++) e.S[i][r] = S[r];
+                    // cdof_dot = v x S ; a += cdof_dot qd ; v += S qd
+                    const double qd = e.v[i];
+                    double t0[3], t1[3], t2[3];
+                    cross3(f.v, S, t0);
+                    cross3(f.v, S + 3, t1);
+                    cross3(f.v + 3, S, t2);
+                    for (int r = 0; r < 3; r++) {
+                        f.a[r] += t0[r] * qd;
+                        f.a[3 + r] += (t1[r] + t2[r]) * qd;
+                    }
+                    for (int r = 0; r < 6; r++) f.v[r] += S[r] * qd;
+                    // rotate the frame about the joint axis through the anchor
+                    double sn, cs;
+                    sincos(e.q[qa + j], &sn, &cs);
+                    if (aid >= 0) {
+                        const int c1 = (aid + 1) % 3, c2 = (aid + 2) % 3;
+                        for (int r = 0; r < 3; r++) {
+                            double a1 = f.R[3 * r + c1], a2 = f.R[3 * r + c2];
+                            f.R[3 * r + c1] = cs * a1 + sn * a2;
+                            f.R[3 * r + c2] = -sn * a1 + cs * a2;
+                        }
+                    } else {
+                        const double *a = c_m.dof_axis[i];
+                        double K[9] = {0, -a[2], a[1], a[2], 0, -a[0], -a[1], a[0], 0}, Rot[9], Rn[9];
+                        for (int r = 0; r < 3; r++) for (int cidx = 0; cidx < 3; cidx++)
+                            Rot[3 * r + cidx] = (r == cidx ? cs : 0.0) + sn * K[3 * r + cidx] + (1.0 - cs) * a[r] * a[cidx];
+                        for (int r = 0; r < 3; r++) for (int cidx = 0; cidx < 3; cidx++)
+                            Rn[3 * r + cidx] = f.R[3 * r] * Rot[cidx] + f.R[3 * r + 1] * Rot[3 + cidx] + f.R[3 * r + 2] * Rot[6 + cidx];
+                        for (int r = 0; r < 9; r++) f.R[r] = Rn[r];
+                    }
+                    for (int r = 0; r < 3; r++)
+                        f.p[r] = anc[r] - (f.R[3 * r] * c_m.dof_anchor[i][0] + f.R[3 * r + 1] * c_m.dof_anchor[i][1] +
+                                           f.R[3 * r + 2] * c_m.dof_anchor[i][2]);
+                }
+            }
+            // body done: world position, spatial inertia about O in world axes, RNE body force
+            for (int r = 0; r < 3; r++) e.xp[b][r] = f.p[r] + e.q[r];
+            double cpos[3];
+            for (int r = 0; r < 3; r++)
+                cpos[r] = f.p[r] + f.R[3 * r] * c_m.body_ipos[b][0] + f.R[3 * r + 1] * c_m.body_ipos[b][1] + f.R[3 * r + 2] * c_m.body_ipos[b][2];
+            const double *in = c_m.body_inertia[b];
+            double Ib[9] = {in[0], in[3], in[4], in[3], in[1], in[5], in[4], in[5], in[2]}, Tm[9], Iw[6];
+            for (int r = 0; r < 3; r++) for (int cidx = 0; cidx < 3; cidx++)
+                Tm[3 * r + cidx] = f.R[3 * r] * Ib[cidx] + f.R[3 * r + 1] * Ib[3 + cidx] + f.R[3 * r + 2] * Ib[6 + cidx];
+            // Iw = Tm R^T, symmetric: xx yy zz xy xz yz
+            Iw[0] = Tm[0] * f.R[0] + Tm[1] * f.R[1] + Tm[2] * f.R[2];
+            Iw[1] = Tm[3] * f.R[3] + Tm[4] * f.R[4] + Tm[5] * f.R[5];
+            Iw[2] = Tm[6] * f.R[6] + Tm[7] * f.R[7] + Tm[8] * f.R[8];
+            Iw[3] = Tm[0] * f.R[3] + Tm[1] * f.R[4] + Tm[2] * f.R[5];
+            Iw[4] = Tm[0] * f.R[6] + Tm[1] * f.R[7] + Tm[2] * f.R[8];
+            Iw[5] = Tm[3] * f.R[6] + Tm[4] * f.R[7] + Tm[5] * f.R[8];
+            const double mass = c_m.body_mass[b], cc = dot3(cpos, cpos);
+            double *ci = e.cin[b];
+            ci[0] = mass;
+            ci[1] = mass * cpos[0]; ci[2] = mass * cpos[1]; ci[3] = mass * cpos[2];
+            ci[4] = Iw[0] + mass * (cc - cpos[0] * cpos[0]);
+            ci[5] = Iw[1] + mass * (cc - cpos[1] * cpos[1]);
+            ci[6] = Iw[2] + mass * (cc - cpos[2] * cpos[2]);
+            ci[7] = Iw[3] - mass * cpos[0] * cpos[1];
+            ci[8] = Iw[4] - mass * cpos[0] * cpos[2];
+            ci[9] = Iw[5] - mass * cpos[1] * cpos[2];
+            double Ia[6], Iv[6];
+            spi_mul(ci, f.a, Ia);
+            spi_mul(ci, f.v, Iv);
+            double c0[3], c1[3], c2[3];
+            cross3(f.v, Iv, c0);            // v x* f = [w x n + v x f ; w x f]
+            cross3(f.v + 3, Iv + 3, c1);
+            cross3(f.v, Iv + 3, c2);
+            for (int r = 0; r < 3; r++) {
+                e.fb[b][r] = Ia[r] + c0[r] + c1[r];
+                e.fb[b][3 + r] = Ia[3 + r] + c2[r];
+            }
+        }
+        e.jf[c] = f;
+    }
+}
+
+// Backward articulated-body sweep.  MODE 0: bias C_i = S_i . F and factor/solve with rhs = tau - C,
+// pivots S.U + armature (forward dynamics).  MODE 1: rhs = e.tau (pre-filled), pivots + kd h (stable PD).
+template <int MODE>
+__device__ void pass_backward(EnvData &e) {
+    const int nchain = c_m.nchain;
+    for (int c = 0; c < nchain; c++) {
+        for (int k = 0; k < 21; k++) e.jb[c].IA[k] = 0.0;
+        for (int k = 0; k < 6; k++) { e.jb[c].pA[k] = 0.0; e.jb[c].F[k] = 0.0; }
+    }
+    for (int c = nchain - 1; c >= 0; c--) {
+        Bwd w = e.jb[c];
+        for (int b = c_m.chain_hi[c]; b >= c_m.chain_lo[c]; b--) {
+            const double *ci = e.cin[b];
+            // add the body's spatial inertia: [[I_O, hx], [hx^T, m 1]]
+            w.IA[sx(0, 0)] += ci[4]; w.IA[sx(1, 1)] += ci[5]; w.IA[sx(2, 2)] += ci[6];
+            w.IA[sx(0, 1)] += ci[7]; w.IA[sx(0, 2)] += ci[8]; w.IA[sx(1, 2)] += ci[9];
+            w.IA[sx(0, 4)] += -ci[3]; w.IA[sx(0, 5)] += ci[2];
+            w.IA[sx(1, 3)] += ci[3];  w.IA[sx(1, 5)] += -ci[1];
+            w.IA[sx(2, 3)] += -ci[2]; w.IA[sx(2, 4)] += ci[1];
+            w.IA[sx(3, 3)] += ci[0]; w.IA[sx(4, 4)] += ci[0]; w.IA[sx(5, 5)] += ci[0];
+            if (MODE == 0) for (int k = 0; k < 6; k++) w.F[k] += e.fb[b][k];
+            const int da = c_m.body_dofadr[b], nd = c_m.body_dofnum[b];
+            for (int i = da + nd - 1; i >= da; i--) {
+                double S[6], U[6];
+#pragma unroll
+                for (int r = 0; r < 6; r++) S[r] = e.S[i][r];
+                double rhs;
+                if (MODE == 0) {
+                    double Ci = dot6(S, w.F);
+                    e.C[i] = Ci;
+                    rhs = e.tau[i] - Ci;
+                } else rhs = e.tau[i];
+#pragma unroll
+                for (int r = 0; r < 6; r++) {
+                    double t = 0.0;
+#pragma unroll
+                    for (int cc = 0; cc < 6; cc++) t += w.IA[sx(r, cc)] * S[cc];
+                    U[r] = t;
+                }
+                double D = dot6(S, U) + c_m.dof_arm[i];
+                if (MODE == 1) D += c_m.kd[i] * c_m.h;
+                const double Dinv = 1.0 / D;
+                const double ui = rhs - dot6(S, w.pA);
+                e.Dinv[i] = Dinv;
+                e.u[i] = ui;
+#pragma unroll
+                for (int r = 0; r < 6; r++) e.U[i][r] = U[r];
+#pragma unroll
+                for (int r = 0; r < 6; r++) {
+                    const double ur = U[r] * Dinv;
+#pragma unroll
+                    for (int cc = r; cc < 6; cc++) w.IA[sx(r, cc)] -= ur * U[cc];
+                    w.pA[r] += ur * ui;
+                }
+            }
+        }
+        const int pc = c_m.chain_parent[c];
+        if (pc >= 0) {
+            for (int k = 0; k < 21; k++) e.jb[pc].IA[k] += w.IA[k];
+            for (int k = 0; k < 6; k++) { e.jb[pc].pA[k] += w.pA[k]; e.jb[pc].F[k] += w.F[k]; }
+        }
+    }
+}
+
+// Forward acceleration sweep of the pure solve: out[i] = x_i where (M + diag) x = rhs.
+__device__ void pass_accel(EnvData &e, double *out) {
+    const int nchain = c_m.nchain;
+    for (int c = 0; c < nchain; c++) {
+        double a[6];
+        const int pc = c_m.chain_parent[c];
+        for (int k = 0; k < 6; k++) a[k] = pc >= 0 ? e.ja[pc][k] : 0.0;
+        const int lo = c_m.body_dofadr[c_m.chain_lo[c]];
+        const int hi = c_m.body_dofadr[c_m.chain_hi[c]] + c_m.body_dofnum[c_m.chain_hi[c]];
+        for (int i = lo; i < hi; i++) {
+            double x = e.Dinv[i] * (e.u[i] - dot6(e.U[i], a));
+            out[i] = x;
+#pragma unroll
+            for (int r = 0; r < 6; r++) a[r] += e.S[i][r] * x;
+        }
+        for (int k = 0; k < 6; k++) e.ja[c][k] = a[k];
+    }
+}
+
+// sim.forward() at the current state (envs/common/mujoco_env.py:100-101): refresh tree data + bias
+__device__ void env_forward(EnvData &e) {
+    pass_kinematics(e);
+    for (int i = 0; i < c_m.nv; i++) e.tau[i] = 0.0;
+    pass_backward<0>(e);
+}
+
+// One iteration of do_simulation (humanoid_v1.py:166-174): compute_torque on the stale tree data, then mj_step.
+__device__ void env_substep(EnvData &e, const double *ctrl /* per dof, [nv] */, double *torque_out) {
+    const int nv = c_m.nv;
+    const double h = c_m.h;
+    // stable PD (humanoid_v1.py:130-156): (M + Kd h) x = -C - Kp e_q - Kd v ; torque = -kp e_q - kd (v + x h)
+    for (int i = 0; i < nv; i++) {
+        double eq = i >= 6 ? e.q[i + 1] - ctrl[i] : 0.0;
+        e.tau[i] = -e.C[i] - c_m.kp[i] * eq - c_m.kd[i] * e.v[i];
+    }
+    pass_backward<1>(e);
+    pass_accel(e, e.qacc);
+    for (int i = 0; i < nv; i++) {
+        double t = 0.0;
+        if (i >= 6) {
+            double eq = e.q[i + 1] - ctrl[i];
+            t = -c_m.kp[i] * eq - c_m.kd[i] * (e.v[i] + e.qacc[i] * h);
+            double lim = c_m.tlim[i];
+            t = t < -lim ? -lim : (t > lim ? lim : t);     // np.clip (humanoid_v1.py:172)
+        }
+        e.tau[i] = t;
+        if (torque_out && i >= 6) torque_out[i - 6] = t;
+    }
+    // mj_step: forward at (q, v) then semi-implicit Euler
+    pass_kinematics(e);
+    pass_backward<0>(e);
+    pass_accel(e, e.qacc);
+    for (int i = 0; i < nv; i++) e.v[i] += h * e.qacc[i];
+    for (int k = 0; k < 3; k++) e.q[k] += h * e.v[k];
+    {
+        double w[3] = {e.v[3], e.v[4], e.v[5]};
+        double n = sqrt(dot3(w, w)), ax[3] = {1.0, 0.0, 0.0};
+        if (n > 1e-15) { ax[0] = w[0] / n; ax[1] = w[1] / n; ax[2] = w[2] / n; }
+        double sn, cs;
+        sincos(0.5 * h * n, &sn, &cs);
+        double qr[4] = {cs, ax[0] * sn, ax[1] * sn, ax[2] * sn};
+        double qn = sqrt(e.q[3] * e.q[3] + e.q[4] * e.q[4] + e.q[5] * e.q[5] + e.q[6] * e.q[6]);
+        double qq[4] = {e.q[3] / qn, e.q[4] / qn, e.q[5] / qn, e.q[6] / qn}, o[4];
+        quat_mul(qq, qr, o);
+        e.q[3] = o[0]; e.q[4] = o[1]; e.q[5] = o[2]; e.q[6] = o[3];
+    }
+    for (int i = 6; i < nv; i++) e.q[i + 1] += h * e.v[i];
+}
+
+// humanoid_v1.py:73-96 get_full_obs (obs_coord 'heading', root_deheading, obs_vel 'full')
+__device__ void env_obs(const EnvData &e, double *obs) {
+    double dq[4], vl[3];
+    de_heading(e.q + 3, dq);
+    obs[0] = e.q[2];
+    obs[1] = dq[0]; obs[2] = dq[1]; obs[3] = dq[2]; obs[4] = dq[3];
+    const int nq = c_m.nq, nv = c_m.nv;
+    for (int k = 7; k < nq; k++) obs[k - 2] = e.q[k];
+    to_heading(e.v, e.q + 3, vl);
+    double *ov = obs + (nq - 2);
+    ov[0] = vl[0]; ov[1] = vl[1]; ov[2] = vl[2];
+    for (int k = 3; k < nv; k++) ov[k] = e.v[k];
+}
+
+// humanoid_v1.py:113-125 get_body_quat
+__device__ void env_body_quat(const double *q, double *bq) {
+    bq[0] = q[3]; bq[1] = q[4]; bq[2] = q[5]; bq[3] = q[6];
+    for (int b = 1; b < c_m.nbody; b++) {
+        const int qa = c_m.body_qposadr[b], nd = c_m.body_dofnum[b];
+        double e0 = q[qa], e1 = nd > 1 ? q[qa + 1] : 0.0, e2 = nd > 2 ? q[qa + 2] : 0.0;
+        quat_from_euler(e0, e1, e2, bq + 4 * b);
+    }
+}
+
+// humanoid_v1.py:98-111 get_ee_pos('heading') from the (stale) body positions
+__device__ void env_ee_pos(const EnvData &e, double *ee) {
+    for (int k = 0; k < EGP_NEE; k++) {
+        const double *x = e.xp[c_m.ee_body[k]];
+        double v[3] = {x[0] - e.q[0], x[1] - e.q[1], x[2] - e.q[2]};
+        to_heading(v, e.q + 3, ee + 3 * k);
+    }
+}
+
+// reward_function.py:4-60 quat_space_reward_v3
+__device__ double env_reward(const EnvData &e, const double *prev_root /*7*/, const double *prev_bq, const double *cur_bq,
+                             const double *row, double dt, int t, int episode_len, int end, double end_reward,
+                             double *info5) {
+    const int nb = c_m.nbody;
+    // get_qvel_fd(prev_qpos, cur_qpos, dt, 'heading')[:6]  (utils/math.py:20-35)
+    double lin[3], qi[4], qrel[4], axis[3], ang, rv[3], fdl[3], fda[3];
+    for (int k = 0; k < 3; k++) lin[k] = (e.q[k] - prev_root[k]) / dt;
+    quat_inv(prev_root + 3, qi);
+    quat_mul(e.q + 3, qi, qrel);
+    rot_from_quat(qrel, axis, &ang);
+    if (1.0 - qrel[0] < 1e-8) { axis[0] = 1.0; }
+    if (ang > M_PI) ang -= 2 * M_PI; else if (ang < -M_PI) ang += 2 * M_PI;
+    for (int k = 0; k < 3; k++) rv[k] = (axis[k] * ang) / dt;
+    to_root(rv, prev_root + 3, fda);
+    to_heading(lin, prev_root + 3, fdl);
+    double rq[4], ee[3 * EGP_NEE];
+    de_heading(e.q + 3, rq);
+    env_ee_pos(e, ee);
+    const double *e_bquat = row + EGP_X_BQUAT, *e_bangvel = row + EGP_X_BANGVEL;
+    double pose2 = 0.0, vd = 0.0;
+    for (int b = 1; b < nb; b++) {
+        double q1[4], qd[4];
+        quat_inv(e_bquat + 4 * b, q1);
+        quat_mul(cur_bq + 4 * b, q1, qd);
+        double w = fmin(fmax(qd[0], -1.0), 1.0);
+        double a = acos(w) * c_m.b_diffw[b - 1];
+        pose2 += a * a;
+        // get_angvel_fd (utils/math.py:38-44) for this body
+        double p1[4], pd[4], av[3], aang;
+        quat_inv(prev_bq + 4 * b, p1);
+        quat_mul(cur_bq + 4 * b, p1, pd);
+        rot_from_quat(pd, av, &aang);
+        if (1.0 - pd[0] < 1e-8) av[0] = 1.0;
+        for (int k = 0; k < 3; k++) {
+            double df = fabs(av[k] * aang / dt - e_bangvel[3 * b + k]);
+            vd += c_m.v_ord == 1 ? df : df * df;
+        }
+    }
+    double pose_dist = sqrt(pose2);
+    double pose_reward = exp(-c_m.k_p * (pose_dist * pose_dist));
+    double vel_dist = c_m.v_ord == 1 ? vd : sqrt(vd);
+    double vel_reward = exp(-c_m.k_v * (vel_dist * vel_dist));
+    double e2 = 0.0;
+    for (int k = 0; k < 3 * EGP_NEE; k++) { double df = ee[k] - row[EGP_X_EE_POS + k]; e2 += df * df; }
+    double ee_dist = sqrt(e2);
+    double ee_reward = exp(-c_m.k_e * (ee_dist * ee_dist));
+    double hd = e.q[2] - row[EGP_X_QPOS + 2], q1[4], qd[4];
+    quat_inv(row + EGP_X_RQ_RMH, q1);
+    quat_mul(rq, q1, qd);
+    double rqd = acos(fmin(fmax(qd[0], -1.0), 1.0));
+    double root_pose_reward = exp(-c_m.k_rh * (hd * hd) - c_m.k_rq * (rqd * rqd));
+    double l2 = 0.0, a2 = 0.0;
+    for (int k = 0; k < 3; k++) {
+        double dl = fdl[k] - row[EGP_X_RLINV_LOCAL + k], da = fda[k] - row[EGP_X_RANGV + k];
+        l2 += dl * dl; a2 += da * da;
+    }
+    double ld = sqrt(l2), ad = sqrt(a2);
+    double root_vel_reward = exp(-c_m.k_rl * (ld * ld) - c_m.k_ra * (ad * ad));
+    double reward = c_m.w_p * pose_reward + c_m.w_v * vel_reward + c_m.w_e * ee_reward + c_m.w_rp * root_pose_reward +
+                    c_m.w_rv * root_vel_reward;
+    reward /= c_m.w_p + c_m.w_v + c_m.w_e + c_m.w_rp + c_m.w_rv;
+    if (c_m.decay) reward *= 1.0 - (double)t / episode_len;
+    if (end) reward += end_reward;
+    info5[0] = pose_reward; info5[1] = vel_reward; info5[2] = ee_reward; info5[3] = root_pose_reward; info5[4] = root_vel_reward;
+    return reward;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 counter-based generator (Salmon et al. 2011), used for perf-mode noise and reset draws
+__device__ __forceinline__ void philox4x32(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+__device__ __forceinline__ double u01(uint32_t a, uint32_t b) {     // (0, 1]
+    unsigned long long x = ((unsigned long long)a << 21) ^ (unsigned long long)(b >> 11);   // 53 bits
+    return ((double)(x & ((1ULL << 53) - 1)) + 1.0) * (1.0 / 9007199254740992.0);
+}
+__device__ __forceinline__ void normal2(uint64_t seed, uint64_t stream, uint32_t a, uint32_t b, double *z0, double *z1) {
+    uint32_t c[4] = {a, b, (uint32_t)stream, (uint32_t)(stream >> 32)};
+    philox4x32(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    double u1 = u01(c[0], c[1]), u2 = u01(c[2], c[3]);
+    double r = sqrt(-2.0 * log(u1)), sn, cs;
+    sincospi(2.0 * u2, &sn, &cs);
+    *z0 = r * cs; *z1 = r * sn;
+}
+
+// ------------------------------------------------------------------------------------------------
+struct RolloutArgs {
+    EgpRolloutCfg cfg;
+    EgpRolloutIn in;
+    EgpTrajOut out;
+    // expert tables
+    const int32_t *take_off;
+    const double *rows, *head_lb, *ctx;
+    int n_takes, ctx_dim;
+    // policy (transposed + padded): W1t [D][H1p], W2t [H1][H2p], W3t [H2][Ap]
+    const double *W1t, *b1, *W2t, *b2, *W3t, *b3, *log_std;
+    int D, H1, H2, A, H1p, H2p, Ap;
+};
+
+// one dense layer for the 32 environments of the CTA: ys[j][lane] = act(b[j] + sum_k Wt[k][j] xs[k][lane])
+template <bool RELU>
+__device__ __forceinline__ void mlp_layer(const double *__restrict__ Wt, const double *__restrict__ bias, int K, int Np,
+                                          const double *xs, double *ys, int lane) {
+    for (int j0 = 0; j0 < Np; j0 += JB) {
+        double acc[JB];
+#pragma unroll
+        for (int jj = 0; jj < JB; jj++) acc[jj] = bias[j0 + jj];
+        for (int k = 0; k < K; k++) {
+            const double xv = xs[k * ENVS_PER_CTA + lane];
+            const double2 *w = reinterpret_cast<const double2 *>(Wt + (size_t)k * Np + j0);
+#pragma unroll
+            for (int jj = 0; jj < JB / 2; jj++) {
+                double2 ww = __ldg(w + jj);
+                acc[2 * jj] += ww.x * xv;
+                acc[2 * jj + 1] += ww.y * xv;
+            }
+        }
+#pragma unroll
+        for (int jj = 0; jj < JB; jj++) ys[(j0 + jj) * ENVS_PER_CTA + lane] = RELU ? fmax(acc[jj], 0.0) : acc[jj];
+    }
+}
+
+__device__ void zfilter(const double *x, double *y, int n, const double *mean, const double *sd, double clip) {
+    for (int k = 0; k < n; k++) {
+        double v = x[k];
+        if (mean) {
+            v = (v - mean[k]) / (sd[k] + 1e-8);
+            if (clip > 0.0) v = fmin(fmax(v, -clip), clip);
+        }
+        y[k] = v;
+    }
+}
+
+__device__ void load_reset(EnvData &e, const RolloutArgs &A, int take, int start) {
+    const double *row = A.rows + (size_t)(A.take_off[take] + start) * EGP_X_STRIDE;
+    for (int k = 0; k < c_m.nq; k++) e.q[k] = row[EGP_X_QPOS + k];
+    for (int k = 0; k < c_m.nv; k++) e.v[k] = row[EGP_X_QVEL + k];
+    env_forward(e);
+}
+
+__global__ void __launch_bounds__(ENVS_PER_CTA)
+rollout_kernel(const RolloutArgs A) {
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x;
+    const int S = c_m.nq - 2 + c_m.nv, nu = c_m.nu, nv = c_m.nv, nb = c_m.nbody;
+    double *xs = smem;                                  // [max(D, H2p)][32]
+    const int xrows = A.D > A.H2p ? A.D : A.H2p;
+    double *h1s = smem + (size_t)xrows * ENVS_PER_CTA;  // [H1p][32] (also receives the action means, rows 0..Ap)
+    const int T = A.cfg.horizon, E = A.cfg.n_env;
+    const double dt = c_m.h * c_m.frame_skip;
+    const int env = blockIdx.x * ENVS_PER_CTA + lane;
+    const bool live = env < E;
+    const int eid = live ? env : E - 1;                 // idle lanes shadow the last env and write nothing
+
+    EnvData e;
+    double obs[MAXV * 2], state[MAXV * 2], nstate[MAXV * 2], ctrl[MAXV], act[MAXV];
+    double bq_a[4 * MAXB], bq_b[4 * MAXB];
+    double *cur_bq = bq_a, *prev_bq = bq_b;
+    double log_acc[EGP_LOG_SIZE];
+    for (int k = 0; k < EGP_LOG_SIZE; k++) log_acc[k] = 0.0;
+    log_acc[EGP_LOG_MIN_C_REWARD] = INFINITY; log_acc[EGP_LOG_MAX_C_REWARD] = -INFINITY;
+    log_acc[EGP_LOG_MIN_EPISODE_REWARD] = INFINITY; log_acc[EGP_LOG_MAX_EPISODE_REWARD] = -INFINITY;
+    double ep_reward = 0.0;
+
+    int n_reset = 0, take, start, cur_t = 0;
+    auto draw_reset = [&](int r) {
+        if (A.in.d_reset_take) {
+            int rr = r < A.cfg.max_resets ? r : A.cfg.max_resets - 1;
+            take = A.in.d_reset_take[(size_t)eid * A.cfg.max_resets + rr];
+            start = A.in.d_reset_start[(size_t)eid * A.cfg.max_resets + rr];
+        } else {
+            uint32_t c[4] = {(uint32_t)eid, (uint32_t)r, (uint32_t)A.cfg.iteration, 0x52535421u};
+            philox4x32(c, (uint32_t)A.cfg.seed, (uint32_t)(A.cfg.seed >> 32));
+            take = (int)(c[0] % (uint32_t)A.n_takes);                              // humanoid_v1.py:210
+            int len = A.take_off[take + 1] - A.take_off[take];
+            int span = len - A.cfg.episode_len - 2 * A.cfg.fr_margin;              // humanoid_v1.py:214
+            start = A.cfg.fr_margin + (span > 0 ? (int)(c[1] % (uint32_t)span) : 0);
+        }
+    };
+    draw_reset(0);
+    load_reset(e, A, take, start);
+    env_body_quat(e.q, cur_bq);
+    env_obs(e, obs);
+    zfilter(obs, state, S, A.in.d_zf_mean, A.in.d_zf_std, A.cfg.zf_clip);
+    for (int i = 0; i < 6; i++) ctrl[i] = 0.0;
+
+    for (int t = 0; t < T; t++) {
+        const size_t n = (size_t)eid * T + t;
+        // ---- policy input cat(ctx[frame], state) -> shared, feature-major (video_state_net.py:62-64)
+        int off = 0;
+        if (A.ctx) {
+            const double *cx = A.ctx + (size_t)(A.take_off[take] + start + cur_t) * A.ctx_dim;
+            for (int k = 0; k < A.ctx_dim; k++) xs[k * ENVS_PER_CTA + lane] = cx[k];
+            off = A.ctx_dim;
+        }
+        for (int k = 0; k < S; k++) xs[(off + k) * ENVS_PER_CTA + lane] = state[k];
+        __syncwarp();
+        // ---- PolicyGaussian forward (policy_gaussian.py:19-24, mlp.py:22-25)
+        mlp_layer<true>(A.W1t, A.b1, A.D, A.H1p, xs, h1s, lane);
+        mlp_layer<true>(A.W2t, A.b2, A.H1, A.H2p, h1s, xs, lane);
+        mlp_layer<false>(A.W3t, A.b3, A.H2, A.Ap, xs, h1s, lane);
+        // ---- sample (distributions.py / policy.py:12-15): a = mu + exp(log_std) eps, or the mean
+        bool mean_flag = A.cfg.mean_action != 0;
+        if (A.in.d_mean_flag) mean_flag = mean_flag || A.in.d_mean_flag[n] != 0;
+        else if (A.cfg.noise_rate < 1.0) {
+            uint32_t c[4] = {(uint32_t)eid, (uint32_t)t, (uint32_t)A.cfg.iteration, 0x4d45414eu};
+            philox4x32(c, (uint32_t)A.cfg.seed, (uint32_t)(A.cfg.seed >> 32));
+            mean_flag = mean_flag || (u01(c[0], c[1]) <= 1.0 - A.cfg.noise_rate);   // binomial(1, 1 - noise_rate)
+        }
+        for (int a = 0; a < nu; a += 2) {
+            double z0 = 0.0, z1 = 0.0;
+            if (!mean_flag) {
+                if (A.in.d_eps) { z0 = A.in.d_eps[n * nu + a]; z1 = a + 1 < nu ? A.in.d_eps[n * nu + a + 1] : 0.0; }
+                else normal2(A.cfg.seed, A.cfg.iteration, (uint32_t)eid, (uint32_t)(t * 64 + a), &z0, &z1);
+            }
+            act[a] = h1s[a * ENVS_PER_CTA + lane] + exp(A.log_std[a]) * z0;
+            if (a + 1 < nu) act[a + 1] = h1s[(a + 1) * ENVS_PER_CTA + lane] + exp(A.log_std[a + 1]) * z1;
+        }
+        if (live) {
+            for (int k = 0; k < S; k++) A.out.d_states[n * S + k] = state[k];
+            for (int a = 0; a < nu; a++) A.out.d_actions[n * nu + a] = act[a];
+            if (A.out.d_raw_obs) for (int k = 0; k < S; k++) A.out.d_raw_obs[n * S + k] = obs[k];
+        }
+        // ---- env.step (humanoid_v1.py:179-199)
+        double prev_root[7];
+        for (int k = 0; k < 7; k++) prev_root[k] = e.q[k];
+        { double *tmp = prev_bq; prev_bq = cur_bq; cur_bq = tmp; }
+        for (int a = 0; a < nu; a++) ctrl[6 + a] = c_m.a_ref[6 + a] + act[a] * c_m.a_scale[6 + a];
+        for (int s = 0; s < c_m.frame_skip; s++) env_substep(e, ctrl, nullptr);
+        cur_t += 1;
+        env_body_quat(e.q, cur_bq);
+        const double head_z = e.xp[c_m.head_body][2];
+        const double lb = isnan(A.cfg.fix_head_lb) ? A.head_lb[take] - 0.1 : A.cfg.fix_head_lb;
+        bool fail = head_z < lb;
+        const bool end = cur_t >= A.cfg.episode_len;
+        env_obs(e, obs);
+        zfilter(obs, nstate, S, A.in.d_zf_mean, A.in.d_zf_std, A.cfg.zf_clip);
+        double info5[5];
+        const double *row = A.rows + (size_t)(A.take_off[take] + start + cur_t) * EGP_X_STRIDE;
+        double rew = env_reward(e, prev_root, prev_bq, cur_bq, row, dt, cur_t, A.cfg.episode_len, end, A.cfg.end_reward, info5);
+        bool bad = !(isfinite(rew) && isfinite(head_z));
+        for (int k = 0; k < S && !bad; k++) bad = !(fabs(obs[k]) < 1e10);
+        if (bad) {      // mj_checkPos/Vel analogue: terminate, reset, count
+            rew = 0.0; fail = true;
+            for (int k = 0; k < 5; k++) info5[k] = 0.0;
+            for (int k = 0; k < S; k++) nstate[k] = 0.0;
+            log_acc[EGP_LOG_NUM_NAN_RESETS] += 1.0;
+        }
+        const bool done = fail || end;
+        if (live) {
+            A.out.d_rewards[n] = rew;
+            A.out.d_masks[n] = (done || t == T - 1) ? 0.0 : 1.0;
+            A.out.d_exps[n] = mean_flag ? 0.0 : 1.0;
+            A.out.d_v_metas[2 * n] = take;
+            A.out.d_v_metas[2 * n + 1] = start;
+            if (A.out.d_next_states) for (int k = 0; k < S; k++) A.out.d_next_states[n * S + k] = nstate[k];
+            if (A.out.d_c_info) for (int k = 0; k < 5; k++) A.out.d_c_info[n * 5 + k] = info5[k];
+        }
+        // LoggerRL.step / end_episode (core/logger_rl.py:24-36)
+        ep_reward += 1.0;
+        log_acc[EGP_LOG_NUM_STEPS] += 1.0;
+        log_acc[EGP_LOG_TOTAL_C_REWARD] += rew;
+        log_acc[EGP_LOG_MIN_C_REWARD] = fmin(log_acc[EGP_LOG_MIN_C_REWARD], rew);
+        log_acc[EGP_LOG_MAX_C_REWARD] = fmax(log_acc[EGP_LOG_MAX_C_REWARD], rew);
+        for (int k = 0; k < 5; k++) log_acc[EGP_LOG_C_INFO + k] += info5[k];
+        if (done || t == T - 1) {
+            log_acc[EGP_LOG_NUM_EPISODES] += 1.0;
+            log_acc[EGP_LOG_TOTAL_REWARD] += ep_reward;
+            log_acc[EGP_LOG_MIN_EPISODE_REWARD] = fmin(log_acc[EGP_LOG_MIN_EPISODE_REWARD], ep_reward);
+            log_acc[EGP_LOG_MAX_EPISODE_REWARD] = fmax(log_acc[EGP_LOG_MAX_EPISODE_REWARD], ep_reward);
+            ep_reward = 0.0;
+        }
+        if (done && t < T - 1) {
+            n_reset++;
+            draw_reset(n_reset);
+            cur_t = 0;
+            load_reset(e, A, take, start);
+            env_body_quat(e.q, cur_bq);
+            env_obs(e, obs);
+            zfilter(obs, state, S, A.in.d_zf_mean, A.in.d_zf_std, A.cfg.zf_clip);
+        } else {
+            for (int k = 0; k < S; k++) state[k] = nstate[k];
+        }
+        __syncwarp();
+    }
+    if (live) {
+        if (A.out.d_final_qpos) for (int k = 0; k < c_m.nq; k++) A.out.d_final_qpos[(size_t)env * c_m.nq + k] = e.q[k];
+        if (A.out.d_final_qvel) for (int k = 0; k < nv; k++) A.out.d_final_qvel[(size_t)env * nv + k] = e.v[k];
+        if (A.out.d_logger) {
+            double *L = A.out.d_logger;
+            atomicAdd(L + EGP_LOG_NUM_STEPS, log_acc[EGP_LOG_NUM_STEPS]);
+            atomicAdd(L + EGP_LOG_NUM_EPISODES, log_acc[EGP_LOG_NUM_EPISODES]);
+            atomicAdd(L + EGP_LOG_TOTAL_REWARD, log_acc[EGP_LOG_TOTAL_REWARD]);
+            atomicAdd(L + EGP_LOG_TOTAL_C_REWARD, log_acc[EGP_LOG_TOTAL_C_REWARD]);
+            atomicAdd(L + EGP_LOG_NUM_NAN_RESETS, log_acc[EGP_LOG_NUM_NAN_RESETS]);
+            for (int k = 0; k < 5; k++) atomicAdd(L + EGP_LOG_C_INFO + k, log_acc[EGP_LOG_C_INFO + k]);
+            // min / max through ordered-int tricks are avoided: rewards are >= 0 except NaN resets; use CAS loops
+            auto amin = [](double *addr, double v) {
+                unsigned long long *a = (unsigned long long *)addr, old = *a, assumed;
+                do { assumed = old; if (__longlong_as_double(assumed) <= v) break;
+                     old = atomicCAS(a, assumed, __double_as_longlong(v)); } while (assumed != old);
+            };
+            auto amax = [](double *addr, double v) {
+                unsigned long long *a = (unsigned long long *)addr, old = *a, assumed;
+                do { assumed = old; if (__longlong_as_double(assumed) >= v) break;
+                     old = atomicCAS(a, assumed, __double_as_longlong(v)); } while (assumed != old);
+            };
+            amin(L + EGP_LOG_MIN_C_REWARD, log_acc[EGP_LOG_MIN_C_REWARD]);
+            amax(L + EGP_LOG_MAX_C_REWARD, log_acc[EGP_LOG_MAX_C_REWARD]);
+            amin(L + EGP_LOG_MIN_EPISODE_REWARD, log_acc[EGP_LOG_MIN_EPISODE_REWARD]);
+            amax(L + EGP_LOG_MAX_EPISODE_REWARD, log_acc[EGP_LOG_MAX_EPISODE_REWARD]);
+        }
+    }
+    (void)nb;
+}
+
+// transposes W [out][in] -> Wt [in][outp] (zero padded), biases padded
+__global__ void transpose_pad_kernel(const double *__restrict__ W, const double *__restrict__ b, int out, int in, int outp,
+                                     double *__restrict__ Wt, double *__restrict__ bp) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < in * outp) {
+        int k = idx / outp, j = idx % outp;
+        Wt[idx] = j < out ? W[(size_t)j * in + k] : 0.0;
+    }
+    if (idx < outp) bp[idx] = idx < out ? b[idx] : 0.0;
+}
+
+// ---- debug / parity kernels ---------------------------------------------------------------------
+__global__ void forward_debug_kernel(int n, const double *qpos, const double *qvel, const double *ctrl, double *bias,
+                                     double *xpos, double *qacc) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    EnvData e;
+    const int nq = c_m.nq, nv = c_m.nv, nb = c_m.nbody;
+    for (int k = 0; k < nq; k++) e.q[k] = qpos[(size_t)i * nq + k];
+    for (int k = 0; k < nv; k++) e.v[k] = qvel[(size_t)i * nv + k];
+    pass_kinematics(e);
+    for (int k = 0; k < nv; k++) e.tau[k] = (k >= 6 && ctrl) ? ctrl[(size_t)i * c_m.nu + k - 6] : 0.0;
+    pass_backward<0>(e);
+    pass_accel(e, e.qacc);
+    for (int k = 0; k < nv; k++) { bias[(size_t)i * nv + k] = e.C[k]; qacc[(size_t)i * nv + k] = e.qacc[k]; }
+    for (int b = 0; b < nb; b++) for (int r = 0; r < 3; r++) xpos[((size_t)i * nb + b) * 3 + r] = e.xp[b][r];
+}
+
+__global__ void env_step_debug_kernel(int n, double *qpos, double *qvel, const double *action, double *obs_out,
+                                      double *head_z, double *torque0) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    EnvData e;
+    const int nq = c_m.nq, nv = c_m.nv, nu = c_m.nu, S = nq - 2 + nv;
+    for (int k = 0; k < nq; k++) e.q[k] = qpos[(size_t)i * nq + k];
+    for (int k = 0; k < nv; k++) e.v[k] = qvel[(size_t)i * nv + k];
+    env_forward(e);
+    double ctrl[MAXV], obs[2 * MAXV];
+    for (int k = 0; k < 6; k++) ctrl[k] = 0.0;
+    for (int a = 0; a < nu; a++) ctrl[6 + a] = c_m.a_ref[6 + a] + action[(size_t)i * nu + a] * c_m.a_scale[6 + a];
+    for (int s = 0; s < c_m.frame_skip; s++) env_substep(e, ctrl, s == 0 ? torque0 + (size_t)i * nu : nullptr);
+    for (int k = 0; k < nq; k++) qpos[(size_t)i * nq + k] = e.q[k];
+    for (int k = 0; k < nv; k++) qvel[(size_t)i * nv + k] = e.v[k];
+    env_obs(e, obs);
+    for (int k = 0; k < S; k++) obs_out[(size_t)i * S + k] = obs[k];
+    head_z[i] = e.xp[c_m.head_body][2];
+}
+
+// gen_expert.py:28-83: one thread per frame; velocities by finite differences against the previous frame
+__global__ void expert_features_kernel(int L, const double *qpos, double *rows, double *head_z) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= L) return;
+    const int nq = c_m.nq, nb = c_m.nbody;
+    const double dt = c_m.h * c_m.frame_skip;
+    EnvData e;
+    double *row = rows + (size_t)i * EGP_X_STRIDE;
+    for (int k = 0; k < EGP_X_STRIDE; k++) row[k] = 0.0;
+    for (int k = 0; k < nq; k++) { e.q[k] = qpos[(size_t)i * nq + k]; row[EGP_X_QPOS + k] = e.q[k]; }
+    for (int k = 0; k < c_m.nv; k++) e.v[k] = 0.0;
+    pass_kinematics(e);
+    de_heading(e.q + 3, row + EGP_X_RQ_RMH);
+    env_ee_pos(e, row + EGP_X_EE_POS);
+    double bq[4 * MAXB];
+    env_body_quat(e.q, bq);
+    for (int k = 0; k < 4 * nb; k++) row[EGP_X_BQUAT + k] = bq[k];
+    head_z[i] = e.xp[c_m.head_body][2];
+    // frame 0 copies the finite differences of frame 1 (gen_expert.py:67-70,76)
+    const int ic = i > 0 ? i : (L > 1 ? 1 : 0);
+    if (L > 1) {
+        const double *cur = qpos + (size_t)ic * nq, *prev = qpos + (size_t)(ic - 1) * nq;
+        double lin[3], qi[4], qrel[4], axis[3], ang, rv[3];
+        for (int k = 0; k < 3; k++) lin[k] = (cur[k] - prev[k]) / dt;
+        quat_inv(prev + 3, qi);
+        quat_mul(cur + 3, qi, qrel);
+        rot_from_quat(qrel, axis, &ang);
+        if (1.0 - qrel[0] < 1e-8) axis[0] = 1.0;
+        if (ang > M_PI) ang -= 2 * M_PI; else if (ang < -M_PI) ang += 2 * M_PI;
+        for (int k = 0; k < 3; k++) rv[k] = axis[k] * ang / dt;
+        double *qv = row + EGP_X_QVEL;
+        qv[0] = lin[0]; qv[1] = lin[1]; qv[2] = lin[2];
+        to_root(rv, prev + 3, qv + 3);
+        for (int k = 7; k < nq; k++) qv[k - 1] = (cur[k] - prev[k]) / dt;
+        to_heading(lin, cur + 3, row + EGP_X_RLINV_LOCAL);
+        for (int k = 0; k < 3; k++) row[EGP_X_RANGV + k] = qv[3 + k];
+        double bqp[4 * MAXB], bqc[4 * MAXB];
+        env_body_quat(prev, bqp);
+        env_body_quat(cur, bqc);
+        for (int b = 0; b < nb; b++) {
+            double p1[4], pd[4], av[3], aang;
+            quat_inv(bqp + 4 * b, p1);
+            quat_mul(bqc + 4 * b, p1, pd);
+            rot_from_quat(pd, av, &aang);
+            if (1.0 - pd[0] < 1e-8) av[0] = 1.0;
+            for (int k = 0; k < 3; k++) row[EGP_X_BANGVEL + 3 * b + k] = av[k] * aang / dt;
+        }
+    }
+}
+
+// out[n][ctx_dim + S] = cat(ctx[frame(n)], states[n]); t within the episode is recovered from the masks:
+// rows are env-major with `horizon` rows per env, an episode starts at t = 0 or after a mask == 0 row.
+__global__ void build_input_kernel(const double *__restrict__ states, const int32_t *__restrict__ v_metas,
+                                   const double *__restrict__ masks, long long n_env, int horizon, int S,
+                                   const int32_t *__restrict__ take_off, const double *__restrict__ ctx, int ctx_dim,
+                                   double *__restrict__ x) {
+    // one warp per env row-block: lane-parallel copy, serial walk over t for the episode-relative index
+    const int lane = threadIdx.x & 31;
+    const long long env = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    if (env >= n_env) return;
+    const int D = ctx_dim + S;
+    int cur_t = 0;
+    for (int t = 0; t < horizon; t++) {
+        const long long n = env * horizon + t;
+        const long long frame = (long long)take_off[v_metas[2 * n]] + v_metas[2 * n + 1] + cur_t;
+        const double *cx = ctx + frame * ctx_dim;
+        double *xr = x + n * D;
+        for (int k = lane; k < ctx_dim; k += 32) xr[k] = cx[k];
+        for (int k = lane; k < S; k += 32) xr[ctx_dim + k] = states[n * S + k];
+        cur_t = masks[n] == 0.0 ? 0 : cur_t + 1;
+    }
+}
+
+static void build_chains(DevModel &d) {
+    // a chain is a maximal run of consecutive bodies b, b+1, ... with parent(b+1) == b where b has one child
+    int nb = d.nbody, nchild[MAXB] = {0};
+    for (int b = 0; b < nb; b++) if (d.body_parent[b] >= 0) nchild[d.body_parent[b]]++;
+    int nc = 0;
+    for (int b = 0; b < nb; b++) {
+        bool cont = b > 0 && d.body_parent[b] == b - 1 && nchild[b - 1] == 1;
+        if (!cont) {
+            d.chain_lo[nc] = b;
+            d.chain_parent[nc] = d.body_parent[b] >= 0 ? d.body_chain[d.body_parent[b]] : -1;
+            nc++;
+        }
+        d.chain_hi[nc - 1] = b;
+        d.body_chain[b] = nc - 1;
+    }
+    d.nchain = nc;
+}
+
+}  // namespace egp
+
+using namespace egp;
+
+extern "C" {
+
+int egp_model_create(const EgpModelDesc *s, int device, EgpModel **out) {
+    if (!s || !out) { set_error("egp_model_create: null argument"); return EGP_EINVAL; }
+    if (s->nbody > MAXB || s->nv > MAXV || s->nbody < 1 || s->nv != s->nq - 1 || s->nu != s->nv - 6) {
+        set_error("egp_model_create: unsupported sizes nq=%d nv=%d nu=%d nbody=%d", s->nq, s->nv, s->nu, s->nbody);
+        return EGP_ESIZE;
+    }
+    if (s->body_dofnum[0] != 6 || s->body_parent[0] != -1) {
+        set_error("egp_model_create: body 0 must be the free-joint root");
+        return EGP_EINVAL;
+    }
+    EgpModel *m = new EgpModel();
+    memset(m, 0, sizeof(*m));
+    DevModel &d = m->host;
+    d.nq = s->nq; d.nv = s->nv; d.nu = s->nu; d.nbody = s->nbody;
+    d.frame_skip = s->frame_skip; d.head_body = s->head_body; d.v_ord = s->v_ord; d.decay = s->decay;
+    for (int k = 0; k < EGP_NEE; k++) d.ee_body[k] = s->ee_body[k];
+    d.h = s->timestep;
+    for (int k = 0; k < 3; k++) d.grav[k] = s->gravity[k];
+    for (int b = 0; b < s->nbody; b++) {
+        d.body_parent[b] = s->body_parent[b]; d.body_dofadr[b] = s->body_dofadr[b];
+        d.body_dofnum[b] = s->body_dofnum[b]; d.body_qposadr[b] = s->body_qposadr[b];
+        if (b > 0 && (s->body_parent[b] < 0 || s->body_parent[b] >= b || s->body_dofnum[b] < 1 || s->body_dofnum[b] > 3)) {
+            delete m;
+            set_error("egp_model_create: body %d: only 1-3 hinge joints on non-root bodies, parents before children", b);
+            return EGP_EINVAL;
+        }
+        d.body_mass[b] = s->body_mass[b];
+        for (int k = 0; k < 3; k++) { d.body_pos[b][k] = s->body_pos[3 * b + k]; d.body_ipos[b][k] = s->body_ipos[3 * b + k]; }
+        for (int k = 0; k < 6; k++) d.body_inertia[b][k] = s->body_inertia[6 * b + k];
+        d.b_diffw[b] = (b < s->nbody - 1 && s->b_diffw) ? s->b_diffw[b] : 1.0;
+    }
+    for (int i = 0; i < s->nv; i++) {
+        d.dof_arm[i] = s->dof_armature[i];
+        int aid = -1;
+        for (int k = 0; k < 3; k++) {
+            d.dof_axis[i][k] = s->dof_axis[3 * i + k];
+            d.dof_anchor[i][k] = s->dof_anchor[3 * i + k];
+        }
+        for (int k = 0; k < 3; k++)
+            if (d.dof_axis[i][k] == 1.0 && d.dof_axis[i][(k + 1) % 3] == 0.0 && d.dof_axis[i][(k + 2) % 3] == 0.0) aid = k;
+        d.dof_axis_id[i] = aid;
+        bool act = i >= 6;
+        d.kp[i] = act ? s->jkp[i - 6] : 0.0;
+        d.kd[i] = act ? s->jkd[i - 6] : 0.0;
+        d.a_ref[i] = act ? s->a_ref[i - 6] : 0.0;
+        d.a_scale[i] = act ? s->a_scale[i - 6] : 0.0;
+        d.tlim[i] = act ? s->torque_lim[i - 6] : 0.0;
+    }
+    d.w_p = s->w_p; d.w_v = s->w_v; d.w_e = s->w_e; d.w_rp = s->w_rp; d.w_rv = s->w_rv;
+    d.k_p = s->k_p; d.k_v = s->k_v; d.k_e = s->k_e; d.k_rh = s->k_rh; d.k_rq = s->k_rq; d.k_rl = s->k_rl; d.k_ra = s->k_ra;
+    build_chains(d);
+    if (d.nchain > MAXC) { delete m; set_error("egp_model_create: too many chains"); return EGP_ESIZE; }
+    m->device = device;
+    *out = m;
+    return EGP_OK;
+}
+
+void egp_model_destroy(EgpModel *m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    if (m->device >= 0 && m->device < 64 && g_bound_model[m->device] == m) g_bound_model[m->device] = nullptr;
+    cudaFree(m->d_take_off); cudaFree(m->d_rows); cudaFree(m->d_head_lb); cudaFree(m->d_ctx); cudaFree(m->d_wbuf);
+    delete m;
+}
+
+int egp_expert_upload(EgpModel *m, int n_takes, const int32_t *take_off, const double *rows, const double *head_lb,
+                      const double *ctx, int ctx_dim) {
+    if (!m || n_takes < 1 || !take_off || !rows || !head_lb) { set_error("egp_expert_upload: bad argument"); return EGP_EINVAL; }
+    EGP_CUDA(cudaSetDevice(m->device));
+    cudaFree(m->d_take_off); cudaFree(m->d_rows); cudaFree(m->d_head_lb); cudaFree(m->d_ctx);
+    m->d_take_off = nullptr; m->d_rows = nullptr; m->d_head_lb = nullptr; m->d_ctx = nullptr;
+    long long total = take_off[n_takes];
+    EGP_CUDA(cudaMalloc(&m->d_take_off, sizeof(int32_t) * (n_takes + 1)));
+    EGP_CUDA(cudaMalloc(&m->d_rows, sizeof(double) * total * EGP_X_STRIDE));
+    EGP_CUDA(cudaMalloc(&m->d_head_lb, sizeof(double) * n_takes));
+    EGP_CUDA(cudaMemcpy(m->d_take_off, take_off, sizeof(int32_t) * (n_takes + 1), cudaMemcpyHostToDevice));
+    EGP_CUDA(cudaMemcpy(m->d_rows, rows, sizeof(double) * total * EGP_X_STRIDE, cudaMemcpyHostToDevice));
+    EGP_CUDA(cudaMemcpy(m->d_head_lb, head_lb, sizeof(double) * n_takes, cudaMemcpyHostToDevice));
+    if (ctx && ctx_dim > 0) {
+        EGP_CUDA(cudaMalloc(&m->d_ctx, sizeof(double) * total * ctx_dim));
+        EGP_CUDA(cudaMemcpy(m->d_ctx, ctx, sizeof(double) * total * ctx_dim, cudaMemcpyHostToDevice));
+    }
+    m->n_takes = n_takes; m->ctx_dim = ctx ? ctx_dim : 0; m->total_frames = total;
+    return EGP_OK;
+}
+
+int egp_expert_features_f64(EgpModel *m, int L, const double *d_qpos, double *d_rows, double *d_head_z, void *stream) {
+    if (!m || L < 1 || !d_qpos || !d_rows || !d_head_z) { set_error("egp_expert_features_f64: bad argument"); return EGP_EINVAL; }
+    int rc = bind_model(m);
+    if (rc) return rc;
+    expert_features_kernel<<<(L + 63) / 64, 64, 0, (cudaStream_t)stream>>>(L, d_qpos, d_rows, d_head_z);
+    EGP_CHECK_LAUNCH("expert_features_kernel");
+    return EGP_OK;
+}
+
+int egp_forward_debug_f64(EgpModel *m, int n, const double *d_qpos, const double *d_qvel, const double *d_ctrl,
+                          double *d_bias, double *d_xpos, double *d_qacc, void *stream) {
+    if (!m || n < 1 || !d_qpos || !d_qvel || !d_bias || !d_xpos || !d_qacc) { set_error("egp_forward_debug_f64: bad argument"); return EGP_EINVAL; }
+    int rc = bind_model(m);
+    if (rc) return rc;
+    forward_debug_kernel<<<(n + 31) / 32, 32, 0, (cudaStream_t)stream>>>(n, d_qpos, d_qvel, d_ctrl, d_bias, d_xpos, d_qacc);
+    EGP_CHECK_LAUNCH("forward_debug_kernel");
+    return EGP_OK;
+}
+
+int egp_env_step_debug_f64(EgpModel *m, int n, double *d_qpos, double *d_qvel, const double *d_action, double *d_obs,
+                           double *d_head_z, double *d_torque0, void *stream) {
+    if (!m || n < 1 || !d_qpos || !d_qvel || !d_action || !d_obs || !d_head_z || !d_torque0) {
+        set_error("egp_env_step_debug_f64: bad argument");
+        return EGP_EINVAL;
+    }
+    int rc = bind_model(m);
+    if (rc) return rc;
+    env_step_debug_kernel<<<(n + 31) / 32, 32, 0, (cudaStream_t)stream>>>(n, d_qpos, d_qvel, d_action, d_obs, d_head_z, d_torque0);
+    EGP_CHECK_LAUNCH("env_step_debug_kernel");
+    return EGP_OK;
+}
+
+int egp_build_input_f64(EgpModel *m, const double *d_states, const int32_t *d_v_metas, const double *d_masks, int64_t n,
+                        int horizon, double *d_x, void *stream) {
+    if (!m || !m->d_ctx || n < 1 || horizon < 1 || n % horizon || !d_states || !d_v_metas || !d_masks || !d_x) {
+        set_error("egp_build_input_f64: bad argument (needs context rows uploaded and n %% horizon == 0)");
+        return EGP_EINVAL;
+    }
+    long long n_env = n / horizon;
+    int S = m->host.nq - 2 + m->host.nv;
+    long long threads = n_env * 32;
+    build_input_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        d_states, d_v_metas, d_masks, n_env, horizon, S, m->d_take_off, m->d_ctx, m->ctx_dim, d_x);
+    EGP_CHECK_LAUNCH("build_input_kernel");
+    return EGP_OK;
+}
+
+int egp_rollout_f64(EgpModel *m, const EgpPolicyWeights *pol, const EgpRolloutCfg *cfg, const EgpRolloutIn *in,
+                    const EgpTrajOut *out, void *stream) {
+    if (!m || !pol || !cfg || !out || !m->d_rows) { set_error("egp_rollout_f64: null argument or experts not uploaded"); return EGP_EINVAL; }
+    const DevModel &d = m->host;
+    const int S = d.nq - 2 + d.nv;
+    if (cfg->n_env < 1 || cfg->horizon < 1 || cfg->episode_len < 1) { set_error("egp_rollout_f64: bad sizes"); return EGP_EINVAL; }
+    if (pol->in_dim != S + m->ctx_dim || pol->out_dim != d.nu) {
+        set_error("egp_rollout_f64: policy dims (in %d out %d) do not match obs %d + ctx %d / nu %d", pol->in_dim, pol->out_dim, S, m->ctx_dim, d.nu);
+        return EGP_ESIZE;
+    }
+    if (!out->d_states || !out->d_actions || !out->d_masks || !out->d_rewards || !out->d_exps || !out->d_v_metas) {
+        set_error("egp_rollout_f64: required trajbatch outputs missing");
+        return EGP_EINVAL;
+    }
+    if (in && ((in->d_reset_take == nullptr) != (in->d_reset_start == nullptr))) { set_error("egp_rollout_f64: reset lists must come in pairs"); return EGP_EINVAL; }
+    if (in && in->d_reset_take && cfg->max_resets < 1) { set_error("egp_rollout_f64: max_resets < 1"); return EGP_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = bind_model(m);
+    if (rc) return rc;
+    auto pad = [](int x) { return (x + JB - 1) / JB * JB; };
+    RolloutArgs A;
+    memset(&A, 0, sizeof A);
+    A.cfg = *cfg;
+    if (in) A.in = *in;
+    A.out = *out;
+    A.take_off = m->d_take_off; A.rows = m->d_rows; A.head_lb = m->d_head_lb; A.ctx = m->d_ctx;
+    A.n_takes = m->n_takes; A.ctx_dim = m->ctx_dim;
+    A.D = pol->in_dim; A.H1 = pol->h1; A.H2 = pol->h2; A.A = pol->out_dim;
+    A.H1p = pad(A.H1); A.H2p = pad(A.H2); A.Ap = pad(A.A);
+    size_t need = (size_t)A.D * A.H1p + A.H1p + (size_t)A.H1 * A.H2p + A.H2p + (size_t)A.H2 * A.Ap + A.Ap;
+    if (need > m->wbuf_elems) {
+        cudaFree(m->d_wbuf);
+        m->d_wbuf = nullptr; m->wbuf_elems = 0;
+        EGP_CUDA(cudaMalloc(&m->d_wbuf, sizeof(double) * need));
+        m->wbuf_elems = need;
+    }
+    double *w = m->d_wbuf;
+    double *W1t = w; w += (size_t)A.D * A.H1p;
+    double *b1 = w; w += A.H1p;
+    double *W2t = w; w += (size_t)A.H1 * A.H2p;
+    double *b2 = w; w += A.H2p;
+    double *W3t = w; w += (size_t)A.H2 * A.Ap;
+    double *b3 = w;
+    transpose_pad_kernel<<<(A.D * A.H1p + 255) / 256, 256, 0, st>>>(pol->d_W1, pol->d_b1, A.H1, A.D, A.H1p, W1t, b1);
+    transpose_pad_kernel<<<(A.H1 * A.H2p + 255) / 256, 256, 0, st>>>(pol->d_W2, pol->d_b2, A.H2, A.H1, A.H2p, W2t, b2);
+    transpose_pad_kernel<<<(A.H2 * A.Ap + 255) / 256, 256, 0, st>>>(pol->d_W3, pol->d_b3, A.A, A.H2, A.Ap, W3t, b3);
+    EGP_CHECK_LAUNCH("transpose_pad_kernel");
+    A.W1t = W1t; A.b1 = b1; A.W2t = W2t; A.b2 = b2; A.W3t = W3t; A.b3 = b3; A.log_std = pol->d_log_std;
+    if (out->d_logger) {
+        double init[EGP_LOG_SIZE] = {0};
+        init[EGP_LOG_MIN_C_REWARD] = INFINITY; init[EGP_LOG_MAX_C_REWARD] = -INFINITY;
+        init[EGP_LOG_MIN_EPISODE_REWARD] = INFINITY; init[EGP_LOG_MAX_EPISODE_REWARD] = -INFINITY;
+        EGP_CUDA(cudaMemcpyAsync(out->d_logger, init, sizeof init, cudaMemcpyHostToDevice, st));
+    }
+    int xrows = A.D > A.H2p ? A.D : A.H2p;
+    size_t smem = sizeof(double) * ENVS_PER_CTA * ((size_t)xrows + A.H1p);
+    if (smem > 227 * 1024) { set_error("egp_rollout_f64: policy too wide for shared memory (%zu bytes)", smem); return EGP_ESIZE; }
+    EGP_CUDA(cudaFuncSetAttribute(rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int blocks = (cfg->n_env + ENVS_PER_CTA - 1) / ENVS_PER_CTA;
+    rollout_kernel<<<blocks, ENVS_PER_CTA, smem, st>>>(A);
+    EGP_CHECK_LAUNCH("rollout_kernel");
+    return EGP_OK;
+}
+
+}  // extern "C"

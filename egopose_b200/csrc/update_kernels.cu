@@ -1,0 +1,577 @@
+// PPO update kernels (K4 GAE scan, K5 loss forward+backward, K6 clip+Adam) - sm_100a, float64.
+// All of these are HBM-bound streaming kernels: coalesced 128-bit accesses, grid sized in multiples
+// of the SM count, one pass over the data (SURVEY.md 8d gives the algorithmic bytes per unit).
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace egp {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char *what) {
+    set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    return EGP_ECUDA;
+}
+int num_sms(int device) {
+    static int cached[64] = {0};
+    if (device < 0) cudaGetDevice(&device);
+    if (device >= 0 && device < 64 && cached[device]) return cached[device];
+    int n = 148;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device);
+    if (device >= 0 && device < 64) cached[device] = n;
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------ K4 GAE
+// core/common.py:5-25.  A_i = delta_i + c_i A_{i+1},  delta_i = r_i + gamma V_{i+1} m_i - V_i,
+// c_i = gamma tau m_i, flat over the batch with A_N = V_N = 0.  Single pass, reverse decoupled
+// look-back: tiles are claimed in processing order from the END of the batch; every tile publishes
+// its affine aggregate (C, D) then its inclusive value; successors chain through them and stop early
+// at any episode boundary (C == 0).  Algorithmic traffic 5 doubles / sample.
+constexpr int GAE_THREADS = 256;
+constexpr int GAE_ITEMS = 4;
+constexpr int GAE_TILE = GAE_THREADS * GAE_ITEMS;
+
+struct GaeWork {            // header of d_work
+    unsigned int next_tile;
+    unsigned int done_tiles;
+    unsigned int pad[2];
+};
+
+struct Moments { double n, mean, m2; };
+
+__device__ __forceinline__ Moments merge(Moments a, Moments b) {
+    if (b.n == 0.0) return a;
+    if (a.n == 0.0) return b;
+    Moments r;
+    r.n = a.n + b.n;
+    double d = b.mean - a.mean;
+    r.mean = a.mean + d * (b.n / r.n);
+    r.m2 = a.m2 + b.m2 + d * d * (a.n * b.n / r.n);
+    return r;
+}
+__device__ __forceinline__ Moments shfl_down(Moments a, int o) {
+    Moments r;
+    r.n = __shfl_down_sync(0xffffffffu, a.n, o);
+    r.mean = __shfl_down_sync(0xffffffffu, a.mean, o);
+    r.m2 = __shfl_down_sync(0xffffffffu, a.m2, o);
+    return r;
+}
+
+__global__ void __launch_bounds__(GAE_THREADS)
+gae_kernel(const double *__restrict__ rew, const double *__restrict__ msk, const double *__restrict__ val,
+           double gamma, double tau, long long n, unsigned int ntiles, double *__restrict__ adv,
+           double *__restrict__ ret, double *__restrict__ stats, GaeWork *work, volatile int *flags,
+           volatile double *pub /* [ntiles][3] C, D, inclusive */, double *partial /* [ntiles][3] */) {
+    __shared__ unsigned int s_p;
+    __shared__ double s_c[GAE_THREADS / 32], s_d[GAE_THREADS / 32];
+    __shared__ double s_ain;
+    __shared__ Moments s_mom[GAE_THREADS / 32];
+    __shared__ bool s_last;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_p = atomicAdd(&work->next_tile, 1u);
+    __syncthreads();
+    const unsigned int p = s_p;                     // processing order, 0 = last tile of the batch
+    const long long tile = (long long)ntiles - 1 - p;
+    // thread 0 owns the HIGHEST indices of the tile
+    const long long lo = tile * GAE_TILE + (long long)(GAE_THREADS - 1 - tid) * GAE_ITEMS;
+    double r[GAE_ITEMS], c[GAE_ITEMS], v[GAE_ITEMS + 1];
+#pragma unroll
+    for (int k = 0; k < GAE_ITEMS; k++) {
+        long long i = lo + k;
+        bool ok = i < n;
+        r[k] = ok ? rew[i] : 0.0;
+        double m = ok ? msk[i] : 0.0;
+        v[k] = ok ? val[i] : 0.0;
+        c[k] = ok ? m : 0.0;                        // holds the mask for now
+    }
+    v[GAE_ITEMS] = (lo + GAE_ITEMS < n) ? val[lo + GAE_ITEMS] : 0.0;
+    double dl[GAE_ITEMS];
+    double C = 1.0, D = 0.0;
+#pragma unroll
+    for (int k = GAE_ITEMS - 1; k >= 0; k--) {      // highest index first
+        double m = c[k];
+        dl[k] = r[k] + gamma * v[k + 1] * m - v[k];
+        c[k] = gamma * tau * m;
+        D = dl[k] + c[k] * D;
+        C = c[k] * C;
+    }
+    // inclusive scan over threads (thread order = descending index): (C,D) o= prev
+    double iC = C, iD = D;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        double pc = __shfl_up_sync(0xffffffffu, iC, o), pd = __shfl_up_sync(0xffffffffu, iD, o);
+        if (lane >= o) { iD = iD + iC * pd; iC = iC * pc; }
+    }
+    if (lane == 31) { s_c[warp] = iC; s_d[warp] = iD; }
+    __syncthreads();
+    double wC = 1.0, wD = 0.0;                      // composition of all earlier warps
+    for (int w = 0; w < warp; w++) { wD = s_d[w] + s_c[w] * wD; wC = s_c[w] * wC; }
+    iD = iD + iC * wD;
+    iC = iC * wC;
+    // exclusive value for this thread
+    double eC = __shfl_up_sync(0xffffffffu, iC, 1), eD = __shfl_up_sync(0xffffffffu, iD, 1);
+    if (lane == 0) { eC = wC; eD = wD; }
+    if (tid == GAE_THREADS - 1) {
+        // publish aggregate, look back, publish inclusive
+        double tC = iC, tD = iD;
+        pub[3 * (size_t)p + 0] = tC;
+        pub[3 * (size_t)p + 1] = tD;
+        __threadfence();
+        flags[p] = 1;
+        double aC = 1.0, aD = 0.0, ain = 0.0;
+        long long q = (long long)p - 1;
+        bool done = false;
+        while (!done) {
+            if (q < 0 || aC == 0.0) { ain = aD; break; }
+            int f;
+            do { f = flags[q]; } while (f == 0);
+            __threadfence();
+            if (f == 2) { ain = aD + aC * pub[3 * (size_t)q + 2]; done = true; }
+            else { aD = aD + aC * pub[3 * (size_t)q + 1]; aC = aC * pub[3 * (size_t)q + 0]; q--; }
+        }
+        pub[3 * (size_t)p + 2] = tD + tC * ain;
+        __threadfence();
+        flags[p] = 2;
+        s_ain = ain;
+    }
+    __syncthreads();
+    double a = eD + eC * s_ain;                     // advantage just above this thread's highest element
+    Moments mom = {0.0, 0.0, 0.0};
+    double out_a[GAE_ITEMS];
+#pragma unroll
+    for (int k = GAE_ITEMS - 1; k >= 0; k--) {
+        a = dl[k] + c[k] * a;
+        out_a[k] = a;
+        if (lo + k < n) {
+            Moments one = {1.0, a, 0.0};
+            mom = merge(mom, one);
+        }
+    }
+    if (lo + GAE_ITEMS <= n) {
+        double2 *pa = reinterpret_cast<double2 *>(adv + lo), *pr = reinterpret_cast<double2 *>(ret + lo);
+        pa[0] = make_double2(out_a[0], out_a[1]);
+        pa[1] = make_double2(out_a[2], out_a[3]);
+        pr[0] = make_double2(v[0] + out_a[0], v[1] + out_a[1]);
+        pr[1] = make_double2(v[2] + out_a[2], v[3] + out_a[3]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < GAE_ITEMS; k++)
+            if (lo + k < n) { adv[lo + k] = out_a[k]; ret[lo + k] = v[k] + out_a[k]; }
+    }
+    // advantage moments (n, mean, M2): deterministic tree inside the tile, tiles merged in index order
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mom = merge(mom, shfl_down(mom, o));
+    if (lane == 0) s_mom[warp] = mom;
+    __syncthreads();
+    if (tid == 0) {
+        Moments t = s_mom[0];
+        for (int w = 1; w < GAE_THREADS / 32; w++) t = merge(t, s_mom[w]);
+        partial[3 * tile + 0] = t.n; partial[3 * tile + 1] = t.mean; partial[3 * tile + 2] = t.m2;
+        __threadfence();
+        s_last = atomicAdd(&work->done_tiles, 1u) == ntiles - 1;
+    }
+    __syncthreads();
+    if (s_last && warp == 0) {
+        __threadfence();
+        Moments t = {0.0, 0.0, 0.0};
+        for (unsigned int k = lane; k < ntiles; k += 32) {
+            Moments o = {partial[3 * k], partial[3 * k + 1], partial[3 * k + 2]};
+            t = merge(t, o);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t = merge(t, shfl_down(t, o));
+        if (lane == 0) { stats[0] = t.n; stats[1] = t.mean; stats[2] = t.m2; }
+    }
+}
+
+__global__ void standardize_kernel(double *x, long long n, const double *stats) {
+    const double mean = stats[1], inv = 1.0 / sqrt(stats[2] / (stats[0] - 1.0));
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        x[i] = (x[i] - mean) * inv;
+}
+
+// ------------------------------------------------------------------------- K5 loss fwd + bwd
+// 16 lanes per row; lane s of a group handles action dims s, s+16, s+32, ... (coalesced 128 B runs).
+constexpr int LPR = 16;
+constexpr double HALF_LOG_2PI = 0.91893853320467274178;
+
+__device__ __forceinline__ double group_sum16(double v) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(256)
+gauss_logp_kernel(const double *__restrict__ mu, const double *__restrict__ act, const double *__restrict__ log_std,
+                  long long n, int adim, double *__restrict__ logp) {
+    const int sub = threadIdx.x & (LPR - 1);
+    const long long g0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / LPR;
+    const long long stride = (long long)gridDim.x * blockDim.x / LPR;
+    for (long long row = g0; row < n; row += stride) {
+        double s = 0.0;
+        for (int j = sub; j < adim; j += LPR) {
+            double ls = log_std[j], d = act[row * adim + j] - mu[row * adim + j];
+            double var = exp(ls) * exp(ls);
+            s += -(d * d) / (2.0 * var) - ls - HALF_LOG_2PI;
+        }
+        s = group_sum16(s);
+        if (sub == 0) logp[row] = s;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+ppo_loss_grad_kernel(const double *__restrict__ mu, const double *__restrict__ act, const double *__restrict__ log_std,
+                     const double *__restrict__ adv, const double *__restrict__ stats, const double *__restrict__ logp0,
+                     const double *__restrict__ exps, double clip_eps, double inv_count, long long n, int adim,
+                     double *__restrict__ dmu, double *__restrict__ dlogstd, double *__restrict__ loss) {
+    const int sub = threadIdx.x & (LPR - 1);
+    const long long g0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / LPR;
+    const long long stride = (long long)gridDim.x * blockDim.x / LPR;
+    const double a_mean = stats[1], a_inv = 1.0 / sqrt(stats[2] / (stats[0] - 1.0));
+    double loss_acc = 0.0;
+    double dls_acc[4] = {0.0, 0.0, 0.0, 0.0};       // adim <= 64
+    for (long long row = g0; row < n; row += stride) {
+        double d[4], iv[4];
+        double s = 0.0;
+        int cnt = 0;
+        for (int j = sub; j < adim; j += LPR, cnt++) {
+            double ls = log_std[j];
+            double sd = exp(ls);
+            double var = sd * sd;
+            d[cnt] = act[row * adim + j] - mu[row * adim + j];
+            iv[cnt] = 1.0 / var;
+            s += -(d[cnt] * d[cnt]) / (2.0 * var) - ls - HALF_LOG_2PI;
+        }
+        s = group_sum16(s);
+        const bool on = exps[row] != 0.0;
+        double coef = 0.0;                           // dL/dlogp
+        if (on) {
+            double ratio = exp(s - logp0[row]);
+            double ah = (adv[row] - a_mean) * a_inv;
+            double lo = 1.0 - clip_eps, hi = 1.0 + clip_eps;
+            double clamped = fmin(fmax(ratio, lo), hi);
+            double s1 = ratio * ah, s2 = clamped * ah;
+            double inrange = (ratio >= lo && ratio <= hi) ? 1.0 : 0.0;
+            // torch.min backward: ties split evenly; clamp backward passes inside the closed range
+            double w = s1 < s2 ? 1.0 : (s1 > s2 ? inrange : 0.5 + 0.5 * inrange);
+            coef = -inv_count * ah * w * ratio;
+            if (sub == 0) loss_acc += -fmin(s1, s2) * inv_count;
+        }
+        cnt = 0;
+        for (int j = sub; j < adim; j += LPR, cnt++) {
+            dmu[row * adim + j] = coef * d[cnt] * iv[cnt];
+            dls_acc[cnt] += coef * (d[cnt] * d[cnt] * iv[cnt] - 1.0);
+        }
+    }
+    // block reduction of the scalar loss
+    loss_acc = warp_sum(loss_acc);
+    if ((threadIdx.x & 31) == 0 && loss_acc != 0.0) atomicAdd(loss, loss_acc);
+    if (dlogstd) {
+        int cnt = 0;
+        for (int j = sub; j < adim; j += LPR, cnt++) {
+            double v = dls_acc[cnt] + __shfl_xor_sync(0xffffffffu, dls_acc[cnt], 16);
+            if ((threadIdx.x & 31) < LPR && v != 0.0) atomicAdd(dlogstd + j, v);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+value_loss_grad_kernel(const double *__restrict__ v, const double *__restrict__ ret, double inv_n, long long n,
+                       double *__restrict__ dv, double *__restrict__ loss) {
+    double acc = 0.0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        double e = v[i] - ret[i];
+        dv[i] = 2.0 * e * inv_n;
+        acc += e * e;
+    }
+    acc = warp_sum(acc);
+    __shared__ double s[8];
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += s[w];
+        atomicAdd(loss, t * inv_n);
+    }
+}
+
+// ---------------------------------------------------------------- elementwise helpers around GEMMs
+__global__ void __launch_bounds__(256)
+bias_relu_kernel(double *__restrict__ y, const double *__restrict__ b, long long total, int dim) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        double t = y[i] + b[i % dim];
+        y[i] = t > 0.0 ? t : 0.0;
+    }
+}
+__global__ void __launch_bounds__(256)
+relu_bwd_kernel(double *__restrict__ dy, const double *__restrict__ y, long long total) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+        if (!(y[i] > 0.0)) dy[i] = 0.0;
+}
+// column sums: block = 32 x 8 threads; each block owns a band of rows, lanes sweep columns (coalesced)
+__global__ void __launch_bounds__(256)
+colsum_kernel(const double *__restrict__ x, long long n, int dim, long long rows_per_block, double *__restrict__ out) {
+    __shared__ double s[8][33];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    long long r0 = blockIdx.x * rows_per_block, r1 = r0 + rows_per_block;
+    if (r1 > n) r1 = n;
+    for (int c0 = 0; c0 < dim; c0 += 32) {
+        int c = c0 + lane;
+        double acc = 0.0;
+        if (c < dim)
+            for (long long r = r0 + w; r < r1; r += 8) acc += x[r * dim + c];
+        s[w][lane] = acc;
+        __syncthreads();
+        if (w == 0 && c < dim) {
+            double t = 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) t += s[k][lane];
+            atomicAdd(out + c, t);
+        }
+        __syncthreads();
+    }
+}
+
+// shifted first/second column moments (batched ZFilter update)
+__global__ void __launch_bounds__(256)
+col_moments_kernel(const double *__restrict__ x, long long n, int dim, long long rows_per_block,
+                   const double *__restrict__ shift, double *__restrict__ out) {
+    __shared__ double s1[8][33], s2[8][33];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    long long r0 = blockIdx.x * rows_per_block, r1 = r0 + rows_per_block;
+    if (r1 > n) r1 = n;
+    for (int c0 = 0; c0 < dim; c0 += 32) {
+        int c = c0 + lane;
+        double a1 = 0.0, a2 = 0.0;
+        if (c < dim) {
+            const double sh = shift ? shift[c] : 0.0;
+            for (long long r = r0 + w; r < r1; r += 8) { double d = x[r * dim + c] - sh; a1 += d; a2 += d * d; }
+        }
+        s1[w][lane] = a1; s2[w][lane] = a2;
+        __syncthreads();
+        if (w == 0 && c < dim) {
+            double t1 = 0.0, t2 = 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) { t1 += s1[k][lane]; t2 += s2[k][lane]; }
+            atomicAdd(out + c, t1);
+            atomicAdd(out + dim + c, t2);
+        }
+        __syncthreads();
+    }
+}
+
+// -------------------------------------------------------------------------------- K6 clip + Adam
+// Deterministic sum of squares (fixed grid, last block folds the partials in index order) so that
+// data-parallel replicas compute bit-identical clip coefficients after the gradient all-reduce.
+constexpr int SUMSQ_BLOCKS = 148;
+__device__ double g_sumsq_partial[SUMSQ_BLOCKS];
+__device__ unsigned int g_sumsq_ticket = 0;
+
+__global__ void __launch_bounds__(256)
+sumsq_kernel(const double *__restrict__ g, long long n, double *__restrict__ norm2) {
+    double acc = 0.0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        acc += g[i] * g[i];
+    acc = warp_sum(acc);
+    __shared__ double s[8];
+    __shared__ bool last;
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; w++) t += s[w];
+        g_sumsq_partial[blockIdx.x] = t;
+        __threadfence();
+        last = atomicAdd(&g_sumsq_ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence();
+        double t = 0.0;
+        for (unsigned int b = 0; b < gridDim.x; b++) t += g_sumsq_partial[b];
+        norm2[0] = t;
+        g_sumsq_ticket = 0;
+    }
+}
+
+// torch.optim.Adam (amsgrad False, weight_decay 0) with the clip_grad_norm_ coefficient folded in:
+// coef = min(1, max_norm / (||g|| + 1e-6)) when max_norm > 0 (torch.nn.utils.clip_grad_norm_).
+__global__ void __launch_bounds__(256)
+adam_kernel(double *__restrict__ p, const double *__restrict__ g, double *__restrict__ m, double *__restrict__ v,
+            long long n, double lr, double b1, double b2, double eps, double bc1, double bc2_sqrt, double max_norm,
+            const double *__restrict__ norm2) {
+    double coef = 1.0;
+    if (max_norm > 0.0) {
+        double c = max_norm / (sqrt(norm2[0]) + 1e-6);
+        coef = c < 1.0 ? c : 1.0;
+    }
+    const double step_size = lr / bc1;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        double gi = g[i] * coef;
+        double mi = m[i] + (gi - m[i]) * (1.0 - b1);        // exp_avg.lerp_(grad, 1 - beta1)
+        double vi = v[i] * b2 + (1.0 - b2) * gi * gi;       // mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+        m[i] = mi;
+        v[i] = vi;
+        double denom = sqrt(vi) / bc2_sqrt + eps;
+        p[i] = p[i] - step_size * (mi / denom);
+    }
+}
+
+static int grid_for(long long n, int threads, int per_sm = 8) {
+    long long want = (n + threads - 1) / threads;
+    long long cap = (long long)num_sms() * per_sm;
+    if (want < 1) want = 1;
+    return (int)(want < cap ? want : cap);
+}
+
+}  // namespace egp
+
+using namespace egp;
+
+extern "C" {
+
+const char *egp_last_error_string(void) { return egp::g_err; }
+int egp_version(void) { return 100; }
+
+int64_t egp_gae_work_bytes(int64_t n) {
+    int64_t nt = (n + GAE_TILE - 1) / GAE_TILE;
+    if (nt < 1) nt = 1;
+    return (int64_t)sizeof(GaeWork) + nt * (int64_t)(sizeof(int) + 6 * sizeof(double)) + 64;
+}
+
+int egp_gae_f64(const double *d_rewards, const double *d_masks, const double *d_values, double gamma, double tau,
+                int64_t n, double *d_adv, double *d_ret, double *d_stats, void *d_work, void *stream) {
+    if (n <= 0 || !d_rewards || !d_masks || !d_values || !d_adv || !d_ret || !d_stats || !d_work) {
+        set_error("egp_gae_f64: bad argument");
+        return EGP_EINVAL;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned int nt = (unsigned int)((n + GAE_TILE - 1) / GAE_TILE);
+    EGP_CUDA(cudaMemsetAsync(d_work, 0, (size_t)egp_gae_work_bytes(n), st));
+    char *base = (char *)d_work;
+    GaeWork *work = (GaeWork *)base;
+    double *pub = (double *)(base + sizeof(GaeWork));
+    double *partial = pub + 3 * (size_t)nt;
+    int *flags = (int *)(partial + 3 * (size_t)nt);
+    gae_kernel<<<nt, GAE_THREADS, 0, st>>>(d_rewards, d_masks, d_values, gamma, tau, (long long)n, nt, d_adv, d_ret,
+                                           d_stats, work, flags, pub, partial);
+    EGP_CHECK_LAUNCH("gae_kernel");
+    return EGP_OK;
+}
+
+int egp_standardize_f64(double *d_x, int64_t n, const double *d_stats, void *stream) {
+    if (n <= 0 || !d_x || !d_stats) { set_error("egp_standardize_f64: bad argument"); return EGP_EINVAL; }
+    standardize_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(d_x, (long long)n, d_stats);
+    EGP_CHECK_LAUNCH("standardize_kernel");
+    return EGP_OK;
+}
+
+int egp_gauss_logp_f64(const double *d_mu, const double *d_actions, const double *d_log_std, int64_t n, int adim,
+                       double *d_logp, void *stream) {
+    if (n <= 0 || adim <= 0 || !d_mu || !d_actions || !d_log_std || !d_logp) {
+        set_error("egp_gauss_logp_f64: bad argument");
+        return EGP_EINVAL;
+    }
+    gauss_logp_kernel<<<grid_for(n * LPR, 256), 256, 0, (cudaStream_t)stream>>>(d_mu, d_actions, d_log_std, (long long)n,
+                                                                              adim, d_logp);
+    EGP_CHECK_LAUNCH("gauss_logp_kernel");
+    return EGP_OK;
+}
+
+int egp_ppo_loss_grad_f64(const double *d_mu, const double *d_actions, const double *d_log_std, const double *d_adv,
+                          const double *d_stats, const double *d_logp0, const double *d_exps, double clip_eps,
+                          double inv_count, int64_t n, int adim, double *d_dmu, double *d_dlogstd, double *d_loss,
+                          void *stream) {
+    if (n <= 0 || adim <= 0 || adim > 4 * LPR || !d_mu || !d_actions || !d_log_std || !d_adv || !d_stats || !d_logp0 ||
+        !d_exps || !d_dmu || !d_loss) {
+        set_error("egp_ppo_loss_grad_f64: bad argument (adim must be <= %d)", 4 * LPR);
+        return EGP_EINVAL;
+    }
+    ppo_loss_grad_kernel<<<grid_for(n * LPR, 256), 256, 0, (cudaStream_t)stream>>>(
+        d_mu, d_actions, d_log_std, d_adv, d_stats, d_logp0, d_exps, clip_eps, inv_count, (long long)n, adim, d_dmu,
+        d_dlogstd, d_loss);
+    EGP_CHECK_LAUNCH("ppo_loss_grad_kernel");
+    return EGP_OK;
+}
+
+int egp_value_loss_grad_f64(const double *d_v, const double *d_ret, double inv_n, int64_t n, double *d_dv,
+                            double *d_loss, void *stream) {
+    if (n <= 0 || !d_v || !d_ret || !d_dv || !d_loss) { set_error("egp_value_loss_grad_f64: bad argument"); return EGP_EINVAL; }
+    value_loss_grad_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(d_v, d_ret, inv_n, (long long)n, d_dv, d_loss);
+    EGP_CHECK_LAUNCH("value_loss_grad_kernel");
+    return EGP_OK;
+}
+
+int egp_bias_relu_f64(double *d_y, const double *d_b, int64_t n, int dim, void *stream) {
+    if (n <= 0 || dim <= 0 || !d_y || !d_b) { set_error("egp_bias_relu_f64: bad argument"); return EGP_EINVAL; }
+    bias_relu_kernel<<<grid_for(n * dim, 256), 256, 0, (cudaStream_t)stream>>>(d_y, d_b, (long long)n * dim, dim);
+    EGP_CHECK_LAUNCH("bias_relu_kernel");
+    return EGP_OK;
+}
+
+int egp_relu_bwd_f64(double *d_dy, const double *d_y, int64_t n, int dim, void *stream) {
+    if (n <= 0 || dim <= 0 || !d_dy || !d_y) { set_error("egp_relu_bwd_f64: bad argument"); return EGP_EINVAL; }
+    relu_bwd_kernel<<<grid_for(n * dim, 256), 256, 0, (cudaStream_t)stream>>>(d_dy, d_y, (long long)n * dim);
+    EGP_CHECK_LAUNCH("relu_bwd_kernel");
+    return EGP_OK;
+}
+
+int egp_colsum_f64(const double *d_x, int64_t n, int dim, double *d_out, void *stream) {
+    if (n <= 0 || dim <= 0 || !d_x || !d_out) { set_error("egp_colsum_f64: bad argument"); return EGP_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    EGP_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * dim, st));
+    int blocks = num_sms() * 4;
+    long long rpb = (n + blocks - 1) / blocks;
+    if (rpb < 8) rpb = 8;
+    blocks = (int)((n + rpb - 1) / rpb);
+    colsum_kernel<<<blocks, 256, 0, st>>>(d_x, (long long)n, dim, rpb, d_out);
+    EGP_CHECK_LAUNCH("colsum_kernel");
+    return EGP_OK;
+}
+
+int egp_col_moments_f64(const double *d_x, int64_t n, int dim, const double *d_shift, double *d_out, void *stream) {
+    if (n <= 0 || dim <= 0 || !d_x || !d_out) { set_error("egp_col_moments_f64: bad argument"); return EGP_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    EGP_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * 2 * dim, st));
+    int blocks = num_sms() * 4;
+    long long rpb = (n + blocks - 1) / blocks;
+    if (rpb < 8) rpb = 8;
+    blocks = (int)((n + rpb - 1) / rpb);
+    col_moments_kernel<<<blocks, 256, 0, st>>>(d_x, (long long)n, dim, rpb, d_shift, d_out);
+    EGP_CHECK_LAUNCH("col_moments_kernel");
+    return EGP_OK;
+}
+
+int egp_sumsq_f64(const double *d_g, int64_t n, double *d_norm2, void *stream) {
+    if (n <= 0 || !d_g || !d_norm2) { set_error("egp_sumsq_f64: bad argument"); return EGP_EINVAL; }
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > SUMSQ_BLOCKS) blocks = SUMSQ_BLOCKS;
+    sumsq_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_g, (long long)n, d_norm2);
+    EGP_CHECK_LAUNCH("sumsq_kernel");
+    return EGP_OK;
+}
+
+int egp_adam_step_f64(double *d_p, const double *d_g, double *d_m, double *d_v, int64_t n, double lr, double beta1,
+                      double beta2, double eps, int64_t step, double max_norm, const double *d_norm2, void *stream) {
+    if (n <= 0 || step < 1 || !d_p || !d_g || !d_m || !d_v || (max_norm > 0.0 && !d_norm2)) {
+        set_error("egp_adam_step_f64: bad argument");
+        return EGP_EINVAL;
+    }
+    double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+    adam_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(d_p, d_g, d_m, d_v, (long long)n, lr, beta1, beta2, eps,
+                                                                   bc1, sqrt(bc2), max_norm, d_norm2);
+    EGP_CHECK_LAUNCH("adam_kernel");
+    return EGP_OK;
+}
+
+}  // extern "C"

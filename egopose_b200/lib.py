@@ -1,0 +1,438 @@
+"""ctypes binding of libegopose_b200.so (include/egopose_b200.h).
+
+There is NO CPU fallback: importing this module is cheap, but every compute entry point requires the
+CUDA library built in-tree (python -m egopose_b200.build) and a CUDA device; failures raise EgpError.
+PyTorch is used only to own device memory / streams (tensor.data_ptr()).
+"""
+import ctypes as C
+import math
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libegopose_b200.so')
+
+X = dict(QPOS=0, QVEL=59, RLINV_LOCAL=117, RANGV=120, RQ_RMH=123, EE_POS=127, BQUAT=142, BANGVEL=226, STRIDE=292)
+NEE = 5
+LOG = dict(NUM_STEPS=0, NUM_EPISODES=1, TOTAL_REWARD=2, TOTAL_C_REWARD=3, MIN_C_REWARD=4, MAX_C_REWARD=5, C_INFO=6,
+           MIN_EPISODE_REWARD=11, MAX_EPISODE_REWARD=12, NUM_NAN_RESETS=13, SIZE=16)
+EE_NAMES = ['LeftFoot', 'RightFoot', 'LeftHand', 'RightHand', 'Head']       # humanoid_v1.py:100
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+_vp = C.c_void_p
+
+
+class EgpError(RuntimeError):
+    pass
+
+
+class ModelDesc(C.Structure):
+    _fields_ = [('nq', C.c_int32), ('nv', C.c_int32), ('nu', C.c_int32), ('nbody', C.c_int32),
+                ('timestep', C.c_double), ('gravity', C.c_double * 3),
+                ('body_parent', _ip), ('body_dofadr', _ip), ('body_dofnum', _ip), ('body_qposadr', _ip),
+                ('body_pos', _dp), ('body_mass', _dp), ('body_ipos', _dp), ('body_inertia', _dp),
+                ('dof_body', _ip), ('dof_parent', _ip),
+                ('dof_armature', _dp), ('dof_axis', _dp), ('dof_anchor', _dp),
+                ('ee_body', C.c_int32 * NEE), ('head_body', C.c_int32), ('frame_skip', C.c_int32),
+                ('jkp', _dp), ('jkd', _dp), ('a_ref', _dp), ('a_scale', _dp), ('torque_lim', _dp), ('b_diffw', _dp),
+                ('w_p', C.c_double), ('w_v', C.c_double), ('w_e', C.c_double), ('w_rp', C.c_double),
+                ('w_rv', C.c_double), ('k_p', C.c_double), ('k_v', C.c_double), ('k_e', C.c_double),
+                ('k_rh', C.c_double), ('k_rq', C.c_double), ('k_rl', C.c_double), ('k_ra', C.c_double),
+                ('v_ord', C.c_int32), ('decay', C.c_int32)]
+
+
+class RolloutCfg(C.Structure):
+    _fields_ = [('n_env', C.c_int32), ('horizon', C.c_int32), ('episode_len', C.c_int32), ('fr_margin', C.c_int32),
+                ('end_reward', C.c_double), ('fix_head_lb', C.c_double), ('noise_rate', C.c_double),
+                ('mean_action', C.c_int32), ('zf_clip', C.c_double), ('seed', C.c_uint64), ('iteration', C.c_uint64),
+                ('max_resets', C.c_int32)]
+
+
+class PolicyWeights(C.Structure):
+    _fields_ = [('in_dim', C.c_int32), ('h1', C.c_int32), ('h2', C.c_int32), ('out_dim', C.c_int32),
+                ('d_W1', _vp), ('d_b1', _vp), ('d_W2', _vp), ('d_b2', _vp), ('d_W3', _vp), ('d_b3', _vp),
+                ('d_log_std', _vp)]
+
+
+class RolloutIn(C.Structure):
+    _fields_ = [('d_eps', _vp), ('d_reset_take', _vp), ('d_reset_start', _vp), ('d_mean_flag', _vp),
+                ('d_zf_mean', _vp), ('d_zf_std', _vp)]
+
+
+class TrajOut(C.Structure):
+    _fields_ = [('d_states', _vp), ('d_actions', _vp), ('d_masks', _vp), ('d_next_states', _vp), ('d_rewards', _vp),
+                ('d_exps', _vp), ('d_v_metas', _vp), ('d_c_info', _vp), ('d_raw_obs', _vp), ('d_final_qpos', _vp),
+                ('d_final_qvel', _vp), ('d_logger', _vp)]
+
+
+# every symbol include/egopose_b200.h declares: name -> (restype, argtypes)
+_i64 = C.c_int64
+_d = C.c_double
+_int = C.c_int
+SYMBOLS = {
+    'egp_last_error_string': (C.c_char_p, []),
+    'egp_version': (_int, []),
+    'egp_model_create': (_int, [C.POINTER(ModelDesc), _int, C.POINTER(_vp)]),
+    'egp_model_destroy': (None, [_vp]),
+    'egp_expert_upload': (_int, [_vp, _int, _ip, _dp, _dp, _dp, _int]),
+    'egp_expert_features_f64': (_int, [_vp, _int, _vp, _vp, _vp, _vp]),
+    'egp_forward_debug_f64': (_int, [_vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'egp_env_step_debug_f64': (_int, [_vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'egp_rollout_f64': (_int, [_vp, C.POINTER(PolicyWeights), C.POINTER(RolloutCfg), C.POINTER(RolloutIn),
+                               C.POINTER(TrajOut), _vp]),
+    'egp_gae_work_bytes': (_i64, [_i64]),
+    'egp_gae_f64': (_int, [_vp, _vp, _vp, _d, _d, _i64, _vp, _vp, _vp, _vp, _vp]),
+    'egp_standardize_f64': (_int, [_vp, _i64, _vp, _vp]),
+    'egp_gauss_logp_f64': (_int, [_vp, _vp, _vp, _i64, _int, _vp, _vp]),
+    'egp_ppo_loss_grad_f64': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _i64, _int, _vp, _vp, _vp, _vp]),
+    'egp_value_loss_grad_f64': (_int, [_vp, _vp, _d, _i64, _vp, _vp, _vp]),
+    'egp_bias_relu_f64': (_int, [_vp, _vp, _i64, _int, _vp]),
+    'egp_relu_bwd_f64': (_int, [_vp, _vp, _i64, _int, _vp]),
+    'egp_colsum_f64': (_int, [_vp, _i64, _int, _vp, _vp]),
+    'egp_col_moments_f64': (_int, [_vp, _i64, _int, _vp, _vp, _vp]),
+    'egp_build_input_f64': (_int, [_vp, _vp, _vp, _vp, _i64, _int, _vp, _vp]),
+    'egp_sumsq_f64': (_int, [_vp, _i64, _vp, _vp]),
+    'egp_adam_step_f64': (_int, [_vp, _vp, _vp, _vp, _i64, _d, _d, _d, _d, _i64, _d, _vp, _vp]),
+}
+
+_lib = None
+launches = 0        # kernels launched through this binding (bench.py's gpu_launches)
+
+
+def load():
+    """Load the C-ABI library; raises EgpError when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise EgpError('libegopose_b200.so is missing - run `python -m egopose_b200.build` '
+                           '(there is no CPU fallback)')
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc, what=''):
+    if rc != 0:
+        raise EgpError('%s failed (%d): %s' % (what, rc, load().egp_last_error_string().decode()))
+
+
+def ptr(t):
+    """device pointer of a torch tensor (or None)"""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise EgpError('expected a CUDA tensor (no CPU fallback)')
+    if not t.is_contiguous():
+        raise EgpError('expected a contiguous tensor')
+    return C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _np_d(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _np_i(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def reward_weights(ws):
+    """defaults of ego_pose/core/reward_function.py:8-12"""
+    ws = ws or {}
+    out = {}
+    for name, dv in (('w_p', 0.5), ('w_v', 0.1), ('w_e', 0.2), ('w_rp', 0.1), ('w_rv', 0.1), ('k_p', 2), ('k_v', 0.005),
+                     ('k_e', 20), ('k_rh', 300), ('k_rq', 300), ('k_rl', 5.0), ('k_ra', 0.5)):
+        out[name] = float(ws.get(name, dv))
+    out['v_ord'] = int(ws.get('v_ord', 2))
+    out['decay'] = int(bool(ws.get('decay', False)))
+    return out
+
+
+class Model:
+    """Owns an EgpModel handle: compiled MJCF constants + cfg constants + expert tables on one device."""
+
+    def __init__(self, md, jkp, jkd, a_ref, a_scale, torque_lim, b_diffw, reward_ws=None, frame_skip=15, device=0):
+        import torch
+        if not torch.cuda.is_available():
+            raise EgpError('a CUDA device is required (no CPU fallback)')
+        self.lib = load()
+        self.md = md
+        self.device = int(device)
+        self.nq, self.nv, self.nu, self.nbody = md.nq, md.nv, md.nu, md.nbody
+        self.S = self.nq - 2 + self.nv
+        self.dt = md.timestep * frame_skip
+        keep = self._keep = {}
+        d = ModelDesc()
+        d.nq, d.nv, d.nu, d.nbody, d.timestep = md.nq, md.nv, md.nu, md.nbody, md.timestep
+        d.gravity[:] = md.gravity
+        for name in ('body_parent', 'body_dofadr', 'body_dofnum', 'body_qposadr', 'dof_body', 'dof_parent'):
+            keep[name] = _np_i(getattr(md, name))
+            setattr(d, name, keep[name].ctypes.data_as(_ip))
+        for name in ('body_pos', 'body_mass', 'body_ipos', 'body_inertia', 'dof_armature', 'dof_axis', 'dof_anchor'):
+            keep[name] = _np_d(getattr(md, name))
+            setattr(d, name, keep[name].ctypes.data_as(_dp))
+        d.ee_body[:] = [md.body_names.index(n) for n in EE_NAMES]
+        d.head_body = md.body_names.index('Head')
+        d.frame_skip = frame_skip
+        for name, val in (('jkp', jkp), ('jkd', jkd), ('a_ref', a_ref), ('a_scale', a_scale), ('torque_lim', torque_lim),
+                          ('b_diffw', b_diffw)):
+            keep[name] = _np_d(val)
+            setattr(d, name, keep[name].ctypes.data_as(_dp))
+        for k, v in reward_weights(reward_ws).items():
+            setattr(d, k, v)
+        self.desc = d
+        h = _vp()
+        torch.cuda.set_device(self.device)
+        check(self.lib.egp_model_create(C.byref(d), self.device, C.byref(h)), 'egp_model_create')
+        self.handle = h
+        self.n_takes = 0
+        self.ctx_dim = 0
+        self.take_off = None
+        self.head_lb = None
+
+    @classmethod
+    def from_cfg_dict(cls, md, cfg, device=0):
+        """cfg: the yml dict of config/egomimic/*.yml (egomimic_config.py:105-122 semantics)"""
+        jp = list(zip(*cfg['joint_params']))
+        mult = cfg.get('jkp_multiplier', 1.0)
+        jkp = np.array(jp[1], dtype=np.float64) * mult
+        jkd = np.array(jp[2], dtype=np.float64) * cfg.get('jkd_multiplier', mult)
+        a_ref = np.deg2rad(np.array(jp[3], dtype=np.float64))
+        b_diffw = np.array(list(zip(*cfg['body_params']))[1], dtype=np.float64)
+        return cls(md, jkp, jkd, a_ref, np.array(jp[4], dtype=np.float64), np.array(jp[5], dtype=np.float64), b_diffw,
+                   cfg.get('reward_weights'), device=device)
+
+    def close(self):
+        if getattr(self, 'handle', None):
+            self.lib.egp_model_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- expert tables ---------------------------------------------------------------------
+    def upload_experts(self, rows, take_off, head_lb, ctx=None):
+        rows, take_off, head_lb = _np_d(rows), _np_i(take_off), _np_d(head_lb)
+        if rows.shape != (take_off[-1], X['STRIDE']):
+            raise EgpError('expert rows must be [total_frames, %d]' % X['STRIDE'])
+        cp, cd = None, 0
+        if ctx is not None:
+            ctx = _np_d(ctx)
+            cp, cd = ctx.ctypes.data_as(_dp), ctx.shape[1]
+        check(self.lib.egp_expert_upload(self.handle, len(head_lb), take_off.ctypes.data_as(_ip),
+                                         rows.ctypes.data_as(_dp), head_lb.ctypes.data_as(_dp), cp, cd),
+              'egp_expert_upload')
+        self.n_takes, self.ctx_dim, self.take_off, self.head_lb = len(head_lb), cd, take_off, head_lb
+
+    def expert_features(self, qpos):
+        """gen_expert.get_expert for one take on the GPU: qpos [L, nq] -> (rows [L, 292] tensor, head_height_lb)"""
+        global launches
+        import torch
+        q = torch.as_tensor(np.ascontiguousarray(qpos), dtype=torch.float64, device='cuda:%d' % self.device)
+        L = q.shape[0]
+        rows = torch.empty((L, X['STRIDE']), dtype=torch.float64, device=q.device)
+        hz = torch.empty(L, dtype=torch.float64, device=q.device)
+        check(self.lib.egp_expert_features_f64(self.handle, L, ptr(q), ptr(rows), ptr(hz), stream_ptr()),
+              'egp_expert_features_f64')
+        launches += 1
+        return rows, float(hz.min().item())
+
+    # ---- debug / parity -----------------------------------------------------------------------
+    def forward_debug(self, qpos, qvel, ctrl=None):
+        global launches
+        import torch
+        n = qpos.shape[0]
+        bias = torch.empty((n, self.nv), dtype=torch.float64, device=qpos.device)
+        xpos = torch.empty((n, self.nbody, 3), dtype=torch.float64, device=qpos.device)
+        qacc = torch.empty((n, self.nv), dtype=torch.float64, device=qpos.device)
+        check(self.lib.egp_forward_debug_f64(self.handle, n, ptr(qpos), ptr(qvel), ptr(ctrl), ptr(bias), ptr(xpos),
+                                             ptr(qacc), stream_ptr()), 'egp_forward_debug_f64')
+        launches += 1
+        return bias, xpos, qacc
+
+    def env_step_debug(self, qpos, qvel, action):
+        """in-place env.step on freshly reset states; returns (obs, head_z, torque of sub-step 0)"""
+        global launches
+        import torch
+        n = qpos.shape[0]
+        obs = torch.empty((n, self.S), dtype=torch.float64, device=qpos.device)
+        hz = torch.empty(n, dtype=torch.float64, device=qpos.device)
+        tq = torch.empty((n, self.nu), dtype=torch.float64, device=qpos.device)
+        check(self.lib.egp_env_step_debug_f64(self.handle, n, ptr(qpos), ptr(qvel), ptr(action), ptr(obs), ptr(hz),
+                                              ptr(tq), stream_ptr()), 'egp_env_step_debug_f64')
+        launches += 1
+        return obs, hz, tq
+
+    # ---- rollout ------------------------------------------------------------------------------
+    def rollout(self, weights, n_env, horizon, episode_len, fr_margin=10, end_reward=0.0, fix_head_lb=None,
+                noise_rate=1.0, mean_action=False, zf_mean=None, zf_std=None, zf_clip=5.0, seed=1, iteration=0,
+                eps=None, reset_take=None, reset_start=None, mean_flag=None, want_next=True, want_raw=True, out=None):
+        """weights: dict with W1,b1,W2,b2,W3,b3,log_std CUDA float64 tensors (torch [out,in] layout).
+        Returns a dict of CUDA tensors in TrajBatchEgo layout (+ logger, c_info, raw_obs, final state)."""
+        global launches
+        import torch
+        dev = weights['W1'].device
+        N, S, nu = n_env * horizon, self.S, self.nu
+        f64 = dict(dtype=torch.float64, device=dev)
+        if out is None:
+            out = {}
+        def buf(name, shape, dtype=torch.float64):
+            t = out.get(name)
+            if t is None or tuple(t.shape) != tuple(shape):
+                t = torch.empty(shape, dtype=dtype, device=dev)
+                out[name] = t
+            return t
+        o = TrajOut()
+        o.d_states = ptr(buf('states', (N, S)))
+        o.d_actions = ptr(buf('actions', (N, nu)))
+        o.d_masks = ptr(buf('masks', (N,)))
+        o.d_next_states = ptr(buf('next_states', (N, S))) if want_next else None
+        o.d_rewards = ptr(buf('rewards', (N,)))
+        o.d_exps = ptr(buf('exps', (N,)))
+        o.d_v_metas = ptr(buf('v_metas', (N, 2), torch.int32))
+        o.d_c_info = ptr(buf('c_info', (N, 5)))
+        o.d_raw_obs = ptr(buf('raw_obs', (N, S))) if want_raw else None
+        o.d_final_qpos = ptr(buf('final_qpos', (n_env, self.nq)))
+        o.d_final_qvel = ptr(buf('final_qvel', (n_env, self.nv)))
+        o.d_logger = ptr(buf('logger', (LOG['SIZE'],)))
+        cfg = RolloutCfg()
+        cfg.n_env, cfg.horizon, cfg.episode_len, cfg.fr_margin = n_env, horizon, episode_len, fr_margin
+        cfg.end_reward = float(end_reward)
+        cfg.fix_head_lb = float('nan') if fix_head_lb is None else float(fix_head_lb)
+        cfg.noise_rate, cfg.mean_action, cfg.zf_clip = float(noise_rate), int(bool(mean_action)), float(zf_clip)
+        cfg.seed, cfg.iteration = int(seed), int(iteration)
+        cfg.max_resets = int(reset_take.shape[1]) if reset_take is not None else 0
+        inp = RolloutIn()
+        inp.d_eps, inp.d_reset_take, inp.d_reset_start = ptr(eps), ptr(reset_take), ptr(reset_start)
+        inp.d_mean_flag, inp.d_zf_mean, inp.d_zf_std = ptr(mean_flag), ptr(zf_mean), ptr(zf_std)
+        pw = PolicyWeights()
+        pw.in_dim, pw.h1 = weights['W1'].shape[1], weights['W1'].shape[0]
+        pw.h2, pw.out_dim = weights['W2'].shape[0], weights['W3'].shape[0]
+        pw.d_W1, pw.d_b1, pw.d_W2, pw.d_b2 = ptr(weights['W1']), ptr(weights['b1']), ptr(weights['W2']), ptr(weights['b2'])
+        pw.d_W3, pw.d_b3, pw.d_log_std = ptr(weights['W3']), ptr(weights['b3']), ptr(weights['log_std'])
+        check(self.lib.egp_rollout_f64(self.handle, C.byref(pw), C.byref(cfg), C.byref(inp), C.byref(o), stream_ptr()),
+              'egp_rollout_f64')
+        launches += 4
+        return out
+
+    def build_input(self, states, v_metas, masks, horizon):
+        global launches
+        import torch
+        n = states.shape[0]
+        x = torch.empty((n, self.ctx_dim + self.S), dtype=torch.float64, device=states.device)
+        check(self.lib.egp_build_input_f64(self.handle, ptr(states), ptr(v_metas), ptr(masks), n, horizon, ptr(x),
+                                           stream_ptr()), 'egp_build_input_f64')
+        launches += 1
+        return x
+
+
+# ---- update-phase kernels (thin wrappers; all tensors CUDA float64 contiguous) ------------------
+def gae(rewards, masks, values, gamma, tau, work=None):
+    """K4 (core/common.py:5-21): returns (adv_raw, returns, stats[3] = n, mean, M2)"""
+    global launches
+    import torch
+    lib = load()
+    n = rewards.numel()
+    adv = torch.empty(n, dtype=torch.float64, device=rewards.device)
+    ret = torch.empty(n, dtype=torch.float64, device=rewards.device)
+    stats = torch.empty(3, dtype=torch.float64, device=rewards.device)
+    nbytes = lib.egp_gae_work_bytes(n)
+    if work is None or work.numel() < nbytes:
+        work = torch.empty(nbytes, dtype=torch.uint8, device=rewards.device)
+    check(lib.egp_gae_f64(ptr(rewards), ptr(masks), ptr(values), gamma, tau, n, ptr(adv), ptr(ret), ptr(stats),
+                          ptr(work), stream_ptr()), 'egp_gae_f64')
+    launches += 1
+    return adv, ret, stats
+
+
+def standardize_(x, stats):
+    global launches
+    check(load().egp_standardize_f64(ptr(x), x.numel(), ptr(stats), stream_ptr()), 'egp_standardize_f64')
+    launches += 1
+    return x
+
+
+def gauss_logp(mu, actions, log_std, out=None):
+    global launches
+    import torch
+    n, a = mu.shape
+    if out is None:
+        out = torch.empty(n, dtype=torch.float64, device=mu.device)
+    check(load().egp_gauss_logp_f64(ptr(mu), ptr(actions), ptr(log_std), n, a, ptr(out), stream_ptr()),
+          'egp_gauss_logp_f64')
+    launches += 1
+    return out
+
+
+def ppo_loss_grad(mu, actions, log_std, adv, stats, logp0, exps, clip_eps, inv_count, dmu, dlogstd, loss):
+    global launches
+    n, a = mu.shape
+    check(load().egp_ppo_loss_grad_f64(ptr(mu), ptr(actions), ptr(log_std), ptr(adv), ptr(stats), ptr(logp0), ptr(exps),
+                                       clip_eps, inv_count, n, a, ptr(dmu), ptr(dlogstd), ptr(loss), stream_ptr()),
+          'egp_ppo_loss_grad_f64')
+    launches += 1
+
+
+def value_loss_grad(v, ret, inv_n, dv, loss):
+    global launches
+    check(load().egp_value_loss_grad_f64(ptr(v), ptr(ret), inv_n, v.numel(), ptr(dv), ptr(loss), stream_ptr()),
+          'egp_value_loss_grad_f64')
+    launches += 1
+
+
+def bias_relu_(y, b):
+    global launches
+    check(load().egp_bias_relu_f64(ptr(y), ptr(b), y.shape[0], y.shape[1], stream_ptr()), 'egp_bias_relu_f64')
+    launches += 1
+    return y
+
+
+def relu_bwd_(dy, y):
+    global launches
+    check(load().egp_relu_bwd_f64(ptr(dy), ptr(y), y.shape[0], y.shape[1], stream_ptr()), 'egp_relu_bwd_f64')
+    launches += 1
+    return dy
+
+
+def colsum(x, out):
+    global launches
+    check(load().egp_colsum_f64(ptr(x), x.shape[0], x.shape[1], ptr(out), stream_ptr()), 'egp_colsum_f64')
+    launches += 1
+    return out
+
+
+def col_moments(x, shift=None):
+    global launches
+    import torch
+    out = torch.empty(2 * x.shape[1], dtype=torch.float64, device=x.device)
+    check(load().egp_col_moments_f64(ptr(x), x.shape[0], x.shape[1], ptr(shift), ptr(out), stream_ptr()),
+          'egp_col_moments_f64')
+    launches += 1
+    return out
+
+
+def sumsq(g, out):
+    global launches
+    check(load().egp_sumsq_f64(ptr(g), g.numel(), ptr(out), stream_ptr()), 'egp_sumsq_f64')
+    launches += 1
+    return out
+
+
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, max_norm=0.0, norm2=None):
+    global launches
+    check(load().egp_adam_step_f64(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), lr, beta1, beta2, eps, step,
+                                   float(max_norm or 0.0), ptr(norm2), stream_ptr()), 'egp_adam_step_f64')
+    launches += 1

@@ -1,0 +1,215 @@
+/* egopose_b200 C ABI - the drop-in boundary of the B200-native PPO rollout-and-update hot path.
+ *
+ * The reference (Khrylx/EgoPose, pure Python) has no FFI of its own; its native seams on this path
+ * are the third-party C ABIs it reaches through mujoco_py / scipy / torch:
+ *   mj_step / mj_forward / mj_fullM    envs/common/mujoco_env.py:22-23,100-101, ego_pose/envs/humanoid_v1.py:134,174
+ *   LAPACK dpotrf/dpotrs               ego_pose/envs/humanoid_v1.py:143 (scipy cho_factor/cho_solve)
+ *   ATen addmm/relu/normal_            agents/agent.py:44-47 (policy forward + Gaussian sample, batch 1)
+ *   python GAE loop                    core/common.py:5-25
+ *   autograd + torch.optim.Adam        agents/agent_pg.py:19-26, agents/agent_ppo.py:44-65
+ * Each entry point below names the reference code it replaces.  The Python host mirror of the
+ * Agent/Policy/Value/TrajBatch API (egopose_b200/) binds these with ctypes; INTEGRATION.md shows the
+ * stub a maintainer of the reference would add.
+ *
+ * Conventions:
+ *   - every pointer argument named d_* is a CUDA device pointer owned by the caller; the library
+ *     allocates only inside *_create / *_upload and frees only in *_destroy
+ *   - all compute entry points are asynchronous on `stream` (a cudaStream_t passed as void*)
+ *   - return 0 on success, negative EGP_E* on failure; egp_last_error_string() describes the last
+ *     failure of the calling thread; nothing throws or aborts across the boundary
+ *   - arithmetic is float64 ("_f64"), the reference dtype (ego_pose/ego_mimic.py:31-32)
+ */
+#ifndef EGOPOSE_B200_H
+#define EGOPOSE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EGP_OK 0
+#define EGP_EINVAL (-1)
+#define EGP_ECUDA (-2)
+#define EGP_ENOMEM (-3)
+#define EGP_ESIZE (-4)
+
+#define EGP_MAX_BODY 24
+#define EGP_MAX_DOF 64
+#define EGP_MAX_CHAIN 12
+#define EGP_NEE 5
+
+/* packed expert row, in doubles (derived from the dict written by ego_pose/data_process/gen_expert.py:28-83) */
+#define EGP_X_QPOS 0
+#define EGP_X_QVEL 59
+#define EGP_X_RLINV_LOCAL 117
+#define EGP_X_RANGV 120
+#define EGP_X_RQ_RMH 123
+#define EGP_X_EE_POS 127
+#define EGP_X_BQUAT 142
+#define EGP_X_BANGVEL 226
+#define EGP_X_STRIDE 292
+
+typedef struct EgpModel EgpModel;       /* opaque: model + PD/reward constants + expert tables on one device */
+
+/* What mujoco_py.load_model_from_path gives the reference (envs/common/mujoco_env.py:22) plus the cfg
+ * constants of ego_pose/utils/egomimic_config.py:94-122.  Host pointers, copied during create. */
+typedef struct {
+    int32_t nq, nv, nu, nbody;
+    double timestep;
+    double gravity[3];
+    const int32_t *body_parent, *body_dofadr, *body_dofnum, *body_qposadr;      /* [nbody] */
+    const double *body_pos, *body_mass, *body_ipos, *body_inertia;              /* [nbody][3],[nbody],[nbody][3],[nbody][6] */
+    const int32_t *dof_body, *dof_parent;                                      /* [nv] */
+    const double *dof_armature, *dof_axis, *dof_anchor;                        /* [nv],[nv][3],[nv][3] */
+    int32_t ee_body[EGP_NEE];           /* LeftFoot RightFoot LeftHand RightHand Head (humanoid_v1.py:100) */
+    int32_t head_body;
+    /* cfg */
+    int32_t frame_skip;                 /* 15, humanoid_v1.py:16 */
+    const double *jkp, *jkd, *a_ref, *a_scale, *torque_lim;                    /* [nu] */
+    const double *b_diffw;                                                     /* [nbody-1] */
+    double w_p, w_v, w_e, w_rp, w_rv, k_p, k_v, k_e, k_rh, k_rq, k_rl, k_ra;   /* reward_function.py:8-12 */
+    int32_t v_ord, decay;
+} EgpModelDesc;
+
+/* Per-rollout settings (the mutable parts of HumanoidEnv / Agent state). */
+typedef struct {
+    int32_t n_env, horizon;             /* E environments x T recorded steps each, rows n = e*T + t */
+    int32_t episode_len;                /* cfg.env_episode_len, humanoid_v1.py:197 */
+    int32_t fr_margin;                  /* cfg.fr_margin, humanoid_v1.py:214 */
+    double end_reward;                  /* env.end_reward, ego_mimic.py:112 */
+    double fix_head_lb;                 /* NaN: expert head_height_lb - 0.1 (humanoid_v1.py:193-196) */
+    double noise_rate;                  /* Agent.noise_rate, agents/agent.py:46 */
+    int32_t mean_action;                /* Agent.mean_action */
+    double zf_clip;                     /* ZFilter clip (5), <=0 disables; stats frozen during a rollout */
+    uint64_t seed;                      /* Philox key for perf-mode noise / reset draws */
+    uint64_t iteration;                 /* Philox stream offset so successive rollouts differ */
+    int32_t max_resets;                 /* parity mode: columns of d_reset_take/start */
+} EgpRolloutCfg;
+
+/* PolicyGaussian(MLP) weights on the device, torch nn.Linear layout [out][in] (core/policy_gaussian.py:8-24,
+ * models/mlp.py:5-25); two hidden relu layers. */
+typedef struct {
+    int32_t in_dim, h1, h2, out_dim;
+    const double *d_W1, *d_b1, *d_W2, *d_b2, *d_W3, *d_b3, *d_log_std;
+} EgpPolicyWeights;
+
+/* Optional inputs; NULL selects the in-kernel Philox path. */
+typedef struct {
+    const double *d_eps;                /* [E*T][nu] standard-normal noise (parity mode) */
+    const int32_t *d_reset_take;        /* [E][max_resets] pre-drawn expert_ind (humanoid_v1.py:210) */
+    const int32_t *d_reset_start;       /* [E][max_resets] pre-drawn start_ind (humanoid_v1.py:214) */
+    const uint8_t *d_mean_flag;         /* [E*T] 1 = mean action this step (agents/agent.py:46) */
+    const double *d_zf_mean, *d_zf_std; /* [S] frozen ZFilter statistics or NULL (identity) */
+} EgpRolloutIn;
+
+/* TrajBatchEgo layout (core/trajbatch.py:6-16, ego_pose/core/trajbatch_ego.py:7-9), all device, row-major. */
+typedef struct {
+    double *d_states;                   /* [N][S] */
+    double *d_actions;                  /* [N][nu] */
+    double *d_masks;                    /* [N] */
+    double *d_next_states;              /* [N][S] or NULL (never read by the update, agent_ego.py:37-42) */
+    double *d_rewards;                  /* [N] */
+    double *d_exps;                     /* [N] */
+    int32_t *d_v_metas;                 /* [N][2] (expert_ind, start_ind) */
+    double *d_c_info;                   /* [N][5] or NULL */
+    double *d_raw_obs;                  /* [N][S] unfiltered observations or NULL */
+    double *d_final_qpos, *d_final_qvel;/* [E][nq], [E][nv] or NULL */
+    double *d_logger;                   /* [EGP_LOG_SIZE] reductions for core/logger_rl.py, or NULL */
+} EgpTrajOut;
+
+/* d_logger slots */
+#define EGP_LOG_NUM_STEPS 0
+#define EGP_LOG_NUM_EPISODES 1
+#define EGP_LOG_TOTAL_REWARD 2      /* env reward is the constant 1.0 -> episode lengths (humanoid_v1.py:192) */
+#define EGP_LOG_TOTAL_C_REWARD 3
+#define EGP_LOG_MIN_C_REWARD 4
+#define EGP_LOG_MAX_C_REWARD 5
+#define EGP_LOG_C_INFO 6            /* 5 slots */
+#define EGP_LOG_MIN_EPISODE_REWARD 11
+#define EGP_LOG_MAX_EPISODE_REWARD 12
+#define EGP_LOG_NUM_NAN_RESETS 13
+#define EGP_LOG_SIZE 16
+
+const char *egp_last_error_string(void);
+int egp_version(void);
+
+/* --- model / expert tables ------------------------------------------------------------------- */
+int egp_model_create(const EgpModelDesc *desc, int device, EgpModel **out);
+void egp_model_destroy(EgpModel *m);
+
+/* replaces HumanoidEnv.load_experts (humanoid_v1.py:45-54): packed rows [total_frames][EGP_X_STRIDE],
+ * take offsets [n_takes+1], per-take head_height_lb, optional per-frame context rows (host pointers) */
+int egp_expert_upload(EgpModel *m, int n_takes, const int32_t *take_off, const double *rows,
+                      const double *head_height_lb, const double *ctx, int ctx_dim);
+
+/* replaces ego_pose/data_process/gen_expert.py:28-83 for one take: d_qpos [L][nq] -> d_rows [L][EGP_X_STRIDE],
+ * d_head_z [L] (head height per frame; min over frames = head_height_lb) */
+int egp_expert_features_f64(EgpModel *m, int L, const double *d_qpos, double *d_rows, double *d_head_z,
+                            void *stream);
+
+/* --- physics, single calls (parity/debug; replaces sim.forward()/sim.step()/compute_torque) ---- */
+/* one mj_forward at (qpos, qvel, ctrl): qfrc_bias [n][nv], xpos [n][nbody][3], qacc = M^-1 (ctrl - bias) [n][nv]
+ * (d_ctrl [n][nu] may be NULL = zero actuation) */
+int egp_forward_debug_f64(EgpModel *m, int n, const double *d_qpos, const double *d_qvel, const double *d_ctrl,
+                          double *d_bias, double *d_xpos, double *d_qacc, void *stream);
+/* env.step(action) for n independent states that have just been reset-forwarded (humanoid_v1.py:158-199):
+ * d_qpos/d_qvel in-out [n][nq]/[n][nv]; d_action [n][nu]; outputs obs [n][S], head_z [n] (stale xpos) */
+int egp_env_step_debug_f64(EgpModel *m, int n, double *d_qpos, double *d_qvel, const double *d_action,
+                           double *d_obs, double *d_head_z, double *d_torque0, void *stream);
+
+/* --- fused rollout (K1+K2+K3): replaces Agent.sample / sample_worker (agents/agent.py:29-111) ---- */
+int egp_rollout_f64(EgpModel *m, const EgpPolicyWeights *pol, const EgpRolloutCfg *cfg, const EgpRolloutIn *in,
+                    const EgpTrajOut *out, void *stream);
+
+/* --- PPO update kernels ---------------------------------------------------------------------- */
+/* K4: core/common.py:5-21 estimate_advantages reverse scan over the flat batch.  d_adv gets the
+ * UN-normalised advantages, d_ret = values + adv, d_stats[0..2] = (n, mean, M2) of adv so that
+ * (adv - mean) / sqrt(M2 / (n - 1)) is the reference's standardisation (:22).
+ * d_work: egp_gae_work_bytes(n) bytes of scratch. */
+int64_t egp_gae_work_bytes(int64_t n);
+int egp_gae_f64(const double *d_rewards, const double *d_masks, const double *d_values, double gamma, double tau,
+                int64_t n, double *d_adv, double *d_ret, double *d_stats, void *d_work, void *stream);
+/* (x - stats.mean) / std in place (materialises the reference's normalised advantages) */
+int egp_standardize_f64(double *d_x, int64_t n, const double *d_stats, void *stream);
+
+/* core/distributions.py:21-22: logp[n] = sum_j log N(a | mu, exp(log_std)) */
+int egp_gauss_logp_f64(const double *d_mu, const double *d_actions, const double *d_log_std, int64_t n, int adim,
+                       double *d_logp, void *stream);
+
+/* K5: agents/agent_ppo.py:58-65 ppo_loss forward + backward wrt mu (and log_std) in one pass.
+ * d_stats as written by egp_gae (advantages are standardised on the fly); inv_count = 1 / #(exps != 0)
+ * over the GLOBAL batch.  d_dmu [n][adim] = dL/dmu; d_dlogstd [adim] (may be NULL) and d_loss[0] are
+ * ACCUMULATED with atomics - zero them first. */
+int egp_ppo_loss_grad_f64(const double *d_mu, const double *d_actions, const double *d_log_std,
+                          const double *d_adv, const double *d_stats, const double *d_logp0, const double *d_exps,
+                          double clip_eps, double inv_count, int64_t n, int adim, double *d_dmu, double *d_dlogstd,
+                          double *d_loss, void *stream);
+
+/* agents/agent_pg.py:22-23: L = mean((V - R)^2); d_dv = 2 (V - R) * inv_n ; d_loss[0] accumulated */
+int egp_value_loss_grad_f64(const double *d_v, const double *d_ret, double inv_n, int64_t n, double *d_dv,
+                            double *d_loss, void *stream);
+
+/* fused bias + relu forward: y = relu(y + b) in place, y [n][dim]; and backward mask dy *= (y > 0) */
+int egp_bias_relu_f64(double *d_y, const double *d_b, int64_t n, int dim, void *stream);
+int egp_relu_bwd_f64(double *d_dy, const double *d_y, int64_t n, int dim, void *stream);
+/* column sums (bias gradients): out[dim] = sum_n x[n][dim] */
+int egp_colsum_f64(const double *d_x, int64_t n, int dim, double *d_out, void *stream);
+/* shifted column moments for the batched ZFilter update (utils/zfilter.py:18-27 merged per rollout):
+ * out[0..dim) = sum_n (x - shift), out[dim..2dim) = sum_n (x - shift)^2 ; d_shift [dim] may be NULL (0) */
+int egp_col_moments_f64(const double *d_x, int64_t n, int dim, const double *d_shift, double *d_out, void *stream);
+/* x[n][S] with per-row context gather: out[n][ctx_dim + S] = cat(ctx[frame(n)], states[n])
+ * (models/video_state_net.py:62-64 'cat(v_out[t], state)'); frame(n) = take_off[v_meta[n][0]] + v_meta[n][1] + t(n) */
+int egp_build_input_f64(EgpModel *m, const double *d_states, const int32_t *d_v_metas, const double *d_masks,
+                        int64_t n, int horizon, double *d_x, void *stream);
+
+/* K6: torch.nn.utils.clip_grad_norm_ (agents/agent_ppo.py:53-56) + torch.optim.Adam step
+ * (ego_pose/ego_mimic.py:70-77) over one flat parameter buffer.  d_norm2: 1 double of scratch. */
+int egp_sumsq_f64(const double *d_g, int64_t n, double *d_norm2, void *stream);
+int egp_adam_step_f64(double *d_p, const double *d_g, double *d_m, double *d_v, int64_t n, double lr, double beta1,
+                      double beta2, double eps, int64_t step, double max_norm, const double *d_norm2, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,133 @@
+"""CUDA update kernels (through the C ABI) vs the CPU oracle and the reference-generated golden fixture.
+Tolerances: float64 arithmetic on both sides; the north-star bound is 1e-5 on the PPO loss."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip('torch')
+
+from oracle import ppo as oppo  # noqa: E402
+import helpers  # noqa: E402
+
+
+def cu(a):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device='cuda')
+
+
+@pytest.mark.parametrize('n', [1, 5, 1023, 1024, 1025, 4096 * 3 + 17, 300 * 700])
+def test_gae_vs_oracle(n):
+    from egopose_b200 import lib
+    rng = np.random.RandomState(n)
+    r, v = rng.rand(n), rng.randn(n)
+    m = (rng.rand(n) > 0.02).astype(np.float64)
+    if n > 300:
+        m[299::300] = 0.0
+    m[-1] = 0.0
+    adv, ret, stats = lib.gae(cu(r), cu(m), cu(v), 0.95, 0.95)
+    if n > 1:
+        adv_n, ret_o = oppo.gae(r, m, v, 0.95, 0.95)
+        got = lib.standardize_(adv.clone(), stats).cpu().numpy()
+        assert np.allclose(got, adv_n, rtol=1e-10, atol=1e-11)
+        assert np.allclose(ret.cpu().numpy(), ret_o, rtol=1e-12, atol=1e-12)
+    else:
+        assert abs(adv.item() - (r[0] - v[0])) < 1e-14
+
+
+def test_gae_no_episode_boundaries_long_chain():
+    """masks all one: the look-back must chain through every tile (no early exit)."""
+    from egopose_b200 import lib
+    n = 1024 * 40 + 3
+    rng = np.random.RandomState(0)
+    r, v, m = rng.rand(n), rng.randn(n), np.ones(n)
+    adv, ret, stats = lib.gae(cu(r), cu(m), cu(v), 0.99, 0.97)
+    adv_n, ret_o = oppo.gae(r, m, v, 0.99, 0.97)
+    assert np.allclose(ret.cpu().numpy(), ret_o, rtol=1e-11, atol=1e-11)
+    assert np.allclose(lib.standardize_(adv, stats).cpu().numpy(), adv_n, rtol=1e-9, atol=1e-10)
+
+
+def test_gae_golden(golden):
+    from egopose_b200 import lib
+    g = golden('ppo_small')
+    adv, ret, stats = lib.gae(cu(g['rewards']), cu(g['masks']), cu(g['values0'].ravel()), 0.95, 0.95)
+    assert np.allclose(ret.cpu().numpy(), g['returns'].ravel(), rtol=1e-12, atol=1e-12)
+    assert np.allclose(lib.standardize_(adv, stats).cpu().numpy(), g['advantages'].ravel(), rtol=1e-10, atol=1e-11)
+
+
+def test_logp_and_loss_golden(golden):
+    """fixed log-probs, surrogate loss and its gradient wrt mu vs torch autograd of the reference formula."""
+    from egopose_b200 import lib
+    g = golden('ppo_small')
+    pol = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith('p0.')}
+    st, ac = torch.from_numpy(g['states']), torch.from_numpy(g['actions'])
+    mu = oppo.policy_mean(st, pol)
+    ls = pol['action_log_std']
+    logp0 = lib.gauss_logp(cu(mu.numpy()), cu(g['actions']), cu(ls.numpy().ravel()))
+    assert np.allclose(logp0.cpu().numpy(), g['fixed_log_probs'].ravel(), rtol=1e-12, atol=1e-12)
+    # perturbed mu so that ratios leave the clip range on both sides
+    rng = np.random.RandomState(4)
+    mu2 = (mu + 0.03 * torch.from_numpy(rng.randn(*mu.shape))).requires_grad_(True)
+    ls2 = ls.clone().requires_grad_(True)
+    adv_raw, ret, stats = lib.gae(cu(g['rewards']), cu(g['masks']), cu(g['values0'].ravel()), 0.95, 0.95)
+    adv = torch.from_numpy(g['advantages'])
+    ind = torch.from_numpy(g['exps']).nonzero().squeeze(1)
+    lp = oppo.log_prob(mu2[ind], ls2, ac[ind])
+    ratio = torch.exp(lp - torch.from_numpy(g['fixed_log_probs'])[ind])
+    a = adv[ind]
+    assert ((ratio < 0.8).sum() > 5) and ((ratio > 1.2).sum() > 5)
+    surr = -torch.min(ratio * a, torch.clamp(ratio, 0.8, 1.2) * a).mean()
+    surr.backward()
+    dmu = torch.zeros_like(cu(g['actions']))
+    dls = torch.zeros(mu.shape[1], dtype=torch.float64, device='cuda')
+    loss = torch.zeros(1, dtype=torch.float64, device='cuda')
+    lib.ppo_loss_grad(cu(mu2.detach().numpy()), cu(g['actions']), cu(ls.numpy().ravel()), adv_raw, stats, logp0,
+                      cu(g['exps']), 0.2, 1.0 / len(ind), dmu, dls, loss)
+    assert abs(loss.item() - surr.item()) < 1e-12 * max(1, abs(surr.item())) + 1e-13
+    assert np.allclose(dmu.cpu().numpy(), mu2.grad.numpy(), rtol=1e-9, atol=1e-13)
+    assert np.allclose(dls.cpu().numpy(), ls2.grad.numpy().ravel(), rtol=1e-9, atol=1e-12)
+
+
+def test_value_loss_and_helpers():
+    from egopose_b200 import lib
+    rng = np.random.RandomState(2)
+    n = 5000
+    v, r = rng.randn(n), rng.randn(n)
+    dv = torch.empty(n, dtype=torch.float64, device='cuda')
+    loss = torch.zeros(1, dtype=torch.float64, device='cuda')
+    lib.value_loss_grad(cu(v), cu(r), 1.0 / n, dv, loss)
+    assert abs(loss.item() - np.mean((v - r) ** 2)) < 1e-12
+    assert np.allclose(dv.cpu().numpy(), 2 * (v - r) / n, rtol=1e-14)
+    y, b = rng.randn(777, 300), rng.randn(300)
+    yy = lib.bias_relu_(cu(y), cu(b))
+    ref = np.maximum(y + b, 0)
+    assert np.array_equal(yy.cpu().numpy(), ref)
+    dy = rng.randn(777, 300)
+    assert np.array_equal(lib.relu_bwd_(cu(dy), yy).cpu().numpy(), dy * (ref > 0))
+    cs = lib.colsum(cu(dy), torch.empty(300, dtype=torch.float64, device='cuda'))
+    assert np.allclose(cs.cpu().numpy(), dy.sum(0), rtol=1e-12, atol=1e-12)
+    sh = rng.randn(300)
+    mo = lib.col_moments(cu(y), cu(sh)).cpu().numpy()
+    assert np.allclose(mo[:300], (y - sh).sum(0), rtol=1e-12, atol=1e-11)
+    assert np.allclose(mo[300:], ((y - sh) ** 2).sum(0), rtol=1e-12)
+
+
+def test_clip_adam_vs_torch():
+    from egopose_b200 import lib
+    rng = np.random.RandomState(3)
+    n = 143904
+    p0 = rng.randn(n) * 0.1
+    for max_norm in (0.0, 40.0, 0.5):
+        p_ref = torch.nn.Parameter(torch.from_numpy(p0.copy()))
+        opt = torch.optim.Adam([p_ref], lr=5e-5)
+        p, m, v = cu(p0), cu(np.zeros(n)), cu(np.zeros(n))
+        nrm = torch.zeros(1, dtype=torch.float64, device='cuda')
+        for step in range(1, 4):
+            g = rng.randn(n) * 0.01 * step
+            p_ref.grad = torch.from_numpy(g.copy())
+            if max_norm > 0:
+                torch.nn.utils.clip_grad_norm_([p_ref], max_norm)
+            opt.step()
+            gg = cu(g)
+            lib.sumsq(gg, nrm)
+            assert abs(nrm.item() - (g ** 2).sum()) < 1e-12 * (g ** 2).sum()
+            lib.adam_step(p, gg, m, v, 5e-5, 0.9, 0.999, 1e-8, step, max_norm, nrm)
+        assert np.allclose(p.cpu().numpy(), p_ref.detach().numpy(), rtol=1e-12, atol=1e-14)
