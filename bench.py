@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""Headline benchmark: env-steps/sec of one full PPO iteration (fused humanoid rollout + PPO update).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  torchrun ... bench.py --gpus N ...        (one rank per GPU, NCCL; environments sharded, weak scaling)
+
+A "step" = one PPO iteration on the BASELINE.json configs[1] workload: subject_03 egomimic humanoid
+(nq 59 / nv 58 / nu 52), E = 4096 environments x T = 300 steps per GPU, policy / value MLP 243 -> 300 ->
+300 -> 52 | 1 (relu), 10 full-batch PPO epochs, float64 like the reference; synthetic experts and CNN
+features (the dataset is not redistributable), random-init weights.
+`value`  = E*T*N / (device time of rollout + update), inputs resident in HBM.
+`e2e`    = same metric through the reference-facing Python API with HOST trajbatches: agent.sample()
+           returns numpy arrays (D2H inside the timed region), agent.update_params(host batch) uploads them.
+`--impl reference` times the CPU oracle port (C physics/rollout on all host cores + torch-CPU float64 PPO
+update, the reference's own libraries) on a bounded sample of the same workload; /root/reference is not
+needed at run time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+WORKLOAD = 'subject_03 egomimic humanoid PPO iteration: 4096 envs x 300 steps per GPU, 2x300 MLP policy/value, 10 epochs'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--envs', type=int, default=4096)
+    ap.add_argument('--horizon', type=int, default=300)
+    ap.add_argument('--hidden', type=int, nargs=2, default=[300, 300])
+    ap.add_argument('--epochs', type=int, default=10)
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cpu-envs', type=int, default=0, help='envs in the CPU sample (0 = 2 per core)')
+    ap.add_argument('--cpu-horizon', type=int, default=20)
+    ap.add_argument('--cpu-update-rows', type=int, default=12288)
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get('hbm_gbs', 6650.0), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons during the timed region"""
+
+    Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '200'], stdout=subprocess.PIPE, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == 'Active' for r in self.rows)]
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': reasons, 'samples': len(sm)}
+
+
+def synthetic_problem(args, n_takes=8):
+    """seeded synthetic experts: smooth in-range trajectories, N(0,1) CNN features"""
+    from egopose_b200.mjcf import load_builtin
+    from egopose_b200.synthetic import synthetic_cnn_feat, synthetic_takes
+    md = load_builtin()
+    L = args.horizon + 2 * 10 + 64
+    return md, synthetic_takes(md, n_takes, L, seed=1), synthetic_cnn_feat(n_takes, L)
+
+
+def build_agent(args, device, takes, cnn):
+    import torch
+    from egopose_b200.agent import AgentEgo
+    from egopose_b200.config import Config
+    from egopose_b200.env import HumanoidEnv
+    from egopose_b200.nets import MLP, FrameContext, PolicyGaussian, Value
+    from egopose_b200.zfilter import ZFilter
+    torch.set_default_dtype(torch.float64)
+    torch.manual_seed(1)
+    cfg = Config('subject_03')
+    cfg.env_episode_len = args.horizon
+    env = HumanoidEnv(cfg, device=device.index)
+    env.seed(cfg.seed)
+    env.set_expert_qpos(['take_%d' % i for i in range(len(takes))], takes, cnn)
+    sd, ad = env.observation_space.shape[0], env.action_space.shape[0]
+    policy = PolicyGaussian(MLP(sd + 128, args.hidden, 'relu'), ad, log_std=cfg.log_std, fix_std=cfg.fix_std).to(device)
+    value = Value(MLP(sd + 128, args.hidden, 'relu')).to(device)
+    opt_p = torch.optim.Adam(policy.parameters(), lr=cfg.policy_lr)
+    opt_v = torch.optim.Adam(value.parameters(), lr=cfg.value_lr)
+    agent = AgentEgo(env=env, dtype=torch.float64, device=device, running_state=ZFilter((sd,), clip=5),
+                     custom_reward=None, num_threads=1, policy_net=policy, policy_vs_net=FrameContext(128),
+                     value_net=value, value_vs_net=FrameContext(128), optimizer_policy=opt_p, optimizer_value=opt_v,
+                     opt_num_epochs=args.epochs, gamma=cfg.gamma, tau=cfg.tau, clip_epsilon=cfg.clip_epsilon,
+                     policy_grad_clip=[(list(policy.parameters()), 40)], num_envs=args.envs, horizon=args.horizon)
+    return agent, cfg
+
+
+def cpu_reference(args, takes, cnn, hidden, threads):
+    """CPU oracle port on a bounded sample -> (env-steps/s for a full iteration, detail dict)"""
+    import torch
+    from oracle import cphys, ppo as oppo
+    import helpers
+    cores = threads or os.cpu_count() or 1
+    orc = cphys.Oracle(episode_len=args.horizon)
+    ctx = np.concatenate(cnn)
+    orc.make_expert(takes, ctx)
+    S, nu = orc.S, orc.nu
+    w = helpers.policy_weights(S + 128, hidden[0], hidden[1], nu, seed=1)
+    E = args.cpu_envs or 2 * cores
+    T = args.cpu_horizon
+    rng = np.random.RandomState(5)
+    L = takes[0].shape[0]
+    rt = rng.randint(0, len(takes), size=(E, T))
+    rs = rng.randint(10, L - args.horizon - 10, size=(E, T))
+    eps = rng.randn(E * T, nu)
+    pol = orc.make_policy(w['W1'], w['b1'], w['W2'], w['b2'], w['W3'], w['b3'], w['log_std'])
+    t0 = time.perf_counter()
+    out = orc.rollout(pol, E, T, rt, rs, eps, n_threads=cores)
+    t_roll = time.perf_counter() - t0
+    # update: reference path (torch CPU float64 autograd + torch.optim.Adam), epochs as configured
+    n_up = min(args.cpu_update_rows, 1 << 20)
+    reps = (n_up + E * T - 1) // (E * T)
+    tile = lambda a: np.concatenate([a] * reps)[:n_up]  # noqa: E731
+    states = np.concatenate([np.concatenate([ctx[:1].repeat(E * T, 0), out['states']], axis=1)] * reps)[:n_up]
+    vw = helpers.policy_weights(S + 128, hidden[0], hidden[1], 1, seed=2)
+    pdict = {'net.affine_layers.0.weight': w['W1'], 'net.affine_layers.0.bias': w['b1'], 'net.affine_layers.1.weight': w['W2'],
+             'net.affine_layers.1.bias': w['b2'], 'action_mean.weight': w['W3'], 'action_mean.bias': w['b3'],
+             'action_log_std': w['log_std']}
+    vdict = {'net.affine_layers.0.weight': vw['W1'], 'net.affine_layers.0.bias': vw['b1'], 'net.affine_layers.1.weight': vw['W2'],
+             'net.affine_layers.1.bias': vw['b2'], 'value_head.weight': vw['W3'], 'value_head.bias': vw['b3']}
+    torch.set_num_threads(cores)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        values = oppo.value_forward(torch.from_numpy(states), {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in vdict.items()}).numpy()
+    masks = tile(out['masks'])
+    masks[-1] = 0
+    adv, ret = oppo.gae(tile(out['rewards']), masks, values, 0.95, 0.95)
+    oppo.ppo_update(pdict, vdict, states, tile(out['actions']), ret, adv, tile(out['exps']), 0.2, 5e-5, 3e-4, 40.0,
+                    epochs=args.epochs, threads=cores)
+    t_up = time.perf_counter() - t0
+    per_step = t_roll / (E * T) + t_up / n_up
+    detail = dict(cores=cores, rollout_steps_per_s=E * T / t_roll, update_samples_per_s=n_up / t_up,
+                  sample='rollout %d envs x %d steps (C oracle, %d threads) + GAE/%d-epoch PPO update on %d rows '
+                         '(torch CPU f64, %d threads); iteration rate = 1/(t_roll/step + t_update/row)'
+                         % (E, T, cores, args.epochs, n_up, cores))
+    return 1.0 / per_step, detail
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    _, takes, cnn = synthetic_problem(args)
+    vals = []
+    for _ in range(max(1, args.warmup > 0)):
+        cpu_reference(args, takes, cnn, args.hidden, 0)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        v, detail = cpu_reference(args, takes, cnn, args.hidden, 0)
+        vals.append(v)
+    ms = (time.perf_counter() - t0) / args.steps * 1e3
+    v = float(np.mean(vals))
+    line = {'impl': 'reference', 'metric': 'env-steps/sec (humanoid PPO rollout+update)', 'value': v, 'unit': 'env-steps/s',
+            'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'hidden': args.hidden, 'epochs': args.epochs},
+            'cpu_baseline': {'value': v, 'unit': 'env-steps/s', 'cores': detail['cores'], 'kind': 'port',
+                             'sample': detail['sample'], 'rollout_steps_per_s': detail['rollout_steps_per_s'],
+                             'update_samples_per_s': detail['update_samples_per_s']},
+            'e2e': {'value': v, 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        return run_reference(args)
+    import torch
+    import torch.distributed as dist
+    from egopose_b200 import lib
+    from egopose_b200.trajbatch import TrajBatchEgo
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm')
+    torch.cuda.set_device(local)
+    device = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=device)
+    md, takes, cnn = synthetic_problem(args)
+    agent, cfg = build_agent(args, device, takes, cnn)
+    agent.env._seed = cfg.seed + 1000 * rank             # decorrelate ranks (agents/agent.py:30-32 analogue)
+    E, T = args.envs, args.horizon
+    N = E * T
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def iteration(host):
+        batch, log = agent.sample(N, to_host=host)
+        agent.env.end_reward = log.avg_c_reward * cfg.gamma / (1 - cfg.gamma)       # ego_mimic.py:112
+        if host:
+            batch = TrajBatchEgo(host={k: getattr(batch, k) for k in batch.fields}, horizon=T)
+        agent.update_params(batch)
+        return log
+
+    for _ in range(args.warmup):
+        iteration(False)
+    clk = ClockSampler(local)
+    barrier()
+    clk.start()
+    l0 = lib.launches
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    ev[0].record()
+    t_roll = t_upd = 0.0
+    for _ in range(args.steps):
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        batch, log = agent.sample(N, to_host=False)
+        agent.env.end_reward = log.avg_c_reward * cfg.gamma / (1 - cfg.gamma)
+        e1.record()
+        agent.update_params(batch)
+        e2.record()
+        e2.synchronize()
+        t_roll += e0.elapsed_time(e1)
+        t_upd += e1.elapsed_time(e2)
+    ev[1].record()
+    barrier()
+    launches = lib.launches - l0
+    clocks = clk.stop()
+    ms = ev[0].elapsed_time(ev[1]) / args.steps
+    tm = torch.tensor([ms, t_roll / args.steps, t_upd / args.steps], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ms, ms_roll, ms_upd = tm.tolist()
+    value = N * world / (ms / 1e3)
+
+    # ---- kernel rooflines: rollout kernel alone, GAE kernel alone (CUDA events on the launching stream)
+    hbm, peak_src = peaks()
+    w = agent._policy_weights()
+    zm, zs, clip = agent._zf()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    times = []
+    for i in range(3):
+        flush.fill_(i)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        agent.env.kernel.rollout(w, E, T, T, cfg.fr_margin, zf_mean=zm, zf_std=zs, zf_clip=clip, seed=7, iteration=900 + i,
+                                 want_next=False, want_raw=True, out=agent._out)
+        b.record()
+        b.synchronize()
+        times.append(a.elapsed_time(b))
+    roll_ms = float(np.median(times))
+    wbytes = 8                                            # float64
+    roll_bytes = (128 + 166 + 115 + 52 + 115 + 5 + 5) * wbytes * N      # ctx + expert row + states/actions/raw_obs/c_info/scalars
+    rewards, masks = agent._out['rewards'], agent._out['masks']
+    vals = torch.randn(N, dtype=torch.float64, device=device)
+    gt = []
+    for i in range(5):
+        flush.fill_(i)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        lib.gae(rewards, masks, vals, cfg.gamma, cfg.tau)
+        b.record()
+        b.synchronize()
+        gt.append(a.elapsed_time(b))
+    gae_ms = float(np.median(gt))
+    roofline = {'kernel': 'rollout_kernel', 'bound': 'hbm', 'achieved': roll_bytes / (roll_ms / 1e3) / 1e9, 'peak': hbm,
+                'unit': 'GB/s', 'frac': roll_bytes / (roll_ms / 1e3) / 1e9 / hbm, 'traffic': None, 'peak_source': peak_src,
+                'ms': roll_ms, 'share_of_step': roll_ms / ms,
+                'note': 'fused rollout is FP64-latency/ALU bound (~400 FLOP/B), not HBM bound (SURVEY 7); see roofline_extra'}
+    extra = {'gae_kernel': {'bound': 'hbm', 'achieved': 5 * wbytes * N / (gae_ms / 1e3) / 1e9, 'peak': hbm, 'unit': 'GB/s',
+                            'frac': 5 * wbytes * N / (gae_ms / 1e3) / 1e9 / hbm, 'ms': gae_ms, 'bytes_per_sample': 40},
+             'rollout_env_substeps_per_s': N * 15 / (roll_ms / 1e3)}
+
+    # ---- e2e through the public API with host trajbatches
+    e2e = None
+    if not args.no_e2e:
+        iteration(True)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        k = max(1, min(args.steps, 2))
+        for _ in range(k):
+            iteration(True)
+        b.record()
+        barrier()
+        t = torch.tensor([a.elapsed_time(b) / k], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        S, nu = agent.env.obs_dim, agent.env.md.nu
+        d2h = N * (2 * S + nu + 3) * 8 + N * 2 * 4 + 16 * 8
+        h2d = N * (S + nu + 3) * 8 + N * 2 * 4
+        e2e = {'value': N * world / (t.item() / 1e3), 'unit': 'env-steps/s', 'h2d_bytes_per_step': h2d,
+               'd2h_bytes_per_step': d2h, 'ms_per_step': t.item()}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, detail = cpu_reference(args, takes, cnn, args.hidden, 0)
+        cpu = {'value': v, 'unit': 'env-steps/s', 'cores': detail['cores'], 'kind': 'port', 'sample': detail['sample'],
+               'rollout_steps_per_s': detail['rollout_steps_per_s'], 'update_samples_per_s': detail['update_samples_per_s']}
+    if rank == 0:
+        line = {'metric': 'env-steps/sec (humanoid PPO rollout+update)', 'value': value, 'unit': 'env-steps/s',
+                'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
+                'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+                'config': {'workload': WORKLOAD, 'envs_per_gpu': E, 'horizon': T, 'hidden': args.hidden,
+                           'epochs': args.epochs, 'parallelism': 'env-sharded dp%d' % world,
+                           'l2': 'inputs larger than L2 (trajbatch %.1f GB per step)' % (N * (2 * 115 + 52) * 8 / 1e9)},
+                'ms_rollout': ms_roll, 'ms_update': ms_upd, 'gpu_launches': launches, 'clocks': clocks,
+                'roofline': roofline, 'roofline_extra': extra, 'e2e': e2e, 'cpu_baseline': cpu,
+                'avg_c_reward': log.avg_c_reward, 'avg_episode_len': log.avg_episode_reward,
+                'nan_resets': log.num_nan_resets}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

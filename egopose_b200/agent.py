@@ -1,0 +1,469 @@
+"""Host mirrors of the reference agents on the PPO hot path, same constructor keywords and methods:
+
+  Agent      agents/agent.py:8-122       sample(min_batch_size) -> (TrajBatch, LoggerRL), set_noise_rate, hooks
+  AgentPG    agents/agent_pg.py:7-57     update_params(batch) -> seconds, update_value / update_policy
+  AgentPPO   agents/agent_ppo.py:6-65    clipped surrogate, grad-norm clip, full-batch epochs
+  AgentEgo   ego_pose/core/agent_ego.py  video-context nets, TrajBatchEgo, v_metas
+
+What changes underneath (B200-first):
+  * sample() launches ONE fused rollout kernel for E independent environments x T steps
+    (egp_rollout_f64) instead of forking `num_threads` Python workers; `num_threads` is accepted and
+    ignored (document: the parallelism is the environment batch, `num_envs`).
+  * update_params() keeps the trajbatch on the device, runs the GAE scan / loss / clip+Adam kernels and
+    dense layers with explicit backward GEMMs; parameters and Adam moments live in flat buffers that the
+    caller's nn.Module parameters and torch.optim.Adam state alias, so state_dict()/checkpoints keep the
+    reference's format (ego_mimic.py:133-139) and set_optimizer_lr (ego_mimic.py:96) keeps working.
+  * with torch.distributed initialised (one process per GPU) environments are sharded across ranks and
+    each PPO epoch does one all-reduce of the flat [value | policy] gradient.
+There is no CPU fallback: every numeric step is a kernel of libegopose_b200.so or a cuBLAS GEMM.
+"""
+import math
+import time
+
+import numpy as np
+import torch
+
+from . import lib
+from .logger_rl import LoggerRL
+from .nets import FrameContext, trunk_ok
+from .trajbatch import TrajBatch, TrajBatchEgo
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist if dist.is_available() and dist.is_initialized() else None
+
+
+class _FlatNet:
+    """Flat parameter / gradient / Adam-moment storage for one optimizer; the module parameters and the
+    torch.optim.Adam state become views of it."""
+
+    def __init__(self, named, optimizer, device):
+        self.names = [n for n, _ in named]
+        self.params = [p for _, p in named]
+        self.optimizer = optimizer
+        sizes = [p.numel() for p in self.params]
+        self.offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        n = int(self.offsets[-1])
+        f64 = dict(dtype=torch.float64, device=device)
+        self.flat = torch.empty(n, **f64)
+        self.grad = torch.zeros(n, **f64)
+        self.m = torch.zeros(n, **f64)
+        self.v = torch.zeros(n, **f64)
+        self.norm2 = torch.zeros(1, **f64)
+        self.step = 0
+        for p, a, b in zip(self.params, self.offsets[:-1], self.offsets[1:]):
+            self.flat[a:b].copy_(p.data.reshape(-1).to(**f64))
+            p.data = self.flat[a:b].view(p.shape)
+        if optimizer is not None:
+            for p, a, b in zip(self.params, self.offsets[:-1], self.offsets[1:]):
+                st = optimizer.state[p]
+                if 'exp_avg' in st:         # resume from an existing Adam state
+                    self.m[a:b].copy_(st['exp_avg'].reshape(-1))
+                    self.v[a:b].copy_(st['exp_avg_sq'].reshape(-1))
+                    self.step = int(st['step'])
+                st['exp_avg'] = self.m[a:b].view(p.shape)
+                st['exp_avg_sq'] = self.v[a:b].view(p.shape)
+                st['step'] = torch.tensor(float(self.step))
+
+    def view(self, buf, name):
+        i = self.names.index(name)
+        return buf[self.offsets[i]:self.offsets[i + 1]].view(self.params[i].shape)
+
+    def hyper(self):
+        g = self.optimizer.param_groups[0]
+        b1, b2 = g.get('betas', (0.9, 0.999))
+        return g['lr'], b1, b2, g.get('eps', 1e-8)
+
+    def adam(self, max_norm=0.0):
+        lr, b1, b2, eps = self.hyper()
+        self.step += 1
+        if max_norm and max_norm > 0:
+            lib.sumsq(self.grad, self.norm2)
+        lib.adam_step(self.flat, self.grad, self.m, self.v, lr, b1, b2, eps, self.step, max_norm or 0.0, self.norm2)
+        for p in self.params:
+            self.optimizer.state[p]['step'].fill_(self.step)
+
+
+class _Trunk:
+    """Two-hidden-layer relu trunk + linear head: explicit forward / backward with reusable activation
+    buffers (models/mlp.py + policy_gaussian.py:19-24 / critic.py:15-18).  GEMMs are cuBLAS (torch.mm with
+    out=), bias+relu, relu-backward and bias gradients are kernels of this library."""
+
+    def __init__(self, flat, head):
+        self.f = flat
+        self.names = ['net.affine_layers.0', 'net.affine_layers.1', head]
+        self.buf = {}
+
+    def W(self, i):
+        return self.f.view(self.f.flat, self.names[i] + '.weight')
+
+    def b(self, i):
+        return self.f.view(self.f.flat, self.names[i] + '.bias')
+
+    def gW(self, i):
+        return self.f.view(self.f.grad, self.names[i] + '.weight')
+
+    def gb(self, i):
+        return self.f.view(self.f.grad, self.names[i] + '.bias')
+
+    def _buf(self, key, shape, like):
+        t = self.buf.get(key)
+        if t is None or tuple(t.shape) != tuple(shape):
+            t = torch.empty(shape, dtype=torch.float64, device=like.device)
+            self.buf[key] = t
+        return t
+
+    def forward(self, x):
+        n = x.shape[0]
+        W0, W1, W2 = self.W(0), self.W(1), self.W(2)
+        h1 = self._buf('h1', (n, W0.shape[0]), x)
+        h2 = self._buf('h2', (n, W1.shape[0]), x)
+        y = self._buf('y', (n, W2.shape[0]), x)
+        torch.mm(x, W0.t(), out=h1)
+        lib.bias_relu_(h1, self.b(0))
+        torch.mm(h1, W1.t(), out=h2)
+        lib.bias_relu_(h2, self.b(1))
+        torch.addmm(self.b(2), h2, W2.t(), out=y)
+        self.x = x
+        return y
+
+    def backward(self, dy):
+        """accumulates nothing: writes the six gradient views of the flat buffer"""
+        x, h1, h2 = self.x, self.buf['h1'], self.buf['h2']
+        n = x.shape[0]
+        torch.mm(dy.t(), h2, out=self.gW(2))
+        lib.colsum(dy, self.gb(2))
+        dh2 = self._buf('dh2', h2.shape, x)
+        torch.mm(dy, self.W(2), out=dh2)
+        lib.relu_bwd_(dh2, h2)
+        torch.mm(dh2.t(), h1, out=self.gW(1))
+        lib.colsum(dh2, self.gb(1))
+        dh1 = self._buf('dh1', h1.shape, x)
+        torch.mm(dh2, self.W(1), out=dh1)
+        lib.relu_bwd_(dh1, h1)
+        torch.mm(dh1.t(), x, out=self.gW(0))
+        lib.colsum(dh1, self.gb(0))
+
+
+class Agent:
+    def __init__(self, env, policy_net, value_net, dtype, device, custom_reward=None, mean_action=False, render=False,
+                 running_state=None, num_threads=1, num_envs=None, horizon=None):
+        self.env = env
+        self.policy_net = policy_net
+        self.value_net = value_net
+        self.dtype = dtype
+        self.device = device
+        self.custom_reward = custom_reward      # the reward is the kernel's quat_v3 (reward_function.py:4-60)
+        self.mean_action = mean_action
+        self.running_state = running_state
+        self.render = render
+        self.num_threads = num_threads          # accepted for API parity; parallelism = num_envs
+        self.num_envs = num_envs
+        self.horizon = horizon
+        self.noise_rate = 1.0
+        self.traj_cls = TrajBatch
+        self.logger_cls = LoggerRL
+        self.sample_modules = [policy_net]
+        self.update_modules = [policy_net, value_net]
+        self.iteration = 0
+        self._out = {}
+        if dtype != torch.float64:
+            raise lib.EgpError('the fused path computes in float64 like the reference (ego_mimic.py:31-32)')
+        if render:
+            raise lib.EgpError('rendering is out of scope of the fused path')
+
+    # hooks kept for API parity (agents/agent.py:78-85,113-122)
+    def pre_episode(self):
+        return
+
+    def pre_sample(self):
+        return
+
+    def push_memory(self, memory, state, action, mask, next_state, reward, exp):
+        raise lib.EgpError('trajectories are written by the rollout kernel; push_memory is not used')
+
+    def trans_policy(self, states):
+        return states
+
+    def trans_value(self, states):
+        return states
+
+    def set_noise_rate(self, noise_rate):
+        self.noise_rate = noise_rate
+
+    def _policy_weights(self):
+        p = self.policy_net
+        if not trunk_ok(p.net):
+            raise lib.EgpError('fused path needs the two-hidden-layer relu MLP trunk')
+        L = p.net.affine_layers
+        w = dict(W1=L[0].weight.data, b1=L[0].bias.data, W2=L[1].weight.data, b2=L[1].bias.data,
+                 W3=p.action_mean.weight.data, b3=p.action_mean.bias.data, log_std=p.action_log_std.data.view(-1))
+        for k, t in w.items():
+            if not t.is_cuda or t.dtype != torch.float64:
+                raise lib.EgpError('policy parameter %s must be a CUDA float64 tensor (move the nets to the GPU)' % k)
+        return {k: t.contiguous() for k, t in w.items()}
+
+    def _zf(self):
+        rs = self.running_state
+        if rs is None:
+            return None, None, 0.0
+        if rs.rs.n < 2:
+            return None, None, rs.clip or 0.0
+        dev = self.policy_net.action_mean.weight.device
+        mean = torch.as_tensor(rs.rs.mean, dtype=torch.float64, device=dev)
+        std = torch.as_tensor(rs.rs.std, dtype=torch.float64, device=dev)
+        return mean, std, rs.clip or 0.0
+
+    def plan(self, min_batch_size):
+        """(E, T): T = horizon or cfg.env_episode_len, E = num_envs or ceil(min_batch / T)"""
+        T = int(self.horizon or self.env.cfg.env_episode_len)
+        E = int(self.num_envs or math.ceil(min_batch_size / T))
+        return E, T
+
+    def sample(self, min_batch_size, to_host=True, parity=None):
+        """agents/agent.py:87-111.  ``parity`` may carry pre-drawn eps / reset_take / reset_start / mean_flag
+        device tensors (SURVEY 7 'RNG parity'); otherwise noise and resets come from in-kernel Philox."""
+        t_start = time.time()
+        self.pre_sample()
+        E, T = self.plan(min_batch_size)
+        w = self._policy_weights()
+        rs = self.running_state
+        if rs is not None and rs.rs.n < 2:
+            # first rollout: statistics from one warm-up rollout of the same size (frozen-stats deviation)
+            warm = self.env.kernel.rollout(w, E, min(T, 8), self.env.cfg.env_episode_len, self.env.cfg.fr_margin,
+                                           fix_head_lb=self.env.fix_head_lb, noise_rate=self.noise_rate,
+                                           seed=self.env._seed, iteration=2 ** 40 + self.iteration, zf_clip=0.0,
+                                           want_next=False)
+            self._merge_obs(warm['raw_obs'])
+        zm, zs, clip = self._zf()
+        p = parity or {}
+        out = self.env.kernel.rollout(
+            w, E, T, self.env.cfg.env_episode_len, self.env.cfg.fr_margin, end_reward=self.env.end_reward,
+            fix_head_lb=self.env.fix_head_lb, noise_rate=self.noise_rate, mean_action=self.mean_action,
+            zf_mean=zm, zf_std=zs, zf_clip=clip, seed=self.env._seed, iteration=self.iteration,
+            eps=p.get('eps'), reset_take=p.get('reset_take'), reset_start=p.get('reset_start'),
+            mean_flag=p.get('mean_flag'), want_next=to_host, want_raw=rs is not None, out=self._out)
+        self.iteration += 1
+        if rs is not None:
+            self._merge_obs(out['raw_obs'])
+        batch = self.traj_cls(dev={k: out.get(k) for k in self.traj_cls.fields}, horizon=T)
+        lg = out['logger']
+        d = _dist()
+        if d is not None:
+            sums = lg.clone()
+            mins = torch.stack([lg[lib.LOG['MIN_C_REWARD']], lg[lib.LOG['MIN_EPISODE_REWARD']]])
+            maxs = torch.stack([lg[lib.LOG['MAX_C_REWARD']], lg[lib.LOG['MAX_EPISODE_REWARD']]])
+            d.all_reduce(sums)
+            d.all_reduce(mins, op=d.ReduceOp.MIN)
+            d.all_reduce(maxs, op=d.ReduceOp.MAX)
+            lg = sums
+            lg[lib.LOG['MIN_C_REWARD']], lg[lib.LOG['MIN_EPISODE_REWARD']] = mins[0], mins[1]
+            lg[lib.LOG['MAX_C_REWARD']], lg[lib.LOG['MAX_EPISODE_REWARD']] = maxs[0], maxs[1]
+        logger = self.logger_cls.from_device(lg.cpu().numpy())     # D2H of 16 doubles: the rollout's sync point
+        if to_host:
+            batch.to_host()
+        logger.sample_time = time.time() - t_start
+        return batch, logger
+
+    def _merge_obs(self, raw):
+        rs = self.running_state.rs
+        shift = torch.as_tensor(rs.mean if rs.n > 0 else np.zeros(rs.shape), dtype=torch.float64, device=raw.device)
+        mo = lib.col_moments(raw, shift)
+        n_b = raw.shape[0]
+        d = _dist()
+        if d is not None:
+            d.all_reduce(mo)
+            n_b *= d.get_world_size()
+        mo = mo.cpu().numpy()
+        S = raw.shape[1]
+        rs.merge_moments(n_b, mo[:S], mo[S:], shift.cpu().numpy())
+
+
+class AgentPG(Agent):
+    def __init__(self, gamma=0.99, tau=0.95, optimizer_policy=None, optimizer_value=None, opt_num_epochs=1,
+                 value_opt_niter=1, **kwargs):
+        super().__init__(**kwargs)
+        self.gamma = gamma
+        self.tau = tau
+        self.optimizer_policy = optimizer_policy
+        self.optimizer_value = optimizer_value
+        self.opt_num_epochs = opt_num_epochs
+        self.value_opt_niter = value_opt_niter
+        self._nets = None
+        self.last_info = {}
+
+    # ---- flat storage ------------------------------------------------------------------------------
+    def _setup(self):
+        if self._nets is not None:
+            return
+        for opt in (self.optimizer_policy, self.optimizer_value):
+            if not isinstance(opt, torch.optim.Adam):
+                raise lib.EgpError('the fused update implements torch.optim.Adam (ego_mimic.py:70-77)')
+            g = opt.param_groups[0]
+            if g.get('weight_decay', 0) or g.get('amsgrad', False):
+                raise lib.EgpError('weight_decay / amsgrad are not supported by the fused Adam')
+        dev = self.policy_net.action_mean.weight.device
+        pol = [(n, p) for n, p in self.policy_net.named_parameters() if p.requires_grad]
+        val = [(n, p) for n, p in self.value_net.named_parameters() if p.requires_grad]
+        if not (trunk_ok(self.policy_net.net) and trunk_ok(self.value_net.net)):
+            raise lib.EgpError('fused path needs two-hidden-layer relu MLP trunks')
+        self._pf = _FlatNet(pol, self.optimizer_policy, dev)
+        self._vf = _FlatNet(val, self.optimizer_value, dev)
+        self._pt = _Trunk(self._pf, 'action_mean')
+        self._vt = _Trunk(self._vf, 'value_head')
+        self._learn_std = 'action_log_std' in self._pf.names
+        self._scal = torch.zeros(4, dtype=torch.float64, device=dev)
+        self._nets = True
+
+    # ---- pieces of update_params ---------------------------------------------------------------------
+    def _device_batch(self, batch):
+        dev = self.policy_net.action_mean.weight.device
+        if getattr(batch, 'dev', None) and batch.dev.get('states') is not None and 'states' not in batch._host:
+            b = batch.dev
+            return b['states'], b['actions'], b['rewards'], b['masks'], b['exps'], b.get('v_metas'), batch.horizon
+        # reference-format host batch (agents/agent_pg.py:43-47): pinned staging + async H2D
+        def up(a, dtype=torch.float64):
+            t = torch.from_numpy(np.ascontiguousarray(a))
+            return t.pin_memory().to(dev, non_blocking=True).to(dtype)
+        vm = up(batch.v_metas, torch.int32) if hasattr(batch, 'v_metas') or 'v_metas' in getattr(batch, '_host', {}) else None
+        return (up(batch.states), up(batch.actions), up(batch.rewards), up(batch.masks), up(batch.exps), vm,
+                getattr(batch, 'horizon', None))
+
+    def _inputs(self, states, v_metas, masks, horizon):
+        """trans_policy / trans_value of the base agent: identity"""
+        return states, states
+
+    def update_value(self, x, returns, inv_n):
+        """agents/agent_pg.py:19-26"""
+        for _ in range(self.value_opt_niter):
+            v = self._vt.forward(x)
+            dv = self._vt._buf('dy', v.shape, x)
+            self._scal[0:1].zero_()
+            lib.value_loss_grad(v.view(-1), returns, inv_n, dv.view(-1), self._scal[0:1])
+            self._vt.backward(dv)
+            d = _dist()
+            if d is not None:
+                d.all_reduce(self._vf.grad)
+            self._vf.adam(0.0)
+
+    def update_params(self, batch):
+        t0 = time.time()
+        self._setup()
+        states, actions, rewards, masks, exps, v_metas, horizon = self._device_batch(batch)
+        xp, xv = self._inputs(states, v_metas, masks, horizon)
+        # values + GAE (agent_pg.py:48-53, core/common.py:5-25)
+        values = self._vt.forward(xv).view(-1)
+        adv, returns, stats = lib.gae(rewards, masks, values.contiguous(), self.gamma, self.tau)
+        n_local = states.shape[0]
+        n_exp = exps.sum()
+        d = _dist()
+        n_global = float(n_local)
+        if d is not None:
+            # global standardisation / denominators: Chan merge of (n, mean, M2) over ranks
+            ws = d.get_world_size()
+            gathered = [torch.empty_like(stats) for _ in range(ws)]
+            d.all_gather(gathered, stats)
+            g = torch.stack(gathered).cpu().numpy()
+            n, mean, m2 = 0.0, 0.0, 0.0
+            for nb, mb, sb in g:
+                tot = n + nb
+                delta = mb - mean
+                m2 = m2 + sb + delta * delta * n * nb / tot
+                mean = mean + delta * nb / tot
+                n = tot
+            stats.copy_(torch.tensor([n, mean, m2], dtype=torch.float64))
+            d.all_reduce(n_exp)
+            n_global = n
+        self._stats = stats
+        self.update_policy(xp, xv, actions, returns, adv, exps, 1.0 / float(n_exp.item()), 1.0 / n_global)
+        torch.cuda.synchronize()
+        return time.time() - t0
+
+    def update_policy(self, xp, xv, actions, returns, adv, exps, inv_count, inv_n):
+        raise NotImplementedError('AgentPG (A2C) policy step is not on the hot path; use AgentPPO / AgentEgo')
+
+
+class AgentPPO(AgentPG):
+    def __init__(self, clip_epsilon=0.2, opt_batch_size=64, use_mini_batch=False, policy_grad_clip=None, **kwargs):
+        super().__init__(**kwargs)
+        self.clip_epsilon = clip_epsilon
+        self.opt_batch_size = opt_batch_size
+        self.use_mini_batch = use_mini_batch
+        self.policy_grad_clip = policy_grad_clip
+        if use_mini_batch:
+            raise lib.EgpError('the mini-batch branch (agent_ppo.py:24-43) is not built; AgentEgo forces full batch '
+                               '(agent_ego.py:11)')
+
+    def _max_norm(self):
+        if not self.policy_grad_clip:
+            return 0.0
+        if len(self.policy_grad_clip) != 1:
+            raise lib.EgpError('one (params, max_norm) clip group is supported (ego_mimic.py:90)')
+        return float(self.policy_grad_clip[0][1])
+
+    def update_policy(self, xp, xv, actions, returns, adv, exps, inv_count, inv_n):
+        """agents/agent_ppo.py:16-51, full-batch branch"""
+        log_std = self.policy_net.action_log_std.data.view(-1)
+        mu = self._pt.forward(xp)
+        logp0 = lib.gauss_logp(mu, actions, log_std)                    # fixed_log_probs (:18-20)
+        max_norm = self._max_norm()
+        surr, vloss = [], []
+        d = _dist()
+        for _ in range(self.opt_num_epochs):
+            self.update_value(xv, returns, inv_n)                        # :46
+            vloss.append(self._scal[0:1].clone())
+            mu = self._pt.forward(xp)
+            dmu = self._pt._buf('dy', mu.shape, xp)
+            self._scal[1:2].zero_()
+            dls = None
+            if self._learn_std:
+                dls = self._pf.view(self._pf.grad, 'action_log_std').view(-1)
+                dls.zero_()
+            lib.ppo_loss_grad(mu, actions, log_std, adv, self._stats, logp0, exps, self.clip_epsilon, inv_count, dmu,
+                              dls, self._scal[1:2])                      # :47,58-65
+            self._pt.backward(dmu)
+            if d is not None:
+                d.all_reduce(self._pf.grad)
+            self._pf.adam(max_norm)                                      # :50-51 clip + step
+            surr.append(self._scal[1:2].clone())
+        self.last_info = dict(surr_loss=surr, value_loss=vloss)
+
+    def losses(self):
+        """per-epoch (surrogate, value) losses of the last update as python floats"""
+        li = self.last_info
+        d = _dist()
+        out = {}
+        for k in ('surr_loss', 'value_loss'):
+            t = torch.cat(li[k]) if li.get(k) else torch.zeros(0)
+            if d is not None and t.numel():
+                d.all_reduce(t)
+            out[k] = t.cpu().numpy()
+        return out
+
+
+class AgentEgo(AgentPPO):
+    def __init__(self, policy_vs_net=None, value_vs_net=None, **kwargs):
+        super().__init__(use_mini_batch=False, **kwargs)
+        self.traj_cls = TrajBatchEgo
+        self.policy_vs_net = policy_vs_net
+        self.value_vs_net = value_vs_net
+        self.sample_modules.append(policy_vs_net)
+        self.update_modules += [policy_vs_net, value_vs_net]
+        for net in (policy_vs_net, value_vs_net):
+            if net is not None and not isinstance(net, FrameContext):
+                raise lib.EgpError('the fused path takes the video context from the per-frame table (nets.FrameContext); '
+                                   'the BiLSTM VideoStateNet producer is SURVEY 8f row 2 (next)')
+
+    def pre_sample(self):
+        if self.policy_vs_net is not None:
+            self.policy_vs_net.set_mode('test')
+
+    def _inputs(self, states, v_metas, masks, horizon):
+        """trans_policy / trans_value (agent_ego.py:28-32): cat(ctx[frame], state) gathered on the device"""
+        if self.env.kernel.ctx_dim == 0:
+            return states, states
+        if horizon is None:
+            raise lib.EgpError('context gather needs the env-major [E, T] batch produced by sample()')
+        x = self.env.kernel.build_input(states, v_metas, masks, horizon)
+        return x, x

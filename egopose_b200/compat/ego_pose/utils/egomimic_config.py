@@ -1,0 +1,1 @@
+from egopose_b200.config import Config  # noqa: F401

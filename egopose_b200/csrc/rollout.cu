@@ -638,7 +638,7 @@ rollout_kernel(const RolloutArgs A) {
     const int S = c_m.nq - 2 + c_m.nv, nu = c_m.nu, nv = c_m.nv, nb = c_m.nbody;
     double *xs = smem;                                  // [max(D, H2p)][32]
     const int xrows = A.D > A.H2p ? A.D : A.H2p;
-    double *h1s = smem + (size_t)xrows * ENVS_PER_CTA;  // [H1p][32] (also receives the action means, rows 0..Ap)
+    double *h1s = smem + (size_t)xrows * ENVS_PER_CTA;  // [max(H1p, Ap)][32] (also receives the action means)
     const int T = A.cfg.horizon, E = A.cfg.n_env;
     const double dt = c_m.h * c_m.frame_skip;
     const int env = blockIdx.x * ENVS_PER_CTA + lane;
@@ -1140,7 +1140,8 @@ int egp_rollout_f64(EgpModel *m, const EgpPolicyWeights *pol, const EgpRolloutCf
         EGP_CUDA(cudaMemcpyAsync(out->d_logger, init, sizeof init, cudaMemcpyHostToDevice, st));
     }
     int xrows = A.D > A.H2p ? A.D : A.H2p;
-    size_t smem = sizeof(double) * ENVS_PER_CTA * ((size_t)xrows + A.H1p);
+    int hrows = A.H1p > A.Ap ? A.H1p : A.Ap;
+    size_t smem = sizeof(double) * ENVS_PER_CTA * ((size_t)xrows + hrows);
     if (smem > 227 * 1024) { set_error("egp_rollout_f64: policy too wide for shared memory (%zu bytes)", smem); return EGP_ESIZE; }
     EGP_CUDA(cudaFuncSetAttribute(rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int blocks = (cfg->n_env + ENVS_PER_CTA - 1) / ENVS_PER_CTA;
