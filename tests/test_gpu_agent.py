@@ -1,0 +1,121 @@
+"""Agent-level parity through the public API: AgentPPO.update_params vs the golden run of the reference's
+own AgentPPO (tests/golden/ppo_small.npz), and AgentEgo.sample + update_params vs the CPU oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip('torch')
+
+from oracle import cphys, ppo as oppo  # noqa: E402
+import helpers  # noqa: E402
+
+
+def _nets_from(g, prefix_p, prefix_v, D, H, A):
+    from egopose_b200.nets import MLP, PolicyGaussian, Value
+    torch.set_default_dtype(torch.float64)
+    pol = PolicyGaussian(MLP(D, H, 'relu'), A, log_std=-2.3, fix_std=True)
+    val = Value(MLP(D, H, 'relu'))
+    pol.load_state_dict({k[len(prefix_p):]: torch.from_numpy(g[k]) for k in g.files if k.startswith(prefix_p)})
+    val.load_state_dict({k[len(prefix_v):]: torch.from_numpy(g[k]) for k in g.files if k.startswith(prefix_v)})
+    return pol.cuda(), val.cuda()
+
+
+def test_agent_ppo_update_matches_reference_golden(golden):
+    from egopose_b200.agent import AgentPPO
+    from egopose_b200.trajbatch import TrajBatch
+    g = golden('ppo_small')
+    gamma, tau, clip, lr_p, lr_v, max_norm = g['hyper']
+    pol, val = _nets_from(g, 'p0.', 'v0.', 24, (32, 16), 6)
+    opt_p = torch.optim.Adam(pol.parameters(), lr=lr_p)
+    opt_v = torch.optim.Adam(val.parameters(), lr=lr_v)
+    agent = AgentPPO(env=None, dtype=torch.float64, device=torch.device('cuda'), policy_net=pol, value_net=val,
+                     optimizer_policy=opt_p, optimizer_value=opt_v, opt_num_epochs=3, gamma=gamma, tau=tau,
+                     clip_epsilon=clip, policy_grad_clip=[(list(pol.parameters()), max_norm)])
+    batch = TrajBatch.from_numpy(states=g['states'], actions=g['actions'], rewards=g['rewards'], masks=g['masks'],
+                                 exps=g['exps'])
+    agent.update_params(batch)
+    losses = agent.losses()
+    # north-star tolerance on the PPO loss: 1e-5; float64 kernels give ~1e-12
+    assert np.allclose(losses['surr_loss'], g['surr_loss'], rtol=1e-9, atol=1e-12)
+    assert np.allclose(losses['value_loss'], g['value_loss'], rtol=1e-10)
+    for k, v in pol.state_dict().items():
+        assert np.allclose(v.cpu().numpy(), g['p3.' + k], rtol=1e-8, atol=1e-10), k
+    for k, v in val.state_dict().items():
+        assert np.allclose(v.cpu().numpy(), g['v3.' + k], rtol=1e-8, atol=1e-10), k
+    # Adam state is exposed through the caller's optimizer (checkpoint format)
+    st = opt_p.state[pol.action_mean.weight]
+    assert int(st['step']) == 3 and st['exp_avg'].abs().sum() > 0
+
+
+def test_agent_ego_sample_and_update_vs_oracle():
+    from egopose_b200.agent import AgentEgo
+    from egopose_b200.config import Config
+    from egopose_b200.env import HumanoidEnv
+    from egopose_b200.nets import MLP, FrameContext, PolicyGaussian, Value
+    from egopose_b200.mjcf import load_builtin
+    from egopose_b200.synthetic import synthetic_cnn_feat, synthetic_takes
+    torch.set_default_dtype(torch.float64)
+    torch.manual_seed(3)
+    E, T, EPL, CD = 24, 10, 8, 16
+    cfg = Config('subject_03')
+    cfg.env_episode_len = EPL
+    env = HumanoidEnv(cfg)
+    md = load_builtin()
+    takes = synthetic_takes(md, 3, 60, seed=4)
+    cnn = synthetic_cnn_feat(3, 60, dim=CD)
+    env.set_expert_qpos(['a', 'b', 'c'], takes, cnn)
+    S, nu = env.obs_dim, md.nu
+    pol = PolicyGaussian(MLP(S + CD, (48, 32), 'relu'), nu, log_std=-2.3, fix_std=True).cuda()
+    val = Value(MLP(S + CD, (48, 32), 'relu')).cuda()
+    p0 = {k: v.cpu().numpy().copy() for k, v in pol.state_dict().items()}
+    v0 = {k: v.cpu().numpy().copy() for k, v in val.state_dict().items()}
+    opt_p = torch.optim.Adam(pol.parameters(), lr=5e-4)
+    opt_v = torch.optim.Adam(val.parameters(), lr=3e-3)
+    agent = AgentEgo(env=env, dtype=torch.float64, device=torch.device('cuda'), running_state=None, custom_reward=None,
+                     num_threads=12, policy_net=pol, policy_vs_net=FrameContext(CD), value_net=val,
+                     value_vs_net=FrameContext(CD), optimizer_policy=opt_p, optimizer_value=opt_v, opt_num_epochs=2,
+                     gamma=0.95, tau=0.95, clip_epsilon=0.2, policy_grad_clip=[(list(pol.parameters()), 40)],
+                     num_envs=E, horizon=T)
+    rng = np.random.RandomState(8)
+    rt, rs = rng.randint(0, 3, size=(E, T)), rng.randint(10, 60 - EPL - 10, size=(E, T))
+    eps = rng.randn(E * T, nu)
+    cu = lambda a, dt=torch.float64: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device='cuda')  # noqa: E731
+    batch, log = agent.sample(E * T, to_host=True, parity=dict(eps=cu(eps), reset_take=cu(rt, torch.int32),
+                                                                reset_start=cu(rs, torch.int32)))
+    # oracle rollout on the same experts (GPU gen_expert rows are checked separately) / noise / resets
+    orc = cphys.Oracle(episode_len=EPL)
+    orc.make_expert([np.array(t) for t in takes], np.concatenate(cnn))
+    pw = orc.make_policy(p0['net.affine_layers.0.weight'], p0['net.affine_layers.0.bias'], p0['net.affine_layers.1.weight'],
+                         p0['net.affine_layers.1.bias'], p0['action_mean.weight'], p0['action_mean.bias'], p0['action_log_std'])
+    ref = orc.rollout(pw, E, T, rt, rs, eps)
+    assert batch.states.shape == (E * T, S) and batch.masks.dtype == np.int64
+    assert np.array_equal(batch.masks, ref['masks'].astype(np.int64))
+    assert helpers.relerr(batch.states, ref['states']) < 1e-6
+    assert np.allclose(batch.rewards, ref['rewards'], rtol=1e-6, atol=1e-9)
+    assert np.array_equal(batch.v_metas, ref['v_metas'])
+    assert abs(log.avg_c_reward - ref['rewards'].mean()) < 1e-8 and log.num_steps == E * T
+    assert abs(log.avg_episode_reward - E * T / (ref['masks'] == 0).sum()) < 1e-12
+    # update from the HOST batch (reference-format call) vs the oracle's PPO update on the oracle's batch
+    from egopose_b200.trajbatch import TrajBatchEgo
+    hb = TrajBatchEgo(host={k: getattr(batch, k) for k in batch.fields}, horizon=T)
+    agent.update_params(hb)
+    frames = np.array(orc._keep['x_off'])[ref['v_metas'][:, 0]] + ref['v_metas'][:, 1]
+    t_in_ep = np.zeros(E * T, dtype=np.int64)
+    for e in range(E):
+        c = 0
+        for t in range(T):
+            t_in_ep[e * T + t] = c
+            c = 0 if ref['masks'][e * T + t] == 0 else c + 1
+    x = np.concatenate([np.concatenate(cnn)[frames + t_in_ep], ref['states']], axis=1)
+    with torch.no_grad():
+        values = oppo.value_forward(torch.from_numpy(x), {k: torch.from_numpy(v) for k, v in v0.items()}).numpy()
+    adv, ret = oppo.gae(ref['rewards'], ref['masks'], values, 0.95, 0.95)
+    new_p, new_v, info = oppo.ppo_update(p0, v0, x, ref['actions'], ret, adv, ref['exps'], 0.2, 5e-4, 3e-3, 40.0, epochs=2)
+    losses = agent.losses()
+    assert np.allclose(losses['surr_loss'], info['surr_loss'], rtol=1e-5, atol=1e-9)      # north star: 1e-5
+    assert np.allclose(losses['value_loss'], info['value_loss'], rtol=1e-5)
+    for k, v in pol.state_dict().items():
+        assert np.allclose(v.cpu().numpy(), new_p[k], rtol=1e-5, atol=1e-8), k
+    for k, v in val.state_dict().items():
+        assert np.allclose(v.cpu().numpy(), new_v[k], rtol=1e-5, atol=1e-8), k
+    env.close()
