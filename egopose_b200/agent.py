@@ -29,9 +29,11 @@ from .nets import FrameContext, trunk_ok
 from .trajbatch import TrajBatch, TrajBatchEgo
 
 
+from . import dist_utils
+
+
 def _dist():
-    import torch.distributed as dist
-    return dist if dist.is_available() and dist.is_initialized() else None
+    return dist_utils.group()
 
 
 class _FlatNet:
@@ -249,17 +251,8 @@ class Agent:
             self._merge_obs(out['raw_obs'])
         batch = self.traj_cls(dev={k: out.get(k) for k in self.traj_cls.fields}, horizon=T)
         lg = out['logger']
-        d = _dist()
-        if d is not None:
-            sums = lg.clone()
-            mins = torch.stack([lg[lib.LOG['MIN_C_REWARD']], lg[lib.LOG['MIN_EPISODE_REWARD']]])
-            maxs = torch.stack([lg[lib.LOG['MAX_C_REWARD']], lg[lib.LOG['MAX_EPISODE_REWARD']]])
-            d.all_reduce(sums)
-            d.all_reduce(mins, op=d.ReduceOp.MIN)
-            d.all_reduce(maxs, op=d.ReduceOp.MAX)
-            lg = sums
-            lg[lib.LOG['MIN_C_REWARD']], lg[lib.LOG['MIN_EPISODE_REWARD']] = mins[0], mins[1]
-            lg[lib.LOG['MAX_C_REWARD']], lg[lib.LOG['MAX_EPISODE_REWARD']] = maxs[0], maxs[1]
+        lg = dist_utils.reduce_logger_(lg.clone(), (lib.LOG['MIN_C_REWARD'], lib.LOG['MIN_EPISODE_REWARD']),
+                                       (lib.LOG['MAX_C_REWARD'], lib.LOG['MAX_EPISODE_REWARD']))
         logger = self.logger_cls.from_device(lg.cpu().numpy())     # D2H of 16 doubles: the rollout's sync point
         if to_host:
             batch.to_host()
@@ -357,24 +350,12 @@ class AgentPG(Agent):
         adv, returns, stats = lib.gae(rewards, masks, values.contiguous(), self.gamma, self.tau)
         n_local = states.shape[0]
         n_exp = exps.sum()
-        d = _dist()
         n_global = float(n_local)
-        if d is not None:
+        if _dist() is not None:
             # global standardisation / denominators: Chan merge of (n, mean, M2) over ranks
-            ws = d.get_world_size()
-            gathered = [torch.empty_like(stats) for _ in range(ws)]
-            d.all_gather(gathered, stats)
-            g = torch.stack(gathered).cpu().numpy()
-            n, mean, m2 = 0.0, 0.0, 0.0
-            for nb, mb, sb in g:
-                tot = n + nb
-                delta = mb - mean
-                m2 = m2 + sb + delta * delta * n * nb / tot
-                mean = mean + delta * nb / tot
-                n = tot
-            stats.copy_(torch.tensor([n, mean, m2], dtype=torch.float64))
-            d.all_reduce(n_exp)
-            n_global = n
+            dist_utils.merge_moments_(stats)
+            dist_utils.allreduce_sum_(n_exp)
+            n_global = float(stats[0].item())
         self._stats = stats
         self.update_policy(xp, xv, actions, returns, adv, exps, 1.0 / float(n_exp.item()), 1.0 / n_global)
         torch.cuda.synchronize()
