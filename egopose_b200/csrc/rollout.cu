@@ -20,6 +20,7 @@
 // __constant__ memory (warp-uniform indices -> broadcast), policy weights pre-transposed/padded and read
 // through the uniform L1/L2 path.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -44,6 +45,11 @@ struct DevModel {
     double dof_arm[MAXV], dof_axis[MAXV][3], dof_anchor[MAXV][3];
     double kp[MAXV], kd[MAXV], a_ref[MAXV], a_scale[MAXV], tlim[MAXV];        // indexed by dof (0 on the root)
     int chain_lo[MAXC], chain_hi[MAXC], chain_parent[MAXC];                   // body ranges, inclusive
+    // T4 schedule: tree level of a chain, warp that owns it, slot of its forward/accel junction record (chains
+    // with children), sibling slot for its backward junction record, number of child chains
+    int chain_level[MAXC], chain_warp[MAXC], chain_pslot[MAXC], chain_cslot[MAXC], chain_nchild[MAXC];
+    int nlevel, nparent, max_sib, t4_ok;
+    int body_xp_slot[MAXB], ee_xp_slot[EGP_NEE], head_xp_slot;                // rows of the shared body-position record
     double w_p, w_v, w_e, w_rp, w_rv, k_p, k_v, k_e, k_rh, k_rq, k_rl, k_ra;
 };
 
@@ -807,6 +813,751 @@ rollout_kernel(const RolloutArgs A) {
     (void)nb;
 }
 
+
+// ================================================================================================
+// T4 variant: CTA = 4 warps x 32 environments.  Lane = environment, warp = owner of a set of kinematic
+// chains; the tree sweeps run level-synchronously (root | spine, legs | arms, head) so the serial depth per
+// pass is 28 of the 58 DoFs, and the policy MLP is split 4 ways.  Hot per-DoF data (joint axes, body anchors,
+// U = I^A S, q, v) live in shared memory [row][env] (bank-conflict free); junction records pass between warps
+// through shared memory; everything else is owner-private thread-local.
+constexpr int T4_WARPS = 4;
+constexpr int T4_THREADS = T4_WARPS * 32;
+
+struct T4Off { int q, v, ax, anc, U, jf, jb, ja, xp, red, total; };
+
+struct T4Local {
+    double cin[MAXB][10], fb[MAXB][6];
+    double Dinv[MAXV], u[MAXV], C[MAXV], tau[MAXV], ctrl[MAXV], x[MAXV];
+    double sav_ax[MAXV][3], sav_anc[MAXB][3];
+    double bqp[MAXB][4], bqc[MAXB][4];
+};
+
+struct T4Ctx {
+    double *sm;
+    int lane, w;
+    T4Off o;
+    __device__ __forceinline__ double &at(int off, int idx) const { return sm[(size_t)(off + idx) * 32 + lane]; }
+};
+
+__device__ __forceinline__ int t4_my_chain(int level, int w) {
+    for (int c = 0; c < c_m.nchain; c++)
+        if (c_m.chain_level[c] == level && c_m.chain_warp[c] == w) return c;
+    return -1;
+}
+
+// spatial motion axis of dof i from the shared rows: hinge [ax; anc x ax], free translation [0; ax]
+__device__ __forceinline__ void t4_load_S(const T4Ctx &x, int i, int b, double *S) {
+    double ax[3] = {x.at(x.o.ax, 3 * i), x.at(x.o.ax, 3 * i + 1), x.at(x.o.ax, 3 * i + 2)};
+    if (c_m.body_dofnum[b] == 6 && i - c_m.body_dofadr[b] < 3) {
+        S[0] = S[1] = S[2] = 0.0; S[3] = ax[0]; S[4] = ax[1]; S[5] = ax[2];
+    } else {
+        double an[3] = {x.at(x.o.anc, 3 * b), x.at(x.o.anc, 3 * b + 1), x.at(x.o.anc, 3 * b + 2)};
+        S[0] = ax[0]; S[1] = ax[1]; S[2] = ax[2];
+        cross3(an, ax, S + 3);
+    }
+}
+
+__device__ void t4_kinematics(const T4Ctx &x, T4Local &l) {
+    for (int L = 0; L < c_m.nlevel; L++) {
+        const int c = t4_my_chain(L, x.w);
+        if (c >= 0) {
+            Fwd f;
+            const int pc = c_m.chain_parent[c];
+            if (pc >= 0) {
+                const int base = x.o.jf + 24 * c_m.chain_pslot[pc];
+#pragma unroll
+                for (int k = 0; k < 3; k++) f.p[k] = x.at(base, k);
+#pragma unroll
+                for (int k = 0; k < 9; k++) f.R[k] = x.at(base, 3 + k);
+#pragma unroll
+                for (int k = 0; k < 6; k++) { f.v[k] = x.at(base, 12 + k); f.a[k] = x.at(base, 18 + k); }
+            }
+            for (int b = c_m.chain_lo[c]; b <= c_m.chain_hi[c]; b++) {
+                const int da = c_m.body_dofadr[b], nd = c_m.body_dofnum[b], qa = c_m.body_qposadr[b];
+                if (nd == 6) {
+                    double q4[4] = {x.at(x.o.q, qa + 3), x.at(x.o.q, qa + 4), x.at(x.o.q, qa + 5), x.at(x.o.q, qa + 6)};
+                    double n = sqrt(q4[0] * q4[0] + q4[1] * q4[1] + q4[2] * q4[2] + q4[3] * q4[3]);
+                    for (int k = 0; k < 4; k++) q4[k] /= n;
+                    quat_to_mat(q4, f.R);
+                    f.p[0] = f.p[1] = f.p[2] = 0.0;
+                    double wl[3] = {x.at(x.o.v, da + 3), x.at(x.o.v, da + 4), x.at(x.o.v, da + 5)}, ww[3];
+                    for (int r = 0; r < 3; r++) ww[r] = f.R[3 * r] * wl[0] + f.R[3 * r + 1] * wl[1] + f.R[3 * r + 2] * wl[2];
+                    for (int k = 0; k < 3; k++) {
+                        for (int r = 0; r < 3; r++) {
+                            x.at(x.o.ax, 3 * (da + k) + r) = r == k ? 1.0 : 0.0;
+                            x.at(x.o.ax, 3 * (da + 3 + k) + r) = f.R[3 * r + k];
+                        }
+                        x.at(x.o.anc, 3 * b + k) = 0.0;
+                    }
+                    double vl[3] = {x.at(x.o.v, da), x.at(x.o.v, da + 1), x.at(x.o.v, da + 2)}, vxw[3];
+                    cross3(vl, ww, vxw);
+                    for (int k = 0; k < 3; k++) {
+                        f.v[k] = ww[k]; f.v[3 + k] = vl[k];
+                        f.a[k] = 0.0; f.a[3 + k] = -c_m.grav[k] + vxw[k];
+                    }
+                } else {
+                    double off[3];
+                    for (int r = 0; r < 3; r++)
+                        off[r] = f.R[3 * r] * c_m.body_pos[b][0] + f.R[3 * r + 1] * c_m.body_pos[b][1] + f.R[3 * r + 2] * c_m.body_pos[b][2];
+                    for (int r = 0; r < 3; r++) f.p[r] += off[r];
+                    double anc[3];
+                    for (int r = 0; r < 3; r++) {
+                        anc[r] = f.p[r] + f.R[3 * r] * c_m.dof_anchor[da][0] + f.R[3 * r + 1] * c_m.dof_anchor[da][1] +
+                                 f.R[3 * r + 2] * c_m.dof_anchor[da][2];
+                        x.at(x.o.anc, 3 * b + r) = anc[r];
+                    }
+                    for (int j = 0; j < nd; j++) {
+                        const int i = da + j;
+                        double ax[3];
+                        const int aid = c_m.dof_axis_id[i];
+                        if (aid >= 0) { ax[0] = f.R[aid]; ax[1] = f.R[3 + aid]; ax[2] = f.R[6 + aid]; }
+                        else for (int r = 0; r < 3; r++)
+                            ax[r] = f.R[3 * r] * c_m.dof_axis[i][0] + f.R[3 * r + 1] * c_m.dof_axis[i][1] + f.R[3 * r + 2] * c_m.dof_axis[i][2];
+                        for (int r = 0; r < 3; r++) x.at(x.o.ax, 3 * i + r) = ax[r];
+                        double S[6];
+                        S[0] = ax[0]; S[1] = ax[1]; S[2] = ax[2];
+                        cross3(anc, ax, S + 3);
+                        const double qd = x.at(x.o.v, i);
+                        double t0[3], t1[3], t2[3];
+                        cross3(f.v, S, t0);
+                        cross3(f.v, S + 3, t1);
+                        cross3(f.v + 3, S, t2);
+                        for (int r = 0; r < 3; r++) {
+                            f.a[r] += t0[r] * qd;
+                            f.a[3 + r] += (t1[r] + t2[r]) * qd;
+                        }
+                        for (int r = 0; r < 6; r++) f.v[r] += S[r] * qd;
+                        double sn, cs;
+                        sincos(x.at(x.o.q, qa + j), &sn, &cs);
+                        if (aid >= 0) {
+                            const int c1 = (aid + 1) % 3, c2 = (aid + 2) % 3;
+                            for (int r = 0; r < 3; r++) {
+                                double a1 = f.R[3 * r + c1], a2 = f.R[3 * r + c2];
+                                f.R[3 * r + c1] = cs * a1 + sn * a2;
+                                f.R[3 * r + c2] = -sn * a1 + cs * a2;
+                            }
+                        } else {
+                            const double *a = c_m.dof_axis[i];
+                            double K[9] = {0, -a[2], a[1], a[2], 0, -a[0], -a[1], a[0], 0}, Rot[9], Rn[9];
+                            for (int r = 0; r < 3; r++) for (int cc = 0; cc < 3; cc++)
+                                Rot[3 * r + cc] = (r == cc ? cs : 0.0) + sn * K[3 * r + cc] + (1.0 - cs) * a[r] * a[cc];
+                            for (int r = 0; r < 3; r++) for (int cc = 0; cc < 3; cc++)
+                                Rn[3 * r + cc] = f.R[3 * r] * Rot[cc] + f.R[3 * r + 1] * Rot[3 + cc] + f.R[3 * r + 2] * Rot[6 + cc];
+                            for (int r = 0; r < 9; r++) f.R[r] = Rn[r];
+                        }
+                    }
+                    for (int r = 0; r < 3; r++)
+                        f.p[r] = anc[r] - (f.R[3 * r] * c_m.dof_anchor[da][0] + f.R[3 * r + 1] * c_m.dof_anchor[da][1] +
+                                           f.R[3 * r + 2] * c_m.dof_anchor[da][2]);
+                }
+                const int xs = c_m.body_xp_slot[b];
+                if (xs >= 0) for (int r = 0; r < 3; r++) x.at(x.o.xp, 3 * xs + r) = f.p[r] + x.at(x.o.q, r);
+                double cpos[3];
+                for (int r = 0; r < 3; r++)
+                    cpos[r] = f.p[r] + f.R[3 * r] * c_m.body_ipos[b][0] + f.R[3 * r + 1] * c_m.body_ipos[b][1] + f.R[3 * r + 2] * c_m.body_ipos[b][2];
+                const double *in = c_m.body_inertia[b];
+                double Ib[9] = {in[0], in[3], in[4], in[3], in[1], in[5], in[4], in[5], in[2]}, Tm[9], Iw[6];
+                for (int r = 0; r < 3; r++) for (int cc = 0; cc < 3; cc++)
+                    Tm[3 * r + cc] = f.R[3 * r] * Ib[cc] + f.R[3 * r + 1] * Ib[3 + cc] + f.R[3 * r + 2] * Ib[6 + cc];
+                Iw[0] = Tm[0] * f.R[0] + Tm[1] * f.R[1] + Tm[2] * f.R[2];
+                Iw[1] = Tm[3] * f.R[3] + Tm[4] * f.R[4] + Tm[5] * f.R[5];
+                Iw[2] = Tm[6] * f.R[6] + Tm[7] * f.R[7] + Tm[8] * f.R[8];
+                Iw[3] = Tm[0] * f.R[3] + Tm[1] * f.R[4] + Tm[2] * f.R[5];
+                Iw[4] = Tm[0] * f.R[6] + Tm[1] * f.R[7] + Tm[2] * f.R[8];
+                Iw[5] = Tm[3] * f.R[6] + Tm[4] * f.R[7] + Tm[5] * f.R[8];
+                const double mass = c_m.body_mass[b], cc2 = dot3(cpos, cpos);
+                double *ci = l.cin[b];
+                ci[0] = mass;
+                ci[1] = mass * cpos[0]; ci[2] = mass * cpos[1]; ci[3] = mass * cpos[2];
+                ci[4] = Iw[0] + mass * (cc2 - cpos[0] * cpos[0]);
+                ci[5] = Iw[1] + mass * (cc2 - cpos[1] * cpos[1]);
+                ci[6] = Iw[2] + mass * (cc2 - cpos[2] * cpos[2]);
+                ci[7] = Iw[3] - mass * cpos[0] * cpos[1];
+                ci[8] = Iw[4] - mass * cpos[0] * cpos[2];
+                ci[9] = Iw[5] - mass * cpos[1] * cpos[2];
+                double Ia[6], Iv[6];
+                spi_mul(ci, f.a, Ia);
+                spi_mul(ci, f.v, Iv);
+                double c0[3], c1[3], c2[3];
+                cross3(f.v, Iv, c0);
+                cross3(f.v + 3, Iv + 3, c1);
+                cross3(f.v, Iv + 3, c2);
+                for (int r = 0; r < 3; r++) {
+                    l.fb[b][r] = Ia[r] + c0[r] + c1[r];
+                    l.fb[b][3 + r] = Ia[3 + r] + c2[r];
+                }
+            }
+            if (c_m.chain_pslot[c] >= 0) {
+                const int base = x.o.jf + 24 * c_m.chain_pslot[c];
+#pragma unroll
+                for (int k = 0; k < 3; k++) x.at(base, k) = f.p[k];
+#pragma unroll
+                for (int k = 0; k < 9; k++) x.at(base, 3 + k) = f.R[k];
+#pragma unroll
+                for (int k = 0; k < 6; k++) { x.at(base, 12 + k) = f.v[k]; x.at(base, 18 + k) = f.a[k]; }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <int MODE>
+__device__ void t4_backward(const T4Ctx &x, T4Local &l) {
+    for (int L = c_m.nlevel - 1; L >= 0; L--) {
+        const int c = t4_my_chain(L, x.w);
+        Bwd w;
+#pragma unroll
+        for (int k = 0; k < 21; k++) w.IA[k] = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; k++) { w.pA[k] = 0.0; w.F[k] = 0.0; }
+        if (c >= 0) {
+            for (int s = 0; s < c_m.chain_nchild[c]; s++) {
+                const int base = x.o.jb + 33 * s;
+#pragma unroll
+                for (int k = 0; k < 21; k++) w.IA[k] += x.at(base, k);
+#pragma unroll
+                for (int k = 0; k < 6; k++) { w.pA[k] += x.at(base, 21 + k); w.F[k] += x.at(base, 27 + k); }
+            }
+        }
+        __syncthreads();            // children records consumed before this level overwrites the slots
+        if (c >= 0) {
+            for (int b = c_m.chain_hi[c]; b >= c_m.chain_lo[c]; b--) {
+                const double *ci = l.cin[b];
+                w.IA[sx(0, 0)] += ci[4]; w.IA[sx(1, 1)] += ci[5]; w.IA[sx(2, 2)] += ci[6];
+                w.IA[sx(0, 1)] += ci[7]; w.IA[sx(0, 2)] += ci[8]; w.IA[sx(1, 2)] += ci[9];
+                w.IA[sx(0, 4)] += -ci[3]; w.IA[sx(0, 5)] += ci[2];
+                w.IA[sx(1, 3)] += ci[3];  w.IA[sx(1, 5)] += -ci[1];
+                w.IA[sx(2, 3)] += -ci[2]; w.IA[sx(2, 4)] += ci[1];
+                w.IA[sx(3, 3)] += ci[0]; w.IA[sx(4, 4)] += ci[0]; w.IA[sx(5, 5)] += ci[0];
+                if (MODE == 0) for (int k = 0; k < 6; k++) w.F[k] += l.fb[b][k];
+                const int da = c_m.body_dofadr[b], nd = c_m.body_dofnum[b];
+                for (int i = da + nd - 1; i >= da; i--) {
+                    double S[6], U[6];
+                    t4_load_S(x, i, b, S);
+                    double rhs;
+                    if (MODE == 0) {
+                        double Ci = dot6(S, w.F);
+                        l.C[i] = Ci;
+                        rhs = l.tau[i] - Ci;
+                    } else rhs = l.tau[i];
+#pragma unroll
+                    for (int r = 0; r < 6; r++) {
+                        double t = 0.0;
+#pragma unroll
+                        for (int cc = 0; cc < 6; cc++) t += w.IA[sx(r, cc)] * S[cc];
+                        U[r] = t;
+                    }
+                    double D = dot6(S, U) + c_m.dof_arm[i];
+                    if (MODE == 1) D += c_m.kd[i] * c_m.h;
+                    const double Dinv = 1.0 / D;
+                    const double ui = rhs - dot6(S, w.pA);
+                    l.Dinv[i] = Dinv;
+                    l.u[i] = ui;
+#pragma unroll
+                    for (int r = 0; r < 6; r++) x.at(x.o.U, 6 * i + r) = U[r];
+#pragma unroll
+                    for (int r = 0; r < 6; r++) {
+                        const double ur = U[r] * Dinv;
+#pragma unroll
+                        for (int cc = r; cc < 6; cc++) w.IA[sx(r, cc)] -= ur * U[cc];
+                        w.pA[r] += ur * ui;
+                    }
+                }
+            }
+            if (c_m.chain_parent[c] >= 0) {
+                const int base = x.o.jb + 33 * c_m.chain_cslot[c];
+#pragma unroll
+                for (int k = 0; k < 21; k++) x.at(base, k) = w.IA[k];
+#pragma unroll
+                for (int k = 0; k < 6; k++) { x.at(base, 21 + k) = w.pA[k]; x.at(base, 27 + k) = w.F[k]; }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__device__ void t4_accel(const T4Ctx &x, T4Local &l) {
+    for (int L = 0; L < c_m.nlevel; L++) {
+        const int c = t4_my_chain(L, x.w);
+        if (c >= 0) {
+            double a[6];
+            const int pc = c_m.chain_parent[c];
+#pragma unroll
+            for (int k = 0; k < 6; k++) a[k] = pc >= 0 ? x.at(x.o.ja + 6 * c_m.chain_pslot[pc], k) : 0.0;
+            for (int b = c_m.chain_lo[c]; b <= c_m.chain_hi[c]; b++) {
+                const int da = c_m.body_dofadr[b], nd = c_m.body_dofnum[b];
+                for (int i = da; i < da + nd; i++) {
+                    double S[6], U[6];
+                    t4_load_S(x, i, b, S);
+#pragma unroll
+                    for (int r = 0; r < 6; r++) U[r] = x.at(x.o.U, 6 * i + r);
+                    const double xi = l.Dinv[i] * (l.u[i] - dot6(U, a));
+                    l.x[i] = xi;
+#pragma unroll
+                    for (int r = 0; r < 6; r++) a[r] += S[r] * xi;
+                }
+            }
+            if (c_m.chain_pslot[c] >= 0)
+#pragma unroll
+                for (int k = 0; k < 6; k++) x.at(x.o.ja + 6 * c_m.chain_pslot[c], k) = a[k];
+        }
+        __syncthreads();
+    }
+}
+
+// loop helper: for every dof i owned by warp w
+#define T4_FOR_OWN_DOFS(i, b)                                                                       \
+    for (int _c = 0; _c < c_m.nchain; _c++)                                                          \
+        if (c_m.chain_warp[_c] == x.w)                                                               \
+            for (int b = c_m.chain_lo[_c]; b <= c_m.chain_hi[_c]; b++)                               \
+                for (int i = c_m.body_dofadr[b]; i < c_m.body_dofadr[b] + c_m.body_dofnum[b]; i++)
+
+__device__ void t4_forward_only(const T4Ctx &x, T4Local &l) {      // sim.forward()
+    t4_kinematics(x, l);
+    T4_FOR_OWN_DOFS(i, b) l.tau[i] = 0.0;
+    t4_backward<0>(x, l);
+}
+
+__device__ void t4_substep(const T4Ctx &x, T4Local &l) {
+    const double h = c_m.h;
+    T4_FOR_OWN_DOFS(i, b) {
+        double eq = i >= 6 ? x.at(x.o.q, i + 1) - l.ctrl[i] : 0.0;
+        l.tau[i] = -l.C[i] - c_m.kp[i] * eq - c_m.kd[i] * x.at(x.o.v, i);
+    }
+    t4_backward<1>(x, l);
+    t4_accel(x, l);
+    T4_FOR_OWN_DOFS(i, b) {
+        double t = 0.0;
+        if (i >= 6) {
+            double eq = x.at(x.o.q, i + 1) - l.ctrl[i];
+            t = -c_m.kp[i] * eq - c_m.kd[i] * (x.at(x.o.v, i) + l.x[i] * h);
+            double lim = c_m.tlim[i];
+            t = t < -lim ? -lim : (t > lim ? lim : t);
+        }
+        l.tau[i] = t;
+    }
+    t4_kinematics(x, l);
+    t4_backward<0>(x, l);
+    t4_accel(x, l);
+    T4_FOR_OWN_DOFS(i, b) {
+        double vn = x.at(x.o.v, i) + h * l.x[i];
+        x.at(x.o.v, i) = vn;
+        if (i >= 6) x.at(x.o.q, i + 1) += h * vn;
+    }
+    if (c_m.chain_warp[0] == x.w) {         // owner of the root: position + quaternion integration
+        for (int k = 0; k < 3; k++) x.at(x.o.q, k) += h * x.at(x.o.v, k);
+        double wv[3] = {x.at(x.o.v, 3), x.at(x.o.v, 4), x.at(x.o.v, 5)};
+        double n = sqrt(dot3(wv, wv)), ax[3] = {1.0, 0.0, 0.0};
+        if (n > 1e-15) { ax[0] = wv[0] / n; ax[1] = wv[1] / n; ax[2] = wv[2] / n; }
+        double sn, cs;
+        sincos(0.5 * h * n, &sn, &cs);
+        double qr[4] = {cs, ax[0] * sn, ax[1] * sn, ax[2] * sn};
+        double q4[4] = {x.at(x.o.q, 3), x.at(x.o.q, 4), x.at(x.o.q, 5), x.at(x.o.q, 6)};
+        double qn = sqrt(q4[0] * q4[0] + q4[1] * q4[1] + q4[2] * q4[2] + q4[3] * q4[3]);
+        for (int k = 0; k < 4; k++) q4[k] /= qn;
+        double o4[4];
+        quat_mul(q4, qr, o4);
+        for (int k = 0; k < 4; k++) x.at(x.o.q, 3 + k) = o4[k];
+    }
+}
+
+// observation entry k (humanoid_v1.py:73-96) from the shared q / v rows; hd = de-headed root quaternion,
+// vl = root linear velocity in the heading frame (both computed redundantly by every thread)
+__device__ __forceinline__ double t4_obs_entry(const T4Ctx &x, int k, const double *hd, const double *vl) {
+    const int nq = c_m.nq;
+    if (k == 0) return x.at(x.o.q, 2);
+    if (k < 5) return hd[k - 1];
+    if (k < nq - 2) return x.at(x.o.q, k + 2);
+    const int j = k - (nq - 2);
+    if (j < 3) return vl[j];
+    return x.at(x.o.v, j);
+}
+
+template <bool RELU>
+__device__ __forceinline__ void t4_mlp_layer(const double *__restrict__ Wt, const double *__restrict__ bias, int K, int Np,
+                                             const double *xs, double *ys, int lane, int w) {
+    for (int j0 = w * JB; j0 < Np; j0 += T4_WARPS * JB) {
+        double acc[JB];
+#pragma unroll
+        for (int jj = 0; jj < JB; jj++) acc[jj] = bias[j0 + jj];
+#pragma unroll 2
+        for (int k = 0; k < K; k++) {
+            const double xv = xs[k * 32 + lane];
+            const double2 *wp = reinterpret_cast<const double2 *>(Wt + (size_t)k * Np + j0);
+#pragma unroll
+            for (int jj = 0; jj < JB / 2; jj++) {
+                double2 ww = __ldg(wp + jj);
+                acc[2 * jj] += ww.x * xv;
+                acc[2 * jj + 1] += ww.y * xv;
+            }
+        }
+#pragma unroll
+        for (int jj = 0; jj < JB; jj++) ys[(j0 + jj) * 32 + lane] = RELU ? fmax(acc[jj], 0.0) : acc[jj];
+    }
+}
+
+__global__ void __launch_bounds__(T4_THREADS, 1)
+rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
+    extern __shared__ double smem[];
+    T4Ctx x;
+    x.sm = smem; x.lane = threadIdx.x & 31; x.w = threadIdx.x >> 5; x.o = O;
+    const int lane = x.lane, w = x.w;
+    const int S = c_m.nq - 2 + c_m.nv, nu = c_m.nu, nv = c_m.nv, nb = c_m.nbody, nq = c_m.nq;
+    double *xs = smem + (size_t)O.ax * 32;               // MLP activations alias the axis / anchor / U rows
+    const int xrows = A.D > A.H2p ? A.D : A.H2p;
+    double *h1s = xs + (size_t)xrows * 32;
+    const int T = A.cfg.horizon, E = A.cfg.n_env;
+    const double dt = c_m.h * c_m.frame_skip;
+    const int env = blockIdx.x * 32 + lane;
+    const bool live = env < E;
+    const int eid = live ? env : E - 1;
+    const bool w0 = w == 0;
+
+    T4Local l;
+    double st[(2 * MAXV + T4_WARPS - 1) / T4_WARPS];     // this thread's strided share of the filtered state
+    double raw[(2 * MAXV + T4_WARPS - 1) / T4_WARPS];
+    double log_acc[EGP_LOG_SIZE];
+    for (int k = 0; k < EGP_LOG_SIZE; k++) log_acc[k] = 0.0;
+    log_acc[EGP_LOG_MIN_C_REWARD] = INFINITY; log_acc[EGP_LOG_MAX_C_REWARD] = -INFINITY;
+    log_acc[EGP_LOG_MIN_EPISODE_REWARD] = INFINITY; log_acc[EGP_LOG_MAX_EPISODE_REWARD] = -INFINITY;
+    double ep_reward = 0.0;
+    int n_reset = 0, take, start, cur_t = 0;
+
+    auto draw_reset = [&](int r) {
+        if (A.in.d_reset_take) {
+            int rr = r < A.cfg.max_resets ? r : A.cfg.max_resets - 1;
+            take = A.in.d_reset_take[(size_t)eid * A.cfg.max_resets + rr];
+            start = A.in.d_reset_start[(size_t)eid * A.cfg.max_resets + rr];
+        } else {
+            uint32_t c[4] = {(uint32_t)eid, (uint32_t)r, (uint32_t)A.cfg.iteration, 0x52535421u};
+            philox4x32(c, (uint32_t)A.cfg.seed, (uint32_t)(A.cfg.seed >> 32));
+            take = (int)(c[0] % (uint32_t)A.n_takes);
+            int len = A.take_off[take + 1] - A.take_off[take];
+            int span = len - A.cfg.episode_len - 2 * A.cfg.fr_margin;
+            start = A.cfg.fr_margin + (span > 0 ? (int)(c[1] % (uint32_t)span) : 0);
+        }
+    };
+    // reset: owners load their dofs of the expert frame, then sim.forward() (humanoid_v1.py:201-226)
+    auto do_reset = [&]() {
+        const double *row = A.rows + (size_t)(A.take_off[take] + start) * EGP_X_STRIDE;
+        T4_FOR_OWN_DOFS(i, b) {
+            x.at(O.v, i) = row[EGP_X_QVEL + i];
+            if (i >= 6) x.at(O.q, i + 1) = row[EGP_X_QPOS + i + 1];
+        }
+        if (c_m.chain_warp[0] == w) for (int k = 0; k < 7; k++) x.at(O.q, k) = row[EGP_X_QPOS + k];
+        __syncthreads();
+        t4_forward_only(x, l);
+        for (int b = 1 + w; b < nb; b += T4_WARPS) {        // body quaternions of this thread's bodies
+            const int qa = c_m.body_qposadr[b], nd = c_m.body_dofnum[b];
+            quat_from_euler(x.at(O.q, qa), nd > 1 ? x.at(O.q, qa + 1) : 0.0, nd > 2 ? x.at(O.q, qa + 2) : 0.0, l.bqc[b]);
+        }
+    };
+    // observation -> strided raw / filtered shares
+    auto make_state = [&](double *dst_raw, double *dst) {
+        double hd[4], vl[3];
+        double q4[4] = {x.at(O.q, 3), x.at(O.q, 4), x.at(O.q, 5), x.at(O.q, 6)};
+        double v3[3] = {x.at(O.v, 0), x.at(O.v, 1), x.at(O.v, 2)};
+        de_heading(q4, hd);
+        to_heading(v3, q4, vl);
+        int s = 0;
+        for (int k = w; k < S; k += T4_WARPS, s++) {
+            double v = t4_obs_entry(x, k, hd, vl);
+            dst_raw[s] = v;
+            if (A.in.d_zf_mean) {
+                v = (v - A.in.d_zf_mean[k]) / (A.in.d_zf_std[k] + 1e-8);
+                if (A.cfg.zf_clip > 0.0) v = fmin(fmax(v, -A.cfg.zf_clip), A.cfg.zf_clip);
+            }
+            dst[s] = v;
+        }
+    };
+
+    draw_reset(0);
+    do_reset();
+    make_state(raw, st);
+    T4_FOR_OWN_DOFS(i, b) l.ctrl[i] = 0.0;
+
+    for (int t = 0; t < T; t++) {
+        const size_t n = (size_t)eid * T + t;
+        // ---- save the tree rows the MLP buffers alias (needed stale by the next sub-step's PD solve)
+        T4_FOR_OWN_DOFS(i, b) for (int r = 0; r < 3; r++) l.sav_ax[i][r] = x.at(O.ax, 3 * i + r);
+        for (int c = 0; c < c_m.nchain; c++)
+            if (c_m.chain_warp[c] == w)
+                for (int b = c_m.chain_lo[c]; b <= c_m.chain_hi[c]; b++)
+                    for (int r = 0; r < 3; r++) l.sav_anc[b][r] = x.at(O.anc, 3 * b + r);
+        __syncthreads();
+        // ---- policy input cat(ctx[frame], state), feature-major
+        int off = 0;
+        if (A.ctx) {
+            const double *cx = A.ctx + (size_t)(A.take_off[take] + start + cur_t) * A.ctx_dim;
+            for (int k = w; k < A.ctx_dim; k += T4_WARPS) xs[k * 32 + lane] = cx[k];
+            off = A.ctx_dim;
+        }
+        {
+            int s = 0;
+            for (int k = w; k < S; k += T4_WARPS, s++) {
+                xs[(off + k) * 32 + lane] = st[s];
+                if (live) {
+                    A.out.d_states[n * S + k] = st[s];
+                    if (A.out.d_raw_obs) A.out.d_raw_obs[n * S + k] = raw[s];
+                }
+            }
+        }
+        __syncthreads();
+        t4_mlp_layer<true>(A.W1t, A.b1, A.D, A.H1p, xs, h1s, lane, w);
+        __syncthreads();
+        t4_mlp_layer<true>(A.W2t, A.b2, A.H1, A.H2p, h1s, xs, lane, w);
+        __syncthreads();
+        t4_mlp_layer<false>(A.W3t, A.b3, A.H2, A.Ap, xs, h1s, lane, w);
+        __syncthreads();
+        bool mean_flag = A.cfg.mean_action != 0;
+        if (A.in.d_mean_flag) mean_flag = mean_flag || A.in.d_mean_flag[n] != 0;
+        else if (A.cfg.noise_rate < 1.0) {
+            uint32_t c[4] = {(uint32_t)eid, (uint32_t)t, (uint32_t)A.cfg.iteration, 0x4d45414eu};
+            philox4x32(c, (uint32_t)A.cfg.seed, (uint32_t)(A.cfg.seed >> 32));
+            mean_flag = mean_flag || (u01(c[0], c[1]) <= 1.0 - A.cfg.noise_rate);
+        }
+        T4_FOR_OWN_DOFS(i, b) {
+            if (i < 6) continue;
+            const int a = i - 6;
+            double z = 0.0;
+            if (!mean_flag) {
+                if (A.in.d_eps) z = A.in.d_eps[n * nu + a];
+                else {
+                    double z0, z1;
+                    normal2(A.cfg.seed, A.cfg.iteration, (uint32_t)eid, (uint32_t)(t * 64 + (a & ~1)), &z0, &z1);
+                    z = (a & 1) ? z1 : z0;
+                }
+            }
+            const double act = h1s[a * 32 + lane] + exp(A.log_std[a]) * z;
+            l.ctrl[i] = c_m.a_ref[i] + act * c_m.a_scale[i];
+            if (live) A.out.d_actions[n * nu + a] = act;
+        }
+        __syncthreads();
+        // ---- restore the aliased tree rows
+        T4_FOR_OWN_DOFS(i, b) for (int r = 0; r < 3; r++) x.at(O.ax, 3 * i + r) = l.sav_ax[i][r];
+        for (int c = 0; c < c_m.nchain; c++)
+            if (c_m.chain_warp[c] == w)
+                for (int b = c_m.chain_lo[c]; b <= c_m.chain_hi[c]; b++)
+                    for (int r = 0; r < 3; r++) x.at(O.anc, 3 * b + r) = l.sav_anc[b][r];
+        // ---- env.step
+        double prev_root[7];
+        for (int k = 0; k < 7; k++) prev_root[k] = x.at(O.q, k);
+        for (int b = 1 + w; b < nb; b += T4_WARPS) for (int k = 0; k < 4; k++) l.bqp[b][k] = l.bqc[b][k];
+        __syncthreads();
+        for (int s = 0; s < c_m.frame_skip; s++) t4_substep(x, l);
+        __syncthreads();
+        cur_t += 1;
+        const double head_z = x.at(O.xp, 3 * c_m.head_xp_slot + 2);
+        const double lb = isnan(A.cfg.fix_head_lb) ? A.head_lb[take] - 0.1 : A.cfg.fix_head_lb;
+        bool fail = head_z < lb;
+        const bool end = cur_t >= A.cfg.episode_len;
+        const double *row = A.rows + (size_t)(A.take_off[take] + start + cur_t) * EGP_X_STRIDE;
+        // body-quaternion terms of the reward for this thread's bodies (reward_function.py:35-41)
+        double pose2 = 0.0, vd = 0.0;
+        for (int b = 1 + w; b < nb; b += T4_WARPS) {
+            const int qa = c_m.body_qposadr[b], nd = c_m.body_dofnum[b];
+            quat_from_euler(x.at(O.q, qa), nd > 1 ? x.at(O.q, qa + 1) : 0.0, nd > 2 ? x.at(O.q, qa + 2) : 0.0, l.bqc[b]);
+            double q1[4], qd[4];
+            quat_inv(row + EGP_X_BQUAT + 4 * b, q1);
+            quat_mul(l.bqc[b], q1, qd);
+            double aa = acos(fmin(fmax(qd[0], -1.0), 1.0)) * c_m.b_diffw[b - 1];
+            pose2 += aa * aa;
+            double p1[4], pd[4], av[3], aang;
+            quat_inv(l.bqp[b], p1);
+            quat_mul(l.bqc[b], p1, pd);
+            rot_from_quat(pd, av, &aang);
+            if (1.0 - pd[0] < 1e-8) av[0] = 1.0;
+            for (int k = 0; k < 3; k++) {
+                double df = fabs(av[k] * aang / dt - row[EGP_X_BANGVEL + 3 * b + k]);
+                vd += c_m.v_ord == 1 ? df : df * df;
+            }
+        }
+        x.at(O.red, 2 * w) = pose2;
+        x.at(O.red, 2 * w + 1) = vd;
+        double nraw[(2 * MAXV + T4_WARPS - 1) / T4_WARPS], nst[(2 * MAXV + T4_WARPS - 1) / T4_WARPS];
+        make_state(nraw, nst);
+        __syncthreads();
+        double rew = 0.0, info5[5] = {0, 0, 0, 0, 0};
+        if (w0) {
+            // sums in body order b = 1.. so the result does not depend on the warp split: re-add per warp share
+            pose2 = x.at(O.red, 0) + x.at(O.red, 2) + x.at(O.red, 4) + x.at(O.red, 6);
+            vd = x.at(O.red, 1) + x.at(O.red, 3) + x.at(O.red, 5) + x.at(O.red, 7);
+            double q7[7];
+            for (int k = 0; k < 7; k++) q7[k] = x.at(O.q, k);
+            double lin[3], qi[4], qrel[4], axis[3], ang, rv[3], fdl[3], fda[3];
+            for (int k = 0; k < 3; k++) lin[k] = (q7[k] - prev_root[k]) / dt;
+            quat_inv(prev_root + 3, qi);
+            quat_mul(q7 + 3, qi, qrel);
+            rot_from_quat(qrel, axis, &ang);
+            if (1.0 - qrel[0] < 1e-8) axis[0] = 1.0;
+            if (ang > M_PI) ang -= 2 * M_PI; else if (ang < -M_PI) ang += 2 * M_PI;
+            for (int k = 0; k < 3; k++) rv[k] = (axis[k] * ang) / dt;
+            to_root(rv, prev_root + 3, fda);
+            to_heading(lin, prev_root + 3, fdl);
+            double rq[4];
+            de_heading(q7 + 3, rq);
+            double e2 = 0.0;
+            for (int k = 0; k < EGP_NEE; k++) {
+                const int xk = c_m.ee_xp_slot[k];
+                double vv[3] = {x.at(O.xp, 3 * xk) - q7[0], x.at(O.xp, 3 * xk + 1) - q7[1], x.at(O.xp, 3 * xk + 2) - q7[2]}, ee[3];
+                to_heading(vv, q7 + 3, ee);
+                for (int r = 0; r < 3; r++) { double df = ee[r] - row[EGP_X_EE_POS + 3 * k + r]; e2 += df * df; }
+            }
+            double pose_dist = sqrt(pose2), vel_dist = c_m.v_ord == 1 ? vd : sqrt(vd), ee_dist = sqrt(e2);
+            info5[0] = exp(-c_m.k_p * (pose_dist * pose_dist));
+            info5[1] = exp(-c_m.k_v * (vel_dist * vel_dist));
+            info5[2] = exp(-c_m.k_e * (ee_dist * ee_dist));
+            double hd2 = q7[2] - row[EGP_X_QPOS + 2], q1[4], qd[4];
+            quat_inv(row + EGP_X_RQ_RMH, q1);
+            quat_mul(rq, q1, qd);
+            double rqd = acos(fmin(fmax(qd[0], -1.0), 1.0));
+            info5[3] = exp(-c_m.k_rh * (hd2 * hd2) - c_m.k_rq * (rqd * rqd));
+            double l2 = 0.0, a2 = 0.0;
+            for (int k = 0; k < 3; k++) {
+                double dl = fdl[k] - row[EGP_X_RLINV_LOCAL + k], da = fda[k] - row[EGP_X_RANGV + k];
+                l2 += dl * dl; a2 += da * da;
+            }
+            double ld = sqrt(l2), ad = sqrt(a2);
+            info5[4] = exp(-c_m.k_rl * (ld * ld) - c_m.k_ra * (ad * ad));
+            rew = c_m.w_p * info5[0] + c_m.w_v * info5[1] + c_m.w_e * info5[2] + c_m.w_rp * info5[3] + c_m.w_rv * info5[4];
+            rew /= c_m.w_p + c_m.w_v + c_m.w_e + c_m.w_rp + c_m.w_rv;
+            if (c_m.decay) rew *= 1.0 - (double)cur_t / A.cfg.episode_len;
+            if (end) rew += A.cfg.end_reward;
+        }
+        // NaN guard (mj_checkPos/Vel analogue): every warp checks its share, warp 0 adds the reward
+        bool bad = !isfinite(head_z) || (w0 && !isfinite(rew));
+        { int s = 0; for (int k = w; k < S && !bad; k += T4_WARPS, s++) bad = !(fabs(nraw[s]) < 1e10); }
+        __syncthreads();
+        x.at(O.red, w) = bad ? 1.0 : 0.0;
+        __syncthreads();
+        bad = (x.at(O.red, 0) + x.at(O.red, 1) + x.at(O.red, 2) + x.at(O.red, 3)) > 0.0;
+        if (bad) {
+            rew = 0.0; fail = true;
+            for (int k = 0; k < 5; k++) info5[k] = 0.0;
+            int s = 0;
+            for (int k = w; k < S; k += T4_WARPS, s++) nst[s] = 0.0;
+            if (w0) log_acc[EGP_LOG_NUM_NAN_RESETS] += 1.0;
+        }
+        const bool done = fail || end;
+        if (live) {
+            if (A.out.d_next_states) { int s = 0; for (int k = w; k < S; k += T4_WARPS, s++) A.out.d_next_states[n * S + k] = nst[s]; }
+            if (w0) {
+                A.out.d_rewards[n] = rew;
+                A.out.d_masks[n] = (done || t == T - 1) ? 0.0 : 1.0;
+                A.out.d_exps[n] = mean_flag ? 0.0 : 1.0;
+                A.out.d_v_metas[2 * n] = take;
+                A.out.d_v_metas[2 * n + 1] = start;
+                if (A.out.d_c_info) for (int k = 0; k < 5; k++) A.out.d_c_info[n * 5 + k] = info5[k];
+            }
+        }
+        if (w0) {
+            ep_reward += 1.0;
+            log_acc[EGP_LOG_NUM_STEPS] += 1.0;
+            log_acc[EGP_LOG_TOTAL_C_REWARD] += rew;
+            log_acc[EGP_LOG_MIN_C_REWARD] = fmin(log_acc[EGP_LOG_MIN_C_REWARD], rew);
+            log_acc[EGP_LOG_MAX_C_REWARD] = fmax(log_acc[EGP_LOG_MAX_C_REWARD], rew);
+            for (int k = 0; k < 5; k++) log_acc[EGP_LOG_C_INFO + k] += info5[k];
+            if (done || t == T - 1) {
+                log_acc[EGP_LOG_NUM_EPISODES] += 1.0;
+                log_acc[EGP_LOG_TOTAL_REWARD] += ep_reward;
+                log_acc[EGP_LOG_MIN_EPISODE_REWARD] = fmin(log_acc[EGP_LOG_MIN_EPISODE_REWARD], ep_reward);
+                log_acc[EGP_LOG_MAX_EPISODE_REWARD] = fmax(log_acc[EGP_LOG_MAX_EPISODE_REWARD], ep_reward);
+                ep_reward = 0.0;
+            }
+        }
+        // per-lane reset decisions differ across lanes but are identical across the 4 warps of a lane;
+        // the tree sweeps contain CTA barriers, so every lane runs the reset sweep and commits selectively
+        const bool need_reset = done && t < T - 1;
+        const int any_reset = __syncthreads_or(need_reset ? 1 : 0);
+        if (any_reset) {
+            // park the continuing lanes' state, run reset + forward for all lanes, then restore the parked ones
+            double keep_q[MAXV + 1], keep_v[MAXV];
+            if (!need_reset) {
+                T4_FOR_OWN_DOFS(i, b) { keep_v[i] = x.at(O.v, i); if (i >= 6) keep_q[i + 1] = x.at(O.q, i + 1); }
+                if (c_m.chain_warp[0] == w) for (int k = 0; k < 7; k++) keep_q[k] = x.at(O.q, k);
+            }
+            T4Local *lp = &l;
+            // continuing lanes must keep their stale tree data: snapshot what forward_only overwrites
+            double k_cin[MAXB][10], k_C[MAXV], k_ax[MAXV][3], k_anc[MAXB][3], k_bqc[MAXB][4], k_xp[3 * (EGP_NEE + 1)];
+            if (!need_reset) {
+                T4_FOR_OWN_DOFS(i, b) { k_C[i] = lp->C[i]; for (int r = 0; r < 3; r++) k_ax[i][r] = x.at(O.ax, 3 * i + r); }
+                for (int c = 0; c < c_m.nchain; c++)
+                    if (c_m.chain_warp[c] == w)
+                        for (int b = c_m.chain_lo[c]; b <= c_m.chain_hi[c]; b++) {
+                            for (int r = 0; r < 10; r++) k_cin[b][r] = lp->cin[b][r];
+                            for (int r = 0; r < 3; r++) k_anc[b][r] = x.at(O.anc, 3 * b + r);
+                        }
+                for (int b = 1 + w; b < nb; b += T4_WARPS) for (int k = 0; k < 4; k++) k_bqc[b][k] = lp->bqc[b][k];
+                if (w0) for (int k = 0; k < 3 * (EGP_NEE + 1); k++) k_xp[k] = x.at(O.xp, k);
+            }
+            int take_new = take, start_new = start;
+            if (need_reset) { n_reset++; draw_reset(n_reset); take_new = take; start_new = start; cur_t = 0; }
+            __syncthreads();
+            if (need_reset) {
+                const double *r0 = A.rows + (size_t)(A.take_off[take_new] + start_new) * EGP_X_STRIDE;
+                T4_FOR_OWN_DOFS(i, b) {
+                    x.at(O.v, i) = r0[EGP_X_QVEL + i];
+                    if (i >= 6) x.at(O.q, i + 1) = r0[EGP_X_QPOS + i + 1];
+                }
+                if (c_m.chain_warp[0] == w) for (int k = 0; k < 7; k++) x.at(O.q, k) = r0[EGP_X_QPOS + k];
+            }
+            __syncthreads();
+            t4_forward_only(x, l);
+            if (need_reset) {
+                for (int b = 1 + w; b < nb; b += T4_WARPS) {
+                    const int qa = c_m.body_qposadr[b], nd = c_m.body_dofnum[b];
+                    quat_from_euler(x.at(O.q, qa), nd > 1 ? x.at(O.q, qa + 1) : 0.0, nd > 2 ? x.at(O.q, qa + 2) : 0.0, l.bqc[b]);
+                }
+                make_state(raw, st);
+            } else {
+                T4_FOR_OWN_DOFS(i, b) { lp->C[i] = k_C[i]; for (int r = 0; r < 3; r++) x.at(O.ax, 3 * i + r) = k_ax[i][r]; }
+                for (int c = 0; c < c_m.nchain; c++)
+                    if (c_m.chain_warp[c] == w)
+                        for (int b = c_m.chain_lo[c]; b <= c_m.chain_hi[c]; b++) {
+                            for (int r = 0; r < 10; r++) lp->cin[b][r] = k_cin[b][r];
+                            for (int r = 0; r < 3; r++) x.at(O.anc, 3 * b + r) = k_anc[b][r];
+                        }
+                for (int b = 1 + w; b < nb; b += T4_WARPS) for (int k = 0; k < 4; k++) lp->bqc[b][k] = k_bqc[b][k];
+                if (w0) for (int k = 0; k < 3 * (EGP_NEE + 1); k++) x.at(O.xp, k) = k_xp[k];
+                int s = 0;
+                for (int k = w; k < S; k += T4_WARPS, s++) { st[s] = nst[s]; raw[s] = nraw[s]; }
+                (void)keep_q; (void)keep_v;
+            }
+        } else {
+            int s = 0;
+            for (int k = w; k < S; k += T4_WARPS, s++) { st[s] = nst[s]; raw[s] = nraw[s]; }
+        }
+        __syncthreads();
+    }
+    if (live) {
+        if (A.out.d_final_qpos) for (int k = w; k < nq; k += T4_WARPS) A.out.d_final_qpos[(size_t)env * nq + k] = x.at(O.q, k);
+        if (A.out.d_final_qvel) for (int k = w; k < nv; k += T4_WARPS) A.out.d_final_qvel[(size_t)env * nv + k] = x.at(O.v, k);
+        if (A.out.d_logger && w0) {
+            double *Lg = A.out.d_logger;
+            atomicAdd(Lg + EGP_LOG_NUM_STEPS, log_acc[EGP_LOG_NUM_STEPS]);
+            atomicAdd(Lg + EGP_LOG_NUM_EPISODES, log_acc[EGP_LOG_NUM_EPISODES]);
+            atomicAdd(Lg + EGP_LOG_TOTAL_REWARD, log_acc[EGP_LOG_TOTAL_REWARD]);
+            atomicAdd(Lg + EGP_LOG_TOTAL_C_REWARD, log_acc[EGP_LOG_TOTAL_C_REWARD]);
+            atomicAdd(Lg + EGP_LOG_NUM_NAN_RESETS, log_acc[EGP_LOG_NUM_NAN_RESETS]);
+            for (int k = 0; k < 5; k++) atomicAdd(Lg + EGP_LOG_C_INFO + k, log_acc[EGP_LOG_C_INFO + k]);
+            auto amin = [](double *addr, double v) {
+                unsigned long long *a = (unsigned long long *)addr, old = *a, assumed;
+                do { assumed = old; if (__longlong_as_double(assumed) <= v) break;
+                     old = atomicCAS(a, assumed, __double_as_longlong(v)); } while (assumed != old);
+            };
+            auto amax = [](double *addr, double v) {
+                unsigned long long *a = (unsigned long long *)addr, old = *a, assumed;
+                do { assumed = old; if (__longlong_as_double(assumed) >= v) break;
+                     old = atomicCAS(a, assumed, __double_as_longlong(v)); } while (assumed != old);
+            };
+            amin(Lg + EGP_LOG_MIN_C_REWARD, log_acc[EGP_LOG_MIN_C_REWARD]);
+            amax(Lg + EGP_LOG_MAX_C_REWARD, log_acc[EGP_LOG_MAX_C_REWARD]);
+            amin(Lg + EGP_LOG_MIN_EPISODE_REWARD, log_acc[EGP_LOG_MIN_EPISODE_REWARD]);
+            amax(Lg + EGP_LOG_MAX_EPISODE_REWARD, log_acc[EGP_LOG_MAX_EPISODE_REWARD]);
+        }
+    }
+}
+
 // transposes W [out][in] -> Wt [in][outp] (zero padded), biases padded
 __global__ void transpose_pad_kernel(const double *__restrict__ W, const double *__restrict__ b, int out, int in, int outp,
                                      double *__restrict__ Wt, double *__restrict__ bp) {
@@ -944,6 +1695,48 @@ static void build_chains(DevModel &d) {
         d.body_chain[b] = nc - 1;
     }
     d.nchain = nc;
+    // ---- T4 schedule
+    int cchild[MAXC] = {0}, per_level_parents[MAXC] = {0}, per_level_count[MAXC] = {0};
+    d.nlevel = 0; d.nparent = 0; d.max_sib = 0; d.t4_ok = 1;
+    for (int c = 0; c < nc; c++) {
+        d.chain_level[c] = d.chain_parent[c] >= 0 ? d.chain_level[d.chain_parent[c]] + 1 : 0;
+        if (d.chain_level[c] + 1 > d.nlevel) d.nlevel = d.chain_level[c] + 1;
+        d.chain_cslot[c] = d.chain_parent[c] >= 0 ? cchild[d.chain_parent[c]]++ : -1;
+    }
+    for (int c = 0; c < nc; c++) {
+        d.chain_nchild[c] = cchild[c];
+        d.chain_pslot[c] = cchild[c] > 0 ? d.nparent++ : -1;
+        if (cchild[c] > d.max_sib) d.max_sib = cchild[c];
+        if (cchild[c] > 0) per_level_parents[d.chain_level[c]]++;
+    }
+    // per level: longest chain to warp 0, next to warp 1, ... (one chain per warp per level)
+    for (int L = 0; L < d.nlevel; L++) {
+        int order[MAXC], n = 0;
+        for (int c = 0; c < nc; c++) if (d.chain_level[c] == L) order[n++] = c;
+        auto ndof = [&](int c) { return d.body_dofadr[d.chain_hi[c]] + d.body_dofnum[d.chain_hi[c]] - d.body_dofadr[d.chain_lo[c]]; };
+        for (int a = 0; a < n; a++) for (int b2 = a + 1; b2 < n; b2++) {
+            // parents first (the trunk continues on warp 0), then by length
+            bool swap = (cchild[order[b2]] > 0 && cchild[order[a]] == 0) ||
+                        ((cchild[order[b2]] > 0) == (cchild[order[a]] > 0) && ndof(order[b2]) > ndof(order[a]));
+            if (swap) { int t = order[a]; order[a] = order[b2]; order[b2] = t; }
+        }
+        per_level_count[L] = n;
+        for (int a = 0; a < n; a++) d.chain_warp[order[a]] = a % 4;
+        if (n > 4 || per_level_parents[L] > 1) d.t4_ok = 0;
+    }
+    // every hinge of a body must share one anchor (the shared rows keep one anchor per body)
+    for (int b = 1; b < nb; b++)
+        for (int j = 1; j < d.body_dofnum[b]; j++)
+            for (int k = 0; k < 3; k++)
+                if (d.dof_anchor[d.body_dofadr[b] + j][k] != d.dof_anchor[d.body_dofadr[b]][k]) d.t4_ok = 0;
+    for (int b = 0; b < nb; b++) d.body_xp_slot[b] = -1;
+    int nslot = 0;
+    for (int k = 0; k < EGP_NEE; k++) {
+        if (d.body_xp_slot[d.ee_body[k]] < 0) d.body_xp_slot[d.ee_body[k]] = nslot++;
+        d.ee_xp_slot[k] = d.body_xp_slot[d.ee_body[k]];
+    }
+    if (d.body_xp_slot[d.head_body] < 0) d.body_xp_slot[d.head_body] = nslot++;
+    d.head_xp_slot = d.body_xp_slot[d.head_body];
 }
 
 }  // namespace egp
@@ -1141,10 +1934,25 @@ int egp_rollout_f64(EgpModel *m, const EgpPolicyWeights *pol, const EgpRolloutCf
     }
     int xrows = A.D > A.H2p ? A.D : A.H2p;
     int hrows = A.H1p > A.Ap ? A.H1p : A.Ap;
+    int blocks = (cfg->n_env + ENVS_PER_CTA - 1) / ENVS_PER_CTA;
+    // variant selection: T4 (4 warps per 32 envs, tree data in shared memory) when the model and the policy
+    // width fit, else the one-warp V1 kernel; EGP_ROLLOUT_VARIANT=1 forces V1 (A/B parity runs)
+    T4Off O;
+    O.q = 0; O.v = O.q + d.nq; O.ax = O.v + d.nv; O.anc = O.ax + 3 * d.nv; O.U = O.anc + 3 * d.nbody;
+    O.jf = O.U + 6 * d.nv; O.jb = O.jf + 24 * d.nparent; O.ja = O.jb + 33 * d.max_sib; O.xp = O.ja + 6 * d.nparent;
+    O.red = O.xp + 3 * (EGP_NEE + 1); O.total = O.red + 8;
+    size_t smem4 = sizeof(double) * 32 * (size_t)O.total;
+    const char *force = getenv("EGP_ROLLOUT_VARIANT");
+    bool use_t4 = d.t4_ok && xrows + hrows <= O.jf - O.ax && smem4 <= 227 * 1024 && !(force && force[0] == '1');
+    if (use_t4) {
+        EGP_CUDA(cudaFuncSetAttribute(rollout_kernel_t4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+        rollout_kernel_t4<<<blocks, T4_THREADS, smem4, st>>>(A, O);
+        EGP_CHECK_LAUNCH("rollout_kernel_t4");
+        return EGP_OK;
+    }
     size_t smem = sizeof(double) * ENVS_PER_CTA * ((size_t)xrows + hrows);
     if (smem > 227 * 1024) { set_error("egp_rollout_f64: policy too wide for shared memory (%zu bytes)", smem); return EGP_ESIZE; }
     EGP_CUDA(cudaFuncSetAttribute(rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int blocks = (cfg->n_env + ENVS_PER_CTA - 1) / ENVS_PER_CTA;
     rollout_kernel<<<blocks, ENVS_PER_CTA, smem, st>>>(A);
     EGP_CHECK_LAUNCH("rollout_kernel");
     return EGP_OK;

@@ -88,3 +88,26 @@ def test_rollout_philox_mode_properties():
     z = ((a['actions'] - d['actions']).view(96, 20, nu)[:, 0] / (np.exp(-2.3) * np.sqrt(2))).cpu().numpy()
     assert abs(z.mean()) < 0.1 and abs(z.std() - 1.0) < 0.1
     model.close()
+
+
+def test_rollout_variants_agree():
+    """T4 (4 warps / 32 envs, shared-memory tree data) and V1 (1 warp) kernels give the same trajectories"""
+    import os
+    orc, model = _setup(3, 64, 8, seed=11)
+    S, nu = orc.S, orc.nu
+    w = helpers.policy_weights(S + 8, 64, 48, nu, seed=2)
+    wd = {k: cu(v.ravel() if k == 'log_std' else v) for k, v in w.items()}
+    outs = []
+    for variant in ('0', '1'):
+        os.environ['EGP_ROLLOUT_VARIANT'] = variant
+        o = model.rollout(wd, 70, 25, episode_len=12, seed=3, iteration=1, end_reward=0.2)
+        torch.cuda.synchronize()
+        outs.append({k: v.clone() for k, v in o.items()})
+    os.environ.pop('EGP_ROLLOUT_VARIANT')
+    a, b = outs
+    assert torch.equal(a['masks'], b['masks']) and torch.equal(a['v_metas'], b['v_metas'])
+    for k in ('states', 'actions', 'next_states', 'rewards', 'c_info', 'final_qpos', 'final_qvel', 'raw_obs'):
+        assert helpers.relerr(a[k].cpu().numpy(), b[k].cpu().numpy()) < 1e-7, k
+    la, lb = a['logger'].cpu().numpy(), b['logger'].cpu().numpy()
+    assert np.allclose(la, lb, rtol=1e-7, atol=1e-9)
+    model.close()
