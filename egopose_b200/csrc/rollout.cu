@@ -1943,7 +1943,7 @@ int egp_rollout_f64(EgpModel *m, const EgpPolicyWeights *pol, const EgpRolloutCf
     O.red = O.xp + 3 * (EGP_NEE + 1); O.total = O.red + 8;
     size_t smem4 = sizeof(double) * 32 * (size_t)O.total;
     const char *force = getenv("EGP_ROLLOUT_VARIANT");
-    bool use_t4 = d.t4_ok && xrows + hrows <= O.jf - O.ax && smem4 <= 227 * 1024 && !(force && force[0] == '1');
+    bool use_t4 = d.t4_ok && xrows + hrows <= O.total - O.ax && smem4 <= 227 * 1024 && !(force && force[0] == '1');
     if (use_t4) {
         EGP_CUDA(cudaFuncSetAttribute(rollout_kernel_t4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
         rollout_kernel_t4<<<blocks, T4_THREADS, smem4, st>>>(A, O);
