@@ -594,6 +594,7 @@ struct RolloutArgs {
     // policy (transposed + padded): W1t [D][H1p], W2t [H1][H2p], W3t [H2][Ap]
     const double *W1t, *b1, *W2t, *b2, *W3t, *b3, *log_std;
     int D, H1, H2, A, H1p, H2p, Ap;
+    int K1p, K2p, K3p;      // T4: k padded to MLP_KC (weights packed as tiles)
 };
 
 // one dense layer for the 32 environments of the CTA: ys[j][lane] = act(b[j] + sum_k Wt[k][j] xs[k][lane])
@@ -1173,26 +1174,63 @@ __device__ __forceinline__ double t4_obs_entry(const T4Ctx &x, int k, const doub
     return x.at(x.o.v, j);
 }
 
+// One dense layer for the CTA's 32 environments, split over the 4 warps by 8-neuron blocks.  Weights come
+// packed as tiles Wp[block][k][8] (k padded to MLP_KC); each warp streams its tiles HBM/L2 -> registers
+// (coalesced 128-bit loads, issued one tile ahead) -> its private shared-memory tile -> broadcast LDS, so the
+// inner loop is FP64-pipe bound instead of waiting on warp-uniform global loads.
+constexpr int MLP_KC = 64;
+constexpr int MLP_TILE = MLP_KC * JB;        // doubles per tile
+
 template <bool RELU>
-__device__ __forceinline__ void t4_mlp_layer(const double *__restrict__ Wt, const double *__restrict__ bias, int K, int Np,
-                                             const double *xs, double *ys, int lane, int w) {
-    for (int j0 = w * JB; j0 < Np; j0 += T4_WARPS * JB) {
-        double acc[JB];
+__device__ __forceinline__ void t4_mlp_layer(const double *__restrict__ Wp, const double *__restrict__ bias, int K, int Kp,
+                                             int Np, const double *xs, double *ys, double *stage, int lane, int w) {
+    const int nchunk = Kp / MLP_KC, njb = Np / JB;
+    const int my_blocks = (njb - w + T4_WARPS - 1) / T4_WARPS;
+    const int ntile = my_blocks * nchunk;
+    if (ntile <= 0) return;
+    double2 pre[MLP_TILE / 64];                                      // this lane's share of the tile in flight
+    auto tile_ptr = [&](int t) {
+        const int jb = w + T4_WARPS * (t / nchunk), c = t % nchunk;
+        return reinterpret_cast<const double2 *>(Wp + ((size_t)jb * Kp + (size_t)c * MLP_KC) * JB);
+    };
+    {
+        const double2 *src = tile_ptr(0);
 #pragma unroll
-        for (int jj = 0; jj < JB; jj++) acc[jj] = bias[j0 + jj];
-#pragma unroll 2
-        for (int k = 0; k < K; k++) {
-            const double xv = xs[k * 32 + lane];
-            const double2 *wp = reinterpret_cast<const double2 *>(Wt + (size_t)k * Np + j0);
+        for (int m = 0; m < MLP_TILE / 64; m++) pre[m] = __ldg(src + lane + 32 * m);
+    }
+    double acc[JB];
+    double2 *st2 = reinterpret_cast<double2 *>(stage);
+    for (int t = 0; t < ntile; t++) {
+        const int jb = w + T4_WARPS * (t / nchunk), c = t % nchunk;
+        if (c == 0) {
+#pragma unroll
+            for (int jj = 0; jj < JB; jj++) acc[jj] = bias[jb * JB + jj];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < MLP_TILE / 64; m++) st2[lane + 32 * m] = pre[m];
+        __syncwarp();
+        if (t + 1 < ntile) {
+            const double2 *src = tile_ptr(t + 1);
+#pragma unroll
+            for (int m = 0; m < MLP_TILE / 64; m++) pre[m] = __ldg(src + lane + 32 * m);
+        }
+        const int k0 = c * MLP_KC;
+        const int kn = K - k0 < MLP_KC ? K - k0 : MLP_KC;
+#pragma unroll 4
+        for (int kk = 0; kk < kn; kk++) {
+            const double xv = xs[(k0 + kk) * 32 + lane];
 #pragma unroll
             for (int jj = 0; jj < JB / 2; jj++) {
-                double2 ww = __ldg(wp + jj);
+                const double2 ww = st2[kk * (JB / 2) + jj];
                 acc[2 * jj] += ww.x * xv;
                 acc[2 * jj + 1] += ww.y * xv;
             }
         }
+        if (c == nchunk - 1) {
 #pragma unroll
-        for (int jj = 0; jj < JB; jj++) ys[(j0 + jj) * 32 + lane] = RELU ? fmax(acc[jj], 0.0) : acc[jj];
+            for (int jj = 0; jj < JB; jj++) ys[(jb * JB + jj) * 32 + lane] = RELU ? fmax(acc[jj], 0.0) : acc[jj];
+        }
     }
 }
 
@@ -1206,6 +1244,8 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
     double *xs = smem + (size_t)O.ax * 32;               // MLP activations alias the axis / anchor / U rows
     const int xrows = A.D > A.H2p ? A.D : A.H2p;
     double *h1s = xs + (size_t)xrows * 32;
+    const int hrows4 = A.H1p > A.Ap ? A.H1p : A.Ap;
+    double *stage = h1s + (size_t)hrows4 * 32 + (size_t)w * MLP_TILE;   // per-warp weight tile
     const int T = A.cfg.horizon, E = A.cfg.n_env;
     const double dt = c_m.h * c_m.frame_skip;
     const int env = blockIdx.x * 32 + lane;
@@ -1303,11 +1343,11 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
             }
         }
         __syncthreads();
-        t4_mlp_layer<true>(A.W1t, A.b1, A.D, A.H1p, xs, h1s, lane, w);
+        t4_mlp_layer<true>(A.W1t, A.b1, A.D, A.K1p, A.H1p, xs, h1s, stage, lane, w);
         __syncthreads();
-        t4_mlp_layer<true>(A.W2t, A.b2, A.H1, A.H2p, h1s, xs, lane, w);
+        t4_mlp_layer<true>(A.W2t, A.b2, A.H1, A.K2p, A.H2p, h1s, xs, stage, lane, w);
         __syncthreads();
-        t4_mlp_layer<false>(A.W3t, A.b3, A.H2, A.Ap, xs, h1s, lane, w);
+        t4_mlp_layer<false>(A.W3t, A.b3, A.H2, A.K3p, A.Ap, xs, h1s, stage, lane, w);
         __syncthreads();
         bool mean_flag = A.cfg.mean_action != 0;
         if (A.in.d_mean_flag) mean_flag = mean_flag || A.in.d_mean_flag[n] != 0;
@@ -1565,6 +1605,17 @@ __global__ void transpose_pad_kernel(const double *__restrict__ W, const double 
     if (idx < in * outp) {
         int k = idx / outp, j = idx % outp;
         Wt[idx] = j < out ? W[(size_t)j * in + k] : 0.0;
+    }
+    if (idx < outp) bp[idx] = idx < out ? b[idx] : 0.0;
+}
+
+// packs W [out][in] -> tiles Wp[out/8][inp][8] (zero padded both ways), biases padded (T4 MLP)
+__global__ void pack_tiles_kernel(const double *__restrict__ W, const double *__restrict__ b, int out, int in, int outp,
+                                  int inp, double *__restrict__ Wp, double *__restrict__ bp) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < inp * outp) {
+        int jb = idx / (inp * JB), rem = idx % (inp * JB), k = rem / JB, jj = rem % JB, j = jb * JB + jj;
+        Wp[idx] = (j < out && k < in) ? W[(size_t)j * in + k] : 0.0;
     }
     if (idx < outp) bp[idx] = idx < out ? b[idx] : 0.0;
 }
@@ -1907,31 +1958,6 @@ int egp_rollout_f64(EgpModel *m, const EgpPolicyWeights *pol, const EgpRolloutCf
     A.n_takes = m->n_takes; A.ctx_dim = m->ctx_dim;
     A.D = pol->in_dim; A.H1 = pol->h1; A.H2 = pol->h2; A.A = pol->out_dim;
     A.H1p = pad(A.H1); A.H2p = pad(A.H2); A.Ap = pad(A.A);
-    size_t need = (size_t)A.D * A.H1p + A.H1p + (size_t)A.H1 * A.H2p + A.H2p + (size_t)A.H2 * A.Ap + A.Ap;
-    if (need > m->wbuf_elems) {
-        cudaFree(m->d_wbuf);
-        m->d_wbuf = nullptr; m->wbuf_elems = 0;
-        EGP_CUDA(cudaMalloc(&m->d_wbuf, sizeof(double) * need));
-        m->wbuf_elems = need;
-    }
-    double *w = m->d_wbuf;
-    double *W1t = w; w += (size_t)A.D * A.H1p;
-    double *b1 = w; w += A.H1p;
-    double *W2t = w; w += (size_t)A.H1 * A.H2p;
-    double *b2 = w; w += A.H2p;
-    double *W3t = w; w += (size_t)A.H2 * A.Ap;
-    double *b3 = w;
-    transpose_pad_kernel<<<(A.D * A.H1p + 255) / 256, 256, 0, st>>>(pol->d_W1, pol->d_b1, A.H1, A.D, A.H1p, W1t, b1);
-    transpose_pad_kernel<<<(A.H1 * A.H2p + 255) / 256, 256, 0, st>>>(pol->d_W2, pol->d_b2, A.H2, A.H1, A.H2p, W2t, b2);
-    transpose_pad_kernel<<<(A.H2 * A.Ap + 255) / 256, 256, 0, st>>>(pol->d_W3, pol->d_b3, A.A, A.H2, A.Ap, W3t, b3);
-    EGP_CHECK_LAUNCH("transpose_pad_kernel");
-    A.W1t = W1t; A.b1 = b1; A.W2t = W2t; A.b2 = b2; A.W3t = W3t; A.b3 = b3; A.log_std = pol->d_log_std;
-    if (out->d_logger) {
-        double init[EGP_LOG_SIZE] = {0};
-        init[EGP_LOG_MIN_C_REWARD] = INFINITY; init[EGP_LOG_MAX_C_REWARD] = -INFINITY;
-        init[EGP_LOG_MIN_EPISODE_REWARD] = INFINITY; init[EGP_LOG_MAX_EPISODE_REWARD] = -INFINITY;
-        EGP_CUDA(cudaMemcpyAsync(out->d_logger, init, sizeof init, cudaMemcpyHostToDevice, st));
-    }
     int xrows = A.D > A.H2p ? A.D : A.H2p;
     int hrows = A.H1p > A.Ap ? A.H1p : A.Ap;
     int blocks = (cfg->n_env + ENVS_PER_CTA - 1) / ENVS_PER_CTA;
@@ -1941,9 +1967,45 @@ int egp_rollout_f64(EgpModel *m, const EgpPolicyWeights *pol, const EgpRolloutCf
     O.q = 0; O.v = O.q + d.nq; O.ax = O.v + d.nv; O.anc = O.ax + 3 * d.nv; O.U = O.anc + 3 * d.nbody;
     O.jf = O.U + 6 * d.nv; O.jb = O.jf + 24 * d.nparent; O.ja = O.jb + 33 * d.max_sib; O.xp = O.ja + 6 * d.nparent;
     O.red = O.xp + 3 * (EGP_NEE + 1); O.total = O.red + 8;
+    const int stage_rows = T4_WARPS * MLP_TILE / 32;
+    if (O.total - O.ax < xrows + hrows + stage_rows && O.ax + xrows + hrows + stage_rows <= 227 * 1024 / 256)
+        O.total = O.ax + xrows + hrows + stage_rows;        // grow the layout up to the shared-memory limit
     size_t smem4 = sizeof(double) * 32 * (size_t)O.total;
     const char *force = getenv("EGP_ROLLOUT_VARIANT");
-    bool use_t4 = d.t4_ok && xrows + hrows <= O.total - O.ax && smem4 <= 227 * 1024 && !(force && force[0] == '1');
+    bool use_t4 = d.t4_ok && xrows + hrows + stage_rows <= O.total - O.ax && smem4 <= 227 * 1024 && !(force && force[0] == '1');
+    auto padk = [](int x) { return (x + MLP_KC - 1) / MLP_KC * MLP_KC; };
+    A.K1p = use_t4 ? padk(A.D) : A.D; A.K2p = use_t4 ? padk(A.H1) : A.H1; A.K3p = use_t4 ? padk(A.H2) : A.H2;
+    size_t need = (size_t)A.K1p * A.H1p + A.H1p + (size_t)A.K2p * A.H2p + A.H2p + (size_t)A.K3p * A.Ap + A.Ap;
+    if (need > m->wbuf_elems) {
+        cudaFree(m->d_wbuf);
+        m->d_wbuf = nullptr; m->wbuf_elems = 0;
+        EGP_CUDA(cudaMalloc(&m->d_wbuf, sizeof(double) * need));
+        m->wbuf_elems = need;
+    }
+    double *w = m->d_wbuf;
+    double *W1t = w; w += (size_t)A.K1p * A.H1p;
+    double *b1 = w; w += A.H1p;
+    double *W2t = w; w += (size_t)A.K2p * A.H2p;
+    double *b2 = w; w += A.H2p;
+    double *W3t = w; w += (size_t)A.K3p * A.Ap;
+    double *b3 = w;
+    if (use_t4) {
+        pack_tiles_kernel<<<(A.K1p * A.H1p + 255) / 256, 256, 0, st>>>(pol->d_W1, pol->d_b1, A.H1, A.D, A.H1p, A.K1p, W1t, b1);
+        pack_tiles_kernel<<<(A.K2p * A.H2p + 255) / 256, 256, 0, st>>>(pol->d_W2, pol->d_b2, A.H2, A.H1, A.H2p, A.K2p, W2t, b2);
+        pack_tiles_kernel<<<(A.K3p * A.Ap + 255) / 256, 256, 0, st>>>(pol->d_W3, pol->d_b3, A.A, A.H2, A.Ap, A.K3p, W3t, b3);
+    } else {
+        transpose_pad_kernel<<<(A.D * A.H1p + 255) / 256, 256, 0, st>>>(pol->d_W1, pol->d_b1, A.H1, A.D, A.H1p, W1t, b1);
+        transpose_pad_kernel<<<(A.H1 * A.H2p + 255) / 256, 256, 0, st>>>(pol->d_W2, pol->d_b2, A.H2, A.H1, A.H2p, W2t, b2);
+        transpose_pad_kernel<<<(A.H2 * A.Ap + 255) / 256, 256, 0, st>>>(pol->d_W3, pol->d_b3, A.A, A.H2, A.Ap, W3t, b3);
+    }
+    EGP_CHECK_LAUNCH("weight packing");
+    A.W1t = W1t; A.b1 = b1; A.W2t = W2t; A.b2 = b2; A.W3t = W3t; A.b3 = b3; A.log_std = pol->d_log_std;
+    if (out->d_logger) {
+        double init[EGP_LOG_SIZE] = {0};
+        init[EGP_LOG_MIN_C_REWARD] = INFINITY; init[EGP_LOG_MAX_C_REWARD] = -INFINITY;
+        init[EGP_LOG_MIN_EPISODE_REWARD] = INFINITY; init[EGP_LOG_MAX_EPISODE_REWARD] = -INFINITY;
+        EGP_CUDA(cudaMemcpyAsync(out->d_logger, init, sizeof init, cudaMemcpyHostToDevice, st));
+    }
     if (use_t4) {
         EGP_CUDA(cudaFuncSetAttribute(rollout_kernel_t4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
         rollout_kernel_t4<<<blocks, T4_THREADS, smem4, st>>>(A, O);
