@@ -50,6 +50,9 @@ struct DevModel {
     int chain_level[MAXC], chain_warp[MAXC], chain_pslot[MAXC], chain_cslot[MAXC], chain_nchild[MAXC];
     int nlevel, nparent, max_sib, t4_ok;
     int body_xp_slot[MAXB], ee_xp_slot[EGP_NEE], head_xp_slot;                // rows of the shared body-position record
+    // TMEM scratch layout (T4): index of a dof / body among those owned by the same warp, column bases (32-bit units)
+    int dof_slot[MAXV], body_slot[MAXB];
+    int tm_dinv, tm_u, tm_tau, tm_c, tm_cin, tm_fb, tm_cols;
     double w_p, w_v, w_e, w_rp, w_rv, k_p, k_v, k_e, k_rh, k_rq, k_rl, k_ra;
 };
 
@@ -827,17 +830,81 @@ constexpr int T4_THREADS = T4_WARPS * 32;
 struct T4Off { int q, v, ax, anc, U, jf, jb, ja, xp, red, total; };
 
 struct T4Local {
-    double cin[MAXB][10], fb[MAXB][6];
-    double Dinv[MAXV], u[MAXV], C[MAXV], tau[MAXV], ctrl[MAXV], x[MAXV];
+    double ctrl[MAXV], x[MAXV];
     double sav_ax[MAXV][3], sav_anc[MAXB][3];
     double bqp[MAXB][4], bqc[MAXB][4];
 };
 
+// ---- Tensor Memory as a per-thread scratchpad.  The kernel issues no tcgen05.mma, so the SM's 256 KB of
+// TMEM is free: each warp owns its 32-lane quarter, each thread gets 512 x 32-bit private columns (256
+// doubles) at ~12 cycles load latency - the values that round-trip between the tree sweeps (pivots, solve
+// right-hand sides, bias forces, body inertias) live there instead of in L2-backed thread-local memory.
+// All accesses are warp-uniform (tcgen05.ld/st are .sync.aligned).
+__device__ __forceinline__ void tm_st1(uint32_t a, double v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(a), "r"(__double2loint(v)), "r"(__double2hiint(v)) : "memory");
+}
+__device__ __forceinline__ double tm_ld1(uint32_t a) {
+    int lo, hi;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];\n\ttcgen05.wait::ld.sync.aligned;" : "=r"(lo), "=r"(hi) : "r"(a) : "memory");
+    return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tm_st2(uint32_t a, double v0, double v1) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(__double2loint(v0)), "r"(__double2hiint(v0)),
+                 "r"(__double2loint(v1)), "r"(__double2hiint(v1)) : "memory");
+}
+__device__ __forceinline__ void tm_ld2(uint32_t a, double &v0, double &v1) {
+    int r[4];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n\ttcgen05.wait::ld.sync.aligned;"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a) : "memory");
+    v0 = __hiloint2double(r[1], r[0]); v1 = __hiloint2double(r[3], r[2]);
+}
+__device__ __forceinline__ void tm_st4(uint32_t a, const double *v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(a),
+                 "r"(__double2loint(v[0])), "r"(__double2hiint(v[0])), "r"(__double2loint(v[1])), "r"(__double2hiint(v[1])),
+                 "r"(__double2loint(v[2])), "r"(__double2hiint(v[2])), "r"(__double2loint(v[3])), "r"(__double2hiint(v[3])) : "memory");
+}
+__device__ __forceinline__ void tm_ld4(uint32_t a, double *v) {
+    int r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n\ttcgen05.wait::ld.sync.aligned;"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(a) : "memory");
+#pragma unroll
+    for (int k = 0; k < 4; k++) v[k] = __hiloint2double(r[2 * k + 1], r[2 * k]);
+}
+__device__ __forceinline__ void tm_st8(uint32_t a, const double *v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(a),
+                 "r"(__double2loint(v[0])), "r"(__double2hiint(v[0])), "r"(__double2loint(v[1])), "r"(__double2hiint(v[1])),
+                 "r"(__double2loint(v[2])), "r"(__double2hiint(v[2])), "r"(__double2loint(v[3])), "r"(__double2hiint(v[3])),
+                 "r"(__double2loint(v[4])), "r"(__double2hiint(v[4])), "r"(__double2loint(v[5])), "r"(__double2hiint(v[5])),
+                 "r"(__double2loint(v[6])), "r"(__double2hiint(v[6])), "r"(__double2loint(v[7])), "r"(__double2hiint(v[7])) : "memory");
+}
+__device__ __forceinline__ void tm_ld8(uint32_t a, double *v) {
+    int r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
+                 "tcgen05.wait::ld.sync.aligned;"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(a) : "memory");
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] = __hiloint2double(r[2 * k + 1], r[2 * k]);
+}
+
 struct T4Ctx {
     double *sm;
     int lane, w;
+    uint32_t tm;        // TMEM base of this warp's lane quarter
     T4Off o;
     __device__ __forceinline__ double &at(int off, int idx) const { return sm[(size_t)(off + idx) * 32 + lane]; }
+    // TMEM column addresses
+    __device__ __forceinline__ uint32_t a_dinv(int i) const { return tm + c_m.tm_dinv + 2 * c_m.dof_slot[i]; }
+    __device__ __forceinline__ uint32_t a_u(int i) const { return tm + c_m.tm_u + 2 * c_m.dof_slot[i]; }
+    __device__ __forceinline__ uint32_t a_tau(int i) const { return tm + c_m.tm_tau + 2 * c_m.dof_slot[i]; }
+    __device__ __forceinline__ uint32_t a_c(int i) const { return tm + c_m.tm_c + 2 * c_m.dof_slot[i]; }
+    __device__ __forceinline__ uint32_t a_cin(int b) const { return tm + c_m.tm_cin + 20 * c_m.body_slot[b]; }
+    __device__ __forceinline__ uint32_t a_fb(int b) const { return tm + c_m.tm_fb + 12 * c_m.body_slot[b]; }
+    __device__ __forceinline__ void st_cin(int b, const double *ci) const { tm_st8(a_cin(b), ci); tm_st2(a_cin(b) + 16, ci[8], ci[9]); }
+    __device__ __forceinline__ void ld_cin(int b, double *ci) const { tm_ld8(a_cin(b), ci); tm_ld2(a_cin(b) + 16, ci[8], ci[9]); }
+    __device__ __forceinline__ void st_fb(int b, const double *f) const { tm_st4(a_fb(b), f); tm_st2(a_fb(b) + 8, f[4], f[5]); }
+    __device__ __forceinline__ void ld_fb(int b, double *f) const { tm_ld4(a_fb(b), f); tm_ld2(a_fb(b) + 8, f[4], f[5]); }
 };
 
 __device__ __forceinline__ int t4_my_chain(int level, int w) {
@@ -967,7 +1034,7 @@ __device__ void t4_kinematics(const T4Ctx &x, T4Local &l) {
                 Iw[4] = Tm[0] * f.R[6] + Tm[1] * f.R[7] + Tm[2] * f.R[8];
                 Iw[5] = Tm[3] * f.R[6] + Tm[4] * f.R[7] + Tm[5] * f.R[8];
                 const double mass = c_m.body_mass[b], cc2 = dot3(cpos, cpos);
-                double *ci = l.cin[b];
+                double ci[10];
                 ci[0] = mass;
                 ci[1] = mass * cpos[0]; ci[2] = mass * cpos[1]; ci[3] = mass * cpos[2];
                 ci[4] = Iw[0] + mass * (cc2 - cpos[0] * cpos[0]);
@@ -983,11 +1050,15 @@ __device__ void t4_kinematics(const T4Ctx &x, T4Local &l) {
                 cross3(f.v, Iv, c0);
                 cross3(f.v + 3, Iv + 3, c1);
                 cross3(f.v, Iv + 3, c2);
+                double fbv[6];
                 for (int r = 0; r < 3; r++) {
-                    l.fb[b][r] = Ia[r] + c0[r] + c1[r];
-                    l.fb[b][3 + r] = Ia[3 + r] + c2[r];
+                    fbv[r] = Ia[r] + c0[r] + c1[r];
+                    fbv[3 + r] = Ia[3 + r] + c2[r];
                 }
+                x.st_cin(b, ci);
+                x.st_fb(b, fbv);
             }
+            tm_wait_st();
             if (c_m.chain_pslot[c] >= 0) {
                 const int base = x.o.jf + 24 * c_m.chain_pslot[c];
 #pragma unroll
@@ -1023,24 +1094,29 @@ __device__ void t4_backward(const T4Ctx &x, T4Local &l) {
         __syncthreads();            // children records consumed before this level overwrites the slots
         if (c >= 0) {
             for (int b = c_m.chain_hi[c]; b >= c_m.chain_lo[c]; b--) {
-                const double *ci = l.cin[b];
+                double ci[10];
+                x.ld_cin(b, ci);
                 w.IA[sx(0, 0)] += ci[4]; w.IA[sx(1, 1)] += ci[5]; w.IA[sx(2, 2)] += ci[6];
                 w.IA[sx(0, 1)] += ci[7]; w.IA[sx(0, 2)] += ci[8]; w.IA[sx(1, 2)] += ci[9];
                 w.IA[sx(0, 4)] += -ci[3]; w.IA[sx(0, 5)] += ci[2];
                 w.IA[sx(1, 3)] += ci[3];  w.IA[sx(1, 5)] += -ci[1];
                 w.IA[sx(2, 3)] += -ci[2]; w.IA[sx(2, 4)] += ci[1];
                 w.IA[sx(3, 3)] += ci[0]; w.IA[sx(4, 4)] += ci[0]; w.IA[sx(5, 5)] += ci[0];
-                if (MODE == 0) for (int k = 0; k < 6; k++) w.F[k] += l.fb[b][k];
+                if (MODE == 0) {
+                    double fbv[6];
+                    x.ld_fb(b, fbv);
+                    for (int k = 0; k < 6; k++) w.F[k] += fbv[k];
+                }
                 const int da = c_m.body_dofadr[b], nd = c_m.body_dofnum[b];
                 for (int i = da + nd - 1; i >= da; i--) {
                     double S[6], U[6];
                     t4_load_S(x, i, b, S);
-                    double rhs;
+                    double rhs = tm_ld1(x.a_tau(i));
                     if (MODE == 0) {
                         double Ci = dot6(S, w.F);
-                        l.C[i] = Ci;
-                        rhs = l.tau[i] - Ci;
-                    } else rhs = l.tau[i];
+                        tm_st1(x.a_c(i), Ci);
+                        rhs -= Ci;
+                    }
 #pragma unroll
                     for (int r = 0; r < 6; r++) {
                         double t = 0.0;
@@ -1052,8 +1128,8 @@ __device__ void t4_backward(const T4Ctx &x, T4Local &l) {
                     if (MODE == 1) D += c_m.kd[i] * c_m.h;
                     const double Dinv = 1.0 / D;
                     const double ui = rhs - dot6(S, w.pA);
-                    l.Dinv[i] = Dinv;
-                    l.u[i] = ui;
+                    tm_st1(x.a_dinv(i), Dinv);
+                    tm_st1(x.a_u(i), ui);
 #pragma unroll
                     for (int r = 0; r < 6; r++) x.at(x.o.U, 6 * i + r) = U[r];
 #pragma unroll
@@ -1065,6 +1141,7 @@ __device__ void t4_backward(const T4Ctx &x, T4Local &l) {
                     }
                 }
             }
+            tm_wait_st();
             if (c_m.chain_parent[c] >= 0) {
                 const int base = x.o.jb + 33 * c_m.chain_cslot[c];
 #pragma unroll
@@ -1092,7 +1169,7 @@ __device__ void t4_accel(const T4Ctx &x, T4Local &l) {
                     t4_load_S(x, i, b, S);
 #pragma unroll
                     for (int r = 0; r < 6; r++) U[r] = x.at(x.o.U, 6 * i + r);
-                    const double xi = l.Dinv[i] * (l.u[i] - dot6(U, a));
+                    const double xi = tm_ld1(x.a_dinv(i)) * (tm_ld1(x.a_u(i)) - dot6(U, a));
                     l.x[i] = xi;
 #pragma unroll
                     for (int r = 0; r < 6; r++) a[r] += S[r] * xi;
@@ -1115,7 +1192,8 @@ __device__ void t4_accel(const T4Ctx &x, T4Local &l) {
 
 __device__ void t4_forward_only(const T4Ctx &x, T4Local &l) {      // sim.forward()
     t4_kinematics(x, l);
-    T4_FOR_OWN_DOFS(i, b) l.tau[i] = 0.0;
+    T4_FOR_OWN_DOFS(i, b) tm_st1(x.a_tau(i), 0.0);
+    tm_wait_st();
     t4_backward<0>(x, l);
 }
 
@@ -1123,8 +1201,9 @@ __device__ void t4_substep(const T4Ctx &x, T4Local &l) {
     const double h = c_m.h;
     T4_FOR_OWN_DOFS(i, b) {
         double eq = i >= 6 ? x.at(x.o.q, i + 1) - l.ctrl[i] : 0.0;
-        l.tau[i] = -l.C[i] - c_m.kp[i] * eq - c_m.kd[i] * x.at(x.o.v, i);
+        tm_st1(x.a_tau(i), -tm_ld1(x.a_c(i)) - c_m.kp[i] * eq - c_m.kd[i] * x.at(x.o.v, i));
     }
+    tm_wait_st();
     t4_backward<1>(x, l);
     t4_accel(x, l);
     T4_FOR_OWN_DOFS(i, b) {
@@ -1135,8 +1214,9 @@ __device__ void t4_substep(const T4Ctx &x, T4Local &l) {
             double lim = c_m.tlim[i];
             t = t < -lim ? -lim : (t > lim ? lim : t);
         }
-        l.tau[i] = t;
+        tm_st1(x.a_tau(i), t);
     }
+    tm_wait_st();
     t4_kinematics(x, l);
     t4_backward<0>(x, l);
     t4_accel(x, l);
@@ -1240,6 +1320,17 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
     T4Ctx x;
     x.sm = smem; x.lane = threadIdx.x & 31; x.w = threadIdx.x >> 5; x.o = O;
     const int lane = x.lane, w = x.w;
+    // allocate the whole Tensor Memory of this SM (1 CTA per SM) as scratch; base address comes back via smem
+    __shared__ uint32_t s_tmem_base;
+    if (w == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(&s_tmem_base)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = s_tmem_base;
+    x.tm = tmem_base + ((uint32_t)(w * 32) << 16);
     const int S = c_m.nq - 2 + c_m.nv, nu = c_m.nu, nv = c_m.nv, nb = c_m.nbody, nq = c_m.nq;
     double *xs = smem + (size_t)O.ax * 32;               // MLP activations alias the axis / anchor / U rows
     const int xrows = A.D > A.H2p ? A.D : A.H2p;
@@ -1510,31 +1601,23 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
         const bool need_reset = done && t < T - 1;
         const int any_reset = __syncthreads_or(need_reset ? 1 : 0);
         if (any_reset) {
-            // park the continuing lanes' state, run reset + forward for all lanes, then restore the parked ones
-            double keep_q[MAXV + 1], keep_v[MAXV];
-            if (!need_reset) {
-                T4_FOR_OWN_DOFS(i, b) { keep_v[i] = x.at(O.v, i); if (i >= 6) keep_q[i + 1] = x.at(O.q, i + 1); }
-                if (c_m.chain_warp[0] == w) for (int k = 0; k < 7; k++) keep_q[k] = x.at(O.q, k);
-            }
-            T4Local *lp = &l;
-            // continuing lanes must keep their stale tree data: snapshot what forward_only overwrites
+            // Lanes that continue their episode must keep their (stale) tree data across the reset sweep that
+            // the whole CTA runs: snapshot it (TMEM accesses stay warp-uniform), and give those lanes their own
+            // current state as sweep input so no garbage is produced; restore with a per-lane select afterwards.
             double k_cin[MAXB][10], k_C[MAXV], k_ax[MAXV][3], k_anc[MAXB][3], k_bqc[MAXB][4], k_xp[3 * (EGP_NEE + 1)];
-            if (!need_reset) {
-                T4_FOR_OWN_DOFS(i, b) { k_C[i] = lp->C[i]; for (int r = 0; r < 3; r++) k_ax[i][r] = x.at(O.ax, 3 * i + r); }
-                for (int c = 0; c < c_m.nchain; c++)
-                    if (c_m.chain_warp[c] == w)
-                        for (int b = c_m.chain_lo[c]; b <= c_m.chain_hi[c]; b++) {
-                            for (int r = 0; r < 10; r++) k_cin[b][r] = lp->cin[b][r];
-                            for (int r = 0; r < 3; r++) k_anc[b][r] = x.at(O.anc, 3 * b + r);
-                        }
-                for (int b = 1 + w; b < nb; b += T4_WARPS) for (int k = 0; k < 4; k++) k_bqc[b][k] = lp->bqc[b][k];
-                if (w0) for (int k = 0; k < 3 * (EGP_NEE + 1); k++) k_xp[k] = x.at(O.xp, k);
-            }
-            int take_new = take, start_new = start;
-            if (need_reset) { n_reset++; draw_reset(n_reset); take_new = take; start_new = start; cur_t = 0; }
+            T4_FOR_OWN_DOFS(i, b) { k_C[i] = tm_ld1(x.a_c(i)); for (int r = 0; r < 3; r++) k_ax[i][r] = x.at(O.ax, 3 * i + r); }
+            for (int c = 0; c < c_m.nchain; c++)
+                if (c_m.chain_warp[c] == w)
+                    for (int b = c_m.chain_lo[c]; b <= c_m.chain_hi[c]; b++) {
+                        x.ld_cin(b, k_cin[b]);
+                        for (int r = 0; r < 3; r++) k_anc[b][r] = x.at(O.anc, 3 * b + r);
+                    }
+            for (int b = 1 + w; b < nb; b += T4_WARPS) for (int k = 0; k < 4; k++) k_bqc[b][k] = l.bqc[b][k];
+            if (w0) for (int k = 0; k < 3 * (EGP_NEE + 1); k++) k_xp[k] = x.at(O.xp, k);
+            if (need_reset) { n_reset++; draw_reset(n_reset); cur_t = 0; }
             __syncthreads();
             if (need_reset) {
-                const double *r0 = A.rows + (size_t)(A.take_off[take_new] + start_new) * EGP_X_STRIDE;
+                const double *r0 = A.rows + (size_t)(A.take_off[take] + start) * EGP_X_STRIDE;
                 T4_FOR_OWN_DOFS(i, b) {
                     x.at(O.v, i) = r0[EGP_X_QVEL + i];
                     if (i >= 6) x.at(O.q, i + 1) = r0[EGP_X_QPOS + i + 1];
@@ -1543,6 +1626,22 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
             }
             __syncthreads();
             t4_forward_only(x, l);
+            // restore parked lanes (uniform TMEM traffic, per-lane select of the value)
+            T4_FOR_OWN_DOFS(i, b) {
+                const double cur = tm_ld1(x.a_c(i));
+                tm_st1(x.a_c(i), need_reset ? cur : k_C[i]);
+                if (!need_reset) for (int r = 0; r < 3; r++) x.at(O.ax, 3 * i + r) = k_ax[i][r];
+            }
+            for (int c = 0; c < c_m.nchain; c++)
+                if (c_m.chain_warp[c] == w)
+                    for (int b = c_m.chain_lo[c]; b <= c_m.chain_hi[c]; b++) {
+                        double cur[10];
+                        x.ld_cin(b, cur);
+                        if (!need_reset) for (int r = 0; r < 10; r++) cur[r] = k_cin[b][r];
+                        x.st_cin(b, cur);
+                        if (!need_reset) for (int r = 0; r < 3; r++) x.at(O.anc, 3 * b + r) = k_anc[b][r];
+                    }
+            tm_wait_st();
             if (need_reset) {
                 for (int b = 1 + w; b < nb; b += T4_WARPS) {
                     const int qa = c_m.body_qposadr[b], nd = c_m.body_dofnum[b];
@@ -1550,18 +1649,10 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
                 }
                 make_state(raw, st);
             } else {
-                T4_FOR_OWN_DOFS(i, b) { lp->C[i] = k_C[i]; for (int r = 0; r < 3; r++) x.at(O.ax, 3 * i + r) = k_ax[i][r]; }
-                for (int c = 0; c < c_m.nchain; c++)
-                    if (c_m.chain_warp[c] == w)
-                        for (int b = c_m.chain_lo[c]; b <= c_m.chain_hi[c]; b++) {
-                            for (int r = 0; r < 10; r++) lp->cin[b][r] = k_cin[b][r];
-                            for (int r = 0; r < 3; r++) x.at(O.anc, 3 * b + r) = k_anc[b][r];
-                        }
-                for (int b = 1 + w; b < nb; b += T4_WARPS) for (int k = 0; k < 4; k++) lp->bqc[b][k] = k_bqc[b][k];
+                for (int b = 1 + w; b < nb; b += T4_WARPS) for (int k = 0; k < 4; k++) l.bqc[b][k] = k_bqc[b][k];
                 if (w0) for (int k = 0; k < 3 * (EGP_NEE + 1); k++) x.at(O.xp, k) = k_xp[k];
-                int s = 0;
-                for (int k = w; k < S; k += T4_WARPS, s++) { st[s] = nst[s]; raw[s] = nraw[s]; }
-                (void)keep_q; (void)keep_v;
+                int s2 = 0;
+                for (int k = w; k < S; k += T4_WARPS, s2++) { st[s2] = nst[s2]; raw[s2] = nraw[s2]; }
             }
         } else {
             int s = 0;
@@ -1596,6 +1687,9 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
             amax(Lg + EGP_LOG_MAX_EPISODE_REWARD, log_acc[EGP_LOG_MAX_EPISODE_REWARD]);
         }
     }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (w == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
 }
 
 // transposes W [out][in] -> Wt [in][outp] (zero padded), biases padded
@@ -1788,6 +1882,18 @@ static void build_chains(DevModel &d) {
     }
     if (d.body_xp_slot[d.head_body] < 0) d.body_xp_slot[d.head_body] = nslot++;
     d.head_xp_slot = d.body_xp_slot[d.head_body];
+    // TMEM scratch slots: position of each dof / body among those owned by the same warp
+    int nd_w[4] = {0, 0, 0, 0}, nb_w[4] = {0, 0, 0, 0};
+    for (int b = 0; b < nb; b++) {
+        int w = d.chain_warp[d.body_chain[b]];
+        d.body_slot[b] = nb_w[w]++;
+        for (int i = d.body_dofadr[b]; i < d.body_dofadr[b] + d.body_dofnum[b]; i++) d.dof_slot[i] = nd_w[w]++;
+    }
+    int ND = 0, NB = 0;
+    for (int w = 0; w < 4; w++) { if (nd_w[w] > ND) ND = nd_w[w]; if (nb_w[w] > NB) NB = nb_w[w]; }
+    d.tm_dinv = 0; d.tm_u = 2 * ND; d.tm_tau = 4 * ND; d.tm_c = 6 * ND; d.tm_cin = 8 * ND; d.tm_fb = 8 * ND + 20 * NB;
+    d.tm_cols = 8 * ND + 32 * NB;
+    if (d.tm_cols > 512) d.t4_ok = 0;
 }
 
 }  // namespace egp
