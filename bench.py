@@ -236,8 +236,8 @@ def main():
     def iteration(host):
         batch, log = agent.sample(N, to_host=host)
         agent.env.end_reward = log.avg_c_reward * cfg.gamma / (1 - cfg.gamma)       # ego_mimic.py:112
-        if host:
-            batch = TrajBatchEgo(host={k: getattr(batch, k) for k in batch.fields}, horizon=T)
+        if host:        # reference-format call: a batch object that only carries host (numpy) arrays
+            batch = TrajBatchEgo(host={k: getattr(batch, k) for k in batch.fields}, horizon=T, pinned=batch._pinned)
         agent.update_params(batch)
         return log
 

@@ -138,14 +138,12 @@ class _Trunk:
         lib.colsum(dy, self.gb(2))
         dh2 = self._buf('dh2', h2.shape, x)
         torch.mm(dy, self.W(2), out=dh2)
-        lib.relu_bwd_(dh2, h2)
+        lib.relu_bwd_colsum_(dh2, h2, self.gb(1))
         torch.mm(dh2.t(), h1, out=self.gW(1))
-        lib.colsum(dh2, self.gb(1))
         dh1 = self._buf('dh1', h1.shape, x)
         torch.mm(dh2, self.W(1), out=dh1)
-        lib.relu_bwd_(dh1, h1)
+        lib.relu_bwd_colsum_(dh1, h1, self.gb(0))
         torch.mm(dh1.t(), x, out=self.gW(0))
-        lib.colsum(dh1, self.gb(0))
 
 
 class Agent:
@@ -170,6 +168,7 @@ class Agent:
         self.update_modules = [policy_net, value_net]
         self.iteration = 0
         self._out = {}
+        self._host_pool = {}        # pinned host staging buffers reused by sample(to_host=True)
         if dtype != torch.float64:
             raise lib.EgpError('the fused path computes in float64 like the reference (ego_mimic.py:31-32)')
         if render:
@@ -255,7 +254,7 @@ class Agent:
                                        (lib.LOG['MAX_C_REWARD'], lib.LOG['MAX_EPISODE_REWARD']))
         logger = self.logger_cls.from_device(lg.cpu().numpy())     # D2H of 16 doubles: the rollout's sync point
         if to_host:
-            batch.to_host()
+            batch.to_host(self._host_pool)
         logger.sample_time = time.time() - t_start
         return batch, logger
 
@@ -315,22 +314,32 @@ class AgentPG(Agent):
         if getattr(batch, 'dev', None) and batch.dev.get('states') is not None and 'states' not in batch._host:
             b = batch.dev
             return b['states'], b['actions'], b['rewards'], b['masks'], b['exps'], b.get('v_metas'), batch.horizon
-        # reference-format host batch (agents/agent_pg.py:43-47): pinned staging + async H2D
-        def up(a, dtype=torch.float64):
-            t = torch.from_numpy(np.ascontiguousarray(a))
-            return t.pin_memory().to(dev, non_blocking=True).to(dtype)
-        vm = up(batch.v_metas, torch.int32) if hasattr(batch, 'v_metas') or 'v_metas' in getattr(batch, '_host', {}) else None
-        return (up(batch.states), up(batch.actions), up(batch.rewards), up(batch.masks), up(batch.exps), vm,
-                getattr(batch, 'horizon', None))
+        # reference-format host batch (agents/agent_pg.py:43-47): async H2D straight from the pinned buffers
+        # sample() handed out, else through a reusable pinned staging buffer
+        def up(name, dtype=torch.float64):
+            src = batch.pinned(name) if hasattr(batch, 'pinned') else None
+            if src is None:
+                a = np.ascontiguousarray(getattr(batch, name))
+                stage = self._host_pool.get('up.' + name)
+                if stage is None or stage.shape != a.shape or stage.dtype != torch.from_numpy(a).dtype:
+                    stage = torch.empty(a.shape, dtype=torch.from_numpy(a).dtype, pin_memory=True)
+                    self._host_pool['up.' + name] = stage
+                stage.numpy()[...] = a
+                src = stage
+            return src.to(dev, non_blocking=True).to(dtype)
+        has_vm = 'v_metas' in getattr(batch, '_host', {}) or (not hasattr(batch, '_host') and hasattr(batch, 'v_metas'))
+        vm = up('v_metas', torch.int32) if has_vm else None
+        return (up('states'), up('actions'), up('rewards'), up('masks'), up('exps'), vm, getattr(batch, 'horizon', None))
 
     def _inputs(self, states, v_metas, masks, horizon):
         """trans_policy / trans_value of the base agent: identity"""
         return states, states
 
-    def update_value(self, x, returns, inv_n):
-        """agents/agent_pg.py:19-26"""
-        for _ in range(self.value_opt_niter):
-            v = self._vt.forward(x)
+    def update_value(self, x, returns, inv_n, reuse_forward=False):
+        """agents/agent_pg.py:19-26.  ``reuse_forward``: the activations of the value forward that produced the
+        GAE inputs are still valid (no parameter step since), so the first epoch skips its forward GEMMs."""
+        for it in range(self.value_opt_niter):
+            v = self._vt.buf['y'] if (reuse_forward and it == 0) else self._vt.forward(x)
             dv = self._vt._buf('dy', v.shape, x)
             self._scal[0:1].zero_()
             lib.value_loss_grad(v.view(-1), returns, inv_n, dv.view(-1), self._scal[0:1])
@@ -347,6 +356,7 @@ class AgentPG(Agent):
         xp, xv = self._inputs(states, v_metas, masks, horizon)
         # values + GAE (agent_pg.py:48-53, core/common.py:5-25)
         values = self._vt.forward(xv).view(-1)
+        self._value_fresh = True
         adv, returns, stats = lib.gae(rewards, masks, values.contiguous(), self.gamma, self.tau)
         n_local = states.shape[0]
         n_exp = exps.sum()
@@ -391,10 +401,11 @@ class AgentPPO(AgentPG):
         max_norm = self._max_norm()
         surr, vloss = [], []
         d = _dist()
-        for _ in range(self.opt_num_epochs):
-            self.update_value(xv, returns, inv_n)                        # :46
+        for ep in range(self.opt_num_epochs):
+            self.update_value(xv, returns, inv_n, reuse_forward=(ep == 0 and self._value_fresh))     # :46
             vloss.append(self._scal[0:1].clone())
-            mu = self._pt.forward(xp)
+            if ep > 0:                                                   # epoch 0 reuses the fixed-log-prob forward
+                mu = self._pt.forward(xp)
             dmu = self._pt._buf('dy', mu.shape, xp)
             self._scal[1:2].zero_()
             dls = None

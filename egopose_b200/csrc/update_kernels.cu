@@ -342,6 +342,36 @@ colsum_kernel(const double *__restrict__ x, long long n, int dim, long long rows
     }
 }
 
+// fused relu backward + bias gradient: dy *= (y > 0) in place and out[c] += sum_rows dy[:, c] (one pass)
+__global__ void __launch_bounds__(256)
+relu_bwd_colsum_kernel(double *__restrict__ dy, const double *__restrict__ y, long long n, int dim, long long rows_per_block,
+                       double *__restrict__ out) {
+    __shared__ double s[8][33];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    long long r0 = blockIdx.x * rows_per_block, r1 = r0 + rows_per_block;
+    if (r1 > n) r1 = n;
+    for (int c0 = 0; c0 < dim; c0 += 32) {
+        int c = c0 + lane;
+        double acc = 0.0;
+        if (c < dim)
+            for (long long r = r0 + w; r < r1; r += 8) {
+                const long long idx = r * dim + c;
+                double g = y[idx] > 0.0 ? dy[idx] : 0.0;
+                dy[idx] = g;
+                acc += g;
+            }
+        s[w][lane] = acc;
+        __syncthreads();
+        if (w == 0 && c < dim) {
+            double t = 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) t += s[k][lane];
+            atomicAdd(out + c, t);
+        }
+        __syncthreads();
+    }
+}
+
 // shifted first/second column moments (batched ZFilter update)
 __global__ void __launch_bounds__(256)
 col_moments_kernel(const double *__restrict__ x, long long n, int dim, long long rows_per_block,
@@ -536,6 +566,19 @@ int egp_colsum_f64(const double *d_x, int64_t n, int dim, double *d_out, void *s
     blocks = (int)((n + rpb - 1) / rpb);
     colsum_kernel<<<blocks, 256, 0, st>>>(d_x, (long long)n, dim, rpb, d_out);
     EGP_CHECK_LAUNCH("colsum_kernel");
+    return EGP_OK;
+}
+
+int egp_relu_bwd_colsum_f64(double *d_dy, const double *d_y, int64_t n, int dim, double *d_out, void *stream) {
+    if (n <= 0 || dim <= 0 || !d_dy || !d_y || !d_out) { set_error("egp_relu_bwd_colsum_f64: bad argument"); return EGP_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    EGP_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * dim, st));
+    int blocks = num_sms() * 8;
+    long long rpb = (n + blocks - 1) / blocks;
+    if (rpb < 8) rpb = 8;
+    blocks = (int)((n + rpb - 1) / rpb);
+    relu_bwd_colsum_kernel<<<blocks, 256, 0, st>>>(d_dy, d_y, (long long)n, dim, rpb, d_out);
+    EGP_CHECK_LAUNCH("relu_bwd_colsum_kernel");
     return EGP_OK;
 }
 

@@ -90,6 +90,7 @@ SYMBOLS = {
     'egp_value_loss_grad_f64': (_int, [_vp, _vp, _d, _i64, _vp, _vp, _vp]),
     'egp_bias_relu_f64': (_int, [_vp, _vp, _i64, _int, _vp]),
     'egp_relu_bwd_f64': (_int, [_vp, _vp, _i64, _int, _vp]),
+    'egp_relu_bwd_colsum_f64': (_int, [_vp, _vp, _i64, _int, _vp, _vp]),
     'egp_colsum_f64': (_int, [_vp, _i64, _int, _vp, _vp]),
     'egp_col_moments_f64': (_int, [_vp, _i64, _int, _vp, _vp, _vp]),
     'egp_build_input_f64': (_int, [_vp, _vp, _vp, _vp, _i64, _int, _vp, _vp]),
@@ -403,6 +404,14 @@ def bias_relu_(y, b):
 def relu_bwd_(dy, y):
     global launches
     check(load().egp_relu_bwd_f64(ptr(dy), ptr(y), y.shape[0], y.shape[1], stream_ptr()), 'egp_relu_bwd_f64')
+    launches += 1
+    return dy
+
+
+def relu_bwd_colsum_(dy, y, out):
+    global launches
+    check(load().egp_relu_bwd_colsum_f64(ptr(dy), ptr(y), y.shape[0], y.shape[1], ptr(out), stream_ptr()),
+          'egp_relu_bwd_colsum_f64')
     launches += 1
     return dy
 

@@ -102,6 +102,10 @@ def test_value_loss_and_helpers():
     assert np.array_equal(yy.cpu().numpy(), ref)
     dy = rng.randn(777, 300)
     assert np.array_equal(lib.relu_bwd_(cu(dy), yy).cpu().numpy(), dy * (ref > 0))
+    fused_out = torch.empty(300, dtype=torch.float64, device='cuda')
+    fused = lib.relu_bwd_colsum_(cu(dy), yy, fused_out)
+    assert np.array_equal(fused.cpu().numpy(), dy * (ref > 0))
+    assert np.allclose(fused_out.cpu().numpy(), (dy * (ref > 0)).sum(0), rtol=1e-12, atol=1e-12)
     cs = lib.colsum(cu(dy), torch.empty(300, dtype=torch.float64, device='cuda'))
     assert np.allclose(cs.cpu().numpy(), dy.sum(0), rtol=1e-12, atol=1e-12)
     sh = rng.randn(300)
