@@ -925,13 +925,26 @@ __device__ __forceinline__ void t4_load_S(const T4Ctx &x, int i, int b, double *
     }
 }
 
-__device__ void t4_kinematics(const T4Ctx &x, T4Local &l) {
+// Forward tree sweep, level-synchronous.
+//   MODE 1: [PD accel + torque] on the OLD tree rows of each dof, then [kinematics refresh] of that dof/body
+//           (two independent dependency chains interleaved in one sweep; the stale-data ordering of the reference
+//           is preserved because every old row is read before it is overwritten)
+//   MODE 0: forward-dynamics accel sweep + semi-implicit Euler integration of the owned dofs
+//   MODE 2: kinematics refresh only (sim.forward() at reset)
+template <int MODE>
+__device__ void t4_forward(const T4Ctx &x, T4Local &l) {
+    const double h = c_m.h;
     for (int L = 0; L < c_m.nlevel; L++) {
         const int c = t4_my_chain(L, x.w);
         if (c >= 0) {
             Fwd f;
+            double a[6];
             const int pc = c_m.chain_parent[c];
-            if (pc >= 0) {
+            if (MODE != 2) {
+#pragma unroll
+                for (int k = 0; k < 6; k++) a[k] = pc >= 0 ? x.at(x.o.ja + 6 * c_m.chain_pslot[pc], k) : 0.0;
+            }
+            if (MODE != 0 && pc >= 0) {
                 const int base = x.o.jf + 24 * c_m.chain_pslot[pc];
 #pragma unroll
                 for (int k = 0; k < 3; k++) f.p[k] = x.at(base, k);
@@ -942,137 +955,203 @@ __device__ void t4_kinematics(const T4Ctx &x, T4Local &l) {
             }
             for (int b = c_m.chain_lo[c]; b <= c_m.chain_hi[c]; b++) {
                 const int da = c_m.body_dofadr[b], nd = c_m.body_dofnum[b], qa = c_m.body_qposadr[b];
-                if (nd == 6) {
-                    double q4[4] = {x.at(x.o.q, qa + 3), x.at(x.o.q, qa + 4), x.at(x.o.q, qa + 5), x.at(x.o.q, qa + 6)};
-                    double n = sqrt(q4[0] * q4[0] + q4[1] * q4[1] + q4[2] * q4[2] + q4[3] * q4[3]);
-                    for (int k = 0; k < 4; k++) q4[k] /= n;
-                    quat_to_mat(q4, f.R);
-                    f.p[0] = f.p[1] = f.p[2] = 0.0;
-                    double wl[3] = {x.at(x.o.v, da + 3), x.at(x.o.v, da + 4), x.at(x.o.v, da + 5)}, ww[3];
-                    for (int r = 0; r < 3; r++) ww[r] = f.R[3 * r] * wl[0] + f.R[3 * r + 1] * wl[1] + f.R[3 * r + 2] * wl[2];
-                    for (int k = 0; k < 3; k++) {
-                        for (int r = 0; r < 3; r++) {
-                            x.at(x.o.ax, 3 * (da + k) + r) = r == k ? 1.0 : 0.0;
-                            x.at(x.o.ax, 3 * (da + 3 + k) + r) = f.R[3 * r + k];
+                // ---- solve part for the dofs of this body (old rows)
+                auto solve_dof = [&](int i, const double *S) {
+                    double U[6];
+#pragma unroll
+                    for (int r = 0; r < 6; r++) U[r] = x.at(x.o.U, 6 * i + r);
+                    const double xi = tm_ld1(x.a_dinv(i)) * (tm_ld1(x.a_u(i)) - dot6(U, a));
+#pragma unroll
+                    for (int r = 0; r < 6; r++) a[r] += S[r] * xi;
+                    if (MODE == 1) {            // torque = clip(-kp e - kd (v + x h))  (humanoid_v1.py:152-155,172)
+                        double t = 0.0;
+                        if (i >= 6) {
+                            const double eq = x.at(x.o.q, i + 1) - l.ctrl[i];
+                            t = -c_m.kp[i] * eq - c_m.kd[i] * (x.at(x.o.v, i) + xi * h);
+                            const double lim = c_m.tlim[i];
+                            t = t < -lim ? -lim : (t > lim ? lim : t);
                         }
-                        x.at(x.o.anc, 3 * b + k) = 0.0;
+                        tm_st1(x.a_tau(i), t);
+                    } else {                    // semi-implicit Euler for hinges; the root is finished below
+                        const double vn = x.at(x.o.v, i) + h * xi;
+                        x.at(x.o.v, i) = vn;
+                        if (i >= 6) x.at(x.o.q, i + 1) += h * vn;
                     }
-                    double vl[3] = {x.at(x.o.v, da), x.at(x.o.v, da + 1), x.at(x.o.v, da + 2)}, vxw[3];
-                    cross3(vl, ww, vxw);
-                    for (int k = 0; k < 3; k++) {
-                        f.v[k] = ww[k]; f.v[3 + k] = vl[k];
-                        f.a[k] = 0.0; f.a[3 + k] = -c_m.grav[k] + vxw[k];
+                };
+                if (nd == 6) {
+                    if (MODE != 2) {
+                        for (int i = da; i < da + 6; i++) { double S[6]; t4_load_S(x, i, b, S); solve_dof(i, S); }
+                        if (MODE == 0) {        // root position + quaternion integration with the NEW velocity
+                            for (int k = 0; k < 3; k++) x.at(x.o.q, qa + k) += h * x.at(x.o.v, da + k);
+                            double wv[3] = {x.at(x.o.v, da + 3), x.at(x.o.v, da + 4), x.at(x.o.v, da + 5)};
+                            double n = sqrt(dot3(wv, wv)), ax[3] = {1.0, 0.0, 0.0};
+                            if (n > 1e-15) { ax[0] = wv[0] / n; ax[1] = wv[1] / n; ax[2] = wv[2] / n; }
+                            double sn, cs;
+                            sincos(0.5 * h * n, &sn, &cs);
+                            double qr[4] = {cs, ax[0] * sn, ax[1] * sn, ax[2] * sn};
+                            double q4[4] = {x.at(x.o.q, qa + 3), x.at(x.o.q, qa + 4), x.at(x.o.q, qa + 5), x.at(x.o.q, qa + 6)};
+                            double qn = sqrt(q4[0] * q4[0] + q4[1] * q4[1] + q4[2] * q4[2] + q4[3] * q4[3]);
+                            for (int k = 0; k < 4; k++) q4[k] /= qn;
+                            double o4[4];
+                            quat_mul(q4, qr, o4);
+                            for (int k = 0; k < 4; k++) x.at(x.o.q, qa + 3 + k) = o4[k];
+                        }
+                    }
+                    if (MODE != 0) {
+                        double q4[4] = {x.at(x.o.q, qa + 3), x.at(x.o.q, qa + 4), x.at(x.o.q, qa + 5), x.at(x.o.q, qa + 6)};
+                        double n = sqrt(q4[0] * q4[0] + q4[1] * q4[1] + q4[2] * q4[2] + q4[3] * q4[3]);
+                        for (int k = 0; k < 4; k++) q4[k] /= n;
+                        quat_to_mat(q4, f.R);
+                        f.p[0] = f.p[1] = f.p[2] = 0.0;
+                        double wl[3] = {x.at(x.o.v, da + 3), x.at(x.o.v, da + 4), x.at(x.o.v, da + 5)}, ww[3];
+                        for (int r = 0; r < 3; r++) ww[r] = f.R[3 * r] * wl[0] + f.R[3 * r + 1] * wl[1] + f.R[3 * r + 2] * wl[2];
+                        for (int k = 0; k < 3; k++) {
+                            for (int r = 0; r < 3; r++) {
+                                x.at(x.o.ax, 3 * (da + k) + r) = r == k ? 1.0 : 0.0;
+                                x.at(x.o.ax, 3 * (da + 3 + k) + r) = f.R[3 * r + k];
+                            }
+                            x.at(x.o.anc, 3 * b + k) = 0.0;
+                        }
+                        double vl[3] = {x.at(x.o.v, da), x.at(x.o.v, da + 1), x.at(x.o.v, da + 2)}, vxw[3];
+                        cross3(vl, ww, vxw);
+                        for (int k = 0; k < 3; k++) {
+                            f.v[k] = ww[k]; f.v[3 + k] = vl[k];
+                            f.a[k] = 0.0; f.a[3 + k] = -c_m.grav[k] + vxw[k];
+                        }
                     }
                 } else {
-                    double off[3];
-                    for (int r = 0; r < 3; r++)
-                        off[r] = f.R[3 * r] * c_m.body_pos[b][0] + f.R[3 * r + 1] * c_m.body_pos[b][1] + f.R[3 * r + 2] * c_m.body_pos[b][2];
-                    for (int r = 0; r < 3; r++) f.p[r] += off[r];
-                    double anc[3];
-                    for (int r = 0; r < 3; r++) {
-                        anc[r] = f.p[r] + f.R[3 * r] * c_m.dof_anchor[da][0] + f.R[3 * r + 1] * c_m.dof_anchor[da][1] +
-                                 f.R[3 * r + 2] * c_m.dof_anchor[da][2];
-                        x.at(x.o.anc, 3 * b + r) = anc[r];
+                    double anc_old[3], anc[3];
+                    if (MODE != 2) for (int r = 0; r < 3; r++) anc_old[r] = x.at(x.o.anc, 3 * b + r);
+                    if (MODE != 0) {
+                        double off[3];
+                        for (int r = 0; r < 3; r++)
+                            off[r] = f.R[3 * r] * c_m.body_pos[b][0] + f.R[3 * r + 1] * c_m.body_pos[b][1] + f.R[3 * r + 2] * c_m.body_pos[b][2];
+                        for (int r = 0; r < 3; r++) f.p[r] += off[r];
+                        for (int r = 0; r < 3; r++) {
+                            anc[r] = f.p[r] + f.R[3 * r] * c_m.dof_anchor[da][0] + f.R[3 * r + 1] * c_m.dof_anchor[da][1] +
+                                     f.R[3 * r + 2] * c_m.dof_anchor[da][2];
+                            x.at(x.o.anc, 3 * b + r) = anc[r];
+                        }
                     }
                     for (int j = 0; j < nd; j++) {
                         const int i = da + j;
-                        double ax[3];
-                        const int aid = c_m.dof_axis_id[i];
-                        if (aid >= 0) { ax[0] = f.R[aid]; ax[1] = f.R[3 + aid]; ax[2] = f.R[6 + aid]; }
-                        else for (int r = 0; r < 3; r++)
-                            ax[r] = f.R[3 * r] * c_m.dof_axis[i][0] + f.R[3 * r + 1] * c_m.dof_axis[i][1] + f.R[3 * r + 2] * c_m.dof_axis[i][2];
-                        for (int r = 0; r < 3; r++) x.at(x.o.ax, 3 * i + r) = ax[r];
-                        double S[6];
-                        S[0] = ax[0]; S[1] = ax[1]; S[2] = ax[2];
-                        cross3(anc, ax, S + 3);
-                        const double qd = x.at(x.o.v, i);
-                        double t0[3], t1[3], t2[3];
-                        cross3(f.v, S, t0);
-                        cross3(f.v, S + 3, t1);
-                        cross3(f.v + 3, S, t2);
-                        for (int r = 0; r < 3; r++) {
-                            f.a[r] += t0[r] * qd;
-                            f.a[3 + r] += (t1[r] + t2[r]) * qd;
+                        if (MODE != 2) {
+                            double S[6];
+                            S[0] = x.at(x.o.ax, 3 * i); S[1] = x.at(x.o.ax, 3 * i + 1); S[2] = x.at(x.o.ax, 3 * i + 2);
+                            cross3(anc_old, S, S + 3);
+                            solve_dof(i, S);
                         }
-                        for (int r = 0; r < 6; r++) f.v[r] += S[r] * qd;
-                        double sn, cs;
-                        sincos(x.at(x.o.q, qa + j), &sn, &cs);
-                        if (aid >= 0) {
-                            const int c1 = (aid + 1) % 3, c2 = (aid + 2) % 3;
+                        if (MODE != 0) {
+                            double ax[3];
+                            const int aid = c_m.dof_axis_id[i];
+                            if (aid >= 0) { ax[0] = f.R[aid]; ax[1] = f.R[3 + aid]; ax[2] = f.R[6 + aid]; }
+                            else for (int r = 0; r < 3; r++)
+                                ax[r] = f.R[3 * r] * c_m.dof_axis[i][0] + f.R[3 * r + 1] * c_m.dof_axis[i][1] + f.R[3 * r + 2] * c_m.dof_axis[i][2];
+                            for (int r = 0; r < 3; r++) x.at(x.o.ax, 3 * i + r) = ax[r];
+                            double S[6];
+                            S[0] = ax[0]; S[1] = ax[1]; S[2] = ax[2];
+                            cross3(anc, ax, S + 3);
+                            const double qd = x.at(x.o.v, i);
+                            double t0[3], t1[3], t2[3];
+                            cross3(f.v, S, t0);
+                            cross3(f.v, S + 3, t1);
+                            cross3(f.v + 3, S, t2);
                             for (int r = 0; r < 3; r++) {
-                                double a1 = f.R[3 * r + c1], a2 = f.R[3 * r + c2];
-                                f.R[3 * r + c1] = cs * a1 + sn * a2;
-                                f.R[3 * r + c2] = -sn * a1 + cs * a2;
+                                f.a[r] += t0[r] * qd;
+                                f.a[3 + r] += (t1[r] + t2[r]) * qd;
                             }
-                        } else {
-                            const double *a = c_m.dof_axis[i];
-                            double K[9] = {0, -a[2], a[1], a[2], 0, -a[0], -a[1], a[0], 0}, Rot[9], Rn[9];
-                            for (int r = 0; r < 3; r++) for (int cc = 0; cc < 3; cc++)
-                                Rot[3 * r + cc] = (r == cc ? cs : 0.0) + sn * K[3 * r + cc] + (1.0 - cs) * a[r] * a[cc];
-                            for (int r = 0; r < 3; r++) for (int cc = 0; cc < 3; cc++)
-                                Rn[3 * r + cc] = f.R[3 * r] * Rot[cc] + f.R[3 * r + 1] * Rot[3 + cc] + f.R[3 * r + 2] * Rot[6 + cc];
-                            for (int r = 0; r < 9; r++) f.R[r] = Rn[r];
+                            for (int r = 0; r < 6; r++) f.v[r] += S[r] * qd;
+                            double sn, cs;
+                            sincos(x.at(x.o.q, qa + j), &sn, &cs);
+                            if (aid >= 0) {
+                                const int c1 = (aid + 1) % 3, c2 = (aid + 2) % 3;
+                                for (int r = 0; r < 3; r++) {
+                                    double a1 = f.R[3 * r + c1], a2 = f.R[3 * r + c2];
+                                    f.R[3 * r + c1] = cs * a1 + sn * a2;
+                                    f.R[3 * r + c2] = -sn * a1 + cs * a2;
+                                }
+                            } else {
+                                const double *av = c_m.dof_axis[i];
+                                double K[9] = {0, -av[2], av[1], av[2], 0, -av[0], -av[1], av[0], 0}, Rot[9], Rn[9];
+                                for (int r = 0; r < 3; r++) for (int cc = 0; cc < 3; cc++)
+                                    Rot[3 * r + cc] = (r == cc ? cs : 0.0) + sn * K[3 * r + cc] + (1.0 - cs) * av[r] * av[cc];
+                                for (int r = 0; r < 3; r++) for (int cc = 0; cc < 3; cc++)
+                                    Rn[3 * r + cc] = f.R[3 * r] * Rot[cc] + f.R[3 * r + 1] * Rot[3 + cc] + f.R[3 * r + 2] * Rot[6 + cc];
+                                for (int r = 0; r < 9; r++) f.R[r] = Rn[r];
+                            }
                         }
                     }
+                    if (MODE != 0)
+                        for (int r = 0; r < 3; r++)
+                            f.p[r] = anc[r] - (f.R[3 * r] * c_m.dof_anchor[da][0] + f.R[3 * r + 1] * c_m.dof_anchor[da][1] +
+                                               f.R[3 * r + 2] * c_m.dof_anchor[da][2]);
+                }
+                if (MODE != 0) {
+                    const int xs = c_m.body_xp_slot[b];
+                    if (xs >= 0) for (int r = 0; r < 3; r++) x.at(x.o.xp, 3 * xs + r) = f.p[r] + x.at(x.o.q, r);
+                    double cpos[3];
                     for (int r = 0; r < 3; r++)
-                        f.p[r] = anc[r] - (f.R[3 * r] * c_m.dof_anchor[da][0] + f.R[3 * r + 1] * c_m.dof_anchor[da][1] +
-                                           f.R[3 * r + 2] * c_m.dof_anchor[da][2]);
+                        cpos[r] = f.p[r] + f.R[3 * r] * c_m.body_ipos[b][0] + f.R[3 * r + 1] * c_m.body_ipos[b][1] + f.R[3 * r + 2] * c_m.body_ipos[b][2];
+                    const double *in = c_m.body_inertia[b];
+                    double Ib[9] = {in[0], in[3], in[4], in[3], in[1], in[5], in[4], in[5], in[2]}, Tm[9], Iw[6];
+                    for (int r = 0; r < 3; r++) for (int cc = 0; cc < 3; cc++)
+                        Tm[3 * r + cc] = f.R[3 * r] * Ib[cc] + f.R[3 * r + 1] * Ib[3 + cc] + f.R[3 * r + 2] * Ib[6 + cc];
+                    Iw[0] = Tm[0] * f.R[0] + Tm[1] * f.R[1] + Tm[2] * f.R[2];
+                    Iw[1] = Tm[3] * f.R[3] + Tm[4] * f.R[4] + Tm[5] * f.R[5];
+                    Iw[2] = Tm[6] * f.R[6] + Tm[7] * f.R[7] + Tm[8] * f.R[8];
+                    Iw[3] = Tm[0] * f.R[3] + Tm[1] * f.R[4] + Tm[2] * f.R[5];
+                    Iw[4] = Tm[0] * f.R[6] + Tm[1] * f.R[7] + Tm[2] * f.R[8];
+                    Iw[5] = Tm[3] * f.R[6] + Tm[4] * f.R[7] + Tm[5] * f.R[8];
+                    const double mass = c_m.body_mass[b], cc2 = dot3(cpos, cpos);
+                    double ci[10];
+                    ci[0] = mass;
+                    ci[1] = mass * cpos[0]; ci[2] = mass * cpos[1]; ci[3] = mass * cpos[2];
+                    ci[4] = Iw[0] + mass * (cc2 - cpos[0] * cpos[0]);
+                    ci[5] = Iw[1] + mass * (cc2 - cpos[1] * cpos[1]);
+                    ci[6] = Iw[2] + mass * (cc2 - cpos[2] * cpos[2]);
+                    ci[7] = Iw[3] - mass * cpos[0] * cpos[1];
+                    ci[8] = Iw[4] - mass * cpos[0] * cpos[2];
+                    ci[9] = Iw[5] - mass * cpos[1] * cpos[2];
+                    double Ia[6], Iv[6];
+                    spi_mul(ci, f.a, Ia);
+                    spi_mul(ci, f.v, Iv);
+                    double c0[3], c1[3], c2[3];
+                    cross3(f.v, Iv, c0);
+                    cross3(f.v + 3, Iv + 3, c1);
+                    cross3(f.v, Iv + 3, c2);
+                    double fbv[6];
+                    for (int r = 0; r < 3; r++) {
+                        fbv[r] = Ia[r] + c0[r] + c1[r];
+                        fbv[3 + r] = Ia[3 + r] + c2[r];
+                    }
+                    x.st_cin(b, ci);
+                    x.st_fb(b, fbv);
                 }
-                const int xs = c_m.body_xp_slot[b];
-                if (xs >= 0) for (int r = 0; r < 3; r++) x.at(x.o.xp, 3 * xs + r) = f.p[r] + x.at(x.o.q, r);
-                double cpos[3];
-                for (int r = 0; r < 3; r++)
-                    cpos[r] = f.p[r] + f.R[3 * r] * c_m.body_ipos[b][0] + f.R[3 * r + 1] * c_m.body_ipos[b][1] + f.R[3 * r + 2] * c_m.body_ipos[b][2];
-                const double *in = c_m.body_inertia[b];
-                double Ib[9] = {in[0], in[3], in[4], in[3], in[1], in[5], in[4], in[5], in[2]}, Tm[9], Iw[6];
-                for (int r = 0; r < 3; r++) for (int cc = 0; cc < 3; cc++)
-                    Tm[3 * r + cc] = f.R[3 * r] * Ib[cc] + f.R[3 * r + 1] * Ib[3 + cc] + f.R[3 * r + 2] * Ib[6 + cc];
-                Iw[0] = Tm[0] * f.R[0] + Tm[1] * f.R[1] + Tm[2] * f.R[2];
-                Iw[1] = Tm[3] * f.R[3] + Tm[4] * f.R[4] + Tm[5] * f.R[5];
-                Iw[2] = Tm[6] * f.R[6] + Tm[7] * f.R[7] + Tm[8] * f.R[8];
-                Iw[3] = Tm[0] * f.R[3] + Tm[1] * f.R[4] + Tm[2] * f.R[5];
-                Iw[4] = Tm[0] * f.R[6] + Tm[1] * f.R[7] + Tm[2] * f.R[8];
-                Iw[5] = Tm[3] * f.R[6] + Tm[4] * f.R[7] + Tm[5] * f.R[8];
-                const double mass = c_m.body_mass[b], cc2 = dot3(cpos, cpos);
-                double ci[10];
-                ci[0] = mass;
-                ci[1] = mass * cpos[0]; ci[2] = mass * cpos[1]; ci[3] = mass * cpos[2];
-                ci[4] = Iw[0] + mass * (cc2 - cpos[0] * cpos[0]);
-                ci[5] = Iw[1] + mass * (cc2 - cpos[1] * cpos[1]);
-                ci[6] = Iw[2] + mass * (cc2 - cpos[2] * cpos[2]);
-                ci[7] = Iw[3] - mass * cpos[0] * cpos[1];
-                ci[8] = Iw[4] - mass * cpos[0] * cpos[2];
-                ci[9] = Iw[5] - mass * cpos[1] * cpos[2];
-                double Ia[6], Iv[6];
-                spi_mul(ci, f.a, Ia);
-                spi_mul(ci, f.v, Iv);
-                double c0[3], c1[3], c2[3];
-                cross3(f.v, Iv, c0);
-                cross3(f.v + 3, Iv + 3, c1);
-                cross3(f.v, Iv + 3, c2);
-                double fbv[6];
-                for (int r = 0; r < 3; r++) {
-                    fbv[r] = Ia[r] + c0[r] + c1[r];
-                    fbv[3 + r] = Ia[3 + r] + c2[r];
-                }
-                x.st_cin(b, ci);
-                x.st_fb(b, fbv);
             }
             tm_wait_st();
             if (c_m.chain_pslot[c] >= 0) {
-                const int base = x.o.jf + 24 * c_m.chain_pslot[c];
+                if (MODE != 2) {
 #pragma unroll
-                for (int k = 0; k < 3; k++) x.at(base, k) = f.p[k];
+                    for (int k = 0; k < 6; k++) x.at(x.o.ja + 6 * c_m.chain_pslot[c], k) = a[k];
+                }
+                if (MODE != 0) {
+                    const int base = x.o.jf + 24 * c_m.chain_pslot[c];
 #pragma unroll
-                for (int k = 0; k < 9; k++) x.at(base, 3 + k) = f.R[k];
+                    for (int k = 0; k < 3; k++) x.at(base, k) = f.p[k];
 #pragma unroll
-                for (int k = 0; k < 6; k++) { x.at(base, 12 + k) = f.v[k]; x.at(base, 18 + k) = f.a[k]; }
+                    for (int k = 0; k < 9; k++) x.at(base, 3 + k) = f.R[k];
+#pragma unroll
+                    for (int k = 0; k < 6; k++) { x.at(base, 12 + k) = f.v[k]; x.at(base, 18 + k) = f.a[k]; }
+                }
             }
         }
         __syncthreads();
     }
 }
 
+// Backward articulated-body sweep.  MODE 0: forward dynamics, bias C_i = S_i . F stored, rhs = tau_i - C_i, pivots
+// S.U + armature.  MODE 1: stable PD (humanoid_v1.py:130-144): rhs_i = -C_i - kp e_i - kd v_i evaluated on the
+// fly from the shared q / v rows and the stored bias, pivots + kd h.
 template <int MODE>
 __device__ void t4_backward(const T4Ctx &x, T4Local &l) {
     for (int L = c_m.nlevel - 1; L >= 0; L--) {
@@ -1111,11 +1190,14 @@ __device__ void t4_backward(const T4Ctx &x, T4Local &l) {
                 for (int i = da + nd - 1; i >= da; i--) {
                     double S[6], U[6];
                     t4_load_S(x, i, b, S);
-                    double rhs = tm_ld1(x.a_tau(i));
+                    double rhs;
                     if (MODE == 0) {
-                        double Ci = dot6(S, w.F);
+                        const double Ci = dot6(S, w.F);
                         tm_st1(x.a_c(i), Ci);
-                        rhs -= Ci;
+                        rhs = tm_ld1(x.a_tau(i)) - Ci;
+                    } else {
+                        const double eq = i >= 6 ? x.at(x.o.q, i + 1) - l.ctrl[i] : 0.0;
+                        rhs = -tm_ld1(x.a_c(i)) - c_m.kp[i] * eq - c_m.kd[i] * x.at(x.o.v, i);
                     }
 #pragma unroll
                     for (int r = 0; r < 6; r++) {
@@ -1154,35 +1236,6 @@ __device__ void t4_backward(const T4Ctx &x, T4Local &l) {
     }
 }
 
-__device__ void t4_accel(const T4Ctx &x, T4Local &l) {
-    for (int L = 0; L < c_m.nlevel; L++) {
-        const int c = t4_my_chain(L, x.w);
-        if (c >= 0) {
-            double a[6];
-            const int pc = c_m.chain_parent[c];
-#pragma unroll
-            for (int k = 0; k < 6; k++) a[k] = pc >= 0 ? x.at(x.o.ja + 6 * c_m.chain_pslot[pc], k) : 0.0;
-            for (int b = c_m.chain_lo[c]; b <= c_m.chain_hi[c]; b++) {
-                const int da = c_m.body_dofadr[b], nd = c_m.body_dofnum[b];
-                for (int i = da; i < da + nd; i++) {
-                    double S[6], U[6];
-                    t4_load_S(x, i, b, S);
-#pragma unroll
-                    for (int r = 0; r < 6; r++) U[r] = x.at(x.o.U, 6 * i + r);
-                    const double xi = tm_ld1(x.a_dinv(i)) * (tm_ld1(x.a_u(i)) - dot6(U, a));
-                    l.x[i] = xi;
-#pragma unroll
-                    for (int r = 0; r < 6; r++) a[r] += S[r] * xi;
-                }
-            }
-            if (c_m.chain_pslot[c] >= 0)
-#pragma unroll
-                for (int k = 0; k < 6; k++) x.at(x.o.ja + 6 * c_m.chain_pslot[c], k) = a[k];
-        }
-        __syncthreads();
-    }
-}
-
 // loop helper: for every dof i owned by warp w
 #define T4_FOR_OWN_DOFS(i, b)                                                                       \
     for (int _c = 0; _c < c_m.nchain; _c++)                                                          \
@@ -1191,55 +1244,18 @@ __device__ void t4_accel(const T4Ctx &x, T4Local &l) {
                 for (int i = c_m.body_dofadr[b]; i < c_m.body_dofadr[b] + c_m.body_dofnum[b]; i++)
 
 __device__ void t4_forward_only(const T4Ctx &x, T4Local &l) {      // sim.forward()
-    t4_kinematics(x, l);
+    t4_forward<2>(x, l);
     T4_FOR_OWN_DOFS(i, b) tm_st1(x.a_tau(i), 0.0);
     tm_wait_st();
     t4_backward<0>(x, l);
 }
 
+// One iteration of do_simulation (humanoid_v1.py:166-174): stable-PD torque on the stale tree data, then mj_step.
 __device__ void t4_substep(const T4Ctx &x, T4Local &l) {
-    const double h = c_m.h;
-    T4_FOR_OWN_DOFS(i, b) {
-        double eq = i >= 6 ? x.at(x.o.q, i + 1) - l.ctrl[i] : 0.0;
-        tm_st1(x.a_tau(i), -tm_ld1(x.a_c(i)) - c_m.kp[i] * eq - c_m.kd[i] * x.at(x.o.v, i));
-    }
-    tm_wait_st();
-    t4_backward<1>(x, l);
-    t4_accel(x, l);
-    T4_FOR_OWN_DOFS(i, b) {
-        double t = 0.0;
-        if (i >= 6) {
-            double eq = x.at(x.o.q, i + 1) - l.ctrl[i];
-            t = -c_m.kp[i] * eq - c_m.kd[i] * (x.at(x.o.v, i) + l.x[i] * h);
-            double lim = c_m.tlim[i];
-            t = t < -lim ? -lim : (t > lim ? lim : t);
-        }
-        tm_st1(x.a_tau(i), t);
-    }
-    tm_wait_st();
-    t4_kinematics(x, l);
-    t4_backward<0>(x, l);
-    t4_accel(x, l);
-    T4_FOR_OWN_DOFS(i, b) {
-        double vn = x.at(x.o.v, i) + h * l.x[i];
-        x.at(x.o.v, i) = vn;
-        if (i >= 6) x.at(x.o.q, i + 1) += h * vn;
-    }
-    if (c_m.chain_warp[0] == x.w) {         // owner of the root: position + quaternion integration
-        for (int k = 0; k < 3; k++) x.at(x.o.q, k) += h * x.at(x.o.v, k);
-        double wv[3] = {x.at(x.o.v, 3), x.at(x.o.v, 4), x.at(x.o.v, 5)};
-        double n = sqrt(dot3(wv, wv)), ax[3] = {1.0, 0.0, 0.0};
-        if (n > 1e-15) { ax[0] = wv[0] / n; ax[1] = wv[1] / n; ax[2] = wv[2] / n; }
-        double sn, cs;
-        sincos(0.5 * h * n, &sn, &cs);
-        double qr[4] = {cs, ax[0] * sn, ax[1] * sn, ax[2] * sn};
-        double q4[4] = {x.at(x.o.q, 3), x.at(x.o.q, 4), x.at(x.o.q, 5), x.at(x.o.q, 6)};
-        double qn = sqrt(q4[0] * q4[0] + q4[1] * q4[1] + q4[2] * q4[2] + q4[3] * q4[3]);
-        for (int k = 0; k < 4; k++) q4[k] /= qn;
-        double o4[4];
-        quat_mul(q4, qr, o4);
-        for (int k = 0; k < 4; k++) x.at(x.o.q, 3 + k) = o4[k];
-    }
+    t4_backward<1>(x, l);       // (M_stale + Kd h) factor + reduce, rhs from the current q, v
+    t4_forward<1>(x, l);        // desired accel -> clipped torque ; kinematics / velocities / body forces at (q, v)
+    t4_backward<0>(x, l);       // bias C, M factor + reduce with rhs = torque - C
+    t4_forward<0>(x, l);        // qacc, semi-implicit Euler
 }
 
 // observation entry k (humanoid_v1.py:73-96) from the shared q / v rows; hd = de-headed root quaternion,
