@@ -1313,15 +1313,27 @@ __device__ __forceinline__ void t4_mlp_layer(const double *__restrict__ Wp, cons
         }
         const int k0 = c * MLP_KC;
         const int kn = K - k0 < MLP_KC ? K - k0 : MLP_KC;
-#pragma unroll 4
+        // software-pipelined: operands of step kk+1 are loaded before the 8 FMAs of step kk issue
+        const double *xp = xs + (size_t)k0 * 32 + lane;
+        double xv = xp[0];
+        double2 wv[JB / 2];
+#pragma unroll
+        for (int jj = 0; jj < JB / 2; jj++) wv[jj] = st2[jj];
+#pragma unroll 2
         for (int kk = 0; kk < kn; kk++) {
-            const double xv = xs[(k0 + kk) * 32 + lane];
+            const int kq = kk + 1 < MLP_KC ? kk + 1 : kk;           // stays inside the tile / activation rows
+            const double xn = xp[(size_t)kq * 32];
+            double2 wn[JB / 2];
+#pragma unroll
+            for (int jj = 0; jj < JB / 2; jj++) wn[jj] = st2[kq * (JB / 2) + jj];
 #pragma unroll
             for (int jj = 0; jj < JB / 2; jj++) {
-                const double2 ww = st2[kk * (JB / 2) + jj];
-                acc[2 * jj] += ww.x * xv;
-                acc[2 * jj + 1] += ww.y * xv;
+                acc[2 * jj] += wv[jj].x * xv;
+                acc[2 * jj + 1] += wv[jj].y * xv;
             }
+            xv = xn;
+#pragma unroll
+            for (int jj = 0; jj < JB / 2; jj++) wv[jj] = wn[jj];
         }
         if (c == nchunk - 1) {
 #pragma unroll
