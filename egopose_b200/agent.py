@@ -96,6 +96,7 @@ class _Trunk:
         self.f = flat
         self.names = ['net.affine_layers.0', 'net.affine_layers.1', head]
         self.buf = {}
+        self.cap = {}
 
     def W(self, i):
         return self.f.view(self.f.flat, self.names[i] + '.weight')
@@ -110,11 +111,14 @@ class _Trunk:
         return self.f.view(self.f.grad, self.names[i] + '.bias')
 
     def _buf(self, key, shape, like):
-        t = self.buf.get(key)
-        if t is None or tuple(t.shape) != tuple(shape):
+        """reusable activation buffer: grows to the largest row count seen, hands out a [:n] view"""
+        t = self.cap.get(key)
+        if t is None or t.shape[0] < shape[0] or tuple(t.shape[1:]) != tuple(shape[1:]):
             t = torch.empty(shape, dtype=torch.float64, device=like.device)
-            self.buf[key] = t
-        return t
+            self.cap[key] = t
+        v = t[:shape[0]]
+        self.buf[key] = v
+        return v
 
     def forward(self, x):
         n = x.shape[0]
@@ -382,9 +386,6 @@ class AgentPPO(AgentPG):
         self.opt_batch_size = opt_batch_size
         self.use_mini_batch = use_mini_batch
         self.policy_grad_clip = policy_grad_clip
-        if use_mini_batch:
-            raise lib.EgpError('the mini-batch branch (agent_ppo.py:24-43) is not built; AgentEgo forces full batch '
-                               '(agent_ego.py:11)')
 
     def _max_norm(self):
         if not self.policy_grad_clip:
@@ -393,32 +394,79 @@ class AgentPPO(AgentPG):
             raise lib.EgpError('one (params, max_norm) clip group is supported (ego_mimic.py:90)')
         return float(self.policy_grad_clip[0][1])
 
+    def _policy_step(self, xp, actions, adv, logp0, exps, inv_count, log_std, max_norm, mu=None):
+        """ppo_loss forward+backward, gradient all-reduce, clip + Adam (agent_ppo.py:47-51 / :38-43)"""
+        if mu is None:
+            mu = self._pt.forward(xp)
+        dmu = self._pt._buf('dy', mu.shape, xp)
+        self._scal[1:2].zero_()
+        dls = None
+        if self._learn_std:
+            dls = self._pf.view(self._pf.grad, 'action_log_std').view(-1)
+            dls.zero_()
+        lib.ppo_loss_grad(mu, actions, log_std, adv, self._stats, logp0, exps, self.clip_epsilon, inv_count, dmu,
+                          dls, self._scal[1:2])
+        self._pt.backward(dmu)
+        if _dist() is not None:
+            _dist().all_reduce(self._pf.grad)
+        self._pf.adam(max_norm)
+        return self._scal[1:2].clone()
+
+    def _update_policy_minibatch(self, xp, xv, actions, returns, adv, exps, logp0, log_std, max_norm):
+        """agents/agent_ppo.py:24-43: per epoch a fresh np.random.shuffle permutation applied on top of the
+        previous one, contiguous slices of opt_batch_size rows, value then policy step per slice with per-slice
+        means.  The permutation is composed on the host and applied with one row-gather per array."""
+        n = xp.shape[0]
+        B = int(self.opt_batch_size)
+        nb = int(math.ceil(n / B))
+        dev = xp.device
+        same_x = xv is xp
+        g = {k: torch.empty_like(t) for k, t in (('xp', xp), ('ac', actions), ('ret', returns), ('adv', adv), ('lp', logp0),
+                                                  ('ex', exps))}
+        if not same_x:
+            g['xv'] = torch.empty_like(xv)
+        cur = np.arange(n)
+        surr, vloss = [], []
+        for _ in range(self.opt_num_epochs):
+            perm = np.arange(n)
+            np.random.shuffle(perm)                                      # :26-27 (global numpy RNG, like the reference)
+            cur = cur[perm]
+            pd = torch.from_numpy(cur).to(dev, non_blocking=True)
+            for k, src in (('xp', xp), ('ac', actions), ('ret', returns), ('adv', adv), ('lp', logp0), ('ex', exps)):
+                lib.gather_rows(src, pd, g[k])
+            if not same_x:
+                lib.gather_rows(xv, pd, g['xv'])
+            gxv = g['xp'] if same_x else g['xv']
+            # exps count of every slice with one device->host copy per epoch
+            pad = nb * B - n
+            ex = torch.cat([g['ex'], g['ex'].new_zeros(pad)]) if pad else g['ex']
+            counts = ex.view(nb, B).sum(1)
+            dist_utils.allreduce_sum_(counts)
+            counts = counts.cpu().numpy()
+            ws = dist_utils.world_size()
+            for i in range(nb):
+                lo, hi = i * B, min((i + 1) * B, n)
+                self.update_value(gxv[lo:hi], g['ret'][lo:hi], 1.0 / ((hi - lo) * ws))
+                vloss.append(self._scal[0:1].clone())
+                surr.append(self._policy_step(g['xp'][lo:hi], g['ac'][lo:hi], g['adv'][lo:hi], g['lp'][lo:hi], g['ex'][lo:hi],
+                                              1.0 / float(counts[i]), log_std, max_norm))
+        self.last_info = dict(surr_loss=surr, value_loss=vloss)
+
     def update_policy(self, xp, xv, actions, returns, adv, exps, inv_count, inv_n):
-        """agents/agent_ppo.py:16-51, full-batch branch"""
+        """agents/agent_ppo.py:16-51"""
         log_std = self.policy_net.action_log_std.data.view(-1)
         mu = self._pt.forward(xp)
         logp0 = lib.gauss_logp(mu, actions, log_std)                    # fixed_log_probs (:18-20)
         max_norm = self._max_norm()
+        if self.use_mini_batch:
+            return self._update_policy_minibatch(xp, xv, actions, returns, adv, exps, logp0, log_std, max_norm)
         surr, vloss = [], []
         d = _dist()
         for ep in range(self.opt_num_epochs):
             self.update_value(xv, returns, inv_n, reuse_forward=(ep == 0 and self._value_fresh))     # :46
             vloss.append(self._scal[0:1].clone())
-            if ep > 0:                                                   # epoch 0 reuses the fixed-log-prob forward
-                mu = self._pt.forward(xp)
-            dmu = self._pt._buf('dy', mu.shape, xp)
-            self._scal[1:2].zero_()
-            dls = None
-            if self._learn_std:
-                dls = self._pf.view(self._pf.grad, 'action_log_std').view(-1)
-                dls.zero_()
-            lib.ppo_loss_grad(mu, actions, log_std, adv, self._stats, logp0, exps, self.clip_epsilon, inv_count, dmu,
-                              dls, self._scal[1:2])                      # :47,58-65
-            self._pt.backward(dmu)
-            if d is not None:
-                d.all_reduce(self._pf.grad)
-            self._pf.adam(max_norm)                                      # :50-51 clip + step
-            surr.append(self._scal[1:2].clone())
+            surr.append(self._policy_step(xp, actions, adv, logp0, exps, inv_count, log_std, max_norm,
+                                          mu=mu if ep == 0 else None))      # epoch 0 reuses the fixed-log-prob forward
         self.last_info = dict(surr_loss=surr, value_loss=vloss)
 
     def losses(self):
@@ -435,8 +483,11 @@ class AgentPPO(AgentPG):
 
 
 class AgentEgo(AgentPPO):
-    def __init__(self, policy_vs_net=None, value_vs_net=None, **kwargs):
-        super().__init__(use_mini_batch=False, **kwargs)
+    def __init__(self, policy_vs_net=None, value_vs_net=None, use_mini_batch=False, **kwargs):
+        # the reference forces the full-batch branch (agent_ego.py:11) because its BiLSTM context packing needs
+        # whole episodes; the per-frame context table has no such constraint, so BASELINE config 5's
+        # mini-batch PPO can be switched on explicitly (use_mini_batch=True, opt_batch_size=...)
+        super().__init__(use_mini_batch=use_mini_batch, **kwargs)
         self.traj_cls = TrajBatchEgo
         self.policy_vs_net = policy_vs_net
         self.value_vs_net = value_vs_net

@@ -342,6 +342,18 @@ colsum_kernel(const double *__restrict__ x, long long n, int dim, long long rows
     }
 }
 
+// out[i][:] = in[perm[i]][:]  (agents/agent_ppo.py:30-32 'states[perm].clone()' for every batch array)
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const double *__restrict__ in, const long long *__restrict__ perm, long long n, int dim,
+                   double *__restrict__ out) {
+    const long long total = n * dim;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long i = idx / dim;
+        const int j = (int)(idx - i * dim);
+        out[idx] = in[perm[i] * dim + j];
+    }
+}
+
 // fused relu backward + bias gradient: dy *= (y > 0) in place and out[c] += sum_rows dy[:, c] (one pass)
 __global__ void __launch_bounds__(256)
 relu_bwd_colsum_kernel(double *__restrict__ dy, const double *__restrict__ y, long long n, int dim, long long rows_per_block,
@@ -566,6 +578,13 @@ int egp_colsum_f64(const double *d_x, int64_t n, int dim, double *d_out, void *s
     blocks = (int)((n + rpb - 1) / rpb);
     colsum_kernel<<<blocks, 256, 0, st>>>(d_x, (long long)n, dim, rpb, d_out);
     EGP_CHECK_LAUNCH("colsum_kernel");
+    return EGP_OK;
+}
+
+int egp_gather_rows_f64(const double *d_in, const int64_t *d_perm, int64_t n, int dim, double *d_out, void *stream) {
+    if (n <= 0 || dim <= 0 || !d_in || !d_perm || !d_out) { set_error("egp_gather_rows_f64: bad argument"); return EGP_EINVAL; }
+    gather_rows_kernel<<<grid_for(n * dim, 256), 256, 0, (cudaStream_t)stream>>>(d_in, (const long long *)d_perm, (long long)n, dim, d_out);
+    EGP_CHECK_LAUNCH("gather_rows_kernel");
     return EGP_OK;
 }
 

@@ -90,6 +90,7 @@ SYMBOLS = {
     'egp_value_loss_grad_f64': (_int, [_vp, _vp, _d, _i64, _vp, _vp, _vp]),
     'egp_bias_relu_f64': (_int, [_vp, _vp, _i64, _int, _vp]),
     'egp_relu_bwd_f64': (_int, [_vp, _vp, _i64, _int, _vp]),
+    'egp_gather_rows_f64': (_int, [_vp, _vp, _i64, _int, _vp, _vp]),
     'egp_relu_bwd_colsum_f64': (_int, [_vp, _vp, _i64, _int, _vp, _vp]),
     'egp_colsum_f64': (_int, [_vp, _i64, _int, _vp, _vp]),
     'egp_col_moments_f64': (_int, [_vp, _i64, _int, _vp, _vp, _vp]),
@@ -406,6 +407,15 @@ def relu_bwd_(dy, y):
     check(load().egp_relu_bwd_f64(ptr(dy), ptr(y), y.shape[0], y.shape[1], stream_ptr()), 'egp_relu_bwd_f64')
     launches += 1
     return dy
+
+
+def gather_rows(src, perm, out):
+    """out[i] = src[perm[i]] for [n] or [n, dim] float64 tensors; perm int64"""
+    global launches
+    dim = 1 if src.dim() == 1 else src.shape[1]
+    check(load().egp_gather_rows_f64(ptr(src), ptr(perm), perm.numel(), dim, ptr(out), stream_ptr()), 'egp_gather_rows_f64')
+    launches += 1
+    return out
 
 
 def relu_bwd_colsum_(dy, y, out):

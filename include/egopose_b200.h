@@ -193,6 +193,8 @@ int egp_value_loss_grad_f64(const double *d_v, const double *d_ret, double inv_n
 /* fused bias + relu forward: y = relu(y + b) in place, y [n][dim]; and backward mask dy *= (y > 0) */
 int egp_bias_relu_f64(double *d_y, const double *d_b, int64_t n, int dim, void *stream);
 int egp_relu_bwd_f64(double *d_dy, const double *d_y, int64_t n, int dim, void *stream);
+/* row gather out[i][:] = in[perm[i]][:] (the mini-batch shuffle of agents/agent_ppo.py:26-32) */
+int egp_gather_rows_f64(const double *d_in, const int64_t *d_perm, int64_t n, int dim, double *d_out, void *stream);
 /* fused: dy *= (y > 0) in place and out[dim] = column sums of the masked dy (bias gradient), one pass */
 int egp_relu_bwd_colsum_f64(double *d_dy, const double *d_y, int64_t n, int dim, double *d_out, void *stream);
 /* column sums (bias gradients): out[dim] = sum_n x[n][dim] */

@@ -67,7 +67,7 @@ def log_prob(mean, log_std, actions):
 
 
 def ppo_update(pol, val, states, actions, returns, advantages, exps, clip_epsilon, lr_p, lr_v, max_norm, epochs,
-               fix_std=True, threads=None, states_v=None):
+               fix_std=True, threads=None, states_v=None, mini_batch=None, perm_rng=None):
     """agents/agent_ppo.py:16-51 (full-batch branch) + agent_pg.py:19-26 update_value + :53-56 clip.
     ``pol`` / ``val`` are dicts name -> float64 numpy arrays in state-dict layout; returns
     (new_pol, new_val, info) with per-epoch surrogate loss, pre-step value loss and policy grad norm."""
@@ -86,6 +86,35 @@ def ppo_update(pol, val, states, actions, returns, advantages, exps, clip_epsilo
     with torch.no_grad():
         fixed_lp = log_prob(policy_mean(st, P), P['action_log_std'], ac)
     info = dict(surr_loss=[], value_loss=[], grad_norm=[], fixed_log_probs=fixed_lp.numpy().copy())
+    if mini_batch:
+        # agents/agent_ppo.py:24-43: cumulative np.random.shuffle permutations, contiguous slices, per-slice means
+        rng = perm_rng if perm_rng is not None else np.random
+        ex = torch.from_numpy(np.asarray(exps, dtype=np.float64).ravel())
+        n = st.shape[0]
+        for _ in range(epochs):
+            perm = np.arange(n)
+            rng.shuffle(perm)
+            perm = torch.from_numpy(perm)
+            st, stv, ac, ret, adv, fixed_lp, ex = st[perm], stv[perm], ac[perm], ret[perm], adv[perm], fixed_lp[perm], ex[perm]
+            for i in range(int(math.ceil(n / mini_batch))):
+                sl = slice(i * mini_batch, min((i + 1) * mini_batch, n))
+                bi = ex[sl].nonzero().squeeze(1)
+                vloss = (value_forward(stv[sl], V) - ret[sl]).pow(2).mean()
+                opt_v.zero_grad()
+                vloss.backward()
+                opt_v.step()
+                lp = log_prob(policy_mean(st[sl][bi], P), P['action_log_std'], ac[sl][bi])
+                ratio = torch.exp(lp - fixed_lp[sl][bi])
+                a = adv[sl][bi]
+                surr = -torch.min(ratio * a, torch.clamp(ratio, 1.0 - clip_epsilon, 1.0 + clip_epsilon) * a).mean()
+                opt_p.zero_grad()
+                surr.backward()
+                if max_norm is not None:
+                    torch.nn.utils.clip_grad_norm_(pparams, max_norm)
+                opt_p.step()
+                info['surr_loss'].append(surr.item())
+                info['value_loss'].append(vloss.item())
+        return ({k: v.detach().numpy() for k, v in P.items()}, {k: v.detach().numpy() for k, v in V.items()}, info)
     for _ in range(epochs):
         vloss = (value_forward(stv, V) - ret).pow(2).mean()
         opt_v.zero_grad()

@@ -107,6 +107,45 @@ def gen_ppo():
     print('ppo_small: surr', surr, 'vloss', vloss, 'gnorm', gnorm)
 
 
+def gen_ppo_minibatch():
+    """agents/agent_ppo.py:24-43 (use_mini_batch=True) on the ppo_small batch: 2 epochs x ceil(640/200) steps"""
+    from agents.agent_ppo import AgentPPO
+    from core.critic import Value
+    from core.policy_gaussian import PolicyGaussian
+    from models.mlp import MLP
+    g = np.load(os.path.join(OUT, 'ppo_small.npz'))
+    torch.manual_seed(1)
+    D, A, H = 24, 6, (32, 16)
+    policy = PolicyGaussian(MLP(D, H, 'relu'), A, log_std=-2.3, fix_std=True)
+    value = Value(MLP(D, H, 'relu'))
+    policy.load_state_dict({k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith('p0.')})
+    value.load_state_dict({k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith('v0.')})
+    opt_p = torch.optim.Adam(policy.parameters(), lr=5e-3)
+    opt_v = torch.optim.Adam(value.parameters(), lr=3e-3)
+    pparams = list(policy.parameters())
+    agent = AgentPPO(env=None, dtype=torch.float64, device=torch.device('cpu'), policy_net=policy, value_net=value,
+                     optimizer_policy=opt_p, optimizer_value=opt_v, opt_num_epochs=2, gamma=0.95, tau=0.95,
+                     clip_epsilon=0.2, policy_grad_clip=[(pparams, 0.05)], use_mini_batch=True, opt_batch_size=200)
+    surr = []
+    orig_loss = agent.ppo_loss
+
+    def rec_loss(*a):
+        loss = orig_loss(*a)
+        surr.append(loss.item())
+        return loss
+    agent.ppo_loss = rec_loss
+    np.random.seed(123)
+    agent.update_policy(torch.from_numpy(g['states']), torch.from_numpy(g['actions']), torch.from_numpy(g['returns']),
+                        torch.from_numpy(g['advantages']), torch.from_numpy(g['exps']))
+    out = {'surr_loss': np.array(surr), 'seed': np.array(123), 'opt_batch_size': np.array(200), 'epochs': np.array(2)}
+    for k, v in policy.state_dict().items():
+        out['p.' + k] = v.numpy().copy()
+    for k, v in value.state_dict().items():
+        out['v.' + k] = v.numpy().copy()
+    np.savez_compressed(os.path.join(OUT, 'ppo_minibatch.npz'), **out)
+    print('ppo_minibatch: surr', np.round(surr, 5))
+
+
 def gen_math():
     from utils.math import (de_heading, get_angvel_fd, get_heading_q, get_qvel_fd, multi_quat_diff, multi_quat_norm,
                             transform_vec)
@@ -275,6 +314,8 @@ if __name__ == '__main__':
     which = sys.argv[1:] or ['ppo', 'math', 'zfilter', 'env']
     if 'ppo' in which:
         gen_ppo()
+    if 'ppo_mb' in which or 'ppo' in which:
+        gen_ppo_minibatch()
     if 'math' in which:
         gen_math()
     if 'zfilter' in which:

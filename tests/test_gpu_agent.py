@@ -47,6 +47,30 @@ def test_agent_ppo_update_matches_reference_golden(golden):
     assert int(st['step']) == 3 and st['exp_avg'].abs().sum() > 0
 
 
+def test_agent_ppo_minibatch_matches_reference_golden(golden):
+    """agents/agent_ppo.py:24-43 mini-batch branch (BASELINE config 5): 2 epochs x 4 slices of <= 200 rows"""
+    from egopose_b200.agent import AgentPPO
+    from egopose_b200.trajbatch import TrajBatch
+    g, m = golden('ppo_small'), golden('ppo_minibatch')
+    gamma, tau, clip, lr_p, lr_v, max_norm = g['hyper']
+    pol, val = _nets_from(g, 'p0.', 'v0.', 24, (32, 16), 6)
+    opt_p = torch.optim.Adam(pol.parameters(), lr=lr_p)
+    opt_v = torch.optim.Adam(val.parameters(), lr=lr_v)
+    agent = AgentPPO(env=None, dtype=torch.float64, device=torch.device('cuda'), policy_net=pol, value_net=val,
+                     optimizer_policy=opt_p, optimizer_value=opt_v, opt_num_epochs=int(m['epochs']), gamma=gamma, tau=tau,
+                     clip_epsilon=clip, policy_grad_clip=[(list(pol.parameters()), max_norm)], use_mini_batch=True,
+                     opt_batch_size=int(m['opt_batch_size']))
+    batch = TrajBatch.from_numpy(states=g['states'], actions=g['actions'], rewards=g['rewards'], masks=g['masks'],
+                                 exps=g['exps'])
+    np.random.seed(int(m['seed']))
+    agent.update_params(batch)
+    assert np.allclose(agent.losses()['surr_loss'], m['surr_loss'], rtol=1e-8, atol=1e-11)
+    for k, v in pol.state_dict().items():
+        assert np.allclose(v.cpu().numpy(), m['p.' + k], rtol=1e-8, atol=1e-10), k
+    for k, v in val.state_dict().items():
+        assert np.allclose(v.cpu().numpy(), m['v.' + k], rtol=1e-8, atol=1e-10), k
+
+
 def test_agent_ego_sample_and_update_vs_oracle():
     from egopose_b200.agent import AgentEgo
     from egopose_b200.config import Config

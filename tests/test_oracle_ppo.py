@@ -39,3 +39,18 @@ def test_zfilter_matches_reference(golden):
     n2, M2, S2 = ppo.zfilter_merge(0, None, None, g['xs'][:13])
     n2, M2, S2 = ppo.zfilter_merge(n2, M2, S2, g['xs'][13:])
     assert n2 == n and np.allclose(M2, M, rtol=1e-12) and np.allclose(S2, S, rtol=1e-11)
+
+
+def test_ppo_minibatch_matches_reference(golden):
+    g, m = golden('ppo_small'), golden('ppo_minibatch')
+    gamma, tau, clip, lr_p, lr_v, max_norm = g['hyper']
+    pol = {k[3:]: g[k] for k in g.files if k.startswith('p0.')}
+    val = {k[3:]: g[k] for k in g.files if k.startswith('v0.')}
+    new_p, new_v, info = ppo.ppo_update(pol, val, g['states'], g['actions'], g['returns'], g['advantages'], g['exps'],
+                                        clip, lr_p, lr_v, max_norm, epochs=int(m['epochs']),
+                                        mini_batch=int(m['opt_batch_size']), perm_rng=np.random.RandomState(int(m['seed'])))
+    assert np.allclose(info['surr_loss'], m['surr_loss'], rtol=1e-10, atol=1e-12)
+    for k in new_p:
+        assert np.allclose(new_p[k], m['p.' + k], rtol=1e-9, atol=1e-11), k
+    for k in new_v:
+        assert np.allclose(new_v[k], m['v.' + k], rtol=1e-9, atol=1e-11), k
