@@ -597,7 +597,8 @@ struct RolloutArgs {
     // policy (transposed + padded): W1t [D][H1p], W2t [H1][H2p], W3t [H2][Ap]
     const double *W1t, *b1, *W2t, *b2, *W3t, *b3, *log_std;
     int D, H1, H2, A, H1p, H2p, Ap;
-    int K1p, K2p, K3p;      // T4: k padded to MLP_KC (weights packed as tiles)
+    int K1p, K2p, K3p;      // T4: k padded to the tile depth (weights packed as tiles)
+    int kc, chunk23;        // T4: tile depth (64 | 32); 1 = chunked layer-2/3 path for wide policies
 };
 
 // one dense layer for the 32 environments of the CTA: ys[j][lane] = act(b[j] + sum_k Wt[k][j] xs[k][lane])
@@ -1274,72 +1275,138 @@ __device__ __forceinline__ double t4_obs_entry(const T4Ctx &x, int k, const doub
 // packed as tiles Wp[block][k][8] (k padded to MLP_KC); each warp streams its tiles HBM/L2 -> registers
 // (coalesced 128-bit loads, issued one tile ahead) -> its private shared-memory tile -> broadcast LDS, so the
 // inner loop is FP64-pipe bound instead of waiting on warp-uniform global loads.
-constexpr int MLP_KC = 64;
-constexpr int MLP_TILE = MLP_KC * JB;        // doubles per tile
+constexpr int MLP_KC_MAX = 64;               // k rows per weight tile (64, or 32 for wide policies)
 
-template <bool RELU>
+// Computes output blocks [jb0, jb1) (8 neurons each, split over the warps) of one dense layer:
+// ys[(j - 8*jb0 + out_row0)][lane] = act(bias[j] + sum_k W[j][k] xs[k][lane]).
+template <bool RELU, int KC>
 __device__ __forceinline__ void t4_mlp_layer(const double *__restrict__ Wp, const double *__restrict__ bias, int K, int Kp,
-                                             int Np, const double *xs, double *ys, double *stage, int lane, int w) {
-    const int nchunk = Kp / MLP_KC, njb = Np / JB;
+                                             int jb0, int jb1, int out_row0, const double *xs, double *ys, double *stage,
+                                             int lane, int w) {
+    constexpr int TILE = KC * JB;
+    const int nchunk = Kp / KC, njb = jb1 - jb0;
     const int my_blocks = (njb - w + T4_WARPS - 1) / T4_WARPS;
-    const int ntile = my_blocks * nchunk;
+    const int ntile = my_blocks > 0 ? my_blocks * nchunk : 0;
     if (ntile <= 0) return;
-    double2 pre[MLP_TILE / 64];                                      // this lane's share of the tile in flight
+    double2 pre[TILE / 64];                                          // this lane's share of the tile in flight
     auto tile_ptr = [&](int t) {
-        const int jb = w + T4_WARPS * (t / nchunk), c = t % nchunk;
-        return reinterpret_cast<const double2 *>(Wp + ((size_t)jb * Kp + (size_t)c * MLP_KC) * JB);
+        const int jb = jb0 + w + T4_WARPS * (t / nchunk), c = t % nchunk;
+        return reinterpret_cast<const double2 *>(Wp + ((size_t)jb * Kp + (size_t)c * KC) * JB);
     };
     {
         const double2 *src = tile_ptr(0);
 #pragma unroll
-        for (int m = 0; m < MLP_TILE / 64; m++) pre[m] = __ldg(src + lane + 32 * m);
+        for (int m = 0; m < TILE / 64; m++) pre[m] = __ldg(src + lane + 32 * m);
     }
     double acc[JB];
     double2 *st2 = reinterpret_cast<double2 *>(stage);
     for (int t = 0; t < ntile; t++) {
-        const int jb = w + T4_WARPS * (t / nchunk), c = t % nchunk;
+        const int jb = jb0 + w + T4_WARPS * (t / nchunk), c = t % nchunk;
         if (c == 0) {
 #pragma unroll
             for (int jj = 0; jj < JB; jj++) acc[jj] = bias[jb * JB + jj];
         }
         __syncwarp();
 #pragma unroll
-        for (int m = 0; m < MLP_TILE / 64; m++) st2[lane + 32 * m] = pre[m];
+        for (int m = 0; m < TILE / 64; m++) st2[lane + 32 * m] = pre[m];
         __syncwarp();
         if (t + 1 < ntile) {
             const double2 *src = tile_ptr(t + 1);
 #pragma unroll
-            for (int m = 0; m < MLP_TILE / 64; m++) pre[m] = __ldg(src + lane + 32 * m);
+            for (int m = 0; m < TILE / 64; m++) pre[m] = __ldg(src + lane + 32 * m);
         }
-        const int k0 = c * MLP_KC;
-        const int kn = K - k0 < MLP_KC ? K - k0 : MLP_KC;
-        // software-pipelined: operands of step kk+1 are loaded before the 8 FMAs of step kk issue
+        const int k0 = c * KC;
+        const int kn = K - k0 < KC ? K - k0 : KC;
         const double *xp = xs + (size_t)k0 * 32 + lane;
-        double xv = xp[0];
-        double2 wv[JB / 2];
-#pragma unroll
-        for (int jj = 0; jj < JB / 2; jj++) wv[jj] = st2[jj];
-#pragma unroll 2
+#pragma unroll 4
         for (int kk = 0; kk < kn; kk++) {
-            const int kq = kk + 1 < MLP_KC ? kk + 1 : kk;           // stays inside the tile / activation rows
-            const double xn = xp[(size_t)kq * 32];
-            double2 wn[JB / 2];
-#pragma unroll
-            for (int jj = 0; jj < JB / 2; jj++) wn[jj] = st2[kq * (JB / 2) + jj];
+            const double xv = xp[(size_t)kk * 32];
 #pragma unroll
             for (int jj = 0; jj < JB / 2; jj++) {
-                acc[2 * jj] += wv[jj].x * xv;
-                acc[2 * jj + 1] += wv[jj].y * xv;
+                const double2 ww = st2[kk * (JB / 2) + jj];
+                acc[2 * jj] += ww.x * xv;
+                acc[2 * jj + 1] += ww.y * xv;
             }
-            xv = xn;
-#pragma unroll
-            for (int jj = 0; jj < JB / 2; jj++) wv[jj] = wn[jj];
         }
         if (c == nchunk - 1) {
 #pragma unroll
-            for (int jj = 0; jj < JB; jj++) ys[(jb * JB + jj) * 32 + lane] = RELU ? fmax(acc[jj], 0.0) : acc[jj];
+            for (int jj = 0; jj < JB; jj++)
+                ys[((jb - jb0) * JB + jj + out_row0) * 32 + lane] = RELU ? fmax(acc[jj], 0.0) : acc[jj];
         }
     }
+}
+
+// acc[8] += W[block jb][k in tiles [t0, t1)] . xs rows (k - row_k0): partial product used by the chunked
+// layer-2/3 path of wide policies (the second hidden layer never exists in full)
+template <int KC>
+__device__ __forceinline__ void t4_mlp_partial(const double *__restrict__ Wp, int K, int Kp, int jb, int t0, int t1, int row_k0,
+                                               const double *xs, double *acc, double *stage, int lane) {
+    constexpr int TILE = KC * JB;
+    double2 *st2 = reinterpret_cast<double2 *>(stage);
+    for (int c = t0; c < t1; c++) {
+        const double2 *src = reinterpret_cast<const double2 *>(Wp + ((size_t)jb * Kp + (size_t)c * KC) * JB);
+        double2 pre[TILE / 64];
+#pragma unroll
+        for (int m = 0; m < TILE / 64; m++) pre[m] = __ldg(src + lane + 32 * m);
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < TILE / 64; m++) st2[lane + 32 * m] = pre[m];
+        __syncwarp();
+        const int k0 = c * KC;
+        const int kn = K - k0 < KC ? K - k0 : KC;
+        for (int kk = 0; kk < kn; kk++) {
+            const double xv = xs[(size_t)(k0 + kk - row_k0) * 32 + lane];
+#pragma unroll
+            for (int jj = 0; jj < JB / 2; jj++) {
+                const double2 ww = st2[kk * (JB / 2) + jj];
+                acc[2 * jj] += ww.x * xv;
+                acc[2 * jj + 1] += ww.y * xv;
+            }
+        }
+    }
+}
+
+// PolicyGaussian trunk + head for the CTA's 32 environments (policy_gaussian.py:19-24, mlp.py:22-25):
+// xs [D rows] -> action means in h1s rows [0, A).  Normal path: three full layers.  Chunked path (second hidden
+// layer too wide for shared memory): layer 2 is produced C2 neurons at a time into the (dead) input rows and
+// immediately folded into register accumulators of the head.
+constexpr int MLP_C2 = 64;
+template <int KC>
+__device__ void t4_policy_forward(const RolloutArgs &A, double *xs, double *h1s, double *stage, int lane, int w) {
+    t4_mlp_layer<true, KC>(A.W1t, A.b1, A.D, A.K1p, 0, A.H1p / JB, 0, xs, h1s, stage, lane, w);
+    __syncthreads();
+    if (!A.chunk23) {
+        t4_mlp_layer<true, KC>(A.W2t, A.b2, A.H1, A.K2p, 0, A.H2p / JB, 0, h1s, xs, stage, lane, w);
+        __syncthreads();
+        t4_mlp_layer<false, KC>(A.W3t, A.b3, A.H2, A.K3p, 0, A.Ap / JB, 0, xs, h1s, stage, lane, w);
+        __syncthreads();
+        return;
+    }
+    double acc3[2][JB];
+    const int nob = A.Ap / JB;                              // head output blocks; warp w owns w and w + 4
+#pragma unroll
+    for (int o = 0; o < 2; o++)
+#pragma unroll
+        for (int jj = 0; jj < JB; jj++) acc3[o][jj] = (w + 4 * o < nob) ? A.b3[(w + 4 * o) * JB + jj] : 0.0;
+    for (int c2 = 0; c2 < A.H2p; c2 += MLP_C2) {
+        const int hi = c2 + MLP_C2 < A.H2p ? c2 + MLP_C2 : A.H2p;
+        t4_mlp_layer<true, KC>(A.W2t, A.b2, A.H1, A.K2p, c2 / JB, hi / JB, 0, h1s, xs, stage, lane, w);
+        __syncthreads();
+        const int khi = hi < A.H2 ? hi : A.H2;              // real neurons of this chunk
+        if (khi > c2) {
+#pragma unroll
+            for (int o = 0; o < 2; o++)
+                if (w + 4 * o < nob)
+                    t4_mlp_partial<KC>(A.W3t, khi, A.K3p, w + 4 * o, c2 / KC, (khi + KC - 1) / KC, c2, xs, acc3[o], stage, lane);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int o = 0; o < 2; o++)
+        if (w + 4 * o < nob)
+#pragma unroll
+            for (int jj = 0; jj < JB; jj++) h1s[((w + 4 * o) * JB + jj) * 32 + lane] = acc3[o][jj];
+    __syncthreads();
 }
 
 __global__ void __launch_bounds__(T4_THREADS, 1)
@@ -1361,10 +1428,11 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
     x.tm = tmem_base + ((uint32_t)(w * 32) << 16);
     const int S = c_m.nq - 2 + c_m.nv, nu = c_m.nu, nv = c_m.nv, nb = c_m.nbody, nq = c_m.nq;
     double *xs = smem + (size_t)O.ax * 32;               // MLP activations alias the axis / anchor / U rows
-    const int xrows = A.D > A.H2p ? A.D : A.H2p;
+    const int h2rows = A.chunk23 ? MLP_C2 : A.H2p;
+    const int xrows = A.D > h2rows ? A.D : h2rows;
     double *h1s = xs + (size_t)xrows * 32;
     const int hrows4 = A.H1p > A.Ap ? A.H1p : A.Ap;
-    double *stage = h1s + (size_t)hrows4 * 32 + (size_t)w * MLP_TILE;   // per-warp weight tile
+    double *stage = h1s + (size_t)hrows4 * 32 + (size_t)w * A.kc * JB;  // per-warp weight tile
     const int T = A.cfg.horizon, E = A.cfg.n_env;
     const double dt = c_m.h * c_m.frame_skip;
     const int env = blockIdx.x * 32 + lane;
@@ -1462,12 +1530,8 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
             }
         }
         __syncthreads();
-        t4_mlp_layer<true>(A.W1t, A.b1, A.D, A.K1p, A.H1p, xs, h1s, stage, lane, w);
-        __syncthreads();
-        t4_mlp_layer<true>(A.W2t, A.b2, A.H1, A.K2p, A.H2p, h1s, xs, stage, lane, w);
-        __syncthreads();
-        t4_mlp_layer<false>(A.W3t, A.b3, A.H2, A.K3p, A.Ap, xs, h1s, stage, lane, w);
-        __syncthreads();
+        if (A.kc == 64) t4_policy_forward<64>(A, xs, h1s, stage, lane, w);
+        else t4_policy_forward<32>(A, xs, h1s, stage, lane, w);
         bool mean_flag = A.cfg.mean_action != 0;
         if (A.in.d_mean_flag) mean_flag = mean_flag || A.in.d_mean_flag[n] != 0;
         else if (A.cfg.noise_rate < 1.0) {
@@ -2101,13 +2165,28 @@ int egp_rollout_f64(EgpModel *m, const EgpPolicyWeights *pol, const EgpRolloutCf
     O.q = 0; O.v = O.q + d.nq; O.ax = O.v + d.nv; O.anc = O.ax + 3 * d.nv; O.U = O.anc + 3 * d.nbody;
     O.jf = O.U + 6 * d.nv; O.jb = O.jf + 24 * d.nparent; O.ja = O.jb + 33 * d.max_sib; O.xp = O.ja + 6 * d.nparent;
     O.red = O.xp + 3 * (EGP_NEE + 1); O.total = O.red + 8;
-    const int stage_rows = T4_WARPS * MLP_TILE / 32;
-    if (O.total - O.ax < xrows + hrows + stage_rows && O.ax + xrows + hrows + stage_rows <= 227 * 1024 / 256)
-        O.total = O.ax + xrows + hrows + stage_rows;        // grow the layout up to the shared-memory limit
-    size_t smem4 = sizeof(double) * 32 * (size_t)O.total;
+    // MLP shared-memory plan inside the alias window [O.ax, limit): input / hidden / weight-stage rows.
+    // Try (tile depth 64, full layers) -> (32, full) -> (32, chunked layer 2/3, second hidden layer never resident).
+    const int limit_rows = 227 * 1024 / 256;
     const char *force = getenv("EGP_ROLLOUT_VARIANT");
-    bool use_t4 = d.t4_ok && xrows + hrows + stage_rows <= O.total - O.ax && smem4 <= 227 * 1024 && !(force && force[0] == '1');
-    auto padk = [](int x) { return (x + MLP_KC - 1) / MLP_KC * MLP_KC; };
+    bool use_t4 = false;
+    A.kc = 64; A.chunk23 = 0;
+    if (d.t4_ok && !(force && force[0] == '1') && A.Ap / JB <= 8) {
+        const int plans[3][2] = {{64, 0}, {32, 0}, {32, 1}};
+        for (int pi = 0; pi < 3 && !use_t4; pi++) {
+            int kc = plans[pi][0], ch = plans[pi][1];
+            int h2r = ch ? MLP_C2 : A.H2p;
+            int xr = A.D > h2r ? A.D : h2r;
+            int need_rows = xr + hrows + T4_WARPS * kc * JB / 32;
+            if (O.ax + need_rows <= limit_rows) {
+                use_t4 = true; A.kc = kc; A.chunk23 = ch;
+                if (O.total - O.ax < need_rows) O.total = O.ax + need_rows;
+            }
+        }
+    }
+    size_t smem4 = sizeof(double) * 32 * (size_t)O.total;
+    const int kcv = A.kc;
+    auto padk = [kcv](int x) { return (x + kcv - 1) / kcv * kcv; };
     A.K1p = use_t4 ? padk(A.D) : A.D; A.K2p = use_t4 ? padk(A.H1) : A.H1; A.K3p = use_t4 ? padk(A.H2) : A.H2;
     size_t need = (size_t)A.K1p * A.H1p + A.H1p + (size_t)A.K2p * A.H2p + A.H2p + (size_t)A.K3p * A.Ap + A.Ap;
     if (need > m->wbuf_elems) {

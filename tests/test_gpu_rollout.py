@@ -25,7 +25,9 @@ def _setup(n_takes, L, ctx_dim, seed):
 
 
 @pytest.mark.parametrize('E,T,ctx_dim,hidden,head_lb', [(5, 14, 0, (24, 16), None), (40, 9, 16, (40, 24), None),
-                                                       (3, 30, 8, (300, 200), -100.0)])
+                                                       (3, 30, 8, (300, 200), -100.0),
+                                                       (4, 5, 128, (376, 376), None),      # tile depth 32 plan
+                                                       (4, 5, 128, (512, 512), None)])     # BASELINE config 3: chunked layers 2/3
 def test_rollout_matches_oracle(E, T, ctx_dim, hidden, head_lb):
     orc, model = _setup(3, 64, ctx_dim, seed=7)
     orc.cfg.fix_head_lb = float('nan') if head_lb is None else head_lb
