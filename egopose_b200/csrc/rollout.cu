@@ -1371,11 +1371,11 @@ __device__ __forceinline__ void t4_mlp_partial(const double *__restrict__ Wp, in
 // layer too wide for shared memory): layer 2 is produced C2 neurons at a time into the (dead) input rows and
 // immediately folded into register accumulators of the head.
 constexpr int MLP_C2 = 64;
-template <int KC>
-__device__ void t4_policy_forward(const RolloutArgs &A, double *xs, double *h1s, double *stage, int lane, int w) {
+template <int KC, bool CHUNK>
+__device__ __forceinline__ void t4_policy_forward(const RolloutArgs &A, double *xs, double *h1s, double *stage, int lane, int w) {
     t4_mlp_layer<true, KC>(A.W1t, A.b1, A.D, A.K1p, 0, A.H1p / JB, 0, xs, h1s, stage, lane, w);
     __syncthreads();
-    if (!A.chunk23) {
+    if (!CHUNK) {
         t4_mlp_layer<true, KC>(A.W2t, A.b2, A.H1, A.K2p, 0, A.H2p / JB, 0, h1s, xs, stage, lane, w);
         __syncthreads();
         t4_mlp_layer<false, KC>(A.W3t, A.b3, A.H2, A.K3p, 0, A.Ap / JB, 0, xs, h1s, stage, lane, w);
@@ -1409,6 +1409,7 @@ __device__ void t4_policy_forward(const RolloutArgs &A, double *xs, double *h1s,
     __syncthreads();
 }
 
+template <int KC, bool CHUNK>
 __global__ void __launch_bounds__(T4_THREADS, 1)
 rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
     extern __shared__ double smem[];
@@ -1428,11 +1429,11 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
     x.tm = tmem_base + ((uint32_t)(w * 32) << 16);
     const int S = c_m.nq - 2 + c_m.nv, nu = c_m.nu, nv = c_m.nv, nb = c_m.nbody, nq = c_m.nq;
     double *xs = smem + (size_t)O.ax * 32;               // MLP activations alias the axis / anchor / U rows
-    const int h2rows = A.chunk23 ? MLP_C2 : A.H2p;
+    const int h2rows = CHUNK ? MLP_C2 : A.H2p;
     const int xrows = A.D > h2rows ? A.D : h2rows;
     double *h1s = xs + (size_t)xrows * 32;
     const int hrows4 = A.H1p > A.Ap ? A.H1p : A.Ap;
-    double *stage = h1s + (size_t)hrows4 * 32 + (size_t)w * A.kc * JB;  // per-warp weight tile
+    double *stage = h1s + (size_t)hrows4 * 32 + (size_t)w * KC * JB;    // per-warp weight tile
     const int T = A.cfg.horizon, E = A.cfg.n_env;
     const double dt = c_m.h * c_m.frame_skip;
     const int env = blockIdx.x * 32 + lane;
@@ -1530,8 +1531,7 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
             }
         }
         __syncthreads();
-        if (A.kc == 64) t4_policy_forward<64>(A, xs, h1s, stage, lane, w);
-        else t4_policy_forward<32>(A, xs, h1s, stage, lane, w);
+        t4_policy_forward<KC, CHUNK>(A, xs, h1s, stage, lane, w);
         bool mean_flag = A.cfg.mean_action != 0;
         if (A.in.d_mean_flag) mean_flag = mean_flag || A.in.d_mean_flag[n] != 0;
         else if (A.cfg.noise_rate < 1.0) {
@@ -2220,10 +2220,15 @@ int egp_rollout_f64(EgpModel *m, const EgpPolicyWeights *pol, const EgpRolloutCf
         EGP_CUDA(cudaMemcpyAsync(out->d_logger, init, sizeof init, cudaMemcpyHostToDevice, st));
     }
     if (use_t4) {
-        EGP_CUDA(cudaFuncSetAttribute(rollout_kernel_t4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
-        rollout_kernel_t4<<<blocks, T4_THREADS, smem4, st>>>(A, O);
-        EGP_CHECK_LAUNCH("rollout_kernel_t4");
-        return EGP_OK;
+        auto launch = [&](auto kern) -> int {
+            EGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+            kern<<<blocks, T4_THREADS, smem4, st>>>(A, O);
+            EGP_CHECK_LAUNCH("rollout_kernel_t4");
+            return EGP_OK;
+        };
+        if (A.kc == 64) return launch(rollout_kernel_t4<64, false>);
+        if (!A.chunk23) return launch(rollout_kernel_t4<32, false>);
+        return launch(rollout_kernel_t4<32, true>);
     }
     size_t smem = sizeof(double) * ENVS_PER_CTA * ((size_t)xrows + hrows);
     if (smem > 227 * 1024) { set_error("egp_rollout_f64: policy too wide for shared memory (%zu bytes)", smem); return EGP_ESIZE; }
