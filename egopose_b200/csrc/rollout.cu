@@ -1259,22 +1259,20 @@ __device__ void t4_substep(const T4Ctx &x, T4Local &l) {
     t4_forward<0>(x, l);        // qacc, semi-implicit Euler
 }
 
-// observation entry k (humanoid_v1.py:73-96) from the shared q / v rows; hd = de-headed root quaternion,
-// vl = root linear velocity in the heading frame (both computed redundantly by every thread)
-__device__ __forceinline__ double t4_obs_entry(const T4Ctx &x, int k, const double *hd, const double *vl) {
+// observation entry k (humanoid_v1.py:73-96) from the shared q / v rows; hd* = de-headed root quaternion,
+// vl* = root linear velocity in the heading frame (both computed redundantly by every thread and passed as
+// scalars: no dynamically indexed thread-local arrays)
+__device__ __forceinline__ double t4_obs_entry(const T4Ctx &x, int k, double hd0, double hd1, double hd2, double hd3,
+                                               double vl0, double vl1, double vl2) {
     const int nq = c_m.nq;
     if (k == 0) return x.at(x.o.q, 2);
-    if (k < 5) return hd[k - 1];
+    if (k < 5) return k == 1 ? hd0 : (k == 2 ? hd1 : (k == 3 ? hd2 : hd3));
     if (k < nq - 2) return x.at(x.o.q, k + 2);
     const int j = k - (nq - 2);
-    if (j < 3) return vl[j];
+    if (j < 3) return j == 0 ? vl0 : (j == 1 ? vl1 : vl2);
     return x.at(x.o.v, j);
 }
 
-// One dense layer for the CTA's 32 environments, split over the 4 warps by 8-neuron blocks.  Weights come
-// packed as tiles Wp[block][k][8] (k padded to MLP_KC); each warp streams its tiles HBM/L2 -> registers
-// (coalesced 128-bit loads, issued one tile ahead) -> its private shared-memory tile -> broadcast LDS, so the
-// inner loop is FP64-pipe bound instead of waiting on warp-uniform global loads.
 constexpr int MLP_KC_MAX = 64;               // k rows per weight tile (64, or 32 for wide policies)
 
 // Computes output blocks [jb0, jb1) (8 neurons each, split over the warps) of one dense layer:
@@ -1489,7 +1487,7 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
         to_heading(v3, q4, vl);
         int s = 0;
         for (int k = w; k < S; k += T4_WARPS, s++) {
-            double v = t4_obs_entry(x, k, hd, vl);
+            double v = t4_obs_entry(x, k, hd[0], hd[1], hd[2], hd[3], vl[0], vl[1], vl[2]);
             dst_raw[s] = v;
             if (A.in.d_zf_mean) {
                 v = (v - A.in.d_zf_mean[k]) / (A.in.d_zf_std[k] + 1e-8);
