@@ -113,3 +113,33 @@ def test_rollout_variants_agree():
     la, lb = a['logger'].cpu().numpy(), b['logger'].cpu().numpy()
     assert np.allclose(la, lb, rtol=1e-7, atol=1e-9)
     model.close()
+
+
+def test_rollout_edge_cases():
+    """smallest batch, NaN guard (mj_checkPos analogue: terminate + reset + count, trajbatch stays finite),
+    Bernoulli mean-action flags (agents/agent.py:46,61)"""
+    orc, model = _setup(2, 64, 0, seed=13)
+    S, nu = orc.S, orc.nu
+    w = helpers.policy_weights(S, 32, 16, nu, seed=7)
+    wd = {k: cu(v.ravel() if k == 'log_std' else v) for k, v in w.items()}
+    # E = 1, T = 1 against the oracle
+    eps = np.random.RandomState(1).randn(1, nu)
+    rt, rs = np.array([[1]]), np.array([[20]])
+    ref = orc.rollout(orc.make_policy(w['W1'], w['b1'], w['W2'], w['b2'], w['W3'], w['b3'], w['log_std']), 1, 1, rt, rs, eps)
+    out = model.rollout(wd, 1, 1, episode_len=12, eps=cu(eps), reset_take=cu(rt, torch.int32), reset_start=cu(rs, torch.int32))
+    assert out['masks'].item() == 0.0 and helpers.relerr(out['next_states'].cpu().numpy(), ref['next_states']) < 1e-9
+    assert abs(out['rewards'].item() - ref['rewards'][0]) < 1e-10
+    # NaN guard: a poisoned policy head makes every action NaN
+    bad = dict(wd)
+    bad['W3'] = torch.full_like(wd['W3'], float('nan'))
+    o = model.rollout(bad, 40, 6, episode_len=12, seed=3)
+    lg = o['logger'].cpu().numpy()
+    assert lg[13] == 40 * 6 and (o['masks'] == 0).all() and (o['rewards'] == 0).all()
+    assert torch.isfinite(o['states']).all() and torch.isfinite(o['next_states']).all()
+    # noise_rate 0.7 -> ~30% mean-action steps, recorded as exps == 0 with zero-noise actions
+    o = model.rollout(wd, 64, 40, episode_len=12, seed=5, noise_rate=0.7)
+    frac = 1.0 - o['exps'].mean().item()
+    assert 0.25 < frac < 0.35
+    o2 = model.rollout(wd, 64, 40, episode_len=12, seed=5, noise_rate=0.7, mean_action=True)
+    assert (o2['exps'] == 0).all()
+    model.close()
