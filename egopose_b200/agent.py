@@ -25,7 +25,7 @@ import torch
 
 from . import lib
 from .logger_rl import LoggerRL
-from .nets import FrameContext, trunk_ok
+from .nets import FrameContext, VideoStateNet, trunk_ok
 from .trajbatch import TrajBatch, TrajBatchEgo
 
 
@@ -134,8 +134,9 @@ class _Trunk:
         self.x = x
         return y
 
-    def backward(self, dy):
-        """accumulates nothing: writes the six gradient views of the flat buffer"""
+    def backward(self, dy, dx_cols=0):
+        """writes the six gradient views of the flat buffer; with dx_cols > 0 also returns dL/dx[:, :dx_cols]
+        (the gradient reaching the video-context columns of the input)"""
         x, h1, h2 = self.x, self.buf['h1'], self.buf['h2']
         n = x.shape[0]
         torch.mm(dy.t(), h2, out=self.gW(2))
@@ -148,6 +149,48 @@ class _Trunk:
         torch.mm(dh2, self.W(1), out=dh1)
         lib.relu_bwd_colsum_(dh1, h1, self.gb(0))
         torch.mm(dh1.t(), x, out=self.gW(0))
+        if dx_cols > 0:
+            dx = self._buf('dx', (n, dx_cols), x)
+            torch.mm(dh1, self.W(0)[:, :dx_cols], out=dx)
+            return dx
+        return None
+
+
+class _NetInput:
+    """Dense-layer input of one net.  Constant tensor (identity / per-frame table), or cat(train_context(), states)
+    rebuilt on every forward when a VideoStateNet produces the context (trans_policy / trans_value,
+    agent_ego.py:28-32): x() hands the trunk a contiguous buffer, backward() feeds dL/dctx to torch autograd so the
+    (Bi)LSTM parameters receive gradients, which are then copied into the flat gradient buffer."""
+
+    def __init__(self, x_const=None, vs=None, states=None, flat=None):
+        self.x_const, self.vs, self.flat = x_const, vs, flat
+        self.ctx = None
+        if vs is not None:
+            self.cd = vs.v_hdim
+            self.xbuf = torch.empty((states.shape[0], self.cd + states.shape[1]), dtype=states.dtype, device=states.device)
+            self.xbuf[:, self.cd:].copy_(states)
+            self.vs_params = [(n, p) for n, p in vs.named_parameters() if p.requires_grad]
+
+    @property
+    def learned(self):
+        return self.vs is not None
+
+    def x(self, grad=True):
+        if self.vs is None:
+            return self.x_const
+        with torch.set_grad_enabled(grad):
+            self.ctx = self.vs.train_context()
+        self.xbuf[:, :self.cd].copy_(self.ctx.detach())
+        return self.xbuf
+
+    def backward(self, dctx):
+        for _, p in self.vs_params:
+            p.grad = None
+        self.ctx.backward(dctx)
+        for n, p in self.vs_params:
+            self.flat.view(self.flat.grad, 'vs.' + n).copy_(p.grad)
+            p.grad = None
+        self.ctx = None
 
 
 class Agent:
@@ -209,6 +252,10 @@ class Agent:
                 raise lib.EgpError('policy parameter %s must be a CUDA float64 tensor (move the nets to the GPU)' % k)
         return {k: t.contiguous() for k, t in w.items()}
 
+    def _rollout_context(self):
+        """(ctx table, win_off) handed to the rollout kernel, or (None, None) for the table uploaded with the experts"""
+        return None, None
+
     def _zf(self):
         rs = self.running_state
         if rs is None:
@@ -236,19 +283,22 @@ class Agent:
         rs = self.running_state
         if rs is not None and rs.rs.n < 2:
             # first rollout: statistics from one warm-up rollout of the same size (frozen-stats deviation)
+            wctx, wwin = self._rollout_context()
             warm = self.env.kernel.rollout(w, E, min(T, 8), self.env.cfg.env_episode_len, self.env.cfg.fr_margin,
                                            fix_head_lb=self.env.fix_head_lb, noise_rate=self.noise_rate,
                                            seed=self.env._seed, iteration=2 ** 40 + self.iteration, zf_clip=0.0,
-                                           want_next=False)
+                                           want_next=False, ctx=wctx, win_off=wwin)
             self._merge_obs(warm['raw_obs'])
         zm, zs, clip = self._zf()
         p = parity or {}
+        ctx, win_off = self._rollout_context()
         out = self.env.kernel.rollout(
             w, E, T, self.env.cfg.env_episode_len, self.env.cfg.fr_margin, end_reward=self.env.end_reward,
             fix_head_lb=self.env.fix_head_lb, noise_rate=self.noise_rate, mean_action=self.mean_action,
             zf_mean=zm, zf_std=zs, zf_clip=clip, seed=self.env._seed, iteration=self.iteration,
             eps=p.get('eps'), reset_take=p.get('reset_take'), reset_start=p.get('reset_start'),
-            mean_flag=p.get('mean_flag'), want_next=to_host, want_raw=rs is not None, out=self._out)
+            mean_flag=p.get('mean_flag'), want_next=to_host, want_raw=rs is not None, out=self._out,
+            ctx=ctx, win_off=win_off)
         self.iteration += 1
         if rs is not None:
             self._merge_obs(out['raw_obs'])
@@ -302,6 +352,11 @@ class AgentPG(Agent):
         dev = self.policy_net.action_mean.weight.device
         pol = [(n, p) for n, p in self.policy_net.named_parameters() if p.requires_grad]
         val = [(n, p) for n, p in self.value_net.named_parameters() if p.requires_grad]
+        # the optimizers also own the video-context nets' parameters (ego_mimic.py:68-69); the grad-norm clip spans
+        # policy_net and policy_vs_net jointly
+        for lst, vs in ((pol, getattr(self, 'policy_vs_net', None)), (val, getattr(self, 'value_vs_net', None))):
+            if isinstance(vs, VideoStateNet):
+                lst += [('vs.' + n, p) for n, p in vs.named_parameters() if p.requires_grad]
         if not (trunk_ok(self.policy_net.net) and trunk_ok(self.value_net.net)):
             raise lib.EgpError('fused path needs two-hidden-layer relu MLP trunks')
         self._pf = _FlatNet(pol, self.optimizer_policy, dev)
@@ -337,17 +392,26 @@ class AgentPG(Agent):
 
     def _inputs(self, states, v_metas, masks, horizon):
         """trans_policy / trans_value of the base agent: identity"""
-        return states, states
+        inp = _NetInput(x_const=states)
+        return inp, inp
 
     def update_value(self, x, returns, inv_n, reuse_forward=False):
         """agents/agent_pg.py:19-26.  ``reuse_forward``: the activations of the value forward that produced the
-        GAE inputs are still valid (no parameter step since), so the first epoch skips its forward GEMMs."""
+        GAE inputs are still valid (no parameter step since), so the first epoch skips its forward GEMMs.
+        ``x`` is a tensor or a _NetInput."""
+        inp = x if isinstance(x, _NetInput) else _NetInput(x_const=x)
         for it in range(self.value_opt_niter):
-            v = self._vt.buf['y'] if (reuse_forward and it == 0) else self._vt.forward(x)
-            dv = self._vt._buf('dy', v.shape, x)
+            if reuse_forward and it == 0 and not inp.learned:
+                v, xt = self._vt.buf['y'], self._vt.x
+            else:
+                xt = inp.x()
+                v = self._vt.forward(xt)
+            dv = self._vt._buf('dy', v.shape, xt)
             self._scal[0:1].zero_()
             lib.value_loss_grad(v.view(-1), returns, inv_n, dv.view(-1), self._scal[0:1])
-            self._vt.backward(dv)
+            dx = self._vt.backward(dv, inp.cd if inp.learned else 0)
+            if inp.learned:
+                inp.backward(dx)
             d = _dist()
             if d is not None:
                 d.all_reduce(self._vf.grad)
@@ -359,8 +423,8 @@ class AgentPG(Agent):
         states, actions, rewards, masks, exps, v_metas, horizon = self._device_batch(batch)
         xp, xv = self._inputs(states, v_metas, masks, horizon)
         # values + GAE (agent_pg.py:48-53, core/common.py:5-25)
-        values = self._vt.forward(xv).view(-1)
-        self._value_fresh = True
+        values = self._vt.forward(xv.x(grad=False)).view(-1)
+        self._value_fresh = not xv.learned
         adv, returns, stats = lib.gae(rewards, masks, values.contiguous(), self.gamma, self.tau)
         n_local = states.shape[0]
         n_exp = exps.sum()
@@ -396,9 +460,10 @@ class AgentPPO(AgentPG):
 
     def _policy_step(self, xp, actions, adv, logp0, exps, inv_count, log_std, max_norm, mu=None):
         """ppo_loss forward+backward, gradient all-reduce, clip + Adam (agent_ppo.py:47-51 / :38-43)"""
-        if mu is None:
-            mu = self._pt.forward(xp)
-        dmu = self._pt._buf('dy', mu.shape, xp)
+        inp = xp if isinstance(xp, _NetInput) else _NetInput(x_const=xp)
+        if mu is None or inp.learned:
+            mu = self._pt.forward(inp.x())
+        dmu = self._pt._buf('dy', mu.shape, mu)
         self._scal[1:2].zero_()
         dls = None
         if self._learn_std:
@@ -406,7 +471,9 @@ class AgentPPO(AgentPG):
             dls.zero_()
         lib.ppo_loss_grad(mu, actions, log_std, adv, self._stats, logp0, exps, self.clip_epsilon, inv_count, dmu,
                           dls, self._scal[1:2])
-        self._pt.backward(dmu)
+        dx = self._pt.backward(dmu, inp.cd if inp.learned else 0)
+        if inp.learned:
+            inp.backward(dx)
         if _dist() is not None:
             _dist().all_reduce(self._pf.grad)
         self._pf.adam(max_norm)
@@ -455,11 +522,14 @@ class AgentPPO(AgentPG):
     def update_policy(self, xp, xv, actions, returns, adv, exps, inv_count, inv_n):
         """agents/agent_ppo.py:16-51"""
         log_std = self.policy_net.action_log_std.data.view(-1)
-        mu = self._pt.forward(xp)
+        mu = self._pt.forward(xp.x(grad=False))
         logp0 = lib.gauss_logp(mu, actions, log_std)                    # fixed_log_probs (:18-20)
         max_norm = self._max_norm()
         if self.use_mini_batch:
-            return self._update_policy_minibatch(xp, xv, actions, returns, adv, exps, logp0, log_std, max_norm)
+            if xp.learned or xv.learned:
+                raise lib.EgpError('mini-batch PPO with a VideoStateNet context is not supported (the reference forces '
+                                   'the full-batch branch for AgentEgo, agent_ego.py:11)')
+            return self._update_policy_minibatch(xp.x_const, xv.x_const, actions, returns, adv, exps, logp0, log_std, max_norm)
         surr, vloss = [], []
         d = _dist()
         for ep in range(self.opt_num_epochs):
@@ -494,19 +564,38 @@ class AgentEgo(AgentPPO):
         self.sample_modules.append(policy_vs_net)
         self.update_modules += [policy_vs_net, value_vs_net]
         for net in (policy_vs_net, value_vs_net):
-            if net is not None and not isinstance(net, FrameContext):
-                raise lib.EgpError('the fused path takes the video context from the per-frame table (nets.FrameContext); '
-                                   'the BiLSTM VideoStateNet producer is SURVEY 8f row 2 (next)')
+            if net is not None and not isinstance(net, (FrameContext, VideoStateNet)):
+                raise lib.EgpError('video context nets must be nets.VideoStateNet (lstm) or nets.FrameContext')
 
     def pre_sample(self):
         if self.policy_vs_net is not None:
             self.policy_vs_net.set_mode('test')
 
+    def _rollout_context(self):
+        """test-mode VideoStateNet output for every (take, start) episode window, evaluated in one batched sweep
+        (replaces pre_episode's per-episode initialize, agent_ego.py:21-22): the kernel looks v_out[t] up on the
+        device across auto-resets"""
+        if isinstance(self.policy_vs_net, VideoStateNet):
+            return self.policy_vs_net.context_table(self.env.cnn_feat, self.env.cfg.env_episode_len)
+        return None, None
+
     def _inputs(self, states, v_metas, masks, horizon):
-        """trans_policy / trans_value (agent_ego.py:28-32): cat(ctx[frame], state) gathered on the device"""
-        if self.env.kernel.ctx_dim == 0:
-            return states, states
-        if horizon is None:
-            raise lib.EgpError('context gather needs the env-major [E, T] batch produced by sample()')
-        x = self.env.kernel.build_input(states, v_metas, masks, horizon)
-        return x, x
+        """trans_policy / trans_value (agent_ego.py:28-32, 44-47): VideoStateNet in train mode, or the per-frame
+        table gathered on the device"""
+        out = []
+        cache = None
+        for vs, flat in ((self.policy_vs_net, self._pf), (self.value_vs_net, self._vf)):
+            if isinstance(vs, VideoStateNet):
+                vs.set_mode('train')
+                vs.initialize((masks, self.env.cnn_feat, v_metas))
+                out.append(_NetInput(vs=vs, states=states, flat=flat))
+                continue
+            if cache is None:
+                if self.env is None or self.env.kernel.ctx_dim == 0:
+                    cache = _NetInput(x_const=states)
+                else:
+                    if horizon is None:
+                        raise lib.EgpError('context gather needs the env-major [E, T] batch produced by sample()')
+                    cache = _NetInput(x_const=self.env.kernel.build_input(states, v_metas, masks, horizon))
+            out.append(cache)
+        return out[0], out[1]

@@ -593,13 +593,21 @@ struct RolloutArgs {
     // expert tables
     const int32_t *take_off;
     const double *rows, *head_lb, *ctx;
-    int n_takes, ctx_dim;
+    const int32_t *win_off;
+    int n_takes, ctx_dim, ctx_mode, ctx_T;
     // policy (transposed + padded): W1t [D][H1p], W2t [H1][H2p], W3t [H2][Ap]
     const double *W1t, *b1, *W2t, *b2, *W3t, *b3, *log_std;
     int D, H1, H2, A, H1p, H2p, Ap;
     int K1p, K2p, K3p;      // T4: k padded to the tile depth (weights packed as tiles)
     int kc, chunk23;        // T4: tile depth (64 | 32); 1 = chunked layer-2/3 path for wide policies
 };
+
+// video-context row of (take, start, t): per-frame table, or one row block per (take, start) episode window
+__device__ __forceinline__ const double *ctx_row(const RolloutArgs &A, int take, int start, int t) {
+    const size_t r = A.ctx_mode == 0 ? (size_t)(A.take_off[take] + start + t)
+                                     : (size_t)(A.win_off[take] + start - A.cfg.fr_margin) * A.ctx_T + t;
+    return A.ctx + r * A.ctx_dim;
+}
 
 // one dense layer for the 32 environments of the CTA: ys[j][lane] = act(b[j] + sum_k Wt[k][j] xs[k][lane])
 template <bool RELU>
@@ -693,7 +701,7 @@ rollout_kernel(const RolloutArgs A) {
         // ---- policy input cat(ctx[frame], state) -> shared, feature-major (video_state_net.py:62-64)
         int off = 0;
         if (A.ctx) {
-            const double *cx = A.ctx + (size_t)(A.take_off[take] + start + cur_t) * A.ctx_dim;
+            const double *cx = ctx_row(A, take, start, cur_t);
             for (int k = 0; k < A.ctx_dim; k++) xs[k * ENVS_PER_CTA + lane] = cx[k];
             off = A.ctx_dim;
         }
@@ -1514,7 +1522,7 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
         // ---- policy input cat(ctx[frame], state), feature-major
         int off = 0;
         if (A.ctx) {
-            const double *cx = A.ctx + (size_t)(A.take_off[take] + start + cur_t) * A.ctx_dim;
+            const double *cx = ctx_row(A, take, start, cur_t);
             for (int k = w; k < A.ctx_dim; k += T4_WARPS) xs[k * 32 + lane] = cx[k];
             off = A.ctx_dim;
         }
@@ -2131,8 +2139,15 @@ int egp_rollout_f64(EgpModel *m, const EgpPolicyWeights *pol, const EgpRolloutCf
     const DevModel &d = m->host;
     const int S = d.nq - 2 + d.nv;
     if (cfg->n_env < 1 || cfg->horizon < 1 || cfg->episode_len < 1) { set_error("egp_rollout_f64: bad sizes"); return EGP_EINVAL; }
-    if (pol->in_dim != S + m->ctx_dim || pol->out_dim != d.nu) {
-        set_error("egp_rollout_f64: policy dims (in %d out %d) do not match obs %d + ctx %d / nu %d", pol->in_dim, pol->out_dim, S, m->ctx_dim, d.nu);
+    const bool ctx_override = in && in->d_ctx;
+    const int ctx_dim = ctx_override ? in->ctx_dim : m->ctx_dim;
+    if (ctx_override && (in->ctx_dim < 1 || (in->ctx_mode == 1 && (!in->d_win_off || in->ctx_T < cfg->episode_len)) ||
+                         (in->ctx_mode != 0 && in->ctx_mode != 1))) {
+        set_error("egp_rollout_f64: bad context table (dim %d mode %d T %d)", in->ctx_dim, in->ctx_mode, in->ctx_T);
+        return EGP_EINVAL;
+    }
+    if (pol->in_dim != S + ctx_dim || pol->out_dim != d.nu) {
+        set_error("egp_rollout_f64: policy dims (in %d out %d) do not match obs %d + ctx %d / nu %d", pol->in_dim, pol->out_dim, S, ctx_dim, d.nu);
         return EGP_ESIZE;
     }
     if (!out->d_states || !out->d_actions || !out->d_masks || !out->d_rewards || !out->d_exps || !out->d_v_metas) {
@@ -2150,8 +2165,13 @@ int egp_rollout_f64(EgpModel *m, const EgpPolicyWeights *pol, const EgpRolloutCf
     A.cfg = *cfg;
     if (in) A.in = *in;
     A.out = *out;
-    A.take_off = m->d_take_off; A.rows = m->d_rows; A.head_lb = m->d_head_lb; A.ctx = m->d_ctx;
-    A.n_takes = m->n_takes; A.ctx_dim = m->ctx_dim;
+    A.take_off = m->d_take_off; A.rows = m->d_rows; A.head_lb = m->d_head_lb;
+    A.n_takes = m->n_takes;
+    A.ctx = ctx_override ? in->d_ctx : m->d_ctx;
+    A.ctx_dim = ctx_dim;
+    A.ctx_mode = ctx_override ? in->ctx_mode : 0;
+    A.ctx_T = ctx_override ? in->ctx_T : 0;
+    A.win_off = ctx_override ? in->d_win_off : nullptr;
     A.D = pol->in_dim; A.H1 = pol->h1; A.H2 = pol->h2; A.A = pol->out_dim;
     A.H1p = pad(A.H1); A.H2p = pad(A.H2); A.Ap = pad(A.A);
     int xrows = A.D > A.H2p ? A.D : A.H2p;

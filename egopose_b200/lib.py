@@ -58,7 +58,8 @@ class PolicyWeights(C.Structure):
 
 class RolloutIn(C.Structure):
     _fields_ = [('d_eps', _vp), ('d_reset_take', _vp), ('d_reset_start', _vp), ('d_mean_flag', _vp),
-                ('d_zf_mean', _vp), ('d_zf_std', _vp)]
+                ('d_zf_mean', _vp), ('d_zf_std', _vp), ('d_ctx', _vp), ('d_win_off', _vp), ('ctx_dim', C.c_int32),
+                ('ctx_mode', C.c_int32), ('ctx_T', C.c_int32)]
 
 
 class TrajOut(C.Structure):
@@ -281,7 +282,8 @@ class Model:
     # ---- rollout ------------------------------------------------------------------------------
     def rollout(self, weights, n_env, horizon, episode_len, fr_margin=10, end_reward=0.0, fix_head_lb=None,
                 noise_rate=1.0, mean_action=False, zf_mean=None, zf_std=None, zf_clip=5.0, seed=1, iteration=0,
-                eps=None, reset_take=None, reset_start=None, mean_flag=None, want_next=True, want_raw=True, out=None):
+                eps=None, reset_take=None, reset_start=None, mean_flag=None, want_next=True, want_raw=True, out=None,
+                ctx=None, win_off=None):
         """weights: dict with W1,b1,W2,b2,W3,b3,log_std CUDA float64 tensors (torch [out,in] layout).
         Returns a dict of CUDA tensors in TrajBatchEgo layout (+ logger, c_info, raw_obs, final state)."""
         global launches
@@ -320,6 +322,9 @@ class Model:
         inp = RolloutIn()
         inp.d_eps, inp.d_reset_take, inp.d_reset_start = ptr(eps), ptr(reset_take), ptr(reset_start)
         inp.d_mean_flag, inp.d_zf_mean, inp.d_zf_std = ptr(mean_flag), ptr(zf_mean), ptr(zf_std)
+        if ctx is not None:         # per-rollout context table (window-indexed when win_off is given)
+            inp.d_ctx, inp.ctx_dim = ptr(ctx), ctx.shape[1]
+            inp.d_win_off, inp.ctx_mode, inp.ctx_T = ptr(win_off), int(win_off is not None), int(episode_len)
         pw = PolicyWeights()
         pw.in_dim, pw.h1 = weights['W1'].shape[1], weights['W1'].shape[0]
         pw.h2, pw.out_dim = weights['W2'].shape[0], weights['W3'].shape[0]

@@ -13,6 +13,7 @@ the rollout and the PPO update read the parameter storage directly from the CUDA
 """
 import math
 
+import numpy as np
 import torch
 import torch.nn as nn
 from torch.distributions import Normal
@@ -130,6 +131,157 @@ class FrameContext(nn.Module):
 
     def forward(self, x):
         raise RuntimeError('FrameContext is consumed inside the fused kernels (egp_rollout / egp_build_input)')
+
+
+class RNN(nn.Module):
+    """models/rnn.py:5-61 mirror (LSTM cells only): parameters live in nn.LSTMCell modules named rnn_f / rnn_b so
+    the state-dict keys match the reference; batch mode runs the whole sequence.  The input projection of all
+    time steps is one GEMM, only the recurrent half is stepped."""
+
+    def __init__(self, input_dim, out_dim, cell_type='lstm', bi_dir=False):
+        super().__init__()
+        if cell_type != 'lstm':
+            raise NotImplementedError('only the lstm cell is on the hot path (egomimic_config.py:54,63)')
+        self.input_dim, self.out_dim, self.cell_type, self.bi_dir = input_dim, out_dim, cell_type, bi_dir
+        self.mode = 'batch'
+        hidden = out_dim // 2 if bi_dir else out_dim
+        self.rnn_f = nn.LSTMCell(input_dim, hidden)
+        if bi_dir:
+            self.rnn_b = nn.LSTMCell(input_dim, hidden)
+        self.hx = self.cx = None
+
+    def set_mode(self, mode):
+        self.mode = mode
+
+    def initialize(self, batch_size=1):
+        if self.mode == 'step':
+            p = self.rnn_f.weight_ih
+            self.hx = torch.zeros((batch_size, self.rnn_f.hidden_size), dtype=p.dtype, device=p.device)
+            self.cx = torch.zeros_like(self.hx)
+
+    @staticmethod
+    def _sweep(cell, x, reverse):
+        """x [L, B, F] -> hidden states [L, B, H] of one direction, zero initial state"""
+        L, B, _ = x.shape
+        H = cell.hidden_size
+        xi = torch.addmm(cell.bias_ih + cell.bias_hh, x.reshape(L * B, -1), cell.weight_ih.t()).view(L, B, 4 * H)
+        h = x.new_zeros((B, H))
+        c = x.new_zeros((B, H))
+        whh_t = cell.weight_hh.t()
+        outs = [None] * L
+        for t in (range(L - 1, -1, -1) if reverse else range(L)):
+            gates = xi[t] + h @ whh_t
+            i, f, g, o = gates.chunk(4, 1)
+            c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
+            h = torch.sigmoid(o) * torch.tanh(c)
+            outs[t] = h
+        return torch.stack(outs, 0)
+
+    def forward(self, x):
+        if self.mode == 'step':
+            self.hx, self.cx = self.rnn_f(x, (self.hx.to(x.device), self.cx.to(x.device)))
+            return self.hx
+        out = self._sweep(self.rnn_f, x, False)
+        if self.bi_dir:
+            out = torch.cat((out, self._sweep(self.rnn_b, x, True)), 2)
+        return out
+
+
+class VideoStateNet(nn.Module):
+    """models/video_state_net.py:8-79 mirror (lstm v_net): same constructor, modes and forward semantics.
+
+    test mode  : initialize(cnn_feat[start-m : start+T+m]) runs the (Bi)LSTM once per episode, forward(state)
+                 prepends v_out[t]                                                            (:36-39,61-64)
+    train mode : initialize((masks, cnn_feat, v_metas)) packs every episode of the batch into a padded
+                 [Tmax+2m, n_ep, F] context, forward re-runs the (Bi)LSTM and gathers rows       (:40-59,65-69)
+
+    Fused-path entry points (used by egopose_b200.agent.AgentEgo): ``context_table`` evaluates test mode for EVERY
+    (take, start) window in one batched sweep so the rollout kernel can look the context up on the device across
+    auto-resets; ``train_context`` is train-mode forward without the concatenation (autograd graph attached)."""
+
+    def __init__(self, cnn_feat_dim, v_hdim=128, v_margin=10, v_net_type='lstm', v_net_param=None, causal=False):
+        super().__init__()
+        if v_net_type != 'lstm':
+            raise NotImplementedError('v_net_type %r: only lstm is selected by the shipped configs' % v_net_type)
+        self.mode = 'test'
+        self.cnn_feat_dim, self.v_net_type, self.v_hdim, self.v_margin = cnn_feat_dim, v_net_type, v_hdim, v_margin
+        self.v_net = RNN(cnn_feat_dim, v_hdim, v_net_type, bi_dir=not causal)
+        self.v_out, self.t = None, 0
+        self.indices = self.cnn_feat_ctx = None
+
+    def set_mode(self, mode):
+        self.mode = mode
+
+    def _p(self):
+        return self.v_net.rnn_f.weight_ih
+
+    def forward_v_net(self, x):
+        return self.v_net(x)
+
+    def initialize(self, x):
+        if self.mode == 'test':
+            m = self.v_margin
+            self.v_out = self.forward_v_net(x.unsqueeze(1)).squeeze(1)[m:-m]
+            self.t = 0
+            return
+        masks, cnn_feat, v_metas = x
+        p = self._p()
+        m = self.v_margin
+        masks_np = masks.detach().cpu().numpy() if torch.is_tensor(masks) else np.asarray(masks)
+        v_metas = v_metas.detach().cpu().numpy() if torch.is_tensor(v_metas) else np.asarray(v_metas)
+        ends = np.nonzero(masks_np == 0)[0]
+        starts = np.concatenate([[0], ends[:-1] + 1])
+        lens = ends - starts + 1
+        tmax = int(lens.max())
+        n = masks_np.shape[0]
+        ep_of = np.repeat(np.arange(len(ends)), lens)
+        self.indices = torch.as_tensor(ep_of * tmax + (np.arange(n) - starts[ep_of]), dtype=torch.long, device=p.device)
+        # frame gather instead of the reference's per-episode python loop
+        feats = cnn_feat if torch.is_tensor(cnn_feat) else None
+        if feats is None:
+            offs = np.concatenate([[0], np.cumsum([c.shape[0] for c in cnn_feat])])
+            feats = torch.as_tensor(np.concatenate(cnn_feat), dtype=p.dtype, device=p.device)
+        else:
+            raise ValueError('cnn_feat must be the per-take list (env.cnn_feat)')
+        meta = v_metas[ends].astype(np.int64)
+        base = offs[meta[:, 0]] + meta[:, 1] - m
+        frame = base[None, :] + np.arange(tmax + 2 * m)[:, None]
+        if frame.min() < 0 or frame.max() >= feats.shape[0]:
+            raise IndexError('episode context window leaves the take (video_state_net.py:55)')
+        self.cnn_feat_ctx = feats[torch.as_tensor(frame, device=p.device)]          # [tmax + 2m, n_ep, F]
+
+    def train_context(self):
+        m = self.v_margin
+        v_ctx = self.forward_v_net(self.cnn_feat_ctx)[m:-m]
+        v_ctx = v_ctx.transpose(0, 1).reshape(-1, self.v_hdim)
+        return v_ctx.index_select(0, self.indices)
+
+    def forward(self, x):
+        if self.mode == 'test':
+            x = torch.cat((self.v_out[[self.t], :], x), dim=1)
+            self.t += 1
+            return x
+        return torch.cat((self.train_context(), x), dim=1)
+
+    @torch.no_grad()
+    def context_table(self, cnn_feat, episode_len, max_batch=4096):
+        """-> (table [n_windows * episode_len, v_hdim], win_off int32 [n_takes + 1]); window w of take k starts at
+        frame start = v_margin + (w - win_off[k]) (the range reset_model samples from, humanoid_v1.py:214) and row
+        w * episode_len + t equals test-mode v_out[t] of an episode started there."""
+        p, m, T = self._p(), self.v_margin, int(episode_len)
+        rows, win_off = [], [0]
+        for feat in cnn_feat:
+            f = torch.as_tensor(feat, dtype=p.dtype, device=p.device)
+            nwin = f.shape[0] - T - 2 * m
+            if nwin <= 0:
+                raise ValueError('take shorter than episode_len + 2 * fr_margin')
+            for lo in range(0, nwin, max_batch):
+                hi = min(nwin, lo + max_batch)
+                idx = torch.arange(T + 2 * m, device=p.device)[:, None] + torch.arange(lo, hi, device=p.device)[None, :]
+                out = self.forward_v_net(f[idx])[m:-m]                      # [T, hi - lo, H]
+                rows.append(out.transpose(0, 1).reshape(-1, self.v_hdim))
+            win_off.append(win_off[-1] + nwin)
+        return torch.cat(rows).contiguous(), torch.tensor(win_off, dtype=torch.int32, device=p.device)
 
 
 def trunk_ok(net):

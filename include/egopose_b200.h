@@ -101,6 +101,13 @@ typedef struct {
     const int32_t *d_reset_start;       /* [E][max_resets] pre-drawn start_ind (humanoid_v1.py:214) */
     const uint8_t *d_mean_flag;         /* [E*T] 1 = mean action this step (agents/agent.py:46) */
     const double *d_zf_mean, *d_zf_std; /* [S] frozen ZFilter statistics or NULL (identity) */
+    /* Optional per-rollout video context table on the device, replacing the per-frame table uploaded with the
+     * experts.  ctx_mode 0: row = take_off[take] + start + t (per frame).  ctx_mode 1: row = (win_off[take] +
+     * start - fr_margin) * ctx_T + t: one test-mode VideoStateNet output v_out[t] per (take, start) episode window
+     * (models/video_state_net.py:36-39,61-64), ctx_T = env_episode_len rows per window. */
+    const double *d_ctx;
+    const int32_t *d_win_off;           /* [n_takes + 1], ctx_mode 1 */
+    int32_t ctx_dim, ctx_mode, ctx_T;
 } EgpRolloutIn;
 
 /* TrajBatchEgo layout (core/trajbatch.py:6-16, ego_pose/core/trajbatch_ego.py:7-9), all device, row-major. */

@@ -143,3 +143,64 @@ def test_agent_ego_sample_and_update_vs_oracle():
     for k, v in val.state_dict().items():
         assert np.allclose(v.cpu().numpy(), new_v[k], rtol=1e-5, atol=1e-8), k
     env.close()
+
+
+def test_agent_ego_with_video_state_net_matches_reference_golden(golden):
+    """AgentEgo.update_params with real BiLSTM VideoStateNets (agent_ego.py:34-57, video_state_net.py train mode)
+    vs the golden run of the reference's own classes; then the all-windows test-mode table feeds the rollout."""
+    import types
+    from egopose_b200.agent import AgentEgo
+    from egopose_b200.nets import MLP, PolicyGaussian, Value, VideoStateNet
+    from egopose_b200.trajbatch import TrajBatchEgo
+    torch.set_default_dtype(torch.float64)
+    g = golden('vsnet_small')
+    F, VH, M, S, A, T = [int(x) for x in g['dims']]
+    gamma, tau, clip, lr_p, lr_v, max_norm = g['hyper']
+
+    def load(net, prefix):
+        net.load_state_dict({k[len(prefix) + 1:]: torch.from_numpy(g[k]) for k in g.files if k.startswith(prefix + '.')})
+        return net.cuda()
+    pvs, vvs = load(VideoStateNet(F, VH, M), 'pvs0'), load(VideoStateNet(F, VH, M), 'vvs0')
+    pol = load(PolicyGaussian(MLP(S + VH, (16, 12), 'relu'), A, log_std=-1.0, fix_std=True), 'p0')
+    val = load(Value(MLP(S + VH, (16, 12), 'relu')), 'v0')
+    pparams = list(pol.parameters()) + list(pvs.parameters())
+    vparams = list(val.parameters()) + list(vvs.parameters())
+    opt_p = torch.optim.Adam(pparams, lr=lr_p)
+    opt_v = torch.optim.Adam(vparams, lr=lr_v)
+    env = types.SimpleNamespace(cnn_feat=[c for c in g['cnn_feat']], kernel=types.SimpleNamespace(ctx_dim=0))
+    agent = AgentEgo(env=env, dtype=torch.float64, device=torch.device('cuda'), running_state=None, custom_reward=None,
+                     policy_net=pol, policy_vs_net=pvs, value_net=val, value_vs_net=vvs, optimizer_policy=opt_p,
+                     optimizer_value=opt_v, opt_num_epochs=3, gamma=gamma, tau=tau, clip_epsilon=clip,
+                     policy_grad_clip=[(pparams, max_norm)])
+    batch = TrajBatchEgo.from_numpy(**{k: g['batch.' + k] for k in ('states', 'actions', 'rewards', 'masks', 'exps', 'v_metas')})
+    agent.update_params(batch)
+    assert np.allclose(agent.losses()['surr_loss'], g['surr_loss'], rtol=1e-8, atol=1e-11)   # north star: 1e-5
+    for prefix, net in (('p3', pol), ('v3', val), ('pvs3', pvs), ('vvs3', vvs)):
+        for k, v in net.state_dict().items():
+            assert np.allclose(v.cpu().numpy(), g[prefix + '.' + k], rtol=1e-7, atol=1e-9), (prefix, k)
+    # Adam state of the BiLSTM parameters is exposed through the caller's optimizer as well
+    assert int(opt_p.state[pvs.v_net.rnn_f.weight_ih]['step']) == 3
+
+
+def test_rollout_with_window_context_table():
+    """ctx_mode 1 (one row block per (take, start) window) reproduces the per-frame table when it is built from it,
+    and AgentEgo.sample feeds the VideoStateNet table to the kernel"""
+    from oracle import cphys
+    import test_gpu_rollout as tr
+    orc, model = tr._setup(3, 64, 8, seed=21)
+    S, nu, T_ep, m = orc.S, orc.nu, 12, 10
+    w = helpers.policy_weights(S + 8, 48, 32, nu, seed=4)
+    wd = {k: tr.cu(v.ravel() if k == 'log_std' else v) for k, v in w.items()}
+    a = {k: v.clone() for k, v in model.rollout(wd, 50, 20, episode_len=T_ep, seed=9, iteration=1).items()}
+    frame_ctx = orc._keep['x_ctx']                         # [3 * 64, 8] per frame
+    nwin = 64 - T_ep - 2 * m
+    table = np.zeros((3 * nwin * T_ep, 8))
+    for k in range(3):
+        for wi in range(nwin):
+            start = m + wi
+            table[(k * nwin + wi) * T_ep:(k * nwin + wi + 1) * T_ep] = frame_ctx[k * 64 + start: k * 64 + start + T_ep]
+    win_off = torch.tensor([0, nwin, 2 * nwin, 3 * nwin], dtype=torch.int32, device='cuda')
+    b = model.rollout(wd, 50, 20, episode_len=T_ep, seed=9, iteration=1, ctx=tr.cu(table), win_off=win_off)
+    for k in ('states', 'actions', 'rewards', 'masks'):
+        assert torch.equal(a[k], b[k]), k
+    model.close()

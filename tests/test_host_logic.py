@@ -150,3 +150,39 @@ def test_synthetic_generators_agree():
     a = synthetic_takes(md, 2, 30, seed=5)
     b = cphys.synthetic_takes(dataclasses.asdict(md), 2, 30, seed=5)
     assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+def test_checkpoint_roundtrip_and_reference_names(tmp_path):
+    """ego_mimic.py:133-139 format; the stream names utils.zfilter.ZFilter like the reference's checkpoints"""
+    from egopose_b200 import checkpoint, zfilter
+    from egopose_b200.nets import MLP, PolicyGaussian, Value
+    torch.manual_seed(0)
+    zf = zfilter.ZFilter((5,), clip=5)
+    for x in np.random.RandomState(0).randn(10, 5):
+        zf(x)
+    pol = PolicyGaussian(MLP(8, (6, 4), 'relu'), 3, log_std=-2.3, fix_std=True).double()
+    val = Value(MLP(8, (6, 4), 'relu')).double()
+    path = str(tmp_path / 'iter_0100.p')
+    checkpoint.save_checkpoint(path, pol, None, val, None, zf)
+    raw = open(path, 'rb').read()
+    assert b'utils.zfilter' in raw and b'egopose_b200' not in raw
+    assert 'utils.zfilter' not in sys.modules or not hasattr(sys.modules['utils.zfilter'], '_RefNamedZFilter')
+    pol2 = PolicyGaussian(MLP(8, (6, 4), 'relu'), 3, log_std=0.0, fix_std=True).double()
+    val2 = Value(MLP(8, (6, 4), 'relu')).double()
+    w_before = pol2.net.affine_layers[0].weight.data_ptr()
+    cp, rs = checkpoint.load_checkpoint(path, pol2, None, val2, None)
+    assert set(cp) == {'policy_dict', 'policy_vs_dict', 'value_dict', 'value_vs_dict', 'running_state'}
+    assert pol2.net.affine_layers[0].weight.data_ptr() == w_before            # in-place load keeps aliasing
+    for k, v in pol.state_dict().items():
+        assert torch.equal(v, pol2.state_dict()[k])
+    assert rs.rs.n == 10 and np.allclose(rs.rs.mean, zf.rs.mean) and np.allclose(rs.rs.std, zf.rs.std) and rs.clip == 5
+    # the reference itself can read it (build container only)
+    if os.path.isdir('/root/reference/utils'):
+        code = ("import sys, pickle; sys.path.insert(0, %r)\nfrom oracle import refimport; refimport.install()\n"
+                "from utils.zfilter import ZFilter\ncp = pickle.load(open(%r, 'rb'))\n"
+                "assert type(cp['running_state']) is ZFilter and cp['running_state'].rs.n == 10\n"
+                "from core.policy_gaussian import PolicyGaussian\nfrom models.mlp import MLP\nimport torch\n"
+                "p = PolicyGaussian(MLP(8, (6, 4), 'relu'), 3).double(); p.load_state_dict(cp['policy_dict']); print('ok')") % (ROOT, path)
+        import subprocess
+        out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True)
+        assert out.stdout.strip().endswith('ok'), out.stderr[-1500:]
