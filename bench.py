@@ -302,13 +302,48 @@ def main():
         b.synchronize()
         gt.append(a.elapsed_time(b))
     gae_ms = float(np.median(gt))
-    roofline = {'kernel': 'rollout_kernel', 'bound': 'hbm', 'achieved': roll_bytes / (roll_ms / 1e3) / 1e9, 'peak': hbm,
-                'unit': 'GB/s', 'frac': roll_bytes / (roll_ms / 1e3) / 1e9 / hbm, 'traffic': None, 'peak_source': peak_src,
-                'ms': roll_ms, 'share_of_step': roll_ms / ms,
-                'note': 'fused rollout is FP64-latency/ALU bound (~400 FLOP/B), not HBM bound (SURVEY 7); see roofline_extra'}
-    extra = {'gae_kernel': {'bound': 'hbm', 'achieved': 5 * wbytes * N / (gae_ms / 1e3) / 1e9, 'peak': hbm, 'unit': 'GB/s',
-                            'frac': 5 * wbytes * N / (gae_ms / 1e3) / 1e9 / hbm, 'ms': gae_ms, 'bytes_per_sample': 40},
+    # `traffic`: dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the committed ncu --set full capture
+    # of this exact configuration (profiles/r1_rollout_t4_full.md / r1_gae_full.md); not re-measured live
+    default_cfg = (E, T, tuple(args.hidden)) == (4096, 300, (300, 300))
+    flops_env_step = 15 * 2 * 21e3 + 2 * (243 * 300 + 300 * 300 + 300 * 52)      # ABA sweeps + policy MLP, FMA = 2
+    fp64_peak = None
+    try:        # live float64 GEMM peak of this box (MEASURED_PEAKS.json carries no FP64 figure)
+        sq = torch.randn(6144, 6144, dtype=torch.float64, device=device)
+        torch.mm(sq, sq)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(3):
+            torch.mm(sq, sq)
+        b.record()
+        b.synchronize()
+        fp64_peak = 3 * 2 * 6144 ** 3 / (a.elapsed_time(b) / 1e3) / 1e12
+        del sq
+    except Exception:
+        pass
+    roofline = {'kernel': 'rollout_kernel_t4', 'bound': 'hbm', 'achieved': roll_bytes / (roll_ms / 1e3) / 1e9, 'peak': hbm,
+                'unit': 'GB/s', 'frac': roll_bytes / (roll_ms / 1e3) / 1e9 / hbm,
+                'traffic': 10.203e9 if default_cfg else None, 'peak_source': peak_src,
+                'ms': roll_ms, 'share_of_step': roll_ms / ms, 'algorithmic_bytes_per_env_step': roll_bytes // N,
+                'note': 'the fused rollout keeps all state on chip (~200 FLOP/B): it is FP64-issue/latency bound, not HBM '
+                        'bound (SURVEY 7); fp64 utilisation below; traffic > algorithmic bytes is thread-local scratch '
+                        'write-back (180 MB footprint > L2)'}
+    extra = {'rollout_fp64': {'achieved': flops_env_step * N / (roll_ms / 1e3) / 1e12, 'peak': fp64_peak, 'unit': 'TFLOP/s',
+                              'frac': (flops_env_step * N / (roll_ms / 1e3) / 1e12 / fp64_peak) if fp64_peak else None,
+                              'peak_source': 'cuBLAS DGEMM 6144^3 measured live on this GPU',
+                              'flop_per_env_step': flops_env_step,
+                              'ncu_fp64_pipe_active_pct': 12.2 if default_cfg else None},
+             'gae_kernel': {'bound': 'hbm', 'achieved': 5 * wbytes * N / (gae_ms / 1e3) / 1e9, 'peak': hbm, 'unit': 'GB/s',
+                            'frac': 5 * wbytes * N / (gae_ms / 1e3) / 1e9 / hbm, 'ms': gae_ms, 'bytes_per_sample': 40,
+                            'traffic': 63.36e6 if default_cfg else None},
+             'update_dgemm': {'bound': 'tensor(fp64)', 'achieved': None, 'peak': fp64_peak, 'unit': 'TFLOP/s'},
              'rollout_env_substeps_per_s': N * 15 / (roll_ms / 1e3)}
+    D_in, H1, H2, A_out = 243, args.hidden[0], args.hidden[1], 52
+    fwd = lambda o: 2 * N * (D_in * H1 + H1 * H2 + H2 * o)                       # noqa: E731
+    bwd = lambda o: 2 * N * (2 * H2 * o + 2 * H1 * H2 + D_in * H1)               # noqa: E731  (no dL/dx of layer 1)
+    upd_flops = args.epochs * (fwd(A_out) + fwd(1) + bwd(A_out) + bwd(1))        # epoch 0 reuses the initial forwards
+    extra['update_dgemm']['achieved'] = upd_flops / (ms_upd / 1e3) / 1e12
+    extra['update_dgemm']['frac'] = extra['update_dgemm']['achieved'] / fp64_peak if fp64_peak else None
+    extra['update_dgemm']['note'] = 'cuBLAS d884 DGEMMs + fused elementwise kernels; whole update phase incl. loss/Adam'
 
     # ---- e2e through the public API with host trajbatches
     e2e = None

@@ -204,3 +204,44 @@ def test_rollout_with_window_context_table():
     for k in ('states', 'actions', 'rewards', 'masks'):
         assert torch.equal(a[k], b[k]), k
     model.close()
+
+
+def test_agent_ego_sample_with_video_state_net():
+    """sample() hands the all-windows VideoStateNet table to the kernel: identical to a manual rollout with that table"""
+    from egopose_b200.agent import AgentEgo
+    from egopose_b200.config import Config
+    from egopose_b200.env import HumanoidEnv
+    from egopose_b200.nets import MLP, PolicyGaussian, Value, VideoStateNet
+    from egopose_b200.mjcf import load_builtin
+    from egopose_b200.synthetic import synthetic_cnn_feat, synthetic_takes
+    torch.set_default_dtype(torch.float64)
+    torch.manual_seed(11)
+    E, T, EPL, F, VH = 20, 9, 8, 12, 10
+    cfg = Config('subject_03')
+    cfg.env_episode_len = EPL
+    env = HumanoidEnv(cfg)
+    md = load_builtin()
+    env.set_expert_qpos(['a', 'b'], synthetic_takes(md, 2, 50, seed=2), synthetic_cnn_feat(2, 50, dim=F))
+    S, nu = env.obs_dim, md.nu
+    pvs, vvs = VideoStateNet(F, VH, cfg.fr_margin).cuda(), VideoStateNet(F, VH, cfg.fr_margin).cuda()
+    pol = PolicyGaussian(MLP(S + VH, (32, 24), 'relu'), nu, log_std=-2.3, fix_std=True).cuda()
+    val = Value(MLP(S + VH, (32, 24), 'relu')).cuda()
+    pparams = list(pol.parameters()) + list(pvs.parameters())
+    agent = AgentEgo(env=env, dtype=torch.float64, device=torch.device('cuda'), running_state=None, custom_reward=None,
+                     policy_net=pol, policy_vs_net=pvs, value_net=val, value_vs_net=vvs,
+                     optimizer_policy=torch.optim.Adam(pparams, lr=1e-3),
+                     optimizer_value=torch.optim.Adam(list(val.parameters()) + list(vvs.parameters()), lr=1e-3),
+                     opt_num_epochs=2, gamma=0.95, tau=0.95, clip_epsilon=0.2, policy_grad_clip=[(pparams, 40)],
+                     num_envs=E, horizon=T)
+    batch, log = agent.sample(E * T, to_host=False)
+    states = batch.dev['states'].clone()
+    table, win_off = pvs.context_table(env.cnn_feat, EPL)
+    w = agent._policy_weights()
+    ref = env.kernel.rollout(w, E, T, EPL, cfg.fr_margin, seed=env._seed, iteration=0, ctx=table, win_off=win_off)
+    assert torch.equal(states, ref['states']) and log.num_steps == E * T
+    p_before = pvs.v_net.rnn_b.weight_hh.detach().clone()
+    agent.update_params(batch)                     # full sample -> update cycle with BiLSTM gradients
+    assert not torch.equal(p_before, pvs.v_net.rnn_b.weight_hh) and torch.isfinite(pvs.v_net.rnn_b.weight_hh).all()
+    losses = agent.losses()
+    assert np.isfinite(losses['surr_loss']).all() and losses['value_loss'][-1] < losses['value_loss'][0]
+    env.close()
