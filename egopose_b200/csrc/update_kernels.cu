@@ -33,19 +33,18 @@ int num_sms(int device) {
 
 // ------------------------------------------------------------------------------------------ K4 GAE
 // core/common.py:5-25.  A_i = delta_i + c_i A_{i+1},  delta_i = r_i + gamma V_{i+1} m_i - V_i,
-// c_i = gamma tau m_i, flat over the batch with A_N = V_N = 0.  Single pass, reverse decoupled
-// look-back: tiles are claimed in processing order from the END of the batch; every tile publishes
-// its affine aggregate (C, D) then its inclusive value; successors chain through them and stop early
-// at any episode boundary (C == 0).  Algorithmic traffic 5 doubles / sample.
+// c_i = gamma tau m_i, flat over the batch with A_N = V_N = 0: an affine recurrence, scanned in reverse.
+//   pass 1 (gae_agg_kernel)   : every 2048-sample tile reduces its samples to one affine map (C, D) with
+//                               A_first = D + C A_in  (thread-local compose -> warp-shuffle scan -> 8 warps)
+//   pass 2 (gae_apply_kernel) : a tile folds the maps of the tiles after it until C hits 0 (the first episode
+//                               boundary - normally the very next tile), rescans with that carry-in, writes
+//                               advantages and returns = V + A, and a Chan (n, mean, M2) partial of A
+//   pass 3 (gae_moments_kernel): merges the partials in tile order (deterministic) into stats[3]
+// No atomics, fences or spinning.  The second read of (r, m, V) comes out of L2 (inputs << 126 MB), so DRAM
+// traffic stays at the algorithmic 5 doubles / sample (3 in, 2 out).
 constexpr int GAE_THREADS = 256;
-constexpr int GAE_ITEMS = 4;
+constexpr int GAE_ITEMS = 8;
 constexpr int GAE_TILE = GAE_THREADS * GAE_ITEMS;
-
-struct GaeWork {            // header of d_work
-    unsigned int next_tile;
-    unsigned int done_tiles;
-    unsigned int pad[2];
-};
 
 struct Moments { double n, mean, m2; };
 
@@ -67,45 +66,45 @@ __device__ __forceinline__ Moments shfl_down(Moments a, int o) {
     return r;
 }
 
-__global__ void __launch_bounds__(GAE_THREADS)
-gae_kernel(const double *__restrict__ rew, const double *__restrict__ msk, const double *__restrict__ val,
-           double gamma, double tau, long long n, unsigned int ntiles, double *__restrict__ adv,
-           double *__restrict__ ret, double *__restrict__ stats, GaeWork *work, volatile int *flags,
-           volatile double *pub /* [ntiles][3] C, D, inclusive */, double *partial /* [ntiles][3] */) {
-    __shared__ unsigned int s_p;
-    __shared__ double s_c[GAE_THREADS / 32], s_d[GAE_THREADS / 32];
-    __shared__ double s_ain;
-    __shared__ Moments s_mom[GAE_THREADS / 32];
-    __shared__ bool s_last;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_p = atomicAdd(&work->next_tile, 1u);
-    __syncthreads();
-    const unsigned int p = s_p;                     // processing order, 0 = last tile of the batch
-    const long long tile = (long long)ntiles - 1 - p;
-    // thread 0 owns the HIGHEST indices of the tile
-    const long long lo = tile * GAE_TILE + (long long)(GAE_THREADS - 1 - tid) * GAE_ITEMS;
-    double r[GAE_ITEMS], c[GAE_ITEMS], v[GAE_ITEMS + 1];
+// loads this thread's GAE_ITEMS samples (thread 0 owns the HIGHEST indices of the tile) and composes them:
+// dl[k] = delta, c[k] = gamma tau m; (C, D) = map of the thread's segment
+__device__ __forceinline__ void gae_load_compose(const double *__restrict__ rew, const double *__restrict__ msk,
+                                                 const double *__restrict__ val, double gamma, double tau, long long n,
+                                                 long long lo, bool vec, double *dl, double *c, double *v, double &C, double &D) {
+    if (vec && lo + GAE_ITEMS < n) {    // interior, 16-byte aligned arrays: 128-bit loads
 #pragma unroll
-    for (int k = 0; k < GAE_ITEMS; k++) {
-        long long i = lo + k;
-        bool ok = i < n;
-        r[k] = ok ? rew[i] : 0.0;
-        double m = ok ? msk[i] : 0.0;
-        v[k] = ok ? val[i] : 0.0;
-        c[k] = ok ? m : 0.0;                        // holds the mask for now
+        for (int k = 0; k < GAE_ITEMS; k += 2) {
+            double2 r2 = *reinterpret_cast<const double2 *>(rew + lo + k);
+            double2 m2 = *reinterpret_cast<const double2 *>(msk + lo + k);
+            double2 v2 = *reinterpret_cast<const double2 *>(val + lo + k);
+            dl[k] = r2.x; dl[k + 1] = r2.y; c[k] = m2.x; c[k + 1] = m2.y; v[k] = v2.x; v[k + 1] = v2.y;
+        }
+        v[GAE_ITEMS] = val[lo + GAE_ITEMS];
+    } else {
+#pragma unroll
+        for (int k = 0; k <= GAE_ITEMS; k++) {
+            const long long i = lo + k;
+            const bool ok = i < n;
+            if (k < GAE_ITEMS) { dl[k] = ok ? rew[i] : 0.0; c[k] = ok ? msk[i] : 0.0; }
+            v[k] = ok ? val[i] : 0.0;
+        }
     }
-    v[GAE_ITEMS] = (lo + GAE_ITEMS < n) ? val[lo + GAE_ITEMS] : 0.0;
-    double dl[GAE_ITEMS];
-    double C = 1.0, D = 0.0;
+    C = 1.0; D = 0.0;
 #pragma unroll
     for (int k = GAE_ITEMS - 1; k >= 0; k--) {      // highest index first
-        double m = c[k];
-        dl[k] = r[k] + gamma * v[k + 1] * m - v[k];
+        const double m = c[k];
+        dl[k] = dl[k] + gamma * v[k + 1] * m - v[k];
         c[k] = gamma * tau * m;
         D = dl[k] + c[k] * D;
         C = c[k] * C;
     }
-    // inclusive scan over threads (thread order = descending index): (C,D) o= prev
+}
+
+// inclusive scan of the per-thread maps over the block in thread order (descending sample index);
+// returns the exclusive map of this thread in (eC, eD) and the tile map in (tC, tD) (valid in every thread)
+__device__ __forceinline__ void gae_block_scan(double C, double D, double &eC, double &eD, double &tC, double &tD) {
+    __shared__ double s_c[GAE_THREADS / 32], s_d[GAE_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double iC = C, iD = D;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -116,36 +115,42 @@ gae_kernel(const double *__restrict__ rew, const double *__restrict__ msk, const
     __syncthreads();
     double wC = 1.0, wD = 0.0;                      // composition of all earlier warps
     for (int w = 0; w < warp; w++) { wD = s_d[w] + s_c[w] * wD; wC = s_c[w] * wC; }
+    tC = 1.0; tD = 0.0;
+    for (int w = 0; w < GAE_THREADS / 32; w++) { tD = s_d[w] + s_c[w] * tD; tC = s_c[w] * tC; }
     iD = iD + iC * wD;
     iC = iC * wC;
-    // exclusive value for this thread
-    double eC = __shfl_up_sync(0xffffffffu, iC, 1), eD = __shfl_up_sync(0xffffffffu, iD, 1);
+    eC = __shfl_up_sync(0xffffffffu, iC, 1);
+    eD = __shfl_up_sync(0xffffffffu, iD, 1);
     if (lane == 0) { eC = wC; eD = wD; }
-    if (tid == GAE_THREADS - 1) {
-        // publish aggregate, look back, publish inclusive
-        double tC = iC, tD = iD;
-        pub[3 * (size_t)p + 0] = tC;
-        pub[3 * (size_t)p + 1] = tD;
-        __threadfence();
-        flags[p] = 1;
-        double aC = 1.0, aD = 0.0, ain = 0.0;
-        long long q = (long long)p - 1;
-        bool done = false;
-        while (!done) {
-            if (q < 0 || aC == 0.0) { ain = aD; break; }
-            int f;
-            do { f = flags[q]; } while (f == 0);
-            __threadfence();
-            if (f == 2) { ain = aD + aC * pub[3 * (size_t)q + 2]; done = true; }
-            else { aD = aD + aC * pub[3 * (size_t)q + 1]; aC = aC * pub[3 * (size_t)q + 0]; q--; }
-        }
-        pub[3 * (size_t)p + 2] = tD + tC * ain;
-        __threadfence();
-        flags[p] = 2;
-        s_ain = ain;
+}
+
+__global__ void __launch_bounds__(GAE_THREADS)
+gae_agg_kernel(const double *__restrict__ rew, const double *__restrict__ msk, const double *__restrict__ val, double gamma,
+               double tau, long long n, bool vec, double *__restrict__ agg /* [ntiles][2] */) {
+    const long long lo = (long long)blockIdx.x * GAE_TILE + (long long)(GAE_THREADS - 1 - threadIdx.x) * GAE_ITEMS;
+    double dl[GAE_ITEMS], c[GAE_ITEMS], v[GAE_ITEMS + 1], C, D, eC, eD, tC, tD;
+    gae_load_compose(rew, msk, val, gamma, tau, n, lo, vec, dl, c, v, C, D);
+    gae_block_scan(C, D, eC, eD, tC, tD);
+    if (threadIdx.x == 0) { agg[2 * (size_t)blockIdx.x] = tC; agg[2 * (size_t)blockIdx.x + 1] = tD; }
+}
+
+__global__ void __launch_bounds__(GAE_THREADS)
+gae_apply_kernel(const double *__restrict__ rew, const double *__restrict__ msk, const double *__restrict__ val, double gamma,
+                 double tau, long long n, bool vec, unsigned int ntiles, const double *__restrict__ agg, double *__restrict__ adv,
+                 double *__restrict__ ret, double *__restrict__ partial /* [ntiles][3] */) {
+    __shared__ Moments s_mom[GAE_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long lo = (long long)blockIdx.x * GAE_TILE + (long long)(GAE_THREADS - 1 - tid) * GAE_ITEMS;
+    double dl[GAE_ITEMS], c[GAE_ITEMS], v[GAE_ITEMS + 1], C, D, eC, eD, tC, tD;
+    gae_load_compose(rew, msk, val, gamma, tau, n, lo, vec, dl, c, v, C, D);
+    // carry-in: advantage of the first sample of the next tile, folded through the following tiles' maps
+    double aC = 1.0, ain = 0.0;
+    for (unsigned int q = blockIdx.x + 1; q < ntiles && aC != 0.0; q++) {
+        ain += aC * agg[2 * (size_t)q + 1];
+        aC *= agg[2 * (size_t)q];
     }
-    __syncthreads();
-    double a = eD + eC * s_ain;                     // advantage just above this thread's highest element
+    gae_block_scan(C, D, eC, eD, tC, tD);
+    double a = eD + eC * ain;                       // advantage just above this thread's highest sample
     Moments mom = {0.0, 0.0, 0.0};
     double out_a[GAE_ITEMS];
 #pragma unroll
@@ -157,18 +162,17 @@ gae_kernel(const double *__restrict__ rew, const double *__restrict__ msk, const
             mom = merge(mom, one);
         }
     }
-    if (lo + GAE_ITEMS <= n) {
-        double2 *pa = reinterpret_cast<double2 *>(adv + lo), *pr = reinterpret_cast<double2 *>(ret + lo);
-        pa[0] = make_double2(out_a[0], out_a[1]);
-        pa[1] = make_double2(out_a[2], out_a[3]);
-        pr[0] = make_double2(v[0] + out_a[0], v[1] + out_a[1]);
-        pr[1] = make_double2(v[2] + out_a[2], v[3] + out_a[3]);
+    if (vec && lo + GAE_ITEMS <= n) {
+#pragma unroll
+        for (int k = 0; k < GAE_ITEMS; k += 2) {
+            *reinterpret_cast<double2 *>(adv + lo + k) = make_double2(out_a[k], out_a[k + 1]);
+            *reinterpret_cast<double2 *>(ret + lo + k) = make_double2(v[k] + out_a[k], v[k + 1] + out_a[k + 1]);
+        }
     } else {
 #pragma unroll
         for (int k = 0; k < GAE_ITEMS; k++)
             if (lo + k < n) { adv[lo + k] = out_a[k]; ret[lo + k] = v[k] + out_a[k]; }
     }
-    // advantage moments (n, mean, M2): deterministic tree inside the tile, tiles merged in index order
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mom = merge(mom, shfl_down(mom, o));
     if (lane == 0) s_mom[warp] = mom;
@@ -176,21 +180,32 @@ gae_kernel(const double *__restrict__ rew, const double *__restrict__ msk, const
     if (tid == 0) {
         Moments t = s_mom[0];
         for (int w = 1; w < GAE_THREADS / 32; w++) t = merge(t, s_mom[w]);
-        partial[3 * tile + 0] = t.n; partial[3 * tile + 1] = t.mean; partial[3 * tile + 2] = t.m2;
-        __threadfence();
-        s_last = atomicAdd(&work->done_tiles, 1u) == ntiles - 1;
+        partial[3 * (size_t)blockIdx.x + 0] = t.n; partial[3 * (size_t)blockIdx.x + 1] = t.mean; partial[3 * (size_t)blockIdx.x + 2] = t.m2;
     }
-    __syncthreads();
-    if (s_last && warp == 0) {
-        __threadfence();
-        Moments t = {0.0, 0.0, 0.0};
-        for (unsigned int k = lane; k < ntiles; k += 32) {
-            Moments o = {partial[3 * k], partial[3 * k + 1], partial[3 * k + 2]};
-            t = merge(t, o);
-        }
+}
+
+__global__ void __launch_bounds__(256)
+gae_moments_kernel(const double *__restrict__ partial, unsigned int ntiles, double *__restrict__ stats) {
+    __shared__ Moments s_mom[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // contiguous slices per thread, merged in tile order
+    const unsigned int per = (ntiles + 255) / 256, k0 = threadIdx.x * per;
+    Moments t = {0.0, 0.0, 0.0};
+    for (unsigned int k = k0; k < k0 + per && k < ntiles; k++) {
+        Moments o = {partial[3 * (size_t)k], partial[3 * (size_t)k + 1], partial[3 * (size_t)k + 2]};
+        t = merge(t, o);
+    }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) t = merge(t, shfl_down(t, o));
-        if (lane == 0) { stats[0] = t.n; stats[1] = t.mean; stats[2] = t.m2; }
+    for (int o = 1; o < 32; o <<= 1) {              // ordered tree: lane l absorbs lane l + o
+        Moments nb = shfl_down(t, o);
+        if ((lane & (2 * o - 1)) == 0) t = merge(t, nb);
+    }
+    if (lane == 0) s_mom[warp] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        Moments r = s_mom[0];
+        for (int w = 1; w < 8; w++) r = merge(r, s_mom[w]);
+        stats[0] = r.n; stats[1] = r.mean; stats[2] = r.m2;
     }
 }
 
@@ -488,7 +503,7 @@ int egp_version(void) { return 100; }
 int64_t egp_gae_work_bytes(int64_t n) {
     int64_t nt = (n + GAE_TILE - 1) / GAE_TILE;
     if (nt < 1) nt = 1;
-    return (int64_t)sizeof(GaeWork) + nt * (int64_t)(sizeof(int) + 6 * sizeof(double)) + 64;
+    return nt * (int64_t)(5 * sizeof(double)) + 64;
 }
 
 int egp_gae_f64(const double *d_rewards, const double *d_masks, const double *d_values, double gamma, double tau,
@@ -499,15 +514,14 @@ int egp_gae_f64(const double *d_rewards, const double *d_masks, const double *d_
     }
     cudaStream_t st = (cudaStream_t)stream;
     unsigned int nt = (unsigned int)((n + GAE_TILE - 1) / GAE_TILE);
-    EGP_CUDA(cudaMemsetAsync(d_work, 0, (size_t)egp_gae_work_bytes(n), st));
-    char *base = (char *)d_work;
-    GaeWork *work = (GaeWork *)base;
-    double *pub = (double *)(base + sizeof(GaeWork));
-    double *partial = pub + 3 * (size_t)nt;
-    int *flags = (int *)(partial + 3 * (size_t)nt);
-    gae_kernel<<<nt, GAE_THREADS, 0, st>>>(d_rewards, d_masks, d_values, gamma, tau, (long long)n, nt, d_adv, d_ret,
-                                           d_stats, work, flags, pub, partial);
-    EGP_CHECK_LAUNCH("gae_kernel");
+    double *agg = (double *)d_work;
+    double *partial = agg + 2 * (size_t)nt;
+    const bool vec = (((uintptr_t)d_rewards | (uintptr_t)d_masks | (uintptr_t)d_values | (uintptr_t)d_adv | (uintptr_t)d_ret) & 15) == 0;
+    gae_agg_kernel<<<nt, GAE_THREADS, 0, st>>>(d_rewards, d_masks, d_values, gamma, tau, (long long)n, vec, agg);
+    gae_apply_kernel<<<nt, GAE_THREADS, 0, st>>>(d_rewards, d_masks, d_values, gamma, tau, (long long)n, vec, nt, agg, d_adv,
+                                                 d_ret, partial);
+    gae_moments_kernel<<<1, 256, 0, st>>>(partial, nt, d_stats);
+    EGP_CHECK_LAUNCH("gae kernels");
     return EGP_OK;
 }
 

@@ -14,7 +14,7 @@ def cu(a):
     return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device='cuda')
 
 
-@pytest.mark.parametrize('n', [1, 5, 1023, 1024, 1025, 4096 * 3 + 17, 300 * 700])
+@pytest.mark.parametrize('n', [1, 5, 1023, 1024, 1025, 2047, 2048, 2049, 4096 * 3 + 17, 300 * 700])
 def test_gae_vs_oracle(n):
     from egopose_b200 import lib
     rng = np.random.RandomState(n)
@@ -36,13 +36,27 @@ def test_gae_vs_oracle(n):
 def test_gae_no_episode_boundaries_long_chain():
     """masks all one: the look-back must chain through every tile (no early exit)."""
     from egopose_b200 import lib
-    n = 1024 * 40 + 3
+    n = 2048 * 40 + 3
     rng = np.random.RandomState(0)
     r, v, m = rng.rand(n), rng.randn(n), np.ones(n)
     adv, ret, stats = lib.gae(cu(r), cu(m), cu(v), 0.99, 0.97)
     adv_n, ret_o = oppo.gae(r, m, v, 0.99, 0.97)
     assert np.allclose(ret.cpu().numpy(), ret_o, rtol=1e-11, atol=1e-11)
     assert np.allclose(lib.standardize_(adv, stats).cpu().numpy(), adv_n, rtol=1e-9, atol=1e-10)
+
+
+def test_gae_unaligned_views():
+    """8-byte-offset tensor views take the scalar load path"""
+    from egopose_b200 import lib
+    n = 5000
+    rng = np.random.RandomState(1)
+    r, v = rng.rand(n + 1), rng.randn(n + 1)
+    m = (rng.rand(n + 1) > 0.05).astype(np.float64)
+    m[-1] = 0
+    adv, ret, stats = lib.gae(cu(r)[1:], cu(m)[1:], cu(v)[1:], 0.95, 0.9)
+    adv_n, ret_o = oppo.gae(r[1:], m[1:], v[1:], 0.95, 0.9)
+    assert np.allclose(ret.cpu().numpy(), ret_o, rtol=1e-12, atol=1e-12)
+    assert np.allclose(lib.standardize_(adv, stats).cpu().numpy(), adv_n, rtol=1e-10, atol=1e-11)
 
 
 def test_gae_golden(golden):
