@@ -291,16 +291,21 @@ def main():
     wbytes = 8                                            # float64
     roll_bytes = (128 + 166 + 115 + 52 + 115 + 5 + 5) * wbytes * N      # ctx + expert row + states/actions/raw_obs/c_info/scalars
     rewards, masks = agent._out['rewards'], agent._out['masks']
-    vals = torch.randn(N, dtype=torch.float64, device=device)
+    # GAE: 12 distinct input sets (12 x 29 MB in + 12 x 20 MB out > L2) processed back to back so that the timed
+    # region is device-bound (one call is ~3 launches of a few microseconds each)
+    sets = [(rewards + 0.01 * i, masks.clone(), torch.randn(N, dtype=torch.float64, device=device)) for i in range(12)]
+    work = torch.empty(lib.load().egp_gae_work_bytes(N), dtype=torch.uint8, device=device)
     gt = []
-    for i in range(5):
-        flush.fill_(i)
+    for rep in range(4):
+        flush.fill_(rep)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        lib.gae(rewards, masks, vals, cfg.gamma, cfg.tau)
+        for r_i, m_i, v_i in sets:
+            lib.gae(r_i, m_i, v_i, cfg.gamma, cfg.tau, work=work)
         b.record()
         b.synchronize()
-        gt.append(a.elapsed_time(b))
+        gt.append(a.elapsed_time(b) / len(sets))
+    del sets
     gae_ms = float(np.median(gt))
     # `traffic`: dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the committed ncu --set full capture
     # of this exact configuration (profiles/r1_rollout_t4_full.md / r1_gae_full.md); not re-measured live
