@@ -295,17 +295,19 @@ def main():
     # region is device-bound (one call is ~3 launches of a few microseconds each)
     sets = [(rewards + 0.01 * i, masks.clone(), torch.randn(N, dtype=torch.float64, device=device)) for i in range(12)]
     work = torch.empty(lib.load().egp_gae_work_bytes(N), dtype=torch.uint8, device=device)
+    outs = [(torch.empty(N, dtype=torch.float64, device=device), torch.empty(N, dtype=torch.float64, device=device),
+             torch.empty(3, dtype=torch.float64, device=device)) for _ in sets]
     gt = []
     for rep in range(4):
         flush.fill_(rep)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        for r_i, m_i, v_i in sets:
-            lib.gae(r_i, m_i, v_i, cfg.gamma, cfg.tau, work=work)
+        for (r_i, m_i, v_i), o_i in zip(sets, outs):
+            lib.gae(r_i, m_i, v_i, cfg.gamma, cfg.tau, work=work, out=o_i)
         b.record()
         b.synchronize()
         gt.append(a.elapsed_time(b) / len(sets))
-    del sets
+    del sets, outs
     gae_ms = float(np.median(gt))
     # `traffic`: dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the committed ncu --set full capture
     # of this exact configuration (profiles/r1_rollout_t4_full.md / r1_gae_full.md); not re-measured live

@@ -347,21 +347,25 @@ class Model:
 
 
 # ---- update-phase kernels (thin wrappers; all tensors CUDA float64 contiguous) ------------------
-def gae(rewards, masks, values, gamma, tau, work=None):
-    """K4 (core/common.py:5-21): returns (adv_raw, returns, stats[3] = n, mean, M2)"""
+def gae(rewards, masks, values, gamma, tau, work=None, out=None):
+    """K4 (core/common.py:5-21): returns (adv_raw, returns, stats[3] = n, mean, M2); ``out`` may carry the three
+    preallocated output tensors"""
     global launches
     import torch
     lib = load()
     n = rewards.numel()
-    adv = torch.empty(n, dtype=torch.float64, device=rewards.device)
-    ret = torch.empty(n, dtype=torch.float64, device=rewards.device)
-    stats = torch.empty(3, dtype=torch.float64, device=rewards.device)
+    if out is not None:
+        adv, ret, stats = out
+    else:
+        adv = torch.empty(n, dtype=torch.float64, device=rewards.device)
+        ret = torch.empty(n, dtype=torch.float64, device=rewards.device)
+        stats = torch.empty(3, dtype=torch.float64, device=rewards.device)
     nbytes = lib.egp_gae_work_bytes(n)
     if work is None or work.numel() < nbytes:
         work = torch.empty(nbytes, dtype=torch.uint8, device=rewards.device)
     check(lib.egp_gae_f64(ptr(rewards), ptr(masks), ptr(values), gamma, tau, n, ptr(adv), ptr(ret), ptr(stats),
                           ptr(work), stream_ptr()), 'egp_gae_f64')
-    launches += 1
+    launches += 3
     return adv, ret, stats
 
 
