@@ -25,7 +25,7 @@ import torch
 
 from . import lib
 from .logger_rl import LoggerRL
-from .nets import FrameContext, VideoStateNet, trunk_ok
+from .nets import FrameContext, VideoForecastNet, VideoStateNet, trunk_ok
 from .trajbatch import TrajBatch, TrajBatchEgo
 
 
@@ -166,9 +166,15 @@ class _NetInput:
         self.x_const, self.vs, self.flat = x_const, vs, flat
         self.ctx = None
         if vs is not None:
-            self.cd = vs.v_hdim
-            self.xbuf = torch.empty((states.shape[0], self.cd + states.shape[1]), dtype=states.dtype, device=states.device)
-            self.xbuf[:, self.cd:].copy_(states)
+            self.states = states
+            self.forecast = isinstance(vs, VideoForecastNet)
+            if self.forecast:           # the whole trunk input is produced by the net: cat(v_out, s_net(states))
+                self.cd = vs.out_dim
+                self.xbuf = torch.empty((states.shape[0], self.cd), dtype=states.dtype, device=states.device)
+            else:
+                self.cd = vs.v_hdim
+                self.xbuf = torch.empty((states.shape[0], self.cd + states.shape[1]), dtype=states.dtype, device=states.device)
+                self.xbuf[:, self.cd:].copy_(states)
             self.vs_params = [(n, p) for n, p in vs.named_parameters() if p.requires_grad]
 
     @property
@@ -179,7 +185,7 @@ class _NetInput:
         if self.vs is None:
             return self.x_const
         with torch.set_grad_enabled(grad):
-            self.ctx = self.vs.train_context()
+            self.ctx = self.vs.train_context(self.states) if self.forecast else self.vs.train_context()
         self.xbuf[:, :self.cd].copy_(self.ctx.detach())
         return self.xbuf
 
@@ -256,6 +262,10 @@ class Agent:
         """(ctx table, win_off) handed to the rollout kernel, or (None, None) for the table uploaded with the experts"""
         return None, None
 
+    def _rollout_extra(self):
+        """extra keyword arguments of lib.Model.rollout (state LSTM, constant per-window context)"""
+        return {}
+
     def _zf(self):
         rs = self.running_state
         if rs is None:
@@ -287,7 +297,7 @@ class Agent:
             warm = self.env.kernel.rollout(w, E, min(T, 8), self.env.cfg.env_episode_len, self.env.cfg.fr_margin,
                                            fix_head_lb=self.env.fix_head_lb, noise_rate=self.noise_rate,
                                            seed=self.env._seed, iteration=2 ** 40 + self.iteration, zf_clip=0.0,
-                                           want_next=False, ctx=wctx, win_off=wwin)
+                                           want_next=False, ctx=wctx, win_off=wwin, **self._rollout_extra())
             self._merge_obs(warm['raw_obs'])
         zm, zs, clip = self._zf()
         p = parity or {}
@@ -298,7 +308,7 @@ class Agent:
             zf_mean=zm, zf_std=zs, zf_clip=clip, seed=self.env._seed, iteration=self.iteration,
             eps=p.get('eps'), reset_take=p.get('reset_take'), reset_start=p.get('reset_start'),
             mean_flag=p.get('mean_flag'), want_next=to_host, want_raw=rs is not None, out=self._out,
-            ctx=ctx, win_off=win_off)
+            ctx=ctx, win_off=win_off, **self._rollout_extra())
         self.iteration += 1
         if rs is not None:
             self._merge_obs(out['raw_obs'])
@@ -355,7 +365,7 @@ class AgentPG(Agent):
         # the optimizers also own the video-context nets' parameters (ego_mimic.py:68-69); the grad-norm clip spans
         # policy_net and policy_vs_net jointly
         for lst, vs in ((pol, getattr(self, 'policy_vs_net', None)), (val, getattr(self, 'value_vs_net', None))):
-            if isinstance(vs, VideoStateNet):
+            if isinstance(vs, (VideoStateNet, VideoForecastNet)):
                 lst += [('vs.' + n, p) for n, p in vs.named_parameters() if p.requires_grad]
         if not (trunk_ok(self.policy_net.net) and trunk_ok(self.value_net.net)):
             raise lib.EgpError('fused path needs two-hidden-layer relu MLP trunks')
@@ -564,8 +574,8 @@ class AgentEgo(AgentPPO):
         self.sample_modules.append(policy_vs_net)
         self.update_modules += [policy_vs_net, value_vs_net]
         for net in (policy_vs_net, value_vs_net):
-            if net is not None and not isinstance(net, (FrameContext, VideoStateNet)):
-                raise lib.EgpError('video context nets must be nets.VideoStateNet (lstm) or nets.FrameContext')
+            if net is not None and not isinstance(net, (FrameContext, VideoStateNet, VideoForecastNet)):
+                raise lib.EgpError('video context nets must be nets.VideoStateNet / VideoForecastNet (lstm) or nets.FrameContext')
 
     def pre_sample(self):
         if self.policy_vs_net is not None:
@@ -575,9 +585,17 @@ class AgentEgo(AgentPPO):
         """test-mode VideoStateNet output for every (take, start) episode window, evaluated in one batched sweep
         (replaces pre_episode's per-episode initialize, agent_ego.py:21-22): the kernel looks v_out[t] up on the
         device across auto-resets"""
-        if isinstance(self.policy_vs_net, VideoStateNet):
+        if isinstance(self.policy_vs_net, (VideoStateNet, VideoForecastNet)):
             return self.policy_vs_net.context_table(self.env.cnn_feat, self.env.cfg.env_episode_len)
         return None, None
+
+    def _rollout_extra(self):
+        """VideoForecastNet (ego_forecast.py:53-56): v_out is one constant row per episode window and the state LSTM
+        is stepped inside the rollout kernel (video_forecast_net.py:57-61,86-93)"""
+        vs = self.policy_vs_net
+        if isinstance(vs, VideoForecastNet):
+            return dict(ctx_const=True, snet=vs.snet_packed())
+        return {}
 
     def _inputs(self, states, v_metas, masks, horizon):
         """trans_policy / trans_value (agent_ego.py:28-32, 44-47): VideoStateNet in train mode, or the per-frame
@@ -585,7 +603,7 @@ class AgentEgo(AgentPPO):
         out = []
         cache = None
         for vs, flat in ((self.policy_vs_net, self._pf), (self.value_vs_net, self._vf)):
-            if isinstance(vs, VideoStateNet):
+            if isinstance(vs, (VideoStateNet, VideoForecastNet)):
                 vs.set_mode('train')
                 vs.initialize((masks, self.env.cnn_feat, v_metas))
                 out.append(_NetInput(vs=vs, states=states, flat=flat))

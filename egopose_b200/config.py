@@ -44,6 +44,9 @@ class Config:
         self.expert_feat_file = '%s/features/expert_%s.p' % (self.data_dir, cfg['expert_feat']) if 'expert_feat' in cfg else None
         self.cnn_feat_file = '%s/features/cnn_feat_%s.p' % (self.data_dir, cfg['cnn_feat']) if 'cnn_feat' in cfg else None
         self.fr_margin = cfg.get('fr_margin', 10)
+        # ego mimic warm start (egoforecast_config.py:38-40)
+        self.ego_mimic_cfg = cfg.get('ego_mimic_cfg', None)
+        self.ego_mimic_iter = cfg.get('ego_mimic_iter', None)
         # training config
         self.gamma = cfg.get('gamma', 0.95)
         self.tau = cfg.get('tau', 0.95)
@@ -52,6 +55,18 @@ class Config:
         self.policy_hsize = cfg.get('policy_hsize', [300, 200])
         self.policy_v_hdim = cfg.get('policy_v_hdim', 128)
         self.policy_v_net = cfg.get('policy_v_net', 'lstm')
+        # egoforecast only (egoforecast_config.py:49-52,62-65); the egomimic defaults select no state net
+        self.policy_v_net_param = cfg.get('policy_v_net_param', None)
+        self.policy_s_net = cfg.get('policy_s_net', 'id')
+        self.policy_s_hdim = cfg.get('policy_s_hdim', None)
+        self.policy_dyn_v = cfg.get('policy_dyn_v', False)
+        self.value_v_net_param = cfg.get('value_v_net_param', None)
+        self.value_s_net = cfg.get('value_s_net', 'id')
+        self.value_s_hdim = cfg.get('value_s_hdim', None)
+        self.value_dyn_v = cfg.get('value_dyn_v', False)
+        self.end_reward = cfg.get('end_reward', True)
+        self.obs_phase = cfg.get('obs_phase', False)
+        self.random_cur_t = cfg.get('random_cur_t', False)
         self.policy_optimizer = cfg.get('policy_optimizer', 'Adam')
         self.policy_lr = cfg.get('policy_lr', 5e-5)
         self.policy_momentum = cfg.get('policy_momentum', 0.0)
@@ -81,7 +96,8 @@ class Config:
         self.adp_noise_rate_cp = pad(cfg.get('adp_noise_rate_cp', [1.0]))
         self.adp_log_std_cp = pad(cfg.get('adp_log_std_cp', [self.log_std]))
         self.adp_policy_lr_cp = pad(cfg.get('adp_policy_lr_cp', [self.policy_lr]))
-        self.adp_noise_rate = self.adp_log_std = self.adp_policy_lr = None
+        self.adp_init_noise_cp = pad(cfg.get('adp_init_noise_cp', [0.0]))         # egoforecast_config.py:91-92
+        self.adp_noise_rate = self.adp_log_std = self.adp_policy_lr = self.adp_init_noise = None
         # env config
         self.mujoco_model = cfg.get('mujoco_model', 'humanoid_1205_v1')
         self.mujoco_model_file = '%s/assets/mujoco_models/%s.xml' % (os.getcwd(), self.mujoco_model)
@@ -114,3 +130,5 @@ class Config:
         self.adp_noise_rate = self.adp_noise_rate_cp[ind] * (1 - t) + self.adp_noise_rate_cp[nind] * t
         self.adp_log_std = self.adp_log_std_cp[ind] * (1 - t) + self.adp_log_std_cp[nind] * t
         self.adp_policy_lr = self.adp_policy_lr_cp[ind] * (1 - t) + self.adp_policy_lr_cp[nind] * t
+        inz = np.pad(self.adp_init_noise_cp, (0, max(0, len(cp) - len(self.adp_init_noise_cp))), 'edge')
+        self.adp_init_noise = inz[ind] * (1 - t) + inz[nind] * t

@@ -600,12 +600,17 @@ struct RolloutArgs {
     int D, H1, H2, A, H1p, H2p, Ap;
     int K1p, K2p, K3p;      // T4: k padded to the tile depth (weights packed as tiles)
     int kc, chunk23;        // T4: tile depth (64 | 32); 1 = chunked layer-2/3 path for wide policies
+    // state LSTM (VideoForecastNet.s_net, step mode): tile-packed [4H][S + H] weights, bias, per-CTA h | c scratch
+    const double *sn_Wp, *sn_b;
+    double *sn_state;
+    int sn_H, sn_Kp;
 };
 
 // video-context row of (take, start, t): per-frame table, or one row block per (take, start) episode window
 __device__ __forceinline__ const double *ctx_row(const RolloutArgs &A, int take, int start, int t) {
     const size_t r = A.ctx_mode == 0 ? (size_t)(A.take_off[take] + start + t)
-                                     : (size_t)(A.win_off[take] + start - A.cfg.fr_margin) * A.ctx_T + t;
+                   : A.ctx_mode == 1 ? (size_t)(A.win_off[take] + start - A.cfg.fr_margin) * A.ctx_T + t
+                                     : (size_t)(A.win_off[take] + start - A.cfg.fr_margin);
     return A.ctx + r * A.ctx_dim;
 }
 
@@ -1415,7 +1420,7 @@ __device__ __forceinline__ void t4_policy_forward(const RolloutArgs &A, double *
     __syncthreads();
 }
 
-template <int KC, bool CHUNK>
+template <int KC, bool CHUNK, bool SNET>
 __global__ void __launch_bounds__(T4_THREADS, 1)
 rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
     extern __shared__ double smem[];
@@ -1436,9 +1441,14 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
     const int S = c_m.nq - 2 + c_m.nv, nu = c_m.nu, nv = c_m.nv, nb = c_m.nbody, nq = c_m.nq;
     double *xs = smem + (size_t)O.ax * 32;               // MLP activations alias the axis / anchor / U rows
     const int h2rows = CHUNK ? MLP_C2 : A.H2p;
-    const int xrows = A.D > h2rows ? A.D : h2rows;
+    int xrows = A.D > h2rows ? A.D : h2rows;
+    int hrows4 = A.H1p > A.Ap ? A.H1p : A.Ap;
+    if (SNET) {                                          // same plan as egp_rollout_f64: LSTM input / gate-chunk rows
+        const int sn_in = c_m.nq - 2 + c_m.nv + A.sn_H;
+        if (xrows < sn_in) xrows = sn_in;
+        if (hrows4 < 256) hrows4 = 256;
+    }
     double *h1s = xs + (size_t)xrows * 32;
-    const int hrows4 = A.H1p > A.Ap ? A.H1p : A.Ap;
     double *stage = h1s + (size_t)hrows4 * 32 + (size_t)w * KC * JB;    // per-warp weight tile
     const int T = A.cfg.horizon, E = A.cfg.n_env;
     const double dt = c_m.h * c_m.frame_skip;
@@ -1509,6 +1519,9 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
     do_reset();
     make_state(raw, st);
     T4_FOR_OWN_DOFS(i, b) l.ctrl[i] = 0.0;
+    // state-LSTM h | c rows of this CTA, [2H][32] (s_net.initialize() at pre_episode, rnn.py:22-26)
+    double *sn_g = SNET ? A.sn_state + (size_t)blockIdx.x * 2 * A.sn_H * 32 : nullptr;
+    if (sn_g) for (int j = w; j < 2 * A.sn_H; j += T4_WARPS) sn_g[j * 32 + lane] = 0.0;
 
     for (int t = 0; t < T; t++) {
         const size_t n = (size_t)eid * T + t;
@@ -1521,7 +1534,7 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
         __syncthreads();
         // ---- policy input cat(ctx[frame], state), feature-major
         int off = 0;
-        if (A.ctx) {
+        if (A.ctx && !sn_g) {
             const double *cx = ctx_row(A, take, start, cur_t);
             for (int k = w; k < A.ctx_dim; k += T4_WARPS) xs[k * 32 + lane] = cx[k];
             off = A.ctx_dim;
@@ -1535,6 +1548,33 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
                     if (A.out.d_raw_obs) A.out.d_raw_obs[n * S + k] = raw[s];
                 }
             }
+        }
+        if (sn_g) {
+            // ---- s_net LSTMCell step on the filtered state (video_forecast_net.py:89-93, rnn.py:36-43):
+            // gates = W [state | h_prev] + b, 64 units (256 packed gate rows 4u + g) at a time through the dense-layer
+            // routine, then c = sig(f) c + sig(i) tanh(g), h = sig(o) tanh(c); policy input = cat(ctx row, h)
+            const int H = A.sn_H;
+            for (int j = w; j < H; j += T4_WARPS) xs[(S + j) * 32 + lane] = sn_g[j * 32 + lane];
+            __syncthreads();
+            for (int c0 = 0; c0 < H; c0 += 64) {
+                const int hi = c0 + 64 < H ? c0 + 64 : H;
+                t4_mlp_layer<false, KC>(A.sn_Wp, A.sn_b, S + H, A.sn_Kp, c0 * 4 / JB, hi * 4 / JB, 0, xs, h1s, stage, lane, w);
+                __syncthreads();
+                for (int u = c0 + w; u < hi; u += T4_WARPS) {
+                    const double *gr = h1s + (size_t)(u - c0) * 4 * 32 + lane;
+                    const double ig = 1.0 / (1.0 + exp(-gr[0])), fg = 1.0 / (1.0 + exp(-gr[32]));
+                    const double gg = tanh(gr[64]), og = 1.0 / (1.0 + exp(-gr[96]));
+                    const double cn = fg * sn_g[(H + u) * 32 + lane] + ig * gg;
+                    sn_g[(H + u) * 32 + lane] = cn;
+                    sn_g[u * 32 + lane] = og * tanh(cn);
+                }
+                __syncthreads();
+            }
+            if (A.ctx) {
+                const double *cx = ctx_row(A, take, start, cur_t);
+                for (int k = w; k < A.ctx_dim; k += T4_WARPS) xs[k * 32 + lane] = cx[k];
+            }
+            for (int j = w; j < H; j += T4_WARPS) xs[(A.ctx_dim + j) * 32 + lane] = sn_g[j * 32 + lane];
         }
         __syncthreads();
         t4_policy_forward<KC, CHUNK>(A, xs, h1s, stage, lane, w);
@@ -1712,7 +1752,10 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
                     }
             for (int b = 1 + w; b < nb; b += T4_WARPS) for (int k = 0; k < 4; k++) k_bqc[b][k] = l.bqc[b][k];
             if (w0) for (int k = 0; k < 3 * (EGP_NEE + 1); k++) k_xp[k] = x.at(O.xp, k);
-            if (need_reset) { n_reset++; draw_reset(n_reset); cur_t = 0; }
+            if (need_reset) {
+                n_reset++; draw_reset(n_reset); cur_t = 0;
+                if (sn_g) for (int j = w; j < 2 * A.sn_H; j += T4_WARPS) sn_g[j * 32 + lane] = 0.0;
+            }
             __syncthreads();
             if (need_reset) {
                 const double *r0 = A.rows + (size_t)(A.take_off[take] + start) * EGP_X_STRIDE;
@@ -2142,11 +2185,16 @@ int egp_rollout_f64(EgpModel *m, const EgpPolicyWeights *pol, const EgpRolloutCf
     const bool ctx_override = in && in->d_ctx;
     const int ctx_dim = ctx_override ? in->ctx_dim : m->ctx_dim;
     if (ctx_override && (in->ctx_dim < 1 || (in->ctx_mode == 1 && (!in->d_win_off || in->ctx_T < cfg->episode_len)) ||
-                         (in->ctx_mode != 0 && in->ctx_mode != 1))) {
+                         (in->ctx_mode == 2 && !in->d_win_off) || in->ctx_mode < 0 || in->ctx_mode > 2)) {
         set_error("egp_rollout_f64: bad context table (dim %d mode %d T %d)", in->ctx_dim, in->ctx_mode, in->ctx_T);
         return EGP_EINVAL;
     }
-    if (pol->in_dim != S + ctx_dim || pol->out_dim != d.nu) {
+    const int snH = in ? in->snet_hdim : 0;
+    if (snH < 0 || (snH & 1) || (snH > 0 && (!in->d_snet_W || !in->d_snet_b || !in->d_snet_state))) {
+        set_error("egp_rollout_f64: bad state-LSTM arguments (hdim %d must be even, W / b / state scratch required)", snH);
+        return EGP_EINVAL;
+    }
+    if (pol->in_dim != (snH ? snH : S) + ctx_dim || pol->out_dim != d.nu) {
         set_error("egp_rollout_f64: policy dims (in %d out %d) do not match obs %d + ctx %d / nu %d", pol->in_dim, pol->out_dim, S, ctx_dim, d.nu);
         return EGP_ESIZE;
     }
@@ -2176,6 +2224,11 @@ int egp_rollout_f64(EgpModel *m, const EgpPolicyWeights *pol, const EgpRolloutCf
     A.H1p = pad(A.H1); A.H2p = pad(A.H2); A.Ap = pad(A.A);
     int xrows = A.D > A.H2p ? A.D : A.H2p;
     int hrows = A.H1p > A.Ap ? A.H1p : A.Ap;
+    if (snH) {                      // LSTM input rows [S + H] and one 64-unit gate chunk (256 rows)
+        if (hrows < 256) hrows = 256;
+        A.sn_H = snH;
+    }
+    const int sn_in = snH ? S + snH : 0;
     int blocks = (cfg->n_env + ENVS_PER_CTA - 1) / ENVS_PER_CTA;
     // variant selection: T4 (4 warps per 32 envs, tree data in shared memory) when the model and the policy
     // width fit, else the one-warp V1 kernel; EGP_ROLLOUT_VARIANT=1 forces V1 (A/B parity runs)
@@ -2195,6 +2248,7 @@ int egp_rollout_f64(EgpModel *m, const EgpPolicyWeights *pol, const EgpRolloutCf
             int kc = plans[pi][0], ch = plans[pi][1];
             int h2r = ch ? MLP_C2 : A.H2p;
             int xr = A.D > h2r ? A.D : h2r;
+            if (xr < sn_in) xr = sn_in;
             int need_rows = xr + hrows + T4_WARPS * kc * JB / 32;
             if (O.ax + need_rows <= limit_rows) {
                 use_t4 = true; A.kc = kc; A.chunk23 = ch;
@@ -2206,7 +2260,10 @@ int egp_rollout_f64(EgpModel *m, const EgpPolicyWeights *pol, const EgpRolloutCf
     const int kcv = A.kc;
     auto padk = [kcv](int x) { return (x + kcv - 1) / kcv * kcv; };
     A.K1p = use_t4 ? padk(A.D) : A.D; A.K2p = use_t4 ? padk(A.H1) : A.H1; A.K3p = use_t4 ? padk(A.H2) : A.H2;
-    size_t need = (size_t)A.K1p * A.H1p + A.H1p + (size_t)A.K2p * A.H2p + A.H2p + (size_t)A.K3p * A.Ap + A.Ap;
+    if (snH && !use_t4) { set_error("egp_rollout_f64: the state LSTM needs the T4 rollout variant (policy too wide?)"); return EGP_ESIZE; }
+    A.sn_Kp = snH ? padk(sn_in) : 0;
+    size_t need = (size_t)A.K1p * A.H1p + A.H1p + (size_t)A.K2p * A.H2p + A.H2p + (size_t)A.K3p * A.Ap + A.Ap +
+                  (size_t)A.sn_Kp * 4 * snH + 4 * snH;
     if (need > m->wbuf_elems) {
         cudaFree(m->d_wbuf);
         m->d_wbuf = nullptr; m->wbuf_elems = 0;
@@ -2219,7 +2276,13 @@ int egp_rollout_f64(EgpModel *m, const EgpPolicyWeights *pol, const EgpRolloutCf
     double *W2t = w; w += (size_t)A.K2p * A.H2p;
     double *b2 = w; w += A.H2p;
     double *W3t = w; w += (size_t)A.K3p * A.Ap;
-    double *b3 = w;
+    double *b3 = w; w += A.Ap;
+    double *snW = w; w += (size_t)A.sn_Kp * 4 * snH;
+    double *snb = w;
+    if (snH) {
+        pack_tiles_kernel<<<(A.sn_Kp * 4 * snH + 255) / 256, 256, 0, st>>>(in->d_snet_W, in->d_snet_b, 4 * snH, sn_in, 4 * snH, A.sn_Kp, snW, snb);
+        A.sn_Wp = snW; A.sn_b = snb; A.sn_state = in->d_snet_state;
+    }
     if (use_t4) {
         pack_tiles_kernel<<<(A.K1p * A.H1p + 255) / 256, 256, 0, st>>>(pol->d_W1, pol->d_b1, A.H1, A.D, A.H1p, A.K1p, W1t, b1);
         pack_tiles_kernel<<<(A.K2p * A.H2p + 255) / 256, 256, 0, st>>>(pol->d_W2, pol->d_b2, A.H2, A.H1, A.H2p, A.K2p, W2t, b2);
@@ -2244,9 +2307,13 @@ int egp_rollout_f64(EgpModel *m, const EgpPolicyWeights *pol, const EgpRolloutCf
             EGP_CHECK_LAUNCH("rollout_kernel_t4");
             return EGP_OK;
         };
-        if (A.kc == 64) return launch(rollout_kernel_t4<64, false>);
-        if (!A.chunk23) return launch(rollout_kernel_t4<32, false>);
-        return launch(rollout_kernel_t4<32, true>);
+        if (snH) {
+            if (A.chunk23) { set_error("egp_rollout_f64: state LSTM with the chunked wide-policy plan is not supported"); return EGP_ESIZE; }
+            return A.kc == 64 ? launch(rollout_kernel_t4<64, false, true>) : launch(rollout_kernel_t4<32, false, true>);
+        }
+        if (A.kc == 64) return launch(rollout_kernel_t4<64, false, false>);
+        if (!A.chunk23) return launch(rollout_kernel_t4<32, false, false>);
+        return launch(rollout_kernel_t4<32, true, false>);
     }
     size_t smem = sizeof(double) * ENVS_PER_CTA * ((size_t)xrows + hrows);
     if (smem > 227 * 1024) { set_error("egp_rollout_f64: policy too wide for shared memory (%zu bytes)", smem); return EGP_ESIZE; }

@@ -232,7 +232,12 @@ gauss_logp_kernel(const double *__restrict__ mu, const double *__restrict__ act,
     const int sub = threadIdx.x & (LPR - 1);
     const long long g0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / LPR;
     const long long stride = (long long)gridDim.x * blockDim.x / LPR;
-    for (long long row = g0; row < n; row += stride) {
+    // warp-uniform trip count: both 16-lane halves of a warp run the same number of iterations (a half whose row is
+    // past the end computes on row n - 1 and discards), so every full-mask shuffle below is executed by all 32 lanes
+    const long long g_lo = (blockIdx.x * (long long)blockDim.x + (threadIdx.x & ~31)) / LPR;
+    for (long long row_u = g_lo, row_t = g0; row_u < n; row_u += stride, row_t += stride) {
+        const bool valid = row_t < n;
+        const long long row = valid ? row_t : n - 1;
         double s = 0.0;
         for (int j = sub; j < adim; j += LPR) {
             double ls = log_std[j], d = act[row * adim + j] - mu[row * adim + j];
@@ -240,7 +245,7 @@ gauss_logp_kernel(const double *__restrict__ mu, const double *__restrict__ act,
             s += -(d * d) / (2.0 * var) - ls - HALF_LOG_2PI;
         }
         s = group_sum16(s);
-        if (sub == 0) logp[row] = s;
+        if (sub == 0 && valid) logp[row] = s;
     }
 }
 
@@ -255,7 +260,12 @@ ppo_loss_grad_kernel(const double *__restrict__ mu, const double *__restrict__ a
     const double a_mean = stats[1], a_inv = 1.0 / sqrt(stats[2] / (stats[0] - 1.0));
     double loss_acc = 0.0;
     double dls_acc[4] = {0.0, 0.0, 0.0, 0.0};       // adim <= 64
-    for (long long row = g0; row < n; row += stride) {
+    // warp-uniform trip count: both 16-lane halves of a warp run the same number of iterations (a half whose row is
+    // past the end computes on row n - 1 and discards), so every full-mask shuffle below is executed by all 32 lanes
+    const long long g_lo = (blockIdx.x * (long long)blockDim.x + (threadIdx.x & ~31)) / LPR;
+    for (long long row_u = g_lo, row_t = g0; row_u < n; row_u += stride, row_t += stride) {
+        const bool valid = row_t < n;
+        const long long row = valid ? row_t : n - 1;
         double d[4], iv[4];
         double s = 0.0;
         int cnt = 0;
@@ -268,7 +278,7 @@ ppo_loss_grad_kernel(const double *__restrict__ mu, const double *__restrict__ a
             s += -(d[cnt] * d[cnt]) / (2.0 * var) - ls - HALF_LOG_2PI;
         }
         s = group_sum16(s);
-        const bool on = exps[row] != 0.0;
+        const bool on = valid && exps[row] != 0.0;
         double coef = 0.0;                           // dL/dlogp
         if (on) {
             double ratio = exp(s - logp0[row]);
@@ -283,7 +293,7 @@ ppo_loss_grad_kernel(const double *__restrict__ mu, const double *__restrict__ a
             if (sub == 0) loss_acc += -fmin(s1, s2) * inv_count;
         }
         cnt = 0;
-        for (int j = sub; j < adim; j += LPR, cnt++) {
+        for (int j = sub; j < adim && valid; j += LPR, cnt++) {
             dmu[row * adim + j] = coef * d[cnt] * iv[cnt];
             dls_acc[cnt] += coef * (d[cnt] * d[cnt] * iv[cnt] - 1.0);
         }
@@ -292,10 +302,11 @@ ppo_loss_grad_kernel(const double *__restrict__ mu, const double *__restrict__ a
     loss_acc = warp_sum(loss_acc);
     if ((threadIdx.x & 31) == 0 && loss_acc != 0.0) atomicAdd(loss, loss_acc);
     if (dlogstd) {
-        int cnt = 0;
-        for (int j = sub; j < adim; j += LPR, cnt++) {
+#pragma unroll
+        for (int cnt = 0; cnt < 4; cnt++) {         // uniform trip count: the shuffle is executed by all 32 lanes
+            const int j = sub + cnt * LPR;
             double v = dls_acc[cnt] + __shfl_xor_sync(0xffffffffu, dls_acc[cnt], 16);
-            if ((threadIdx.x & 31) < LPR && v != 0.0) atomicAdd(dlogstd + j, v);
+            if (j < adim && (threadIdx.x & 31) < LPR && v != 0.0) atomicAdd(dlogstd + j, v);
         }
     }
 }

@@ -59,7 +59,8 @@ class PolicyWeights(C.Structure):
 class RolloutIn(C.Structure):
     _fields_ = [('d_eps', _vp), ('d_reset_take', _vp), ('d_reset_start', _vp), ('d_mean_flag', _vp),
                 ('d_zf_mean', _vp), ('d_zf_std', _vp), ('d_ctx', _vp), ('d_win_off', _vp), ('ctx_dim', C.c_int32),
-                ('ctx_mode', C.c_int32), ('ctx_T', C.c_int32)]
+                ('ctx_mode', C.c_int32), ('ctx_T', C.c_int32), ('d_snet_W', _vp), ('d_snet_b', _vp), ('d_snet_state', _vp),
+                ('snet_hdim', C.c_int32)]
 
 
 class TrajOut(C.Structure):
@@ -283,7 +284,7 @@ class Model:
     def rollout(self, weights, n_env, horizon, episode_len, fr_margin=10, end_reward=0.0, fix_head_lb=None,
                 noise_rate=1.0, mean_action=False, zf_mean=None, zf_std=None, zf_clip=5.0, seed=1, iteration=0,
                 eps=None, reset_take=None, reset_start=None, mean_flag=None, want_next=True, want_raw=True, out=None,
-                ctx=None, win_off=None):
+                ctx=None, win_off=None, ctx_const=False, snet=None):
         """weights: dict with W1,b1,W2,b2,W3,b3,log_std CUDA float64 tensors (torch [out,in] layout).
         Returns a dict of CUDA tensors in TrajBatchEgo layout (+ logger, c_info, raw_obs, final state)."""
         global launches
@@ -325,6 +326,13 @@ class Model:
         if ctx is not None:         # per-rollout context table (window-indexed when win_off is given)
             inp.d_ctx, inp.ctx_dim = ptr(ctx), ctx.shape[1]
             inp.d_win_off, inp.ctx_mode, inp.ctx_T = ptr(win_off), int(win_off is not None), int(episode_len)
+            if ctx_const:           # one row per (take, start) window, constant over the episode (VideoForecastNet v_out)
+                inp.ctx_mode, inp.ctx_T = 2, 1
+        if snet is not None:        # (W [4H, S + H], b [4H], H): state LSTM stepped inside the kernel
+            sW, sb, sH = snet
+            inp.d_snet_W, inp.d_snet_b, inp.snet_hdim = ptr(sW), ptr(sb), int(sH)
+            inp.d_snet_state = ptr(buf('snet_state', ((n_env + 31) // 32 * 2 * int(sH) * 32,)))
+            launches += 1
         pw = PolicyWeights()
         pw.in_dim, pw.h1 = weights['W1'].shape[1], weights['W1'].shape[0]
         pw.h2, pw.out_dim = weights['W2'].shape[0], weights['W3'].shape[0]

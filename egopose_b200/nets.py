@@ -284,6 +284,156 @@ class VideoStateNet(nn.Module):
         return torch.cat(rows).contiguous(), torch.tensor(win_off, dtype=torch.int32, device=p.device)
 
 
+class VideoForecastNet(nn.Module):
+    """models/video_forecast_net.py:8-111 mirror (lstm v_net, 'lstm' | 'id' s_net, dynamic_v False - what the shipped
+    egoforecast configs select): same constructor, modes, forward semantics and state-dict keys (v_net.rnn_f.*,
+    s_net.rnn_f.*).
+
+    test mode  : initialize(cnn_feat[start-m : ...]) runs the causal LSTM over the m = v_margin frames BEFORE the episode
+                 start, v_out = last hidden state (constant over the episode); forward(state) steps the state LSTM
+                 once and returns cat(v_out, h_t)                                                   (:57-61, 86-93)
+    train mode : initialize((masks, cnn_feat, v_metas)) splits the flat batch into episodes; forward(states) re-runs
+                 the causal LSTM per episode and unrolls the state LSTM over every episode from a zero state (:62-107)
+
+    Fused-path entry points (egopose_b200.agent.AgentEgo): ``context_table`` = test-mode v_out for EVERY (take, start)
+    window (one row per window, rollout ctx_mode 2); ``snet_packed`` = the state-LSTM weights in the row order the
+    rollout kernel steps them in; ``train_context(states)`` = train-mode forward with the autograd graph attached.
+    The reference pads every episode to the longest one (:97-101); here episodes are sorted by length and each unroll
+    step only touches the episodes still alive, so the work is proportional to the batch, not to n_ep x Tmax."""
+
+    def __init__(self, cnn_feat_dim, state_dim, v_hdim=128, v_margin=10, v_net_type='lstm', v_net_param=None,
+                 s_hdim=None, s_net_type='id', dynamic_v=False):
+        super().__init__()
+        if v_net_type != 'lstm':
+            raise NotImplementedError('v_net_type %r: only lstm is selected by the shipped configs' % v_net_type)
+        if s_net_type not in ('lstm', 'id'):
+            raise NotImplementedError('s_net_type %r' % s_net_type)
+        if dynamic_v:
+            raise NotImplementedError('dynamic_v is not selected by any shipped config (egoforecast_config.py:52,65)')
+        s_hdim = state_dim if s_hdim is None else s_hdim
+        self.mode = 'test'
+        self.cnn_feat_dim, self.state_dim = cnn_feat_dim, state_dim
+        self.v_net_type, self.v_hdim, self.v_margin = v_net_type, v_hdim, v_margin
+        self.s_net_type, self.s_hdim, self.dynamic_v = s_net_type, s_hdim, dynamic_v
+        self.out_dim = v_hdim + s_hdim
+        self.v_net = RNN(cnn_feat_dim, v_hdim, v_net_type, bi_dir=False)
+        if s_net_type == 'lstm':
+            self.s_net = RNN(state_dim, s_hdim, s_net_type, bi_dir=False)
+        self.v_out, self.t = None, 0
+        self._ep = None
+        self.set_mode('test')
+
+    def set_mode(self, mode):
+        self.mode = mode
+        if self.s_net_type == 'lstm':
+            self.s_net.set_mode('batch' if mode == 'train' else 'step')
+
+    def _p(self):
+        return self.v_net.rnn_f.weight_ih
+
+    def forward_v_net(self, x):
+        return self.v_net(x)
+
+    def initialize(self, x):
+        if self.mode == 'test':
+            self.v_out = self.forward_v_net(x.unsqueeze(1)[:self.v_margin])[-1]
+            if self.s_net_type == 'lstm':
+                self.s_net.initialize()
+            self.t = 0
+            return
+        masks, cnn_feat, v_metas = x
+        p, m = self._p(), self.v_margin
+        masks_np = masks.detach().cpu().numpy() if torch.is_tensor(masks) else np.asarray(masks)
+        v_metas = v_metas.detach().cpu().numpy() if torch.is_tensor(v_metas) else np.asarray(v_metas)
+        ends = np.nonzero(masks_np == 0)[0]
+        starts = np.concatenate([[0], ends[:-1] + 1])
+        lens = ends - starts + 1
+        order = np.argsort(-lens, kind='stable')                    # longest episode first
+        lens_s, starts_s = lens[order], starts[order]
+        tmax = int(lens_s[0])
+        # alive[t] = number of (sorted) episodes with length > t; rows[t] = flat batch rows of their step t
+        alive = np.searchsorted(-lens_s, -np.arange(tmax), side='left')
+        rows = [torch.as_tensor(starts_s[:alive[t]] + t, dtype=torch.long, device=p.device) for t in range(tmax)]
+        n = masks_np.shape[0]
+        rank = np.empty(len(ends), dtype=np.int64)
+        rank[order] = np.arange(len(ends))
+        ep_of = np.repeat(np.arange(len(ends)), lens)
+        offs = np.concatenate([[0], np.cumsum([c.shape[0] for c in cnn_feat])])
+        feats = torch.as_tensor(np.concatenate(cnn_feat), dtype=p.dtype, device=p.device)
+        meta = v_metas[ends].astype(np.int64)
+        base = offs[meta[:, 0]] + meta[:, 1] - m
+        if base.min() < 0:
+            raise IndexError('episode context window leaves the take (video_forecast_net.py:82)')
+        frame = base[None, :] + np.arange(m)[:, None]
+        self._ep = dict(n=n, tmax=tmax, alive=alive, rows=rows,
+                        ep_of=torch.as_tensor(ep_of, dtype=torch.long, device=p.device),
+                        cnn_ctx=feats[torch.as_tensor(frame, device=p.device)])      # [m, n_ep, F]
+
+    def train_context(self, states):
+        """-> [N, v_hdim + s_hdim] = cat(v_out of the row's episode, state-LSTM output at the row)"""
+        e = self._ep
+        v_ep = self.forward_v_net(e['cnn_ctx'])[-1]                                  # [n_ep, v_hdim]
+        v_out = v_ep.index_select(0, e['ep_of'])
+        if self.s_net_type != 'lstm':
+            return torch.cat((v_out, states), dim=1)
+        cell = self.s_net.rnn_f
+        H = cell.hidden_size
+        xi = torch.addmm(cell.bias_ih + cell.bias_hh, states, cell.weight_ih.t())    # input projection of every row
+        whh_t = cell.weight_hh.t()
+        h = states.new_zeros((int(e['alive'][0]), H))
+        c = torch.zeros_like(h)
+        outs = []
+        for t in range(e['tmax']):
+            na = int(e['alive'][t])
+            h, c = h[:na], c[:na]
+            gates = xi.index_select(0, e['rows'][t]) + h @ whh_t
+            i, f, g, o = gates.chunk(4, 1)
+            c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
+            h = torch.sigmoid(o) * torch.tanh(c)
+            outs.append(h)
+        s_out = states.new_zeros((e['n'], H)).index_copy(0, torch.cat(e['rows']), torch.cat(outs))
+        return torch.cat((v_out, s_out), dim=1)
+
+    def forward(self, x):
+        if self.mode == 'test':
+            if self.s_net_type == 'lstm':
+                x = self.s_net(x)
+            x = torch.cat((self.v_out.to(x.device), x), dim=1)
+            self.t += 1
+            return x
+        return self.train_context(x)
+
+    @torch.no_grad()
+    def context_table(self, cnn_feat, episode_len, max_batch=8192):
+        """-> (table [n_windows, v_hdim], win_off int32 [n_takes + 1]); window w of take k starts at frame
+        start = v_margin + (w - win_off[k]) (the range reset_model samples from, humanoid_v1.py:214)."""
+        p, m, T = self._p(), self.v_margin, int(episode_len)
+        rows, win_off = [], [0]
+        for feat in cnn_feat:
+            f = torch.as_tensor(feat, dtype=p.dtype, device=p.device)
+            nwin = f.shape[0] - T - 2 * m
+            if nwin <= 0:
+                raise ValueError('take shorter than episode_len + 2 * fr_margin')
+            for lo in range(0, nwin, max_batch):
+                hi = min(nwin, lo + max_batch)
+                idx = torch.arange(m, device=p.device)[:, None] + torch.arange(lo, hi, device=p.device)[None, :]
+                rows.append(self.forward_v_net(f[idx])[-1])
+            win_off.append(win_off[-1] + nwin)
+        return torch.cat(rows).contiguous(), torch.tensor(win_off, dtype=torch.int32, device=p.device)
+
+    @torch.no_grad()
+    def snet_packed(self):
+        """state-LSTM weights for egp_rollout_f64 (include/egopose_b200.h, EgpRolloutIn.d_snet_W / d_snet_b):
+        row 4u + g = cat(weight_ih[g H + u], weight_hh[g H + u]), bias = bias_ih + bias_hh, g = (i, f, g, o)"""
+        if self.s_net_type != 'lstm':
+            return None
+        cell = self.s_net.rnn_f
+        H = cell.hidden_size
+        W = torch.cat((cell.weight_ih, cell.weight_hh), dim=1).view(4, H, -1).transpose(0, 1).reshape(4 * H, -1)
+        b = (cell.bias_ih + cell.bias_hh).view(4, H).t().reshape(-1)
+        return W.contiguous(), b.contiguous(), H
+
+
 def trunk_ok(net):
     """the fused kernels implement the two-hidden-layer relu trunk every shipped yml selects
     (config/egomimic/subject_03.yml:14-16,21-23)"""

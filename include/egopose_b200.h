@@ -106,8 +106,18 @@ typedef struct {
      * start - fr_margin) * ctx_T + t: one test-mode VideoStateNet output v_out[t] per (take, start) episode window
      * (models/video_state_net.py:36-39,61-64), ctx_T = env_episode_len rows per window. */
     const double *d_ctx;
-    const int32_t *d_win_off;           /* [n_takes + 1], ctx_mode 1 */
+    const int32_t *d_win_off;           /* [n_takes + 1], ctx_mode 1 / 2 */
     int32_t ctx_dim, ctx_mode, ctx_T;
+    /* ctx_mode 2: ONE row per (take, start) window, row = win_off[take] + start - fr_margin, constant over the
+     * episode: test-mode VideoForecastNet v_out (models/video_forecast_net.py:58-59, causal LSTM over the fr_margin
+     * frames before the episode start).
+     * Optional state LSTM stepped once per env step on the filtered state (VideoForecastNet.s_net in 'step' mode,
+     * models/video_forecast_net.py:60-61,89-93 + models/rnn.py:22-26,36-43): h, c = 0 at every episode start, the
+     * policy input becomes cat(ctx row, h_t) instead of cat(ctx row, state).  snet_hdim = 0 disables. */
+    const double *d_snet_W;             /* [4H][S + H]: row 4u + g = cat(weight_ih[g*H + u], weight_hh[g*H + u]), g = i,f,g,o */
+    const double *d_snet_b;             /* [4H] bias_ih + bias_hh in the same row order */
+    double *d_snet_state;               /* caller-owned scratch, ceil(E / 32) * 2H * 32 doubles */
+    int32_t snet_hdim;                  /* H (even) */
 } EgpRolloutIn;
 
 /* TrajBatchEgo layout (core/trajbatch.py:6-16, ego_pose/core/trajbatch_ego.py:7-9), all device, row-major. */

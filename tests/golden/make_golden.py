@@ -213,6 +213,83 @@ def gen_vsnet():
     print('vsnet_small: surr', np.round(surr, 6), 'test_v_out', out['test_v_out'].shape)
 
 
+def gen_fcnet():
+    """models/video_forecast_net.py + models/rnn.py (causal LSTM v_out + per-step state LSTM) in test mode, and
+    ego_pose/core/agent_ego.py update_params with real forecast vs-nets (train mode, padded unroll) on a small
+    synthetic batch (3 takes, margin 4, feature dim 8, v_hdim 6, s_hdim 10)."""
+    import types
+    from core.critic import Value
+    from core.policy_gaussian import PolicyGaussian
+    from ego_pose.core.agent_ego import AgentEgo
+    from models.mlp import MLP
+    from models.video_forecast_net import VideoForecastNet
+    torch.manual_seed(11)
+    rng = np.random.RandomState(11)
+    F, VH, M, S, A, T, SH = 8, 6, 4, 10, 4, 7, 10
+    cnn_feat = [rng.randn(34, F) for _ in range(3)]
+    pvs = VideoForecastNet(F, S, VH, M, 'lstm', None, SH, 'lstm', False)
+    vvs = VideoForecastNet(F, S, VH, M, 'lstm', None, SH, 'lstm', False)
+    pol = PolicyGaussian(MLP(pvs.out_dim, (16, 12), 'relu'), A, log_std=-1.0, fix_std=True)
+    val = Value(MLP(vvs.out_dim, (16, 12), 'relu'))
+    out = {'cnn_feat': np.stack(cnn_feat), 'dims': np.array([F, VH, M, S, A, T, SH])}
+    for name, net in (('pvs0', pvs), ('vvs0', vvs), ('p0', pol), ('v0', val)):
+        for k, v in net.state_dict().items():
+            out['%s.%s' % (name, k)] = v.numpy().copy()
+    # test mode (agent_ego.py:21-22 + agents/agent.py:44): initialize on the episode window, then step 5 states
+    pvs.set_mode('test')
+    test_states = rng.randn(5, S)
+    with torch.no_grad():
+        pvs.initialize(torch.from_numpy(cnn_feat[1][9 - M: 9 + T + M]))
+        out['test_v_out'] = pvs.v_out.numpy().copy()
+        out['test_x'] = np.concatenate([pvs(torch.from_numpy(test_states[[i]])).numpy() for i in range(5)])
+        out['test_mu'] = pol(torch.from_numpy(out['test_x'])).loc.numpy().copy()
+    out['test_states'] = test_states
+    lens = [7, 3, 5, 7, 2, 6, 1]
+    metas = [(0, 4), (1, 9), (2, 5), (1, 6), (0, 12), (2, 8), (1, 20)]
+    N = sum(lens)
+    masks = np.ones(N)
+    v_metas = np.zeros((N, 2), dtype=np.int64)
+    i = 0
+    for ln, mt in zip(lens, metas):
+        v_metas[i:i + ln] = mt
+        masks[i + ln - 1] = 0
+        i += ln
+    batch = types.SimpleNamespace(states=rng.randn(N, S), actions=rng.randn(N, A) * 0.5, rewards=rng.rand(N), masks=masks,
+                                  exps=(rng.rand(N) > 0.15).astype(np.float64), v_metas=v_metas)
+    for k in ('states', 'actions', 'rewards', 'masks', 'exps', 'v_metas'):
+        out['batch.' + k] = getattr(batch, k)
+    # train-mode forward of the policy context on the batch (video_forecast_net.py:94-109)
+    pvs.set_mode('train')
+    pvs.initialize((torch.from_numpy(masks), cnn_feat, v_metas))
+    with torch.no_grad():
+        out['train_x'] = pvs(torch.from_numpy(batch.states)).numpy().copy()
+    pparams = list(pol.parameters()) + list(pvs.parameters())
+    vparams = list(val.parameters()) + list(vvs.parameters())
+    opt_p = torch.optim.Adam(pparams, lr=3e-3)
+    opt_v = torch.optim.Adam(vparams, lr=2e-3)
+    env = types.SimpleNamespace(cnn_feat=cnn_feat)
+    agent = AgentEgo(env=env, dtype=torch.float64, device=torch.device('cpu'), running_state=None, custom_reward=None,
+                     policy_net=pol, policy_vs_net=pvs, value_net=val, value_vs_net=vvs, optimizer_policy=opt_p,
+                     optimizer_value=opt_v, opt_num_epochs=3, gamma=0.95, tau=0.95, clip_epsilon=0.2,
+                     policy_grad_clip=[(pparams, 0.5)])
+    surr = []
+    orig_loss = agent.ppo_loss
+
+    def rec_loss(*a):
+        loss = orig_loss(*a)
+        surr.append(loss.item())
+        return loss
+    agent.ppo_loss = rec_loss
+    agent.update_params(batch)
+    out['surr_loss'] = np.array(surr)
+    for name, net in (('pvs3', pvs), ('vvs3', vvs), ('p3', pol), ('v3', val)):
+        for k, v in net.state_dict().items():
+            out['%s.%s' % (name, k)] = v.numpy().copy()
+    out['hyper'] = np.array([0.95, 0.95, 0.2, 3e-3, 2e-3, 0.5])
+    np.savez_compressed(os.path.join(OUT, 'fcnet_small.npz'), **out)
+    print('fcnet_small: surr', np.round(surr, 6), 'test_x', out['test_x'].shape)
+
+
 def gen_math():
     from utils.math import (de_heading, get_angvel_fd, get_heading_q, get_qvel_fd, multi_quat_diff, multi_quat_norm,
                             transform_vec)
@@ -378,13 +455,15 @@ def gen_env():
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['ppo', 'math', 'zfilter', 'env', 'vsnet']
+    which = sys.argv[1:] or ['ppo', 'math', 'zfilter', 'env', 'vsnet', 'fcnet']
     if 'ppo' in which:
         gen_ppo()
     if 'ppo_mb' in which or 'ppo' in which:
         gen_ppo_minibatch()
     if 'vsnet' in which:
         gen_vsnet()
+    if 'fcnet' in which:
+        gen_fcnet()
     if 'math' in which:
         gen_math()
     if 'zfilter' in which:

@@ -100,6 +100,43 @@ def test_logp_and_loss_golden(golden):
     assert np.allclose(dls.cpu().numpy(), ls2.grad.numpy().ravel(), rtol=1e-9, atol=1e-12)
 
 
+@pytest.mark.parametrize('n,adim', [(1, 52), (31, 4), (33, 52), (257, 17), (4099, 52)])
+def test_loss_kernels_ragged_sizes(n, adim):
+    """row counts that leave half a warp without a row, action dims that are not a multiple of the 16 lanes per row
+    (regression: full-mask shuffles under a divergent row loop)"""
+    from egopose_b200 import lib
+    rng = np.random.RandomState(n + adim)
+    mu, ac = rng.randn(n, adim) * 0.1, rng.randn(n, adim) * 0.2
+    ls = rng.uniform(-1.5, -0.5, size=adim)
+    adv = rng.randn(n) * 2 + 1
+    exps = (rng.rand(n) > 0.2).astype(np.float64)
+    exps[0] = 1.0
+    mu0 = mu + 0.05 * rng.randn(n, adim)
+    lp0 = oppo.log_prob(torch.from_numpy(mu0), torch.from_numpy(ls), torch.from_numpy(ac))
+    logp0 = lib.gauss_logp(cu(mu0), cu(ac), cu(ls))
+    assert np.allclose(logp0.cpu().numpy(), lp0.numpy().ravel(), rtol=1e-12, atol=1e-12)
+    mean, m2 = adv.mean(), ((adv - adv.mean()) ** 2).sum()
+    stats = cu(np.array([n, mean, m2 if n > 1 else 1.0, 0.0]))
+    nn_ = max(n - 1, 1)
+    a_std = (torch.from_numpy(adv) - mean) / np.sqrt((m2 if n > 1 else 1.0) / nn_) if n > 1 else torch.from_numpy(adv - mean)
+    mu_t = torch.from_numpy(mu).requires_grad_(True)
+    ls_t = torch.from_numpy(ls).requires_grad_(True)
+    ind = torch.from_numpy(exps).nonzero().squeeze(1)
+    ratio = torch.exp(oppo.log_prob(mu_t[ind], ls_t, torch.from_numpy(ac)[ind]) - lp0[ind])
+    a = a_std[ind].view(-1, 1)
+    surr = -torch.min(ratio * a, torch.clamp(ratio, 0.8, 1.2) * a).mean()
+    surr.backward()
+    dmu = torch.zeros(n, adim, dtype=torch.float64, device='cuda')
+    dls = torch.zeros(adim, dtype=torch.float64, device='cuda')
+    loss = torch.zeros(1, dtype=torch.float64, device='cuda')
+    if n == 1:
+        stats = cu(np.array([2.0, mean, 1.0, 0.0]))        # (adv - mean) / sqrt(1 / 1): same standardisation as a_std
+    lib.ppo_loss_grad(cu(mu), cu(ac), cu(ls), cu(adv), stats, logp0, cu(exps), 0.2, 1.0 / len(ind), dmu, dls, loss)
+    assert abs(loss.item() - surr.item()) < 1e-11 * max(1, abs(surr.item()))
+    assert np.allclose(dmu.cpu().numpy(), mu_t.grad.numpy(), rtol=1e-9, atol=1e-13)
+    assert np.allclose(dls.cpu().numpy(), ls_t.grad.numpy(), rtol=1e-9, atol=1e-12)
+
+
 def test_value_loss_and_helpers():
     from egopose_b200 import lib
     rng = np.random.RandomState(2)
