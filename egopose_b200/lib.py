@@ -99,6 +99,11 @@ SYMBOLS = {
     'egp_build_input_f64': (_int, [_vp, _vp, _vp, _vp, _i64, _int, _vp, _vp]),
     'egp_sumsq_f64': (_int, [_vp, _i64, _vp, _vp]),
     'egp_adam_step_f64': (_int, [_vp, _vp, _vp, _vp, _i64, _d, _d, _d, _d, _i64, _d, _vp, _vp]),
+    'egp_oz_slice_rows_f64': (_int, [_vp, _i64, _int, _i64, _int, _vp, _int, _vp, _vp, _vp]),
+    'egp_oz_colmax_f64': (_int, [_vp, _i64, _int, _i64, _vp, _vp]),
+    'egp_oz_slice_cols_t_f64': (_int, [_vp, _i64, _int, _i64, _int, _vp, _vp, _i64, _vp, _vp]),
+    'egp_oz_gemm_work_bytes': (_i64, [_i64, _int, _i64]),
+    'egp_oz_gemm_f64': (_int, [_vp, _vp, _i64, _vp, _vp, _int, _i64, _int, _vp, _int, _vp, _i64, _vp, _i64, _vp]),
 }
 
 _lib = None
@@ -472,3 +477,82 @@ def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, max_norm=0.0, norm2=None)
     check(load().egp_adam_step_f64(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), lr, beta1, beta2, eps, step,
                                    float(max_norm or 0.0), ptr(norm2), stream_ptr()), 'egp_adam_step_f64')
     launches += 1
+
+
+# ---- float64 dense layers on the int8 tensor cores (csrc/ozaki.cu) ----------------------------------------------
+def _pad16(k):
+    return (int(k) + 15) // 16 * 16
+
+
+def oz_slice_rows(x, n_slices, colmax=None, out=None):
+    """x [M, K] float64 (row stride >= K) -> (int8 slices [S, M, Kp], int32 exponents [M]); scale constant along K.
+    ``colmax`` ([K] float64, zeroed by the caller) additionally receives the column abs-max of x."""
+    global launches
+    import torch
+    M, K = x.shape
+    if x.stride(1) != 1:
+        raise EgpError('oz_slice_rows: x must be row-major')
+    kp = _pad16(K)
+    if out is None:
+        out = (torch.empty((n_slices, M, kp), dtype=torch.int8, device=x.device),
+               torch.empty((M,), dtype=torch.int32, device=x.device))
+    sl, ex = out
+    check(load().egp_oz_slice_rows_f64(ptr(x), M, K, x.stride(0), n_slices, ptr(sl), kp, ptr(ex), ptr(colmax), stream_ptr()),
+          'egp_oz_slice_rows_f64')
+    launches += 1
+    return sl, ex
+
+
+def oz_colmax(x, colmax=None):
+    global launches
+    import torch
+    if colmax is None:
+        colmax = torch.zeros(x.shape[1], dtype=torch.float64, device=x.device)
+    check(load().egp_oz_colmax_f64(ptr(x), x.shape[0], x.shape[1], x.stride(0), ptr(colmax), stream_ptr()), 'egp_oz_colmax_f64')
+    launches += 1
+    return colmax
+
+
+def oz_slice_colsT(x, n_slices, colmax, out=None):
+    """x [N, F] float64 -> (int8 slices [S, F, Np] transposed, int32 exponents [F]); scale constant along the rows"""
+    global launches
+    import torch
+    N, F = x.shape
+    if x.stride(1) != 1:
+        raise EgpError('oz_slice_colsT: x must be row-major')
+    npad = _pad16(N)
+    if out is None:
+        out = (torch.empty((n_slices, F, npad), dtype=torch.int8, device=x.device),
+               torch.empty((F,), dtype=torch.int32, device=x.device))
+    sl, ex = out
+    check(load().egp_oz_slice_cols_t_f64(ptr(x), N, F, x.stride(0), n_slices, ptr(colmax), ptr(sl), npad, ptr(ex), stream_ptr()),
+          'egp_oz_slice_cols_t_f64')
+    launches += 2
+    return sl, ex
+
+
+_oz_work = {}
+
+
+def oz_gemm(a, ea, b, eb, bias=None, relu=False, out=None):
+    """C [M, N] = A B^T (+ bias, relu) from row-scaled slices a [S, M, Kp], b [S, N, Kp] and exponents ea [M], eb [N]"""
+    global launches
+    import torch
+    S, M, kp = a.shape
+    N = b.shape[1]
+    if b.shape[0] != S or b.shape[2] != kp:
+        raise EgpError('oz_gemm: slice shapes do not match: %s vs %s' % (tuple(a.shape), tuple(b.shape)))
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float64, device=a.device)
+    lib = load()
+    need = lib.egp_oz_gemm_work_bytes(M, N, kp)
+    work = None
+    if need:
+        work = _oz_work.get(a.device)
+        if work is None or work.numel() < need:
+            work = torch.empty(need, dtype=torch.uint8, device=a.device)
+            _oz_work[a.device] = work
+    check(lib.egp_oz_gemm_f64(ptr(a), ptr(ea), M, ptr(b), ptr(eb), N, kp, S, ptr(bias), int(bool(relu)), ptr(out), out.stride(0),
+                              ptr(work), need, stream_ptr()), 'egp_oz_gemm_f64')
+    launches += 2 if need else 1
+    return out

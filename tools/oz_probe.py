@@ -1,0 +1,158 @@
+"""Probe / bring-up of the Ozaki int8 tcgen05 GEMM (csrc/ozaki.cu) on a B200:
+slices reconstruct the input, the GEMM equals an exact integer matmul of the same slices bit for bit, error vs the
+float64 product, timing against cuBLAS DGEMM.   python tools/oz_probe.py [quick]"""
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from egopose_b200 import lib  # noqa: E402
+
+torch.manual_seed(0)
+dev = 'cuda'
+
+
+def recon(sl, ex, axis_scale_rows=True):
+    S = sl.shape[0]
+    v = torch.zeros(sl.shape[1:], dtype=torch.float64, device=sl.device)
+    for t in range(S):
+        v += sl[t].double() * 2.0 ** (1 - 7 * (t + 1))
+    return v * torch.ldexp(torch.ones_like(ex, dtype=torch.float64), ex)[:, None]
+
+
+def exact_ref(a, ea, b, eb, bias=None, relu=False):
+    """same arithmetic as the kernel: exact integer brackets (float64 holds them exactly), Horner, scales"""
+    S = a.shape[0]
+    A, B = a.double(), b.double()
+    acc = []
+    for d in range(S):
+        s = torch.zeros((a.shape[1], b.shape[1]), dtype=torch.float64, device=a.device)
+        for t in range(d + 1):
+            s += A[t] @ B[d - t].t()
+        acc.append(s)
+    h = acc[S - 1]
+    for d in range(S - 2, -1, -1):
+        h = h * 0.0078125 + acc[d]
+    h = h * torch.ldexp(torch.ones_like(ea, dtype=torch.float64), ea - 12)[:, None]
+    h = h * torch.ldexp(torch.ones_like(eb, dtype=torch.float64), eb)[None, :]
+    if bias is not None:
+        h = h + bias[None, :]
+    if relu:
+        h = torch.relu(h)
+    return h
+
+
+def check(M, N, K, S, bias=False, relu=False, scale_rows=True):
+    x = torch.randn(M, K, device=dev, dtype=torch.float64)
+    if scale_rows:
+        x *= torch.exp(3 * torch.randn(M, 1, device=dev, dtype=torch.float64))
+    w = torch.randn(N, K, device=dev, dtype=torch.float64) / K ** 0.5
+    a, ea = lib.oz_slice_rows(x, S)
+    b, eb = lib.oz_slice_rows(w, S)
+    torch.cuda.synchronize()
+    ra = recon(a[:, :, :K], ea)
+    amax = x.abs().max(1, keepdim=True).values
+    e_sl = ((ra - x).abs() / amax).max().item()
+    assert (a[:, :, K:] == 0).all(), 'padding not zero'
+    bv = torch.randn(N, device=dev, dtype=torch.float64) if bias else None
+    c = lib.oz_gemm(a, ea, b, eb, bias=bv, relu=relu)
+    torch.cuda.synchronize()
+    ref = exact_ref(a, ea, b, eb, bv, relu)
+    exact = torch.equal(c, ref)
+    true = x @ w.t()
+    if bias:
+        true = true + bv
+    if relu:
+        true = torch.relu(true)
+    bound = amax * w.abs().max(1).values[None, :] * K
+    e_rel = ((c - true).abs() / bound).max().item()
+    e_typ = ((c - true).abs().max() / true.abs().max()).item()
+    print('M %7d N %4d K %4d S %d bias %d relu %d | slice resid %.2e (<= %.2e) | bit-exact vs integer ref: %s | err/bound %.2e  err/max|C| %.2e'
+          % (M, N, K, S, bias, relu, e_sl, 2.0 ** (-7 * S), exact, e_rel, e_typ), flush=True)
+    if not exact:
+        d = (c - ref).abs()
+        bad = (d > 0).nonzero()
+        print('   mismatches %d of %d, first at %s: got %r want %r' % (bad.shape[0], c.numel(), bad[0].tolist(),
+                                                                       c[tuple(bad[0])].item(), ref[tuple(bad[0])].item()))
+        rows = torch.unique(bad[:, 0])[:20].tolist()
+        cols = torch.unique(bad[:, 1])[:20].tolist()
+        print('   bad rows (first 20)', rows, 'bad cols (first 20)', cols)
+    return exact
+
+
+def check_wgrad(Ns, F1, F2, S):
+    """dW [F1, F2] = dY^T X over Ns samples through the transposed column-scaled slices + split-K"""
+    dy = torch.randn(Ns, F1, device=dev, dtype=torch.float64) * torch.exp(torch.randn(Ns, 1, device=dev, dtype=torch.float64))
+    x = torch.relu(torch.randn(Ns, F2, device=dev, dtype=torch.float64))
+    a, ea = lib.oz_slice_colsT(dy, S, lib.oz_colmax(dy))
+    b, eb = lib.oz_slice_colsT(x, S, lib.oz_colmax(x))
+    torch.cuda.synchronize()
+    ra = recon(a[:, :, :Ns], ea)
+    e_sl = ((ra - dy.t()).abs() / dy.abs().max(0).values[:, None]).max().item()
+    c = lib.oz_gemm(a, ea, b, eb)
+    torch.cuda.synchronize()
+    true = dy.t() @ x
+    e_typ = ((c - true).abs().max() / true.abs().max()).item()
+    ok = True
+    if Ns <= 70000:
+        ref = exact_ref(a, ea, b, eb)
+        ok = torch.allclose(c, ref, rtol=1e-14, atol=0)        # split-K partial sums are added in float64
+    print('wgrad Ns %8d F1 %3d F2 %3d S %d | slice resid %.2e | matches integer ref: %s | err/max|C| %.2e' % (Ns, F1, F2, S, e_sl, ok, e_typ), flush=True)
+    return ok
+
+
+def bench(M, N, K, S, iters=10):
+    x = torch.randn(M, K, device=dev, dtype=torch.float64)
+    w = torch.randn(N, K, device=dev, dtype=torch.float64)
+    a, ea = lib.oz_slice_rows(x, S)
+    b, eb = lib.oz_slice_rows(w, S)
+    out = torch.empty(M, N, device=dev, dtype=torch.float64)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    for _ in range(3):
+        lib.oz_gemm(a, ea, b, eb, out=out)
+    ev[0].record()
+    for _ in range(iters):
+        lib.oz_gemm(a, ea, b, eb, out=out)
+    ev[1].record()
+    out2 = torch.empty(M, N, device=dev, dtype=torch.float64)
+    for _ in range(2):
+        torch.mm(x, w.t(), out=out2)
+    ev[2].record()
+    for _ in range(iters):
+        torch.mm(x, w.t(), out=out2)
+    ev[3].record()
+    torch.cuda.synchronize()
+    t_oz, t_bl = ev[0].elapsed_time(ev[1]) / iters, ev[2].elapsed_time(ev[3]) / iters
+    fl = 2.0 * M * N * K
+    sl = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    sl[0].record()
+    for _ in range(iters):
+        lib.oz_slice_rows(x, S, out=(a, ea))
+    sl[1].record()
+    torch.cuda.synchronize()
+    t_sl = sl[0].elapsed_time(sl[1]) / iters
+    print('bench M %8d N %4d K %4d S %d | ozaki gemm %.3f ms (%.1f TFLOP/s f64-equivalent) | cuBLAS DGEMM %.3f ms (%.1f TFLOP/s) | slicing A %.3f ms (%.0f GB/s)'
+          % (M, N, K, S, t_oz, fl / t_oz * 1e-9, t_bl, fl / t_bl * 1e-9, t_sl, M * K * (8 + S) / t_sl * 1e-6), flush=True)
+
+
+if __name__ == '__main__':
+    quick = 'quick' in sys.argv
+    ok = True
+    ok &= check(128, 64, 64, 4, scale_rows=False)
+    ok &= check(128, 64, 128, 4)
+    ok &= check(100, 52, 200, 5, bias=True)
+    ok &= check(1000, 300, 243, 6, bias=True, relu=True)
+    ok &= check(4096 + 17, 304, 300, 3)
+    ok &= check(513, 1, 300, 7, bias=True)
+    ok &= check(2000, 300, 640, 8)
+    ok &= check_wgrad(5000, 52, 300, 5)
+    ok &= check_wgrad(65536 + 100, 300, 243, 6)
+    print('ALL OK' if ok else 'FAILURES', flush=True)
+    if not quick and ok:
+        for S in (4, 5, 6):
+            bench(1228800, 300, 243, S)
+            bench(1228800, 300, 300, S)
+        ok &= check_wgrad(1228800, 300, 300, 6)
+        t0 = time.time()
