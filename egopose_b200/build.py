@@ -29,7 +29,8 @@ def needs_build():
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
-    cmd = [nvcc()] + NVCC_FLAGS + ['-o', LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    extra = os.environ.get('EGP_NVCC_EXTRA', '').split()
+    cmd = [nvcc()] + NVCC_FLAGS + extra + ['-o', LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     # the container's CC wrapper lacks a few runtime bits; pin the host compiler when present
     if os.path.exists('/usr/bin/g++'):
         cmd += ['-ccbin', '/usr/bin/g++']

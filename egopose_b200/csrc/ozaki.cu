@@ -5,182 +5,234 @@
 // (ego_pose/ego_mimic.py:31-32).  tcgen05 has no FP64 kind, so the product is evaluated with the Ozaki scheme on the
 // int8 tensor cores (B200 has them, 2x the bf16 rate):
 //
-//   row i of A:   a_ik = 2^ea_i * sum_{t=1..S} qa_t[i][k] 2^(1-7t),  qa_t in [-64, 64]  (int8 "slices", exact
-//   row j of B:   b_jk = 2^eb_j * sum_{u=1..S} qb_u[j][k] 2^(1-7u)    residual < 2^(-7S) relative to the row maximum)
+//   row i of A:   a_ik = 2^ea_i * sum_{t=1..S} qa_t[i][k] 2^(1-7t),  qa_t in [-64, 64]  (int8 "slices": the signed
+//   row j of B:   b_jk = 2^eb_j * sum_{u=1..S} qb_u[j][k] 2^(1-7u)    base-128 digits of round(a 2^(7S-1-e)))
 //   C_ij = sum_k a_ik b_jk = 2^(ea_i + eb_j - 12) * sum_{d=0..S-1} 2^(-7d) * [ sum_{t+u-2=d} sum_k qa_t qb_u ]
 //
 // Every bracket is an int8 x int8 -> int32 GEMM accumulated EXACTLY in Tensor Memory (one accumulator per d, all
 // slice pairs of equal weight share it); pairs with t+u > S+1 are below the slicing residual and dropped.  The
-// result differs from the float64 product by <= (S+2) 2^(-7S) |a_i|_max |b_j|_max K  (S = 6: 2e-12, S = 5: 2e-10) and
-// is independent of tile shapes and launch geometry (integer accumulation), so the kernel is tested bit-exactly
-// against an integer matmul of the same slices.
+// result differs from the float64 product by <= (S+2) 2^(-7S) |a_i|_max |b_j|_max K  (S = 6: 2e-12, S = 7: 1.6e-14,
+// the rounding level of a DGEMM itself) and is independent of tile shapes and launch geometry (integer
+// accumulation), so the kernel is tested bit-exactly against an integer matmul of the same slices.
 //
 // Kernels:
 //   oz_slice_rows_kernel   f64 [M][K] -> int8 [S][M][Kp] + per-row exponent (scale constant along K = columns)
 //   oz_slice_colsT_kernel  f64 [N][F] -> int8 [S][F][Np] + per-column exponent, transposed (for the weight-gradient
-//                          GEMMs whose contraction runs over the samples)
-//   oz_gemm_kernel         warp-specialised tcgen05 GEMM: TMA (3-D boxes {64 B, rows, S slices}, 64-byte swizzle)
-//                          -> mbarrier ring -> single-thread tcgen05.mma.kind::i8 into S TMEM accumulators ->
-//                          4 epilogue warps tcgen05.ld, Horner over d in float64, scale, bias, relu, store
-//   oz_splitk_reduce_kernel  sums the split-K partials of the weight-gradient GEMMs and applies the scales
+//                          GEMMs whose contraction runs over the samples); optional extra row of ones (bias gradient)
+//   oz_gemm_kernel         persistent warp-specialised tcgen05 GEMM, one CTA per SM looping over (split, m, n) tiles:
+//                          warp 0 TMA producer (3-D boxes {32 B, rows, S slices}, 32-byte swizzle) -> mbarrier ring that
+//                          runs ahead across tiles -> warp 1 single-thread tcgen05.mma.kind::i8 into S TMEM accumulators
+//                          -> 8 epilogue warps: tcgen05.ld, exact int64 Horner over d, one rounding to float64, scale,
+//                          bias, relu / relu-backward mask, store; TMEM is handed back to the MMA warp as soon as the
+//                          last accumulator chunk is in registers
 #include <cuda.h>
 #include <math.h>
 #include <string.h>
 
-#include "common.cuh"
+#include "ozaki.cuh"
 
 namespace egp {
 namespace oz {
 
-constexpr int BM = 128, BN = 64, BK = 64;       // CTA tile; BK in int8 elements = bytes (one 64 B swizzle row)
 constexpr int UMMA_K = 32;                      // K per tcgen05.mma for 8-bit operands
-constexpr int MAX_S = 8;
-constexpr int GEMM_THREADS = 192;               // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
-constexpr int SMEM_LIMIT = 227 * 1024;
+constexpr int EPI_WARPS = 8;
+constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;   // warp 0: TMA producer, warp 1: MMA issuer, warps 2-9: epilogue
+constexpr int SMEM_LIMIT = 227 * 1024 - 2048;   // dynamic shared memory: 227 KB minus the static barriers
+constexpr int MAX_STAGES = 12;
 
 // ---------------------------------------------------------------------------------------------------------------
 // slicing
-// exponent e with |x| / 2^e < 1 for |x| <= amax (amax / 2^e in [0.5, 1)); 0 for a zero row
+// exponent e with |x| / 2^e < 1 for |x| <= amax (amax / 2^e in [0.5, 1)); 0 for a zero / non-finite row; rows below
+// 2^-900 are flushed to zero (the scale 2^(7S-1-e) must stay finite)
 __device__ __forceinline__ int oz_exponent(double amax) {
     if (!(amax > 0.0) || !isfinite(amax)) return 0;
     int e;
     frexp(amax, &e);
-    return e;
+    return e < -900 ? -900 : e;
 }
 
-// q_1..q_S of x / 2^e, packed per slice by the caller
+__device__ __forceinline__ double pow2(int k) {            // 2^k, k in [-1022, 1023]
+    return __longlong_as_double((long long)(k + 1023) << 52);
+}
+
+// signed base-128 digits q_1..q_S (q in [-64, 64]) of X = round(x * scale), X = sum_t q_t 128^(S-t).  The digits come
+// off the low end in 21-bit signed groups so that the per-digit work is 32-bit integer arithmetic.
+__device__ __forceinline__ int oz_low_digit(int &x) {
+    const int d = ((x + 64) & 127) - 64;
+    x = (x - d) >> 7;
+    return d;
+}
 template <int S>
-__device__ __forceinline__ void oz_slices(double x, int e, int8_t *q) {
-    double r = ldexp(x, 6 - e);                 // |r| <= 64
-    if (!isfinite(r)) r = 0.0;
+__device__ __forceinline__ void oz_digits(double x, double scale, int *q) {
+    double r = x * scale;
+    if (!(fabs(r) <= 9.3e18)) r = 0.0;         // NaN / inf / out of int64 range
+    long long X = __double2ll_rn(r);
+    constexpr int NG = (S - 1) / 3;            // full 3-digit groups taken from the low end (leaves 1..3 digits)
 #pragma unroll
-    for (int t = 0; t < S; t++) {
-        double qi = rint(r);
-        q[t] = (int8_t)(int)qi;
-        r = (r - qi) * 128.0;
+    for (int gi = 0; gi < NG; gi++) {
+        const int t = S - 1 - 3 * gi;
+        int xl = (int)(((unsigned)X + (1u << 20)) & ((1u << 21) - 1u)) - (1 << 20);
+        X = (X - xl) >> 21;
+        q[t] = oz_low_digit(xl);
+        q[t - 1] = oz_low_digit(xl);
+        q[t - 2] = xl;
     }
+    int xh = (int)X;
+#pragma unroll
+    for (int t = S - 1 - 3 * NG; t > 0; t--) q[t] = oz_low_digit(xh);
+    q[0] = xh;
 }
 
-// One warp per row (grid-stride).  Lane l owns the 8-element chunks l, l + 32, ... of the row: 64 B loads, 8 B stores
-// per slice.  Optionally accumulates the column abs-max of the matrix into colmax (bit pattern max of |x| >= 0).
-template <int S>
+// One warp per row (grid-stride).  Lane l owns the 4-element groups l, l + 32, ... of the row: 32 B loads, 4 B stores
+// per slice (128 B per warp and slice).  Optionally accumulates the column abs-max of the matrix into colmax (bit
+// patterns of |x| >= 0 ordered like unsigned integers).
+template <int S, int P>
 __global__ void __launch_bounds__(256)
 oz_slice_rows_kernel(const double *__restrict__ x, long long M, int K, long long ldx, int8_t *__restrict__ out, int Kp,
                      int32_t *__restrict__ exps, unsigned long long *__restrict__ colmax) {
     const int lane = threadIdx.x & 31;
     const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     const long long nwarp = ((long long)gridDim.x * blockDim.x) >> 5;
-    const int nchunk = Kp / 8;
-    constexpr int MAXC = 3;                     // K <= 768
-    double cmax[MAXC][8];
+    const int ngroup = Kp / 4;
+    const bool vec = ((ldx & 1) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    double cmax[P][4];
 #pragma unroll
-    for (int c = 0; c < MAXC; c++)
+    for (int p = 0; p < P; p++)
 #pragma unroll
-        for (int j = 0; j < 8; j++) cmax[c][j] = 0.0;
+        for (int j = 0; j < 4; j++) cmax[p][j] = 0.0;
     for (long long row = warp; row < M; row += nwarp) {
-        double v[MAXC][8];
+        const double *xr = x + row * ldx;
+        double v[P][4];
         double amax = 0.0;
 #pragma unroll
-        for (int c = 0; c < MAXC; c++) {
-            const int ch = lane + 32 * c;
+        for (int p = 0; p < P; p++) {
+            const int k0 = (lane + 32 * p) * 4;
+            if (vec && k0 + 3 < K) {
+                const double2 a = *reinterpret_cast<const double2 *>(xr + k0);
+                const double2 b = *reinterpret_cast<const double2 *>(xr + k0 + 2);
+                v[p][0] = a.x; v[p][1] = a.y; v[p][2] = b.x; v[p][3] = b.y;
+            } else {
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const int k = ch * 8 + j;
-                v[c][j] = (ch < nchunk && k < K) ? x[row * ldx + k] : 0.0;
-                amax = fmax(amax, fabs(v[c][j]));
-                cmax[c][j] = fmax(cmax[c][j], fabs(v[c][j]));
+                for (int j = 0; j < 4; j++) v[p][j] = (k0 + j < K) ? xr[k0 + j] : 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const double a = fabs(v[p][j]);
+                amax = fmax(amax, a);
+                cmax[p][j] = fmax(cmax[p][j], a);
             }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
         const int e = oz_exponent(amax);
         if (lane == 0) exps[row] = e;
+        const double scale = pow2(7 * S - 1 - e);
 #pragma unroll
-        for (int c = 0; c < MAXC; c++) {
-            const int ch = lane + 32 * c;
-            if (ch >= nchunk) continue;
-            int8_t q[8][S];
+        for (int p = 0; p < P; p++) {
+            const int gi = lane + 32 * p;
+            if (gi >= ngroup) continue;
+            uint32_t pk[S];
 #pragma unroll
-            for (int j = 0; j < 8; j++) oz_slices<S>(v[c][j], e, q[j]);
+            for (int t = 0; t < S; t++) pk[t] = 0u;
 #pragma unroll
-            for (int t = 0; t < S; t++) {
-                unsigned long long pk = 0;
+            for (int j = 0; j < 4; j++) {
+                int q[S];
+                oz_digits<S>(v[p][j], scale, q);
 #pragma unroll
-                for (int j = 0; j < 8; j++) pk |= (unsigned long long)(uint8_t)q[j][t] << (8 * j);
-                *reinterpret_cast<unsigned long long *>(out + ((size_t)t * M + row) * Kp + ch * 8) = pk;
+                for (int t = 0; t < S; t++) pk[t] |= (uint32_t)(uint8_t)(int8_t)q[t] << (8 * j);
             }
+#pragma unroll
+            for (int t = 0; t < S; t++)
+                *reinterpret_cast<uint32_t *>(out + ((size_t)t * M + row) * Kp + gi * 4) = pk[t];
         }
     }
     if (colmax) {
 #pragma unroll
-        for (int c = 0; c < MAXC; c++) {
-            const int ch = lane + 32 * c;
+        for (int p = 0; p < P; p++)
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const int k = ch * 8 + j;
-                if (ch < nchunk && k < K && cmax[c][j] > 0.0) atomicMax(colmax + k, (unsigned long long)__double_as_longlong(cmax[c][j]));
+            for (int j = 0; j < 4; j++) {
+                const int k = (lane + 32 * p) * 4 + j;
+                if (k < K && cmax[p][j] > 0.0) atomicMax(colmax + k, (unsigned long long)__double_as_longlong(cmax[p][j]));
             }
-        }
     }
 }
 
-// column abs-max only (when the row slices are not needed): block = 256 threads, rows strided over blocks
+// column abs-max only (when the row slices are not needed): block = 256 threads = 8 row lanes x 32 features
 __global__ void __launch_bounds__(256)
 oz_colmax_kernel(const double *__restrict__ x, long long N, int F, long long ldx, long long rows_per_block,
                  unsigned long long *__restrict__ colmax) {
+    __shared__ double red[8][33];
     const long long r0 = blockIdx.x * rows_per_block;
     const long long r1 = r0 + rows_per_block < N ? r0 + rows_per_block : N;
-    for (int f = threadIdx.x; f < F; f += blockDim.x) {
+    const int fl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    for (int f0 = 0; f0 < F; f0 += 32) {
+        const int f = f0 + fl;
         double m = 0.0;
-        for (long long r = r0; r < r1; r++) m = fmax(m, fabs(x[r * ldx + f]));
-        if (m > 0.0) atomicMax(colmax + f, (unsigned long long)__double_as_longlong(m));
+        if (f < F)
+            for (long long r = r0 + rl; r < r1; r += 8) m = fmax(m, fabs(x[r * ldx + f]));
+        red[rl][fl] = m;
+        __syncthreads();
+        if (rl == 0 && f < F) {
+#pragma unroll
+            for (int i = 1; i < 8; i++) m = fmax(m, red[i][fl]);
+            if (m > 0.0) atomicMax(colmax + f, (unsigned long long)__double_as_longlong(m));
+        }
+        __syncthreads();
     }
 }
 
-__global__ void oz_col_exps_kernel(const unsigned long long *__restrict__ colmax, int F, int32_t *__restrict__ exps) {
+__global__ void oz_col_exps_kernel(const unsigned long long *__restrict__ colmax, int F, int ones_row, int32_t *__restrict__ exps) {
     int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f < F) exps[f] = oz_exponent(__longlong_as_double((long long)colmax[f]));
+    else if (f == F && ones_row) exps[f] = 1;
 }
 
-// Transposed, column-scaled slices: x [N][F] -> out [S][F][Np].  Block tile = 128 samples x 32 features: coalesced
-// f64 reads along the features, shared-memory transpose, 16 B stores along the samples.
+// Transposed, column-scaled slices: x [N][F] -> out [S][F (+1)][Np].  Block tile = 128 samples x 32 features: coalesced
+// f64 reads along the features, shared-memory transpose, 16 B stores along the samples.  With ones_row the virtual
+// feature F is 1.0 for every valid sample (its products are the column sums = bias gradients).
 template <int S>
 __global__ void __launch_bounds__(256)
 oz_slice_colsT_kernel(const double *__restrict__ x, long long N, int F, long long ldx, const int32_t *__restrict__ exps,
-                      int8_t *__restrict__ out, long long Np) {
+                      int8_t *__restrict__ out, long long Np, int ones_row) {
     __shared__ double tile[128][33];
     const long long n0 = (long long)blockIdx.x * 128;
     const int f0 = blockIdx.y * 32;
+    const int FT = F + (ones_row ? 1 : 0);
     {
         const int fl = threadIdx.x & 31, rl = threadIdx.x >> 5;       // 8 rows per pass
 #pragma unroll 4
         for (int r = rl; r < 128; r += 8) {
             const long long n = n0 + r;
             const int f = f0 + fl;
-            tile[r][fl] = (n < N && f < F) ? x[n * ldx + f] : 0.0;
+            double v = 0.0;
+            if (n < N) {
+                if (f < F) v = x[n * ldx + f];
+                else if (f == F && ones_row) v = 1.0;
+            }
+            tile[r][fl] = v;
         }
     }
     __syncthreads();
     // thread -> (feature fl, group of 16 samples g): 32 x 8 = 256 threads
     const int g = threadIdx.x & 7, fl = threadIdx.x >> 3;
     const int f = f0 + fl;
-    if (f >= F) return;
+    if (f >= FT) return;
     const long long nb = n0 + g * 16;
     if (nb >= Np) return;
-    const int e = exps[f];
+    const double scale = pow2(7 * S - 1 - exps[f]);
     uint32_t pk[S][4];
 #pragma unroll
     for (int t = 0; t < S; t++) pk[t][0] = pk[t][1] = pk[t][2] = pk[t][3] = 0u;
 #pragma unroll
     for (int j = 0; j < 16; j++) {
-        int8_t q[S];
-        oz_slices<S>(tile[g * 16 + j][fl], e, q);
+        int q[S];
+        oz_digits<S>(tile[g * 16 + j][fl], scale, q);
 #pragma unroll
-        for (int t = 0; t < S; t++) pk[t][j >> 2] |= (uint32_t)(uint8_t)q[t] << (8 * (j & 3));
+        for (int t = 0; t < S; t++) pk[t][j >> 2] |= (uint32_t)(uint8_t)(int8_t)q[t] << (8 * (j & 3));
     }
 #pragma unroll
     for (int t = 0; t < S; t++)
-        *reinterpret_cast<uint4 *>(out + ((size_t)t * F + f) * Np + nb) = make_uint4(pk[t][0], pk[t][1], pk[t][2], pk[t][3]);
+        *reinterpret_cast<uint4 *>(out + ((size_t)t * FT + f) * Np + nb) = make_uint4(pk[t][0], pk[t][1], pk[t][2], pk[t][3]);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -192,6 +244,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done;
@@ -220,54 +275,96 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_
         "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
         "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u) : "memory");
 }
-// K-major operand tile in the canonical 64-byte-swizzle layout (what TMA SWIZZLE_64B writes): rows of 64 B, 8-row
-// groups of 512 B (stride byte offset), descriptor version 1 (Blackwell), layout type 4 = SWIZZLE_64B
-__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t saddr) {
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
+// K-major operand tile in the canonical 32-byte-swizzle layout (what TMA SWIZZLE_32B writes): rows of 32 B, 8-row
+// groups of 256 B (stride byte offset), descriptor version 1 (Blackwell), layout type 6 = SWIZZLE_32B
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t saddr) {
+    if (BK == 64)   // 64-byte swizzle: 8-row groups of 512 B, layout type 4
+        return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46) | (6ull << 61);
 }
-// instruction descriptor: dense, S32 accumulate, signed int8 A and B, both K-major, N = 64, M = 128
-constexpr uint32_t IDESC_I8 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// instruction descriptor: dense, S32 accumulate, signed int8 A and B, both K-major, M = 128
+__host__ __device__ constexpr uint32_t idesc_i8(int bn) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
 
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, int *r) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(taddr) : "memory");
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, int *r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr) : "memory");
+}
+
+// sum_d acc_d 2^(-7d) for column j: two exact integer Horner groups (d < 4 | d >= 4) joined by one rounding in the fma.
+// SMALLK (contraction <= 448): neighbouring accumulators are first merged in int32 (|acc_d| <= (d + 1) K 2^12).
+template <int S, bool SMALLK>
+__device__ __forceinline__ double oz_horner(const int (&acc)[S][8], int j, double rs_hi, double rs_lo) {
+    constexpr int G = S < 4 ? S : 4, L = S - G;
+    long long hi, lo = 0;
+    if constexpr (SMALLK) {
+        const int c01 = acc[0][j] * 128 + acc[1][j];
+        if constexpr (G == 3) hi = (long long)c01 * 128 + acc[2][j];
+        else hi = (long long)c01 * 16384 + (acc[2][j] * 128 + acc[3][j]);
+        if constexpr (L == 1) lo = acc[G][j];
+        if constexpr (L >= 2) {
+            const int c45 = acc[G][j] * 128 + acc[G + 1][j];
+            if constexpr (L == 2) lo = c45;
+            if constexpr (L == 3) lo = (long long)c45 * 128 + acc[G + 2][j];
+            if constexpr (L == 4) lo = (long long)c45 * 16384 + (acc[G + 2][j] * 128 + acc[G + 3][j]);
+        }
+    } else {
+        hi = acc[0][j];
+#pragma unroll
+        for (int d = 1; d < G; d++) hi = hi * 128 + acc[d][j];
+        if constexpr (L > 0) {
+            lo = acc[G][j];
+#pragma unroll
+            for (int d = G + 1; d < S; d++) lo = lo * 128 + acc[d][j];
+        }
+    }
+    double h = (double)hi * rs_hi;              // rs_hi = 2^(row exponent - 7 (G - 1)), rs_lo = 2^(row exponent - 7 (S - 1))
+    if constexpr (L > 0) h = fma((double)lo, rs_lo, h);
+    return h;
 }
 
 struct GemmArgs {
     long long M;                // rows of A (output rows)
     int N;                      // rows of B (output columns)
-    int nkb;                    // number of 64-wide k blocks over the (padded) contraction
-    int kb_per_split;           // split-K: k blocks per grid.z slice (== nkb when gridDim.z == 1)
-    int S, stages, tmem_cols;
+    int nkb;                    // number of BK-wide k blocks over the (padded) contraction
+    int kb_per_split;           // split-K: k blocks per split (== nkb when splits == 1)
+    int mt, nt, splits;         // tile counts
+    int stages, tmem_cols;
     const int32_t *ea, *eb;     // row exponents of A / B
     const double *bias;         // [N] or null
     int relu;
-    double *C;                  // [M][ldc] final output, or split-K partials [gridDim.z][M][ldc] (raw, unscaled)
+    const double *mask;         // [M][ldm] or null
+    long long ldm;
+    double *C;                  // [M][ldc] final output, or split-K partials [splits][M][ldc] (raw, unscaled)
     long long ldc;
-    int partial;                // 1: write raw partial sums (scales applied by the reduce kernel)
+    int partial;                // 1: write raw partial sums (scales applied by the caller's reduce kernel)
+    int smallk;                 // contraction per split <= 448: int32 pre-merge of neighbouring accumulators is exact
+    int mask_vec;               // mask rows can be read with 16-byte loads
+    int tma_store;              // output through shared memory + TMA (needs even ldc and a 16-byte aligned base)
 };
 
-template <int S>
+template <int S, int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const GemmArgs g) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    constexpr uint32_t A_SLICE = BM * BK, B_SLICE = BN * BK;            // 8192, 4096 bytes
+    constexpr uint32_t A_SLICE = BM * BK, B_SLICE = BN * BK;
     constexpr uint32_t STAGE = S * (A_SLICE + B_SLICE);
-    __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], acc_bar;
+    constexpr uint32_t IDESC = idesc_i8(BN);
+    __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tfull_bar, tempty_bar;
     __shared__ uint32_t s_tmem;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_blk = blockIdx.x, m_blk = blockIdx.y;
-    const int kb0 = blockIdx.z * g.kb_per_split;
-    const int kb1 = kb0 + g.kb_per_split < g.nkb ? kb0 + g.kb_per_split : g.nkb;
     const int stages = g.stages;
+    const long long ntiles = (long long)g.mt * g.nt * g.splits;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
         for (int s = 0; s < stages; s++) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
-        mbar_init(smem_u32(&acc_bar), 1);
+        mbar_init(smem_u32(&tfull_bar), 1);
+        mbar_init(smem_u32(&tempty_bar), EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -280,104 +377,184 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t tmem = s_tmem;
 
     if (warp == 0) {
-        // ===== TMA producer: one 3-D box per operand and stage, all S slices at once
+        // ===== TMA producer: one 3-D box per operand and stage (all S slices at once); the ring runs ahead across tiles
         if (lane == 0) {
-            for (int kb = kb0, it = 0; kb < kb1; kb++, it++) {
-                const int s = it % stages;
-                if (it >= stages) mbar_wait(smem_u32(&empty_bar[s]), ((it / stages) - 1) & 1);
-                const uint32_t fb = smem_u32(&full_bar[s]);
-                mbar_expect_tx(fb, STAGE);
-                const uint32_t sa = smem_u32(smem + (size_t)s * STAGE);
-                tma_load_3d(sa, &tmA, fb, kb * BK, m_blk * BM, 0);
-                tma_load_3d(sa + S * A_SLICE, &tmB, fb, kb * BK, n_blk * BN, 0);
+            uint32_t it = 0;
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int n_blk = (int)(tile % g.nt);
+                const long long rest = tile / g.nt;
+                const int m_blk = (int)(rest % g.mt);
+                const int z = (int)(rest / g.mt);
+                const int kb0 = z * g.kb_per_split;
+                const int kb1 = kb0 + g.kb_per_split < g.nkb ? kb0 + g.kb_per_split : g.nkb;
+                for (int kb = kb0; kb < kb1; kb++, it++) {
+                    const uint32_t s = it % stages;
+                    if (it >= (uint32_t)stages) mbar_wait(smem_u32(&empty_bar[s]), ((it / stages) - 1) & 1);
+                    const uint32_t fb = smem_u32(&full_bar[s]);
+                    mbar_expect_tx(fb, STAGE);
+                    const uint32_t sa = smem_u32(smem + (size_t)s * STAGE);
+                    tma_load_3d(sa, &tmA, fb, kb * BK, m_blk * BM, 0);
+                    tma_load_3d(sa + S * A_SLICE, &tmB, fb, kb * BK, n_blk * BN, 0);
+                }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer: slice pair (t, u) accumulates into TMEM accumulator d = t + u (columns d * BN ...)
         if (lane == 0) {
-            for (int kb = kb0, it = 0; kb < kb1; kb++, it++) {
-                const int s = it % stages;
-                mbar_wait(smem_u32(&full_bar[s]), (it / stages) & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t sa = smem_u32(smem + (size_t)s * STAGE), sb = sa + S * A_SLICE;
+            uint32_t it = 0, tc = 0;
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tc++) {
+                const int z = (int)(tile / ((long long)g.nt * g.mt));
+                const int kb0 = z * g.kb_per_split;
+                const int kb1 = kb0 + g.kb_per_split < g.nkb ? kb0 + g.kb_per_split : g.nkb;
+                if (tc > 0) {                                         // epilogue has drained the previous tile
+                    mbar_wait(smem_u32(&tempty_bar), (tc - 1) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+                for (int kb = kb0; kb < kb1; kb++, it++) {
+                    const uint32_t s = it % stages;
+                    mbar_wait(smem_u32(&full_bar[s]), (it / stages) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t sa = smem_u32(smem + (size_t)s * STAGE), sb = sa + S * A_SLICE;
 #pragma unroll
-                for (int t = 0; t < S; t++) {
+                    for (int k2 = 0; k2 < BK / UMMA_K; k2++) {
 #pragma unroll
-                    for (int u = 0; u < S - t; u++) {
+                        for (int t = 0; t < S; t++) {
+                            const uint64_t ad = umma_desc_sw32(sa + t * A_SLICE + k2 * UMMA_K);
 #pragma unroll
-                        for (int k2 = 0; k2 < BK / UMMA_K; k2++) {
-                            const uint64_t ad = umma_desc_sw64(sa + t * A_SLICE + k2 * UMMA_K);
-                            const uint64_t bd = umma_desc_sw64(sb + u * B_SLICE + k2 * UMMA_K);
-                            umma_i8(tmem + (uint32_t)((t + u) * BN), ad, bd, IDESC_I8, (it > 0 || t > 0 || k2 > 0) ? 1u : 0u);
+                            for (int u = 0; u < S - t; u++) {
+                                const uint64_t bd = umma_desc_sw32(sb + u * B_SLICE + k2 * UMMA_K);
+                                umma_i8(tmem + (uint32_t)((t + u) * BN), ad, bd, IDESC, (kb > kb0 || t > 0 || k2 > 0) ? 1u : 0u);
+                            }
+                        }
+                    }
+                    umma_commit(smem_u32(&empty_bar[s]));            // frees the smem stage when these MMAs retire
+                }
+                umma_commit(smem_u32(&tfull_bar));                    // accumulators of this tile complete
+            }
+        }
+    } else {
+        // ===== epilogue: warp w reads TMEM lanes 32 (w % 4) ..; one output row per thread, half of the tile's columns.
+        // Drain: accumulators -> exact integer Horner -> one double per element in registers, then TMEM goes back to the
+        // MMA warp.  Post: scale / bias / relu / mask, 32 x 8 blocks through a 64-byte-swizzled shared buffer -> TMA store
+        // (full sectors, clipped at the matrix edge by the tensor map); overlaps the next tile's MMAs.
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        constexpr int HC = BN / 2;                                     // columns per warp
+        uint8_t *obuf = smem + (size_t)stages * STAGE + (size_t)(warp - 2) * 4096;
+        double *colc = reinterpret_cast<double *>(smem + (size_t)stages * STAGE + EPI_WARPS * 4096) + (warp - 2) * 2 * HC;
+        uint32_t tc = 0, nstore = 0;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tc++) {
+            const int n_blk = (int)(tile % g.nt);
+            const long long rest = tile / g.nt;
+            const int m_blk = (int)(rest % g.mt);
+            const int z = (int)(rest / g.mt);
+            const long long row = (long long)m_blk * BM + q * 32 + lane;
+            const bool row_ok = row < g.M;
+            const int col0 = n_blk * BN + half * HC;
+            // per-row scale folded into the Horner constants; per-column scale 2^eb and bias staged once per tile
+            int ea = (!g.partial && row_ok) ? g.ea[row] - 12 : 0;
+            ea = ea < -960 ? -960 : (ea > 960 ? 960 : ea);
+            const double rs_hi = pow2(ea - 7 * ((S < 4 ? S : 4) - 1)), rs_lo = pow2(ea - 7 * (S - 1));
+            double *crow = g.C + ((size_t)z * (g.partial ? g.M : 0) + (row_ok ? row : 0)) * g.ldc;
+            const double *mrow = (g.mask && row_ok) ? g.mask + row * g.ldm : nullptr;
+            if (!g.partial) {
+                __syncwarp();
+                for (int c = lane; c < HC; c += 32) {
+                    const int col = col0 + c;
+                    int eb = col < g.N ? g.eb[col] : 0;
+                    eb = eb < -1022 ? -1022 : (eb > 1023 ? 1023 : eb);
+                    colc[2 * c] = pow2(eb);
+                    colc[2 * c + 1] = (g.bias && col < g.N) ? g.bias[col] : 0.0;
+                }
+                __syncwarp();
+            }
+            mbar_wait(smem_u32(&tfull_bar), tc & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            double hv[HC];
+#pragma unroll
+            for (int c0 = 0; c0 < HC; c0 += 8) {
+                int acc[S][8];
+#pragma unroll
+                for (int d = 0; d < S; d++) tmem_ld8(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(d * BN + half * HC + c0), acc[d]);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (c0 + 8 >= HC) {                                    // last chunk is in registers: release TMEM
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&tempty_bar));
+                }
+                if (g.smallk) {
+#pragma unroll
+                    for (int jj = 0; jj < 8; jj++) hv[c0 + jj] = oz_horner<S, true>(acc, jj, rs_hi, rs_lo);
+                } else {
+#pragma unroll
+                    for (int jj = 0; jj < 8; jj++) hv[c0 + jj] = oz_horner<S, false>(acc, jj, rs_hi, rs_lo);
+                }
+            }
+#pragma unroll
+            for (int c0 = 0; c0 < HC; c0 += 8) {
+                const int colb = col0 + c0;
+                double v[8];
+#pragma unroll
+                for (int jj = 0; jj < 8; jj++) v[jj] = hv[c0 + jj];
+                if (!g.partial) {
+#pragma unroll
+                    for (int jj = 0; jj < 8; jj += 2) {
+                        const double4 cb = *reinterpret_cast<const double4 *>(colc + 2 * (c0 + jj));    // broadcast LDS.128 x2
+                        v[jj] = fma(v[jj], cb.x, cb.y);
+                        v[jj + 1] = fma(v[jj + 1], cb.z, cb.w);
+                    }
+                    if (g.relu) {
+#pragma unroll
+                        for (int jj = 0; jj < 8; jj++) {               // max(v, 0) on the integer pipe
+                            long long b = __double_as_longlong(v[jj]);
+                            b &= ~(b >> 63);
+                            v[jj] = __longlong_as_double(b);
+                        }
+                    }
+                    if (mrow) {
+                        if (g.mask_vec && colb + 8 <= g.N) {
+#pragma unroll
+                            for (int jj = 0; jj < 8; jj += 2) {
+                                const longlong2 mk = *reinterpret_cast<const longlong2 *>(mrow + colb + jj);
+                                if (!(mk.x > 0)) v[jj] = 0.0;           // bit pattern > 0  <=>  value > +0
+                                if (!(mk.y > 0)) v[jj + 1] = 0.0;
+                            }
+                        } else {
+#pragma unroll
+                            for (int jj = 0; jj < 8; jj++)
+                                if (colb + jj < g.N && !(mrow[colb + jj] > 0.0)) v[jj] = 0.0;
                         }
                     }
                 }
-                umma_commit(smem_u32(&empty_bar[s]));            // frees the smem stage when these MMAs retire
-            }
-            umma_commit(smem_u32(&acc_bar));                      // accumulators complete
-        }
-    } else {
-        // ===== epilogue: warp w reads TMEM lanes 32 (w % 4) ..; one output row per thread
-        const int q = warp & 3;
-        const long long row = (long long)m_blk * BM + q * 32 + lane;
-        mbar_wait(smem_u32(&acc_bar), 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const bool row_ok = row < g.M;
-        double sa_row = 1.0;
-        if (!g.partial && row_ok) sa_row = ldexp(1.0, g.ea[row] - 12);
-        double *crow = g.C + ((size_t)blockIdx.z * (g.partial ? g.M : 0) + (row_ok ? row : 0)) * g.ldc;
-        const bool empty = kb1 <= kb0;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 16) {
-            int acc[S][16];
-#pragma unroll
-            for (int d = 0; d < S; d++) tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(d * BN + c0), acc[d]);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-            for (int j = 0; j < 16; j += 2) {
-                double v[2];
-#pragma unroll
-                for (int jj = 0; jj < 2; jj++) {
-                    double h = (double)acc[S - 1][j + jj];
-#pragma unroll
-                    for (int d = S - 2; d >= 0; d--) h = h * 0.0078125 + (double)acc[d][j + jj];
-                    if (empty) h = 0.0;
-                    const int col = n_blk * BN + c0 + j + jj;
-                    if (!g.partial && col < g.N) {
-                        h = h * sa_row * ldexp(1.0, g.eb[col]);
-                        if (g.bias) h += g.bias[col];
-                        if (g.relu) h = fmax(h, 0.0);
+                if (g.tma_store) {
+                    uint8_t *buf = obuf + (nstore & 1) * 2048;
+                    if (nstore >= 2) {                                  // the store that last read this buffer has drained it
+                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        __syncwarp();
                     }
-                    v[jj] = h;
-                }
-                const int col = n_blk * BN + c0 + j;
-                if (row_ok) {
-                    if (col + 1 < g.N && ((g.ldc & 1) == 0)) *reinterpret_cast<double2 *>(crow + col) = make_double2(v[0], v[1]);
-                    else {
-                        if (col < g.N) crow[col] = v[0];
-                        if (col + 1 < g.N) crow[col + 1] = v[1];
+                    const uint32_t rb = smem_u32(buf) + lane * 64, sw = (lane >> 1) & 3;
+#pragma unroll
+                    for (int c = 0; c < 4; c++)
+                        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(rb + ((c ^ sw) << 4)), "d"(v[2 * c]), "d"(v[2 * c + 1]) : "memory");
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                                     ::"l"((uint64_t)&tmC), "r"(smem_u32(buf)), "r"(colb), "r"(m_blk * BM + q * 32), "r"(z) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
+                    nstore++;
+                } else if (row_ok) {
+#pragma unroll
+                    for (int jj = 0; jj < 8; jj++)
+                        if (colb + jj < g.N) crow[colb + jj] = v[jj];
                 }
             }
         }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    __syncwarp();
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)g.tmem_cols) : "memory");
-}
-
-// C[m][n] = 2^(ea_m + eb_n - 12) * sum_z partial[z][m][n]
-__global__ void __launch_bounds__(256)
-oz_splitk_reduce_kernel(const double *__restrict__ part, int splits, long long M, int N, long long ldp, const int32_t *__restrict__ ea,
-                        const int32_t *__restrict__ eb, double *__restrict__ C, long long ldc) {
-    const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (idx >= M * N) return;
-    const long long m = idx / N;
-    const int n = (int)(idx % N);
-    double s = 0.0;
-    for (int z = 0; z < splits; z++) s += part[((size_t)z * M + m) * ldp + n];
-    C[m * ldc + n] = s * ldexp(1.0, ea[m] - 12) * ldexp(1.0, eb[n]);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -396,7 +573,7 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// int8 slices [S][rows][Kp] -> 3-D tensor map, box {64 B, box_rows, S}, 64-byte swizzle, zero fill out of bounds
+// int8 slices [S][rows][Kp] -> 3-D tensor map, box {32 B, box_rows, S}, 32-byte swizzle, zero fill out of bounds
 static int make_map(CUtensorMap *tm, const int8_t *base, long long rows, long long Kp, int S, int box_rows) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return EGP_ECUDA; }
@@ -405,35 +582,173 @@ static int make_map(CUtensorMap *tm, const int8_t *base, long long rows, long lo
     cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, (cuuint32_t)S};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    BK == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with %d (rows %lld Kp %lld S %d)", (int)r, rows, Kp, S); return EGP_ECUDA; }
     return EGP_OK;
 }
 
-template <int S>
-static int launch_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, GemmArgs g, dim3 grid, cudaStream_t st) {
+// float64 output [splits][rows][ld] -> 3-D tensor map, box {8 columns, 32 rows, 1}, 64-byte swizzle (the epilogue's staging layout)
+static int make_map_out(CUtensorMap *tm, const double *base, long long rows, int cols, long long ld, int splits) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return EGP_ECUDA; }
+    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)splits};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 8, (cuuint64_t)ld * 8 * (cuuint64_t)rows};
+    cuuint32_t box[3] = {8, 32, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (output) failed with %d (rows %lld cols %d ld %lld)", (int)r, rows, cols, ld); return EGP_ECUDA; }
+    return EGP_OK;
+}
+
+constexpr int OUT_STAGE_BYTES = EPI_WARPS * 4096 + EPI_WARPS * 2 * 40 * 8;   // per epilogue warp: two 32 x 64 B staging buffers + (2^eb, bias) per column
+
+template <int S, int BN>
+static int launch_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC, GemmArgs g, cudaStream_t st) {
+    static_assert(S * BN <= 512, "accumulators exceed Tensor Memory");
     const size_t stage = (size_t)S * (BM * BK + BN * BK);
-    int stages = (int)((SMEM_LIMIT - 2048) / stage);
-    if (stages > 8) stages = 8;
-    if (stages > g.kb_per_split) stages = g.kb_per_split > 0 ? g.kb_per_split : 1;
-    if (stages < 1) { set_error("egp_oz_gemm_f64: S = %d does not fit shared memory", S); return EGP_ESIZE; }
+    int stages = (int)((SMEM_LIMIT - 1024 - OUT_STAGE_BYTES) / stage);
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    if (stages < 2) { set_error("egp_oz_gemm_f64: S = %d does not fit shared memory", S); return EGP_ESIZE; }
     g.stages = stages;
-    g.S = S;
     int cols = S * BN, p2 = 32;
     while (p2 < cols) p2 <<= 1;
     g.tmem_cols = p2;
-    const size_t smem = stage * stages + 1024;
-    EGP_CUDA(cudaFuncSetAttribute(oz_gemm_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    oz_gemm_kernel<S><<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, g);
+    const size_t smem = stage * stages + OUT_STAGE_BYTES + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        EGP_CUDA(cudaFuncSetAttribute(oz_gemm_kernel<S, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        attr_set = true;
+    }
+    const long long ntiles = (long long)g.mt * g.nt * g.splits;
+    const int grid = (int)(ntiles < num_sms() ? ntiles : num_sms());
+    oz_gemm_kernel<S, BN><<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, tmC, g);
     EGP_CHECK_LAUNCH("oz_gemm_kernel");
     return EGP_OK;
 }
 
-}  // namespace oz
-}  // namespace egp
+static inline int pick_bn(int n, int S) {
+    // N tile: 80 covers 300/301-wide layers in 4 tiles; 64 otherwise and whenever S * 80 exceeds the 512 TMEM columns
+    if (S > 6) return 64;
+    const int t64 = (n + 63) / 64, t80 = (n + 79) / 80;
+    return (t80 * 80 <= t64 * 64 || t80 < t64) ? 80 : 64;
+}
 
-using namespace egp;
-using namespace egp::oz;
+int choose_splits(long long m, int n, long long kp, int S) {
+    const int bn = pick_bn(n, S);
+    const long long tiles = ((m + BM - 1) / BM) * ((n + bn - 1) / bn);
+    const long long nkb = (kp + BK - 1) / BK;
+    const long long max_kb = (16384 / S * 32 / BK) & ~1LL;   // int32 accumulators: kb * BK * 4096 * S < 2^31
+    long long splits = (nkb + max_kb - 1) / max_kb;
+    if (tiles < num_sms() && nkb >= 64) {                     // few output tiles, long contraction: fill the SMs
+        long long want = num_sms() / tiles;
+        if (want > nkb / 8) want = nkb / 8;
+        if (want > splits) splits = want;
+    }
+    if (splits < 1) splits = 1;
+    return (int)splits;
+}
+
+long long gemm_work_bytes(long long m, int n, long long kp, int force_splits) {
+    return (long long)force_splits * m * (long long)((n + 1) & ~1) * 8;
+}
+
+int gemm(const int8_t *a, const int32_t *ea, long long m, const int8_t *b, const int32_t *eb, int n, long long kp, int S,
+         GemmOut &o, cudaStream_t st) {
+    if (!a || !b || m < 1 || n < 1 || kp < 16 || (kp & 15) || S < 3 || S > MAX_S) {
+        set_error("egp_oz_gemm_f64: bad argument (m %lld n %d kp %lld S %d)", m, n, kp, S);
+        return EGP_EINVAL;
+    }
+    const int bn = pick_bn(n, S);
+    CUtensorMap tmA, tmB;
+    int rc = make_map(&tmA, a, m, kp, S, BM);
+    if (rc) return rc;
+    rc = make_map(&tmB, b, n, kp, S, bn);
+    if (rc) return rc;
+    GemmArgs g;
+    memset(&g, 0, sizeof g);
+    g.M = m; g.N = n; g.nkb = (int)((kp + BK - 1) / BK);
+    g.ea = ea; g.eb = eb; g.bias = o.bias; g.relu = o.relu; g.mask = o.mask; g.ldm = o.ldm;
+    g.mt = (int)((m + BM - 1) / BM);
+    g.nt = (n + bn - 1) / bn;
+    int splits = o.force_splits > 0 ? o.force_splits : 1;
+    const long long max_kb = (16384 / S * 32 / BK) & ~1LL;
+    if (o.force_splits <= 0 && g.nkb > max_kb) {
+        set_error("egp_oz_gemm_f64: contraction of %lld needs split-K (int32 accumulators)", kp);
+        return EGP_ESIZE;
+    }
+    g.kb_per_split = (g.nkb + splits - 1) / splits;
+    splits = (g.nkb + g.kb_per_split - 1) / g.kb_per_split;            // no empty split
+    if (g.kb_per_split > max_kb) { set_error("egp_oz_gemm_f64: %d k blocks per split overflow int32 accumulators", g.kb_per_split); return EGP_ESIZE; }
+    g.splits = splits;
+    if (o.force_splits > 0) {
+        const long long ldp = (n + 1) & ~1;
+        if (!o.work || o.work_bytes < splits * m * ldp * 8) { set_error("egp_oz_gemm_f64: split-K workspace too small"); return EGP_EINVAL; }
+        if (o.bias || o.relu || o.mask) { set_error("egp_oz_gemm_f64: bias / relu / mask are not supported on the split-K path"); return EGP_EINVAL; }
+        g.partial = 1; g.C = o.work; g.ldc = ldp;
+        o.ldp = ldp;
+    } else {
+        if (!o.C || !ea || !eb || o.ldc < n) { set_error("egp_oz_gemm_f64: bad output argument"); return EGP_EINVAL; }
+        g.partial = 0; g.C = o.C; g.ldc = o.ldc;
+    }
+    o.splits_used = splits;
+    g.smallk = (long long)g.kb_per_split * BK <= 448;
+    g.mask_vec = g.mask && ((g.ldm & 1) == 0) && ((reinterpret_cast<uintptr_t>(g.mask) & 15) == 0);
+    g.tma_store = ((g.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
+    CUtensorMap tmC;
+    memset(&tmC, 0, sizeof tmC);
+    if (g.tma_store) {
+        rc = make_map_out(&tmC, g.C, m, n, g.ldc, g.partial ? splits : 1);
+        if (rc) return rc;
+    }
+#define OZ_LAUNCH(S_, BN_) rc = launch_gemm<S_, BN_>(tmA, tmB, tmC, g, st)
+    if (bn == 80) {
+        switch (S) {
+            case 3: OZ_LAUNCH(3, 80); break;
+            case 4: OZ_LAUNCH(4, 80); break;
+            case 5: OZ_LAUNCH(5, 80); break;
+            default: OZ_LAUNCH(6, 80); break;
+        }
+    } else {
+        switch (S) {
+            case 3: OZ_LAUNCH(3, 64); break;
+            case 4: OZ_LAUNCH(4, 64); break;
+            case 5: OZ_LAUNCH(5, 64); break;
+            case 6: OZ_LAUNCH(6, 64); break;
+            case 7: OZ_LAUNCH(7, 64); break;
+            default: OZ_LAUNCH(8, 64); break;
+        }
+    }
+#undef OZ_LAUNCH
+    return rc;
+}
+
+// C[m][n] = 2^(ea_m + eb_n - 12) * sum_z partial[z][m][n]
+__global__ void __launch_bounds__(256)
+oz_splitk_reduce_kernel(const double *__restrict__ part, int splits, long long M, int N, long long ldp, const int32_t *__restrict__ ea,
+                        const int32_t *__restrict__ eb, double *__restrict__ C, long long ldc) {
+    const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (idx >= M * N) return;
+    const long long m = idx / N;
+    const int n = (int)(idx % N);
+    double s = 0.0;
+    for (int z = 0; z < splits; z++) s += part[((size_t)z * M + m) * ldp + n];
+    C[m * ldc + n] = s * ldexp(1.0, ea[m] - 12) * ldexp(1.0, eb[n]);
+}
+
+template <int S>
+static int launch_slice_rows(const double *x, long long m, int k, long long ldx, int8_t *out, int kp, int32_t *exps,
+                             unsigned long long *colmax, cudaStream_t st) {
+    long long warps = m < (long long)num_sms() * 64 ? m : (long long)num_sms() * 64;
+    int blocks = (int)((warps * 32 + 255) / 256);
+    const int P = (kp + 127) / 128;
+    if (P <= 1) oz_slice_rows_kernel<S, 1><<<blocks, 256, 0, st>>>(x, m, k, ldx, out, kp, exps, colmax);
+    else if (P == 2) oz_slice_rows_kernel<S, 2><<<blocks, 256, 0, st>>>(x, m, k, ldx, out, kp, exps, colmax);
+    else if (P == 3) oz_slice_rows_kernel<S, 3><<<blocks, 256, 0, st>>>(x, m, k, ldx, out, kp, exps, colmax);
+    else oz_slice_rows_kernel<S, 6><<<blocks, 256, 0, st>>>(x, m, k, ldx, out, kp, exps, colmax);
+    EGP_CHECK_LAUNCH("oz_slice_rows_kernel");
+    return EGP_OK;
+}
 
 #define OZ_DISPATCH_S(S, CALL)                       \
     switch (S) {                                     \
@@ -446,102 +761,88 @@ using namespace egp::oz;
         default: set_error("Ozaki slice count %d outside [3, 8]", S); return EGP_EINVAL; \
     }
 
-extern "C" {
-
-int egp_oz_slice_rows_f64(const double *d_x, int64_t m, int k, int64_t ldx, int n_slices, int8_t *d_out, int kp,
-                          int32_t *d_exps, double *d_colmax, void *stream) {
-    if (!d_x || !d_out || !d_exps || m < 1 || k < 1 || ldx < k || kp < k || (kp & 15) || kp > 768) {
+int slice_rows(const double *x, long long m, int k, long long ldx, int S, int8_t *out, int kp, int32_t *exps,
+               unsigned long long *colmax, cudaStream_t st) {
+    if (!x || !out || !exps || m < 1 || k < 1 || ldx < k || kp < k || (kp & 15) || kp > 768) {
         set_error("egp_oz_slice_rows_f64: bad argument (k %d kp %d must satisfy k <= kp <= 768, kp %% 16 == 0)", k, kp);
         return EGP_EINVAL;
     }
-    cudaStream_t st = (cudaStream_t)stream;
-    long long warps = m < (long long)num_sms() * 64 ? m : (long long)num_sms() * 64;
-    int blocks = (int)((warps * 32 + 255) / 256);
-    OZ_DISPATCH_S(n_slices, (oz_slice_rows_kernel<S_><<<blocks, 256, 0, st>>>(d_x, m, k, ldx, d_out, kp, d_exps, (unsigned long long *)d_colmax)));
-    EGP_CHECK_LAUNCH("oz_slice_rows_kernel");
-    return EGP_OK;
+    int rc = EGP_OK;
+    OZ_DISPATCH_S(S, rc = launch_slice_rows<S_>(x, m, k, ldx, out, kp, exps, colmax, st));
+    return rc;
 }
 
-int egp_oz_colmax_f64(const double *d_x, int64_t n, int f, int64_t ldx, double *d_colmax, void *stream) {
-    if (!d_x || !d_colmax || n < 1 || f < 1 || ldx < f) { set_error("egp_oz_colmax_f64: bad argument"); return EGP_EINVAL; }
-    int blocks = num_sms() * 8;
+int col_absmax(const double *x, long long n, int f, long long ldx, unsigned long long *colmax, cudaStream_t st) {
+    if (!x || !colmax || n < 1 || f < 1 || ldx < f) { set_error("egp_oz_colmax_f64: bad argument"); return EGP_EINVAL; }
+    int blocks = num_sms() * 4;
     long long rpb = (n + blocks - 1) / blocks;
-    if (rpb < 16) rpb = 16;
+    if (rpb < 32) rpb = 32;
     blocks = (int)((n + rpb - 1) / rpb);
-    oz_colmax_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_x, n, f, ldx, rpb, (unsigned long long *)d_colmax);
+    oz_colmax_kernel<<<blocks, 256, 0, st>>>(x, n, f, ldx, rpb, colmax);
     EGP_CHECK_LAUNCH("oz_colmax_kernel");
     return EGP_OK;
 }
 
-int egp_oz_slice_cols_t_f64(const double *d_x, int64_t n, int f, int64_t ldx, int n_slices, const double *d_colmax,
-                           int8_t *d_out, int64_t np, int32_t *d_exps, void *stream) {
-    if (!d_x || !d_out || !d_exps || !d_colmax || n < 1 || f < 1 || ldx < f || np < n || (np & 15)) {
-        set_error("egp_oz_slice_cols_t_f64: bad argument (np %lld must be >= n and a multiple of 16)", (long long)np);
+int slice_colsT(const double *x, long long n, int f, long long ldx, int S, const unsigned long long *colmax, int8_t *out,
+                long long np, int32_t *exps, int ones_row, cudaStream_t st) {
+    if (!x || !out || !exps || !colmax || n < 1 || f < 1 || ldx < f || np < n || (np & 15)) {
+        set_error("egp_oz_slice_cols_t_f64: bad argument (np %lld must be >= n and a multiple of 16)", np);
         return EGP_EINVAL;
     }
-    cudaStream_t st = (cudaStream_t)stream;
-    oz_col_exps_kernel<<<(f + 127) / 128, 128, 0, st>>>((const unsigned long long *)d_colmax, f, d_exps);
-    dim3 grid((unsigned)((np + 127) / 128), (unsigned)((f + 31) / 32));
-    OZ_DISPATCH_S(n_slices, (oz_slice_colsT_kernel<S_><<<grid, 256, 0, st>>>(d_x, n, f, ldx, d_exps, d_out, np)));
+    const int ft = f + (ones_row ? 1 : 0);
+    oz_col_exps_kernel<<<(ft + 127) / 128, 128, 0, st>>>(colmax, f, ones_row, exps);
+    dim3 grid((unsigned)((np + 127) / 128), (unsigned)((ft + 31) / 32));
+    OZ_DISPATCH_S(S, (oz_slice_colsT_kernel<S_><<<grid, 256, 0, st>>>(x, n, f, ldx, exps, out, np, ones_row)));
     EGP_CHECK_LAUNCH("oz_slice_colsT_kernel");
     return EGP_OK;
 }
 
-int64_t egp_oz_gemm_work_bytes(int64_t m, int n, int64_t kp) {
-    // split-K partials are only used when the output has few tiles and the contraction is long
-    long long tiles = ((m + BM - 1) / BM) * ((n + BN - 1) / BN);
-    long long nkb = (kp + BK - 1) / BK;
-    if (tiles >= 2LL * 148 || nkb < 64) return 0;
-    long long splits = (nkb + 511) / 512;                 // <= 32768 samples per split: int32 accumulation cannot overflow
-    long long want = (4LL * 148 + tiles - 1) / tiles;
-    if (want > splits) splits = want;
-    if (splits > nkb) splits = nkb;
-    return (int64_t)(splits * m * (long long)((n + 1) & ~1) * 8);
+}  // namespace oz
+}  // namespace egp
+
+using namespace egp;
+using namespace egp::oz;
+
+extern "C" {
+
+int egp_oz_slice_rows_f64(const double *d_x, int64_t m, int k, int64_t ldx, int n_slices, int8_t *d_out, int kp,
+                          int32_t *d_exps, double *d_colmax, void *stream) {
+    return slice_rows(d_x, m, k, ldx, n_slices, d_out, kp, d_exps, (unsigned long long *)d_colmax, (cudaStream_t)stream);
+}
+
+int egp_oz_colmax_f64(const double *d_x, int64_t n, int f, int64_t ldx, double *d_colmax, void *stream) {
+    return col_absmax(d_x, n, f, ldx, (unsigned long long *)d_colmax, (cudaStream_t)stream);
+}
+
+int egp_oz_slice_cols_t_f64(const double *d_x, int64_t n, int f, int64_t ldx, int n_slices, const double *d_colmax,
+                           int8_t *d_out, int64_t np, int32_t *d_exps, int ones_row, void *stream) {
+    return slice_colsT(d_x, n, f, ldx, n_slices, (const unsigned long long *)d_colmax, d_out, np, d_exps, ones_row, (cudaStream_t)stream);
+}
+
+int64_t egp_oz_gemm_work_bytes(int64_t m, int n, int64_t kp, int n_slices) {
+    const int splits = choose_splits(m, n, kp, n_slices);
+    return splits > 1 ? gemm_work_bytes(m, n, kp, splits) : 0;
 }
 
 int egp_oz_gemm_f64(const int8_t *d_a, const int32_t *d_ea, int64_t m, const int8_t *d_b, const int32_t *d_eb, int n, int64_t kp,
-                    int n_slices, const double *d_bias, int relu, double *d_c, int64_t ldc, void *d_work, int64_t work_bytes,
-                    void *stream) {
-    if (!d_a || !d_b || !d_ea || !d_eb || !d_c || m < 1 || n < 1 || kp < 16 || (kp & 15) || ldc < n) {
+                    int n_slices, const double *d_bias, int relu, const double *d_mask, int64_t ldm, double *d_c, int64_t ldc,
+                    void *d_work, int64_t work_bytes, void *stream) {
+    if (!d_a || !d_b || !d_ea || !d_eb || !d_c || m < 1 || n < 1 || ldc < n) {
         set_error("egp_oz_gemm_f64: bad argument (m %lld n %d kp %lld ldc %lld)", (long long)m, n, (long long)kp, (long long)ldc);
         return EGP_EINVAL;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    CUtensorMap tmA, tmB;
-    int rc = make_map(&tmA, d_a, m, kp, n_slices, BM);
-    if (rc) return rc;
-    rc = make_map(&tmB, d_b, n, kp, n_slices, BN);
-    if (rc) return rc;
-    GemmArgs g;
-    memset(&g, 0, sizeof g);
-    g.M = m; g.N = n; g.nkb = (int)((kp + BK - 1) / BK);
-    g.ea = d_ea; g.eb = d_eb; g.bias = d_bias; g.relu = relu;
-    const long long mt = (m + BM - 1) / BM, nt = (n + BN - 1) / BN;
-    const int64_t need = egp_oz_gemm_work_bytes(m, n, kp);
-    int splits = 1;
-    long long ldp = (n + 1) & ~1;
-    if (need > 0) {
-        if (!d_work || work_bytes < need) { set_error("egp_oz_gemm_f64: split-K workspace too small (%lld < %lld bytes)", (long long)work_bytes, (long long)need); return EGP_EINVAL; }
-        splits = (int)(need / (m * ldp * 8));
-    } else if ((long long)g.nkb * BK * 4096LL * n_slices >= (1LL << 31)) {
-        set_error("egp_oz_gemm_f64: contraction of %lld needs split-K (int32 accumulators)", (long long)kp);
-        return EGP_ESIZE;
-    }
-    g.kb_per_split = (g.nkb + splits - 1) / splits;
-    splits = (g.nkb + g.kb_per_split - 1) / g.kb_per_split;
-    if (mt > 65535 || splits > 65535) {
-        // grid.y limit: rows beyond 65535 * 128 = 8.4 M per call are not needed by the configurations in scope
-        set_error("egp_oz_gemm_f64: too many row tiles (%lld) for one launch", mt);
-        return EGP_ESIZE;
-    }
-    if (splits > 1) { g.partial = 1; g.C = (double *)d_work; g.ldc = ldp; g.bias = nullptr; g.relu = 0; }
-    else { g.partial = 0; g.C = d_c; g.ldc = ldc; }
-    dim3 grid((unsigned)nt, (unsigned)mt, (unsigned)splits);
-    OZ_DISPATCH_S(n_slices, { rc = launch_gemm<S_>(tmA, tmB, g, grid, st); if (rc) return rc; });
+    GemmOut o;
+    o.C = d_c; o.ldc = ldc; o.bias = d_bias; o.relu = relu; o.mask = d_mask; o.ldm = ldm;
+    const int splits = choose_splits(m, n, kp, n_slices);
     if (splits > 1) {
-        if (d_bias || relu) { set_error("egp_oz_gemm_f64: bias / relu are not supported on the split-K path"); return EGP_EINVAL; }
+        o.force_splits = splits; o.work = (double *)d_work; o.work_bytes = work_bytes;
+    }
+    int rc = gemm(d_a, d_ea, m, d_b, d_eb, n, kp, n_slices, o, st);
+    if (rc) return rc;
+    if (splits > 1) {
         long long tot = m * (long long)n;
-        oz_splitk_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>((const double *)d_work, splits, m, n, ldp, d_ea, d_eb, d_c, ldc);
+        oz_splitk_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(o.work, o.splits_used, m, n, o.ldp, d_ea, d_eb, d_c, ldc);
         EGP_CHECK_LAUNCH("oz_splitk_reduce_kernel");
     }
     return EGP_OK;

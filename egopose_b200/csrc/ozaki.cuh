@@ -1,0 +1,46 @@
+// Internal interface of the int8-tensor-core float64 GEMM (ozaki.cu), shared with the chunked MLP driver (oz_mlp.cu).
+#pragma once
+#include "common.cuh"
+
+namespace egp {
+namespace oz {
+
+constexpr int BM = 128;             // output rows per tile (tcgen05 M)
+#ifndef OZ_BK
+#define OZ_BK 32
+#endif
+constexpr int BK = OZ_BK;           // contraction bytes per stage row (32: one tcgen05.mma.kind::i8 K step, 32-byte swizzle; 64: two, 64-byte swizzle)
+constexpr int MAX_S = 8;
+
+inline long long round_up(long long a, long long b) { return (a + b - 1) / b * b; }
+
+// f64 [m][k] (ld ldx) -> int8 [S][m][kp] + exps[m]; optional column abs-max (bit patterns, atomicMax) of x
+int slice_rows(const double *x, long long m, int k, long long ldx, int S, int8_t *out, int kp, int32_t *exps,
+               unsigned long long *colmax, cudaStream_t st);
+int col_absmax(const double *x, long long n, int f, long long ldx, unsigned long long *colmax, cudaStream_t st);
+// f64 [n][f] -> int8 [S][f (+1 row of ones)][np], exps[f (+1)] from colmax
+int slice_colsT(const double *x, long long n, int f, long long ldx, int S, const unsigned long long *colmax, int8_t *out,
+                long long np, int32_t *exps, int ones_row, cudaStream_t st);
+
+struct GemmOut {
+    double *C = nullptr;            // [m][ldc]
+    long long ldc = 0;
+    const double *bias = nullptr;   // [n] added before relu
+    int relu = 0;
+    const double *mask = nullptr;   // [m][ldm]: C = mask > 0 ? C : 0 (relu backward)
+    long long ldm = 0;
+    // split-K (weight gradients): raw partial sums [splits][m][ldp] go to work; the caller reduces them
+    double *work = nullptr;
+    long long work_bytes = 0;
+    int force_splits = 0;           // > 0: use exactly this many splits (and write partials even when 1)
+    int splits_used = 0;            // out
+    long long ldp = 0;              // out
+};
+long long gemm_work_bytes(long long m, int n, long long kp, int force_splits);
+int choose_splits(long long m, int n, long long kp, int S);
+// C = A B^T from slices A [S][m][kp], B [S][n][kp]
+int gemm(const int8_t *a, const int32_t *ea, long long m, const int8_t *b, const int32_t *eb, int n, long long kp, int S,
+         GemmOut &o, cudaStream_t st);
+
+}  // namespace oz
+}  // namespace egp

@@ -101,9 +101,9 @@ SYMBOLS = {
     'egp_adam_step_f64': (_int, [_vp, _vp, _vp, _vp, _i64, _d, _d, _d, _d, _i64, _d, _vp, _vp]),
     'egp_oz_slice_rows_f64': (_int, [_vp, _i64, _int, _i64, _int, _vp, _int, _vp, _vp, _vp]),
     'egp_oz_colmax_f64': (_int, [_vp, _i64, _int, _i64, _vp, _vp]),
-    'egp_oz_slice_cols_t_f64': (_int, [_vp, _i64, _int, _i64, _int, _vp, _vp, _i64, _vp, _vp]),
-    'egp_oz_gemm_work_bytes': (_i64, [_i64, _int, _i64]),
-    'egp_oz_gemm_f64': (_int, [_vp, _vp, _i64, _vp, _vp, _int, _i64, _int, _vp, _int, _vp, _i64, _vp, _i64, _vp]),
+    'egp_oz_slice_cols_t_f64': (_int, [_vp, _i64, _int, _i64, _int, _vp, _vp, _i64, _vp, _int, _vp]),
+    'egp_oz_gemm_work_bytes': (_i64, [_i64, _int, _i64, _int]),
+    'egp_oz_gemm_f64': (_int, [_vp, _vp, _i64, _vp, _vp, _int, _i64, _int, _vp, _int, _vp, _i64, _vp, _i64, _vp, _i64, _vp]),
 }
 
 _lib = None
@@ -513,20 +513,22 @@ def oz_colmax(x, colmax=None):
     return colmax
 
 
-def oz_slice_colsT(x, n_slices, colmax, out=None):
-    """x [N, F] float64 -> (int8 slices [S, F, Np] transposed, int32 exponents [F]); scale constant along the rows"""
+def oz_slice_colsT(x, n_slices, colmax, out=None, ones_row=False):
+    """x [N, F] float64 -> (int8 slices [S, F, Np] transposed, int32 exponents [F]); scale constant along the rows.
+    ``ones_row`` appends the virtual feature F = 1.0 for every sample (bias gradient through the same GEMM)."""
     global launches
     import torch
     N, F = x.shape
     if x.stride(1) != 1:
         raise EgpError('oz_slice_colsT: x must be row-major')
     npad = _pad16(N)
+    ft = F + (1 if ones_row else 0)
     if out is None:
-        out = (torch.empty((n_slices, F, npad), dtype=torch.int8, device=x.device),
-               torch.empty((F,), dtype=torch.int32, device=x.device))
+        out = (torch.empty((n_slices, ft, npad), dtype=torch.int8, device=x.device),
+               torch.empty((ft,), dtype=torch.int32, device=x.device))
     sl, ex = out
-    check(load().egp_oz_slice_cols_t_f64(ptr(x), N, F, x.stride(0), n_slices, ptr(colmax), ptr(sl), npad, ptr(ex), stream_ptr()),
-          'egp_oz_slice_cols_t_f64')
+    check(load().egp_oz_slice_cols_t_f64(ptr(x), N, F, x.stride(0), n_slices, ptr(colmax), ptr(sl), npad, ptr(ex),
+                                         int(bool(ones_row)), stream_ptr()), 'egp_oz_slice_cols_t_f64')
     launches += 2
     return sl, ex
 
@@ -534,8 +536,9 @@ def oz_slice_colsT(x, n_slices, colmax, out=None):
 _oz_work = {}
 
 
-def oz_gemm(a, ea, b, eb, bias=None, relu=False, out=None):
-    """C [M, N] = A B^T (+ bias, relu) from row-scaled slices a [S, M, Kp], b [S, N, Kp] and exponents ea [M], eb [N]"""
+def oz_gemm(a, ea, b, eb, bias=None, relu=False, out=None, mask=None):
+    """C [M, N] = A B^T (+ bias, relu; * (mask > 0)) from row-scaled slices a [S, M, Kp], b [S, N, Kp] and exponents
+    ea [M], eb [N]"""
     global launches
     import torch
     S, M, kp = a.shape
@@ -545,14 +548,15 @@ def oz_gemm(a, ea, b, eb, bias=None, relu=False, out=None):
     if out is None:
         out = torch.empty((M, N), dtype=torch.float64, device=a.device)
     lib = load()
-    need = lib.egp_oz_gemm_work_bytes(M, N, kp)
+    need = lib.egp_oz_gemm_work_bytes(M, N, kp, S)
     work = None
     if need:
         work = _oz_work.get(a.device)
         if work is None or work.numel() < need:
             work = torch.empty(need, dtype=torch.uint8, device=a.device)
             _oz_work[a.device] = work
-    check(lib.egp_oz_gemm_f64(ptr(a), ptr(ea), M, ptr(b), ptr(eb), N, kp, S, ptr(bias), int(bool(relu)), ptr(out), out.stride(0),
-                              ptr(work), need, stream_ptr()), 'egp_oz_gemm_f64')
+    check(lib.egp_oz_gemm_f64(ptr(a), ptr(ea), M, ptr(b), ptr(eb), N, kp, S, ptr(bias), int(bool(relu)), ptr(mask),
+                              mask.stride(0) if mask is not None else 0, ptr(out), out.stride(0), ptr(work), need, stream_ptr()),
+          'egp_oz_gemm_f64')
     launches += 2 if need else 1
     return out

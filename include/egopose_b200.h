@@ -233,22 +233,25 @@ int egp_adam_step_f64(double *d_p, const double *d_g, double *d_m, double *d_v, 
 /* --- float64 dense layers on the int8 tensor cores (Ozaki scheme, egopose_b200/csrc/ozaki.cu) --------------
  * Replace the cuBLAS DGEMMs behind models/mlp.py:22-25 / core/policy_gaussian.py:19-24 / core/critic.py:15-18 forward
  * and backward in agents/agent_pg.py:19-26 and agents/agent_ppo.py:44-51.
- * Slices: x = 2^e * sum_{t=1..S} q_t 2^(1-7t), q_t int8 in [-64, 64], e constant along the contraction. */
+ * Slices: x = 2^e * sum_{t=1..S} q_t 2^(1-7t), q_t int8 in [-64, 64] (signed base-128 digits of round(x 2^(7S-1-e))),
+ * e constant along the contraction. */
 /* d_x [m][k] (leading dimension ldx) -> d_out [S][m][kp] (kp >= k, multiple of 16, zero padded), d_exps [m];
  * d_colmax (optional, [k] doubles zeroed by the caller) receives the column abs-max of x (for the colsT slicing) */
 int egp_oz_slice_rows_f64(const double *d_x, int64_t m, int k, int64_t ldx, int n_slices, int8_t *d_out, int kp,
                           int32_t *d_exps, double *d_colmax, void *stream);
 /* column abs-max only: d_colmax [f] (zeroed by the caller) */
 int egp_oz_colmax_f64(const double *d_x, int64_t n, int f, int64_t ldx, double *d_colmax, void *stream);
-/* d_x [n][f] -> transposed column-scaled slices d_out [S][f][np] (np >= n, multiple of 16), d_exps [f] from d_colmax [f] */
+/* d_x [n][f] -> transposed column-scaled slices d_out [S][f + ones_row][np] (np >= n, multiple of 16), d_exps [f + ones_row]
+ * from d_colmax [f]; ones_row = 1 appends the constant feature 1.0 (its products are column sums = bias gradients) */
 int egp_oz_slice_cols_t_f64(const double *d_x, int64_t n, int f, int64_t ldx, int n_slices, const double *d_colmax,
-                           int8_t *d_out, int64_t np, int32_t *d_exps, void *stream);
-/* C [m][n] (ldc) = A B^T (+ bias[n], relu) from slices A [S][m][kp], B [S][n][kp] and their exponents.  Long
- * contractions with few output tiles (weight gradients) run split-K through d_work (egp_oz_gemm_work_bytes). */
-int64_t egp_oz_gemm_work_bytes(int64_t m, int n, int64_t kp);
+                           int8_t *d_out, int64_t np, int32_t *d_exps, int ones_row, void *stream);
+/* C [m][n] (ldc) = A B^T (+ bias[n], relu; zeroed where d_mask [m][ldm] <= 0) from slices A [S][m][kp], B [S][n][kp] and
+ * their exponents.  Long contractions with few output tiles (weight gradients) run split-K through d_work
+ * (egp_oz_gemm_work_bytes; bias / relu / mask are not available there). */
+int64_t egp_oz_gemm_work_bytes(int64_t m, int n, int64_t kp, int n_slices);
 int egp_oz_gemm_f64(const int8_t *d_a, const int32_t *d_ea, int64_t m, const int8_t *d_b, const int32_t *d_eb, int n,
-                    int64_t kp, int n_slices, const double *d_bias, int relu, double *d_c, int64_t ldc, void *d_work,
-                    int64_t work_bytes, void *stream);
+                    int64_t kp, int n_slices, const double *d_bias, int relu, const double *d_mask, int64_t ldm,
+                    double *d_c, int64_t ldc, void *d_work, int64_t work_bytes, void *stream);
 
 #ifdef __cplusplus
 }

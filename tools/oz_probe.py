@@ -22,8 +22,9 @@ def recon(sl, ex, axis_scale_rows=True):
     return v * torch.ldexp(torch.ones_like(ex, dtype=torch.float64), ex)[:, None]
 
 
-def exact_ref(a, ea, b, eb, bias=None, relu=False):
-    """same arithmetic as the kernel: exact integer brackets (float64 holds them exactly), Horner, scales"""
+def exact_ref(a, ea, b, eb, bias=None, relu=False, mask=None):
+    """same arithmetic as the kernel: exact integer brackets (float64 holds them exactly), two exact Horner groups
+    (d < 4 and d >= 4) joined with one rounding, scales, bias, relu, mask"""
     S = a.shape[0]
     A, B = a.double(), b.double()
     acc = []
@@ -32,19 +33,28 @@ def exact_ref(a, ea, b, eb, bias=None, relu=False):
         for t in range(d + 1):
             s += A[t] @ B[d - t].t()
         acc.append(s)
-    h = acc[S - 1]
-    for d in range(S - 2, -1, -1):
-        h = h * 0.0078125 + acc[d]
-    h = h * torch.ldexp(torch.ones_like(ea, dtype=torch.float64), ea - 12)[:, None]
-    h = h * torch.ldexp(torch.ones_like(eb, dtype=torch.float64), eb)[None, :]
+    G = min(S, 4)
+    hi = acc[0].clone()
+    for d in range(1, G):
+        hi = hi * 128.0 + acc[d]
+    h = hi * 2.0 ** (-7 * (G - 1))
+    if S > G:
+        lo = acc[G].clone()
+        for d in range(G + 1, S):
+            lo = lo * 128.0 + acc[d]
+        h = h + lo * 2.0 ** (-7 * (S - 1))
+    h = h * (torch.ldexp(torch.ones_like(ea, dtype=torch.float64), ea - 12)[:, None]
+             * torch.ldexp(torch.ones_like(eb, dtype=torch.float64), eb)[None, :])
     if bias is not None:
         h = h + bias[None, :]
     if relu:
         h = torch.relu(h)
+    if mask is not None:
+        h = torch.where(mask > 0, h, torch.zeros_like(h))
     return h
 
 
-def check(M, N, K, S, bias=False, relu=False, scale_rows=True):
+def check(M, N, K, S, bias=False, relu=False, scale_rows=True, mask=False):
     x = torch.randn(M, K, device=dev, dtype=torch.float64)
     if scale_rows:
         x *= torch.exp(3 * torch.randn(M, 1, device=dev, dtype=torch.float64))
@@ -57,15 +67,19 @@ def check(M, N, K, S, bias=False, relu=False, scale_rows=True):
     e_sl = ((ra - x).abs() / amax).max().item()
     assert (a[:, :, K:] == 0).all(), 'padding not zero'
     bv = torch.randn(N, device=dev, dtype=torch.float64) if bias else None
-    c = lib.oz_gemm(a, ea, b, eb, bias=bv, relu=relu)
+    mk = torch.randn(M, N, device=dev, dtype=torch.float64) if mask else None
+    assert a.abs().max() <= 64 and b.abs().max() <= 64, 'digit out of range'
+    c = lib.oz_gemm(a, ea, b, eb, bias=bv, relu=relu, mask=mk)
     torch.cuda.synchronize()
-    ref = exact_ref(a, ea, b, eb, bv, relu)
+    ref = exact_ref(a, ea, b, eb, bv, relu, mk)
     exact = torch.equal(c, ref)
     true = x @ w.t()
     if bias:
         true = true + bv
     if relu:
         true = torch.relu(true)
+    if mask:
+        true = torch.where(mk > 0, true, torch.zeros_like(true))
     bound = amax * w.abs().max(1).values[None, :] * K
     e_rel = ((c - true).abs() / bound).max().item()
     e_typ = ((c - true).abs().max() / true.abs().max()).item()
@@ -87,13 +101,13 @@ def check_wgrad(Ns, F1, F2, S):
     dy = torch.randn(Ns, F1, device=dev, dtype=torch.float64) * torch.exp(torch.randn(Ns, 1, device=dev, dtype=torch.float64))
     x = torch.relu(torch.randn(Ns, F2, device=dev, dtype=torch.float64))
     a, ea = lib.oz_slice_colsT(dy, S, lib.oz_colmax(dy))
-    b, eb = lib.oz_slice_colsT(x, S, lib.oz_colmax(x))
+    b, eb = lib.oz_slice_colsT(x, S, lib.oz_colmax(x), ones_row=True)
     torch.cuda.synchronize()
     ra = recon(a[:, :, :Ns], ea)
     e_sl = ((ra - dy.t()).abs() / dy.abs().max(0).values[:, None]).max().item()
     c = lib.oz_gemm(a, ea, b, eb)
     torch.cuda.synchronize()
-    true = dy.t() @ x
+    true = dy.t() @ torch.cat([x, torch.ones(Ns, 1, device=dev, dtype=torch.float64)], 1)
     e_typ = ((c - true).abs().max() / true.abs().max()).item()
     ok = True
     if Ns <= 70000:
@@ -137,6 +151,39 @@ def bench(M, N, K, S, iters=10):
           % (M, N, K, S, t_oz, fl / t_oz * 1e-9, t_bl, fl / t_bl * 1e-9, t_sl, M * K * (8 + S) / t_sl * 1e-6), flush=True)
 
 
+def bench_wgrad(Ns, F1, F2, S, iters=20):
+    dy = torch.randn(Ns, F1, device=dev, dtype=torch.float64)
+    x = torch.relu(torch.randn(Ns, F2, device=dev, dtype=torch.float64))
+    a, ea = lib.oz_slice_colsT(x, S, lib.oz_colmax(x), ones_row=True)
+    b, eb = lib.oz_slice_colsT(dy, S, lib.oz_colmax(dy))
+    out = torch.empty(F2 + 1, F1, device=dev, dtype=torch.float64)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+    for _ in range(3):
+        lib.oz_gemm(a, ea, b, eb, out=out)
+    ev[0].record()
+    for _ in range(iters):
+        lib.oz_gemm(a, ea, b, eb, out=out)
+    ev[1].record()
+    out2 = torch.empty(F2, F1, device=dev, dtype=torch.float64)
+    for _ in range(2):
+        torch.mm(x.t(), dy, out=out2)
+    ev[2].record()
+    for _ in range(iters):
+        torch.mm(x.t(), dy, out=out2)
+    ev[3].record()
+    cm = torch.zeros(F2, device=dev, dtype=torch.float64)
+    ev[4].record()
+    for _ in range(iters):
+        lib.oz_colmax(x, cm)
+        lib.oz_slice_colsT(x, S, cm, out=(a, ea), ones_row=True)
+    ev[5].record()
+    torch.cuda.synchronize()
+    t_oz, t_bl, t_sl = ev[0].elapsed_time(ev[1]) / iters, ev[2].elapsed_time(ev[3]) / iters, ev[4].elapsed_time(ev[5]) / iters
+    fl = 2.0 * Ns * F1 * F2
+    print('bench wgrad Ns %8d F1 %3d F2 %3d S %d | ozaki %.3f ms (%.1f TFLOP/s f64-eq) | cuBLAS %.3f ms (%.1f TFLOP/s) | colmax+sliceT %.3f ms (%.0f GB/s)'
+          % (Ns, F1, F2, S, t_oz, fl / t_oz * 1e-9, t_bl, fl / t_bl * 1e-9, t_sl, Ns * F2 * (16 + S) / t_sl * 1e-6), flush=True)
+
+
 if __name__ == '__main__':
     quick = 'quick' in sys.argv
     ok = True
@@ -147,12 +194,24 @@ if __name__ == '__main__':
     ok &= check(4096 + 17, 304, 300, 3)
     ok &= check(513, 1, 300, 7, bias=True)
     ok &= check(2000, 300, 640, 8)
+    ok &= check(18944, 300, 300, 6, bias=False, mask=True)
+    ok &= check(3000, 244, 52, 6)
     ok &= check_wgrad(5000, 52, 300, 5)
     ok &= check_wgrad(65536 + 100, 300, 243, 6)
     print('ALL OK' if ok else 'FAILURES', flush=True)
-    if not quick and ok:
-        for S in (4, 5, 6):
+    if not quick and ok and "full" not in sys.argv:
+        for S in (4, 6):
+            bench(1228800, 300, 243, S)
+        bench(18944, 300, 300, 6, iters=50)
+        bench_wgrad(18944, 300, 300, 6)
+    if "full" in sys.argv and ok:
+        for S in (4, 5, 6, 7):
             bench(1228800, 300, 243, S)
             bench(1228800, 300, 300, S)
+        bench(18944, 300, 300, 6, iters=50)
+        bench(18944, 52, 300, 6, iters=50)
+        bench_wgrad(18944, 300, 300, 6)
+        bench_wgrad(1228800, 300, 300, 6)
+        ok &= check_wgrad(18944, 300, 300, 6)
         ok &= check_wgrad(1228800, 300, 300, 6)
         t0 = time.time()
