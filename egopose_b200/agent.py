@@ -18,6 +18,7 @@ What changes underneath (B200-first):
 There is no CPU fallback: every numeric step is a kernel of libegopose_b200.so or a cuBLAS GEMM.
 """
 import math
+import os
 import time
 
 import numpy as np
@@ -109,6 +110,15 @@ class _Trunk:
 
     def gb(self, i):
         return self.f.view(self.f.grad, self.names[i] + '.bias')
+
+    def weights(self):
+        return (self.W(0), self.b(0), self.W(1), self.b(1), self.W(2), self.b(2))
+
+    def grads(self):
+        return (self.gW(0), self.gb(0), self.gW(1), self.gb(1), self.gW(2), self.gb(2))
+
+    def dims(self):
+        return (self.W(0).shape[1], self.W(0).shape[0], self.W(1).shape[0], self.W(2).shape[0])
 
     def _buf(self, key, shape, like):
         """reusable activation buffer: grows to the largest row count seen, hands out a [:n] view"""
@@ -338,7 +348,7 @@ class Agent:
 
 class AgentPG(Agent):
     def __init__(self, gamma=0.99, tau=0.95, optimizer_policy=None, optimizer_value=None, opt_num_epochs=1,
-                 value_opt_niter=1, **kwargs):
+                 value_opt_niter=1, gemm=None, oz_slices=None, **kwargs):
         super().__init__(**kwargs)
         self.gamma = gamma
         self.tau = tau
@@ -348,6 +358,14 @@ class AgentPG(Agent):
         self.value_opt_niter = value_opt_niter
         self._nets = None
         self.last_info = {}
+        # dense layers of the update: 'ozaki' = float64 on the int8 tensor cores (csrc/ozaki.cu, csrc/oz_mlp.cu),
+        # 'cublas' = cuBLAS DGEMM.  Nets whose input is produced by a learned context net always use cuBLAS.
+        self.gemm = gemm or os.environ.get('EGP_GEMM', 'ozaki')
+        self.oz_slices = int(oz_slices or os.environ.get('EGP_OZ_SLICES', 6))
+        if self.gemm not in ('ozaki', 'cublas'):
+            raise lib.EgpError("gemm must be 'ozaki' or 'cublas'")
+        self._ozs = {}
+        self._xcaches = {}
 
     # ---- flat storage ------------------------------------------------------------------------------
     def _setup(self):
@@ -405,12 +423,52 @@ class AgentPG(Agent):
         inp = _NetInput(x_const=states)
         return inp, inp
 
-    def update_value(self, x, returns, inv_n, reuse_forward=False):
+    # ---- int8-tensor-core dense layers --------------------------------------------------------------
+    def _oz(self, trunk, inp):
+        """OzMlp of a trunk when its input is a constant tensor and the ozaki backend is selected, else None"""
+        if self.gemm != 'ozaki' or inp.learned:
+            return None
+        dims = tuple(int(v) for v in trunk.dims())
+        oz = self._ozs.get(dims)
+        if oz is None:
+            oz = lib.OzMlp(*dims, n_slices=self.oz_slices, device=trunk.W(0).device)
+            self._ozs[dims] = oz
+        return oz
+
+    def _xcache(self, oz, x):
+        """input-slice cache of one constant input tensor for the current update (shared by nets with the same input)"""
+        key = (x.data_ptr(), x.shape[0], x.shape[1])
+        ent = self._xcaches.get(key)
+        if ent is None:
+            # reuse an allocation of the same size from an earlier update
+            for k in list(self._xcaches):
+                if k[1:] == key[1:] and not self._xcaches[k].get('live'):
+                    ent = self._xcaches.pop(k)
+                    break
+            if ent is None:
+                ent = oz.new_cache(x.shape[0])
+            ent['valid'] = False
+            ent['live'] = True
+            self._xcaches[key] = ent
+        return ent
+
+    def update_value(self, x, returns, inv_n, reuse_forward=False, cache=True):
         """agents/agent_pg.py:19-26.  ``reuse_forward``: the activations of the value forward that produced the
         GAE inputs are still valid (no parameter step since), so the first epoch skips its forward GEMMs.
         ``x`` is a tensor or a _NetInput."""
         inp = x if isinstance(x, _NetInput) else _NetInput(x_const=x)
+        oz = self._oz(self._vt, inp)
         for it in range(self.value_opt_niter):
+            if oz is not None:
+                xt = inp.x_const
+                self._scal[0:1].zero_()
+                oz.step(self._vt.weights(), xt, grads=self._vt.grads(), cache=self._xcache(oz, xt) if cache else None,
+                        loss=dict(kind='value', returns=returns, inv_n=inv_n, loss=self._scal[0:1]))
+                d = _dist()
+                if d is not None:
+                    d.all_reduce(self._vf.grad)
+                self._vf.adam(0.0)
+                continue
             if reuse_forward and it == 0 and not inp.learned:
                 v, xt = self._vt.buf['y'], self._vt.x
             else:
@@ -433,8 +491,16 @@ class AgentPG(Agent):
         states, actions, rewards, masks, exps, v_metas, horizon = self._device_batch(batch)
         xp, xv = self._inputs(states, v_metas, masks, horizon)
         # values + GAE (agent_pg.py:48-53, core/common.py:5-25)
-        values = self._vt.forward(xv.x(grad=False)).view(-1)
-        self._value_fresh = not xv.learned
+        for ent in self._xcaches.values():
+            ent['live'] = False
+        oz = self._oz(self._vt, xv)
+        if oz is not None:
+            xt = xv.x_const
+            values = oz.step(self._vt.weights(), xt, y=self._vt._buf('y', (xt.shape[0], 1), xt), cache=self._xcache(oz, xt)).view(-1)
+            self._value_fresh = False
+        else:
+            values = self._vt.forward(xv.x(grad=False)).view(-1)
+            self._value_fresh = not xv.learned
         adv, returns, stats = lib.gae(rewards, masks, values.contiguous(), self.gamma, self.tau)
         n_local = states.shape[0]
         n_exp = exps.sum()
@@ -468,9 +534,24 @@ class AgentPPO(AgentPG):
             raise lib.EgpError('one (params, max_norm) clip group is supported (ego_mimic.py:90)')
         return float(self.policy_grad_clip[0][1])
 
-    def _policy_step(self, xp, actions, adv, logp0, exps, inv_count, log_std, max_norm, mu=None):
+    def _policy_step(self, xp, actions, adv, logp0, exps, inv_count, log_std, max_norm, mu=None, cache=True):
         """ppo_loss forward+backward, gradient all-reduce, clip + Adam (agent_ppo.py:47-51 / :38-43)"""
         inp = xp if isinstance(xp, _NetInput) else _NetInput(x_const=xp)
+        oz = self._oz(self._pt, inp)
+        if oz is not None:
+            xt = inp.x_const
+            self._scal[1:2].zero_()
+            dls = None
+            if self._learn_std:
+                dls = self._pf.view(self._pf.grad, 'action_log_std').view(-1)
+                dls.zero_()
+            oz.step(self._pt.weights(), xt, grads=self._pt.grads(), cache=self._xcache(oz, xt) if cache else None,
+                    loss=dict(kind='ppo', actions=actions, log_std=log_std, adv=adv, stats=self._stats, logp0=logp0, exps=exps,
+                              clip_eps=self.clip_epsilon, inv_count=inv_count, dlogstd=dls, loss=self._scal[1:2]))
+            if _dist() is not None:
+                _dist().all_reduce(self._pf.grad)
+            self._pf.adam(max_norm)
+            return self._scal[1:2].clone()
         if mu is None or inp.learned:
             mu = self._pt.forward(inp.x())
         dmu = self._pt._buf('dy', mu.shape, mu)
@@ -523,16 +604,21 @@ class AgentPPO(AgentPG):
             ws = dist_utils.world_size()
             for i in range(nb):
                 lo, hi = i * B, min((i + 1) * B, n)
-                self.update_value(gxv[lo:hi], g['ret'][lo:hi], 1.0 / ((hi - lo) * ws))
+                self.update_value(gxv[lo:hi], g['ret'][lo:hi], 1.0 / ((hi - lo) * ws), cache=False)
                 vloss.append(self._scal[0:1].clone())
                 surr.append(self._policy_step(g['xp'][lo:hi], g['ac'][lo:hi], g['adv'][lo:hi], g['lp'][lo:hi], g['ex'][lo:hi],
-                                              1.0 / float(counts[i]), log_std, max_norm))
+                                              1.0 / float(counts[i]), log_std, max_norm, cache=False))
         self.last_info = dict(surr_loss=surr, value_loss=vloss)
 
     def update_policy(self, xp, xv, actions, returns, adv, exps, inv_count, inv_n):
         """agents/agent_ppo.py:16-51"""
         log_std = self.policy_net.action_log_std.data.view(-1)
-        mu = self._pt.forward(xp.x(grad=False))
+        oz = self._oz(self._pt, xp)
+        if oz is not None:
+            xt = xp.x_const
+            mu = oz.step(self._pt.weights(), xt, y=self._pt._buf('y', (xt.shape[0], self._pt.dims()[3]), xt), cache=self._xcache(oz, xt))
+        else:
+            mu = self._pt.forward(xp.x(grad=False))
         logp0 = lib.gauss_logp(mu, actions, log_std)                    # fixed_log_probs (:18-20)
         max_norm = self._max_norm()
         if self.use_mini_batch:

@@ -266,21 +266,32 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm,
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem], int8 x int8 -> int32
-__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[smem] * B[smem], int8 x int8 -> int32.  Shared-memory descriptors are passed as their low words (start
+// address >> 4, leading byte offset 1) plus the constant high word, so the issuing loop only does 32-bit uniform adds.
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
-        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u) : "memory");
+        ".reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %4, p;\n\t"
+        "}" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate) : "memory");
 }
-// K-major operand tile in the canonical 32-byte-swizzle layout (what TMA SWIZZLE_32B writes): rows of 32 B, 8-row
-// groups of 256 B (stride byte offset), descriptor version 1 (Blackwell), layout type 6 = SWIZZLE_32B
-__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t saddr) {
-    if (BK == 64)   // 64-byte swizzle: 8-row groups of 512 B, layout type 4
-        return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46) | (6ull << 61);
+// K-major operand tile in the canonical swizzled layout that TMA writes: rows of BK bytes, 8-row groups of 8 BK bytes
+// (stride byte offset), descriptor version 1 (Blackwell), layout type 6 = SWIZZLE_32B / 4 = SWIZZLE_64B
+constexpr uint32_t DESC_HI = (uint32_t)((8 * BK) >> 4) | (1u << 14) | ((BK == 64 ? 4u : 6u) << 29);
+constexpr uint32_t DESC_LO_FLAGS = 1u << 16;
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(pred));
+    return pred != 0;
 }
 // instruction descriptor: dense, S32 accumulate, signed int8 A and B, both K-major, M = 128
 __host__ __device__ constexpr uint32_t idesc_i8(int bn) {
@@ -399,39 +410,58 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer: slice pair (t, u) accumulates into TMEM accumulator d = t + u (columns d * BN ...)
-        if (lane == 0) {
-            uint32_t it = 0, tc = 0;
-            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tc++) {
-                const int z = (int)(tile / ((long long)g.nt * g.mt));
-                const int kb0 = z * g.kb_per_split;
-                const int kb1 = kb0 + g.kb_per_split < g.nkb ? kb0 + g.kb_per_split : g.nkb;
-                if (tc > 0) {                                         // epilogue has drained the previous tile
-                    mbar_wait(smem_u32(&tempty_bar), (tc - 1) & 1);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                }
-                for (int kb = kb0; kb < kb1; kb++, it++) {
-                    const uint32_t s = it % stages;
-                    mbar_wait(smem_u32(&full_bar[s]), (it / stages) & 1);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t sa = smem_u32(smem + (size_t)s * STAGE), sb = sa + S * A_SLICE;
+        // ===== MMA issuer: slice pair (t, u) accumulates into TMEM accumulator d = t + u (columns d * BN ...).  The whole
+        // warp walks the (uniform) tile / stage loop so that descriptors live in uniform registers; one elected lane
+        // issues the tcgen05 instructions.
+        uint32_t it = 0, tc = 0;
+        const uint32_t smem_base4 = __shfl_sync(0xffffffffu, smem_u32(smem) >> 4, 0);
+#ifdef OZ_PROFILE
+        long long t_te = 0, t_full = 0, t_tot = clock64(), t0;
+#define OZ_T0 t0 = clock64()
+#define OZ_ACC(v) v += clock64() - t0
+#else
+#define OZ_T0
+#define OZ_ACC(v)
+#endif
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tc++) {
+            const int z = (int)(tile / ((long long)g.nt * g.mt));
+            const int kb0 = z * g.kb_per_split;
+            const int kb1 = kb0 + g.kb_per_split < g.nkb ? kb0 + g.kb_per_split : g.nkb;
+            if (tc > 0) {                                         // epilogue has drained the previous tile
+                OZ_T0;
+                mbar_wait(smem_u32(&tempty_bar), (tc - 1) & 1);
+                OZ_ACC(t_te);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
+            for (int kb = kb0; kb < kb1; kb++, it++) {
+                const uint32_t s = it % stages;
+                OZ_T0;
+                mbar_wait(smem_u32(&full_bar[s]), (it / stages) & 1);
+                OZ_ACC(t_full);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sa4 = (smem_base4 + s * (STAGE >> 4)) | DESC_LO_FLAGS, sb4 = sa4 + ((S * A_SLICE) >> 4);
+                const uint32_t first = kb > kb0 ? 1u : 0u;
+                if (elect_one()) {
 #pragma unroll
                     for (int k2 = 0; k2 < BK / UMMA_K; k2++) {
 #pragma unroll
                         for (int t = 0; t < S; t++) {
-                            const uint64_t ad = umma_desc_sw32(sa + t * A_SLICE + k2 * UMMA_K);
 #pragma unroll
-                            for (int u = 0; u < S - t; u++) {
-                                const uint64_t bd = umma_desc_sw32(sb + u * B_SLICE + k2 * UMMA_K);
-                                umma_i8(tmem + (uint32_t)((t + u) * BN), ad, bd, IDESC, (kb > kb0 || t > 0 || k2 > 0) ? 1u : 0u);
-                            }
+                            for (int u = 0; u < S - t; u++)
+                                umma_i8(tmem + (uint32_t)((t + u) * BN), sa4 + ((t * A_SLICE + k2 * UMMA_K) >> 4),
+                                        sb4 + ((u * B_SLICE + k2 * UMMA_K) >> 4), DESC_HI, IDESC, (t > 0 || k2 > 0) ? 1u : first);
                         }
                     }
                     umma_commit(smem_u32(&empty_bar[s]));            // frees the smem stage when these MMAs retire
                 }
-                umma_commit(smem_u32(&tfull_bar));                    // accumulators of this tile complete
+                __syncwarp();
             }
+            if (elect_one()) umma_commit(smem_u32(&tfull_bar));       // accumulators of this tile complete
+            __syncwarp();
         }
+#ifdef OZ_PROFILE
+        if (blockIdx.x == 0 && lane == 0) printf("mma warp: total %lld  wait tempty %lld  wait full %lld  tiles %u\n", clock64() - t_tot, t_te, t_full, tc);
+#endif
     } else {
         // ===== epilogue: warp w reads TMEM lanes 32 (w % 4) ..; one output row per thread, half of the tile's columns.
         // Drain: accumulators -> exact integer Horner -> one double per element in registers, then TMEM goes back to the
@@ -442,6 +472,9 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint8_t *obuf = smem + (size_t)stages * STAGE + (size_t)(warp - 2) * 4096;
         double *colc = reinterpret_cast<double *>(smem + (size_t)stages * STAGE + EPI_WARPS * 4096) + (warp - 2) * 2 * HC;
         uint32_t tc = 0, nstore = 0;
+#ifdef OZ_PROFILE
+        long long e_wait = 0, e_drain = 0, e_post = 0, e_tot = clock64(), e0;
+#endif
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tc++) {
             const int n_blk = (int)(tile % g.nt);
             const long long rest = tile / g.nt;
@@ -467,7 +500,13 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 __syncwarp();
             }
+#ifdef OZ_PROFILE
+            e0 = clock64();
+#endif
             mbar_wait(smem_u32(&tfull_bar), tc & 1);
+#ifdef OZ_PROFILE
+            e_wait += clock64() - e0; e0 = clock64();
+#endif
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             double hv[HC];
 #pragma unroll
@@ -489,6 +528,9 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int jj = 0; jj < 8; jj++) hv[c0 + jj] = oz_horner<S, false>(acc, jj, rs_hi, rs_lo);
                 }
             }
+#ifdef OZ_PROFILE
+            e_drain += clock64() - e0; e0 = clock64();
+#endif
 #pragma unroll
             for (int c0 = 0; c0 < HC; c0 += 8) {
                 const int colb = col0 + c0;
@@ -549,7 +591,13 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (colb + jj < g.N) crow[colb + jj] = v[jj];
                 }
             }
+#ifdef OZ_PROFILE
+            e_post += clock64() - e0;
+#endif
         }
+#ifdef OZ_PROFILE
+        if (blockIdx.x == 0 && warp == 2 && lane == 0) printf("epi warp: total %lld  wait tfull %lld  drain %lld  post %lld\n", clock64() - e_tot, e_wait, e_drain, e_post);
+#endif
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -632,6 +680,11 @@ static inline int pick_bn(int n, int S) {
     if (S > 6) return 64;
     const int t64 = (n + 63) / 64, t80 = (n + 79) / 80;
     return (t80 * 80 <= t64 * 64 || t80 < t64) ? 80 : 64;
+}
+
+long long gemm_tiles(long long m, int n, int S) {
+    const int bn = pick_bn(n, S);
+    return ((m + BM - 1) / BM) * ((n + bn - 1) / bn);
 }
 
 int choose_splits(long long m, int n, long long kp, int S) {

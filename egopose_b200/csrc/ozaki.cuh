@@ -38,6 +38,7 @@ struct GemmOut {
 };
 long long gemm_work_bytes(long long m, int n, long long kp, int force_splits);
 int choose_splits(long long m, int n, long long kp, int S);
+long long gemm_tiles(long long m, int n, int S);      // output tiles of one split
 // C = A B^T from slices A [S][m][kp], B [S][n][kp]
 int gemm(const int8_t *a, const int32_t *ea, long long m, const int8_t *b, const int32_t *eb, int n, long long kp, int S,
          GemmOut &o, cudaStream_t st);

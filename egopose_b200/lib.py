@@ -69,6 +69,18 @@ class TrajOut(C.Structure):
                 ('d_final_qvel', _vp), ('d_logger', _vp)]
 
 
+class MlpNet(C.Structure):
+    _fields_ = [('in_dim', C.c_int32), ('h1', C.c_int32), ('h2', C.c_int32), ('out_dim', C.c_int32),
+                ('d_W1', _vp), ('d_b1', _vp), ('d_W2', _vp), ('d_b2', _vp), ('d_W3', _vp), ('d_b3', _vp),
+                ('d_gW1', _vp), ('d_gb1', _vp), ('d_gW2', _vp), ('d_gb2', _vp), ('d_gW3', _vp), ('d_gb3', _vp)]
+
+
+class MlpLoss(C.Structure):
+    _fields_ = [('kind', C.c_int32), ('d_actions', _vp), ('d_log_std', _vp), ('d_adv', _vp), ('d_stats', _vp),
+                ('d_logp0', _vp), ('d_exps', _vp), ('clip_eps', C.c_double), ('inv_count', C.c_double),
+                ('d_dlogstd', _vp), ('d_returns', _vp), ('inv_n', C.c_double), ('d_loss', _vp)]
+
+
 # every symbol include/egopose_b200.h declares: name -> (restype, argtypes)
 _i64 = C.c_int64
 _d = C.c_double
@@ -104,6 +116,11 @@ SYMBOLS = {
     'egp_oz_slice_cols_t_f64': (_int, [_vp, _i64, _int, _i64, _int, _vp, _vp, _i64, _vp, _int, _vp]),
     'egp_oz_gemm_work_bytes': (_i64, [_i64, _int, _i64, _int]),
     'egp_oz_gemm_f64': (_int, [_vp, _vp, _i64, _vp, _vp, _int, _i64, _int, _vp, _int, _vp, _i64, _vp, _i64, _vp, _i64, _vp]),
+    'egp_oz_mlp_chunk_rows': (_i64, []),
+    'egp_oz_mlp_work_bytes': (_i64, [_int, _int, _int, _int, _i64, _int]),
+    'egp_oz_mlp_xcache_bytes': (_i64, [_int, _i64, _i64, _int]),
+    'egp_oz_mlp_step_f64': (_int, [C.POINTER(MlpNet), _vp, _i64, _i64, C.POINTER(MlpLoss), _vp, _int, _i64, _vp, _int, _vp, _i64,
+                                   _vp]),
 }
 
 _lib = None
@@ -560,3 +577,68 @@ def oz_gemm(a, ea, b, eb, bias=None, relu=False, out=None, mask=None):
           'egp_oz_gemm_f64')
     launches += 2 if need else 1
     return out
+
+
+# ---- chunked MLP forward / loss / backward on the int8 tensor cores (csrc/oz_mlp.cu) -------------------------------
+def _raw(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class OzMlp:
+    """Workspace + input-slice cache of egp_oz_mlp_step_f64 for one (in, h1, h2, out) shape.  ``weights`` / ``grads`` are
+    6-tuples of contiguous float64 CUDA tensors (W1, b1, W2, b2, W3, b3) in torch nn.Linear layout."""
+
+    def __init__(self, in_dim, h1, h2, out_dim, n_slices=6, chunk_rows=None, device=None):
+        import torch
+        lib = load()
+        self.dims = (int(in_dim), int(h1), int(h2), int(out_dim))
+        self.S = int(n_slices)
+        self.chunk = int(chunk_rows or lib.egp_oz_mlp_chunk_rows())
+        self.device = device
+        nbytes = lib.egp_oz_mlp_work_bytes(*self.dims, self.chunk, self.S)
+        self.work = torch.empty(nbytes, dtype=torch.uint8, device=device)
+
+    def launches_per_chunk(self, bwd):
+        return 36 if bwd else 7
+
+    def new_cache(self, n):
+        import torch
+        nbytes = load().egp_oz_mlp_xcache_bytes(self.dims[0], n, self.chunk, self.S)
+        return dict(buf=torch.empty(nbytes, dtype=torch.uint8, device=self.device), n=int(n), valid=False)
+
+    def step(self, weights, x, grads=None, loss=None, y=None, cache=None):
+        """loss: None (forward only, returns y), or dict(kind='ppo', actions, log_std, adv, stats, logp0, exps, clip_eps,
+        inv_count, dlogstd, loss) / dict(kind='value', returns, inv_n, loss)"""
+        global launches
+        import torch
+        n = x.shape[0]
+        if x.stride(1) != 1 or x.shape[1] != self.dims[0] or x.dtype != torch.float64:
+            raise EgpError('OzMlp.step: x must be a row-major float64 [n, %d] tensor' % self.dims[0])
+        net = MlpNet(*self.dims, *[_raw(w) for w in weights], *([_raw(g) for g in grads] if grads is not None else [None] * 6))
+        ls = MlpLoss()
+        ls.kind = 0
+        if loss is not None:
+            if loss['kind'] == 'ppo':
+                ls.kind = 1
+                ls.d_actions, ls.d_log_std, ls.d_adv, ls.d_stats = (_raw(loss[k]) for k in ('actions', 'log_std', 'adv', 'stats'))
+                ls.d_logp0, ls.d_exps = _raw(loss['logp0']), _raw(loss['exps'])
+                ls.clip_eps, ls.inv_count = float(loss['clip_eps']), float(loss['inv_count'])
+                ls.d_dlogstd = _raw(loss.get('dlogstd'))
+            else:
+                ls.kind = 2
+                ls.d_returns, ls.inv_n = _raw(loss['returns']), float(loss['inv_n'])
+            ls.d_loss = _raw(loss['loss'])
+        elif y is None:
+            y = torch.empty((n, self.dims[3]), dtype=torch.float64, device=x.device)
+        state = 0
+        if cache is not None:
+            if cache['n'] != n:
+                raise EgpError('OzMlp.step: input cache was sized for %d rows, got %d' % (cache['n'], n))
+            state = 2 if cache['valid'] else 1
+        check(load().egp_oz_mlp_step_f64(C.byref(net), ptr(x[:1]) if not x.is_contiguous() else ptr(x), x.stride(0), n, C.byref(ls),
+                                         _raw(y), self.S, self.chunk, _raw(cache['buf']) if cache is not None else None, state,
+                                         _raw(self.work), self.work.numel(), stream_ptr()), 'egp_oz_mlp_step_f64')
+        if cache is not None:
+            cache['valid'] = True
+        launches += ((n + self.chunk - 1) // self.chunk) * self.launches_per_chunk(loss is not None) + 7
+        return y

@@ -253,6 +253,38 @@ int egp_oz_gemm_f64(const int8_t *d_a, const int32_t *d_ea, int64_t m, const int
                     int64_t kp, int n_slices, const double *d_bias, int relu, const double *d_mask, int64_t ldm,
                     double *d_c, int64_t ldc, void *d_work, int64_t work_bytes, void *stream);
 
+/* --- chunked MLP forward / loss / backward on the int8 tensor cores (egopose_b200/csrc/oz_mlp.cu) ------------
+ * One optimisation step's forward + loss + backward of a two-hidden-layer relu MLP (models/mlp.py:22-25 trunk,
+ * core/policy_gaussian.py:19-24 or core/critic.py:15-18 head), i.e. the autograd graph of agents/agent_pg.py:19-26
+ * (value) and agents/agent_ppo.py:44-51,58-65 (policy), in row chunks whose intermediates stay L2-resident. */
+typedef struct {
+    int32_t in_dim, h1, h2, out_dim;
+    const double *d_W1, *d_b1, *d_W2, *d_b2, *d_W3, *d_b3;      /* torch nn.Linear layout [out][in] */
+    double *d_gW1, *d_gb1, *d_gW2, *d_gb2, *d_gW3, *d_gb3;      /* gradients, same layouts (NULL for forward only) */
+} EgpMlpNet;
+
+typedef struct {
+    int32_t kind;                       /* 0 forward only, 1 PPO clipped surrogate (agent_ppo.py:58-65), 2 value MSE (agent_pg.py:22-23) */
+    /* kind 1: per-sample arrays over the whole batch, see egp_ppo_loss_grad_f64 */
+    const double *d_actions, *d_log_std, *d_adv, *d_stats, *d_logp0, *d_exps;
+    double clip_eps, inv_count;
+    double *d_dlogstd;                  /* [out_dim] accumulated, or NULL */
+    /* kind 2 */
+    const double *d_returns;
+    double inv_n;
+    double *d_loss;                     /* [1] accumulated */
+} EgpMlpLoss;
+
+int64_t egp_oz_mlp_chunk_rows(void);   /* 128 rows x number of SMs */
+int64_t egp_oz_mlp_work_bytes(int in_dim, int h1, int h2, int out_dim, int64_t chunk_rows, int n_slices);
+int64_t egp_oz_mlp_xcache_bytes(int in_dim, int64_t n, int64_t chunk_rows, int n_slices);
+/* d_x [n][in_dim] (leading dimension ldx).  kind 0 writes y [n][out_dim] to d_y; kinds 1 / 2 write the six gradients
+ * (overwritten) and optionally y.  d_xcache / xcache_state: 0 none, 1 fill while running, 2 reuse (same x, n, chunk_rows,
+ * n_slices as when it was filled): the int8 slices of the constant input are then read instead of recomputed. */
+int egp_oz_mlp_step_f64(const EgpMlpNet *net, const double *d_x, int64_t ldx, int64_t n, const EgpMlpLoss *loss, double *d_y,
+                        int n_slices, int64_t chunk_rows, void *d_xcache, int xcache_state, void *d_work, int64_t work_bytes,
+                        void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,7 +20,8 @@ def _nets_from(g, prefix_p, prefix_v, D, H, A):
     return pol.cuda(), val.cuda()
 
 
-def test_agent_ppo_update_matches_reference_golden(golden):
+@pytest.mark.parametrize('gemm', ['ozaki', 'cublas'])
+def test_agent_ppo_update_matches_reference_golden(golden, gemm):
     from egopose_b200.agent import AgentPPO
     from egopose_b200.trajbatch import TrajBatch
     g = golden('ppo_small')
@@ -30,7 +31,7 @@ def test_agent_ppo_update_matches_reference_golden(golden):
     opt_v = torch.optim.Adam(val.parameters(), lr=lr_v)
     agent = AgentPPO(env=None, dtype=torch.float64, device=torch.device('cuda'), policy_net=pol, value_net=val,
                      optimizer_policy=opt_p, optimizer_value=opt_v, opt_num_epochs=3, gamma=gamma, tau=tau,
-                     clip_epsilon=clip, policy_grad_clip=[(list(pol.parameters()), max_norm)])
+                     clip_epsilon=clip, policy_grad_clip=[(list(pol.parameters()), max_norm)], gemm=gemm)
     batch = TrajBatch.from_numpy(states=g['states'], actions=g['actions'], rewards=g['rewards'], masks=g['masks'],
                                  exps=g['exps'])
     agent.update_params(batch)
@@ -47,7 +48,8 @@ def test_agent_ppo_update_matches_reference_golden(golden):
     assert int(st['step']) == 3 and st['exp_avg'].abs().sum() > 0
 
 
-def test_agent_ppo_minibatch_matches_reference_golden(golden):
+@pytest.mark.parametrize('gemm', ['ozaki', 'cublas'])
+def test_agent_ppo_minibatch_matches_reference_golden(golden, gemm):
     """agents/agent_ppo.py:24-43 mini-batch branch (BASELINE config 5): 2 epochs x 4 slices of <= 200 rows"""
     from egopose_b200.agent import AgentPPO
     from egopose_b200.trajbatch import TrajBatch
@@ -59,7 +61,7 @@ def test_agent_ppo_minibatch_matches_reference_golden(golden):
     agent = AgentPPO(env=None, dtype=torch.float64, device=torch.device('cuda'), policy_net=pol, value_net=val,
                      optimizer_policy=opt_p, optimizer_value=opt_v, opt_num_epochs=int(m['epochs']), gamma=gamma, tau=tau,
                      clip_epsilon=clip, policy_grad_clip=[(list(pol.parameters()), max_norm)], use_mini_batch=True,
-                     opt_batch_size=int(m['opt_batch_size']))
+                     opt_batch_size=int(m['opt_batch_size']), gemm=gemm)
     batch = TrajBatch.from_numpy(states=g['states'], actions=g['actions'], rewards=g['rewards'], masks=g['masks'],
                                  exps=g['exps'])
     np.random.seed(int(m['seed']))
