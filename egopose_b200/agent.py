@@ -362,6 +362,7 @@ class AgentPG(Agent):
         # 'cublas' = cuBLAS DGEMM.  Nets whose input is produced by a learned context net always use cuBLAS.
         self.gemm = gemm or os.environ.get('EGP_GEMM', 'ozaki')
         self.oz_slices = int(oz_slices or os.environ.get('EGP_OZ_SLICES', 6))
+        self.oz_chunk_waves = int(os.environ.get('EGP_OZ_CHUNK_WAVES', 8))
         if self.gemm not in ('ozaki', 'cublas'):
             raise lib.EgpError("gemm must be 'ozaki' or 'cublas'")
         self._ozs = {}
@@ -429,15 +430,19 @@ class AgentPG(Agent):
         if self.gemm != 'ozaki' or inp.learned:
             return None
         dims = tuple(int(v) for v in trunk.dims())
-        oz = self._ozs.get(dims)
+        # rows per chunk: 8 waves of one 128-row tile per SM (per-kernel fixed costs amortised), less for small batches
+        base = lib.load().egp_oz_mlp_chunk_rows()
+        n = inp.x_const.shape[0]
+        chunk = int(min(self.oz_chunk_waves, -(-n // base)) * base)
+        oz = self._ozs.get(dims + (chunk,))
         if oz is None:
-            oz = lib.OzMlp(*dims, n_slices=self.oz_slices, device=trunk.W(0).device)
-            self._ozs[dims] = oz
+            oz = lib.OzMlp(*dims, n_slices=self.oz_slices, chunk_rows=chunk, device=trunk.W(0).device)
+            self._ozs[dims + (chunk,)] = oz
         return oz
 
     def _xcache(self, oz, x):
         """input-slice cache of one constant input tensor for the current update (shared by nets with the same input)"""
-        key = (x.data_ptr(), x.shape[0], x.shape[1])
+        key = (x.data_ptr(), x.shape[0], x.shape[1], oz.chunk, oz.S)
         ent = self._xcaches.get(key)
         if ent is None:
             # reuse an allocation of the same size from an earlier update

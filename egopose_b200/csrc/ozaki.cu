@@ -147,13 +147,21 @@ oz_slice_rows_kernel(const double *__restrict__ x, long long M, int K, long long
         }
     }
     if (colmax) {
+        // block-level maximum first (all warps own the same columns), then one atomic per column and block
+        // (only the exponent of the maximum is consumed: the high words, monotonic for non-negative doubles, suffice)
+        __shared__ uint32_t red[8][P * 128];
+        const int w = threadIdx.x >> 5;
 #pragma unroll
         for (int p = 0; p < P; p++)
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int k = (lane + 32 * p) * 4 + j;
-                if (k < K && cmax[p][j] > 0.0) atomicMax(colmax + k, (unsigned long long)__double_as_longlong(cmax[p][j]));
-            }
+            for (int j = 0; j < 4; j++) red[w][(lane + 32 * p) * 4 + j] = (uint32_t)__double2hiint(cmax[p][j]);
+        __syncthreads();
+        for (int k = threadIdx.x; k < K; k += blockDim.x) {
+            uint32_t m = red[0][k];
+#pragma unroll
+            for (int i = 1; i < 8; i++) m = max(m, red[i][k]);
+            if (m > 0u) atomicMax(colmax + k, (unsigned long long)m << 32);
+        }
     }
 }
 
@@ -792,7 +800,7 @@ oz_splitk_reduce_kernel(const double *__restrict__ part, int splits, long long M
 template <int S>
 static int launch_slice_rows(const double *x, long long m, int k, long long ldx, int8_t *out, int kp, int32_t *exps,
                              unsigned long long *colmax, cudaStream_t st) {
-    long long warps = m < (long long)num_sms() * 64 ? m : (long long)num_sms() * 64;
+    long long warps = m < (long long)num_sms() * 32 ? m : (long long)num_sms() * 32;
     int blocks = (int)((warps * 32 + 255) / 256);
     const int P = (kp + 127) / 128;
     if (P <= 1) oz_slice_rows_kernel<S, 1><<<blocks, 256, 0, st>>>(x, m, k, ldx, out, kp, exps, colmax);
