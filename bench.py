@@ -58,6 +58,14 @@ def peaks():
     return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
+def tensor_peak():
+    """dense bf16 TFLOP/s measured on this pool (burst, for a kernel timed alone); int8 tcgen05 runs at twice that rate"""
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        return json.load(open(p)).get('bf16_tflops', 1590.0), 'measured (MEASURED_PEAKS.json)'
+    return 1590.0, 'fallback (B200_PROFILING.md)'
+
+
 class ClockSampler:
     """samples nvidia-smi clocks / throttle reasons during the timed region"""
 
@@ -344,13 +352,49 @@ def main():
                             'traffic': 63.36e6 if default_cfg else None},
              'update_dgemm': {'bound': 'tensor(fp64)', 'achieved': None, 'peak': fp64_peak, 'unit': 'TFLOP/s'},
              'rollout_env_substeps_per_s': N * 15 / (roll_ms / 1e3)}
+    # the update's dominant kernel alone: [N, 243] x [300, 243]^T float64 product on the int8 tensor cores (first policy /
+    # value layer), operands 1.9 GB + output 2.9 GB > L2.  Algorithmic int8 work = 2 M N K x S (S + 1) / 2 slice pairs.
+    if agent.gemm == 'ozaki':
+        try:
+            S_oz = agent.oz_slices
+            xg = torch.randn(N, 243, dtype=torch.float64, device=device)
+            wg = torch.randn(args.hidden[0], 243, dtype=torch.float64, device=device) / 16
+            a_sl, a_ex = lib.oz_slice_rows(xg, S_oz)
+            b_sl, b_ex = lib.oz_slice_rows(wg, S_oz)
+            og = torch.empty(N, args.hidden[0], dtype=torch.float64, device=device)
+            for _ in range(3):
+                lib.oz_gemm(a_sl, a_ex, b_sl, b_ex, out=og)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(5):
+                lib.oz_gemm(a_sl, a_ex, b_sl, b_ex, out=og)
+            b.record()
+            b.synchronize()
+            g_ms = a.elapsed_time(b) / 5
+            pairs = S_oz * (S_oz + 1) // 2
+            tops = 2.0 * N * args.hidden[0] * 243 * pairs / (g_ms / 1e3) / 1e12
+            tp, tp_src = tensor_peak()
+            extra['oz_gemm_kernel'] = {'kernel': 'oz_gemm_kernel<%d,80>' % S_oz, 'bound': 'tensor', 'achieved': tops, 'peak': 2 * tp,
+                                       'unit': 'TOP/s (int8)', 'frac': tops / (2 * tp), 'ms': g_ms,
+                                       'peak_source': '2 x dense bf16 ' + tp_src + ' (kind::i8 issues at twice the bf16 rate)',
+                                       'f64_equivalent_tflops': 2.0 * N * args.hidden[0] * 243 / (g_ms / 1e3) / 1e12,
+                                       'slices': S_oz, 'slice_pairs': pairs,
+                                       'traffic': 4.79e9 if default_cfg and S_oz == 6 else None,
+                                       'note': 'unpadded algorithmic work; the tiles pad N 300->320 and K 243->256'}
+            del xg, wg, a_sl, b_sl, og
+        except Exception as exc:        # the headline numbers above do not depend on this probe
+            extra['oz_gemm_kernel'] = {'error': str(exc)}
     D_in, H1, H2, A_out = 243, args.hidden[0], args.hidden[1], 52
     fwd = lambda o: 2 * N * (D_in * H1 + H1 * H2 + H2 * o)                       # noqa: E731
     bwd = lambda o: 2 * N * (2 * H2 * o + 2 * H1 * H2 + D_in * H1)               # noqa: E731  (no dL/dx of layer 1)
-    upd_flops = args.epochs * (fwd(A_out) + fwd(1) + bwd(A_out) + bwd(1))        # epoch 0 reuses the initial forwards
+    upd_flops = args.epochs * (fwd(A_out) + fwd(1) + bwd(A_out) + bwd(1))        # the two initial forwards are not counted
     extra['update_dgemm']['achieved'] = upd_flops / (ms_upd / 1e3) / 1e12
     extra['update_dgemm']['frac'] = extra['update_dgemm']['achieved'] / fp64_peak if fp64_peak else None
-    extra['update_dgemm']['note'] = 'cuBLAS d884 DGEMMs + fused elementwise kernels; whole update phase incl. loss/Adam'
+    extra['update_dgemm']['backend'] = agent.gemm
+    extra['update_dgemm']['note'] = ('float64 dense layers on the int8 tensor cores (Ozaki scheme, %d slices): useful float64 FLOPs of the '
+                                     'whole update phase incl. slicing / loss / Adam, against the cuBLAS DGEMM peak' % agent.oz_slices
+                                     if agent.gemm == 'ozaki' else
+                                     'cuBLAS d884 DGEMMs + fused elementwise kernels; whole update phase incl. loss/Adam')
 
     # ---- e2e through the public API with host trajbatches
     e2e = None
@@ -384,6 +428,9 @@ def main():
                 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
                 'config': {'workload': WORKLOAD, 'envs_per_gpu': E, 'horizon': T, 'hidden': args.hidden,
                            'epochs': args.epochs, 'parallelism': 'env-sharded dp%d' % world,
+                           'update_gemm': ('float64 in/out on int8 tcgen05 (Ozaki, %d slices, error <= %.0e of row x column maxima)'
+                                           % (agent.oz_slices, (agent.oz_slices + 2) * 2.0 ** (-7 * agent.oz_slices))
+                                           if agent.gemm == 'ozaki' else 'cuBLAS DGEMM'),
                            'l2': 'inputs larger than L2 (trajbatch %.1f GB per step)' % (N * (2 * 115 + 52) * 8 / 1e9)},
                 'ms_rollout': ms_roll, 'ms_update': ms_upd, 'gpu_launches': launches, 'clocks': clocks,
                 'roofline': roofline, 'roofline_extra': extra, 'e2e': e2e, 'cpu_baseline': cpu,
