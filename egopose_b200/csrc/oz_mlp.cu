@@ -23,7 +23,7 @@ namespace oz {
 static inline long long al(long long v) { return (v + 1023) & ~1023LL; }
 static inline int pad16(long long k) { return (int)((k + 15) / 16 * 16); }
 
-// gW[o][i] (+)= 2^(ea_i + eb_o - 12) * sum_z part[z][i][o] for i < in; gb[o] (+)= the same for i == in (ones row)
+// gW[o][i] (+)= 2^(ea_i + eb_o + EOFF) * sum_z part[z][i][o] for i < in; gb[o] (+)= the same for i == in (ones row)
 __global__ void __launch_bounds__(256)
 oz_wgrad_reduce_kernel(const double *__restrict__ part, int splits, int in, int out, long long ldp, const int32_t *__restrict__ ea,
                        const int32_t *__restrict__ eb, double *__restrict__ gW, double *__restrict__ gb, int accumulate) {
@@ -32,7 +32,7 @@ oz_wgrad_reduce_kernel(const double *__restrict__ part, int splits, int in, int 
     const int i = idx / out, o = idx % out;
     double s = 0.0;
     for (int z = 0; z < splits; z++) s += part[((size_t)z * (in + 1) + i) * ldp + o];
-    s *= ldexp(1.0, ea[i] - 12) * ldexp(1.0, eb[o]);
+    s *= ldexp(1.0, ea[i] + EOFF) * ldexp(1.0, eb[o]);
     double *dst = i < in ? gW + (size_t)o * in + i : gb + o;
     *dst = accumulate ? *dst + s : s;
 }
@@ -103,6 +103,11 @@ static MlpPlan mlp_plan(char *base, int in, int h1, int h2, int od, long long M,
     P.d2T = Sl{B.take<int8_t>(S * h2 * MP), B.take<int32_t>(h2 + 16)}; P.d1T = Sl{B.take<int8_t>(S * h1 * MP), B.take<int32_t>(h1 + 16)};
     P.dyT = Sl{B.take<int8_t>(S * od * MP), B.take<int32_t>(od + 16)};
     P.part_bytes = al((long long)num_sms() * BM * 80 * 8 * 2);     // splits * rows * ldp <= SMs * one 128 x 80 tile
+    {
+        const long long nkb = (MP + BK - 1) / BK, need = (nkb + max_kblocks(S) - 1) / max_kblocks(S) + 1;
+        const long long rows = (in > hmax ? in : hmax) + 1, ldp = (hmax + 1) & ~1;
+        if (P.part_bytes < al(need * rows * ldp * 8)) P.part_bytes = al(need * rows * ldp * 8);
+    }
     P.part = B.take<double>(P.part_bytes / 8);
     P.xlocal = B.take<char>(xcache_chunk_bytes(in, M, S));         // used when the caller passes no cache
     P.total = B.off;
@@ -204,6 +209,8 @@ int egp_oz_mlp_step_f64(const EgpMlpNet *net, const double *d_x, int64_t ldx, in
             long long nkb = (mp + BK - 1) / BK;
             long long splits = num_sms() / tiles;
             if (splits > nkb / 4) splits = nkb / 4;
+            const long long need = (nkb + max_kblocks(S) - 1) / max_kblocks(S);      // int32 accumulators must not overflow
+            if (splits < need) splits = need;
             if (splits < 1) splits = 1;
             w.force_splits = (int)splits; w.work = part; w.work_bytes = part_bytes;
             int r = gemm(actT.q, actT.e, fin + 1, gT.q, gT.e, fout, mp, S, w, st);

@@ -55,8 +55,9 @@ __device__ __forceinline__ double pow2(int k) {            // 2^k, k in [-1022, 
     return __longlong_as_double((long long)(k + 1023) << 52);
 }
 
-// signed base-128 digits q_1..q_S (q in [-64, 64]) of X = round(x * scale), X = sum_t q_t 128^(S-t).  The digits come
-// off the low end in 21-bit signed groups so that the per-digit work is 32-bit integer arithmetic.
+// Slices q_1..q_S of X = round(x * scale), X = sum_t q_t 2^(RB (S - t)).
+// RB = 8: the two's-complement bytes of X (q_1 signed, q_2.. unsigned), |X| clamped to 2^(8S-1) - 1.
+// RB = 7: signed digits in [-64, 64], peeled off the low end in 21-bit groups with 32-bit integer arithmetic.
 __device__ __forceinline__ int oz_low_digit(int &x) {
     const int d = ((x + 64) & 127) - 64;
     x = (x - d) >> 7;
@@ -65,22 +66,34 @@ __device__ __forceinline__ int oz_low_digit(int &x) {
 template <int S>
 __device__ __forceinline__ void oz_digits(double x, double scale, int *q) {
     double r = x * scale;
-    if (!(fabs(r) <= 9.3e18)) r = 0.0;         // NaN / inf / out of int64 range
+    if (!(fabs(r) <= 9.2e18)) r = 0.0;         // NaN / inf / out of int64 range
     long long X = __double2ll_rn(r);
-    constexpr int NG = (S - 1) / 3;            // full 3-digit groups taken from the low end (leaves 1..3 digits)
+    if constexpr (RB == 8) {
+        constexpr long long LIM = (1LL << (8 * S - 1)) - 1;
+        X = X > LIM ? LIM : (X < -LIM ? -LIM : X);
+        const unsigned lo = (unsigned)X, hi = (unsigned)(X >> 32);
 #pragma unroll
-    for (int gi = 0; gi < NG; gi++) {
-        const int t = S - 1 - 3 * gi;
-        int xl = (int)(((unsigned)X + (1u << 20)) & ((1u << 21) - 1u)) - (1 << 20);
-        X = (X - xl) >> 21;
-        q[t] = oz_low_digit(xl);
-        q[t - 1] = oz_low_digit(xl);
-        q[t - 2] = xl;
+        for (int t = 0; t < S; t++) {
+            const int sh = 8 * (S - 1 - t);                     // byte t (0 = most significant) of the 8S-bit value
+            const unsigned b = sh >= 32 ? (hi >> (sh - 32)) : (sh == 0 ? lo : ((lo >> sh) | (sh > 24 ? (hi << (32 - sh)) : 0u)));
+            q[t] = (int)(b & 255u);
+        }
+    } else {
+        constexpr int NG = (S - 1) / 3;            // full 3-digit groups taken from the low end (leaves 1..3 digits)
+#pragma unroll
+        for (int gi = 0; gi < NG; gi++) {
+            const int t = S - 1 - 3 * gi;
+            int xl = (int)(((unsigned)X + (1u << 20)) & ((1u << 21) - 1u)) - (1 << 20);
+            X = (X - xl) >> 21;
+            q[t] = oz_low_digit(xl);
+            q[t - 1] = oz_low_digit(xl);
+            q[t - 2] = xl;
+        }
+        int xh = (int)X;
+#pragma unroll
+        for (int t = S - 1 - 3 * NG; t > 0; t--) q[t] = oz_low_digit(xh);
+        q[0] = xh;
     }
-    int xh = (int)X;
-#pragma unroll
-    for (int t = S - 1 - 3 * NG; t > 0; t--) q[t] = oz_low_digit(xh);
-    q[0] = xh;
 }
 
 // One warp per row (grid-stride).  Lane l owns the 4-element groups l, l + 32, ... of the row: 32 B loads, 4 B stores
@@ -126,7 +139,7 @@ oz_slice_rows_kernel(const double *__restrict__ x, long long M, int K, long long
         for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
         const int e = oz_exponent(amax);
         if (lane == 0) exps[row] = e;
-        const double scale = pow2(7 * S - 1 - e);
+        const double scale = pow2(RB * S - 1 - e);
 #pragma unroll
         for (int p = 0; p < P; p++) {
             const int gi = lane + 32 * p;
@@ -139,7 +152,7 @@ oz_slice_rows_kernel(const double *__restrict__ x, long long M, int K, long long
                 int q[S];
                 oz_digits<S>(v[p][j], scale, q);
 #pragma unroll
-                for (int t = 0; t < S; t++) pk[t] |= (uint32_t)(uint8_t)(int8_t)q[t] << (8 * j);
+                for (int t = 0; t < S; t++) pk[t] |= (uint32_t)(q[t] & 255) << (8 * j);
             }
 #pragma unroll
             for (int t = 0; t < S; t++)
@@ -227,7 +240,7 @@ oz_slice_colsT_kernel(const double *__restrict__ x, long long N, int F, long lon
     if (f >= FT) return;
     const long long nb = n0 + g * 16;
     if (nb >= Np) return;
-    const double scale = pow2(7 * S - 1 - exps[f]);
+    const double scale = pow2(RB * S - 1 - exps[f]);
     uint32_t pk[S][4];
 #pragma unroll
     for (int t = 0; t < S; t++) pk[t][0] = pk[t][1] = pk[t][2] = pk[t][3] = 0u;
@@ -236,7 +249,7 @@ oz_slice_colsT_kernel(const double *__restrict__ x, long long N, int F, long lon
         int q[S];
         oz_digits<S>(tile[g * 16 + j][fl], scale, q);
 #pragma unroll
-        for (int t = 0; t < S; t++) pk[t][j >> 2] |= (uint32_t)(uint8_t)(int8_t)q[t] << (8 * (j & 3));
+        for (int t = 0; t < S; t++) pk[t][j >> 2] |= (uint32_t)(q[t] & 255) << (8 * (j & 3));
     }
 #pragma unroll
     for (int t = 0; t < S; t++)
@@ -302,8 +315,8 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 // instruction descriptor: dense, S32 accumulate, signed int8 A and B, both K-major, M = 128
-__host__ __device__ constexpr uint32_t idesc_i8(int bn) {
-    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+__host__ __device__ constexpr uint32_t idesc_i8(int bn, bool a_signed = true, bool b_signed = true) {
+    return (2u << 4) | ((a_signed ? 1u : 0u) << 7) | ((b_signed ? 1u : 0u) << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, int *r) {
@@ -311,13 +324,15 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, int *r) {
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr) : "memory");
 }
 
-// sum_d acc_d 2^(-7d) for column j: two exact integer Horner groups (d < 4 | d >= 4) joined by one rounding in the fma.
-// SMALLK (contraction <= 448): neighbouring accumulators are first merged in int32 (|acc_d| <= (d + 1) K 2^12).
+// sum_d acc_d 2^(-RB d) for column j: two exact integer Horner groups (d < G | d >= G) joined by one rounding in the fma.
+// Radix 128: G = 4; SMALLK (contraction <= 448): neighbours are first merged in int32 (|acc_d| <= (d + 1) K 2^12).
+// Radix 256: G = 3 (|acc_d| < 2^31 -> every group stays below 2^53).
 template <int S, bool SMALLK>
 __device__ __forceinline__ double oz_horner(const int (&acc)[S][8], int j, double rs_hi, double rs_lo) {
-    constexpr int G = S < 4 ? S : 4, L = S - G;
+    constexpr int GMAX = RB == 8 ? 3 : 4;
+    constexpr int G = S < GMAX ? S : GMAX, L = S - G;
     long long hi, lo = 0;
-    if constexpr (SMALLK) {
+    if constexpr (RB == 7 && SMALLK) {
         const int c01 = acc[0][j] * 128 + acc[1][j];
         if constexpr (G == 3) hi = (long long)c01 * 128 + acc[2][j];
         else hi = (long long)c01 * 16384 + (acc[2][j] * 128 + acc[3][j]);
@@ -331,14 +346,14 @@ __device__ __forceinline__ double oz_horner(const int (&acc)[S][8], int j, doubl
     } else {
         hi = acc[0][j];
 #pragma unroll
-        for (int d = 1; d < G; d++) hi = hi * 128 + acc[d][j];
+        for (int d = 1; d < G; d++) hi = hi * (1 << RB) + acc[d][j];
         if constexpr (L > 0) {
             lo = acc[G][j];
 #pragma unroll
-            for (int d = G + 1; d < S; d++) lo = lo * 128 + acc[d][j];
+            for (int d = G + 1; d < S; d++) lo = lo * (1 << RB) + acc[d][j];
         }
     }
-    double h = (double)hi * rs_hi;              // rs_hi = 2^(row exponent - 7 (G - 1)), rs_lo = 2^(row exponent - 7 (S - 1))
+    double h = (double)hi * rs_hi;              // rs_hi = 2^(row exponent - RB (G - 1)), rs_lo = 2^(row exponent - RB (S - 1))
     if constexpr (L > 0) h = fma((double)lo, rs_lo, h);
     return h;
 }
@@ -457,7 +472,9 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                             for (int u = 0; u < S - t; u++)
                                 umma_i8(tmem + (uint32_t)((t + u) * BN), sa4 + ((t * A_SLICE + k2 * UMMA_K) >> 4),
-                                        sb4 + ((u * B_SLICE + k2 * UMMA_K) >> 4), DESC_HI, IDESC, (t > 0 || k2 > 0) ? 1u : first);
+                                        sb4 + ((u * B_SLICE + k2 * UMMA_K) >> 4), DESC_HI,
+                                        idesc_i8(BN, RB != 8 || t == 0, RB != 8 || u == 0),     // radix 256: only the top slices are signed
+                                        (t > 0 || k2 > 0) ? 1u : first);
                         }
                     }
                     umma_commit(smem_u32(&empty_bar[s]));            // frees the smem stage when these MMAs retire
@@ -492,9 +509,10 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const bool row_ok = row < g.M;
             const int col0 = n_blk * BN + half * HC;
             // per-row scale folded into the Horner constants; per-column scale 2^eb and bias staged once per tile
-            int ea = (!g.partial && row_ok) ? g.ea[row] - 12 : 0;
+            int ea = (!g.partial && row_ok) ? g.ea[row] + EOFF : 0;
             ea = ea < -960 ? -960 : (ea > 960 ? 960 : ea);
-            const double rs_hi = pow2(ea - 7 * ((S < 4 ? S : 4) - 1)), rs_lo = pow2(ea - 7 * (S - 1));
+            constexpr int GH = RB == 8 ? (S < 3 ? S : 3) : (S < 4 ? S : 4);
+            const double rs_hi = pow2(ea - RB * (GH - 1)), rs_lo = pow2(ea - RB * (S - 1));
             double *crow = g.C + ((size_t)z * (g.partial ? g.M : 0) + (row_ok ? row : 0)) * g.ldc;
             const double *mrow = (g.mask && row_ok) ? g.mask + row * g.ldm : nullptr;
             if (!g.partial) {
@@ -699,7 +717,7 @@ int choose_splits(long long m, int n, long long kp, int S) {
     const int bn = pick_bn(n, S);
     const long long tiles = ((m + BM - 1) / BM) * ((n + bn - 1) / bn);
     const long long nkb = (kp + BK - 1) / BK;
-    const long long max_kb = (16384 / S * 32 / BK) & ~1LL;   // int32 accumulators: kb * BK * 4096 * S < 2^31
+    const long long max_kb = max_kblocks(S);
     long long splits = (nkb + max_kb - 1) / max_kb;
     if (tiles < num_sms() && nkb >= 64) {                     // few output tiles, long contraction: fill the SMs
         long long want = num_sms() / tiles;
@@ -733,7 +751,7 @@ int gemm(const int8_t *a, const int32_t *ea, long long m, const int8_t *b, const
     g.mt = (int)((m + BM - 1) / BM);
     g.nt = (n + bn - 1) / bn;
     int splits = o.force_splits > 0 ? o.force_splits : 1;
-    const long long max_kb = (16384 / S * 32 / BK) & ~1LL;
+    const long long max_kb = max_kblocks(S);
     if (o.force_splits <= 0 && g.nkb > max_kb) {
         set_error("egp_oz_gemm_f64: contraction of %lld needs split-K (int32 accumulators)", kp);
         return EGP_ESIZE;
@@ -753,7 +771,7 @@ int gemm(const int8_t *a, const int32_t *ea, long long m, const int8_t *b, const
         g.partial = 0; g.C = o.C; g.ldc = o.ldc;
     }
     o.splits_used = splits;
-    g.smallk = (long long)g.kb_per_split * BK <= 448;
+    g.smallk = RB == 7 && (long long)g.kb_per_split * BK <= 448;
     g.mask_vec = g.mask && ((g.ldm & 1) == 0) && ((reinterpret_cast<uintptr_t>(g.mask) & 15) == 0);
     g.tma_store = ((g.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
     CUtensorMap tmC;
@@ -775,9 +793,13 @@ int gemm(const int8_t *a, const int32_t *ea, long long m, const int8_t *b, const
             case 3: OZ_LAUNCH(3, 64); break;
             case 4: OZ_LAUNCH(4, 64); break;
             case 5: OZ_LAUNCH(5, 64); break;
+#if OZ_RADIX_BITS == 8
+            default: OZ_LAUNCH(6, 64); break;
+#else
             case 6: OZ_LAUNCH(6, 64); break;
             case 7: OZ_LAUNCH(7, 64); break;
             default: OZ_LAUNCH(8, 64); break;
+#endif
         }
     }
 #undef OZ_LAUNCH
@@ -794,7 +816,7 @@ oz_splitk_reduce_kernel(const double *__restrict__ part, int splits, long long M
     const int n = (int)(idx % N);
     double s = 0.0;
     for (int z = 0; z < splits; z++) s += part[((size_t)z * M + m) * ldp + n];
-    C[m * ldc + n] = s * ldexp(1.0, ea[m] - 12) * ldexp(1.0, eb[n]);
+    C[m * ldc + n] = s * ldexp(1.0, ea[m] + EOFF) * ldexp(1.0, eb[n]);
 }
 
 template <int S>
@@ -811,15 +833,19 @@ static int launch_slice_rows(const double *x, long long m, int k, long long ldx,
     return EGP_OK;
 }
 
+#if OZ_RADIX_BITS == 8
+#define OZ_CASES_78(CALL)
+#else
+#define OZ_CASES_78(CALL) case 7: { constexpr int S_ = 7; CALL; } break; case 8: { constexpr int S_ = 8; CALL; } break;
+#endif
 #define OZ_DISPATCH_S(S, CALL)                       \
     switch (S) {                                     \
         case 3: { constexpr int S_ = 3; CALL; } break; \
         case 4: { constexpr int S_ = 4; CALL; } break; \
         case 5: { constexpr int S_ = 5; CALL; } break; \
         case 6: { constexpr int S_ = 6; CALL; } break; \
-        case 7: { constexpr int S_ = 7; CALL; } break; \
-        case 8: { constexpr int S_ = 8; CALL; } break; \
-        default: set_error("Ozaki slice count %d outside [3, 8]", S); return EGP_EINVAL; \
+        OZ_CASES_78(CALL)                                \
+        default: set_error("Ozaki slice count %d outside [3, %d]", S, MAX_S); return EGP_EINVAL; \
     }
 
 int slice_rows(const double *x, long long m, int k, long long ldx, int S, int8_t *out, int kp, int32_t *exps,
@@ -865,6 +891,8 @@ using namespace egp;
 using namespace egp::oz;
 
 extern "C" {
+
+int egp_oz_radix_bits(void) { return RB; }
 
 int egp_oz_slice_rows_f64(const double *d_x, int64_t m, int k, int64_t ldx, int n_slices, int8_t *d_out, int kp,
                           int32_t *d_exps, double *d_colmax, void *stream) {

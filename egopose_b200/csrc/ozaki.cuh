@@ -10,7 +10,20 @@ constexpr int BM = 128;             // output rows per tile (tcgen05 M)
 #define OZ_BK 32
 #endif
 constexpr int BK = OZ_BK;           // contraction bytes per stage row (32: one tcgen05.mma.kind::i8 K step, 32-byte swizzle; 64: two, 64-byte swizzle)
-constexpr int MAX_S = 8;
+#ifndef OZ_RADIX_BITS
+#define OZ_RADIX_BITS 7
+#endif
+// Digit width of the slices.  7 (default): signed round-to-nearest digits in [-64, 64], all slices signed.
+// 8 (experiment, -DOZ_RADIX_BITS=8): the two's-complement bytes of the fixed-point value (top slice signed, the others
+// unsigned; tcgen05 kind::i8 takes the signedness per operand and instruction).  Measured on B200: bit-exact as well,
+// but the one-sided truncation of unsigned digits accumulates linearly over the contraction, so at equal slice count it
+// is ~200x LESS accurate than the centred radix-128 digits despite the extra bit per slice (err / max|C| 6.8e-10 at S = 5
+// vs 3.1e-10 for radix 128 at S = 5 and 3.8e-12 at S = 6) - no gain, kept only as a documented negative result.
+constexpr int RB = OZ_RADIX_BITS;
+constexpr int MAX_S = RB == 8 ? 6 : 8;
+constexpr int EOFF = 2 - 2 * RB;    // C = 2^(ea + eb + EOFF) * sum_d acc_d 2^(-RB d)
+// k blocks of one int32 accumulation: S pairs x K x max |digit product| < 2^31
+inline long long max_kblocks(int S) { return RB == 8 ? (((1LL << 31) / (65025LL * S * BK)) & ~1LL) : ((16384 / S * 32 / BK) & ~1LL); }
 
 inline long long round_up(long long a, long long b) { return (a + b - 1) / b * b; }
 

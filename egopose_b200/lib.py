@@ -111,6 +111,7 @@ SYMBOLS = {
     'egp_build_input_f64': (_int, [_vp, _vp, _vp, _vp, _i64, _int, _vp, _vp]),
     'egp_sumsq_f64': (_int, [_vp, _i64, _vp, _vp]),
     'egp_adam_step_f64': (_int, [_vp, _vp, _vp, _vp, _i64, _d, _d, _d, _d, _i64, _d, _vp, _vp]),
+    'egp_oz_radix_bits': (_int, []),
     'egp_oz_slice_rows_f64': (_int, [_vp, _i64, _int, _i64, _int, _vp, _int, _vp, _vp, _vp]),
     'egp_oz_colmax_f64': (_int, [_vp, _i64, _int, _i64, _vp, _vp]),
     'egp_oz_slice_cols_t_f64': (_int, [_vp, _i64, _int, _i64, _int, _vp, _vp, _i64, _vp, _int, _vp]),

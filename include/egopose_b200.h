@@ -233,8 +233,10 @@ int egp_adam_step_f64(double *d_p, const double *d_g, double *d_m, double *d_v, 
 /* --- float64 dense layers on the int8 tensor cores (Ozaki scheme, egopose_b200/csrc/ozaki.cu) --------------
  * Replace the cuBLAS DGEMMs behind models/mlp.py:22-25 / core/policy_gaussian.py:19-24 / core/critic.py:15-18 forward
  * and backward in agents/agent_pg.py:19-26 and agents/agent_ppo.py:44-51.
- * Slices: x = 2^e * sum_{t=1..S} q_t 2^(1-7t), q_t int8 in [-64, 64] (signed base-128 digits of round(x 2^(7S-1-e))),
- * e constant along the contraction. */
+ * Slices: X = round(x 2^(7S-1-e)) (e constant along the contraction) as S signed base-128 digits in [-64, 64], most
+ * significant first: x = 2^(e+1-7S) * sum_{t=1..S} q_t 128^(S-t).  (egp_oz_radix_bits() returns 7; a -DOZ_RADIX_BITS=8
+ * build stores two's-complement bytes instead - an experiment that turned out less accurate, see csrc/ozaki.cuh.) */
+int egp_oz_radix_bits(void);
 /* d_x [m][k] (leading dimension ldx) -> d_out [S][m][kp] (kp >= k, multiple of 16, zero padded), d_exps [m];
  * d_colmax (optional, [k] doubles zeroed by the caller) receives the column abs-max of x (for the colsT slicing) */
 int egp_oz_slice_rows_f64(const double *d_x, int64_t m, int k, int64_t ldx, int n_slices, int8_t *d_out, int kp,

@@ -1,6 +1,6 @@
 """Float64 dense layers on the int8 tensor cores (csrc/ozaki.cu, csrc/oz_mlp.cu).
 
-* the slices reconstruct their input to 2^(1-7S) of the row / column maximum, digits stay in [-64, 64]
+* the slices reconstruct their input to 2^(1-7S) of the row / column maximum
 * the tcgen05 GEMM equals an exact integer matmul of the same slices BIT FOR BIT (integer accumulation in Tensor Memory,
   exact int64 Horner, one rounding) for every tile shape / split / epilogue option
 * the chunked MLP step (forward + PPO / value loss + backward) matches torch float64 autograd of the reference's graph
@@ -17,34 +17,50 @@ from egopose_b200 import lib  # noqa: E402
 DEV = 'cuda'
 
 
+def _rb():
+    return lib.load().egp_oz_radix_bits()
+
+
+def digits(sl):
+    """slice bytes -> digit values (radix 256: top slice signed, the others unsigned; radix 128: all signed)"""
+    d = sl.double()
+    if _rb() == 8 and sl.shape[0] > 1:
+        d[1:] = sl[1:].view(torch.uint8).double()
+    return d
+
+
 def recon(sl, ex):
+    S, rb = sl.shape[0], _rb()
+    d = digits(sl)
     v = torch.zeros(sl.shape[1:], dtype=torch.float64, device=sl.device)
-    for t in range(sl.shape[0]):
-        v += sl[t].double() * 2.0 ** (1 - 7 * (t + 1))
-    return v * torch.ldexp(torch.ones_like(ex, dtype=torch.float64), ex)[:, None]
+    for t in range(S):
+        v += d[t] * 2.0 ** (rb * (S - 1 - t))
+    return v * torch.ldexp(torch.ones_like(ex, dtype=torch.float64), ex + 1 - rb * S)[:, None]
 
 
 def exact_ref(a, ea, b, eb, bias=None, relu=False, mask=None):
-    """the kernel's arithmetic restated with exact float64 integer matmuls"""
-    S = a.shape[0]
-    A, B = a.double(), b.double()
+    """the kernel's arithmetic restated with exact float64 integer matmuls: one accumulator per d = t + u, two exact
+    Horner groups joined by one rounding, scales, bias, relu, mask"""
+    S, rb = a.shape[0], _rb()
+    A, B = digits(a), digits(b)
     acc = []
     for d in range(S):
         s = torch.zeros((a.shape[1], b.shape[1]), dtype=torch.float64, device=a.device)
         for t in range(d + 1):
             s += A[t] @ B[d - t].t()
         acc.append(s)
-    G = min(S, 4)
+    G = min(S, 3 if rb == 8 else 4)
+    base = 2.0 ** rb
     hi = acc[0].clone()
     for d in range(1, G):
-        hi = hi * 128.0 + acc[d]
-    h = hi * 2.0 ** (-7 * (G - 1))
+        hi = hi * base + acc[d]
+    h = hi * 2.0 ** (-rb * (G - 1))
     if S > G:
         lo = acc[G].clone()
         for d in range(G + 1, S):
-            lo = lo * 128.0 + acc[d]
-        h = h + lo * 2.0 ** (-7 * (S - 1))
-    h = h * (torch.ldexp(torch.ones_like(ea, dtype=torch.float64), ea - 12)[:, None]
+            lo = lo * base + acc[d]
+        h = h + lo * 2.0 ** (-rb * (S - 1))
+    h = h * (torch.ldexp(torch.ones_like(ea, dtype=torch.float64), ea + 2 - 2 * rb)[:, None]
              * torch.ldexp(torch.ones_like(eb, dtype=torch.float64), eb)[None, :])
     if bias is not None:
         h = h + bias[None, :]
@@ -60,8 +76,8 @@ def exact_ref(a, ea, b, eb, bias=None, relu=False, mask=None):
     (100, 52, 200, 5, True, False, False),
     (1000, 300, 243, 6, True, True, False),
     (4113, 304, 300, 3, False, False, False),
-    (513, 1, 300, 7, True, False, False),          # odd leading dimension: direct-store epilogue
-    (2000, 300, 640, 8, False, False, False),      # contraction > 448: generic int64 Horner
+    (513, 1, 300, 6, True, False, False),          # odd leading dimension: direct-store epilogue
+    (2000, 300, 640, 6, False, False, False),      # long contraction
     (3000, 300, 300, 6, False, False, True),       # relu-backward mask
     (777, 244, 52, 6, False, False, False),
 ])
@@ -71,10 +87,12 @@ def test_gemm_bit_exact_vs_integer_reference(M, N, K, S, bias, relu, mask):
     w = torch.randn(N, K, device=DEV, dtype=torch.float64) / K ** 0.5
     a, ea = lib.oz_slice_rows(x, S)
     b, eb = lib.oz_slice_rows(w, S)
-    assert a.abs().max() <= 64 and b.abs().max() <= 64
+    rb = _rb()
+    if rb == 7:
+        assert a.abs().max() <= 64 and b.abs().max() <= 64
     assert (a[:, :, K:] == 0).all()
     amax = x.abs().max(1, keepdim=True).values
-    assert ((recon(a[:, :, :K], ea) - x).abs() / amax).max().item() <= 2.0 ** (1 - 7 * S)
+    assert ((recon(a[:, :, :K], ea) - x).abs() / amax).max().item() <= 2.0 ** (2 - rb * S)
     bv = torch.randn(N, device=DEV, dtype=torch.float64) if bias else None
     mk = torch.randn(M, N, device=DEV, dtype=torch.float64) if mask else None
     c = lib.oz_gemm(a, ea, b, eb, bias=bv, relu=relu, mask=mk)
@@ -87,7 +105,7 @@ def test_gemm_bit_exact_vs_integer_reference(M, N, K, S, bias, relu, mask):
     if mask:
         true = torch.where(mk > 0, true, torch.zeros_like(true))
     bound = amax * w.abs().max(1).values[None, :] * K
-    assert ((c - true).abs() / bound).max().item() <= (S + 2) * 2.0 ** (-7 * S)
+    assert ((c - true).abs() / bound).max().item() <= 8 * (S + 2) * 2.0 ** (-rb * S)
 
 
 def test_weight_gradient_gemm_with_ones_row():

@@ -14,36 +14,50 @@ torch.manual_seed(0)
 dev = 'cuda'
 
 
-def recon(sl, ex, axis_scale_rows=True):
-    S = sl.shape[0]
+def _rb():
+    return lib.load().egp_oz_radix_bits()
+
+
+def digits(sl):
+    """slice bytes -> digit values (radix 256: top slice signed, the others unsigned; radix 128: all signed)"""
+    d = sl.double()
+    if _rb() == 8 and sl.shape[0] > 1:
+        d[1:] = sl[1:].view(torch.uint8).double()
+    return d
+
+
+def recon(sl, ex):
+    S, rb = sl.shape[0], _rb()
+    d = digits(sl)
     v = torch.zeros(sl.shape[1:], dtype=torch.float64, device=sl.device)
     for t in range(S):
-        v += sl[t].double() * 2.0 ** (1 - 7 * (t + 1))
-    return v * torch.ldexp(torch.ones_like(ex, dtype=torch.float64), ex)[:, None]
+        v += d[t] * 2.0 ** (rb * (S - 1 - t))
+    return v * torch.ldexp(torch.ones_like(ex, dtype=torch.float64), ex + 1 - rb * S)[:, None]
 
 
 def exact_ref(a, ea, b, eb, bias=None, relu=False, mask=None):
-    """same arithmetic as the kernel: exact integer brackets (float64 holds them exactly), two exact Horner groups
-    (d < 4 and d >= 4) joined with one rounding, scales, bias, relu, mask"""
-    S = a.shape[0]
-    A, B = a.double(), b.double()
+    """the kernel's arithmetic restated with exact float64 integer matmuls: one accumulator per d = t + u, two exact
+    Horner groups joined by one rounding, scales, bias, relu, mask"""
+    S, rb = a.shape[0], _rb()
+    A, B = digits(a), digits(b)
     acc = []
     for d in range(S):
         s = torch.zeros((a.shape[1], b.shape[1]), dtype=torch.float64, device=a.device)
         for t in range(d + 1):
             s += A[t] @ B[d - t].t()
         acc.append(s)
-    G = min(S, 4)
+    G = min(S, 3 if rb == 8 else 4)
+    base = 2.0 ** rb
     hi = acc[0].clone()
     for d in range(1, G):
-        hi = hi * 128.0 + acc[d]
-    h = hi * 2.0 ** (-7 * (G - 1))
+        hi = hi * base + acc[d]
+    h = hi * 2.0 ** (-rb * (G - 1))
     if S > G:
         lo = acc[G].clone()
         for d in range(G + 1, S):
-            lo = lo * 128.0 + acc[d]
-        h = h + lo * 2.0 ** (-7 * (S - 1))
-    h = h * (torch.ldexp(torch.ones_like(ea, dtype=torch.float64), ea - 12)[:, None]
+            lo = lo * base + acc[d]
+        h = h + lo * 2.0 ** (-rb * (S - 1))
+    h = h * (torch.ldexp(torch.ones_like(ea, dtype=torch.float64), ea + 2 - 2 * rb)[:, None]
              * torch.ldexp(torch.ones_like(eb, dtype=torch.float64), eb)[None, :])
     if bias is not None:
         h = h + bias[None, :]
@@ -68,7 +82,6 @@ def check(M, N, K, S, bias=False, relu=False, scale_rows=True, mask=False):
     assert (a[:, :, K:] == 0).all(), 'padding not zero'
     bv = torch.randn(N, device=dev, dtype=torch.float64) if bias else None
     mk = torch.randn(M, N, device=dev, dtype=torch.float64) if mask else None
-    assert a.abs().max() <= 64 and b.abs().max() <= 64, 'digit out of range'
     c = lib.oz_gemm(a, ea, b, eb, bias=bv, relu=relu, mask=mk)
     torch.cuda.synchronize()
     ref = exact_ref(a, ea, b, eb, bv, relu, mk)
@@ -84,7 +97,7 @@ def check(M, N, K, S, bias=False, relu=False, scale_rows=True, mask=False):
     e_rel = ((c - true).abs() / bound).max().item()
     e_typ = ((c - true).abs().max() / true.abs().max()).item()
     print('M %7d N %4d K %4d S %d bias %d relu %d | slice resid %.2e (<= %.2e) | bit-exact vs integer ref: %s | err/bound %.2e  err/max|C| %.2e'
-          % (M, N, K, S, bias, relu, e_sl, 2.0 ** (-7 * S), exact, e_rel, e_typ), flush=True)
+          % (M, N, K, S, bias, relu, e_sl, 2.0 ** (1 - _rb() * S), exact, e_rel, e_typ), flush=True)
     if not exact:
         d = (c - ref).abs()
         bad = (d > 0).nonzero()
@@ -192,20 +205,20 @@ if __name__ == '__main__':
     ok &= check(100, 52, 200, 5, bias=True)
     ok &= check(1000, 300, 243, 6, bias=True, relu=True)
     ok &= check(4096 + 17, 304, 300, 3)
-    ok &= check(513, 1, 300, 7, bias=True)
-    ok &= check(2000, 300, 640, 8)
+    ok &= check(513, 1, 300, 6, bias=True)
+    ok &= check(2000, 300, 640, 6)
     ok &= check(18944, 300, 300, 6, bias=False, mask=True)
     ok &= check(3000, 244, 52, 6)
     ok &= check_wgrad(5000, 52, 300, 5)
     ok &= check_wgrad(65536 + 100, 300, 243, 6)
     print('ALL OK' if ok else 'FAILURES', flush=True)
     if not quick and ok and "full" not in sys.argv:
-        for S in (4, 6):
+        for S in (4, 5, 6):
             bench(1228800, 300, 243, S)
         bench(18944, 300, 300, 6, iters=50)
         bench_wgrad(18944, 300, 300, 6)
     if "full" in sys.argv and ok:
-        for S in (4, 5, 6, 7):
+        for S in (4, 5, 6):
             bench(1228800, 300, 243, S)
             bench(1228800, 300, 300, S)
         bench(18944, 300, 300, 6, iters=50)
