@@ -138,7 +138,7 @@ def _weights(dims, seed):
     return [(torch.randn(s, generator=g, dtype=torch.float64) * (0.3 if len(s) == 1 else 1.0 / s[-1] ** 0.5)).to(DEV) for s in shapes]
 
 
-@pytest.mark.parametrize('n,chunk', [(1000, 256), (300, 1024), (2500, 1024)])
+@pytest.mark.parametrize('n,chunk', [(1000, 256), (300, 1024), (2500, 1024), (5, 128), (129, 128)])
 def test_mlp_step_value_loss_matches_autograd(n, chunk):
     dims = (40, 64, 48, 1)
     W = _weights(dims, 1)
