@@ -3,7 +3,7 @@
 // The PPO update (agents/agent_pg.py:19-26, agents/agent_ppo.py:44-51) is dominated by the GEMMs of the two MLPs
 // (models/mlp.py:22-25, core/policy_gaussian.py:19-24, core/critic.py:15-18) over the whole trajbatch in float64
 // (ego_pose/ego_mimic.py:31-32).  tcgen05 has no FP64 kind, so the product is evaluated with the Ozaki scheme on the
-// int8 tensor cores (B200 has them, 2x the bf16 rate):
+// int8 tensor cores (B200 has them, 2x the bf16 rate).  With the default radix (ozaki.cuh: RB = 7):
 //
 //   row i of A:   a_ik = 2^ea_i * sum_{t=1..S} qa_t[i][k] 2^(1-7t),  qa_t in [-64, 64]  (int8 "slices": the signed
 //   row j of B:   b_jk = 2^eb_j * sum_{u=1..S} qb_u[j][k] 2^(1-7u)    base-128 digits of round(a 2^(7S-1-e)))
@@ -21,12 +21,14 @@
 //                          GEMMs whose contraction runs over the samples); optional extra row of ones (bias gradient)
 //   oz_gemm_kernel         persistent warp-specialised tcgen05 GEMM, one CTA per SM looping over (split, m, n) tiles:
 //                          warp 0 TMA producer (3-D boxes {32 B, rows, S slices}, 32-byte swizzle) -> mbarrier ring that
-//                          runs ahead across tiles -> warp 1 single-thread tcgen05.mma.kind::i8 into S TMEM accumulators
+//                          runs ahead across tiles -> warp 1 (uniform loop, one elected lane) tcgen05.mma.kind::i8 into S TMEM
+//                          accumulators, A slice kept in the operand collector across the B slices it pairs with
 //                          -> 8 epilogue warps: tcgen05.ld, exact int64 Horner over d, one rounding to float64, scale,
 //                          bias, relu / relu-backward mask, store; TMEM is handed back to the MMA warp as soon as the
 //                          last accumulator chunk is in registers
 #include <cuda.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "ozaki.cuh"
@@ -289,16 +291,29 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 }
 // D[tmem] (+)= A[smem] * B[smem], int8 x int8 -> int32.  Shared-memory descriptors are passed as their low words (start
 // address >> 4, leading byte offset 1) plus the constant high word, so the issuing loop only does 32-bit uniform adds.
+// COLL: A-operand collector usage - 0 discard (default), 1 fill, 2 use, 3 lastuse: consecutive MMAs of one A slice with
+// different B slices keep A in the collector buffer instead of re-reading it from shared memory.
+template <int COLL>
 __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        ".reg .b64 da, db;\n\t"
-        "setp.ne.b32 p, %5, 0;\n\t"
-        "mov.b64 da, {%1, %3};\n\t"
-        "mov.b64 db, {%2, %3};\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %4, p;\n\t"
-        "}" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate) : "memory");
+#define OZ_MMA_ASM(Q)                                                                                     \
+    asm volatile(                                                                                         \
+        "{\n\t"                                                                                           \
+        ".reg .pred p;\n\t"                                                                               \
+        ".reg .b64 da, db;\n\t"                                                                           \
+        "setp.ne.b32 p, %5, 0;\n\t"                                                                       \
+        "mov.b64 da, {%1, %3};\n\t"                                                                       \
+        "mov.b64 db, {%2, %3};\n\t"                                                                       \
+        "tcgen05.mma.cta_group::1.kind::i8" Q " [%0], da, db, %4, p;\n\t"                                 \
+        "}" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate) : "memory")
+#ifdef OZ_NO_COLLECTOR
+    OZ_MMA_ASM("");
+#else
+    if constexpr (COLL == 1) OZ_MMA_ASM(".collector::a::fill");
+    else if constexpr (COLL == 2) OZ_MMA_ASM(".collector::a::use");
+    else if constexpr (COLL == 3) OZ_MMA_ASM(".collector::a::lastuse");
+    else OZ_MMA_ASM("");
+#endif
+#undef OZ_MMA_ASM
 }
 // K-major operand tile in the canonical swizzled layout that TMA writes: rows of BK bytes, 8-row groups of 8 BK bytes
 // (stride byte offset), descriptor version 1 (Blackwell), layout type 6 = SWIZZLE_32B / 4 = SWIZZLE_64B
@@ -470,11 +485,16 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                         for (int t = 0; t < S; t++) {
 #pragma unroll
-                            for (int u = 0; u < S - t; u++)
-                                umma_i8(tmem + (uint32_t)((t + u) * BN), sa4 + ((t * A_SLICE + k2 * UMMA_K) >> 4),
-                                        sb4 + ((u * B_SLICE + k2 * UMMA_K) >> 4), DESC_HI,
-                                        idesc_i8(BN, RB != 8 || t == 0, RB != 8 || u == 0),     // radix 256: only the top slices are signed
-                                        (t > 0 || k2 > 0) ? 1u : first);
+                            for (int u = 0; u < S - t; u++) {
+                                const uint32_t td = tmem + (uint32_t)((t + u) * BN), al = sa4 + ((t * A_SLICE + k2 * UMMA_K) >> 4),
+                                               bl = sb4 + ((u * B_SLICE + k2 * UMMA_K) >> 4), acc_flag = (t > 0 || k2 > 0) ? 1u : first;
+                                const uint32_t id = idesc_i8(BN, RB != 8 || t == 0, RB != 8 || u == 0);     // radix 256: only the top slices are signed
+                                const int n_u = S - t;
+                                if (n_u == 1) umma_i8<0>(td, al, bl, DESC_HI, id, acc_flag);
+                                else if (u == 0) umma_i8<1>(td, al, bl, DESC_HI, id, acc_flag);
+                                else if (u == n_u - 1) umma_i8<3>(td, al, bl, DESC_HI, id, acc_flag);
+                                else umma_i8<2>(td, al, bl, DESC_HI, id, acc_flag);
+                            }
                         }
                     }
                     umma_commit(smem_u32(&empty_bar[s]));            // frees the smem stage when these MMAs retire
@@ -704,6 +724,9 @@ static int launch_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUt
 static inline int pick_bn(int n, int S) {
     // N tile: 80 covers 300/301-wide layers in 4 tiles; 64 otherwise and whenever S * 80 exceeds the 512 TMEM columns
     if (S > 6) return 64;
+    static const char *force = getenv("EGP_OZ_BN");
+    if (force && atoi(force) == 64) return 64;
+    if (force && atoi(force) == 80) return 80;
     const int t64 = (n + 63) / 64, t80 = (n + 79) / 80;
     return (t80 * 80 <= t64 * 64 || t80 < t64) ? 80 : 64;
 }
