@@ -98,48 +98,115 @@ __device__ __forceinline__ void oz_digits(double x, double scale, int *q) {
     }
 }
 
+// Radix-128 fast path for four elements at once.  Adding C = sum_i 64 * 128^i to X turns the balanced digits into the plain
+// 7-bit fields of Y = X + C (digit_i = field_i - 64, carries resolved by the one 64-bit add), so every slice is a shift +
+// mask per element, a byte merge and one SWAR per-byte subtraction - no sequential digit peeling.
+template <int S>
+__device__ __forceinline__ void oz_y(double x, double scale, unsigned &lo, unsigned &hi) {
+    double r = x * scale;
+    if (!(fabs(r) <= 9.2e18)) r = 0.0;         // NaN / inf / out of int64 range
+    long long C = 0;
+#pragma unroll
+    for (int i = 0; i < S; i++) C = C * 128 + 64;
+    const long long Y = __double2ll_rn(r) + C;
+    lo = (unsigned)Y;
+    hi = (unsigned)(Y >> 32);
+}
+// packed int8 digits of slice t (0 = most significant) of four elements
+template <int S>
+__device__ __forceinline__ uint32_t oz_pack4(const unsigned (&lo)[4], const unsigned (&hi)[4], int t) {
+    const int sh = 7 * (S - 1 - t);
+    const unsigned mask = t == 0 ? 255u : 127u;               // the top field can reach 128 (digit +64)
+    unsigned f[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) f[j] = (sh >= 32 ? (hi[j] >> (sh - 32)) : __funnelshift_r(lo[j], hi[j], sh)) & mask;
+    const unsigned W = f[0] | (f[1] << 8) | (f[2] << 16) | (f[3] << 24);
+    const unsigned H = 0x80808080u, Cb = 0x40404040u;
+    return ((W | H) - Cb) ^ (~W & H);                         // per-byte W - 64 (two's complement bytes)
+}
+
 // One warp per row (grid-stride).  Lane l owns the 4-element groups l, l + 32, ... of the row: 32 B loads, 4 B stores
 // per slice (128 B per warp and slice).  Optionally accumulates the column abs-max of the matrix into colmax (bit
 // patterns of |x| >= 0 ordered like unsigned integers).
+// exponent from the high word of the row / column abs-max (monotonic for non-negative doubles): e with max / 2^e in
+// [0.5, 1); zero / subnormal rows get the floor -900 (their digits are zero), non-finite rows 0
+__device__ __forceinline__ int oz_exponent_hi(unsigned h) {
+    if (h >= 0x7ff00000u) return 0;
+    const int e = (int)(h >> 20) - 1022;
+    return e < -900 ? -900 : e;
+}
+
+__device__ __forceinline__ void cp_async_n(void *smem_dst, const void *gsrc, int bytes, bool valid) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    const int sz = valid ? bytes : 0;            // src-size 0: the destination bytes are zero-filled
+    if (bytes == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+
+// One warp per row (grid-stride), 4 warps per block.  The next row of a warp streams into the other half of its private
+// shared-memory double buffer with cp.async while the current one is sliced (every lane reads back exactly the bytes it
+// requested, so no barrier is involved).
+constexpr int ROWS_WARPS = 4;
 template <int S, int P>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(32 * ROWS_WARPS)
 oz_slice_rows_kernel(const double *__restrict__ x, long long M, int K, long long ldx, int8_t *__restrict__ out, int Kp,
                      int32_t *__restrict__ exps, unsigned long long *__restrict__ colmax) {
-    const int lane = threadIdx.x & 31;
-    const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-    const long long nwarp = ((long long)gridDim.x * blockDim.x) >> 5;
+    extern __shared__ __align__(16) double rows_smem[];             // [ROWS_WARPS][2][P * 128] doubles, then the reduction words
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const long long warp = (long long)blockIdx.x * ROWS_WARPS + w;
+    const long long nwarp = (long long)gridDim.x * ROWS_WARPS;
     const int ngroup = Kp / 4;
     const bool vec = ((ldx & 1) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
-    double cmax[P][4];
+    double *mybuf = rows_smem + (size_t)w * 2 * (P * 128);
+    unsigned cmax[P][4];                        // running column maxima as high words
 #pragma unroll
     for (int p = 0; p < P; p++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) cmax[p][j] = 0.0;
-    for (long long row = warp; row < M; row += nwarp) {
+        for (int j = 0; j < 4; j++) cmax[p][j] = 0u;
+    auto issue = [&](long long row, int buf) {
         const double *xr = x + row * ldx;
-        double v[P][4];
-        double amax = 0.0;
+        double *b = mybuf + buf * (P * 128);
 #pragma unroll
         for (int p = 0; p < P; p++) {
             const int k0 = (lane + 32 * p) * 4;
+            double *dst = b + k0;
             if (vec && k0 + 3 < K) {
-                const double2 a = *reinterpret_cast<const double2 *>(xr + k0);
-                const double2 b = *reinterpret_cast<const double2 *>(xr + k0 + 2);
-                v[p][0] = a.x; v[p][1] = a.y; v[p][2] = b.x; v[p][3] = b.y;
+                cp_async_n(dst, xr + k0, 16, true);
+                cp_async_n(dst + 2, xr + k0 + 2, 16, true);
             } else {
 #pragma unroll
-                for (int j = 0; j < 4; j++) v[p][j] = (k0 + j < K) ? xr[k0 + j] : 0.0;
-            }
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const double a = fabs(v[p][j]);
-                amax = fmax(amax, a);
-                cmax[p][j] = fmax(cmax[p][j], a);
+                for (int j = 0; j < 4; j++) cp_async_n(dst + j, k0 + j < K ? xr + k0 + j : x, 8, k0 + j < K);
             }
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (warp < M) issue(warp, 0);
+    int buf = 0;
+    for (long long row = warp; row < M; row += nwarp, buf ^= 1) {
+        if (row + nwarp < M) {
+            issue(row + nwarp, buf ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        const double *b = mybuf + buf * (P * 128);
+        double v[P][4];
+        unsigned hmax = 0u;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
-        const int e = oz_exponent(amax);
+        for (int p = 0; p < P; p++) {
+            const int k0 = (lane + 32 * p) * 4;
+            const double2 a0 = *reinterpret_cast<const double2 *>(b + k0);
+            const double2 a1 = *reinterpret_cast<const double2 *>(b + k0 + 2);
+            v[p][0] = a0.x; v[p][1] = a0.y; v[p][2] = a1.x; v[p][3] = a1.y;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const unsigned h = (unsigned)__double2hiint(v[p][j]) & 0x7fffffffu;
+                hmax = max(hmax, h);
+                cmax[p][j] = max(cmax[p][j], h);
+            }
+        }
+        hmax = __reduce_max_sync(0xffffffffu, hmax);
+        const int e = oz_exponent_hi(hmax);
         if (lane == 0) exps[row] = e;
         const double scale = pow2(RB * S - 1 - e);
 #pragma unroll
@@ -147,14 +214,22 @@ oz_slice_rows_kernel(const double *__restrict__ x, long long M, int K, long long
             const int gi = lane + 32 * p;
             if (gi >= ngroup) continue;
             uint32_t pk[S];
+            if constexpr (RB == 7) {
+                unsigned ylo[4], yhi[4];
 #pragma unroll
-            for (int t = 0; t < S; t++) pk[t] = 0u;
+                for (int j = 0; j < 4; j++) oz_y<S>(v[p][j], scale, ylo[j], yhi[j]);
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                int q[S];
-                oz_digits<S>(v[p][j], scale, q);
+                for (int t = 0; t < S; t++) pk[t] = oz_pack4<S>(ylo, yhi, t);
+            } else {
 #pragma unroll
-                for (int t = 0; t < S; t++) pk[t] |= (uint32_t)(q[t] & 255) << (8 * j);
+                for (int t = 0; t < S; t++) pk[t] = 0u;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    int q[S];
+                    oz_digits<S>(v[p][j], scale, q);
+#pragma unroll
+                    for (int t = 0; t < S; t++) pk[t] |= (uint32_t)(q[t] & 255) << (8 * j);
+                }
             }
 #pragma unroll
             for (int t = 0; t < S; t++)
@@ -163,18 +238,17 @@ oz_slice_rows_kernel(const double *__restrict__ x, long long M, int K, long long
     }
     if (colmax) {
         // block-level maximum first (all warps own the same columns), then one atomic per column and block
-        // (only the exponent of the maximum is consumed: the high words, monotonic for non-negative doubles, suffice)
-        __shared__ uint32_t red[8][P * 128];
-        const int w = threadIdx.x >> 5;
+        // (only the exponent of the maximum is consumed: the high words suffice)
+        uint32_t *red = reinterpret_cast<uint32_t *>(rows_smem + (size_t)ROWS_WARPS * 2 * (P * 128));
 #pragma unroll
         for (int p = 0; p < P; p++)
 #pragma unroll
-            for (int j = 0; j < 4; j++) red[w][(lane + 32 * p) * 4 + j] = (uint32_t)__double2hiint(cmax[p][j]);
+            for (int j = 0; j < 4; j++) red[w * (P * 128) + (lane + 32 * p) * 4 + j] = cmax[p][j];
         __syncthreads();
         for (int k = threadIdx.x; k < K; k += blockDim.x) {
-            uint32_t m = red[0][k];
+            uint32_t m = red[k];
 #pragma unroll
-            for (int i = 1; i < 8; i++) m = max(m, red[i][k]);
+            for (int i = 1; i < ROWS_WARPS; i++) m = max(m, red[i * (P * 128) + k]);
             if (m > 0u) atomicMax(colmax + k, (unsigned long long)m << 32);
         }
     }
@@ -213,49 +287,92 @@ __global__ void oz_col_exps_kernel(const unsigned long long *__restrict__ colmax
 // Transposed, column-scaled slices: x [N][F] -> out [S][F (+1)][Np].  Block tile = 128 samples x 32 features: coalesced
 // f64 reads along the features, shared-memory transpose, 16 B stores along the samples.  With ones_row the virtual
 // feature F is 1.0 for every valid sample (its products are the column sums = bias gradients).
+// Each block walks TPB consecutive 128-sample tiles of one 32-feature panel; the next tile streams into the other half of
+// a double buffer with cp.async (8 B per element, zero-filled outside the matrix) while the current one is sliced.
+constexpr int COLST_TPB = 4;
+
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc, bool valid) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    const int sz = valid ? 8 : 0;                // src-size 0: the 8 destination bytes are zero-filled
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+
 template <int S>
 __global__ void __launch_bounds__(256)
 oz_slice_colsT_kernel(const double *__restrict__ x, long long N, int F, long long ldx, const int32_t *__restrict__ exps,
                       int8_t *__restrict__ out, long long Np, int ones_row) {
-    __shared__ double tile[128][33];
-    const long long n0 = (long long)blockIdx.x * 128;
+    extern __shared__ __align__(16) double colst_tile[];           // [2][128][32], columns rotated by 2 per 16-row group
     const int f0 = blockIdx.y * 32;
     const int FT = F + (ones_row ? 1 : 0);
-    {
-        const int fl = threadIdx.x & 31, rl = threadIdx.x >> 5;       // 8 rows per pass
+    const long long ntile = (Np + 127) / 128;
+    const long long t0 = (long long)blockIdx.x * COLST_TPB;
+    const long long t1 = t0 + COLST_TPB < ntile ? t0 + COLST_TPB : ntile;
+    const int lfl = threadIdx.x & 31, lrl = threadIdx.x >> 5;       // loader: feature lane, 8 rows per pass
+    auto issue = [&](long long tile_idx, int buf) {
+        double *tb = colst_tile + buf * (128 * 32);
+        const long long n0 = tile_idx * 128;
+        const int f = f0 + lfl;
 #pragma unroll 4
-        for (int r = rl; r < 128; r += 8) {
+        for (int r = lrl; r < 128; r += 8) {
             const long long n = n0 + r;
-            const int f = f0 + fl;
-            double v = 0.0;
-            if (n < N) {
-                if (f < F) v = x[n * ldx + f];
-                else if (f == F && ones_row) v = 1.0;
-            }
-            tile[r][fl] = v;
+            double *dst = tb + r * 32 + ((lfl + 2 * (r >> 4)) & 31);
+            const bool ok = n < N && f < F;
+            cp_async8(dst, ok ? x + n * ldx + f : x, ok);
         }
-    }
-    __syncthreads();
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
     // thread -> (feature fl, group of 16 samples g): 32 x 8 = 256 threads
     const int g = threadIdx.x & 7, fl = threadIdx.x >> 3;
     const int f = f0 + fl;
-    if (f >= FT) return;
-    const long long nb = n0 + g * 16;
-    if (nb >= Np) return;
-    const double scale = pow2(RB * S - 1 - exps[f]);
-    uint32_t pk[S][4];
+    const int fc = (fl + 2 * g) & 31;
+    const double scale = f < FT ? pow2(RB * S - 1 - exps[f]) : 0.0;
+    const bool ones = ones_row && f == F;
+    if (t0 < t1) issue(t0, 0);
+    for (long long ti = t0; ti < t1; ti++) {
+        const int buf = (int)((ti - t0) & 1);
+        if (ti + 1 < t1) {
+            issue(ti + 1, buf ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        const double *tb = colst_tile + buf * (128 * 32);
+        const long long nb = ti * 128 + g * 16;
+        if (f < FT && nb < Np) {
+            uint32_t pk[S][4];
 #pragma unroll
-    for (int t = 0; t < S; t++) pk[t][0] = pk[t][1] = pk[t][2] = pk[t][3] = 0u;
+            for (int jq = 0; jq < 4; jq++) {
+                double v[4];
 #pragma unroll
-    for (int j = 0; j < 16; j++) {
-        int q[S];
-        oz_digits<S>(tile[g * 16 + j][fl], scale, q);
+                for (int j = 0; j < 4; j++) {
+                    v[j] = tb[(g * 16 + jq * 4 + j) * 32 + fc];
+                    if (ones) v[j] = (nb + jq * 4 + j < N) ? 1.0 : 0.0;
+                }
+                if constexpr (RB == 7) {
+                    unsigned ylo[4], yhi[4];
 #pragma unroll
-        for (int t = 0; t < S; t++) pk[t][j >> 2] |= (uint32_t)(q[t] & 255) << (8 * (j & 3));
+                    for (int j = 0; j < 4; j++) oz_y<S>(v[j], scale, ylo[j], yhi[j]);
+#pragma unroll
+                    for (int t = 0; t < S; t++) pk[t][jq] = oz_pack4<S>(ylo, yhi, t);
+                } else {
+#pragma unroll
+                    for (int t = 0; t < S; t++) pk[t][jq] = 0u;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        int q[S];
+                        oz_digits<S>(v[j], scale, q);
+#pragma unroll
+                        for (int t = 0; t < S; t++) pk[t][jq] |= (uint32_t)(q[t] & 255) << (8 * j);
+                    }
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < S; t++)
+                *reinterpret_cast<uint4 *>(out + ((size_t)t * FT + f) * Np + nb) = make_uint4(pk[t][0], pk[t][1], pk[t][2], pk[t][3]);
+        }
+        __syncthreads();                                            // the buffer is refilled two iterations later
     }
-#pragma unroll
-    for (int t = 0; t < S; t++)
-        *reinterpret_cast<uint4 *>(out + ((size_t)t * FT + f) * Np + nb) = make_uint4(pk[t][0], pk[t][1], pk[t][2], pk[t][3]);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -842,18 +959,32 @@ oz_splitk_reduce_kernel(const double *__restrict__ part, int splits, long long M
     C[m * ldc + n] = s * ldexp(1.0, ea[m] + EOFF) * ldexp(1.0, eb[n]);
 }
 
+template <int S, int P>
+static int launch_slice_rows_p(const double *x, long long m, int k, long long ldx, int8_t *out, int kp, int32_t *exps,
+                               unsigned long long *colmax, cudaStream_t st) {
+    const int smem = ROWS_WARPS * 2 * (P * 128) * 8 + ROWS_WARPS * (P * 128) * 4;
+    static int per_sm = 0;
+    if (!per_sm) {
+        EGP_CUDA(cudaFuncSetAttribute(oz_slice_rows_kernel<S, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        EGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, oz_slice_rows_kernel<S, P>, 32 * ROWS_WARPS, smem));
+        if (per_sm < 1) per_sm = 1;
+    }
+    long long blocks = (m + ROWS_WARPS - 1) / ROWS_WARPS;
+    const long long cap = (long long)num_sms() * per_sm;              // one resident wave, rows grid-strided over it
+    if (blocks > cap) blocks = cap;
+    oz_slice_rows_kernel<S, P><<<(unsigned)blocks, 32 * ROWS_WARPS, smem, st>>>(x, m, k, ldx, out, kp, exps, colmax);
+    EGP_CHECK_LAUNCH("oz_slice_rows_kernel");
+    return EGP_OK;
+}
+
 template <int S>
 static int launch_slice_rows(const double *x, long long m, int k, long long ldx, int8_t *out, int kp, int32_t *exps,
                              unsigned long long *colmax, cudaStream_t st) {
-    long long warps = m < (long long)num_sms() * 32 ? m : (long long)num_sms() * 32;
-    int blocks = (int)((warps * 32 + 255) / 256);
     const int P = (kp + 127) / 128;
-    if (P <= 1) oz_slice_rows_kernel<S, 1><<<blocks, 256, 0, st>>>(x, m, k, ldx, out, kp, exps, colmax);
-    else if (P == 2) oz_slice_rows_kernel<S, 2><<<blocks, 256, 0, st>>>(x, m, k, ldx, out, kp, exps, colmax);
-    else if (P == 3) oz_slice_rows_kernel<S, 3><<<blocks, 256, 0, st>>>(x, m, k, ldx, out, kp, exps, colmax);
-    else oz_slice_rows_kernel<S, 6><<<blocks, 256, 0, st>>>(x, m, k, ldx, out, kp, exps, colmax);
-    EGP_CHECK_LAUNCH("oz_slice_rows_kernel");
-    return EGP_OK;
+    if (P <= 1) return launch_slice_rows_p<S, 1>(x, m, k, ldx, out, kp, exps, colmax, st);
+    if (P == 2) return launch_slice_rows_p<S, 2>(x, m, k, ldx, out, kp, exps, colmax, st);
+    if (P == 3) return launch_slice_rows_p<S, 3>(x, m, k, ldx, out, kp, exps, colmax, st);
+    return launch_slice_rows_p<S, 6>(x, m, k, ldx, out, kp, exps, colmax, st);
 }
 
 #if OZ_RADIX_BITS == 8
@@ -893,6 +1024,18 @@ int col_absmax(const double *x, long long n, int f, long long ldx, unsigned long
     return EGP_OK;
 }
 
+template <int S>
+static int launch_colsT(dim3 grid, int smem, const double *x, long long n, int f, long long ldx, const int32_t *exps, int8_t *out,
+                        long long np, int ones_row, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        EGP_CUDA(cudaFuncSetAttribute(oz_slice_colsT_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr = true;
+    }
+    oz_slice_colsT_kernel<S><<<grid, 256, smem, st>>>(x, n, f, ldx, exps, out, np, ones_row);
+    return EGP_OK;
+}
+
 int slice_colsT(const double *x, long long n, int f, long long ldx, int S, const unsigned long long *colmax, int8_t *out,
                 long long np, int32_t *exps, int ones_row, cudaStream_t st) {
     if (!x || !out || !exps || !colmax || n < 1 || f < 1 || ldx < f || np < n || (np & 15)) {
@@ -901,8 +1044,12 @@ int slice_colsT(const double *x, long long n, int f, long long ldx, int S, const
     }
     const int ft = f + (ones_row ? 1 : 0);
     oz_col_exps_kernel<<<(ft + 127) / 128, 128, 0, st>>>(colmax, f, ones_row, exps);
-    dim3 grid((unsigned)((np + 127) / 128), (unsigned)((ft + 31) / 32));
-    OZ_DISPATCH_S(S, (oz_slice_colsT_kernel<S_><<<grid, 256, 0, st>>>(x, n, f, ldx, exps, out, np, ones_row)));
+    const long long ntile = (np + 127) / 128;
+    dim3 grid((unsigned)((ntile + COLST_TPB - 1) / COLST_TPB), (unsigned)((ft + 31) / 32));
+    const int smem = 2 * 128 * 32 * 8;
+    int rc = EGP_OK;
+    OZ_DISPATCH_S(S, rc = launch_colsT<S_>(grid, smem, x, n, f, ldx, exps, out, np, ones_row, st));
+    if (rc) return rc;
     EGP_CHECK_LAUNCH("oz_slice_colsT_kernel");
     return EGP_OK;
 }
