@@ -599,8 +599,14 @@ class OzMlp:
         nbytes = lib.egp_oz_mlp_work_bytes(*self.dims, self.chunk, self.S)
         self.work = torch.empty(nbytes, dtype=torch.uint8, device=device)
 
-    def launches_per_chunk(self, bwd):
-        return 36 if bwd else 7
+    @staticmethod
+    def launch_count(n_chunks, bwd, slice_x, fill_cache):
+        """kernels launched by one egp_oz_mlp_step_f64 call (csrc/oz_mlp.cu): weight slicing + per chunk the x slicing
+        (unless cached), 3 GEMMs + 2 row / 2 transposed slicings forward, loss, 5 GEMMs + 3 reductions + slicings backward"""
+        prep = 3 + (6 if bwd else 0)
+        x = (3 if (bwd or fill_cache) else 1) if slice_x else 0
+        per_chunk = x + (9 + 1 + 17 if bwd else 5)
+        return prep + n_chunks * per_chunk
 
     def new_cache(self, n):
         import torch
@@ -639,7 +645,7 @@ class OzMlp:
         check(load().egp_oz_mlp_step_f64(C.byref(net), ptr(x[:1]) if not x.is_contiguous() else ptr(x), x.stride(0), n, C.byref(ls),
                                          _raw(y), self.S, self.chunk, _raw(cache['buf']) if cache is not None else None, state,
                                          _raw(self.work), self.work.numel(), stream_ptr()), 'egp_oz_mlp_step_f64')
+        launches += self.launch_count((n + self.chunk - 1) // self.chunk, loss is not None, state != 2, state == 1)
         if cache is not None:
             cache['valid'] = True
-        launches += ((n + self.chunk - 1) // self.chunk) * self.launches_per_chunk(loss is not None) + 7
         return y
