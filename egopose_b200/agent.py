@@ -359,7 +359,7 @@ class AgentPG(Agent):
         self._nets = None
         self.last_info = {}
         # dense layers of the update: 'ozaki' = float64 on the int8 tensor cores (csrc/ozaki.cu, csrc/oz_mlp.cu),
-        # 'cublas' = cuBLAS DGEMM.  Nets whose input is produced by a learned context net always use cuBLAS.
+        # 'cublas' = cuBLAS DGEMM.
         self.gemm = gemm or os.environ.get('EGP_GEMM', 'ozaki')
         self.oz_slices = int(oz_slices or os.environ.get('EGP_OZ_SLICES', 6))
         self.oz_chunk_waves = int(os.environ.get('EGP_OZ_CHUNK_WAVES', 8))
@@ -426,13 +426,13 @@ class AgentPG(Agent):
 
     # ---- int8-tensor-core dense layers --------------------------------------------------------------
     def _oz(self, trunk, inp):
-        """OzMlp of a trunk when its input is a constant tensor and the ozaki backend is selected, else None"""
-        if self.gemm != 'ozaki' or inp.learned:
+        """OzMlp of a trunk when the ozaki backend is selected, else None"""
+        if self.gemm != 'ozaki':
             return None
         dims = tuple(int(v) for v in trunk.dims())
         # rows per chunk: 8 waves of one 128-row tile per SM (per-kernel fixed costs amortised), less for small batches
         base = lib.load().egp_oz_mlp_chunk_rows()
-        n = inp.x_const.shape[0]
+        n = (inp.xbuf if inp.learned else inp.x_const).shape[0]
         chunk = int(min(self.oz_chunk_waves, -(-n // base)) * base)
         oz = self._ozs.get(dims + (chunk,))
         if oz is None:
@@ -465,10 +465,14 @@ class AgentPG(Agent):
         oz = self._oz(self._vt, inp)
         for it in range(self.value_opt_niter):
             if oz is not None:
-                xt = inp.x_const
+                xt = inp.x() if inp.learned else inp.x_const
+                dx = self._vt._buf('dx', (xt.shape[0], inp.cd), xt) if inp.learned else None
                 self._scal[0:1].zero_()
-                oz.step(self._vt.weights(), xt, grads=self._vt.grads(), cache=self._xcache(oz, xt) if cache else None,
+                oz.step(self._vt.weights(), xt, grads=self._vt.grads(), dx=dx,
+                        cache=self._xcache(oz, xt) if (cache and not inp.learned) else None,
                         loss=dict(kind='value', returns=returns, inv_n=inv_n, loss=self._scal[0:1]))
+                if inp.learned:
+                    inp.backward(dx)
                 d = _dist()
                 if d is not None:
                     d.all_reduce(self._vf.grad)
@@ -500,8 +504,9 @@ class AgentPG(Agent):
             ent['live'] = False
         oz = self._oz(self._vt, xv)
         if oz is not None:
-            xt = xv.x_const
-            values = oz.step(self._vt.weights(), xt, y=self._vt._buf('y', (xt.shape[0], 1), xt), cache=self._xcache(oz, xt)).view(-1)
+            xt = xv.x(grad=False) if xv.learned else xv.x_const
+            values = oz.step(self._vt.weights(), xt, y=self._vt._buf('y', (xt.shape[0], 1), xt),
+                             cache=None if xv.learned else self._xcache(oz, xt)).view(-1)
             self._value_fresh = False
         else:
             values = self._vt.forward(xv.x(grad=False)).view(-1)
@@ -544,15 +549,19 @@ class AgentPPO(AgentPG):
         inp = xp if isinstance(xp, _NetInput) else _NetInput(x_const=xp)
         oz = self._oz(self._pt, inp)
         if oz is not None:
-            xt = inp.x_const
+            xt = inp.x() if inp.learned else inp.x_const
+            dx = self._pt._buf('dx', (xt.shape[0], inp.cd), xt) if inp.learned else None
             self._scal[1:2].zero_()
             dls = None
             if self._learn_std:
                 dls = self._pf.view(self._pf.grad, 'action_log_std').view(-1)
                 dls.zero_()
-            oz.step(self._pt.weights(), xt, grads=self._pt.grads(), cache=self._xcache(oz, xt) if cache else None,
+            oz.step(self._pt.weights(), xt, grads=self._pt.grads(), dx=dx,
+                    cache=self._xcache(oz, xt) if (cache and not inp.learned) else None,
                     loss=dict(kind='ppo', actions=actions, log_std=log_std, adv=adv, stats=self._stats, logp0=logp0, exps=exps,
                               clip_eps=self.clip_epsilon, inv_count=inv_count, dlogstd=dls, loss=self._scal[1:2]))
+            if inp.learned:
+                inp.backward(dx)
             if _dist() is not None:
                 _dist().all_reduce(self._pf.grad)
             self._pf.adam(max_norm)
@@ -620,8 +629,9 @@ class AgentPPO(AgentPG):
         log_std = self.policy_net.action_log_std.data.view(-1)
         oz = self._oz(self._pt, xp)
         if oz is not None:
-            xt = xp.x_const
-            mu = oz.step(self._pt.weights(), xt, y=self._pt._buf('y', (xt.shape[0], self._pt.dims()[3]), xt), cache=self._xcache(oz, xt))
+            xt = xp.x(grad=False) if xp.learned else xp.x_const
+            mu = oz.step(self._pt.weights(), xt, y=self._pt._buf('y', (xt.shape[0], self._pt.dims()[3]), xt),
+                         cache=None if xp.learned else self._xcache(oz, xt))
         else:
             mu = self._pt.forward(xp.x(grad=False))
         logp0 = lib.gauss_logp(mu, actions, log_std)                    # fixed_log_probs (:18-20)

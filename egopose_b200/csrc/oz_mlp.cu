@@ -75,7 +75,7 @@ int64_t egp_oz_mlp_xcache_bytes(int in_dim, int64_t n, int64_t chunk_rows, int n
 }
 
 struct MlpPlan {
-    Sl W1s, W2s, W3s, W3T, W2T, a1s, a2s, d2s, dys, a1T, a2T, d2T, d1T, dyT;
+    Sl W1s, W2s, W3s, W3T, W2T, a1s, a2s, d2s, dys, a1T, a2T, d2T, d1T, dyT, d1s, W1Tc;
     unsigned long long *cmax[8];
     double *a1, *a2, *d1, *d2, *ybuf, *dy, *part;
     long long part_bytes;
@@ -83,7 +83,7 @@ struct MlpPlan {
     long long total;
 };
 
-static MlpPlan mlp_plan(char *base, int in, int h1, int h2, int od, long long M, int S) {
+static MlpPlan mlp_plan(char *base, int in, int h1, int h2, int od, long long M, int S, int dx_cols = 0) {
     MlpPlan P;
     const long long MP = pad16(M);
     const int kin = pad16(in), kh1 = pad16(h1), kh2 = pad16(h2), kod = pad16(od);
@@ -102,6 +102,10 @@ static MlpPlan mlp_plan(char *base, int in, int h1, int h2, int od, long long M,
     P.a1T = Sl{B.take<int8_t>(S * (h1 + 1) * MP), B.take<int32_t>(h1 + 16)}; P.a2T = Sl{B.take<int8_t>(S * (h2 + 1) * MP), B.take<int32_t>(h2 + 16)};
     P.d2T = Sl{B.take<int8_t>(S * h2 * MP), B.take<int32_t>(h2 + 16)}; P.d1T = Sl{B.take<int8_t>(S * h1 * MP), B.take<int32_t>(h1 + 16)};
     P.dyT = Sl{B.take<int8_t>(S * od * MP), B.take<int32_t>(od + 16)};
+    if (dx_cols > 0) {              // data gradient of the first layer: row slices of dh1, W1[:, :dx_cols]^T slices
+        P.d1s = Sl{B.take<int8_t>(S * M * kh1), B.take<int32_t>(M)};
+        P.W1Tc = Sl{B.take<int8_t>((long long)S * dx_cols * kh1), B.take<int32_t>(dx_cols + 16)};
+    }
     P.part_bytes = al((long long)num_sms() * BM * 80 * 8 * 2);     // splits * rows * ldp <= SMs * one 128 x 80 tile
     {
         const long long nkb = (MP + BK - 1) / BK, need = (nkb + max_kblocks(S) - 1) / max_kblocks(S) + 1;
@@ -115,7 +119,7 @@ static MlpPlan mlp_plan(char *base, int in, int h1, int h2, int od, long long M,
 }
 
 int64_t egp_oz_mlp_work_bytes(int in_dim, int h1, int h2, int out_dim, int64_t chunk_rows, int n_slices) {
-    return mlp_plan(nullptr, in_dim, h1, h2, out_dim, chunk_rows, n_slices).total;
+    return mlp_plan(nullptr, in_dim, h1, h2, out_dim, chunk_rows, n_slices, in_dim).total;     // room for any dx_cols <= in_dim
 }
 
 /* One forward (+ loss + backward) pass of a two-hidden-layer relu MLP over x [n][in_dim] (leading dimension ldx).
@@ -133,7 +137,9 @@ int egp_oz_mlp_step_f64(const EgpMlpNet *net, const double *d_x, int64_t ldx, in
     const int in = net->in_dim, h1 = net->h1, h2 = net->h2, od = net->out_dim, S = n_slices;
     const bool bwd = loss->kind != 0;
     if (in < 1 || h1 < 1 || h2 < 1 || od < 1 || in > 768 || h1 > 768 || h2 > 768 || od > 768) { set_error("egp_oz_mlp_step_f64: layer widths must be in [1, 768]"); return EGP_ESIZE; }
-    if (work_bytes < egp_oz_mlp_work_bytes(in, h1, h2, od, chunk_rows, S)) { set_error("egp_oz_mlp_step_f64: workspace too small"); return EGP_EINVAL; }
+    const int dxc = (bwd && net->d_dx) ? net->dx_cols : 0;
+    if (dxc < 0 || dxc > in) { set_error("egp_oz_mlp_step_f64: dx_cols outside [0, in_dim]"); return EGP_EINVAL; }
+    if (work_bytes < mlp_plan(nullptr, in, h1, h2, od, chunk_rows, S, dxc).total) { set_error("egp_oz_mlp_step_f64: workspace too small"); return EGP_EINVAL; }
     if (bwd && (!net->d_gW1 || !net->d_gb1 || !net->d_gW2 || !net->d_gb2 || !net->d_gW3 || !net->d_gb3)) { set_error("egp_oz_mlp_step_f64: gradient pointers missing"); return EGP_EINVAL; }
     if (!bwd && !d_y) { set_error("egp_oz_mlp_step_f64: forward-only pass needs d_y"); return EGP_EINVAL; }
     if (xcache_state && !d_xcache) { set_error("egp_oz_mlp_step_f64: cache state without cache"); return EGP_EINVAL; }
@@ -141,9 +147,9 @@ int egp_oz_mlp_step_f64(const EgpMlpNet *net, const double *d_x, int64_t ldx, in
     const long long M = chunk_rows, MP = pad16(M);
     const int kin = pad16(in), kh1 = pad16(h1), kh2 = pad16(h2), kod = pad16(od);
     const int hmax = h1 > h2 ? h1 : h2;
-    const MlpPlan P = mlp_plan((char *)d_work, in, h1, h2, od, M, S);
+    const MlpPlan P = mlp_plan((char *)d_work, in, h1, h2, od, M, S, dxc);
     const Sl &W1s = P.W1s, &W2s = P.W2s, &W3s = P.W3s, &W3T = P.W3T, &W2T = P.W2T, &a1s = P.a1s, &a2s = P.a2s, &d2s = P.d2s, &dys = P.dys,
-             &a1T = P.a1T, &a2T = P.a2T, &d2T = P.d2T, &d1T = P.d1T, &dyT = P.dyT;
+             &a1T = P.a1T, &a2T = P.a2T, &d2T = P.d2T, &d1T = P.d1T, &dyT = P.dyT, &d1s = P.d1s, &W1Tc = P.W1Tc;
     unsigned long long *const *cmax = P.cmax;
     double *a1 = P.a1, *a2 = P.a2, *d1 = P.d1, *d2 = P.d2, *ybuf = P.ybuf, *dy = P.dy, *part = P.part;
     const long long part_bytes = P.part_bytes;
@@ -162,6 +168,11 @@ int egp_oz_mlp_step_f64(const EgpMlpNet *net, const double *d_x, int64_t ldx, in
         OZ_TRY(slice_colsT(net->d_W3, od, h2, h2, S, cmax[0], W3T.q, kod, W3T.e, 0, st));
         OZ_TRY(col_absmax(net->d_W2, h2, h1, h1, cmax[1], st));
         OZ_TRY(slice_colsT(net->d_W2, h2, h1, h1, S, cmax[1], W2T.q, kh2, W2T.e, 0, st));
+        if (dxc > 0) {          // W1[:, :dxc]^T: rows = input feature, contraction over h1
+            EGP_CUDA(cudaMemsetAsync(cmax[2], 0, cmax_bytes, st));
+            OZ_TRY(col_absmax(net->d_W1, h1, dxc, in, cmax[2], st));
+            OZ_TRY(slice_colsT(net->d_W1, h1, dxc, in, S, cmax[2], W1Tc.q, kh1, W1Tc.e, 0, st));
+        }
     }
     const long long xc_stride = xcache_chunk_bytes(in, M, S);
     long long chunk_idx = 0;
@@ -233,7 +244,13 @@ int egp_oz_mlp_step_f64(const EgpMlpNet *net, const double *d_x, int64_t ldx, in
         o = GemmOut(); o.C = d1; o.ldc = h1; o.mask = a1; o.ldm = h1;
         OZ_TRY(gemm(d2s.q, d2s.e, m, W2T.q, W2T.e, h1, kh2, S, o, st));
         EGP_CUDA(cudaMemsetAsync(cmax[7], 0, cmax_bytes, st));
-        OZ_TRY(col_absmax(d1, m, h1, h1, cmax[7], st));
+        if (dxc > 0) {
+            OZ_TRY(slice_rows(d1, m, h1, h1, S, d1s.q, kh1, d1s.e, cmax[7], st));
+            o = GemmOut(); o.C = net->d_dx + r0 * dxc; o.ldc = dxc;
+            OZ_TRY(gemm(d1s.q, d1s.e, m, W1Tc.q, W1Tc.e, dxc, kh1, S, o, st));
+        } else {
+            OZ_TRY(col_absmax(d1, m, h1, h1, cmax[7], st));
+        }
         OZ_TRY(slice_colsT(d1, m, h1, h1, S, cmax[7], d1T.q, mp, d1T.e, 0, st));
         OZ_TRY(wgrad(xT, in, d1T, h1, net->d_gW1, net->d_gb1));
     }

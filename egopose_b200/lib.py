@@ -72,7 +72,8 @@ class TrajOut(C.Structure):
 class MlpNet(C.Structure):
     _fields_ = [('in_dim', C.c_int32), ('h1', C.c_int32), ('h2', C.c_int32), ('out_dim', C.c_int32),
                 ('d_W1', _vp), ('d_b1', _vp), ('d_W2', _vp), ('d_b2', _vp), ('d_W3', _vp), ('d_b3', _vp),
-                ('d_gW1', _vp), ('d_gb1', _vp), ('d_gW2', _vp), ('d_gb2', _vp), ('d_gW3', _vp), ('d_gb3', _vp)]
+                ('d_gW1', _vp), ('d_gb1', _vp), ('d_gW2', _vp), ('d_gb2', _vp), ('d_gW3', _vp), ('d_gb3', _vp),
+                ('d_dx', _vp), ('dx_cols', C.c_int32)]
 
 
 class MlpLoss(C.Structure):
@@ -600,12 +601,12 @@ class OzMlp:
         self.work = torch.empty(nbytes, dtype=torch.uint8, device=device)
 
     @staticmethod
-    def launch_count(n_chunks, bwd, slice_x, fill_cache):
+    def launch_count(n_chunks, bwd, slice_x, fill_cache, dx=False):
         """kernels launched by one egp_oz_mlp_step_f64 call (csrc/oz_mlp.cu): weight slicing + per chunk the x slicing
         (unless cached), 3 GEMMs + 2 row / 2 transposed slicings forward, loss, 5 GEMMs + 3 reductions + slicings backward"""
-        prep = 3 + (6 if bwd else 0)
+        prep = 3 + (6 if bwd else 0) + (3 if dx else 0)
         x = (3 if (bwd or fill_cache) else 1) if slice_x else 0
-        per_chunk = x + (9 + 1 + 17 if bwd else 5)
+        per_chunk = x + (9 + 1 + 17 if bwd else 5) + (1 if dx else 0)
         return prep + n_chunks * per_chunk
 
     def new_cache(self, n):
@@ -613,15 +614,18 @@ class OzMlp:
         nbytes = load().egp_oz_mlp_xcache_bytes(self.dims[0], n, self.chunk, self.S)
         return dict(buf=torch.empty(nbytes, dtype=torch.uint8, device=self.device), n=int(n), valid=False)
 
-    def step(self, weights, x, grads=None, loss=None, y=None, cache=None):
+    def step(self, weights, x, grads=None, loss=None, y=None, cache=None, dx=None):
         """loss: None (forward only, returns y), or dict(kind='ppo', actions, log_std, adv, stats, logp0, exps, clip_eps,
-        inv_count, dlogstd, loss) / dict(kind='value', returns, inv_n, loss)"""
+        inv_count, dlogstd, loss) / dict(kind='value', returns, inv_n, loss); dx ([n, c], optional) receives dL/dx[:, :c]"""
         global launches
         import torch
         n = x.shape[0]
         if x.stride(1) != 1 or x.shape[1] != self.dims[0] or x.dtype != torch.float64:
             raise EgpError('OzMlp.step: x must be a row-major float64 [n, %d] tensor' % self.dims[0])
-        net = MlpNet(*self.dims, *[_raw(w) for w in weights], *([_raw(g) for g in grads] if grads is not None else [None] * 6))
+        net = MlpNet(*self.dims, *[_raw(w) for w in weights], *([_raw(g) for g in grads] if grads is not None else [None] * 6),
+                     _raw(dx), int(dx.shape[1]) if dx is not None else 0)
+        if dx is not None and (dx.shape[0] != n or not dx.is_contiguous() or loss is None):
+            raise EgpError('OzMlp.step: dx must be a contiguous [n, dx_cols] tensor of a backward pass')
         ls = MlpLoss()
         ls.kind = 0
         if loss is not None:
@@ -645,7 +649,7 @@ class OzMlp:
         check(load().egp_oz_mlp_step_f64(C.byref(net), ptr(x[:1]) if not x.is_contiguous() else ptr(x), x.stride(0), n, C.byref(ls),
                                          _raw(y), self.S, self.chunk, _raw(cache['buf']) if cache is not None else None, state,
                                          _raw(self.work), self.work.numel(), stream_ptr()), 'egp_oz_mlp_step_f64')
-        launches += self.launch_count((n + self.chunk - 1) // self.chunk, loss is not None, state != 2, state == 1)
+        launches += self.launch_count((n + self.chunk - 1) // self.chunk, loss is not None, state != 2, state == 1, dx is not None)
         if cache is not None:
             cache['valid'] = True
         return y

@@ -263,6 +263,10 @@ typedef struct {
     int32_t in_dim, h1, h2, out_dim;
     const double *d_W1, *d_b1, *d_W2, *d_b2, *d_W3, *d_b3;      /* torch nn.Linear layout [out][in] */
     double *d_gW1, *d_gb1, *d_gW2, *d_gb2, *d_gW3, *d_gb3;      /* gradients, same layouts (NULL for forward only) */
+    /* optional: dL/dx[:, :dx_cols] -> d_dx [n][dx_cols] (the gradient reaching a learned video-context net whose output
+     * occupies the first input columns: models/video_state_net.py:62-69, agent_ego.py:28-32); NULL / 0 to skip */
+    double *d_dx;
+    int32_t dx_cols;
 } EgpMlpNet;
 
 typedef struct {

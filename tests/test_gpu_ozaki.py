@@ -198,3 +198,26 @@ def test_mlp_step_ppo_loss_matches_autograd():
     assert abs(loss.item() - loss_t.item()) < 1e-9 * abs(loss_t.item())          # north star: 1e-5
     for g, wt in zip(grads, Wt):
         assert torch.allclose(g, wt.grad, rtol=1e-7, atol=1e-9 * wt.grad.abs().max().item())
+
+
+@pytest.mark.parametrize('dxc', [16, 40])
+def test_mlp_step_input_gradient_matches_autograd(dxc):
+    """dL/dx[:, :c]: the gradient handed to a learned video-context net (agent_ego.py:28-32)"""
+    dims = (40, 64, 48, 1)
+    n, chunk = 700, 256
+    W = _weights(dims, 7)
+    torch.manual_seed(11)
+    x = torch.randn(n, dims[0], device=DEV, dtype=torch.float64)
+    ret = torch.randn(n, device=DEV, dtype=torch.float64)
+    xt = x.clone().requires_grad_(True)
+    Wt = [w.clone().requires_grad_(True) for w in W]
+    ((_torch_mlp(Wt, xt).view(-1) - ret) ** 2).mean().backward()
+    oz = lib.OzMlp(*dims, n_slices=6, chunk_rows=chunk, device=DEV)
+    grads = [torch.zeros_like(w) for w in W]
+    loss = torch.zeros(1, device=DEV, dtype=torch.float64)
+    dx = torch.full((n, dxc), float('nan'), device=DEV, dtype=torch.float64)
+    oz.step(W, x, grads=grads, loss=dict(kind='value', returns=ret, inv_n=1.0 / n, loss=loss), dx=dx)
+    ref = xt.grad[:, :dxc]
+    assert torch.allclose(dx, ref, rtol=1e-8, atol=1e-10 * ref.abs().max().item())
+    for g, wt in zip(grads, Wt):
+        assert torch.allclose(g, wt.grad, rtol=1e-8, atol=1e-10 * wt.grad.abs().max().item())
