@@ -1515,8 +1515,38 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
         }
     };
 
+    // evaluation roll-out: reset_env_state(state_pred[frame], env.data.qpos) (ego_mimic_eval.py:93-99): joint angles,
+    // height and velocities from the predicted observation, root xy / heading kept from the simulated state
+    // (align_human_state, utils/tools.py:71-75); the caller runs sim.forward() afterwards
+    auto load_state_pred = [&]() {
+        const double *sp = A.in.d_state_pred + (size_t)(A.take_off[take] + start + cur_t) * S;
+        T4_FOR_OWN_DOFS(i, b) {
+            if (i >= 3) x.at(O.v, i) = sp[nq - 2 + i];
+            if (i >= 6) x.at(O.q, i + 1) = sp[i - 1];
+        }
+        if (c_m.chain_warp[0] == w) {
+            const double qw = x.at(O.q, 3), qz = x.at(O.q, 6), hn = sqrt(qw * qw + qz * qz);
+            const double hq[4] = {qw / hn, 0.0, 0.0, qz / hn};              // get_heading_q, utils/math.py:60-65
+            double o4[4];
+            quat_mul(hq, sp + 1, o4);
+            x.at(O.q, 2) = sp[0];
+            for (int k = 0; k < 4; k++) x.at(O.q, 3 + k) = o4[k];
+            const double cz = hq[0] * hq[0] - hq[3] * hq[3], sz = 2.0 * hq[0] * hq[3];     // quat_mul_vec(hq, v)
+            const double vx = sp[nq - 2], vy = sp[nq - 1];
+            x.at(O.v, 0) = cz * vx - sz * vy;
+            x.at(O.v, 1) = sz * vx + cz * vy;
+            x.at(O.v, 2) = sp[nq];
+        }
+    };
+
     draw_reset(0);
     do_reset();
+    if (A.cfg.eval_mode) {
+        __syncthreads();
+        load_state_pred();
+        __syncthreads();
+        t4_forward_only(x, l);
+    }
     make_state(raw, st);
     T4_FOR_OWN_DOFS(i, b) l.ctrl[i] = 0.0;
     // state-LSTM h | c rows of this CTA, [2H][32] (s_net.initialize() at pre_episode, rnn.py:22-26)
@@ -1525,6 +1555,10 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
 
     for (int t = 0; t < T; t++) {
         const size_t n = (size_t)eid * T + t;
+        if (A.out.d_qpos_traj && live) {                    // env.data.qpos / qvel before the step (ego_mimic_eval.py:136-138)
+            for (int k = w; k < nq; k += T4_WARPS) A.out.d_qpos_traj[n * nq + k] = x.at(O.q, k);
+            for (int k = w; k < nv; k += T4_WARPS) A.out.d_qvel_traj[n * nv + k] = x.at(O.v, k);
+        }
         // ---- save the tree rows the MLP buffers alias (needed stale by the next sub-step's PD solve)
         T4_FOR_OWN_DOFS(i, b) for (int r = 0; r < 3; r++) l.sav_ax[i][r] = x.at(O.ax, 3 * i + r);
         for (int c = 0; c < c_m.nchain; c++)
@@ -1619,7 +1653,7 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
         const double head_z = x.at(O.xp, 3 * c_m.head_xp_slot + 2);
         const double lb = isnan(A.cfg.fix_head_lb) ? A.head_lb[take] - 0.1 : A.cfg.fix_head_lb;
         bool fail = head_z < lb;
-        const bool end = cur_t >= A.cfg.episode_len;
+        const bool end = cur_t >= (A.in.d_fix_len ? A.in.d_fix_len[eid] : A.cfg.episode_len);
         const double *row = A.rows + (size_t)(A.take_off[take] + start + cur_t) * EGP_X_STRIDE;
         // body-quaternion terms of the reward for this thread's bodies (reward_function.py:35-41)
         double pose2 = 0.0, vd = 0.0;
@@ -1752,12 +1786,15 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
                     }
             for (int b = 1 + w; b < nb; b += T4_WARPS) for (int k = 0; k < 4; k++) k_bqc[b][k] = l.bqc[b][k];
             if (w0) for (int k = 0; k < 3 * (EGP_NEE + 1); k++) k_xp[k] = x.at(O.xp, k);
-            if (need_reset) {
+            const bool tele = A.cfg.eval_mode && need_reset && !end;   // fail-safe: replace the state, keep the clock
+            if (need_reset && !tele) {
                 n_reset++; draw_reset(n_reset); cur_t = 0;
                 if (sn_g) for (int j = w; j < 2 * A.sn_H; j += T4_WARPS) sn_g[j * 32 + lane] = 0.0;
             }
+            if (tele && w0) log_acc[EGP_LOG_NUM_FAILSAFE_RESETS] += 1.0;
             __syncthreads();
-            if (need_reset) {
+            if (tele) load_state_pred();
+            else if (need_reset) {
                 const double *r0 = A.rows + (size_t)(A.take_off[take] + start) * EGP_X_STRIDE;
                 T4_FOR_OWN_DOFS(i, b) {
                     x.at(O.v, i) = r0[EGP_X_QVEL + i];
@@ -1784,10 +1821,11 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
                     }
             tm_wait_st();
             if (need_reset) {
-                for (int b = 1 + w; b < nb; b += T4_WARPS) {
-                    const int qa = c_m.body_qposadr[b], nd = c_m.body_dofnum[b];
-                    quat_from_euler(x.at(O.q, qa), nd > 1 ? x.at(O.q, qa + 1) : 0.0, nd > 2 ? x.at(O.q, qa + 2) : 0.0, l.bqc[b]);
-                }
+                if (!tele)                                  // set_state() alone leaves env.bquat stale (ego_mimic_eval.py:98)
+                    for (int b = 1 + w; b < nb; b += T4_WARPS) {
+                        const int qa = c_m.body_qposadr[b], nd = c_m.body_dofnum[b];
+                        quat_from_euler(x.at(O.q, qa), nd > 1 ? x.at(O.q, qa + 1) : 0.0, nd > 2 ? x.at(O.q, qa + 2) : 0.0, l.bqc[b]);
+                    }
                 make_state(raw, st);
             } else {
                 for (int b = 1 + w; b < nb; b += T4_WARPS) for (int k = 0; k < 4; k++) l.bqc[b][k] = k_bqc[b][k];
@@ -1811,6 +1849,7 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
             atomicAdd(Lg + EGP_LOG_TOTAL_REWARD, log_acc[EGP_LOG_TOTAL_REWARD]);
             atomicAdd(Lg + EGP_LOG_TOTAL_C_REWARD, log_acc[EGP_LOG_TOTAL_C_REWARD]);
             atomicAdd(Lg + EGP_LOG_NUM_NAN_RESETS, log_acc[EGP_LOG_NUM_NAN_RESETS]);
+            if (A.cfg.eval_mode) atomicAdd(Lg + EGP_LOG_NUM_FAILSAFE_RESETS, log_acc[EGP_LOG_NUM_FAILSAFE_RESETS]);
             for (int k = 0; k < 5; k++) atomicAdd(Lg + EGP_LOG_C_INFO + k, log_acc[EGP_LOG_C_INFO + k]);
             auto amin = [](double *addr, double v) {
                 unsigned long long *a = (unsigned long long *)addr, old = *a, assumed;
@@ -2261,6 +2300,10 @@ int egp_rollout_f64(EgpModel *m, const EgpPolicyWeights *pol, const EgpRolloutCf
     auto padk = [kcv](int x) { return (x + kcv - 1) / kcv * kcv; };
     A.K1p = use_t4 ? padk(A.D) : A.D; A.K2p = use_t4 ? padk(A.H1) : A.H1; A.K3p = use_t4 ? padk(A.H2) : A.H2;
     if (snH && !use_t4) { set_error("egp_rollout_f64: the state LSTM needs the T4 rollout variant (policy too wide?)"); return EGP_ESIZE; }
+    const bool ev = cfg->eval_mode || (in && in->d_fix_len) || out->d_qpos_traj || out->d_qvel_traj;
+    if (ev && !use_t4) { set_error("egp_rollout_f64: evaluation roll-outs (eval_mode / fix_len / qpos_traj) need the T4 rollout variant"); return EGP_ESIZE; }
+    if (cfg->eval_mode && !(in && in->d_state_pred)) { set_error("egp_rollout_f64: eval_mode needs d_state_pred"); return EGP_EINVAL; }
+    if ((out->d_qpos_traj == nullptr) != (out->d_qvel_traj == nullptr)) { set_error("egp_rollout_f64: d_qpos_traj / d_qvel_traj come in pairs"); return EGP_EINVAL; }
     A.sn_Kp = snH ? padk(sn_in) : 0;
     size_t need = (size_t)A.K1p * A.H1p + A.H1p + (size_t)A.K2p * A.H2p + A.H2p + (size_t)A.K3p * A.Ap + A.Ap +
                   (size_t)A.sn_Kp * 4 * snH + 4 * snH;

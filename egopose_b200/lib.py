@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(HERE, 'libegopose_b200.so')
 X = dict(QPOS=0, QVEL=59, RLINV_LOCAL=117, RANGV=120, RQ_RMH=123, EE_POS=127, BQUAT=142, BANGVEL=226, STRIDE=292)
 NEE = 5
 LOG = dict(NUM_STEPS=0, NUM_EPISODES=1, TOTAL_REWARD=2, TOTAL_C_REWARD=3, MIN_C_REWARD=4, MAX_C_REWARD=5, C_INFO=6,
-           MIN_EPISODE_REWARD=11, MAX_EPISODE_REWARD=12, NUM_NAN_RESETS=13, SIZE=16)
+           MIN_EPISODE_REWARD=11, MAX_EPISODE_REWARD=12, NUM_NAN_RESETS=13, NUM_FAILSAFE_RESETS=14, SIZE=16)
 EE_NAMES = ['LeftFoot', 'RightFoot', 'LeftHand', 'RightHand', 'Head']       # humanoid_v1.py:100
 
 _dp = C.POINTER(C.c_double)
@@ -47,7 +47,7 @@ class RolloutCfg(C.Structure):
     _fields_ = [('n_env', C.c_int32), ('horizon', C.c_int32), ('episode_len', C.c_int32), ('fr_margin', C.c_int32),
                 ('end_reward', C.c_double), ('fix_head_lb', C.c_double), ('noise_rate', C.c_double),
                 ('mean_action', C.c_int32), ('zf_clip', C.c_double), ('seed', C.c_uint64), ('iteration', C.c_uint64),
-                ('max_resets', C.c_int32)]
+                ('max_resets', C.c_int32), ('eval_mode', C.c_int32)]
 
 
 class PolicyWeights(C.Structure):
@@ -60,13 +60,13 @@ class RolloutIn(C.Structure):
     _fields_ = [('d_eps', _vp), ('d_reset_take', _vp), ('d_reset_start', _vp), ('d_mean_flag', _vp),
                 ('d_zf_mean', _vp), ('d_zf_std', _vp), ('d_ctx', _vp), ('d_win_off', _vp), ('ctx_dim', C.c_int32),
                 ('ctx_mode', C.c_int32), ('ctx_T', C.c_int32), ('d_snet_W', _vp), ('d_snet_b', _vp), ('d_snet_state', _vp),
-                ('snet_hdim', C.c_int32)]
+                ('snet_hdim', C.c_int32), ('d_fix_len', _vp), ('d_state_pred', _vp)]
 
 
 class TrajOut(C.Structure):
     _fields_ = [('d_states', _vp), ('d_actions', _vp), ('d_masks', _vp), ('d_next_states', _vp), ('d_rewards', _vp),
                 ('d_exps', _vp), ('d_v_metas', _vp), ('d_c_info', _vp), ('d_raw_obs', _vp), ('d_final_qpos', _vp),
-                ('d_final_qvel', _vp), ('d_logger', _vp)]
+                ('d_final_qvel', _vp), ('d_logger', _vp), ('d_qpos_traj', _vp), ('d_qvel_traj', _vp)]
 
 
 class MlpNet(C.Structure):
@@ -308,7 +308,8 @@ class Model:
     def rollout(self, weights, n_env, horizon, episode_len, fr_margin=10, end_reward=0.0, fix_head_lb=None,
                 noise_rate=1.0, mean_action=False, zf_mean=None, zf_std=None, zf_clip=5.0, seed=1, iteration=0,
                 eps=None, reset_take=None, reset_start=None, mean_flag=None, want_next=True, want_raw=True, out=None,
-                ctx=None, win_off=None, ctx_const=False, snet=None):
+                ctx=None, win_off=None, ctx_const=False, snet=None, eval_mode=False, fix_len=None, state_pred=None,
+                want_traj=False):
         """weights: dict with W1,b1,W2,b2,W3,b3,log_std CUDA float64 tensors (torch [out,in] layout).
         Returns a dict of CUDA tensors in TrajBatchEgo layout (+ logger, c_info, raw_obs, final state)."""
         global launches
@@ -337,6 +338,9 @@ class Model:
         o.d_final_qpos = ptr(buf('final_qpos', (n_env, self.nq)))
         o.d_final_qvel = ptr(buf('final_qvel', (n_env, self.nv)))
         o.d_logger = ptr(buf('logger', (LOG['SIZE'],)))
+        if want_traj:               # env.data.qpos / qvel before every step (evaluation roll-outs)
+            o.d_qpos_traj = ptr(buf('qpos_traj', (N, self.nq)))
+            o.d_qvel_traj = ptr(buf('qvel_traj', (N, self.nv)))
         cfg = RolloutCfg()
         cfg.n_env, cfg.horizon, cfg.episode_len, cfg.fr_margin = n_env, horizon, episode_len, fr_margin
         cfg.end_reward = float(end_reward)
@@ -344,9 +348,16 @@ class Model:
         cfg.noise_rate, cfg.mean_action, cfg.zf_clip = float(noise_rate), int(bool(mean_action)), float(zf_clip)
         cfg.seed, cfg.iteration = int(seed), int(iteration)
         cfg.max_resets = int(reset_take.shape[1]) if reset_take is not None else 0
+        cfg.eval_mode = int(bool(eval_mode))
         inp = RolloutIn()
         inp.d_eps, inp.d_reset_take, inp.d_reset_start = ptr(eps), ptr(reset_take), ptr(reset_start)
         inp.d_mean_flag, inp.d_zf_mean, inp.d_zf_std = ptr(mean_flag), ptr(zf_mean), ptr(zf_std)
+        if fix_len is not None:     # per-environment episode length, int32 [n_env]
+            inp.d_fix_len = ptr(fix_len)
+        if state_pred is not None:  # [total_frames, S] predicted observations (eval_mode state replacement)
+            if tuple(state_pred.shape) != (int(self.take_off[-1]), S):
+                raise EgpError('state_pred must be [total_frames = %d, %d]' % (int(self.take_off[-1]), S))
+            inp.d_state_pred = ptr(state_pred)
         if ctx is not None:         # per-rollout context table (window-indexed when win_off is given)
             inp.d_ctx, inp.ctx_dim = ptr(ctx), ctx.shape[1]
             inp.d_win_off, inp.ctx_mode, inp.ctx_T = ptr(win_off), int(win_off is not None), int(episode_len)

@@ -85,6 +85,11 @@ typedef struct {
     uint64_t seed;                      /* Philox key for perf-mode noise / reset draws */
     uint64_t iteration;                 /* Philox stream offset so successive rollouts differ */
     int32_t max_resets;                 /* parity mode: columns of d_reset_take/start */
+    /* Evaluation roll-out (ego_pose/ego_mimic_eval.py:102-177): a failing environment is NOT restarted; its state is
+     * replaced in place by the d_state_pred row of the next frame, aligned to the simulated root position / heading
+     * (reset_env_state :93-99, utils/tools.py:71-75), and the episode clock keeps running ('naivefs' fail-safe :167-173
+     * with fix_head_lb = 0.3, :52-53).  The first state of every episode is placed the same way (:127). */
+    int32_t eval_mode;
 } EgpRolloutCfg;
 
 /* PolicyGaussian(MLP) weights on the device, torch nn.Linear layout [out][in] (core/policy_gaussian.py:8-24,
@@ -118,6 +123,9 @@ typedef struct {
     const double *d_snet_b;             /* [4H] bias_ih + bias_hh in the same row order */
     double *d_snet_state;               /* caller-owned scratch, ceil(E / 32) * 2H * 32 doubles */
     int32_t snet_hdim;                  /* H (even) */
+    const int32_t *d_fix_len;           /* [E] per-environment episode length (env.set_fix_sampling(len=), humanoid_v1.py:197) or NULL */
+    const double *d_state_pred;         /* eval_mode: [total_frames][S] predicted observations (qpos[2:] | qvel in the
+                                         * heading frame, humanoid_v1.py:73-96), row = take_off[take] + start + cur_t */
 } EgpRolloutIn;
 
 /* TrajBatchEgo layout (core/trajbatch.py:6-16, ego_pose/core/trajbatch_ego.py:7-9), all device, row-major. */
@@ -133,6 +141,8 @@ typedef struct {
     double *d_raw_obs;                  /* [N][S] unfiltered observations or NULL */
     double *d_final_qpos, *d_final_qvel;/* [E][nq], [E][nv] or NULL */
     double *d_logger;                   /* [EGP_LOG_SIZE] reductions for core/logger_rl.py, or NULL */
+    double *d_qpos_traj, *d_qvel_traj;  /* [N][nq], [N][nv] simulator state BEFORE step t (traj_pred / vel_pred of
+                                         * ego_mimic_eval.py:136-138) or NULL */
 } EgpTrajOut;
 
 /* d_logger slots */
@@ -146,6 +156,7 @@ typedef struct {
 #define EGP_LOG_MIN_EPISODE_REWARD 11
 #define EGP_LOG_MAX_EPISODE_REWARD 12
 #define EGP_LOG_NUM_NAN_RESETS 13
+#define EGP_LOG_NUM_FAILSAFE_RESETS 14  /* eval_mode: in-place state replacements (num_reset, ego_mimic_eval.py:170) */
 #define EGP_LOG_SIZE 16
 
 const char *egp_last_error_string(void);

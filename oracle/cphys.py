@@ -231,6 +231,18 @@ class Oracle:
                            C.byref(fail), C.byref(end))
         return bool(fail.value), bool(end.value)
 
+    def env_set_state(self, env, qpos, qvel):
+        """MujocoEnv.set_state (envs/common/mujoco_env.py:95-101): overwrite qpos / qvel, sim.forward()"""
+        q, v = _d(qpos), _d(qvel)
+        self.L.eo_env_set_state(C.byref(self.model), C.byref(env), _p(q), _p(v))
+
+    def policy_mean(self, policy, x):
+        """PolicyGaussian action mean of one input row (core/policy_gaussian.py:19-24)"""
+        x = _d(x)
+        mean, scratch = np.zeros(policy.out_dim), np.zeros(policy.h1 + policy.h2)
+        self.L.eo_policy_mean(C.byref(policy), _p(x), _p(mean), _p(scratch))
+        return mean
+
     def env_obs(self, env):
         out = np.zeros(self.S)
         self.L.eo_env_obs(C.byref(self.model), C.byref(env), _p(out))

@@ -1,0 +1,86 @@
+"""TEST INFRASTRUCTURE ONLY - never imported by the product path.
+
+CPU restatement of the evaluation roll-out of ego_pose/ego_mimic_eval.py:93-177 (eval_expert) on top of the C
+oracle's env primitives: one take from frame fr_margin, mean action, ZFilter frozen (update=False), simulator
+state recorded BEFORE every step, and the 'naivefs' fail-safe (fix_head_lb, :52-53,167-173): a failing humanoid is
+not restarted, its state is replaced by the predicted observation of the next frame aligned to the simulated root
+(reset_env_state :93-99 + align_human_state utils/tools.py:71-75) and the episode clock keeps running.
+
+Pinned by tests/golden/eval_traj.npz (the reference's own HumanoidEnv / align_human_state / PolicyGaussian driven in
+the script's call order on the restated physics, tests/golden/make_golden.py gen_eval).  The state-regression net
+that produces ``state_pred`` in the reference (models/video_reg_net.py) is outside the hot path: the table is an
+input here.  The 'valuefs' rule (value < 0.6 x running mean over all takes, :167) is not restated.
+"""
+import numpy as np
+
+from . import cphys
+
+
+def quat_mul(q1, q0):
+    """utils/transformation.py:1379-1391 quaternion_multiply(q1, q0), (w, x, y, z)"""
+    w0, x0, y0, z0 = q0
+    w1, x1, y1, z1 = q1
+    return np.array([-x1 * x0 - y1 * y0 - z1 * z0 + w1 * w0, x1 * w0 + y1 * z0 - z1 * y0 + w1 * x0,
+                     -x1 * z0 + y1 * w0 + z1 * x0 + w1 * y0, x1 * y0 - y1 * x0 + z1 * w0 + w1 * z0])
+
+
+def heading_q(q):
+    """utils/math.py:60-65 get_heading_q"""
+    hq = np.array([q[0], 0.0, 0.0, q[3]])
+    return hq / np.linalg.norm(hq)
+
+
+def reset_env_state(orc, env, state, nq):
+    """ego_mimic_eval.py:93-99: qpos[2:], qvel from the predicted observation; align_human_state (utils/tools.py:71-75)
+    keeps the simulated root xy and heading; env.set_state -> sim.forward()"""
+    ref_qpos = np.array(env.d.qpos[:nq])
+    qpos = ref_qpos.copy()
+    qpos[2:] = state[:nq - 2]
+    qvel = np.array(state[nq - 2:], dtype=np.float64)
+    hq = heading_q(ref_qpos[3:7])
+    qpos[3:7] = quat_mul(hq, qpos[3:7])
+    c, s = hq[0] * hq[0] - hq[3] * hq[3], 2.0 * hq[0] * hq[3]          # quat_mul_vec(hq, v): rotation about z
+    qvel[:3] = [c * qvel[0] - s * qvel[1], s * qvel[0] + c * qvel[1], qvel[2]]
+    orc.env_set_state(env, qpos, qvel)
+    return orc.env_obs(env)
+
+
+def eval_take(orc, policy, take, fr_margin, test_len, state_pred, ctx=None, zf_mean=None, zf_std=None, zf_clip=5.0,
+              fail_safe='naivefs'):
+    """state_pred [L, S] and ctx [L, ctx_dim] are indexed by the take's frame (frame = fr_margin + t).
+    Returns dict(traj_pred [n, nq], vel_pred [n, nv], states [n, S], actions, rewards, num_reset)."""
+    nq, nv = orc.nq, orc.nv
+
+    def zf(x):
+        if zf_mean is None:
+            return x
+        y = (x - zf_mean) / (zf_std + 1e-8)
+        return np.clip(y, -zf_clip, zf_clip) if zf_clip > 0 else y
+
+    orc.cfg.episode_len = int(test_len)                 # env.set_fix_sampling(expert_ind, fr_margin, test_len)
+    env = cphys.EoEnv()
+    orc.env_reset(env, int(take), int(fr_margin))
+    state = zf(reset_env_state(orc, env, state_pred[fr_margin], nq))
+    out = dict(traj_pred=[], vel_pred=[], states=[], actions=[], rewards=[], num_reset=0)
+    for t in range(test_len):
+        out['traj_pred'].append(np.array(env.d.qpos[:nq]))
+        out['vel_pred'].append(np.array(env.d.qvel[:nv]))
+        x = state if ctx is None else np.concatenate([ctx[fr_margin + t], state])
+        action = orc.policy_mean(policy, x)
+        fail, end = orc.env_step(env, action)
+        next_state = zf(orc.env_obs(env))
+        rew, _ = orc.env_reward(env, end)
+        out['states'].append(state)
+        out['actions'].append(action)
+        out['rewards'].append(rew)
+        if end:
+            break
+        if fail_safe == 'naivefs' and fail:
+            out['num_reset'] += 1
+            state = zf(reset_env_state(orc, env, state_pred[fr_margin + t + 1], nq))
+        else:
+            state = next_state
+    for k in ('traj_pred', 'vel_pred', 'states', 'actions'):
+        out[k] = np.array(out[k])
+    out['rewards'] = np.array(out['rewards'])
+    return out

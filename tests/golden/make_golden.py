@@ -11,6 +11,8 @@ Runs only in the build container (needs /root/reference):   python tests/golden/
   env_traj.npz      ego_pose/envs/humanoid_v1.py + ego_pose/core/reward_function.py stepped on the
                     restated physics through oracle/mujoco_shim.py (pins env logic, NOT MuJoCo itself),
                     and the gen_expert.py feature pipeline re-driven with the reference's own helpers
+  eval_traj.npz     ego_pose/ego_mimic_eval.py:93-177 evaluation roll-out ('naivefs' fail-safe) re-driven with the
+                    reference's own env / align_human_state / PolicyGaussian / ZFilter on the restated physics
 """
 import os
 import pickle
@@ -454,8 +456,130 @@ def gen_env():
     np.savez_compressed(os.path.join(OUT, 'env_traj.npz'), **out)
 
 
+def gen_eval():
+    """ego_pose/ego_mimic_eval.py:93-177 (eval_expert) re-driven in the script's call order with the reference's own
+    HumanoidEnv (set_fix_sampling / set_fix_head_lb / reset / step), align_human_state, PolicyGaussian + MLP and
+    ZFilter(update=False) on the restated physics; 'naivefs' fail-safe; state_pred = perturbed expert observations
+    (the state-regression net of the script is outside the hot path)."""
+    orc = cphys.Oracle()
+    mujoco_shim.install(orc)
+    work = tempfile.mkdtemp(prefix='egopose_golden_eval_')
+    os.symlink(os.path.join(refimport.REF, 'config'), os.path.join(work, 'config'))
+    os.symlink(os.path.join(refimport.REF, 'assets'), os.path.join(work, 'assets'))
+    os.makedirs(os.path.join(work, 'datasets', 'meta'))
+    os.makedirs(os.path.join(work, 'datasets', 'features'))
+    take_names = ['take_a', 'take_b']
+    import yaml
+    yaml.safe_dump({'train': take_names, 'test': take_names},
+                   open(os.path.join(work, 'datasets', 'meta', 'meta_subject_03.yml'), 'w'))
+    os.chdir(work)
+
+    from core.policy_gaussian import PolicyGaussian
+    from ego_pose.core.reward_function import quat_space_reward_v3
+    from ego_pose.envs.humanoid_v1 import HumanoidEnv
+    from ego_pose.utils.egomimic_config import Config
+    from models.mlp import MLP
+    from utils.tools import align_human_state
+    from utils.zfilter import ZFilter
+
+    FM, CTX = 5, 6
+    lens = [40, 33]
+    takes = [cphys.synthetic_takes(orc.md, 1, L, seed=31 + i)[0] for i, L in enumerate(lens)]
+    cfg = Config('subject_03', create_dirs=False)
+    cfg.fr_margin = FM
+    env = HumanoidEnv(cfg)
+    env.seed(1)
+    # expert dict through the oracle's gen_expert restatement (itself pinned by env_traj.npz)
+    X = cphys.X
+    expert_dict = {}
+    for n, q in zip(take_names, takes):
+        rows, lb = orc.expert_features(q)
+        ex = {'qpos': q, 'len': q.shape[0], 'height_lb': q[:, 2].min(), 'head_height_lb': lb}
+        for key, col, w in (('qvel', 'QVEL', 58), ('rlinv_local', 'RLINV_LOCAL', 3), ('rangv', 'RANGV', 3), ('rq_rmh', 'RQ_RMH', 4),
+                            ('ee_pos', 'EE_POS', 15), ('bquat', 'BQUAT', 84), ('bangvel', 'BANGVEL', 63)):
+            ex[key] = rows[:, X[col]:X[col] + w].copy()
+        expert_dict[n] = ex
+    rng = np.random.RandomState(41)
+    cnn = {n: rng.randn(L, CTX) for n, L in zip(take_names, lens)}
+    pickle.dump(expert_dict, open(cfg.expert_feat_file, 'wb'))
+    pickle.dump((cnn, {}), open(cfg.cnn_feat_file, 'wb'))
+    env.load_experts(take_names, cfg.expert_feat_file, cfg.cnn_feat_file)
+
+    state_dim, action_dim = env.observation_space.shape[0], env.action_space.shape[0]
+    torch.manual_seed(7)
+    policy_net = PolicyGaussian(MLP(state_dim + CTX, (32, 16), 'relu'), action_dim, log_std=-2.3, fix_std=True)
+    running_state = ZFilter((state_dim,), clip=5)
+    for _ in range(50):                                  # some statistics, then frozen
+        running_state(0.5 * rng.randn(state_dim))
+    out = dict(fr_margin=FM, lens=np.array(lens), zf_mean=running_state.rs.mean.copy(), zf_std=running_state.rs.std.copy())
+    for k, v in policy_net.state_dict().items():
+        out['policy.' + k] = v.numpy().copy()
+
+    def reset_env_state(state, ref_qpos):                # ego_mimic_eval.py:93-99
+        qpos = ref_qpos.copy()
+        qpos[2:] = state[:qpos.size - 2]
+        qvel = state[qpos.size - 2:].copy()
+        align_human_state(qpos, qvel, ref_qpos)
+        env.set_state(qpos, qvel)
+        return env.get_obs()
+
+    for ti, name in enumerate(take_names):
+        L = lens[ti]
+        test_len = L - 2 * FM
+        # state_pred: the expert's own observation of every frame plus a perturbation
+        sp = np.zeros((L, state_dim))
+        for fr in range(L):
+            env.set_state(expert_dict[name]['qpos'][fr].copy(), expert_dict[name]['qvel'][fr].copy())
+            sp[fr] = env.get_obs()
+        sp[:, 5:] += 0.02 * rng.randn(L, state_dim - 5)       # joints / velocities; root height + quaternion kept
+        # fail line a little below the starting head height: a contact-less humanoid crosses it every few steps
+        env.set_state(expert_dict[name]['qpos'][FM].copy(), expert_dict[name]['qvel'][FM].copy())
+        head_lb = env.get_body_com('Head')[2] - 0.03
+        env.set_fix_head_lb(head_lb)
+        env.set_fix_sampling(ti, FM, test_len)
+        state = env.reset()
+        cnn_feat = env.get_episode_cnn_feat()
+        assert cnn_feat.shape[0] == L
+        state = reset_env_state(sp[FM], env.data.qpos)
+        state = running_state(state, update=False)
+        traj_pred, vel_pred, states, actions, rewards, num_reset = [], [], [], [], [], 0
+        for t in range(test_len):
+            traj_pred.append(env.data.qpos.copy())
+            vel_pred.append(env.data.qvel.copy())
+            x = torch.from_numpy(np.concatenate([cnn_feat[FM + t], state])).unsqueeze(0)
+            with torch.no_grad():
+                action = policy_net.select_action(x, mean_action=True)[0].numpy()
+            next_state, _r, done, info = env.step(action)
+            next_state = running_state(next_state, update=False)
+            reward, _ = quat_space_reward_v3(env, state, action, info)
+            states.append(state)
+            actions.append(action)
+            rewards.append(reward)
+            if info['end']:
+                break
+            if info['fail']:                             # --fail-safe naivefs
+                num_reset += 1
+                state = reset_env_state(sp[FM + t + 1], env.data.qpos)
+                state = running_state(state, update=False)
+            else:
+                state = next_state
+        pre = 'take%d.' % ti
+        out[pre + 'qpos'] = takes[ti]
+        out[pre + 'cnn'] = cnn[name]
+        out[pre + 'state_pred'] = sp
+        out[pre + 'head_lb'] = head_lb
+        out[pre + 'traj_pred'] = np.vstack(traj_pred)
+        out[pre + 'vel_pred'] = np.vstack(vel_pred)
+        out[pre + 'states'] = np.vstack(states)
+        out[pre + 'actions'] = np.vstack(actions)
+        out[pre + 'rewards'] = np.array(rewards)
+        out[pre + 'num_reset'] = num_reset
+        print('eval take', ti, 'steps', len(rewards), 'num_reset', num_reset)
+    np.savez_compressed(os.path.join(OUT, 'eval_traj.npz'), **out)
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['ppo', 'math', 'zfilter', 'env', 'vsnet', 'fcnet']
+    which = sys.argv[1:] or ['ppo', 'math', 'zfilter', 'env', 'vsnet', 'fcnet', 'eval']
     if 'ppo' in which:
         gen_ppo()
     if 'ppo_mb' in which or 'ppo' in which:
@@ -468,5 +592,7 @@ if __name__ == '__main__':
         gen_math()
     if 'zfilter' in which:
         gen_zfilter()
+    if 'eval' in which:
+        gen_eval()
     if 'env' in which:
         gen_env()
