@@ -1791,7 +1791,7 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
                 n_reset++; draw_reset(n_reset); cur_t = 0;
                 if (sn_g) for (int j = w; j < 2 * A.sn_H; j += T4_WARPS) sn_g[j * 32 + lane] = 0.0;
             }
-            if (tele && w0) log_acc[EGP_LOG_NUM_FAILSAFE_RESETS] += 1.0;
+            if (tele && w0 && n_reset == 0) log_acc[EGP_LOG_NUM_FAILSAFE_RESETS] += 1.0;   // first episode of the environment only
             __syncthreads();
             if (tele) load_state_pred();
             else if (need_reset) {

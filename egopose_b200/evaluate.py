@@ -1,0 +1,106 @@
+"""Evaluation roll-outs on the fused rollout kernel.
+
+Mirrors ego_pose/ego_mimic_eval.py:102-195: every take of the loaded expert list is rolled out once from frame
+``fr_margin`` for ``len - 2 * fr_margin`` steps under the mean action with frozen ZFilter statistics, the simulator
+state is recorded before every step, and the result is the ``(results, meta)`` pair the script pickles
+(``results = {'traj_pred', 'traj_orig', 'vel_pred'}`` keyed by take, ``meta = {'algo', 'num_reset'}``, :186-193) and
+ego_pose/eval_pose.py:31-66 consumes.  All takes run in ONE kernel launch (environment e = take e, per-environment
+episode length); the reference loops over takes and steps in Python.
+
+Fail-safe (:167-173): 'naivefs' (head below ``fix_head_lb`` = 0.3, :52-53) replaces the state of a fallen humanoid in
+place by ``state_pred`` of the next frame, aligned to the simulated root (reset_env_state :93-99), inside the kernel;
+'none' never replaces it.  ``state_pred`` is what the reference obtains from its state-regression net
+(models/video_reg_net.py, outside the hot path): pass its per-take predictions, or leave it None to use the
+expert's own observation of each frame.  The 'valuefs' rule needs the value net inside the step loop and a running
+mean shared across takes in script order; it is not built (raises).
+"""
+import pickle
+
+import numpy as np
+import torch
+
+from . import lib
+
+
+def expert_obs_table(model):
+    """[total_frames, S]: HumanoidEnv.get_obs() (humanoid_v1.py:73-96) of every expert frame, read off the packed
+    expert rows: qpos[2] | de-headed root quaternion | hinge angles | root velocity in the heading frame | qvel[3:]"""
+    X, r = lib.X, model.rows_host
+    nq, nv = model.nq, model.nv
+    return np.ascontiguousarray(np.concatenate(
+        [r[:, X['QPOS'] + 2:X['QPOS'] + 3], r[:, X['RQ_RMH']:X['RQ_RMH'] + 4], r[:, X['QPOS'] + 7:X['QPOS'] + nq],
+         r[:, X['RLINV_LOCAL']:X['RLINV_LOCAL'] + 3], r[:, X['QVEL'] + 3:X['QVEL'] + nv]], axis=1))
+
+
+def _context_table(env, policy_vs_net, dev):
+    """per-frame context rows for whole-take episodes: test-mode VideoStateNet.initialize(cnn_feat) over the full
+    take (ego_mimic_eval.py:122-124), placed at the frames it describes; None -> the table uploaded with the experts"""
+    from .nets import VideoStateNet
+    if not isinstance(policy_vs_net, VideoStateNet):
+        return None
+    m = policy_vs_net.v_margin
+    p = policy_vs_net._p()
+    rows = []
+    with torch.no_grad():
+        for feat in env.cnn_feat:
+            f = torch.as_tensor(feat, dtype=p.dtype, device=p.device)
+            t = torch.zeros((f.shape[0], policy_vs_net.v_hdim), dtype=p.dtype, device=p.device)
+            t[m:f.shape[0] - m] = policy_vs_net.forward_v_net(f.unsqueeze(1)).squeeze(1)[m:-m]
+            rows.append(t)
+    return torch.cat(rows).to(dev).contiguous()
+
+
+def eval_takes(env, policy_net, policy_vs_net=None, running_state=None, state_pred=None, fail_safe='naivefs',
+               fix_head_lb=0.3, show_noise=False, seed=1, algo='ego_mimic'):
+    """-> (results, meta, info).  ``state_pred``: None or a per-take list of [len, S] arrays indexed by frame."""
+    if fail_safe not in ('naivefs', 'none'):
+        raise NotImplementedError("fail_safe %r: only 'naivefs' and 'none' run on the fused path" % (fail_safe,))
+    model, cfg = env.kernel, env.cfg
+    fm = int(cfg.fr_margin)
+    off = np.asarray(model.take_off, dtype=np.int64)
+    lens = np.diff(off)
+    test_len = lens - 2 * fm
+    if test_len.min() < 1:
+        raise ValueError('a take is shorter than 2 * fr_margin + 1 frames')
+    E, T = len(lens), int(test_len.max())
+    dev = policy_net.action_mean.weight.device
+    L = policy_net.net.affine_layers
+    w = dict(W1=L[0].weight.data, b1=L[0].bias.data, W2=L[1].weight.data, b2=L[1].bias.data,
+             W3=policy_net.action_mean.weight.data, b3=policy_net.action_mean.bias.data,
+             log_std=policy_net.action_log_std.data.view(-1))
+    w = {k: t.contiguous() for k, t in w.items()}
+    sp = expert_obs_table(model) if state_pred is None else np.concatenate([np.asarray(a, dtype=np.float64) for a in state_pred])
+    cu = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=dev)  # noqa: E731
+    zm = zs = None
+    clip = 0.0
+    if running_state is not None:
+        zm, zs = cu(running_state.rs.mean, torch.float64), cu(running_state.rs.std, torch.float64)
+        clip = running_state.clip or 0.0
+    head_lb = fix_head_lb if fail_safe == 'naivefs' else -1e30          # 'none': the fail rule never fires
+    out = model.rollout(
+        w, E, T, episode_len=T, fr_margin=fm, fix_head_lb=head_lb, mean_action=not show_noise, zf_mean=zm, zf_std=zs,
+        zf_clip=clip, seed=seed, reset_take=cu(np.arange(E)[:, None], torch.int32),
+        reset_start=cu(np.full((E, 1), fm), torch.int32), want_next=False, want_raw=False,
+        ctx=_context_table(env, policy_vs_net, dev), eval_mode=True, fix_len=cu(test_len, torch.int32),
+        state_pred=cu(sp, torch.float64), want_traj=True)
+    qpos = out['qpos_traj'].view(E, T, model.nq).cpu().numpy()
+    qvel = out['qvel_traj'].view(E, T, model.nv).cpu().numpy()
+    rewards = out['rewards'].view(E, T).cpu().numpy()
+    X = lib.X
+    results = {'traj_pred': {}, 'traj_orig': {}, 'vel_pred': {}}
+    for e, take in enumerate(env.expert_list):
+        n = int(test_len[e])
+        results['traj_pred'][take] = qpos[e, :n].copy()
+        results['vel_pred'][take] = qvel[e, :n].copy()
+        results['traj_orig'][take] = model.rows_host[off[e] + fm:off[e] + fm + n, X['QPOS']:X['QPOS'] + model.nq].copy()
+    num_reset = int(round(float(out['logger'][lib.LOG['NUM_FAILSAFE_RESETS']].item())))
+    meta = {'algo': algo, 'num_reset': num_reset}
+    info = {'rewards': {take: rewards[e, :int(test_len[e])].copy() for e, take in enumerate(env.expert_list)},
+            'test_len': {take: int(test_len[e]) for e, take in enumerate(env.expert_list)}}
+    return results, meta, info
+
+
+def save_results(results, meta, path):
+    """the pickle ego_mimic_eval.py:192 writes and eval_pose.py:31 reads"""
+    with open(path, 'wb') as f:
+        pickle.dump((results, meta), f)

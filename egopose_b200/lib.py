@@ -264,6 +264,7 @@ class Model:
                                          rows.ctypes.data_as(_dp), head_lb.ctypes.data_as(_dp), cp, cd),
               'egp_expert_upload')
         self.n_takes, self.ctx_dim, self.take_off, self.head_lb = len(head_lb), cd, take_off, head_lb
+        self.rows_host = rows           # host copy of the packed expert rows (evaluate.expert_obs_table)
 
     def expert_features(self, qpos):
         """gen_expert.get_expert for one take on the GPU: qpos [L, nq] -> (rows [L, 292] tensor, head_height_lb)"""

@@ -1,0 +1,114 @@
+"""Evaluation roll-outs on the fused kernel (eval_mode: in-place fail-safe state replacement, per-environment episode
+length, recorded simulator states) vs the reference golden (tests/golden/eval_traj.npz, reference env code driven in
+ego_mimic_eval.py's call order) and vs the CPU oracle's eval loop through the public egopose_b200.evaluate API."""
+import pickle
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip('torch')
+
+from oracle import cphys, evalloop  # noqa: E402
+import helpers  # noqa: E402
+from test_oracle_eval import setup_eval  # noqa: E402
+
+
+def cu(a, dtype=torch.float64):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype, device='cuda')
+
+
+def test_eval_rollout_matches_reference_golden(golden):
+    g = golden('eval_traj')
+    orc, _, fm = setup_eval(g)
+    lens = [int(x) for x in g['lens']]
+    cnn = np.concatenate([g['take%d.cnn' % i] for i in range(2)])
+    sp = np.concatenate([g['take%d.state_pred' % i] for i in range(2)])
+    model = helpers.make_model()
+    model.upload_experts(orc._keep['x_rows'], orc._keep['x_off'], orc._keep['x_lb'], cnn)
+    w = dict(W1=g['policy.net.affine_layers.0.weight'], b1=g['policy.net.affine_layers.0.bias'],
+             W2=g['policy.net.affine_layers.1.weight'], b2=g['policy.net.affine_layers.1.bias'],
+             W3=g['policy.action_mean.weight'], b3=g['policy.action_mean.bias'], log_std=g['policy.action_log_std'].ravel())
+    wd = {k: cu(v) for k, v in w.items()}
+    # the two takes use different fail lines in the golden: one launch per take (the kernel's fix_head_lb is global)
+    for ti in range(2):
+        pre = 'take%d.' % ti
+        n = lens[ti] - 2 * fm
+        out = model.rollout(wd, 1, n, episode_len=n, fr_margin=fm, fix_head_lb=float(g[pre + 'head_lb']), mean_action=True,
+                            zf_mean=cu(g['zf_mean']), zf_std=cu(g['zf_std']), zf_clip=5.0,
+                            reset_take=cu([[ti]], torch.int32), reset_start=cu([[fm]], torch.int32), eval_mode=True,
+                            fix_len=cu([n], torch.int32), state_pred=cu(sp), want_traj=True)
+        torch.cuda.synchronize()
+        nrec = g[pre + 'traj_pred'].shape[0]
+        assert nrec == n
+        assert int(out['logger'][14].item()) == int(g[pre + 'num_reset']) > 3
+        # every replacement re-anchors the state, so errors do not accumulate over the take
+        assert np.allclose(out['qpos_traj'].cpu().numpy(), g[pre + 'traj_pred'], rtol=1e-7, atol=1e-8)
+        assert np.allclose(out['qvel_traj'].cpu().numpy(), g[pre + 'vel_pred'], rtol=1e-6, atol=1e-6)
+        assert np.allclose(out['states'].cpu().numpy(), g[pre + 'states'], rtol=1e-6, atol=1e-6)
+        assert np.allclose(out['actions'].cpu().numpy(), g[pre + 'actions'], rtol=1e-6, atol=1e-8)
+        assert np.allclose(out['rewards'].cpu().numpy(), g[pre + 'rewards'], rtol=1e-6, atol=1e-9)
+
+
+@pytest.mark.parametrize('fail_safe', ['naivefs', 'none'])
+def test_eval_takes_api_matches_oracle(fail_safe, tmp_path):
+    from egopose_b200 import evaluate
+    from egopose_b200.config import Config
+    from egopose_b200.env import HumanoidEnv
+    from egopose_b200.nets import MLP, FrameContext, PolicyGaussian
+    from egopose_b200.zfilter import ZFilter
+    torch.set_default_dtype(torch.float64)
+    torch.manual_seed(3)
+    cfg = Config('subject_03')
+    cfg.fr_margin = 4
+    env = HumanoidEnv(cfg, device=0)
+    lens, ctxd = [30, 22, 41], 8
+    takes = [cphys.synthetic_takes(cphys.Oracle().md, 1, L, seed=50 + i)[0] for i, L in enumerate(lens)]
+    rng = np.random.RandomState(8)
+    cnn = [rng.randn(L, ctxd) for L in lens]
+    names = ['t%d' % i for i in range(3)]
+    env.set_expert_qpos(names, takes, cnn)
+    S, nu = env.obs_dim, env.md.nu
+    pol = PolicyGaussian(MLP(S + ctxd, (32, 16), 'relu'), nu, log_std=-2.3, fix_std=True).cuda()
+    rs = ZFilter((S,), clip=5)
+    for _ in range(30):
+        rs(0.5 * rng.randn(S))
+    head_lb = 0.75                       # above the default 0.3 so that the short test takes do fall below it
+    results, meta, info = evaluate.eval_takes(env, pol, FrameContext(ctxd), rs, fail_safe=fail_safe, fix_head_lb=head_lb)
+    # ---- oracle: same takes (hands zeroed as set_expert_qpos / gen_expert.py:38-39 do), same tables
+    orc = cphys.Oracle()
+    orc.cfg.fr_margin = 4
+    orc.cfg.fix_head_lb = head_lb if fail_safe == 'naivefs' else -1e30
+    tz = []
+    for q in takes:
+        q = q.copy()
+        for hand in ('LeftHand', 'RightHand'):
+            a, b = env.body_qposaddr[hand]
+            q[:, a:b] = 0.0
+        tz.append(q)
+    orc.make_expert(tz)
+    sd = {k: v.detach().cpu().numpy() for k, v in pol.state_dict().items()}
+    opol = orc.make_policy(sd['net.affine_layers.0.weight'], sd['net.affine_layers.0.bias'], sd['net.affine_layers.1.weight'],
+                           sd['net.affine_layers.1.bias'], sd['action_mean.weight'], sd['action_mean.bias'], sd['action_log_std'])
+    sp_all = evaluate.expert_obs_table(env.kernel)
+    off = np.asarray(env.kernel.take_off)
+    total = 0
+    for ti, name in enumerate(names):
+        ref = evalloop.eval_take(orc, opol, ti, 4, lens[ti] - 8, sp_all[off[ti]:off[ti + 1]], ctx=cnn[ti], zf_mean=rs.rs.mean,
+                                 zf_std=rs.rs.std, zf_clip=5.0, fail_safe=fail_safe)
+        total += ref['num_reset']
+        assert results['traj_pred'][name].shape == (lens[ti] - 8, 59)
+        if fail_safe == 'naivefs':
+            assert np.allclose(results['traj_pred'][name], ref['traj_pred'], rtol=1e-7, atol=1e-8)
+            assert np.allclose(results['vel_pred'][name], ref['vel_pred'], rtol=1e-6, atol=1e-6)
+        else:       # free fall for the whole take: chaotic growth of rounding differences, compare the early part tightly
+            assert np.allclose(results['traj_pred'][name][:12], ref['traj_pred'][:12], rtol=1e-6, atol=1e-7)
+            assert np.all(np.isfinite(results['traj_pred'][name]))
+        assert np.array_equal(results['traj_orig'][name], tz[ti][4:lens[ti] - 4])
+    assert meta == {'algo': 'ego_mimic', 'num_reset': total}
+    assert (total > 3) == (fail_safe == 'naivefs')
+    path = tmp_path / 'iter_0000_test_naivefs.p'
+    evaluate.save_results(results, meta, str(path))
+    r2, m2 = pickle.load(open(path, 'rb'))      # the (results, meta) pair eval_pose.py:31 unpacks
+    assert set(r2) == {'traj_pred', 'traj_orig', 'vel_pred'} and m2['num_reset'] == total
+    env.close()
