@@ -1654,7 +1654,9 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
         const double lb = isnan(A.cfg.fix_head_lb) ? A.head_lb[take] - 0.1 : A.cfg.fix_head_lb;
         bool fail = head_z < lb;
         const bool end = cur_t >= (A.in.d_fix_len ? A.in.d_fix_len[eid] : A.cfg.episode_len);
-        const double *row = A.rows + (size_t)(A.take_off[take] + start + cur_t) * EGP_X_STRIDE;
+        // expert frame of the reward, clamped to the take (a window may end on the take's last frame in evaluation)
+        const int xfr = min(A.take_off[take] + start + cur_t, A.take_off[take + 1] - 1);
+        const double *row = A.rows + (size_t)xfr * EGP_X_STRIDE;
         // body-quaternion terms of the reward for this thread's bodies (reward_function.py:35-41)
         double pose2 = 0.0, vd = 0.0;
         for (int b = 1 + w; b < nb; b += T4_WARPS) {

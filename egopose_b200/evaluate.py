@@ -100,6 +100,69 @@ def eval_takes(env, policy_net, policy_vs_net=None, running_state=None, state_pr
     return results, meta, info
 
 
+def eval_forecast(env, policy_net, policy_vs_net, running_state=None, test_len=None, show_noise=False, seed=1):
+    """ego_pose/ego_forecast_eval.py:95-204 ('save' mode with --gt-init): every take is cut into windows starting every
+    ``fr_margin`` frames (:188-196); each window is one environment of ONE kernel launch, started from the expert state
+    of its first frame and rolled out ``test_len`` steps under the mean action.  A fall does not end a window (the
+    script only logs it, :171-176).  -> (results, meta): results['traj_pred' | 'traj_orig'][take] =
+    [n_windows, fr_margin + test_len, nq], the first fr_margin rows being the ground-truth past (:126-136).
+    The initialisation from an ego-mimic result file (no --gt-init, :107-121) is not built."""
+    from .nets import VideoForecastNet
+    model, cfg = env.kernel, env.cfg
+    fm = int(cfg.fr_margin)
+    T = int(test_len or cfg.env_episode_len)
+    off = np.asarray(model.take_off, dtype=np.int64)
+    lens = np.diff(off)
+    win = [(k, s0) for k in range(len(lens)) for s0 in range(fm, int(lens[k]) - T + 1, fm)]
+    if not win:
+        raise ValueError('no take holds fr_margin + test_len frames')
+    E = len(win)
+    dev = policy_net.action_mean.weight.device
+    L = policy_net.net.affine_layers
+    w = dict(W1=L[0].weight.data, b1=L[0].bias.data, W2=L[1].weight.data, b2=L[1].bias.data,
+             W3=policy_net.action_mean.weight.data, b3=policy_net.action_mean.bias.data,
+             log_std=policy_net.action_log_std.data.view(-1))
+    w = {k: t.contiguous() for k, t in w.items()}
+    cu = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=dev)  # noqa: E731
+    extra = {}
+    if isinstance(policy_vs_net, VideoForecastNet):
+        # test-mode v_out of every window (video_forecast_net.py:58-59): causal LSTM over the fr_margin frames before
+        # its start; one constant row per window, rows ordered like ``win``; the state LSTM runs inside the kernel
+        p = policy_vs_net._p()
+        rows, win_off = [], [0]
+        with torch.no_grad():
+            for k in range(len(lens)):
+                f = torch.as_tensor(env.cnn_feat[k], dtype=p.dtype, device=p.device)
+                nst = max(0, int(lens[k]) - T - fm + 1)                       # starts fm .. len - T, every frame
+                if nst:
+                    idx = torch.arange(fm, device=p.device)[:, None] + torch.arange(nst, device=p.device)[None, :]
+                    rows.append(policy_vs_net.forward_v_net(f[idx])[-1])
+                win_off.append(win_off[-1] + nst)
+        extra = dict(ctx=torch.cat(rows).contiguous(), win_off=torch.tensor(win_off, dtype=torch.int32, device=dev),
+                     ctx_const=True, snet=policy_vs_net.snet_packed())
+    zm = zs = None
+    clip = 0.0
+    if running_state is not None:
+        zm, zs = cu(running_state.rs.mean, torch.float64), cu(running_state.rs.std, torch.float64)
+        clip = running_state.clip or 0.0
+    out = model.rollout(
+        w, E, T, episode_len=T, fr_margin=fm, fix_head_lb=-1e30, mean_action=not show_noise, zf_mean=zm, zf_std=zs,
+        zf_clip=clip, seed=seed, reset_take=cu([[k] for k, _ in win], torch.int32),
+        reset_start=cu([[s0] for _, s0 in win], torch.int32), want_next=False, want_raw=False, want_traj=True, **extra)
+    qpos = out['qpos_traj'].view(E, T, model.nq).cpu().numpy()
+    X = lib.X
+    eq = model.rows_host[:, X['QPOS']:X['QPOS'] + model.nq]
+    results = {'traj_pred': {}, 'traj_orig': {}}
+    for k, take in enumerate(env.expert_list):
+        ids = [e for e, (kk, _) in enumerate(win) if kk == k]
+        if not ids:
+            continue
+        past = [eq[off[k] + win[e][1] - fm:off[k] + win[e][1]] for e in ids]
+        results['traj_pred'][take] = np.stack([np.concatenate([pa, qpos[e]]) for pa, e in zip(past, ids)])
+        results['traj_orig'][take] = np.stack([eq[off[k] + win[e][1] - fm:off[k] + win[e][1] + T] for e in ids])
+    return results, {'algo': 'ego_forecast'}
+
+
 def save_results(results, meta, path):
     """the pickle ego_mimic_eval.py:192 writes and eval_pose.py:31 reads"""
     with open(path, 'wb') as f:

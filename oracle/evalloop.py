@@ -84,3 +84,28 @@ def eval_take(orc, policy, take, fr_margin, test_len, state_pred, ctx=None, zf_m
         out[k] = np.array(out[k])
     out['rewards'] = np.array(out['rewards'])
     return out
+
+
+def forecast_window(orc, policy, take, start, test_len, ctx=None, zf_mean=None, zf_std=None, zf_clip=5.0):
+    """One window of ego_pose/ego_forecast_eval.py:95-180 with --gt-init: reset to the expert state of frame ``start``,
+    ``test_len`` mean-action steps, simulator qpos recorded before every step; a fall does not stop the window
+    (:171-176).  ``ctx`` [L, ctx_dim] is a per-frame context table (identity video net)."""
+    nq = orc.nq
+
+    def zf(x):
+        if zf_mean is None:
+            return x
+        y = (x - zf_mean) / (zf_std + 1e-8)
+        return np.clip(y, -zf_clip, zf_clip) if zf_clip > 0 else y
+
+    orc.cfg.episode_len = int(test_len)
+    env = cphys.EoEnv()
+    orc.env_reset(env, int(take), int(start))
+    state = zf(orc.env_obs(env))
+    traj = []
+    for t in range(test_len):
+        traj.append(np.array(env.d.qpos[:nq]))
+        x = state if ctx is None else np.concatenate([ctx[start + t], state])
+        orc.env_step(env, orc.policy_mean(policy, x))
+        state = zf(orc.env_obs(env))
+    return np.array(traj)

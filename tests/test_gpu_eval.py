@@ -112,3 +112,65 @@ def test_eval_takes_api_matches_oracle(fail_safe, tmp_path):
     r2, m2 = pickle.load(open(path, 'rb'))      # the (results, meta) pair eval_pose.py:31 unpacks
     assert set(r2) == {'traj_pred', 'traj_orig', 'vel_pred'} and m2['num_reset'] == total
     env.close()
+
+
+def test_eval_forecast_windows():
+    """ego_forecast_eval.py 'save' mode with --gt-init: windows every fr_margin frames, one environment each"""
+    from egopose_b200 import evaluate
+    from egopose_b200.config import Config
+    from egopose_b200.env import HumanoidEnv
+    from egopose_b200.nets import MLP, FrameContext, PolicyGaussian, VideoForecastNet
+    from egopose_b200.zfilter import ZFilter
+    torch.set_default_dtype(torch.float64)
+    torch.manual_seed(5)
+    cfg = Config('subject_03', task='egoforecast')
+    cfg.fr_margin, cfg.env_episode_len = 6, 9
+    env = HumanoidEnv(cfg, device=0)
+    lens, ctxd, T, fm = [33, 27], 8, 9, 6
+    md = cphys.Oracle().md
+    takes = [cphys.synthetic_takes(md, 1, L, seed=70 + i)[0] for i, L in enumerate(lens)]
+    rng = np.random.RandomState(9)
+    cnn = [rng.randn(L, ctxd) for L in lens]
+    env.set_expert_qpos(['a', 'b'], takes, cnn)
+    S, nu = env.obs_dim, env.md.nu
+    rs = ZFilter((S,), clip=5)
+    for _ in range(30):
+        rs(0.5 * rng.randn(S))
+    # ---- per-frame context (identity video net) vs the oracle loop
+    pol = PolicyGaussian(MLP(S + ctxd, (32, 16), 'relu'), nu, log_std=-2.3, fix_std=True).cuda()
+    results, meta = evaluate.eval_forecast(env, pol, FrameContext(ctxd), rs)
+    assert meta == {'algo': 'ego_forecast'}
+    orc = cphys.Oracle()
+    orc.cfg.fr_margin = fm
+    orc.cfg.fix_head_lb = -1e30
+    tz = []
+    for q in takes:
+        q = q.copy()
+        for hand in ('LeftHand', 'RightHand'):
+            a, b = env.body_qposaddr[hand]
+            q[:, a:b] = 0.0
+        tz.append(q)
+    orc.make_expert(tz)
+    sd = {k: v.detach().cpu().numpy() for k, v in pol.state_dict().items()}
+    opol = orc.make_policy(sd['net.affine_layers.0.weight'], sd['net.affine_layers.0.bias'], sd['net.affine_layers.1.weight'],
+                           sd['net.affine_layers.1.bias'], sd['action_mean.weight'], sd['action_mean.bias'], sd['action_log_std'])
+    for k, name in enumerate(['a', 'b']):
+        starts = list(range(fm, lens[k] - T + 1, fm))
+        assert results['traj_pred'][name].shape == (len(starts), fm + T, 59) == results['traj_orig'][name].shape
+        assert starts[-1] + T == lens[k] or starts[-1] + T + fm > lens[k]
+        for wi, s0 in enumerate(starts):
+            ref = evalloop.forecast_window(orc, opol, k, s0, T, ctx=cnn[k], zf_mean=rs.rs.mean, zf_std=rs.rs.std)
+            assert np.array_equal(results['traj_pred'][name][wi, :fm], tz[k][s0 - fm:s0])
+            assert np.allclose(results['traj_pred'][name][wi, fm:], ref, rtol=1e-6, atol=1e-7)
+            assert np.array_equal(results['traj_orig'][name][wi], tz[k][s0 - fm:s0 + T])
+    # ---- VideoForecastNet: constant per-window context + in-kernel state LSTM (numerics of that path are pinned by
+    #      test_gpu_forecast.py); here: the plumbing of the evaluation windows
+    pvs = VideoForecastNet(ctxd, S, 16, fm, 'lstm', None, 20, 'lstm').cuda()
+    pol2 = PolicyGaussian(MLP(pvs.out_dim, (32, 16), 'relu'), nu, log_std=-2.3, fix_std=True).cuda()
+    r2, _ = evaluate.eval_forecast(env, pol2, pvs, rs)
+    for k, name in enumerate(['a', 'b']):
+        assert r2['traj_pred'][name].shape == results['traj_pred'][name].shape
+        assert np.all(np.isfinite(r2['traj_pred'][name]))
+        for wi, s0 in enumerate(range(fm, lens[k] - T + 1, fm)):       # first simulated frame = expert state of the window start
+            assert np.allclose(r2['traj_pred'][name][wi, fm], tz[k][s0], atol=1e-14)
+    env.close()
