@@ -1934,7 +1934,7 @@ __global__ void env_step_debug_kernel(int n, double *qpos, double *qvel, const d
 }
 
 // gen_expert.py:28-83: one thread per frame; velocities by finite differences against the previous frame
-__global__ void expert_features_kernel(int L, const double *qpos, double *rows, double *head_z) {
+__global__ void expert_features_kernel(int L, const double *qpos, double *rows, double *head_z, double *extras) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= L) return;
     const int nq = c_m.nq, nb = c_m.nbody;
@@ -1951,6 +1951,17 @@ __global__ void expert_features_kernel(int L, const double *qpos, double *rows, 
     env_body_quat(e.q, bq);
     for (int k = 0; k < 4 * nb; k++) row[EGP_X_BQUAT + k] = bq[k];
     head_z[i] = e.xp[c_m.head_body][2];
+    if (extras) {       // gen_expert.py:49-50,44: head_pos = get_body_com('Head'), com = subtree_com[0], ee_wpos = get_ee_pos(None)
+        double *x = extras + (size_t)i * EGP_XE_STRIDE;
+        double mt = 0.0, mc[3] = {0.0, 0.0, 0.0};
+        for (int b = 0; b < nb; b++) { mt += e.cin[b][0]; for (int k = 0; k < 3; k++) mc[k] += e.cin[b][1 + k]; }
+        for (int k = 0; k < 3; k++) {
+            x[EGP_XE_HEAD_POS + k] = e.xp[c_m.head_body][k];
+            x[EGP_XE_COM + k] = mc[k] / mt + e.q[k];            // first moments are kept about the root position
+        }
+        for (int j = 0; j < EGP_NEE; j++)
+            for (int k = 0; k < 3; k++) x[EGP_XE_EE_WPOS + 3 * j + k] = e.xp[c_m.ee_body[j]][k];   // world frame (humanoid_v1.py:106-110)
+    }
     // frame 0 copies the finite differences of frame 1 (gen_expert.py:67-70,76)
     const int ic = i > 0 ? i : (L > 1 ? 1 : 0);
     if (L > 1) {
@@ -2171,10 +2182,15 @@ int egp_expert_upload(EgpModel *m, int n_takes, const int32_t *take_off, const d
 }
 
 int egp_expert_features_f64(EgpModel *m, int L, const double *d_qpos, double *d_rows, double *d_head_z, void *stream) {
+    return egp_expert_features_ex_f64(m, L, d_qpos, d_rows, d_head_z, nullptr, stream);
+}
+
+int egp_expert_features_ex_f64(EgpModel *m, int L, const double *d_qpos, double *d_rows, double *d_head_z, double *d_extras,
+                               void *stream) {
     if (!m || L < 1 || !d_qpos || !d_rows || !d_head_z) { set_error("egp_expert_features_f64: bad argument"); return EGP_EINVAL; }
     int rc = bind_model(m);
     if (rc) return rc;
-    expert_features_kernel<<<(L + 63) / 64, 64, 0, (cudaStream_t)stream>>>(L, d_qpos, d_rows, d_head_z);
+    expert_features_kernel<<<(L + 63) / 64, 64, 0, (cudaStream_t)stream>>>(L, d_qpos, d_rows, d_head_z, d_extras);
     EGP_CHECK_LAUNCH("expert_features_kernel");
     return EGP_OK;
 }

@@ -93,6 +93,7 @@ SYMBOLS = {
     'egp_model_destroy': (None, [_vp]),
     'egp_expert_upload': (_int, [_vp, _int, _ip, _dp, _dp, _dp, _int]),
     'egp_expert_features_f64': (_int, [_vp, _int, _vp, _vp, _vp, _vp]),
+    'egp_expert_features_ex_f64': (_int, [_vp, _int, _vp, _vp, _vp, _vp, _vp]),
     'egp_forward_debug_f64': (_int, [_vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'egp_env_step_debug_f64': (_int, [_vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'egp_rollout_f64': (_int, [_vp, C.POINTER(PolicyWeights), C.POINTER(RolloutCfg), C.POINTER(RolloutIn),
@@ -266,17 +267,21 @@ class Model:
         self.n_takes, self.ctx_dim, self.take_off, self.head_lb = len(head_lb), cd, take_off, head_lb
         self.rows_host = rows           # host copy of the packed expert rows (evaluate.expert_obs_table)
 
-    def expert_features(self, qpos):
-        """gen_expert.get_expert for one take on the GPU: qpos [L, nq] -> (rows [L, 292] tensor, head_height_lb)"""
+    def expert_features(self, qpos, extras=False):
+        """gen_expert.get_expert for one take on the GPU: qpos [L, nq] -> (rows [L, 292] tensor, head_height_lb);
+        extras=True also returns [L, 21] = head_pos 3 | com 3 | ee_wpos 15 (the dict keys that are not rollout inputs)"""
         global launches
         import torch
         q = torch.as_tensor(np.ascontiguousarray(qpos), dtype=torch.float64, device='cuda:%d' % self.device)
         L = q.shape[0]
         rows = torch.empty((L, X['STRIDE']), dtype=torch.float64, device=q.device)
         hz = torch.empty(L, dtype=torch.float64, device=q.device)
-        check(self.lib.egp_expert_features_f64(self.handle, L, ptr(q), ptr(rows), ptr(hz), stream_ptr()),
-              'egp_expert_features_f64')
+        ex = torch.empty((L, 21), dtype=torch.float64, device=q.device) if extras else None
+        check(self.lib.egp_expert_features_ex_f64(self.handle, L, ptr(q), ptr(rows), ptr(hz), ptr(ex), stream_ptr()),
+              'egp_expert_features_ex_f64')
         launches += 1
+        if extras:
+            return rows, float(hz.min().item()), ex
         return rows, float(hz.min().item())
 
     # ---- debug / parity -----------------------------------------------------------------------

@@ -175,6 +175,14 @@ int egp_expert_upload(EgpModel *m, int n_takes, const int32_t *take_off, const d
  * d_head_z [L] (head height per frame; min over frames = head_height_lb) */
 int egp_expert_features_f64(EgpModel *m, int L, const double *d_qpos, double *d_rows, double *d_head_z,
                             void *stream);
+/* same, plus the expert-dict keys that are not rollout inputs (gen_expert.py:44,49-50,79): d_extras [L][EGP_XE_STRIDE]
+ * = head_pos 3 | com 3 | ee_wpos 15 (end-effector body positions in the world frame, get_ee_pos(None)); NULL to skip */
+#define EGP_XE_HEAD_POS 0
+#define EGP_XE_COM 3
+#define EGP_XE_EE_WPOS 6
+#define EGP_XE_STRIDE 21
+int egp_expert_features_ex_f64(EgpModel *m, int L, const double *d_qpos, double *d_rows, double *d_head_z,
+                               double *d_extras, void *stream);
 
 /* --- physics, single calls (parity/debug; replaces sim.forward()/sim.step()/compute_torque) ---- */
 /* one mj_forward at (qpos, qvel, ctrl): qfrc_bias [n][nv], xpos [n][nbody][3], qacc = M^-1 (ctrl - bias) [n][nv]

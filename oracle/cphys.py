@@ -197,6 +197,21 @@ class Oracle:
         self.L.eo_expert_features(C.byref(self.model), qpos.shape[0], _p(qpos), C.c_double(self.dt), _p(rows), C.byref(hz))
         return rows, hz.value
 
+    def expert_extras(self, qpos):
+        """the expert-dict keys that are not rollout inputs (gen_expert.py:44,49-50): head_pos = get_body_com('Head')
+        (body frame origin, humanoid_v1.py / mujoco_env.py get_body_com), com = data.subtree_com[0] (whole-body centre
+        of mass, mujoco_env.py get_com), ee_wpos = get_ee_pos(None) (humanoid_v1.py:98-111): [L,3], [L,3], [L,15]"""
+        mass = np.asarray(self.md['body_mass'], dtype=np.float64)
+        ee = [self.md['body_names'].index(n) for n in EE_NAMES]
+        head = self.md['body_names'].index('Head')
+        hp, com, eew = [], [], []
+        for q in np.asarray(qpos, dtype=np.float64):
+            xpos, _, xipos, _, _ = self.kinematics(q)
+            hp.append(xpos[head])
+            com.append((mass[:, None] * xipos).sum(0) / mass.sum())
+            eew.append(np.concatenate([xpos[b] for b in ee]))          # transform None: world positions, root not subtracted
+        return np.array(hp), np.array(com), np.array(eew)
+
     def make_expert(self, takes_qpos, ctx=None):
         rows, lbs, off = [], [], [0]
         for q in takes_qpos:

@@ -11,6 +11,7 @@ Runs only in the build container (needs /root/reference):   python tests/golden/
   env_traj.npz      ego_pose/envs/humanoid_v1.py + ego_pose/core/reward_function.py stepped on the
                     restated physics through oracle/mujoco_shim.py (pins env logic, NOT MuJoCo itself),
                     and the gen_expert.py feature pipeline re-driven with the reference's own helpers
+  expert_file.npz   ego_pose/data_process/gen_expert.py:28-83 get_expert, all 13 keys + scalars, with an lb:ub cut
   eval_traj.npz     ego_pose/ego_mimic_eval.py:93-177 evaluation roll-out ('naivefs' fail-safe) re-driven with the
                     reference's own env / align_human_state / PolicyGaussian / ZFilter on the restated physics
 """
@@ -578,8 +579,68 @@ def gen_eval():
     np.savez_compressed(os.path.join(OUT, 'eval_traj.npz'), **out)
 
 
+
+def gen_expert_file():
+    """ego_pose/data_process/gen_expert.py:28-83 get_expert re-driven with the reference's own env methods for ALL keys
+    of the expert dict (incl. the ones the rollout never reads: rlinv, com, head_pos, obs, ee_wpos) and the lb:ub cut"""
+    orc = cphys.Oracle()
+    mujoco_shim.install(orc)
+    work = tempfile.mkdtemp(prefix='egopose_golden_gx_')
+    os.symlink(os.path.join(refimport.REF, 'config'), os.path.join(work, 'config'))
+    os.symlink(os.path.join(refimport.REF, 'assets'), os.path.join(work, 'assets'))
+    os.makedirs(os.path.join(work, 'datasets', 'meta'))
+    import yaml
+    yaml.safe_dump({'train': ['t'], 'test': ['t']}, open(os.path.join(work, 'datasets', 'meta', 'meta_subject_03.yml'), 'w'))
+    os.chdir(work)
+    from ego_pose.envs.humanoid_v1 import HumanoidEnv
+    from ego_pose.utils.egomimic_config import Config
+    from utils.math import de_heading, get_angvel_fd, get_qvel_fd, transform_vec
+    cfg = Config('subject_03', create_dirs=False)
+    env = HumanoidEnv(cfg)
+    rng = np.random.RandomState(61)
+    expert_qpos = cphys.synthetic_takes(orc.md, 1, 20, seed=61)[0]
+    expert_qpos[:, 32:35] = 0.3 * rng.randn(20, 3)          # noisy hand data that get_expert removes (:38-39)
+    expert_qpos[:, 42:45] = 0.3 * rng.randn(20, 3)
+    raw = expert_qpos.copy()
+    lb, ub = 2, 17
+    feat_keys = ['qvel', 'rlinv', 'rlinv_local', 'rangv', 'rq_rmh', 'com', 'head_pos', 'obs', 'ee_pos', 'ee_wpos', 'bquat', 'bangvel']
+    expert = {k: [] for k in feat_keys}
+    for i in range(expert_qpos.shape[0]):
+        qpos = expert_qpos[i]
+        qpos[slice(*env.body_qposaddr['LeftHand'])] = 0.0
+        qpos[slice(*env.body_qposaddr['RightHand'])] = 0.0
+        env.data.qpos[:] = qpos
+        env.sim.forward()
+        expert['rq_rmh'].append(de_heading(qpos[3:7]))
+        expert['obs'].append(env.get_obs())
+        expert['ee_pos'].append(env.get_ee_pos(cfg.obs_coord))
+        expert['ee_wpos'].append(env.get_ee_pos(None))
+        expert['bquat'].append(env.get_body_quat())
+        expert['com'].append(env.get_com())
+        expert['head_pos'].append(env.get_body_com('Head').copy())
+        if i > 0:
+            qvel = get_qvel_fd(expert_qpos[i - 1], qpos, env.dt)
+            expert['qvel'].append(qvel)
+            expert['rlinv'].append(qvel[:3].copy())
+            expert['rlinv_local'].append(transform_vec(qvel[:3].copy(), qpos[3:7], cfg.obs_coord))
+            expert['rangv'].append(qvel[3:6].copy())
+    for k in ('qvel', 'rlinv', 'rlinv_local', 'rangv'):
+        expert[k].insert(0, expert[k][0].copy())
+    for i in range(1, expert_qpos.shape[0]):
+        expert['bangvel'].append(get_angvel_fd(expert['bquat'][i - 1], expert['bquat'][i], env.dt))
+    expert['bangvel'].insert(0, expert['bangvel'][0].copy())
+    out = {'raw_qpos': raw, 'lb': lb, 'ub': ub, 'qpos': expert_qpos[lb:ub]}
+    for k in feat_keys:
+        out[k] = np.vstack(expert[k][lb:ub])
+    out['len'] = out['qpos'].shape[0]
+    out['height_lb'] = out['qpos'][:, 2].min()
+    out['head_height_lb'] = out['head_pos'][:, 2].min()
+    np.savez_compressed(os.path.join(OUT, 'expert_file.npz'), **out)
+    print('expert_file ok', out['len'], out['head_height_lb'])
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['ppo', 'math', 'zfilter', 'env', 'vsnet', 'fcnet', 'eval']
+    which = sys.argv[1:] or ['ppo', 'math', 'zfilter', 'env', 'vsnet', 'fcnet', 'eval', 'expert_file']
     if 'ppo' in which:
         gen_ppo()
     if 'ppo_mb' in which or 'ppo' in which:
@@ -594,5 +655,7 @@ if __name__ == '__main__':
         gen_zfilter()
     if 'eval' in which:
         gen_eval()
+    if 'expert_file' in which:
+        gen_expert_file()
     if 'env' in which:
         gen_env()
