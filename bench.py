@@ -317,6 +317,31 @@ def main():
         gt.append(a.elapsed_time(b) / len(sets))
     del sets, outs
     gae_ms = float(np.median(gt))
+    # the same scan at BASELINE config 5's batch (65536 envs x 300 steps = 19.66 M samples, 786 MB algorithmic): at that
+    # size the three launches are bandwidth- instead of latency-dominated
+    gae_big = None
+    try:
+        NB = 65536 * 300
+        rb = (torch.rand(NB, dtype=torch.float64, device=device), (torch.rand(NB, dtype=torch.float64, device=device) > 0.11).double(),
+              torch.randn(NB, dtype=torch.float64, device=device))
+        ob = (torch.empty(NB, dtype=torch.float64, device=device), torch.empty(NB, dtype=torch.float64, device=device),
+              torch.empty(3, dtype=torch.float64, device=device))
+        wb = torch.empty(lib.load().egp_gae_work_bytes(NB), dtype=torch.uint8, device=device)
+        bt = []
+        for rep in range(5):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            lib.gae(rb[0], rb[1], rb[2], cfg.gamma, cfg.tau, work=wb, out=ob)
+            b.record()
+            b.synchronize()
+            bt.append(a.elapsed_time(b))
+        bms = float(np.median(bt[1:]))
+        gae_big = {'bound': 'hbm', 'samples': NB, 'ms': bms, 'achieved': 5 * wbytes * NB / (bms / 1e3) / 1e9, 'peak': hbm,
+                   'unit': 'GB/s', 'frac': 5 * wbytes * NB / (bms / 1e3) / 1e9 / hbm, 'bytes_per_sample': 40,
+                   'note': 'BASELINE config 5 batch (19.66 M samples, inputs + outputs 786 MB > L2), one call = 3 launches'}
+        del rb, ob, wb
+    except Exception as e:        # noqa: BLE001
+        gae_big = {'error': str(e)[:200]}
     # `traffic`: dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the committed ncu --set full capture
     # of this exact configuration (profiles/r1_rollout_t4_full.md / r1_gae_full.md); not re-measured live
     default_cfg = (E, T, tuple(args.hidden)) == (4096, 300, (300, 300))
@@ -350,6 +375,7 @@ def main():
              'gae_kernel': {'bound': 'hbm', 'achieved': 5 * wbytes * N / (gae_ms / 1e3) / 1e9, 'peak': hbm, 'unit': 'GB/s',
                             'frac': 5 * wbytes * N / (gae_ms / 1e3) / 1e9 / hbm, 'ms': gae_ms, 'bytes_per_sample': 40,
                             'traffic': 63.36e6 if default_cfg else None},
+             'gae_kernel_config5': gae_big,
              'update_dgemm': {'bound': 'tensor(fp64)', 'achieved': None, 'peak': fp64_peak, 'unit': 'TFLOP/s'},
              'rollout_env_substeps_per_s': N * 15 / (roll_ms / 1e3)}
     # the update's dominant kernel alone: [N, 243] x [300, 243]^T float64 product on the int8 tensor cores (first policy /
