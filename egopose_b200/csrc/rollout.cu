@@ -1541,9 +1541,17 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
 
     draw_reset(0);
     do_reset();
-    if (A.cfg.eval_mode) {
+    if (A.cfg.eval_mode || A.in.d_init_qpos) {
         __syncthreads();
-        load_state_pred();
+        if (A.in.d_init_qpos) {                             // env.set_state(qpos, qvel) right after reset (ego_forecast_eval.py:119-121)
+            T4_FOR_OWN_DOFS(i, b) {
+                x.at(O.v, i) = A.in.d_init_qvel[(size_t)eid * nv + i];
+                if (i >= 6) x.at(O.q, i + 1) = A.in.d_init_qpos[(size_t)eid * nq + i + 1];
+            }
+            if (c_m.chain_warp[0] == w) for (int k = 0; k < 7; k++) x.at(O.q, k) = A.in.d_init_qpos[(size_t)eid * nq + k];
+        } else {
+            load_state_pred();
+        }
         __syncthreads();
         t4_forward_only(x, l);
     }
@@ -2318,7 +2326,8 @@ int egp_rollout_f64(EgpModel *m, const EgpPolicyWeights *pol, const EgpRolloutCf
     auto padk = [kcv](int x) { return (x + kcv - 1) / kcv * kcv; };
     A.K1p = use_t4 ? padk(A.D) : A.D; A.K2p = use_t4 ? padk(A.H1) : A.H1; A.K3p = use_t4 ? padk(A.H2) : A.H2;
     if (snH && !use_t4) { set_error("egp_rollout_f64: the state LSTM needs the T4 rollout variant (policy too wide?)"); return EGP_ESIZE; }
-    const bool ev = cfg->eval_mode || (in && in->d_fix_len) || out->d_qpos_traj || out->d_qvel_traj;
+    const bool ev = cfg->eval_mode || (in && (in->d_fix_len || in->d_init_qpos || in->d_init_qvel)) || out->d_qpos_traj || out->d_qvel_traj;
+    if (in && ((in->d_init_qpos == nullptr) != (in->d_init_qvel == nullptr))) { set_error("egp_rollout_f64: d_init_qpos / d_init_qvel come in pairs"); return EGP_EINVAL; }
     if (ev && !use_t4) { set_error("egp_rollout_f64: evaluation roll-outs (eval_mode / fix_len / qpos_traj) need the T4 rollout variant"); return EGP_ESIZE; }
     if (cfg->eval_mode && !(in && in->d_state_pred)) { set_error("egp_rollout_f64: eval_mode needs d_state_pred"); return EGP_EINVAL; }
     if ((out->d_qpos_traj == nullptr) != (out->d_qvel_traj == nullptr)) { set_error("egp_rollout_f64: d_qpos_traj / d_qvel_traj come in pairs"); return EGP_EINVAL; }

@@ -100,13 +100,60 @@ def eval_takes(env, policy_net, policy_vs_net=None, running_state=None, state_pr
     return results, meta, info
 
 
-def eval_forecast(env, policy_net, policy_vs_net, running_state=None, test_len=None, show_noise=False, seed=1):
+def _quat_mul(q1, q0):
+    """utils/transformation.py:1379-1391 quaternion_multiply, (w, x, y, z)"""
+    w0, x0, y0, z0 = q0
+    w1, x1, y1, z1 = q1
+    return np.array([-x1 * x0 - y1 * y0 - z1 * z0 + w1 * w0, x1 * w0 + y1 * z0 - z1 * y0 + w1 * x0,
+                     -x1 * z0 + y1 * w0 + z1 * x0 + w1 * y0, x1 * y0 - y1 * x0 + z1 * w0 + w1 * z0])
+
+
+def _heading_q(q):
+    hq = np.array([q[0], 0.0, 0.0, q[3]])
+    return hq / np.linalg.norm(hq)
+
+
+def sync_traj(qpos_traj, qvel_traj, ref_qpos):
+    """ego_pose/utils/tools.py:18-32: rotate / translate a predicted trajectory so that its first frame has the heading
+    and xy position of ``ref_qpos`` (both heading quaternions are rotations about z)"""
+    h0 = _heading_q(qpos_traj[0, 3:7])
+    rel = _quat_mul(_heading_q(ref_qpos[3:7]), np.array([h0[0], -h0[1], -h0[2], -h0[3]]))
+    c, s = rel[0] * rel[0] - rel[3] * rel[3], 2.0 * rel[0] * rel[3]
+    start = np.array([qpos_traj[0, 0], qpos_traj[0, 1], ref_qpos[2]])
+    qp, qv = qpos_traj.copy(), qvel_traj.copy()
+    d = qpos_traj[:, :3] - start
+    qp[:, 0] = c * d[:, 0] - s * d[:, 1] + ref_qpos[0]
+    qp[:, 1] = s * d[:, 0] + c * d[:, 1] + ref_qpos[1]
+    for i in range(qp.shape[0]):
+        qp[i, 3:7] = _quat_mul(rel, qpos_traj[i, 3:7])
+    qv[:, 0] = c * qvel_traj[:, 0] - s * qvel_traj[:, 1]
+    qv[:, 1] = s * qvel_traj[:, 0] + c * qvel_traj[:, 1]
+    return qp, qv
+
+
+def forecast_window_init(expert_qpos, em_traj, em_vel, start, fm, test_len, em_offset):
+    """ego_forecast_eval.py:107-136 without --gt-init: the window starts from the ego-mimic prediction of frame
+    ``start`` (synced to the expert pose fm frames earlier when the prediction reaches that far back).
+    -> (qpos0, qvel0, past [fm, nq]): initial simulator state and the fm 'past' rows of traj_pred"""
+    lo = max(0, start - fm - em_offset)
+    sp, vp = em_traj[lo:start + test_len - em_offset], em_vel[lo:start + test_len - em_offset]
+    miss = fm + test_len - sp.shape[0]
+    if start - fm - em_offset >= 0:
+        sp, vp = sync_traj(sp, vp, expert_qpos[start - fm])
+    ind = fm - miss
+    past = np.stack([expert_qpos[start - fm + j] if j < miss else sp[j - miss] for j in range(fm)])
+    return sp[ind].copy(), vp[ind].copy(), past
+
+
+def eval_forecast(env, policy_net, policy_vs_net, running_state=None, test_len=None, show_noise=False, seed=1, em_res=None,
+                  em_fr_margin=None):
     """ego_pose/ego_forecast_eval.py:95-204 ('save' mode with --gt-init): every take is cut into windows starting every
     ``fr_margin`` frames (:188-196); each window is one environment of ONE kernel launch, started from the expert state
     of its first frame and rolled out ``test_len`` steps under the mean action.  A fall does not end a window (the
     script only logs it, :171-176).  -> (results, meta): results['traj_pred' | 'traj_orig'][take] =
-    [n_windows, fr_margin + test_len, nq], the first fr_margin rows being the ground-truth past (:126-136).
-    The initialisation from an ego-mimic result file (no --gt-init, :107-121) is not built."""
+    [n_windows, fr_margin + test_len, nq], the first fr_margin rows being the past (:126-136).
+    ``em_res`` = the ``results`` dict of an ego-mimic evaluation (``eval_takes`` / ego_mimic_eval.py:186) and
+    ``em_fr_margin`` its fr_margin: windows then start from the ego-mimic prediction (no --gt-init, :107-121)."""
     from .nets import VideoForecastNet
     model, cfg = env.kernel, env.cfg
     fm = int(cfg.fr_margin)
@@ -145,19 +192,30 @@ def eval_forecast(env, policy_net, policy_vs_net, running_state=None, test_len=N
     if running_state is not None:
         zm, zs = cu(running_state.rs.mean, torch.float64), cu(running_state.rs.std, torch.float64)
         clip = running_state.clip or 0.0
+    X = lib.X
+    eq = model.rows_host[:, X['QPOS']:X['QPOS'] + model.nq]
+    pasts = None
+    if em_res is not None:
+        if em_fr_margin is None:
+            raise ValueError('em_fr_margin (fr_margin of the ego-mimic evaluation) is required with em_res')
+        q0, v0, pasts = [], [], []
+        for k, s0 in win:
+            take = env.expert_list[k]
+            a, b, c = forecast_window_init(eq[off[k]:off[k + 1]], np.asarray(em_res['traj_pred'][take]),
+                                           np.asarray(em_res['vel_pred'][take]), s0, fm, T, int(em_fr_margin))
+            q0.append(a), v0.append(b), pasts.append(c)
+        extra.update(init_qpos=cu(np.stack(q0), torch.float64), init_qvel=cu(np.stack(v0), torch.float64))
     out = model.rollout(
         w, E, T, episode_len=T, fr_margin=fm, fix_head_lb=-1e30, mean_action=not show_noise, zf_mean=zm, zf_std=zs,
         zf_clip=clip, seed=seed, reset_take=cu([[k] for k, _ in win], torch.int32),
         reset_start=cu([[s0] for _, s0 in win], torch.int32), want_next=False, want_raw=False, want_traj=True, **extra)
     qpos = out['qpos_traj'].view(E, T, model.nq).cpu().numpy()
-    X = lib.X
-    eq = model.rows_host[:, X['QPOS']:X['QPOS'] + model.nq]
     results = {'traj_pred': {}, 'traj_orig': {}}
     for k, take in enumerate(env.expert_list):
         ids = [e for e, (kk, _) in enumerate(win) if kk == k]
         if not ids:
             continue
-        past = [eq[off[k] + win[e][1] - fm:off[k] + win[e][1]] for e in ids]
+        past = [eq[off[k] + win[e][1] - fm:off[k] + win[e][1]] if pasts is None else pasts[e] for e in ids]
         results['traj_pred'][take] = np.stack([np.concatenate([pa, qpos[e]]) for pa, e in zip(past, ids)])
         results['traj_orig'][take] = np.stack([eq[off[k] + win[e][1] - fm:off[k] + win[e][1] + T] for e in ids])
     return results, {'algo': 'ego_forecast'}

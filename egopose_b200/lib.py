@@ -60,7 +60,7 @@ class RolloutIn(C.Structure):
     _fields_ = [('d_eps', _vp), ('d_reset_take', _vp), ('d_reset_start', _vp), ('d_mean_flag', _vp),
                 ('d_zf_mean', _vp), ('d_zf_std', _vp), ('d_ctx', _vp), ('d_win_off', _vp), ('ctx_dim', C.c_int32),
                 ('ctx_mode', C.c_int32), ('ctx_T', C.c_int32), ('d_snet_W', _vp), ('d_snet_b', _vp), ('d_snet_state', _vp),
-                ('snet_hdim', C.c_int32), ('d_fix_len', _vp), ('d_state_pred', _vp)]
+                ('snet_hdim', C.c_int32), ('d_fix_len', _vp), ('d_state_pred', _vp), ('d_init_qpos', _vp), ('d_init_qvel', _vp)]
 
 
 class TrajOut(C.Structure):
@@ -315,7 +315,7 @@ class Model:
                 noise_rate=1.0, mean_action=False, zf_mean=None, zf_std=None, zf_clip=5.0, seed=1, iteration=0,
                 eps=None, reset_take=None, reset_start=None, mean_flag=None, want_next=True, want_raw=True, out=None,
                 ctx=None, win_off=None, ctx_const=False, snet=None, eval_mode=False, fix_len=None, state_pred=None,
-                want_traj=False):
+                want_traj=False, init_qpos=None, init_qvel=None):
         """weights: dict with W1,b1,W2,b2,W3,b3,log_std CUDA float64 tensors (torch [out,in] layout).
         Returns a dict of CUDA tensors in TrajBatchEgo layout (+ logger, c_info, raw_obs, final state)."""
         global launches
@@ -358,6 +358,10 @@ class Model:
         inp = RolloutIn()
         inp.d_eps, inp.d_reset_take, inp.d_reset_start = ptr(eps), ptr(reset_take), ptr(reset_start)
         inp.d_mean_flag, inp.d_zf_mean, inp.d_zf_std = ptr(mean_flag), ptr(zf_mean), ptr(zf_std)
+        if init_qpos is not None:   # [n_env, nq] / [n_env, nv] state set right after the first reset
+            if tuple(init_qpos.shape) != (n_env, self.nq) or tuple(init_qvel.shape) != (n_env, self.nv):
+                raise EgpError('init_qpos / init_qvel must be [n_env, nq] / [n_env, nv]')
+            inp.d_init_qpos, inp.d_init_qvel = ptr(init_qpos), ptr(init_qvel)
         if fix_len is not None:     # per-environment episode length, int32 [n_env]
             inp.d_fix_len = ptr(fix_len)
         if state_pred is not None:  # [total_frames, S] predicted observations (eval_mode state replacement)

@@ -126,6 +126,8 @@ typedef struct {
     const int32_t *d_fix_len;           /* [E] per-environment episode length (env.set_fix_sampling(len=), humanoid_v1.py:197) or NULL */
     const double *d_state_pred;         /* eval_mode: [total_frames][S] predicted observations (qpos[2:] | qvel in the
                                          * heading frame, humanoid_v1.py:73-96), row = take_off[take] + start + cur_t */
+    const double *d_init_qpos, *d_init_qvel;    /* [E][nq], [E][nv] or NULL: simulator state set right after the first reset of
+                                         * every environment (env.set_state of the ego-mimic prediction, ego_forecast_eval.py:119-121) */
 } EgpRolloutIn;
 
 /* TrajBatchEgo layout (core/trajbatch.py:6-16, ego_pose/core/trajbatch_ego.py:7-9), all device, row-major. */

@@ -86,10 +86,44 @@ def eval_take(orc, policy, take, fr_margin, test_len, state_pred, ctx=None, zf_m
     return out
 
 
-def forecast_window(orc, policy, take, start, test_len, ctx=None, zf_mean=None, zf_std=None, zf_clip=5.0):
+def sync_traj(qpos_traj, qvel_traj, ref_qpos):
+    """ego_pose/utils/tools.py:18-32"""
+    h0 = heading_q(qpos_traj[0, 3:7])
+    rel = quat_mul(heading_q(ref_qpos[3:7]), np.array([h0[0], -h0[1], -h0[2], -h0[3]]))     # quaternion_inverse of a unit q
+    c, s = rel[0] * rel[0] - rel[3] * rel[3], 2.0 * rel[0] * rel[3]
+    R = np.array([[c, -s, 0.0], [s, c, 0.0], [0.0, 0.0, 1.0]])                                # quat_mul_vec(rel, .)
+    start_pos = np.array([qpos_traj[0, 0], qpos_traj[0, 1], ref_qpos[2]])
+    qp, qv = [], []
+    for qpos, qvel in zip(qpos_traj, qvel_traj):
+        nq_, nv_ = qpos.copy(), qvel.copy()
+        nq_[:2] = (R @ (qpos[:3] - start_pos))[:2] + ref_qpos[:2]
+        nq_[3:7] = quat_mul(rel, qpos[3:7])
+        nv_[:3] = R @ qvel[:3]
+        qp.append(nq_)
+        qv.append(nv_)
+    return np.vstack(qp), np.vstack(qv)
+
+
+def forecast_init(expert_qpos, em_traj, em_vel, start, fm, test_len, em_offset):
+    """ego_forecast_eval.py:107-136 without --gt-init -> (qpos0, qvel0, past rows of traj_pred [fm, nq])"""
+    lo = max(0, start - fm - em_offset)
+    state_pred = em_traj[lo: start + test_len - em_offset]
+    vel_pred = em_vel[lo: start + test_len - em_offset]
+    miss_len = fm + test_len - state_pred.shape[0]
+    if start - fm - em_offset >= 0:
+        state_pred, vel_pred = sync_traj(state_pred, vel_pred, expert_qpos[start - fm])
+    ind = fm - miss_len
+    past = []
+    for t in range(-fm, 0):
+        past.append(expert_qpos[start + t] if t + fm < miss_len else state_pred[t + fm - miss_len])
+    return state_pred[ind].copy(), vel_pred[ind].copy(), np.array(past)
+
+
+def forecast_window(orc, policy, take, start, test_len, ctx=None, zf_mean=None, zf_std=None, zf_clip=5.0, init=None):
     """One window of ego_pose/ego_forecast_eval.py:95-180 with --gt-init: reset to the expert state of frame ``start``,
     ``test_len`` mean-action steps, simulator qpos recorded before every step; a fall does not stop the window
-    (:171-176).  ``ctx`` [L, ctx_dim] is a per-frame context table (identity video net)."""
+    (:171-176).  ``ctx`` [L, ctx_dim] is a per-frame context table (identity video net); ``init`` = (qpos, qvel) replaces
+    the expert start state (no --gt-init)."""
     nq = orc.nq
 
     def zf(x):
@@ -101,6 +135,8 @@ def forecast_window(orc, policy, take, start, test_len, ctx=None, zf_mean=None, 
     orc.cfg.episode_len = int(test_len)
     env = cphys.EoEnv()
     orc.env_reset(env, int(take), int(start))
+    if init is not None:                                # env.set_state(qpos, qvel) of the ego-mimic prediction (:119-121)
+        orc.env_set_state(env, init[0], init[1])
     state = zf(orc.env_obs(env))
     traj = []
     for t in range(test_len):

@@ -12,6 +12,7 @@ Runs only in the build container (needs /root/reference):   python tests/golden/
                     restated physics through oracle/mujoco_shim.py (pins env logic, NOT MuJoCo itself),
                     and the gen_expert.py feature pipeline re-driven with the reference's own helpers
   expert_file.npz   ego_pose/data_process/gen_expert.py:28-83 get_expert, all 13 keys + scalars, with an lb:ub cut
+  eval_forecast.npz ego_pose/ego_forecast_eval.py:95-180 windows with and without --gt-init (reference env + sync_traj)
   eval_traj.npz     ego_pose/ego_mimic_eval.py:93-177 evaluation roll-out ('naivefs' fail-safe) re-driven with the
                     reference's own env / align_human_state / PolicyGaussian / ZFilter on the restated physics
 """
@@ -639,8 +640,106 @@ def gen_expert_file():
     print('expert_file ok', out['len'], out['head_height_lb'])
 
 
+
+def gen_eval_forecast():
+    """ego_pose/ego_forecast_eval.py:95-180 re-driven in the script's call order (reference HumanoidEnv, sync_traj,
+    PolicyGaussian, ZFilter) with and without --gt-init; the ego-mimic result it starts from is a perturbed, rotated and
+    shifted copy of the expert (the kind of output ego_mimic_eval.py writes)."""
+    orc = cphys.Oracle()
+    mujoco_shim.install(orc)
+    work = tempfile.mkdtemp(prefix='egopose_golden_fc_')
+    os.symlink(os.path.join(refimport.REF, 'config'), os.path.join(work, 'config'))
+    os.symlink(os.path.join(refimport.REF, 'assets'), os.path.join(work, 'assets'))
+    os.makedirs(os.path.join(work, 'datasets', 'meta'))
+    os.makedirs(os.path.join(work, 'datasets', 'features'))
+    import yaml
+    yaml.safe_dump({'train': ['t'], 'test': ['t']}, open(os.path.join(work, 'datasets', 'meta', 'meta_subject_03.yml'), 'w'))
+    os.chdir(work)
+    from core.policy_gaussian import PolicyGaussian
+    from ego_pose.envs.humanoid_v1 import HumanoidEnv
+    from ego_pose.utils.egomimic_config import Config
+    from ego_pose.utils.tools import sync_traj
+    from models.mlp import MLP
+    from utils.zfilter import ZFilter
+
+    FM, EMO, T, CTX, L = 6, 4, 8, 5, 34
+    q = cphys.synthetic_takes(orc.md, 1, L, seed=77)[0]
+    cfg = Config('subject_03', create_dirs=False)
+    cfg.fr_margin = FM
+    env = HumanoidEnv(cfg)
+    env.seed(1)
+    X = cphys.X
+    rows, lb = orc.expert_features(q)
+    ex = {'qpos': q, 'len': L, 'height_lb': q[:, 2].min(), 'head_height_lb': lb}
+    for key, col, w in (('qvel', 'QVEL', 58), ('rlinv_local', 'RLINV_LOCAL', 3), ('rangv', 'RANGV', 3), ('rq_rmh', 'RQ_RMH', 4),
+                        ('ee_pos', 'EE_POS', 15), ('bquat', 'BQUAT', 84), ('bangvel', 'BANGVEL', 63)):
+        ex[key] = rows[:, X[col]:X[col] + w].copy()
+    rng = np.random.RandomState(78)
+    cnn = {'t': rng.randn(L, CTX)}
+    pickle.dump({'t': ex}, open(cfg.expert_feat_file, 'wb'))
+    pickle.dump((cnn, {}), open(cfg.cnn_feat_file, 'wb'))
+    env.load_experts(['t'], cfg.expert_feat_file, cfg.cnn_feat_file)
+    env.set_fix_head_lb(-1e30)                           # the script does not stop on a fall (:171-176)
+    # ego-mimic result: frames EMO .. L - EMO of the take, yawed by 0.7 rad, shifted, perturbed
+    from utils.transformation import quaternion_about_axis, quaternion_multiply
+    from utils.math import quat_mul_vec
+    yaw = quaternion_about_axis(0.7, [0, 0, 1])
+    em_traj, em_vel = q[EMO:L - EMO].copy(), ex['qvel'][EMO:L - EMO].copy()
+    for i in range(em_traj.shape[0]):
+        em_traj[i, :3] = quat_mul_vec(yaw, em_traj[i, :3]) + np.array([0.4, -0.3, 0.0])
+        em_traj[i, 3:7] = quaternion_multiply(yaw, em_traj[i, 3:7])
+        em_vel[i, :3] = quat_mul_vec(yaw, em_vel[i, :3])
+    em_traj[:, 7:] += 0.02 * rng.randn(*em_traj[:, 7:].shape)
+    em_vel[:, 6:] += 0.05 * rng.randn(*em_vel[:, 6:].shape)
+    state_dim, action_dim = env.observation_space.shape[0], env.action_space.shape[0]
+    torch.manual_seed(9)
+    policy_net = PolicyGaussian(MLP(state_dim + CTX, (32, 16), 'relu'), action_dim, log_std=-2.3, fix_std=True)
+    running_state = ZFilter((state_dim,), clip=5)
+    for _ in range(50):
+        running_state(0.5 * rng.randn(state_dim))
+    out = dict(fr_margin=FM, em_offset=EMO, test_len=T, qpos=q, cnn=cnn['t'], em_traj=em_traj, em_vel=em_vel,
+               zf_mean=running_state.rs.mean.copy(), zf_std=running_state.rs.std.copy())
+    for k, v in policy_net.state_dict().items():
+        out['policy.' + k] = v.numpy().copy()
+
+    def eval_expert(start_ind, gt_init):                 # ego_forecast_eval.py:95-180
+        traj_pred = []
+        env.set_fix_sampling(0, start_ind, T)
+        state = env.reset()
+        miss_len = 0
+        if not gt_init:
+            state_pred = em_traj[max(0, start_ind - FM - EMO): start_ind + T - EMO]
+            vel_pred = em_vel[max(0, start_ind - FM - EMO): start_ind + T - EMO]
+            miss_len = FM + T - state_pred.shape[0]
+            if start_ind - FM - EMO >= 0:
+                ref_qpos = env.get_expert_attr('qpos', env.get_expert_index(-FM)).copy()
+                state_pred, vel_pred = sync_traj(state_pred, vel_pred, ref_qpos)
+            ind = FM - miss_len
+            env.set_state(state_pred[ind].copy(), vel_pred[ind].copy())
+            state = env.get_obs()
+        state = running_state(state, update=False)
+        for t in range(-FM, 0):
+            epos = env.get_expert_attr('qpos', env.get_expert_index(t)).copy()
+            traj_pred.append(epos.copy() if (gt_init or t + FM < miss_len) else state_pred[t + FM - miss_len].copy())
+        for t in range(T):
+            traj_pred.append(env.data.qpos.copy())
+            x = torch.from_numpy(np.concatenate([cnn['t'][start_ind + t], state])).unsqueeze(0)
+            with torch.no_grad():
+                action = policy_net.select_action(x, mean_action=True)[0].numpy()
+            next_state, _r, _done, _info = env.step(action)
+            state = running_state(next_state, update=False)
+        return np.vstack(traj_pred)
+
+    starts = list(range(FM, L - T + 1, FM))
+    out['starts'] = np.array(starts)
+    out['traj_pred_gt'] = np.stack([eval_expert(s0, True) for s0 in starts])
+    out['traj_pred_em'] = np.stack([eval_expert(s0, False) for s0 in starts])
+    print('eval_forecast starts', starts, out['traj_pred_em'].shape)
+    np.savez_compressed(os.path.join(OUT, 'eval_forecast.npz'), **out)
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['ppo', 'math', 'zfilter', 'env', 'vsnet', 'fcnet', 'eval', 'expert_file']
+    which = sys.argv[1:] or ['ppo', 'math', 'zfilter', 'env', 'vsnet', 'fcnet', 'eval', 'expert_file', 'eval_forecast']
     if 'ppo' in which:
         gen_ppo()
     if 'ppo_mb' in which or 'ppo' in which:
@@ -657,5 +756,7 @@ if __name__ == '__main__':
         gen_eval()
     if 'expert_file' in which:
         gen_expert_file()
+    if 'eval_forecast' in which:
+        gen_eval_forecast()
     if 'env' in which:
         gen_env()

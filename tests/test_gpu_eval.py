@@ -174,3 +174,39 @@ def test_eval_forecast_windows():
         for wi, s0 in enumerate(range(fm, lens[k] - T + 1, fm)):       # first simulated frame = expert state of the window start
             assert np.allclose(r2['traj_pred'][name][wi, fm], tz[k][s0], atol=1e-14)
     env.close()
+
+
+def test_eval_forecast_from_ego_mimic_result_matches_reference_golden(golden):
+    """ego_forecast_eval.py without --gt-init: window start states from an ego-mimic result file (sync_traj, missing
+    past), vs the golden produced by the reference's own env / sync_traj in the script's call order"""
+    from egopose_b200 import evaluate
+    from egopose_b200.config import Config
+    from egopose_b200.env import HumanoidEnv
+    from egopose_b200.nets import MLP, FrameContext, PolicyGaussian
+    from egopose_b200.zfilter import ZFilter
+    torch.set_default_dtype(torch.float64)
+    g = golden('eval_forecast')
+    fm, T, emo = int(g['fr_margin']), int(g['test_len']), int(g['em_offset'])
+    cfg = Config('subject_03', task='egoforecast')
+    cfg.fr_margin, cfg.env_episode_len = fm, T
+    env = HumanoidEnv(cfg, device=0)
+    env.set_expert_qpos(['t'], [g['qpos']], [g['cnn']])
+    S, nu, ctxd = env.obs_dim, env.md.nu, g['cnn'].shape[1]
+    pol = PolicyGaussian(MLP(S + ctxd, (32, 16), 'relu'), nu, log_std=-2.3, fix_std=True)
+    pol.load_state_dict({k[len('policy.'):]: torch.from_numpy(g[k]) for k in g.files if k.startswith('policy.')})
+    pol = pol.cuda()
+    rs = ZFilter((S,), clip=5)
+    rs.rs._n, rs.rs._M = 50, g['zf_mean'].copy()
+    rs.rs._S = (g['zf_std'] ** 2) * 49
+    assert np.allclose(rs.rs.std, g['zf_std']) and np.allclose(rs.rs.mean, g['zf_mean'])
+    # the synthetic take keeps the hand joints at zero, so set_expert_qpos' hand zeroing leaves it unchanged
+    r_gt, _ = evaluate.eval_forecast(env, pol, FrameContext(ctxd), rs)
+    assert np.allclose(r_gt['traj_pred']['t'], g['traj_pred_gt'], rtol=1e-6, atol=1e-7)
+    em_res = {'traj_pred': {'t': g['em_traj']}, 'vel_pred': {'t': g['em_vel']}}
+    r_em, meta = evaluate.eval_forecast(env, pol, FrameContext(ctxd), rs, em_res=em_res, em_fr_margin=emo)
+    assert meta == {'algo': 'ego_forecast'}
+    assert r_em['traj_pred']['t'].shape == g['traj_pred_em'].shape
+    assert np.allclose(r_em['traj_pred']['t'][:, :fm], g['traj_pred_em'][:, :fm], rtol=1e-12, atol=1e-12)
+    assert np.allclose(r_em['traj_pred']['t'][:, fm:], g['traj_pred_em'][:, fm:], rtol=1e-6, atol=1e-7)
+    assert not np.allclose(r_em['traj_pred']['t'][:, fm], r_gt['traj_pred']['t'][:, fm], atol=1e-3)
+    env.close()

@@ -49,3 +49,31 @@ def test_reset_env_state_keeps_root_xy_and_heading(golden):
     assert np.allclose(evalloop.heading_q(after[3:7]), evalloop.heading_q(before[3:7]), atol=1e-12)
     # the observation of the replaced state is the prediction itself (de-heading undoes the alignment)
     assert np.allclose(obs, sp, atol=1e-12)
+
+
+def setup_forecast(g):
+    fm = int(g['fr_margin'])
+    orc = cphys.Oracle()
+    orc.cfg.fr_margin = fm
+    orc.cfg.fix_head_lb = -1e30
+    orc.make_expert([g['qpos']])
+    pol = orc.make_policy(g['policy.net.affine_layers.0.weight'], g['policy.net.affine_layers.0.bias'],
+                          g['policy.net.affine_layers.1.weight'], g['policy.net.affine_layers.1.bias'],
+                          g['policy.action_mean.weight'], g['policy.action_mean.bias'], g['policy.action_log_std'])
+    return orc, pol, fm
+
+
+def test_forecast_windows_match_reference(golden):
+    """ego_forecast_eval.py windows with --gt-init and from an ego-mimic result (sync_traj, missing-past handling)"""
+    g = golden('eval_forecast')
+    orc, pol, fm = setup_forecast(g)
+    T, emo = int(g['test_len']), int(g['em_offset'])
+    assert int(g['starts'][0]) - fm - emo < 0 <= int(g['starts'][1]) - fm - emo      # both branches of :111-115
+    for wi, s0 in enumerate(int(x) for x in g['starts']):
+        ref = evalloop.forecast_window(orc, pol, 0, s0, T, ctx=g['cnn'], zf_mean=g['zf_mean'], zf_std=g['zf_std'])
+        assert np.allclose(ref, g['traj_pred_gt'][wi, fm:], rtol=1e-9, atol=1e-10)
+        assert np.array_equal(g['traj_pred_gt'][wi, :fm], g['qpos'][s0 - fm:s0])
+        q0, v0, past = evalloop.forecast_init(g['qpos'], g['em_traj'], g['em_vel'], s0, fm, T, emo)
+        ref = evalloop.forecast_window(orc, pol, 0, s0, T, ctx=g['cnn'], zf_mean=g['zf_mean'], zf_std=g['zf_std'], init=(q0, v0))
+        assert np.allclose(past, g['traj_pred_em'][wi, :fm], rtol=1e-12, atol=1e-12)
+        assert np.allclose(ref, g['traj_pred_em'][wi, fm:], rtol=1e-9, atol=1e-10)
