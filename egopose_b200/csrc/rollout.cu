@@ -600,6 +600,9 @@ struct RolloutArgs {
     int D, H1, H2, A, H1p, H2p, Ap;
     int K1p, K2p, K3p;      // T4: k padded to the tile depth (weights packed as tiles)
     int kc, chunk23;        // T4: tile depth (64 | 32); 1 = chunked layer-2/3 path for wide policies
+    // value net of the 'valuefs' evaluation rule (same plan as the policy, head padded to vAp rows), its context table
+    const double *vW1t, *vb1, *vW2t, *vb2, *vW3t, *vb3, *vctx;
+    int vAp;
     // state LSTM (VideoForecastNet.s_net, step mode): tile-packed [4H][S + H] weights, bias, per-CTA h | c scratch
     const double *sn_Wp, *sn_b;
     double *sn_state;
@@ -1420,7 +1423,7 @@ __device__ __forceinline__ void t4_policy_forward(const RolloutArgs &A, double *
     __syncthreads();
 }
 
-template <int KC, bool CHUNK, bool SNET>
+template <int KC, bool CHUNK, bool SNET, bool VALFS = false>
 __global__ void __launch_bounds__(T4_THREADS, 1)
 rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
     extern __shared__ double smem[];
@@ -1466,6 +1469,9 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
     log_acc[EGP_LOG_MIN_EPISODE_REWARD] = INFINITY; log_acc[EGP_LOG_MAX_EPISODE_REWARD] = -INFINITY;
     double ep_reward = 0.0;
     int n_reset = 0, take, start, cur_t = 0;
+    // 'valuefs' (ego_mimic_eval.py:156-159,167): running mean of the value-net outputs, continued across launches
+    double vs_n = 0.0, vs_mean = 0.0, value = 0.0;
+    if (VALFS && A.in.d_value_stat) { vs_n = A.in.d_value_stat[2 * eid]; vs_mean = A.in.d_value_stat[2 * eid + 1]; }
 
     auto draw_reset = [&](int r) {
         if (A.in.d_reset_take) {
@@ -1619,6 +1625,28 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
             for (int j = w; j < H; j += T4_WARPS) xs[(A.ctx_dim + j) * 32 + lane] = sn_g[j * 32 + lane];
         }
         __syncthreads();
+        if (VALFS) {
+            // value = value_net(value_vs_net(state)) on cat(value context row, state); value_stat.push(value)
+            if (A.vctx) {
+                const double *cx = A.vctx + (ctx_row(A, take, start, cur_t) - A.ctx);
+                for (int k = w; k < A.ctx_dim; k += T4_WARPS) xs[k * 32 + lane] = cx[k];
+                __syncthreads();
+            }
+            RolloutArgs V = A;
+            V.W1t = A.vW1t; V.b1 = A.vb1; V.W2t = A.vW2t; V.b2 = A.vb2; V.W3t = A.vW3t; V.b3 = A.vb3; V.Ap = A.vAp;
+            t4_policy_forward<KC, CHUNK>(V, xs, h1s, stage, lane, w);
+            value = h1s[lane];
+            vs_n += 1.0;
+            vs_mean += (value - vs_mean) / vs_n;
+            if (live && w0 && A.out.d_values) A.out.d_values[n] = value;
+            __syncthreads();
+            // the dense layers overwrote the input rows: rebuild the policy input
+            const double *cx = ctx_row(A, take, start, cur_t);
+            for (int k = w; k < A.ctx_dim; k += T4_WARPS) xs[k * 32 + lane] = cx[k];
+            int s = 0;
+            for (int k = w; k < S; k += T4_WARPS, s++) xs[(A.ctx_dim + k) * 32 + lane] = st[s];
+            __syncthreads();
+        }
         t4_policy_forward<KC, CHUNK>(A, xs, h1s, stage, lane, w);
         bool mean_flag = A.cfg.mean_action != 0;
         if (A.in.d_mean_flag) mean_flag = mean_flag || A.in.d_mean_flag[n] != 0;
@@ -1661,6 +1689,7 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
         const double head_z = x.at(O.xp, 3 * c_m.head_xp_slot + 2);
         const double lb = isnan(A.cfg.fix_head_lb) ? A.head_lb[take] - 0.1 : A.cfg.fix_head_lb;
         bool fail = head_z < lb;
+        if (VALFS && A.cfg.eval_mode == 2) fail = value < 0.6 * vs_mean;        // ego_mimic_eval.py:167
         const bool end = cur_t >= (A.in.d_fix_len ? A.in.d_fix_len[eid] : A.cfg.episode_len);
         // expert frame of the reward, clamped to the take (a window may end on the take's last frame in evaluation)
         const int xfr = min(A.take_off[take] + start + cur_t, A.take_off[take + 1] - 1);
@@ -1849,6 +1878,7 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
         }
         __syncthreads();
     }
+    if (VALFS && live && w0 && A.in.d_value_stat) { A.in.d_value_stat[2 * env] = vs_n; A.in.d_value_stat[2 * env + 1] = vs_mean; }
     if (live) {
         if (A.out.d_final_qpos) for (int k = w; k < nq; k += T4_WARPS) A.out.d_final_qpos[(size_t)env * nq + k] = x.at(O.q, k);
         if (A.out.d_final_qvel) for (int k = w; k < nv; k += T4_WARPS) A.out.d_final_qvel[(size_t)env * nv + k] = x.at(O.v, k);
@@ -2332,8 +2362,23 @@ int egp_rollout_f64(EgpModel *m, const EgpPolicyWeights *pol, const EgpRolloutCf
     if (cfg->eval_mode && !(in && in->d_state_pred)) { set_error("egp_rollout_f64: eval_mode needs d_state_pred"); return EGP_EINVAL; }
     if ((out->d_qpos_traj == nullptr) != (out->d_qvel_traj == nullptr)) { set_error("egp_rollout_f64: d_qpos_traj / d_qvel_traj come in pairs"); return EGP_EINVAL; }
     A.sn_Kp = snH ? padk(sn_in) : 0;
+    const EgpPolicyWeights *vn = in ? in->value_net : nullptr;
+    if (cfg->eval_mode == 2 && !vn) { set_error("egp_rollout_f64: eval_mode 2 ('valuefs') needs value_net"); return EGP_EINVAL; }
+    if (vn) {
+        if (!use_t4 || snH || A.chunk23) { set_error("egp_rollout_f64: value_net needs the plain T4 rollout variant (no state LSTM, no chunked wide policy)"); return EGP_ESIZE; }
+        if (vn->in_dim != pol->in_dim || vn->h1 != pol->h1 || vn->h2 != pol->h2 || vn->out_dim != 1 || !vn->d_W1 || !vn->d_b1 ||
+            !vn->d_W2 || !vn->d_b2 || !vn->d_W3 || !vn->d_b3) {
+            set_error("egp_rollout_f64: value_net must be a [%d, %d, %d, 1] MLP like the policy trunk", pol->in_dim, pol->h1, pol->h2);
+            return EGP_EINVAL;
+        }
+        if (in->d_vctx && !A.ctx) { set_error("egp_rollout_f64: d_vctx without a policy context table"); return EGP_EINVAL; }
+        A.vAp = pad(1);
+        A.vctx = in->d_vctx;
+    }
     size_t need = (size_t)A.K1p * A.H1p + A.H1p + (size_t)A.K2p * A.H2p + A.H2p + (size_t)A.K3p * A.Ap + A.Ap +
                   (size_t)A.sn_Kp * 4 * snH + 4 * snH;
+    const size_t vneed = vn ? (size_t)A.K1p * A.H1p + A.H1p + (size_t)A.K2p * A.H2p + A.H2p + (size_t)A.K3p * A.vAp + A.vAp : 0;
+    need += vneed;
     if (need > m->wbuf_elems) {
         cudaFree(m->d_wbuf);
         m->d_wbuf = nullptr; m->wbuf_elems = 0;
@@ -2348,7 +2393,19 @@ int egp_rollout_f64(EgpModel *m, const EgpPolicyWeights *pol, const EgpRolloutCf
     double *W3t = w; w += (size_t)A.K3p * A.Ap;
     double *b3 = w; w += A.Ap;
     double *snW = w; w += (size_t)A.sn_Kp * 4 * snH;
-    double *snb = w;
+    double *snb = w; w += 4 * snH;
+    if (vn) {
+        double *v1 = w; w += (size_t)A.K1p * A.H1p;
+        double *vb1 = w; w += A.H1p;
+        double *v2 = w; w += (size_t)A.K2p * A.H2p;
+        double *vb2 = w; w += A.H2p;
+        double *v3 = w; w += (size_t)A.K3p * A.vAp;
+        double *vb3 = w;
+        pack_tiles_kernel<<<(A.K1p * A.H1p + 255) / 256, 256, 0, st>>>(vn->d_W1, vn->d_b1, A.H1, A.D, A.H1p, A.K1p, v1, vb1);
+        pack_tiles_kernel<<<(A.K2p * A.H2p + 255) / 256, 256, 0, st>>>(vn->d_W2, vn->d_b2, A.H2, A.H1, A.H2p, A.K2p, v2, vb2);
+        pack_tiles_kernel<<<(A.K3p * A.vAp + 255) / 256, 256, 0, st>>>(vn->d_W3, vn->d_b3, 1, A.H2, A.vAp, A.K3p, v3, vb3);
+        A.vW1t = v1; A.vb1 = vb1; A.vW2t = v2; A.vb2 = vb2; A.vW3t = v3; A.vb3 = vb3;
+    }
     if (snH) {
         pack_tiles_kernel<<<(A.sn_Kp * 4 * snH + 255) / 256, 256, 0, st>>>(in->d_snet_W, in->d_snet_b, 4 * snH, sn_in, 4 * snH, A.sn_Kp, snW, snb);
         A.sn_Wp = snW; A.sn_b = snb; A.sn_state = in->d_snet_state;
@@ -2381,6 +2438,7 @@ int egp_rollout_f64(EgpModel *m, const EgpPolicyWeights *pol, const EgpRolloutCf
             if (A.chunk23) { set_error("egp_rollout_f64: state LSTM with the chunked wide-policy plan is not supported"); return EGP_ESIZE; }
             return A.kc == 64 ? launch(rollout_kernel_t4<64, false, true>) : launch(rollout_kernel_t4<32, false, true>);
         }
+        if (vn) return A.kc == 64 ? launch(rollout_kernel_t4<64, false, false, true>) : launch(rollout_kernel_t4<32, false, false, true>);
         if (A.kc == 64) return launch(rollout_kernel_t4<64, false, false>);
         if (!A.chunk23) return launch(rollout_kernel_t4<32, false, false>);
         return launch(rollout_kernel_t4<32, true, false>);

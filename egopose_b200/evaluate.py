@@ -11,8 +11,8 @@ Fail-safe (:167-173): 'naivefs' (head below ``fix_head_lb`` = 0.3, :52-53) repla
 place by ``state_pred`` of the next frame, aligned to the simulated root (reset_env_state :93-99), inside the kernel;
 'none' never replaces it.  ``state_pred`` is what the reference obtains from its state-regression net
 (models/video_reg_net.py, outside the hot path): pass its per-take predictions, or leave it None to use the
-expert's own observation of each frame.  The 'valuefs' rule needs the value net inside the step loop and a running
-mean shared across takes in script order; it is not built (raises).
+expert's own observation of each frame.  'valuefs' (the script's default) evaluates the value net inside the step
+loop and replaces the state when value < 0.6 x the running mean of all values so far.
 """
 import pickle
 
@@ -34,8 +34,11 @@ def expert_obs_table(model):
 
 def _context_table(env, policy_vs_net, dev):
     """per-frame context rows for whole-take episodes: test-mode VideoStateNet.initialize(cnn_feat) over the full
-    take (ego_mimic_eval.py:122-124), placed at the frames it describes; None -> the table uploaded with the experts"""
+    take (ego_mimic_eval.py:122-124), placed at the frames it describes; a tensor / array is taken as the table itself;
+    anything else (FrameContext, None) -> the table uploaded with the experts"""
     from .nets import VideoStateNet
+    if isinstance(policy_vs_net, (np.ndarray, torch.Tensor)):      # a ready per-frame table [total_frames, dim]
+        return torch.as_tensor(policy_vs_net, dtype=torch.float64, device=dev).contiguous()
     if not isinstance(policy_vs_net, VideoStateNet):
         return None
     m = policy_vs_net.v_margin
@@ -50,11 +53,27 @@ def _context_table(env, policy_vs_net, dev):
     return torch.cat(rows).to(dev).contiguous()
 
 
+def _mlp_weights(net, head):
+    L = net.net.affine_layers
+    w = dict(W1=L[0].weight.data, b1=L[0].bias.data, W2=L[1].weight.data, b2=L[1].bias.data, W3=head.weight.data, b3=head.bias.data)
+    return {k: t.contiguous() for k, t in w.items()}
+
+
 def eval_takes(env, policy_net, policy_vs_net=None, running_state=None, state_pred=None, fail_safe='naivefs',
-               fix_head_lb=0.3, show_noise=False, seed=1, algo='ego_mimic'):
-    """-> (results, meta, info).  ``state_pred``: None or a per-take list of [len, S] arrays indexed by frame."""
-    if fail_safe not in ('naivefs', 'none'):
-        raise NotImplementedError("fail_safe %r: only 'naivefs' and 'none' run on the fused path" % (fail_safe,))
+               fix_head_lb=0.3, show_noise=False, seed=1, algo='ego_mimic', value_net=None, value_vs_net=None,
+               sequential=True):
+    """-> (results, meta, info).  ``state_pred``: None or a per-take list of [len, S] arrays indexed by frame.
+    fail_safe 'valuefs' (the script's default, :29,167) needs ``value_net`` (+ ``value_vs_net``): the value net runs
+    inside the step loop and a state is replaced when value < 0.6 x the running mean of all values so far.  The script
+    shares that mean across takes in list order: ``sequential=True`` reproduces it with one launch per take (the
+    statistic is carried on the device); ``sequential=False`` runs all takes in one launch with a mean per take."""
+    if fail_safe not in ('naivefs', 'none', 'valuefs'):
+        raise ValueError('fail_safe %r' % (fail_safe,))
+    if fail_safe == 'valuefs':
+        if value_net is None:
+            raise ValueError("fail_safe 'valuefs' needs value_net")
+        return _eval_takes_valuefs(env, policy_net, policy_vs_net, running_state, state_pred, show_noise, seed, algo,
+                                   value_net, value_vs_net, sequential)
     model, cfg = env.kernel, env.cfg
     fm = int(cfg.fr_margin)
     off = np.asarray(model.take_off, dtype=np.int64)
@@ -98,6 +117,58 @@ def eval_takes(env, policy_net, policy_vs_net=None, running_state=None, state_pr
     info = {'rewards': {take: rewards[e, :int(test_len[e])].copy() for e, take in enumerate(env.expert_list)},
             'test_len': {take: int(test_len[e]) for e, take in enumerate(env.expert_list)}}
     return results, meta, info
+
+
+def _eval_takes_valuefs(env, policy_net, policy_vs_net, running_state, state_pred, show_noise, seed, algo, value_net,
+                        value_vs_net, sequential):
+    model, cfg = env.kernel, env.cfg
+    fm = int(cfg.fr_margin)
+    off = np.asarray(model.take_off, dtype=np.int64)
+    lens = np.diff(off)
+    test_len = lens - 2 * fm
+    if test_len.min() < 1:
+        raise ValueError('a take is shorter than 2 * fr_margin + 1 frames')
+    n_takes = len(lens)
+    dev = policy_net.action_mean.weight.device
+    w = _mlp_weights(policy_net, policy_net.action_mean)
+    w['log_std'] = policy_net.action_log_std.data.view(-1).contiguous()
+    vw = _mlp_weights(value_net, value_net.value_head)
+    sp = expert_obs_table(model) if state_pred is None else np.concatenate([np.asarray(a, dtype=np.float64) for a in state_pred])
+    cu = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=dev)  # noqa: E731
+    zm = zs = None
+    clip = 0.0
+    if running_state is not None:
+        zm, zs = cu(running_state.rs.mean, torch.float64), cu(running_state.rs.std, torch.float64)
+        clip = running_state.clip or 0.0
+    ctx, vctx, sp_d = _context_table(env, policy_vs_net, dev), _context_table(env, value_vs_net, dev), cu(sp, torch.float64)
+    if ctx is not None and vctx is None and model.ctx_dim == 0:
+        raise ValueError('value_vs_net: no context table for the value net')
+    if ctx is not None and vctx is None:
+        vctx = torch.as_tensor(np.concatenate(env.cnn_feat), dtype=torch.float64, device=dev).contiguous()
+    groups = [[e] for e in range(n_takes)] if sequential else [list(range(n_takes))]
+    stat = torch.zeros((1, 2), dtype=torch.float64, device=dev)        # (n, mean) of value_stat, shared in script order
+    X = lib.X
+    results = {'traj_pred': {}, 'traj_orig': {}, 'vel_pred': {}}
+    info = {'rewards': {}, 'values': {}, 'test_len': {}}
+    num_reset = 0
+    for g in groups:
+        E, T = len(g), int(test_len[g].max())
+        vs = stat if sequential else torch.zeros((E, 2), dtype=torch.float64, device=dev)
+        out = model.rollout(
+            w, E, T, episode_len=T, fr_margin=fm, fix_head_lb=-1e30, mean_action=not show_noise, zf_mean=zm, zf_std=zs,
+            zf_clip=clip, seed=seed, reset_take=cu(np.asarray(g)[:, None], torch.int32),
+            reset_start=cu(np.full((E, 1), fm), torch.int32), want_next=False, want_raw=False, ctx=ctx, eval_mode=2,
+            fix_len=cu(test_len[g], torch.int32), state_pred=sp_d, want_traj=True, value_weights=vw, vctx=vctx, value_stat=vs)
+        qpos = out['qpos_traj'].view(E, T, model.nq).cpu().numpy()
+        qvel = out['qvel_traj'].view(E, T, model.nv).cpu().numpy()
+        rew, val = out['rewards'].view(E, T).cpu().numpy(), out['values'].view(E, T).cpu().numpy()
+        num_reset += int(round(float(out['logger'][lib.LOG['NUM_FAILSAFE_RESETS']].item())))
+        for i, e in enumerate(g):
+            take, n = env.expert_list[e], int(test_len[e])
+            results['traj_pred'][take], results['vel_pred'][take] = qpos[i, :n].copy(), qvel[i, :n].copy()
+            results['traj_orig'][take] = model.rows_host[off[e] + fm:off[e] + fm + n, X['QPOS']:X['QPOS'] + model.nq].copy()
+            info['rewards'][take], info['values'][take], info['test_len'][take] = rew[i, :n].copy(), val[i, :n].copy(), n
+    return results, {'algo': algo, 'num_reset': num_reset}, info
 
 
 def _quat_mul(q1, q0):

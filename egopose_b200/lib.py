@@ -60,13 +60,14 @@ class RolloutIn(C.Structure):
     _fields_ = [('d_eps', _vp), ('d_reset_take', _vp), ('d_reset_start', _vp), ('d_mean_flag', _vp),
                 ('d_zf_mean', _vp), ('d_zf_std', _vp), ('d_ctx', _vp), ('d_win_off', _vp), ('ctx_dim', C.c_int32),
                 ('ctx_mode', C.c_int32), ('ctx_T', C.c_int32), ('d_snet_W', _vp), ('d_snet_b', _vp), ('d_snet_state', _vp),
-                ('snet_hdim', C.c_int32), ('d_fix_len', _vp), ('d_state_pred', _vp), ('d_init_qpos', _vp), ('d_init_qvel', _vp)]
+                ('snet_hdim', C.c_int32), ('d_fix_len', _vp), ('d_state_pred', _vp), ('value_net', _vp), ('d_vctx', _vp), ('d_value_stat', _vp),
+                ('d_init_qpos', _vp), ('d_init_qvel', _vp)]
 
 
 class TrajOut(C.Structure):
     _fields_ = [('d_states', _vp), ('d_actions', _vp), ('d_masks', _vp), ('d_next_states', _vp), ('d_rewards', _vp),
                 ('d_exps', _vp), ('d_v_metas', _vp), ('d_c_info', _vp), ('d_raw_obs', _vp), ('d_final_qpos', _vp),
-                ('d_final_qvel', _vp), ('d_logger', _vp), ('d_qpos_traj', _vp), ('d_qvel_traj', _vp)]
+                ('d_final_qvel', _vp), ('d_logger', _vp), ('d_values', _vp), ('d_qpos_traj', _vp), ('d_qvel_traj', _vp)]
 
 
 class MlpNet(C.Structure):
@@ -315,7 +316,7 @@ class Model:
                 noise_rate=1.0, mean_action=False, zf_mean=None, zf_std=None, zf_clip=5.0, seed=1, iteration=0,
                 eps=None, reset_take=None, reset_start=None, mean_flag=None, want_next=True, want_raw=True, out=None,
                 ctx=None, win_off=None, ctx_const=False, snet=None, eval_mode=False, fix_len=None, state_pred=None,
-                want_traj=False, init_qpos=None, init_qvel=None):
+                want_traj=False, init_qpos=None, init_qvel=None, value_weights=None, vctx=None, value_stat=None):
         """weights: dict with W1,b1,W2,b2,W3,b3,log_std CUDA float64 tensors (torch [out,in] layout).
         Returns a dict of CUDA tensors in TrajBatchEgo layout (+ logger, c_info, raw_obs, final state)."""
         global launches
@@ -354,10 +355,25 @@ class Model:
         cfg.noise_rate, cfg.mean_action, cfg.zf_clip = float(noise_rate), int(bool(mean_action)), float(zf_clip)
         cfg.seed, cfg.iteration = int(seed), int(iteration)
         cfg.max_resets = int(reset_take.shape[1]) if reset_take is not None else 0
-        cfg.eval_mode = int(bool(eval_mode))
+        cfg.eval_mode = int(eval_mode)          # 0 training, 1 'naivefs', 2 'valuefs'
         inp = RolloutIn()
         inp.d_eps, inp.d_reset_take, inp.d_reset_start = ptr(eps), ptr(reset_take), ptr(reset_start)
         inp.d_mean_flag, inp.d_zf_mean, inp.d_zf_std = ptr(mean_flag), ptr(zf_mean), ptr(zf_std)
+        if value_weights is not None:   # Value(MLP) evaluated before every step ('valuefs'): W1,b1,W2,b2,W3,b3 like ``weights``
+            vw = PolicyWeights()
+            vw.in_dim, vw.h1 = value_weights['W1'].shape[1], value_weights['W1'].shape[0]
+            vw.h2, vw.out_dim = value_weights['W2'].shape[0], value_weights['W3'].shape[0]
+            vw.d_W1, vw.d_b1, vw.d_W2 = ptr(value_weights['W1']), ptr(value_weights['b1']), ptr(value_weights['W2'])
+            vw.d_b2, vw.d_W3, vw.d_b3 = ptr(value_weights['b2']), ptr(value_weights['W3']), ptr(value_weights['b3'])
+            self._keep['vw'] = vw
+            inp.value_net = C.cast(C.pointer(vw), _vp)
+            inp.d_vctx = ptr(vctx)
+            if value_stat is not None:  # [n_env, 2] (n, mean) running statistic, read and written back
+                if tuple(value_stat.shape) != (n_env, 2):
+                    raise EgpError('value_stat must be [n_env, 2]')
+                inp.d_value_stat = ptr(value_stat)
+            o.d_values = ptr(buf('values', (N,)))
+            launches += 3
         if init_qpos is not None:   # [n_env, nq] / [n_env, nv] state set right after the first reset
             if tuple(init_qpos.shape) != (n_env, self.nq) or tuple(init_qvel.shape) != (n_env, self.nv):
                 raise EgpError('init_qpos / init_qvel must be [n_env, nq] / [n_env, nv]')

@@ -88,7 +88,8 @@ typedef struct {
     /* Evaluation roll-out (ego_pose/ego_mimic_eval.py:102-177): a failing environment is NOT restarted; its state is
      * replaced in place by the d_state_pred row of the next frame, aligned to the simulated root position / heading
      * (reset_env_state :93-99, utils/tools.py:71-75), and the episode clock keeps running ('naivefs' fail-safe :167-173
-     * with fix_head_lb = 0.3, :52-53).  The first state of every episode is placed the same way (:127). */
+     * with fix_head_lb = 0.3, :52-53).  The first state of every episode is placed the same way (:127).
+     * 1 = fail rule of the environment ('naivefs'), 2 = value rule ('valuefs', see EgpRolloutIn.value_net). */
     int32_t eval_mode;
 } EgpRolloutCfg;
 
@@ -126,6 +127,14 @@ typedef struct {
     const int32_t *d_fix_len;           /* [E] per-environment episode length (env.set_fix_sampling(len=), humanoid_v1.py:197) or NULL */
     const double *d_state_pred;         /* eval_mode: [total_frames][S] predicted observations (qpos[2:] | qvel in the
                                          * heading frame, humanoid_v1.py:73-96), row = take_off[take] + start + cur_t */
+    /* eval_mode 2 ('valuefs', ego_mimic_eval.py:156-159,167): the value net is evaluated on cat(value context row, state)
+     * before every step, its output is pushed into a running mean (utils/zfilter.py:18-27) and the state is replaced when
+     * value < 0.6 * mean.  value_net: HOST pointer to the Value(MLP) weights (same in_dim / hidden sizes as the policy,
+     * out_dim 1); d_vctx: value_vs_net's context table (same shape / indexing as the policy's, NULL = the policy's);
+     * d_value_stat: [E][2] (n, mean) read at launch and written back, so successive launches continue one statistic. */
+    const EgpPolicyWeights *value_net;
+    const double *d_vctx;
+    double *d_value_stat;
     const double *d_init_qpos, *d_init_qvel;    /* [E][nq], [E][nv] or NULL: simulator state set right after the first reset of
                                          * every environment (env.set_state of the ego-mimic prediction, ego_forecast_eval.py:119-121) */
 } EgpRolloutIn;
@@ -143,6 +152,7 @@ typedef struct {
     double *d_raw_obs;                  /* [N][S] unfiltered observations or NULL */
     double *d_final_qpos, *d_final_qvel;/* [E][nq], [E][nv] or NULL */
     double *d_logger;                   /* [EGP_LOG_SIZE] reductions for core/logger_rl.py, or NULL */
+    double *d_values;                   /* [N] value-net output per step (value_net given) or NULL */
     double *d_qpos_traj, *d_qvel_traj;  /* [N][nq], [N][nv] simulator state BEFORE step t (traj_pred / vel_pred of
                                          * ego_mimic_eval.py:136-138) or NULL */
 } EgpTrajOut;

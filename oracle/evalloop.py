@@ -9,7 +9,7 @@ not restarted, its state is replaced by the predicted observation of the next fr
 Pinned by tests/golden/eval_traj.npz (the reference's own HumanoidEnv / align_human_state / PolicyGaussian driven in
 the script's call order on the restated physics, tests/golden/make_golden.py gen_eval).  The state-regression net
 that produces ``state_pred`` in the reference (models/video_reg_net.py) is outside the hot path: the table is an
-input here.  The 'valuefs' rule (value < 0.6 x running mean over all takes, :167) is not restated.
+input here.  'valuefs' (value < 0.6 x running mean over all takes, :156-159,167) is restated with the Value MLP.
 """
 import numpy as np
 
@@ -46,9 +46,11 @@ def reset_env_state(orc, env, state, nq):
 
 
 def eval_take(orc, policy, take, fr_margin, test_len, state_pred, ctx=None, zf_mean=None, zf_std=None, zf_clip=5.0,
-              fail_safe='naivefs'):
+              fail_safe='naivefs', value_policy=None, vctx=None, value_stat=None):
     """state_pred [L, S] and ctx [L, ctx_dim] are indexed by the take's frame (frame = fr_margin + t).
-    Returns dict(traj_pred [n, nq], vel_pred [n, nv], states [n, S], actions, rewards, num_reset)."""
+    fail_safe 'valuefs' (:156-159,167): ``value_policy`` = the Value MLP as an EoPolicy with out_dim 1, ``vctx`` its
+    context table, ``value_stat`` = [n, mean] list shared across takes (RunningStat(1), utils/zfilter.py:18-27).
+    Returns dict(traj_pred [n, nq], vel_pred [n, nv], states [n, S], actions, rewards, values, num_reset)."""
     nq, nv = orc.nq, orc.nv
 
     def zf(x):
@@ -61,11 +63,18 @@ def eval_take(orc, policy, take, fr_margin, test_len, state_pred, ctx=None, zf_m
     env = cphys.EoEnv()
     orc.env_reset(env, int(take), int(fr_margin))
     state = zf(reset_env_state(orc, env, state_pred[fr_margin], nq))
-    out = dict(traj_pred=[], vel_pred=[], states=[], actions=[], rewards=[], num_reset=0)
+    out = dict(traj_pred=[], vel_pred=[], states=[], actions=[], rewards=[], values=[], num_reset=0)
     for t in range(test_len):
         out['traj_pred'].append(np.array(env.d.qpos[:nq]))
         out['vel_pred'].append(np.array(env.d.qvel[:nv]))
         x = state if ctx is None else np.concatenate([ctx[fr_margin + t], state])
+        value = 0.0
+        if value_policy is not None:
+            vt = vctx if vctx is not None else ctx
+            value = float(orc.policy_mean(value_policy, state if vt is None else np.concatenate([vt[fr_margin + t], state]))[0])
+            value_stat[0] += 1                                      # RunningStat.push
+            value_stat[1] += (value - value_stat[1]) / value_stat[0]
+            out['values'].append(value)
         action = orc.policy_mean(policy, x)
         fail, end = orc.env_step(env, action)
         next_state = zf(orc.env_obs(env))
@@ -75,7 +84,7 @@ def eval_take(orc, policy, take, fr_margin, test_len, state_pred, ctx=None, zf_m
         out['rewards'].append(rew)
         if end:
             break
-        if fail_safe == 'naivefs' and fail:
+        if (fail_safe == 'naivefs' and fail) or (fail_safe == 'valuefs' and value < 0.6 * value_stat[1]):
             out['num_reset'] += 1
             state = zf(reset_env_state(orc, env, state_pred[fr_margin + t + 1], nq))
         else:
@@ -83,6 +92,7 @@ def eval_take(orc, policy, take, fr_margin, test_len, state_pred, ctx=None, zf_m
     for k in ('traj_pred', 'vel_pred', 'states', 'actions'):
         out[k] = np.array(out[k])
     out['rewards'] = np.array(out['rewards'])
+    out['values'] = np.array(out['values'])
     return out
 
 

@@ -577,6 +577,55 @@ def gen_eval():
         out[pre + 'rewards'] = np.array(rewards)
         out[pre + 'num_reset'] = num_reset
         print('eval take', ti, 'steps', len(rewards), 'num_reset', num_reset)
+    # ---- the script's default fail-safe 'valuefs' (:156-159,167): value net in the loop, ONE RunningStat over both takes
+    from core.critic import Value
+    from utils.zfilter import RunningStat
+    torch.manual_seed(17)
+    value_net = Value(MLP(state_dim + CTX, (32, 16), 'relu'))
+    with torch.no_grad():                                # a head that reacts to the state (the default init is x0.1, bias 0)
+        value_net.value_head.weight.mul_(60.0)
+        value_net.value_head.bias.fill_(1.0)
+    for k, v in value_net.state_dict().items():
+        out['value.' + k] = v.numpy().copy()
+    vcnn = {n: rng.randn(L, CTX) for n, L in zip(take_names, lens)}      # value_vs_net has its own context
+    value_stat = RunningStat(1)
+    env.set_fix_head_lb(None)
+    margin = np.inf
+    for ti, name in enumerate(take_names):
+        L = lens[ti]
+        test_len = L - 2 * FM
+        sp = out['take%d.state_pred' % ti]
+        env.set_fix_sampling(ti, FM, test_len)
+        state = env.reset()
+        state = running_state(reset_env_state(sp[FM], env.data.qpos), update=False)
+        traj_pred, vel_pred, values, num_reset = [], [], [], 0
+        for t in range(test_len):
+            traj_pred.append(env.data.qpos.copy())
+            vel_pred.append(env.data.qvel.copy())
+            with torch.no_grad():
+                value = value_net(torch.from_numpy(np.concatenate([vcnn[name][FM + t], state])).unsqueeze(0)).item()
+                value_stat.push(np.array([value]))
+                x = torch.from_numpy(np.concatenate([cnn[name][FM + t], state])).unsqueeze(0)
+                action = policy_net.select_action(x, mean_action=True)[0].numpy()
+            values.append(value)
+            next_state, _r, done, info = env.step(action)
+            next_state = running_state(next_state, update=False)
+            if info['end']:
+                break
+            margin = min(margin, abs(value - 0.6 * value_stat.mean[0]))
+            if value < 0.6 * value_stat.mean[0]:
+                num_reset += 1
+                state = running_state(reset_env_state(sp[FM + t + 1], env.data.qpos), update=False)
+            else:
+                state = next_state
+        pre = 'vfs.take%d.' % ti
+        out[pre + 'vcnn'] = vcnn[name]
+        out[pre + 'traj_pred'] = np.vstack(traj_pred)
+        out[pre + 'vel_pred'] = np.vstack(vel_pred)
+        out[pre + 'values'] = np.array(values)
+        out[pre + 'num_reset'] = num_reset
+        print('valuefs take', ti, 'steps', len(values), 'num_reset', num_reset, 'min decision margin', margin)
+    out['vfs.value_stat'] = np.array([value_stat.n, value_stat.mean[0]])
     np.savez_compressed(os.path.join(OUT, 'eval_traj.npz'), **out)
 
 

@@ -210,3 +210,50 @@ def test_eval_forecast_from_ego_mimic_result_matches_reference_golden(golden):
     assert np.allclose(r_em['traj_pred']['t'][:, fm:], g['traj_pred_em'][:, fm:], rtol=1e-6, atol=1e-7)
     assert not np.allclose(r_em['traj_pred']['t'][:, fm], r_gt['traj_pred']['t'][:, fm], atol=1e-3)
     env.close()
+
+
+def test_eval_takes_valuefs_matches_reference_golden(golden):
+    """fail_safe='valuefs' (the script's default): value net inside the kernel's step loop, running mean carried across
+    the per-take launches; vs the golden produced by the reference's env / Value / RunningStat in script order"""
+    from egopose_b200 import evaluate
+    from egopose_b200.config import Config
+    from egopose_b200.env import HumanoidEnv
+    from egopose_b200.nets import MLP, FrameContext, PolicyGaussian, Value
+    from egopose_b200.zfilter import ZFilter
+    torch.set_default_dtype(torch.float64)
+    g = golden('eval_traj')
+    fm = int(g['fr_margin'])
+    cfg = Config('subject_03')
+    cfg.fr_margin = fm
+    env = HumanoidEnv(cfg, device=0)
+    takes = [g['take%d.qpos' % i] for i in range(2)]
+    env.set_expert_qpos(['a', 'b'], takes, [g['take%d.cnn' % i] for i in range(2)])
+    S, nu, ctxd = env.obs_dim, env.md.nu, g['take0.cnn'].shape[1]
+    pol = PolicyGaussian(MLP(S + ctxd, (32, 16), 'relu'), nu, log_std=-2.3, fix_std=True)
+    pol.load_state_dict({k[len('policy.'):]: torch.from_numpy(g[k]) for k in g.files if k.startswith('policy.')})
+    val = Value(MLP(S + ctxd, (32, 16), 'relu'))
+    val.load_state_dict({k[len('value.'):]: torch.from_numpy(g[k]) for k in g.files if k.startswith('value.')})
+    pol, val = pol.cuda(), val.cuda()
+    rs = ZFilter((S,), clip=5)
+    rs.rs._n, rs.rs._M = 50, g['zf_mean'].copy()
+    rs.rs._S = (g['zf_std'] ** 2) * 49
+
+    # the value net has its own per-frame context table (value_vs_net of the script)
+    vtab = np.concatenate([g['vfs.take%d.vcnn' % i] for i in range(2)])
+    sp = [g['take%d.state_pred' % i] for i in range(2)]
+    results, meta, info = evaluate.eval_takes(env, pol, FrameContext(ctxd), rs, fail_safe='valuefs', value_net=val,
+                                              value_vs_net=vtab, sequential=True, state_pred=sp)
+    batched = evaluate.eval_takes(env, pol, FrameContext(ctxd), rs, fail_safe='valuefs', value_net=val, value_vs_net=vtab,
+                                  sequential=False, state_pred=sp)
+    total = 0
+    for i, name in enumerate(['a', 'b']):
+        vpre = 'vfs.take%d.' % i
+        total += int(g[vpre + 'num_reset'])
+        assert np.allclose(info['values'][name], g[vpre + 'values'], rtol=1e-6, atol=1e-7)
+        assert np.allclose(results['traj_pred'][name], g[vpre + 'traj_pred'], rtol=1e-6, atol=1e-7)
+        assert np.allclose(results['vel_pred'][name], g[vpre + 'vel_pred'], rtol=1e-5, atol=1e-5)
+    assert meta == {'algo': 'ego_mimic', 'num_reset': total} and total >= 6
+    # one launch for all takes: the first take sees the same statistic, later takes start their own
+    assert np.allclose(batched[0]['traj_pred']['a'], results['traj_pred']['a'], rtol=1e-9, atol=1e-10)
+    assert batched[0]['traj_pred']['b'].shape == results['traj_pred']['b'].shape
+    env.close()

@@ -77,3 +77,30 @@ def test_forecast_windows_match_reference(golden):
         ref = evalloop.forecast_window(orc, pol, 0, s0, T, ctx=g['cnn'], zf_mean=g['zf_mean'], zf_std=g['zf_std'], init=(q0, v0))
         assert np.allclose(past, g['traj_pred_em'][wi, :fm], rtol=1e-12, atol=1e-12)
         assert np.allclose(ref, g['traj_pred_em'][wi, fm:], rtol=1e-9, atol=1e-10)
+
+
+def value_policy(orc, g):
+    return orc.make_policy(g['value.net.affine_layers.0.weight'], g['value.net.affine_layers.0.bias'],
+                           g['value.net.affine_layers.1.weight'], g['value.net.affine_layers.1.bias'],
+                           g['value.value_head.weight'], g['value.value_head.bias'], np.zeros(1))
+
+
+def test_eval_rollout_valuefs_matches_reference(golden):
+    """the script's default fail-safe: value net in the loop, one running mean shared by the takes in list order"""
+    g = golden('eval_traj')
+    orc, pol, fm = setup_eval(g)
+    orc2 = cphys.Oracle()                       # second handle: make_policy keeps one weight set alive per Oracle
+    vpol = value_policy(orc2, g)
+    orc.cfg.fix_head_lb = float('nan')
+    stat = [0, 0.0]
+    for ti in range(2):
+        pre, vpre = 'take%d.' % ti, 'vfs.take%d.' % ti
+        L = g[pre + 'qpos'].shape[0]
+        out = evalloop.eval_take(orc, pol, ti, fm, L - 2 * fm, g[pre + 'state_pred'], ctx=g[pre + 'cnn'], zf_mean=g['zf_mean'],
+                                 zf_std=g['zf_std'], zf_clip=5.0, fail_safe='valuefs', value_policy=vpol, vctx=g[vpre + 'vcnn'],
+                                 value_stat=stat)
+        assert out['num_reset'] == int(g[vpre + 'num_reset']) >= 3
+        assert np.allclose(out['values'], g[vpre + 'values'], rtol=1e-8, atol=1e-9)
+        assert np.allclose(out['traj_pred'], g[vpre + 'traj_pred'], rtol=1e-8, atol=1e-9)
+        assert np.allclose(out['vel_pred'], g[vpre + 'vel_pred'], rtol=1e-7, atol=1e-7)
+    assert stat[0] == int(g['vfs.value_stat'][0]) and abs(stat[1] - g['vfs.value_stat'][1]) < 1e-10
