@@ -643,11 +643,28 @@ class AgentPPO(AgentPG):
             return self._update_policy_minibatch(xp.x_const, xv.x_const, actions, returns, adv, exps, logp0, log_std, max_norm)
         surr, vloss = [], []
         d = _dist()
+        # The value chain (10 x [forward / loss / backward / Adam] of the value net) and the policy chain never exchange
+        # data inside update_policy (advantages / returns are fixed before the epochs, agent_ppo.py:44-51), so they are
+        # issued on two streams (EGP_UPDATE_STREAMS=1 restores one): slicing (HBM-bound) and GEMM (tensor-bound) kernels of
+        # the two chains overlap at tile-wave tails.  Same arithmetic, same order within each chain.
+        two = (os.environ.get('EGP_UPDATE_STREAMS', '2') == '2' and oz is not None and not xp.learned and not xv.learned)
+        if two:
+            cur = torch.cuda.current_stream()
+            if getattr(self, '_vstream', None) is None:
+                self._vstream = torch.cuda.Stream()
+            self._vstream.wait_stream(cur)
         for ep in range(self.opt_num_epochs):
-            self.update_value(xv, returns, inv_n, reuse_forward=(ep == 0 and self._value_fresh))     # :46
-            vloss.append(self._scal[0:1].clone())
+            if two:
+                with torch.cuda.stream(self._vstream):
+                    self.update_value(xv, returns, inv_n)
+                    vloss.append(self._scal[0:1].clone())
+            else:
+                self.update_value(xv, returns, inv_n, reuse_forward=(ep == 0 and self._value_fresh))     # :46
+                vloss.append(self._scal[0:1].clone())
             surr.append(self._policy_step(xp, actions, adv, logp0, exps, inv_count, log_std, max_norm,
                                           mu=mu if ep == 0 else None))      # epoch 0 reuses the fixed-log-prob forward
+        if two:
+            torch.cuda.current_stream().wait_stream(self._vstream)
         self.last_info = dict(surr_loss=surr, value_loss=vloss)
 
     def losses(self):
