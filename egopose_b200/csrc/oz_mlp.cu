@@ -37,6 +37,81 @@ oz_wgrad_reduce_kernel(const double *__restrict__ part, int splits, int in, int 
     *dst = accumulate ? *dst + s : s;
 }
 
+// ---- scalar head (critic.py:15-18, value_head Linear(h2, 1)) in plain float64, HBM-bound -------------------------------
+// As a tensor-core GEMM the 1-wide head pads to a 64-column tile and needs the row AND the transposed slices of the
+// last hidden layer; as three streaming kernels it reads that layer twice and writes its gradient once.
+constexpr int HEAD_MAXJ = 16;       // hidden width <= 512 (wider heads take the GEMM path); 8 x 513 doubles of shared memory
+constexpr int HEAD_WARPS = 8;
+
+// y[n] = b + a2[n] . w            (one warp per row, fixed shuffle order: deterministic)
+__global__ void __launch_bounds__(32 * HEAD_WARPS)
+head1_fwd_kernel(const double *__restrict__ a2, long long m, int h2, const double *__restrict__ w, const double *__restrict__ b,
+                 double *__restrict__ y) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = (long long)blockIdx.x * HEAD_WARPS + (threadIdx.x >> 5), nwarp = (long long)gridDim.x * HEAD_WARPS;
+    double wl[HEAD_MAXJ];
+#pragma unroll
+    for (int j = 0; j < HEAD_MAXJ; j++) wl[j] = lane + 32 * j < h2 ? w[lane + 32 * j] : 0.0;
+    const double bias = b[0];
+    for (long long r = warp; r < m; r += nwarp) {
+        const double *row = a2 + r * h2;
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < HEAD_MAXJ; j++)
+            if (lane + 32 * j < h2) s += row[lane + 32 * j] * wl[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) y[r] = s + bias;
+    }
+}
+
+// d2[n][k] = a2[n][k] > 0 ? dy[n] w[k] : 0 ; part[block][k] = sum over the block's rows of dy[n] a2[n][k], part[block][h2] = sum dy[n]
+__global__ void __launch_bounds__(32 * HEAD_WARPS)
+head1_bwd_kernel(const double *__restrict__ a2, const double *__restrict__ dy, long long m, int h2, const double *__restrict__ w,
+                 double *__restrict__ d2, double *__restrict__ part) {
+    __shared__ double red[HEAD_WARPS][32 * HEAD_MAXJ + 1];
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    const long long per = (m + gridDim.x - 1) / gridDim.x, r0 = (long long)blockIdx.x * per, r1 = r0 + per < m ? r0 + per : m;
+    double wl[HEAD_MAXJ], acc[HEAD_MAXJ], sdy = 0.0;
+#pragma unroll
+    for (int j = 0; j < HEAD_MAXJ; j++) { wl[j] = lane + 32 * j < h2 ? w[lane + 32 * j] : 0.0; acc[j] = 0.0; }
+    for (long long r = r0 + wp; r < r1; r += HEAD_WARPS) {
+        const double g = dy[r];
+        const double *row = a2 + r * h2;
+        double *out = d2 + r * h2;
+        sdy += g;
+#pragma unroll
+        for (int j = 0; j < HEAD_MAXJ; j++)
+            if (lane + 32 * j < h2) {
+                const double a = row[lane + 32 * j];
+                out[lane + 32 * j] = a > 0.0 ? g * wl[j] : 0.0;
+                acc[j] += g * a;
+            }
+    }
+#pragma unroll
+    for (int j = 0; j < HEAD_MAXJ; j++) red[wp][lane + 32 * j] = acc[j];
+    if (lane == 0) red[wp][32 * HEAD_MAXJ] = sdy;
+    __syncthreads();
+    for (int k = threadIdx.x; k <= h2; k += blockDim.x) {
+        const int src = k < h2 ? k : 32 * HEAD_MAXJ;
+        double t = 0.0;
+#pragma unroll
+        for (int q = 0; q < HEAD_WARPS; q++) t += red[q][src];
+        part[(size_t)blockIdx.x * (h2 + 1) + k] = t;
+    }
+}
+
+// gW[k] (+)= sum_blocks part[block][k] in block order ; gb (+)= part[.][h2]
+__global__ void head1_reduce_kernel(const double *__restrict__ part, int nblocks, int h2, double *__restrict__ gW, double *__restrict__ gb,
+                                    int accumulate) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > h2) return;
+    double t = 0.0;
+    for (int b = 0; b < nblocks; b++) t += part[(size_t)b * (h2 + 1) + k];
+    double *dst = k < h2 ? gW + k : gb;
+    *dst = accumulate ? *dst + t : t;
+}
+
 struct Buf {
     char *base;
     long long off = 0, cap;
@@ -160,12 +235,17 @@ int egp_oz_mlp_step_f64(const EgpMlpNet *net, const double *d_x, int64_t ldx, in
 #define OZ_TRY(call) do { rc = (call); if (rc) return rc; } while (0)
     OZ_TRY(slice_rows(net->d_W1, h1, in, in, S, W1s.q, kin, W1s.e, nullptr, st));
     OZ_TRY(slice_rows(net->d_W2, h2, h1, h1, S, W2s.q, kh1, W2s.e, nullptr, st));
-    OZ_TRY(slice_rows(net->d_W3, od, h2, h2, S, W3s.q, kh2, W3s.e, nullptr, st));
+    // scalar head (the critic): streamed in plain float64 instead of padding a 1-wide GEMM to a tensor-core tile
+    const bool head1 = od == 1 && h2 <= 32 * HEAD_MAXJ;
+    const int head_blocks = num_sms() * 4;
+    if (!head1) OZ_TRY(slice_rows(net->d_W3, od, h2, h2, S, W3s.q, kh2, W3s.e, nullptr, st));
     if (bwd) {
         EGP_CUDA(cudaMemsetAsync(cmax[0], 0, cmax_bytes, st));
         EGP_CUDA(cudaMemsetAsync(cmax[1], 0, cmax_bytes, st));
-        OZ_TRY(col_absmax(net->d_W3, od, h2, h2, cmax[0], st));
-        OZ_TRY(slice_colsT(net->d_W3, od, h2, h2, S, cmax[0], W3T.q, kod, W3T.e, 0, st));
+        if (!head1) {
+            OZ_TRY(col_absmax(net->d_W3, od, h2, h2, cmax[0], st));
+            OZ_TRY(slice_colsT(net->d_W3, od, h2, h2, S, cmax[0], W3T.q, kod, W3T.e, 0, st));
+        }
         OZ_TRY(col_absmax(net->d_W2, h2, h1, h1, cmax[1], st));
         OZ_TRY(slice_colsT(net->d_W2, h2, h1, h1, S, cmax[1], W2T.q, kh2, W2T.e, 0, st));
         if (dxc > 0) {          // W1[:, :dxc]^T: rows = input feature, contraction over h1
@@ -197,12 +277,17 @@ int egp_oz_mlp_step_f64(const EgpMlpNet *net, const double *d_x, int64_t ldx, in
         if (bwd) OZ_TRY(slice_colsT(a1, m, h1, h1, S, cmax[3], a1T.q, mp, a1T.e, 1, st));
         o = GemmOut(); o.C = a2; o.ldc = h2; o.bias = net->d_b2; o.relu = 1;
         OZ_TRY(gemm(a1s.q, a1s.e, m, W2s.q, W2s.e, h2, kh1, S, o, st));
-        if (bwd) EGP_CUDA(cudaMemsetAsync(cmax[4], 0, cmax_bytes, st));
-        OZ_TRY(slice_rows(a2, m, h2, h2, S, a2s.q, kh2, a2s.e, bwd ? cmax[4] : nullptr, st));
-        if (bwd) OZ_TRY(slice_colsT(a2, m, h2, h2, S, cmax[4], a2T.q, mp, a2T.e, 1, st));
         double *yc = d_y ? d_y + r0 * od : ybuf;
-        o = GemmOut(); o.C = yc; o.ldc = od; o.bias = net->d_b3;
-        OZ_TRY(gemm(a2s.q, a2s.e, m, W3s.q, W3s.e, od, kh2, S, o, st));
+        if (head1) {
+            head1_fwd_kernel<<<head_blocks, 32 * HEAD_WARPS, 0, st>>>(a2, m, h2, net->d_W3, net->d_b3, yc);
+            EGP_CHECK_LAUNCH("head1_fwd_kernel");
+        } else {
+            if (bwd) EGP_CUDA(cudaMemsetAsync(cmax[4], 0, cmax_bytes, st));
+            OZ_TRY(slice_rows(a2, m, h2, h2, S, a2s.q, kh2, a2s.e, bwd ? cmax[4] : nullptr, st));
+            if (bwd) OZ_TRY(slice_colsT(a2, m, h2, h2, S, cmax[4], a2T.q, mp, a2T.e, 1, st));
+            o = GemmOut(); o.C = yc; o.ldc = od; o.bias = net->d_b3;
+            OZ_TRY(gemm(a2s.q, a2s.e, m, W3s.q, W3s.e, od, kh2, S, o, st));
+        }
         if (!bwd) continue;
         // ---- loss on the chunk: dL/dy
         if (loss->kind == 1) {
@@ -231,12 +316,20 @@ int egp_oz_mlp_step_f64(const EgpMlpNet *net, const double *d_x, int64_t ldx, in
             EGP_CHECK_LAUNCH("oz_wgrad_reduce_kernel");
             return EGP_OK;
         };
-        EGP_CUDA(cudaMemsetAsync(cmax[5], 0, cmax_bytes, st));
-        OZ_TRY(slice_rows(dy, m, od, od, S, dys.q, kod, dys.e, cmax[5], st));
-        OZ_TRY(slice_colsT(dy, m, od, od, S, cmax[5], dyT.q, mp, dyT.e, 0, st));
-        OZ_TRY(wgrad(a2T, h2, dyT, od, net->d_gW3, net->d_gb3));
-        o = GemmOut(); o.C = d2; o.ldc = h2; o.mask = a2; o.ldm = h2;
-        OZ_TRY(gemm(dys.q, dys.e, m, W3T.q, W3T.e, h2, kod, S, o, st));
+        if (head1) {
+            if ((long long)head_blocks * (h2 + 1) * 8 > part_bytes) { set_error("egp_oz_mlp_step_f64: head workspace"); return EGP_EINVAL; }
+            head1_bwd_kernel<<<head_blocks, 32 * HEAD_WARPS, 0, st>>>(a2, dy, m, h2, net->d_W3, d2, part);
+            EGP_CHECK_LAUNCH("head1_bwd_kernel");
+            head1_reduce_kernel<<<(h2 + 1 + 127) / 128, 128, 0, st>>>(part, head_blocks, h2, net->d_gW3, net->d_gb3, acc);
+            EGP_CHECK_LAUNCH("head1_reduce_kernel");
+        } else {
+            EGP_CUDA(cudaMemsetAsync(cmax[5], 0, cmax_bytes, st));
+            OZ_TRY(slice_rows(dy, m, od, od, S, dys.q, kod, dys.e, cmax[5], st));
+            OZ_TRY(slice_colsT(dy, m, od, od, S, cmax[5], dyT.q, mp, dyT.e, 0, st));
+            OZ_TRY(wgrad(a2T, h2, dyT, od, net->d_gW3, net->d_gb3));
+            o = GemmOut(); o.C = d2; o.ldc = h2; o.mask = a2; o.ldm = h2;
+            OZ_TRY(gemm(dys.q, dys.e, m, W3T.q, W3T.e, h2, kod, S, o, st));
+        }
         EGP_CUDA(cudaMemsetAsync(cmax[6], 0, cmax_bytes, st));
         OZ_TRY(slice_rows(d2, m, h2, h2, S, d2s.q, kh2, d2s.e, cmax[6], st));
         OZ_TRY(slice_colsT(d2, m, h2, h2, S, cmax[6], d2T.q, mp, d2T.e, 0, st));

@@ -638,12 +638,15 @@ class OzMlp:
         self.work = torch.empty(nbytes, dtype=torch.uint8, device=device)
 
     @staticmethod
-    def launch_count(n_chunks, bwd, slice_x, fill_cache, dx=False):
+    def launch_count(n_chunks, bwd, slice_x, fill_cache, dx=False, head1=False):
         """kernels launched by one egp_oz_mlp_step_f64 call (csrc/oz_mlp.cu): weight slicing + per chunk the x slicing
         (unless cached), 3 GEMMs + 2 row / 2 transposed slicings forward, loss, 5 GEMMs + 3 reductions + slicings backward"""
         prep = 3 + (6 if bwd else 0) + (3 if dx else 0)
         x = (3 if (bwd or fill_cache) else 1) if slice_x else 0
         per_chunk = x + (9 + 1 + 17 if bwd else 5) + (1 if dx else 0)
+        if head1:       # scalar head streamed in float64: no slices of the last hidden layer, head forward / backward + reduce
+            prep -= 1 + (3 if bwd else 0)
+            per_chunk -= (3 + 4) if bwd else 1
         return prep + n_chunks * per_chunk
 
     def new_cache(self, n):
@@ -686,7 +689,8 @@ class OzMlp:
         check(load().egp_oz_mlp_step_f64(C.byref(net), ptr(x[:1]) if not x.is_contiguous() else ptr(x), x.stride(0), n, C.byref(ls),
                                          _raw(y), self.S, self.chunk, _raw(cache['buf']) if cache is not None else None, state,
                                          _raw(self.work), self.work.numel(), stream_ptr()), 'egp_oz_mlp_step_f64')
-        launches += self.launch_count((n + self.chunk - 1) // self.chunk, loss is not None, state != 2, state == 1, dx is not None)
+        launches += self.launch_count((n + self.chunk - 1) // self.chunk, loss is not None, state != 2, state == 1, dx is not None,
+                                      head1=self.dims[3] == 1 and self.dims[2] <= 512)
         if cache is not None:
             cache['valid'] = True
         return y
