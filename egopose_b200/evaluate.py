@@ -23,13 +23,18 @@ from . import lib
 
 
 def expert_obs_table(model):
-    """[total_frames, S]: HumanoidEnv.get_obs() (humanoid_v1.py:73-96) of every expert frame, read off the packed
-    expert rows: qpos[2] | de-headed root quaternion | hinge angles | root velocity in the heading frame | qvel[3:]"""
+    """[total_frames, S]: HumanoidEnv.get_obs() (humanoid_v1.py:73-96) of every expert frame (qpos, qvel), read off the packed
+    expert rows: qpos[2] | de-headed root quaternion | hinge angles | root velocity in the heading frame | qvel[3:].
+    The heading transform is applied here (utils/math.py:47-59) rather than taken from ``rlinv_local``: a take's frame 0
+    copies frame 1's finite differences (gen_expert.py:67-70), so its stored rlinv_local belongs to frame 1's heading."""
     X, r = lib.X, model.rows_host
     nq, nv = model.nq, model.nv
-    return np.ascontiguousarray(np.concatenate(
-        [r[:, X['QPOS'] + 2:X['QPOS'] + 3], r[:, X['RQ_RMH']:X['RQ_RMH'] + 4], r[:, X['QPOS'] + 7:X['QPOS'] + nq],
-         r[:, X['RLINV_LOCAL']:X['RLINV_LOCAL'] + 3], r[:, X['QVEL'] + 3:X['QVEL'] + nv]], axis=1))
+    q, v = r[:, X['QPOS']:X['QPOS'] + nq], r[:, X['QVEL']:X['QVEL'] + nv]
+    hn = np.sqrt(q[:, 3] ** 2 + q[:, 6] ** 2)
+    hw, hz = q[:, 3] / hn, q[:, 6] / hn
+    c, s = hw * hw - hz * hz, 2.0 * hw * hz                     # rotation about z by the heading; transform_vec applies R^T
+    vl = np.stack([c * v[:, 0] + s * v[:, 1], -s * v[:, 0] + c * v[:, 1], v[:, 2]], axis=1)
+    return np.ascontiguousarray(np.concatenate([q[:, 2:3], r[:, X['RQ_RMH']:X['RQ_RMH'] + 4], q[:, 7:], vl, v[:, 3:]], axis=1))
 
 
 def _context_table(env, policy_vs_net, dev):
