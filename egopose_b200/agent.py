@@ -544,7 +544,7 @@ class AgentPPO(AgentPG):
             raise lib.EgpError('one (params, max_norm) clip group is supported (ego_mimic.py:90)')
         return float(self.policy_grad_clip[0][1])
 
-    def _policy_step(self, xp, actions, adv, logp0, exps, inv_count, log_std, max_norm, mu=None, cache=True):
+    def _policy_step(self, xp, actions, adv, logp0, exps, inv_count, log_std, max_norm, mu=None, cache=True, init_logp0=False):
         """ppo_loss forward+backward, gradient all-reduce, clip + Adam (agent_ppo.py:47-51 / :38-43)"""
         inp = xp if isinstance(xp, _NetInput) else _NetInput(x_const=xp)
         oz = self._oz(self._pt, inp)
@@ -559,7 +559,8 @@ class AgentPPO(AgentPG):
             oz.step(self._pt.weights(), xt, grads=self._pt.grads(), dx=dx,
                     cache=self._xcache(oz, xt) if (cache and not inp.learned) else None,
                     loss=dict(kind='ppo', actions=actions, log_std=log_std, adv=adv, stats=self._stats, logp0=logp0, exps=exps,
-                              clip_eps=self.clip_epsilon, inv_count=inv_count, dlogstd=dls, loss=self._scal[1:2]))
+                              clip_eps=self.clip_epsilon, inv_count=inv_count, dlogstd=dls, loss=self._scal[1:2],
+                              init_logp0=init_logp0))
             if inp.learned:
                 inp.backward(dx)
             if _dist() is not None:
@@ -628,13 +629,21 @@ class AgentPPO(AgentPG):
         """agents/agent_ppo.py:16-51"""
         log_std = self.policy_net.action_log_std.data.view(-1)
         oz = self._oz(self._pt, xp)
-        if oz is not None:
-            xt = xp.x(grad=False) if xp.learned else xp.x_const
-            mu = oz.step(self._pt.weights(), xt, y=self._pt._buf('y', (xt.shape[0], self._pt.dims()[3]), xt),
-                         cache=None if xp.learned else self._xcache(oz, xt))
+        # Full-batch branch on the tensor-core back end: the first epoch's policy pass runs at the parameters that define
+        # fixed_log_probs (:18-20), so its loss kernel WRITES them (ratio = exp(0) = 1 there, in the reference as well) and
+        # the separate no-grad forward over the batch is skipped
+        fuse0 = oz is not None and not self.use_mini_batch and not xp.learned and os.environ.get('EGP_FUSE_LOGP0', '1') == '1'
+        mu = None
+        if fuse0:
+            logp0 = self._pt._buf('logp0', (actions.shape[0],), actions)
         else:
-            mu = self._pt.forward(xp.x(grad=False))
-        logp0 = lib.gauss_logp(mu, actions, log_std)                    # fixed_log_probs (:18-20)
+            if oz is not None:
+                xt = xp.x(grad=False) if xp.learned else xp.x_const
+                mu = oz.step(self._pt.weights(), xt, y=self._pt._buf('y', (xt.shape[0], self._pt.dims()[3]), xt),
+                             cache=None if xp.learned else self._xcache(oz, xt))
+            else:
+                mu = self._pt.forward(xp.x(grad=False))
+            logp0 = lib.gauss_logp(mu, actions, log_std)                # fixed_log_probs (:18-20)
         max_norm = self._max_norm()
         if self.use_mini_batch:
             if xp.learned or xv.learned:
@@ -662,7 +671,8 @@ class AgentPPO(AgentPG):
                 self.update_value(xv, returns, inv_n, reuse_forward=(ep == 0 and self._value_fresh))     # :46
                 vloss.append(self._scal[0:1].clone())
             surr.append(self._policy_step(xp, actions, adv, logp0, exps, inv_count, log_std, max_norm,
-                                          mu=mu if ep == 0 else None))      # epoch 0 reuses the fixed-log-prob forward
+                                          mu=mu if ep == 0 else None,       # epoch 0 reuses the fixed-log-prob forward
+                                          init_logp0=fuse0 and ep == 0))
         if two:
             torch.cuda.current_stream().wait_stream(self._vstream)
         self.last_info = dict(surr_loss=surr, value_loss=vloss)

@@ -291,8 +291,9 @@ int egp_oz_mlp_step_f64(const EgpMlpNet *net, const double *d_x, int64_t ldx, in
         if (!bwd) continue;
         // ---- loss on the chunk: dL/dy
         if (loss->kind == 1) {
-            OZ_TRY(egp_ppo_loss_grad_f64(yc, loss->d_actions + r0 * od, loss->d_log_std, loss->d_adv + r0, loss->d_stats, loss->d_logp0 + r0,
-                                         loss->d_exps + r0, loss->clip_eps, loss->inv_count, m, od, dy, loss->d_dlogstd, loss->d_loss, st));
+            OZ_TRY(ppo_loss_grad_launch(yc, loss->d_actions + r0 * od, loss->d_log_std, loss->d_adv + r0, loss->d_stats,
+                                        const_cast<double *>(loss->d_logp0) + r0, loss->init_logp0, loss->d_exps + r0, loss->clip_eps,
+                                        loss->inv_count, m, od, dy, loss->d_dlogstd, loss->d_loss, st));
         } else if (loss->kind == 2) {
             if (od != 1) { set_error("egp_oz_mlp_step_f64: value loss needs out_dim 1"); return EGP_EINVAL; }
             OZ_TRY(egp_value_loss_grad_f64(yc, loss->d_returns + r0, loss->inv_n, m, dy, loss->d_loss, st));

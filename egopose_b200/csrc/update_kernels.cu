@@ -251,9 +251,9 @@ gauss_logp_kernel(const double *__restrict__ mu, const double *__restrict__ act,
 
 __global__ void __launch_bounds__(256)
 ppo_loss_grad_kernel(const double *__restrict__ mu, const double *__restrict__ act, const double *__restrict__ log_std,
-                     const double *__restrict__ adv, const double *__restrict__ stats, const double *__restrict__ logp0,
+                     const double *__restrict__ adv, const double *__restrict__ stats, double *logp0,
                      const double *__restrict__ exps, double clip_eps, double inv_count, long long n, int adim,
-                     double *__restrict__ dmu, double *__restrict__ dlogstd, double *__restrict__ loss) {
+                     double *__restrict__ dmu, double *__restrict__ dlogstd, double *__restrict__ loss, int record) {
     const int sub = threadIdx.x & (LPR - 1);
     const long long g0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / LPR;
     const long long stride = (long long)gridDim.x * blockDim.x / LPR;
@@ -279,9 +279,12 @@ ppo_loss_grad_kernel(const double *__restrict__ mu, const double *__restrict__ a
         }
         s = group_sum16(s);
         const bool on = valid && exps[row] != 0.0;
+        // record: this IS the pass that defines fixed_log_probs (agent_ppo.py:18-20: same parameters, same arithmetic as
+        // the first epoch's forward, so the reference's ratio there is exp(0) = 1 as well)
+        if (record && valid && sub == 0) logp0[row] = s;
         double coef = 0.0;                           // dL/dlogp
         if (on) {
-            double ratio = exp(s - logp0[row]);
+            double ratio = record ? 1.0 : exp(s - logp0[row]);
             double ah = (adv[row] - a_mean) * a_inv;
             double lo = 1.0 - clip_eps, hi = 1.0 + clip_eps;
             double clamped = fmin(fmax(ratio, lo), hi);
@@ -559,6 +562,16 @@ int egp_ppo_loss_grad_f64(const double *d_mu, const double *d_actions, const dou
                           const double *d_stats, const double *d_logp0, const double *d_exps, double clip_eps,
                           double inv_count, int64_t n, int adim, double *d_dmu, double *d_dlogstd, double *d_loss,
                           void *stream) {
+    return egp::ppo_loss_grad_launch(d_mu, d_actions, d_log_std, d_adv, d_stats, const_cast<double *>(d_logp0), 0, d_exps, clip_eps,
+                                     inv_count, n, adim, d_dmu, d_dlogstd, d_loss, stream);
+}
+
+}  // extern "C" (the launcher below has C++ linkage)
+
+int egp::ppo_loss_grad_launch(const double *d_mu, const double *d_actions, const double *d_log_std, const double *d_adv,
+                              const double *d_stats, double *d_logp0, int record, const double *d_exps, double clip_eps,
+                              double inv_count, int64_t n, int adim, double *d_dmu, double *d_dlogstd, double *d_loss,
+                              void *stream) {
     if (n <= 0 || adim <= 0 || adim > 4 * LPR || !d_mu || !d_actions || !d_log_std || !d_adv || !d_stats || !d_logp0 ||
         !d_exps || !d_dmu || !d_loss) {
         set_error("egp_ppo_loss_grad_f64: bad argument (adim must be <= %d)", 4 * LPR);
@@ -566,10 +579,12 @@ int egp_ppo_loss_grad_f64(const double *d_mu, const double *d_actions, const dou
     }
     ppo_loss_grad_kernel<<<grid_for(n * LPR, 256), 256, 0, (cudaStream_t)stream>>>(
         d_mu, d_actions, d_log_std, d_adv, d_stats, d_logp0, d_exps, clip_eps, inv_count, (long long)n, adim, d_dmu,
-        d_dlogstd, d_loss);
+        d_dlogstd, d_loss, record);
     EGP_CHECK_LAUNCH("ppo_loss_grad_kernel");
     return EGP_OK;
 }
+
+extern "C" {
 
 int egp_value_loss_grad_f64(const double *d_v, const double *d_ret, double inv_n, int64_t n, double *d_dv,
                             double *d_loss, void *stream) {

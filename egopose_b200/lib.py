@@ -80,7 +80,7 @@ class MlpNet(C.Structure):
 class MlpLoss(C.Structure):
     _fields_ = [('kind', C.c_int32), ('d_actions', _vp), ('d_log_std', _vp), ('d_adv', _vp), ('d_stats', _vp),
                 ('d_logp0', _vp), ('d_exps', _vp), ('clip_eps', C.c_double), ('inv_count', C.c_double),
-                ('d_dlogstd', _vp), ('d_returns', _vp), ('inv_n', C.c_double), ('d_loss', _vp)]
+                ('d_dlogstd', _vp), ('d_returns', _vp), ('inv_n', C.c_double), ('d_loss', _vp), ('init_logp0', C.c_int32)]
 
 
 # every symbol include/egopose_b200.h declares: name -> (restype, argtypes)
@@ -675,6 +675,7 @@ class OzMlp:
                 ls.d_logp0, ls.d_exps = _raw(loss['logp0']), _raw(loss['exps'])
                 ls.clip_eps, ls.inv_count = float(loss['clip_eps']), float(loss['inv_count'])
                 ls.d_dlogstd = _raw(loss.get('dlogstd'))
+                ls.init_logp0 = int(bool(loss.get('init_logp0', False)))
             else:
                 ls.kind = 2
                 ls.d_returns, ls.inv_n = _raw(loss['returns']), float(loss['inv_n'])

@@ -310,6 +310,9 @@ typedef struct {
     const double *d_returns;
     double inv_n;
     double *d_loss;                     /* [1] accumulated */
+    /* kind 1: 1 = this pass runs at the parameters that define fixed_log_probs (agent_ppo.py:18-20, first epoch): logp is
+     * WRITTEN to d_logp0 and the ratio is 1, so no separate forward pass for the fixed log-probs is needed */
+    int32_t init_logp0;
 } EgpMlpLoss;
 
 int64_t egp_oz_mlp_chunk_rows(void);   /* 128 rows x number of SMs */
