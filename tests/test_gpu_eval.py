@@ -257,3 +257,23 @@ def test_eval_takes_valuefs_matches_reference_golden(golden):
     assert np.allclose(batched[0]['traj_pred']['a'], results['traj_pred']['a'], rtol=1e-9, atol=1e-10)
     assert batched[0]['traj_pred']['b'].shape == results['traj_pred']['b'].shape
     env.close()
+
+
+def test_eval_script_synthetic(tmp_path):
+    """examples/eval_egomimic.py: the command line of ego_mimic_eval.py end to end (ragged synthetic takes, reference
+    layer sizes [300, 200], both fail-safes), result file names and pickle layout of ego_mimic_eval.py:186-192"""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(helpers.ROOT, 'examples'))
+    import eval_egomimic
+    p = eval_egomimic.main(['--synthetic', '--takes', '2', '--len', '36', '--fail-safe', 'valuefs', '--out', str(tmp_path)])
+    assert p.endswith('iter_0000_test.p')
+    results, meta = pickle.load(open(p, 'rb'))
+    assert set(results) == {'traj_pred', 'traj_orig', 'vel_pred'} and meta['algo'] == 'ego_mimic' and meta['num_reset'] >= 0
+    assert results['traj_pred']['take_0'].shape == (16, 59) and results['traj_pred']['take_1'].shape == (23, 59)
+    assert results['vel_pred']['take_1'].shape == (23, 58) and np.all(np.isfinite(results['traj_pred']['take_1']))
+    assert np.allclose(results['traj_pred']['take_0'][0], results['traj_orig']['take_0'][0], atol=1e-12)   # starts on the expert
+    p2 = eval_egomimic.main(['--synthetic', '--takes', '2', '--len', '36', '--fail-safe', 'naivefs', '--out', str(tmp_path)])
+    assert p2.endswith('iter_0000_test_naivefs.p')
+    r2, m2 = pickle.load(open(p2, 'rb'))
+    assert r2['traj_pred']['take_1'].shape == (23, 59) and m2['num_reset'] >= 0 and np.all(np.isfinite(r2['traj_pred']['take_1']))
