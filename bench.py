@@ -205,7 +205,8 @@ def run_reference(args):
     line = {'impl': 'reference', 'metric': 'env-steps/sec (humanoid PPO rollout+update)', 'value': v, 'unit': 'env-steps/s',
             'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'hidden': args.hidden, 'epochs': args.epochs},
+            'config': {'workload': WORKLOAD, 'envs_per_gpu': args.envs, 'horizon': args.horizon, 'hidden': args.hidden,
+                       'epochs': args.epochs, 'parallelism': 'host threads (rank 0 only)'},
             'cpu_baseline': {'value': v, 'unit': 'env-steps/s', 'cores': detail['cores'], 'kind': 'port',
                              'sample': detail['sample'], 'rollout_steps_per_s': detail['rollout_steps_per_s'],
                              'update_samples_per_s': detail['update_samples_per_s']},
