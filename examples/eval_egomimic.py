@@ -22,7 +22,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
-from egopose_b200 import checkpoint, evaluate  # noqa: E402
+from egopose_b200 import checkpoint, evaluate, metrics  # noqa: E402
 from egopose_b200.config import Config  # noqa: E402
 from egopose_b200.env import HumanoidEnv  # noqa: E402
 from egopose_b200.nets import MLP, FrameContext, PolicyGaussian, Value, VideoStateNet  # noqa: E402
@@ -106,6 +106,8 @@ def main(argv=None):
         d = np.linalg.norm(results['traj_pred'][take][:, 7:] - results['traj_orig'][take][:, 7:], axis=1).mean()
         print('%-12s frames %4d  mean joint-angle distance to the expert %.4f  mean reward %.4f'
               % (take, results['traj_pred'][take].shape[0], d, info['rewards'][take].mean()))
+    m = metrics.compute_metrics(results)                                                    # eval_pose.py:31-66 ('stats' mode)
+    print('all - pose dist: %.4f, vel dist: %.4f, accels: %.4f' % (m['pose_dist'], m['vel_dist'], m['smoothness']))
     print('num reset: %d' % meta['num_reset'])
     print('saved results to %s' % res_path)
     env.close()

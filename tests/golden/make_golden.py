@@ -13,6 +13,7 @@ Runs only in the build container (needs /root/reference):   python tests/golden/
                     and the gen_expert.py feature pipeline re-driven with the reference's own helpers
   expert_file.npz   ego_pose/data_process/gen_expert.py:28-83 get_expert, all 13 keys + scalars, with an lb:ub cut
   eval_forecast.npz ego_pose/ego_forecast_eval.py:95-180 windows with and without --gt-init (reference env + sync_traj)
+  pose_metrics.npz  ego_pose/utils/metrics.py + the aggregation of ego_pose/eval_pose.py:31-66
   eval_traj.npz     ego_pose/ego_mimic_eval.py:93-177 evaluation roll-out ('naivefs' fail-safe) re-driven with the
                     reference's own env / align_human_state / PolicyGaussian / ZFilter on the restated physics
 """
@@ -787,8 +788,37 @@ def gen_eval_forecast():
     np.savez_compressed(os.path.join(OUT, 'eval_forecast.npz'), **out)
 
 
+
+def gen_metrics():
+    """ego_pose/utils/metrics.py (get_joint_angles / get_joint_vels / get_joint_accels / get_mean_dist / get_mean_abs) and the
+    aggregation of ego_pose/eval_pose.py:31-66 on two synthetic (prediction, ground truth) trajectory pairs"""
+    from ego_pose.utils.metrics import get_joint_accels, get_joint_angles, get_joint_vels, get_mean_abs, get_mean_dist
+    orc = cphys.Oracle()
+    rng = np.random.RandomState(91)
+    dt = 1 / 30.0
+    out, tot = {}, np.zeros(3)
+    for i, L in enumerate((17, 12)):
+        gt = cphys.synthetic_takes(orc.md, 1, L, seed=90 + i)[0]
+        pred = gt.copy()
+        pred[:, :3] += 0.05 * rng.randn(L, 3)
+        q = pred[:, 3:7] + 0.1 * rng.randn(L, 4)
+        pred[:, 3:7] = q / np.linalg.norm(q, axis=1, keepdims=True)
+        pred[:, 7:] += 0.1 * rng.randn(L, gt.shape[1] - 7)
+        pred[3] = pred[2]                                    # identical consecutive frames: the zero-rotation branch
+        angs_gt, vels_gt = get_joint_angles(gt), get_joint_vels(gt, dt)
+        angs, vels = get_joint_angles(pred), get_joint_vels(pred, dt)
+        accels = get_joint_accels(vels, dt)
+        m = np.array([get_mean_dist(angs, angs_gt), get_mean_dist(vels, vels_gt), get_mean_abs(accels)])
+        tot += m
+        out.update({'gt%d' % i: gt, 'pred%d' % i: pred, 'angs%d' % i: angs, 'vels%d' % i: vels, 'accels%d' % i: accels,
+                    'metrics%d' % i: m})
+    out['global'] = tot / 2
+    np.savez_compressed(os.path.join(OUT, 'pose_metrics.npz'), **out)
+    print('pose_metrics ok', out['global'])
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['ppo', 'math', 'zfilter', 'env', 'vsnet', 'fcnet', 'eval', 'expert_file', 'eval_forecast']
+    which = sys.argv[1:] or ['ppo', 'math', 'zfilter', 'env', 'vsnet', 'fcnet', 'eval', 'expert_file', 'eval_forecast', 'metrics']
     if 'ppo' in which:
         gen_ppo()
     if 'ppo_mb' in which or 'ppo' in which:
@@ -807,5 +837,7 @@ if __name__ == '__main__':
         gen_expert_file()
     if 'eval_forecast' in which:
         gen_eval_forecast()
+    if 'metrics' in which:
+        gen_metrics()
     if 'env' in which:
         gen_env()
