@@ -69,6 +69,18 @@ class _FlatNet:
                 st['exp_avg_sq'] = self.v[a:b].view(p.shape)
                 st['step'] = torch.tensor(float(self.step))
 
+    def realias(self):
+        """Re-establish parameter <-> flat-buffer aliasing after the caller moved the modules (utils/torch.py:13-27
+        to_cpu / to_device around checkpointing, ego_mimic.py:134: module.to() rebinds p.data to fresh tensors).  The
+        module tensors are the source of truth at that point (the caller may also have loaded a state dict)."""
+        moved = False
+        for p, a, b in zip(self.params, self.offsets[:-1], self.offsets[1:]):
+            if p.data.data_ptr() != self.flat[a:b].data_ptr() or p.data.device != self.flat.device:
+                self.flat[a:b].copy_(p.data.reshape(-1).to(self.flat.device, torch.float64))
+                p.data = self.flat[a:b].view(p.shape)
+                moved = True
+        return moved
+
     def view(self, buf, name):
         i = self.names.index(name)
         return buf[self.offsets[i]:self.offsets[i + 1]].view(self.params[i].shape)
@@ -371,6 +383,8 @@ class AgentPG(Agent):
     # ---- flat storage ------------------------------------------------------------------------------
     def _setup(self):
         if self._nets is not None:
+            self._pf.realias()
+            self._vf.realias()
             return
         for opt in (self.optimizer_policy, self.optimizer_value):
             if not isinstance(opt, torch.optim.Adam):
@@ -453,8 +467,8 @@ class AgentPG(Agent):
             if ent is None:
                 ent = oz.new_cache(x.shape[0])
             ent['valid'] = False
-            ent['live'] = True
             self._xcaches[key] = ent
+        ent['live'] = True
         return ent
 
     def update_value(self, x, returns, inv_n, reuse_forward=False, cache=True):
@@ -500,8 +514,11 @@ class AgentPG(Agent):
         states, actions, rewards, masks, exps, v_metas, horizon = self._device_batch(batch)
         xp, xv = self._inputs(states, v_metas, masks, horizon)
         # values + GAE (agent_pg.py:48-53, core/common.py:5-25)
+        # input slices are valid for ONE update only: the rollout buffers (and the caching allocator's blocks) keep
+        # their addresses across iterations, so a pointer match says nothing about the contents
         for ent in self._xcaches.values():
             ent['live'] = False
+            ent['valid'] = False
         oz = self._oz(self._vt, xv)
         if oz is not None:
             xt = xv.x(grad=False) if xv.learned else xv.x_const
@@ -521,7 +538,10 @@ class AgentPG(Agent):
             dist_utils.allreduce_sum_(n_exp)
             n_global = float(stats[0].item())
         self._stats = stats
-        self.update_policy(xp, xv, actions, returns, adv, exps, 1.0 / float(n_exp.item()), 1.0 / n_global)
+        n_exp = float(n_exp.item())
+        # a batch without sampled rows (mean actions only) has no surrogate term: zero policy gradient instead of
+        # the reference's NaN mean over an empty selection (agent_ppo.py:45,64)
+        self.update_policy(xp, xv, actions, returns, adv, exps, 1.0 / n_exp if n_exp > 0 else 0.0, 1.0 / n_global)
         torch.cuda.synchronize()
         return time.time() - t0
 
@@ -622,7 +642,7 @@ class AgentPPO(AgentPG):
                 self.update_value(gxv[lo:hi], g['ret'][lo:hi], 1.0 / ((hi - lo) * ws), cache=False)
                 vloss.append(self._scal[0:1].clone())
                 surr.append(self._policy_step(g['xp'][lo:hi], g['ac'][lo:hi], g['adv'][lo:hi], g['lp'][lo:hi], g['ex'][lo:hi],
-                                              1.0 / float(counts[i]), log_std, max_norm, cache=False))
+                                              (1.0 / float(counts[i])) if counts[i] > 0 else 0.0, log_std, max_norm, cache=False))
         self.last_info = dict(surr_loss=surr, value_loss=vloss)
 
     def update_policy(self, xp, xv, actions, returns, adv, exps, inv_count, inv_n):

@@ -27,36 +27,12 @@
 
 #include "common.cuh"
 
+#include "tree.cuh"
+
 namespace egp {
 
-constexpr int MAXB = EGP_MAX_BODY;
-constexpr int MAXV = EGP_MAX_DOF;
-constexpr int MAXC = EGP_MAX_CHAIN;
 constexpr int ENVS_PER_CTA = 32;
 constexpr int JB = 8;                       // output neurons per register block in the policy MLP
-
-struct DevModel {
-    int nq, nv, nu, nbody, nchain, frame_skip, head_body, v_ord, decay;
-    int ee_body[EGP_NEE];
-    double h, grav[3];
-    int body_parent[MAXB], body_dofadr[MAXB], body_dofnum[MAXB], body_qposadr[MAXB], body_chain[MAXB];
-    double body_pos[MAXB][3], body_mass[MAXB], body_ipos[MAXB][3], body_inertia[MAXB][6], b_diffw[MAXB];
-    int dof_axis_id[MAXV];
-    double dof_arm[MAXV], dof_axis[MAXV][3], dof_anchor[MAXV][3];
-    double kp[MAXV], kd[MAXV], a_ref[MAXV], a_scale[MAXV], tlim[MAXV];        // indexed by dof (0 on the root)
-    int chain_lo[MAXC], chain_hi[MAXC], chain_parent[MAXC];                   // body ranges, inclusive
-    // T4 schedule: tree level of a chain, warp that owns it, slot of its forward/accel junction record (chains
-    // with children), sibling slot for its backward junction record, number of child chains
-    int chain_level[MAXC], chain_warp[MAXC], chain_pslot[MAXC], chain_cslot[MAXC], chain_nchild[MAXC];
-    int nlevel, nparent, max_sib, t4_ok;
-    int body_xp_slot[MAXB], ee_xp_slot[EGP_NEE], head_xp_slot;                // rows of the shared body-position record
-    // TMEM scratch layout (T4): index of a dof / body among those owned by the same warp, column bases (32-bit units)
-    int dof_slot[MAXV], body_slot[MAXB];
-    int tm_dinv, tm_u, tm_tau, tm_c, tm_cin, tm_fb, tm_cols;
-    double w_p, w_v, w_e, w_rp, w_rv, k_p, k_v, k_e, k_rh, k_rq, k_rl, k_ra;
-};
-
-__constant__ DevModel c_m;
 
 }  // namespace egp
 
@@ -86,31 +62,10 @@ static int bind_model(const EgpModel *m) {
 
 // ------------------------------------------------------------------------------------------------
 // small device math
-__device__ __forceinline__ void cross3(const double *a, const double *b, double *o) {
-    double x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
-    o[0] = x; o[1] = y; o[2] = z;
-}
-__device__ __forceinline__ double dot3(const double *a, const double *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
-__device__ __forceinline__ double dot6(const double *a, const double *b) {
-    return a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3] + a[4] * b[4] + a[5] * b[5];
-}
 // quaternion helpers (w, x, y, z), utils/transformation.py:1379-1421 conventions
-__device__ __forceinline__ void quat_mul(const double *q1, const double *q0, double *o) {
-    double w0 = q0[0], x0 = q0[1], y0 = q0[2], z0 = q0[3], w1 = q1[0], x1 = q1[1], y1 = q1[2], z1 = q1[3];
-    o[0] = -x1 * x0 - y1 * y0 - z1 * z0 + w1 * w0;
-    o[1] = x1 * w0 + y1 * z0 - z1 * y0 + w1 * x0;
-    o[2] = -x1 * z0 + y1 * w0 + z1 * x0 + w1 * y0;
-    o[3] = x1 * y0 - y1 * x0 + z1 * w0 + w1 * z0;
-}
 __device__ __forceinline__ void quat_inv(const double *q, double *o) {
     double n = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
     o[0] = q[0] / n; o[1] = -q[1] / n; o[2] = -q[2] / n; o[3] = -q[3] / n;
-}
-__device__ __forceinline__ void quat_to_mat(const double *q, double *R) {      // unit quaternion
-    double w = q[0], x = q[1], y = q[2], z = q[3];
-    R[0] = w * w + x * x - y * y - z * z; R[1] = 2 * (x * y - w * z);           R[2] = 2 * (x * z + w * y);
-    R[3] = 2 * (x * y + w * z);           R[4] = w * w - x * x + y * y - z * z; R[5] = 2 * (y * z - w * x);
-    R[6] = 2 * (x * z - w * y);           R[7] = 2 * (y * z + w * x);           R[8] = w * w - x * x - y * y + z * z;
 }
 // utils/math.py:62-67,80-81: heading quaternion (w,0,0,z)/|.| and de_heading
 __device__ __forceinline__ void heading_cs(const double *q, double *hw, double *hz) {
@@ -162,31 +117,7 @@ __device__ __forceinline__ void quat_from_euler(double ai, double aj, double ak,
     q[0] = cj * cc + sj * ss; q[1] = cj * sc - sj * cs; q[2] = cj * ss + sj * cc; q[3] = cj * cs - sj * sc;
 }
 
-// symmetric 6x6 in packed upper storage
-__device__ __forceinline__ constexpr int sx(int r, int c) { return r <= c ? r * 6 - r * (r - 1) / 2 + (c - r) : c * 6 - c * (c - 1) / 2 + (r - c); }
-
-// spatial inertia (m, h = m c, I_O) applied to a motion vector [w; v]
-__device__ __forceinline__ void spi_mul(const double *ci /*10*/, const double *x, double *f) {
-    const double m = ci[0], *hh = ci + 1, *I = ci + 4;
-    double hxl[3], hxw[3];
-    cross3(hh, x + 3, hxl);
-    cross3(hh, x, hxw);
-    f[0] = I[0] * x[0] + I[3] * x[1] + I[4] * x[2] + hxl[0];
-    f[1] = I[3] * x[0] + I[1] * x[1] + I[5] * x[2] + hxl[1];
-    f[2] = I[4] * x[0] + I[5] * x[1] + I[2] * x[2] + hxl[2];
-    f[3] = m * x[3] - hxw[0];
-    f[4] = m * x[4] - hxw[1];
-    f[5] = m * x[5] - hxw[2];
-}
-
-// ------------------------------------------------------------------------------------------------
 // per-environment scratch (thread-local)
-struct Fwd {            // forward carry along a chain: body frame (relative to O), spatial velocity, bias accel
-    double p[3], R[9], v[6], a[6];
-};
-struct Bwd {            // backward carry: articulated inertia, bias force of the pure solve, RNE force
-    double IA[21], pA[6], F[6];
-};
 
 struct EnvData {
     double q[MAXV + 1], v[MAXV];
@@ -689,7 +620,7 @@ rollout_kernel(const RolloutArgs A) {
             take = A.in.d_reset_take[(size_t)eid * A.cfg.max_resets + rr];
             start = A.in.d_reset_start[(size_t)eid * A.cfg.max_resets + rr];
         } else {
-            uint32_t c[4] = {(uint32_t)eid, (uint32_t)r, (uint32_t)A.cfg.iteration, 0x52535421u};
+            uint32_t c[4] = {(uint32_t)eid, (uint32_t)r, (uint32_t)A.cfg.iteration, 0x52535421u ^ (uint32_t)(A.cfg.iteration >> 32)};
             philox4x32(c, (uint32_t)A.cfg.seed, (uint32_t)(A.cfg.seed >> 32));
             take = (int)(c[0] % (uint32_t)A.n_takes);                              // humanoid_v1.py:210
             int len = A.take_off[take + 1] - A.take_off[take];
@@ -723,7 +654,7 @@ rollout_kernel(const RolloutArgs A) {
         bool mean_flag = A.cfg.mean_action != 0;
         if (A.in.d_mean_flag) mean_flag = mean_flag || A.in.d_mean_flag[n] != 0;
         else if (A.cfg.noise_rate < 1.0) {
-            uint32_t c[4] = {(uint32_t)eid, (uint32_t)t, (uint32_t)A.cfg.iteration, 0x4d45414eu};
+            uint32_t c[4] = {(uint32_t)eid, (uint32_t)t, (uint32_t)A.cfg.iteration, 0x4d45414eu ^ (uint32_t)(A.cfg.iteration >> 32)};
             philox4x32(c, (uint32_t)A.cfg.seed, (uint32_t)(A.cfg.seed >> 32));
             mean_flag = mean_flag || (u01(c[0], c[1]) <= 1.0 - A.cfg.noise_rate);   // binomial(1, 1 - noise_rate)
         }
@@ -841,13 +772,10 @@ rollout_kernel(const RolloutArgs A) {
 // pass is 28 of the 58 DoFs, and the policy MLP is split 4 ways.  Hot per-DoF data (joint axes, body anchors,
 // U = I^A S, q, v) live in shared memory [row][env] (bank-conflict free); junction records pass between warps
 // through shared memory; everything else is owner-private thread-local.
-constexpr int T4_WARPS = 4;
+constexpr int T4_WARPS = 8;                  // warps per CTA: 4 chain warps (tree sweeps) + 4 helper warps (policy MLP, obs, reward)
 constexpr int T4_THREADS = T4_WARPS * 32;
 
-struct T4Off { int q, v, ax, anc, U, jf, jb, ja, xp, red, total; };
-
 struct T4Local {
-    double ctrl[MAXV], x[MAXV];
     double sav_ax[MAXV][3], sav_anc[MAXB][3];
     double bqp[MAXB][4], bqc[MAXB][4];
 };
@@ -905,15 +833,26 @@ __device__ __forceinline__ void tm_ld8(uint32_t a, double *v) {
     for (int k = 0; k < 8; k++) v[k] = __hiloint2double(r[2 * k + 1], r[2 * k]);
 }
 
+// loads without the wait: issue several, then ONE tm_wait_ld over all destination registers (the operands make the
+// dependency visible to the compiler)
+__device__ __forceinline__ void tm_ld4_nowait(uint32_t a, int (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(a) : "memory");
+}
+__device__ __forceinline__ void tm_wait_ld8(int (&r)[8]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]) :: "memory");
+}
+
+// storage context of the tree sweeps (csrc/tree.cuh) on the device: shared rows [row][env] + Tensor Memory scratch
+extern __shared__ double t4_smem[];          // the CTA's dynamic shared memory (named here so that non-inlined sweeps
+                                             // address it as shared memory, not through a generic pointer)
 struct T4Ctx {
-    double *sm;
     int lane, w;
     uint32_t tm;        // TMEM base of this warp's lane quarter
     T4Off o;
-    __device__ __forceinline__ double &at(int off, int idx) const { return sm[(size_t)(off + idx) * 32 + lane]; }
+    __device__ __forceinline__ double &at(int off, int idx) const { return t4_smem[(off + idx) * 32 + lane]; }
     // TMEM column addresses
-    __device__ __forceinline__ uint32_t a_dinv(int i) const { return tm + c_m.tm_dinv + 2 * c_m.dof_slot[i]; }
-    __device__ __forceinline__ uint32_t a_u(int i) const { return tm + c_m.tm_u + 2 * c_m.dof_slot[i]; }
+    __device__ __forceinline__ uint32_t a_ctrl(int i) const { return tm + c_m.tm_ctrl + 2 * c_m.dof_slot[i]; }
     __device__ __forceinline__ uint32_t a_tau(int i) const { return tm + c_m.tm_tau + 2 * c_m.dof_slot[i]; }
     __device__ __forceinline__ uint32_t a_c(int i) const { return tm + c_m.tm_c + 2 * c_m.dof_slot[i]; }
     __device__ __forceinline__ uint32_t a_cin(int b) const { return tm + c_m.tm_cin + 20 * c_m.body_slot[b]; }
@@ -922,334 +861,41 @@ struct T4Ctx {
     __device__ __forceinline__ void ld_cin(int b, double *ci) const { tm_ld8(a_cin(b), ci); tm_ld2(a_cin(b) + 16, ci[8], ci[9]); }
     __device__ __forceinline__ void st_fb(int b, const double *f) const { tm_st4(a_fb(b), f); tm_st2(a_fb(b) + 8, f[4], f[5]); }
     __device__ __forceinline__ void ld_fb(int b, double *f) const { tm_ld4(a_fb(b), f); tm_ld2(a_fb(b) + 8, f[4], f[5]); }
+    // N consecutive per-dof values (N = 1 or 3) at column `col` of this thread's scratch; a 3-wide load is issued as one
+    // 4-wide access (the extra double is the next slot / array, always inside the allocation)
+    template <int N> __device__ __forceinline__ void tld(int col, double *v) const {
+        if (N == 1) v[0] = tm_ld1(tm + col);
+        else { double t[4]; tm_ld4(tm + col, t); v[0] = t[0]; v[1] = t[1]; v[2] = t[2]; }
+    }
+    template <int N> __device__ __forceinline__ void tst(int col, const double *v) const {
+        if (N == 1) tm_st1(tm + col, v[0]);
+        else { tm_st2(tm + col, v[0], v[1]); tm_st1(tm + col + 4, v[2]); }
+    }
+    __device__ __forceinline__ void twait_st() const { tm_wait_st(); }
 };
 
-__device__ __forceinline__ int t4_my_chain(int level, int w) {
-    for (int c = 0; c < c_m.nchain; c++)
-        if (c_m.chain_level[c] == level && c_m.chain_warp[c] == w) return c;
-    return -1;
-}
+// barrier of the four chain warps (the helper warps never enter the sweeps)
+__device__ __forceinline__ void t4_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-// spatial motion axis of dof i from the shared rows: hinge [ax; anc x ax], free translation [0; ax]
-__device__ __forceinline__ void t4_load_S(const T4Ctx &x, int i, int b, double *S) {
-    double ax[3] = {x.at(x.o.ax, 3 * i), x.at(x.o.ax, 3 * i + 1), x.at(x.o.ax, 3 * i + 2)};
-    if (c_m.body_dofnum[b] == 6 && i - c_m.body_dofadr[b] < 3) {
-        S[0] = S[1] = S[2] = 0.0; S[3] = ax[0]; S[4] = ax[1]; S[5] = ax[2];
-    } else {
-        double an[3] = {x.at(x.o.anc, 3 * b), x.at(x.o.anc, 3 * b + 1), x.at(x.o.anc, 3 * b + 2)};
-        S[0] = ax[0]; S[1] = ax[1]; S[2] = ax[2];
-        cross3(an, ax, S + 3);
-    }
-}
-
-// Forward tree sweep, level-synchronous.
-//   MODE 1: [PD accel + torque] on the OLD tree rows of each dof, then [kinematics refresh] of that dof/body
-//           (two independent dependency chains interleaved in one sweep; the stale-data ordering of the reference
-//           is preserved because every old row is read before it is overwritten)
-//   MODE 0: forward-dynamics accel sweep + semi-implicit Euler integration of the owned dofs
-//   MODE 2: kinematics refresh only (sim.forward() at reset)
+// level-synchronous tree sweeps (root | spine, legs | arms, head): one chain per warp and level, junction records
+// cross warps through shared memory (csrc/tree.cuh holds the per-chain work)
 template <int MODE>
-__device__ void t4_forward(const T4Ctx &x, T4Local &l) {
-    const double h = c_m.h;
+__device__ __noinline__ void t4_forward(const T4Ctx x) {
     for (int L = 0; L < c_m.nlevel; L++) {
-        const int c = t4_my_chain(L, x.w);
-        if (c >= 0) {
-            Fwd f;
-            double a[6];
-            const int pc = c_m.chain_parent[c];
-            if (MODE != 2) {
-#pragma unroll
-                for (int k = 0; k < 6; k++) a[k] = pc >= 0 ? x.at(x.o.ja + 6 * c_m.chain_pslot[pc], k) : 0.0;
-            }
-            if (MODE != 0 && pc >= 0) {
-                const int base = x.o.jf + 24 * c_m.chain_pslot[pc];
-#pragma unroll
-                for (int k = 0; k < 3; k++) f.p[k] = x.at(base, k);
-#pragma unroll
-                for (int k = 0; k < 9; k++) f.R[k] = x.at(base, 3 + k);
-#pragma unroll
-                for (int k = 0; k < 6; k++) { f.v[k] = x.at(base, 12 + k); f.a[k] = x.at(base, 18 + k); }
-            }
-            for (int b = c_m.chain_lo[c]; b <= c_m.chain_hi[c]; b++) {
-                const int da = c_m.body_dofadr[b], nd = c_m.body_dofnum[b], qa = c_m.body_qposadr[b];
-                // ---- solve part for the dofs of this body (old rows)
-                auto solve_dof = [&](int i, const double *S) {
-                    double U[6];
-#pragma unroll
-                    for (int r = 0; r < 6; r++) U[r] = x.at(x.o.U, 6 * i + r);
-                    const double xi = tm_ld1(x.a_dinv(i)) * (tm_ld1(x.a_u(i)) - dot6(U, a));
-#pragma unroll
-                    for (int r = 0; r < 6; r++) a[r] += S[r] * xi;
-                    if (MODE == 1) {            // torque = clip(-kp e - kd (v + x h))  (humanoid_v1.py:152-155,172)
-                        double t = 0.0;
-                        if (i >= 6) {
-                            const double eq = x.at(x.o.q, i + 1) - l.ctrl[i];
-                            t = -c_m.kp[i] * eq - c_m.kd[i] * (x.at(x.o.v, i) + xi * h);
-                            const double lim = c_m.tlim[i];
-                            t = t < -lim ? -lim : (t > lim ? lim : t);
-                        }
-                        tm_st1(x.a_tau(i), t);
-                    } else {                    // semi-implicit Euler for hinges; the root is finished below
-                        const double vn = x.at(x.o.v, i) + h * xi;
-                        x.at(x.o.v, i) = vn;
-                        if (i >= 6) x.at(x.o.q, i + 1) += h * vn;
-                    }
-                };
-                if (nd == 6) {
-                    if (MODE != 2) {
-                        for (int i = da; i < da + 6; i++) { double S[6]; t4_load_S(x, i, b, S); solve_dof(i, S); }
-                        if (MODE == 0) {        // root position + quaternion integration with the NEW velocity
-                            for (int k = 0; k < 3; k++) x.at(x.o.q, qa + k) += h * x.at(x.o.v, da + k);
-                            double wv[3] = {x.at(x.o.v, da + 3), x.at(x.o.v, da + 4), x.at(x.o.v, da + 5)};
-                            double n = sqrt(dot3(wv, wv)), ax[3] = {1.0, 0.0, 0.0};
-                            if (n > 1e-15) { ax[0] = wv[0] / n; ax[1] = wv[1] / n; ax[2] = wv[2] / n; }
-                            double sn, cs;
-                            sincos(0.5 * h * n, &sn, &cs);
-                            double qr[4] = {cs, ax[0] * sn, ax[1] * sn, ax[2] * sn};
-                            double q4[4] = {x.at(x.o.q, qa + 3), x.at(x.o.q, qa + 4), x.at(x.o.q, qa + 5), x.at(x.o.q, qa + 6)};
-                            double qn = sqrt(q4[0] * q4[0] + q4[1] * q4[1] + q4[2] * q4[2] + q4[3] * q4[3]);
-                            for (int k = 0; k < 4; k++) q4[k] /= qn;
-                            double o4[4];
-                            quat_mul(q4, qr, o4);
-                            for (int k = 0; k < 4; k++) x.at(x.o.q, qa + 3 + k) = o4[k];
-                        }
-                    }
-                    if (MODE != 0) {
-                        double q4[4] = {x.at(x.o.q, qa + 3), x.at(x.o.q, qa + 4), x.at(x.o.q, qa + 5), x.at(x.o.q, qa + 6)};
-                        double n = sqrt(q4[0] * q4[0] + q4[1] * q4[1] + q4[2] * q4[2] + q4[3] * q4[3]);
-                        for (int k = 0; k < 4; k++) q4[k] /= n;
-                        quat_to_mat(q4, f.R);
-                        f.p[0] = f.p[1] = f.p[2] = 0.0;
-                        double wl[3] = {x.at(x.o.v, da + 3), x.at(x.o.v, da + 4), x.at(x.o.v, da + 5)}, ww[3];
-                        for (int r = 0; r < 3; r++) ww[r] = f.R[3 * r] * wl[0] + f.R[3 * r + 1] * wl[1] + f.R[3 * r + 2] * wl[2];
-                        for (int k = 0; k < 3; k++) {
-                            for (int r = 0; r < 3; r++) {
-                                x.at(x.o.ax, 3 * (da + k) + r) = r == k ? 1.0 : 0.0;
-                                x.at(x.o.ax, 3 * (da + 3 + k) + r) = f.R[3 * r + k];
-                            }
-                            x.at(x.o.anc, 3 * b + k) = 0.0;
-                        }
-                        double vl[3] = {x.at(x.o.v, da), x.at(x.o.v, da + 1), x.at(x.o.v, da + 2)}, vxw[3];
-                        cross3(vl, ww, vxw);
-                        for (int k = 0; k < 3; k++) {
-                            f.v[k] = ww[k]; f.v[3 + k] = vl[k];
-                            f.a[k] = 0.0; f.a[3 + k] = -c_m.grav[k] + vxw[k];
-                        }
-                    }
-                } else {
-                    double anc_old[3], anc[3];
-                    if (MODE != 2) for (int r = 0; r < 3; r++) anc_old[r] = x.at(x.o.anc, 3 * b + r);
-                    if (MODE != 0) {
-                        double off[3];
-                        for (int r = 0; r < 3; r++)
-                            off[r] = f.R[3 * r] * c_m.body_pos[b][0] + f.R[3 * r + 1] * c_m.body_pos[b][1] + f.R[3 * r + 2] * c_m.body_pos[b][2];
-                        for (int r = 0; r < 3; r++) f.p[r] += off[r];
-                        for (int r = 0; r < 3; r++) {
-                            anc[r] = f.p[r] + f.R[3 * r] * c_m.dof_anchor[da][0] + f.R[3 * r + 1] * c_m.dof_anchor[da][1] +
-                                     f.R[3 * r + 2] * c_m.dof_anchor[da][2];
-                            x.at(x.o.anc, 3 * b + r) = anc[r];
-                        }
-                    }
-                    for (int j = 0; j < nd; j++) {
-                        const int i = da + j;
-                        if (MODE != 2) {
-                            double S[6];
-                            S[0] = x.at(x.o.ax, 3 * i); S[1] = x.at(x.o.ax, 3 * i + 1); S[2] = x.at(x.o.ax, 3 * i + 2);
-                            cross3(anc_old, S, S + 3);
-                            solve_dof(i, S);
-                        }
-                        if (MODE != 0) {
-                            double ax[3];
-                            const int aid = c_m.dof_axis_id[i];
-                            if (aid >= 0) { ax[0] = f.R[aid]; ax[1] = f.R[3 + aid]; ax[2] = f.R[6 + aid]; }
-                            else for (int r = 0; r < 3; r++)
-                                ax[r] = f.R[3 * r] * c_m.dof_axis[i][0] + f.R[3 * r + 1] * c_m.dof_axis[i][1] + f.R[3 * r + 2] * c_m.dof_axis[i][2];
-                            for (int r = 0; r < 3; r++) x.at(x.o.ax, 3 * i + r) = ax[r];
-                            double S[6];
-                            S[0] = ax[0]; S[1] = ax[1]; S[2] = ax[2];
-                            cross3(anc, ax, S + 3);
-                            const double qd = x.at(x.o.v, i);
-                            double t0[3], t1[3], t2[3];
-                            cross3(f.v, S, t0);
-                            cross3(f.v, S + 3, t1);
-                            cross3(f.v + 3, S, t2);
-                            for (int r = 0; r < 3; r++) {
-                                f.a[r] += t0[r] * qd;
-                                f.a[3 + r] += (t1[r] + t2[r]) * qd;
-                            }
-                            for (int r = 0; r < 6; r++) f.v[r] += S[r] * qd;
-                            double sn, cs;
-                            sincos(x.at(x.o.q, qa + j), &sn, &cs);
-                            if (aid >= 0) {
-                                const int c1 = (aid + 1) % 3, c2 = (aid + 2) % 3;
-                                for (int r = 0; r < 3; r++) {
-                                    double a1 = f.R[3 * r + c1], a2 = f.R[3 * r + c2];
-                                    f.R[3 * r + c1] = cs * a1 + sn * a2;
-                                    f.R[3 * r + c2] = -sn * a1 + cs * a2;
-                                }
-                            } else {
-                                const double *av = c_m.dof_axis[i];
-                                double K[9] = {0, -av[2], av[1], av[2], 0, -av[0], -av[1], av[0], 0}, Rot[9], Rn[9];
-                                for (int r = 0; r < 3; r++) for (int cc = 0; cc < 3; cc++)
-                                    Rot[3 * r + cc] = (r == cc ? cs : 0.0) + sn * K[3 * r + cc] + (1.0 - cs) * av[r] * av[cc];
-                                for (int r = 0; r < 3; r++) for (int cc = 0; cc < 3; cc++)
-                                    Rn[3 * r + cc] = f.R[3 * r] * Rot[cc] + f.R[3 * r + 1] * Rot[3 + cc] + f.R[3 * r + 2] * Rot[6 + cc];
-                                for (int r = 0; r < 9; r++) f.R[r] = Rn[r];
-                            }
-                        }
-                    }
-                    if (MODE != 0)
-                        for (int r = 0; r < 3; r++)
-                            f.p[r] = anc[r] - (f.R[3 * r] * c_m.dof_anchor[da][0] + f.R[3 * r + 1] * c_m.dof_anchor[da][1] +
-                                               f.R[3 * r + 2] * c_m.dof_anchor[da][2]);
-                }
-                if (MODE != 0) {
-                    const int xs = c_m.body_xp_slot[b];
-                    if (xs >= 0) for (int r = 0; r < 3; r++) x.at(x.o.xp, 3 * xs + r) = f.p[r] + x.at(x.o.q, r);
-                    double cpos[3];
-                    for (int r = 0; r < 3; r++)
-                        cpos[r] = f.p[r] + f.R[3 * r] * c_m.body_ipos[b][0] + f.R[3 * r + 1] * c_m.body_ipos[b][1] + f.R[3 * r + 2] * c_m.body_ipos[b][2];
-                    const double *in = c_m.body_inertia[b];
-                    double Ib[9] = {in[0], in[3], in[4], in[3], in[1], in[5], in[4], in[5], in[2]}, Tm[9], Iw[6];
-                    for (int r = 0; r < 3; r++) for (int cc = 0; cc < 3; cc++)
-                        Tm[3 * r + cc] = f.R[3 * r] * Ib[cc] + f.R[3 * r + 1] * Ib[3 + cc] + f.R[3 * r + 2] * Ib[6 + cc];
-                    Iw[0] = Tm[0] * f.R[0] + Tm[1] * f.R[1] + Tm[2] * f.R[2];
-                    Iw[1] = Tm[3] * f.R[3] + Tm[4] * f.R[4] + Tm[5] * f.R[5];
-                    Iw[2] = Tm[6] * f.R[6] + Tm[7] * f.R[7] + Tm[8] * f.R[8];
-                    Iw[3] = Tm[0] * f.R[3] + Tm[1] * f.R[4] + Tm[2] * f.R[5];
-                    Iw[4] = Tm[0] * f.R[6] + Tm[1] * f.R[7] + Tm[2] * f.R[8];
-                    Iw[5] = Tm[3] * f.R[6] + Tm[4] * f.R[7] + Tm[5] * f.R[8];
-                    const double mass = c_m.body_mass[b], cc2 = dot3(cpos, cpos);
-                    double ci[10];
-                    ci[0] = mass;
-                    ci[1] = mass * cpos[0]; ci[2] = mass * cpos[1]; ci[3] = mass * cpos[2];
-                    ci[4] = Iw[0] + mass * (cc2 - cpos[0] * cpos[0]);
-                    ci[5] = Iw[1] + mass * (cc2 - cpos[1] * cpos[1]);
-                    ci[6] = Iw[2] + mass * (cc2 - cpos[2] * cpos[2]);
-                    ci[7] = Iw[3] - mass * cpos[0] * cpos[1];
-                    ci[8] = Iw[4] - mass * cpos[0] * cpos[2];
-                    ci[9] = Iw[5] - mass * cpos[1] * cpos[2];
-                    double Ia[6], Iv[6];
-                    spi_mul(ci, f.a, Ia);
-                    spi_mul(ci, f.v, Iv);
-                    double c0[3], c1[3], c2[3];
-                    cross3(f.v, Iv, c0);
-                    cross3(f.v + 3, Iv + 3, c1);
-                    cross3(f.v, Iv + 3, c2);
-                    double fbv[6];
-                    for (int r = 0; r < 3; r++) {
-                        fbv[r] = Ia[r] + c0[r] + c1[r];
-                        fbv[3 + r] = Ia[3 + r] + c2[r];
-                    }
-                    x.st_cin(b, ci);
-                    x.st_fb(b, fbv);
-                }
-            }
-            tm_wait_st();
-            if (c_m.chain_pslot[c] >= 0) {
-                if (MODE != 2) {
-#pragma unroll
-                    for (int k = 0; k < 6; k++) x.at(x.o.ja + 6 * c_m.chain_pslot[c], k) = a[k];
-                }
-                if (MODE != 0) {
-                    const int base = x.o.jf + 24 * c_m.chain_pslot[c];
-#pragma unroll
-                    for (int k = 0; k < 3; k++) x.at(base, k) = f.p[k];
-#pragma unroll
-                    for (int k = 0; k < 9; k++) x.at(base, 3 + k) = f.R[k];
-#pragma unroll
-                    for (int k = 0; k < 6; k++) { x.at(base, 12 + k) = f.v[k]; x.at(base, 18 + k) = f.a[k]; }
-                }
-            }
-        }
-        __syncthreads();
+        const int c = c_m.lvl_chain[L][x.w];
+        if (c >= 0) t5_fwd_chain<MODE>(x, c);
+        t4_bar();
     }
 }
 
-// Backward articulated-body sweep.  MODE 0: forward dynamics, bias C_i = S_i . F stored, rhs = tau_i - C_i, pivots
-// S.U + armature.  MODE 1: stable PD (humanoid_v1.py:130-144): rhs_i = -C_i - kp e_i - kd v_i evaluated on the
-// fly from the shared q / v rows and the stored bias, pivots + kd h.
-template <int MODE>
-__device__ void t4_backward(const T4Ctx &x, T4Local &l) {
+__device__ __noinline__ void t4_backward(const T4Ctx x, const int MODE) {
     for (int L = c_m.nlevel - 1; L >= 0; L--) {
-        const int c = t4_my_chain(L, x.w);
+        const int c = c_m.lvl_chain[L][x.w];
         Bwd w;
-#pragma unroll
-        for (int k = 0; k < 21; k++) w.IA[k] = 0.0;
-#pragma unroll
-        for (int k = 0; k < 6; k++) { w.pA[k] = 0.0; w.F[k] = 0.0; }
-        if (c >= 0) {
-            for (int s = 0; s < c_m.chain_nchild[c]; s++) {
-                const int base = x.o.jb + 33 * s;
-#pragma unroll
-                for (int k = 0; k < 21; k++) w.IA[k] += x.at(base, k);
-#pragma unroll
-                for (int k = 0; k < 6; k++) { w.pA[k] += x.at(base, 21 + k); w.F[k] += x.at(base, 27 + k); }
-            }
-        }
-        __syncthreads();            // children records consumed before this level overwrites the slots
-        if (c >= 0) {
-            for (int b = c_m.chain_hi[c]; b >= c_m.chain_lo[c]; b--) {
-                double ci[10];
-                x.ld_cin(b, ci);
-                w.IA[sx(0, 0)] += ci[4]; w.IA[sx(1, 1)] += ci[5]; w.IA[sx(2, 2)] += ci[6];
-                w.IA[sx(0, 1)] += ci[7]; w.IA[sx(0, 2)] += ci[8]; w.IA[sx(1, 2)] += ci[9];
-                w.IA[sx(0, 4)] += -ci[3]; w.IA[sx(0, 5)] += ci[2];
-                w.IA[sx(1, 3)] += ci[3];  w.IA[sx(1, 5)] += -ci[1];
-                w.IA[sx(2, 3)] += -ci[2]; w.IA[sx(2, 4)] += ci[1];
-                w.IA[sx(3, 3)] += ci[0]; w.IA[sx(4, 4)] += ci[0]; w.IA[sx(5, 5)] += ci[0];
-                if (MODE == 0) {
-                    double fbv[6];
-                    x.ld_fb(b, fbv);
-                    for (int k = 0; k < 6; k++) w.F[k] += fbv[k];
-                }
-                const int da = c_m.body_dofadr[b], nd = c_m.body_dofnum[b];
-                for (int i = da + nd - 1; i >= da; i--) {
-                    double S[6], U[6];
-                    t4_load_S(x, i, b, S);
-                    double rhs;
-                    if (MODE == 0) {
-                        const double Ci = dot6(S, w.F);
-                        tm_st1(x.a_c(i), Ci);
-                        rhs = tm_ld1(x.a_tau(i)) - Ci;
-                    } else {
-                        const double eq = i >= 6 ? x.at(x.o.q, i + 1) - l.ctrl[i] : 0.0;
-                        rhs = -tm_ld1(x.a_c(i)) - c_m.kp[i] * eq - c_m.kd[i] * x.at(x.o.v, i);
-                    }
-#pragma unroll
-                    for (int r = 0; r < 6; r++) {
-                        double t = 0.0;
-#pragma unroll
-                        for (int cc = 0; cc < 6; cc++) t += w.IA[sx(r, cc)] * S[cc];
-                        U[r] = t;
-                    }
-                    double D = dot6(S, U) + c_m.dof_arm[i];
-                    if (MODE == 1) D += c_m.kd[i] * c_m.h;
-                    const double Dinv = 1.0 / D;
-                    const double ui = rhs - dot6(S, w.pA);
-                    tm_st1(x.a_dinv(i), Dinv);
-                    tm_st1(x.a_u(i), ui);
-#pragma unroll
-                    for (int r = 0; r < 6; r++) x.at(x.o.U, 6 * i + r) = U[r];
-#pragma unroll
-                    for (int r = 0; r < 6; r++) {
-                        const double ur = U[r] * Dinv;
-#pragma unroll
-                        for (int cc = r; cc < 6; cc++) w.IA[sx(r, cc)] -= ur * U[cc];
-                        w.pA[r] += ur * ui;
-                    }
-                }
-            }
-            tm_wait_st();
-            if (c_m.chain_parent[c] >= 0) {
-                const int base = x.o.jb + 33 * c_m.chain_cslot[c];
-#pragma unroll
-                for (int k = 0; k < 21; k++) x.at(base, k) = w.IA[k];
-#pragma unroll
-                for (int k = 0; k < 6; k++) { x.at(base, 21 + k) = w.pA[k]; x.at(base, 27 + k) = w.F[k]; }
-            }
-        }
-        __syncthreads();
+        t5_bwd_gather(x, c, w);
+        t4_bar();                   // children records consumed before this level overwrites the slots
+        if (c >= 0) t5_bwd_chain(x, c, w, MODE);
+        t4_bar();
     }
 }
 
@@ -1260,19 +906,19 @@ __device__ void t4_backward(const T4Ctx &x, T4Local &l) {
             for (int b = c_m.chain_lo[_c]; b <= c_m.chain_hi[_c]; b++)                               \
                 for (int i = c_m.body_dofadr[b]; i < c_m.body_dofadr[b] + c_m.body_dofnum[b]; i++)
 
-__device__ void t4_forward_only(const T4Ctx &x, T4Local &l) {      // sim.forward()
-    t4_forward<2>(x, l);
+__device__ void t4_forward_only(const T4Ctx &x) {      // sim.forward(); chain warps only
+    t4_forward<2>(x);
     T4_FOR_OWN_DOFS(i, b) tm_st1(x.a_tau(i), 0.0);
     tm_wait_st();
-    t4_backward<0>(x, l);
+    t4_backward(x, 0);
 }
 
 // One iteration of do_simulation (humanoid_v1.py:166-174): stable-PD torque on the stale tree data, then mj_step.
-__device__ void t4_substep(const T4Ctx &x, T4Local &l) {
-    t4_backward<1>(x, l);       // (M_stale + Kd h) factor + reduce, rhs from the current q, v
-    t4_forward<1>(x, l);        // desired accel -> clipped torque ; kinematics / velocities / body forces at (q, v)
-    t4_backward<0>(x, l);       // bias C, M factor + reduce with rhs = torque - C
-    t4_forward<0>(x, l);        // qacc, semi-implicit Euler
+__device__ void t4_substep(const T4Ctx &x) {
+    t4_backward(x, 1);          // (M_stale + Kd h) factor + reduce, rhs from the current q, v
+    t4_forward<1>(x);           // desired accel -> clipped torque ; kinematics / velocities / body forces at (q, v)
+    t4_backward(x, 0);          // bias C, M factor + reduce with rhs = torque - C
+    t4_forward<0>(x);           // qacc, semi-implicit Euler
 }
 
 // observation entry k (humanoid_v1.py:73-96) from the shared q / v rows; hd* = de-headed root quaternion,
@@ -1396,30 +1042,22 @@ __device__ __forceinline__ void t4_policy_forward(const RolloutArgs &A, double *
         __syncthreads();
         return;
     }
-    double acc3[2][JB];
-    const int nob = A.Ap / JB;                              // head output blocks; warp w owns w and w + 4
+    double acc3[JB];
+    const int nob = A.Ap / JB;                              // head output blocks (<= T4_WARPS, checked on the host): warp w owns block w
 #pragma unroll
-    for (int o = 0; o < 2; o++)
-#pragma unroll
-        for (int jj = 0; jj < JB; jj++) acc3[o][jj] = (w + 4 * o < nob) ? A.b3[(w + 4 * o) * JB + jj] : 0.0;
+    for (int jj = 0; jj < JB; jj++) acc3[jj] = w < nob ? A.b3[w * JB + jj] : 0.0;
     for (int c2 = 0; c2 < A.H2p; c2 += MLP_C2) {
         const int hi = c2 + MLP_C2 < A.H2p ? c2 + MLP_C2 : A.H2p;
         t4_mlp_layer<true, KC>(A.W2t, A.b2, A.H1, A.K2p, c2 / JB, hi / JB, 0, h1s, xs, stage, lane, w);
         __syncthreads();
         const int khi = hi < A.H2 ? hi : A.H2;              // real neurons of this chunk
-        if (khi > c2) {
-#pragma unroll
-            for (int o = 0; o < 2; o++)
-                if (w + 4 * o < nob)
-                    t4_mlp_partial<KC>(A.W3t, khi, A.K3p, w + 4 * o, c2 / KC, (khi + KC - 1) / KC, c2, xs, acc3[o], stage, lane);
-        }
+        if (khi > c2 && w < nob)
+            t4_mlp_partial<KC>(A.W3t, khi, A.K3p, w, c2 / KC, (khi + KC - 1) / KC, c2, xs, acc3, stage, lane);
         __syncthreads();
     }
+    if (w < nob)
 #pragma unroll
-    for (int o = 0; o < 2; o++)
-        if (w + 4 * o < nob)
-#pragma unroll
-            for (int jj = 0; jj < JB; jj++) h1s[((w + 4 * o) * JB + jj) * 32 + lane] = acc3[o][jj];
+        for (int jj = 0; jj < JB; jj++) h1s[(w * JB + jj) * 32 + lane] = acc3[jj];
     __syncthreads();
 }
 
@@ -1428,7 +1066,7 @@ __global__ void __launch_bounds__(T4_THREADS, 1)
 rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
     extern __shared__ double smem[];
     T4Ctx x;
-    x.sm = smem; x.lane = threadIdx.x & 31; x.w = threadIdx.x >> 5; x.o = O;
+    x.lane = threadIdx.x & 31; x.w = threadIdx.x >> 5; x.o = O;
     const int lane = x.lane, w = x.w;
     // allocate the whole Tensor Memory of this SM (1 CTA per SM) as scratch; base address comes back via smem
     __shared__ uint32_t s_tmem_base;
@@ -1440,7 +1078,8 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = s_tmem_base;
-    x.tm = tmem_base + ((uint32_t)(w * 32) << 16);
+    x.tm = tmem_base + ((uint32_t)((w & 3) * 32) << 16);     // warps w and w + 4 share a lane quarter
+    const bool cw = w < T4_CW;                             // chain warp: owns tree sweeps (helper warps: MLP / obs / reward only)
     const int S = c_m.nq - 2 + c_m.nv, nu = c_m.nu, nv = c_m.nv, nb = c_m.nbody, nq = c_m.nq;
     double *xs = smem + (size_t)O.ax * 32;               // MLP activations alias the axis / anchor / U rows
     const int h2rows = CHUNK ? MLP_C2 : A.H2p;
@@ -1479,7 +1118,7 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
             take = A.in.d_reset_take[(size_t)eid * A.cfg.max_resets + rr];
             start = A.in.d_reset_start[(size_t)eid * A.cfg.max_resets + rr];
         } else {
-            uint32_t c[4] = {(uint32_t)eid, (uint32_t)r, (uint32_t)A.cfg.iteration, 0x52535421u};
+            uint32_t c[4] = {(uint32_t)eid, (uint32_t)r, (uint32_t)A.cfg.iteration, 0x52535421u ^ (uint32_t)(A.cfg.iteration >> 32)};
             philox4x32(c, (uint32_t)A.cfg.seed, (uint32_t)(A.cfg.seed >> 32));
             take = (int)(c[0] % (uint32_t)A.n_takes);
             int len = A.take_off[take + 1] - A.take_off[take];
@@ -1496,7 +1135,7 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
         }
         if (c_m.chain_warp[0] == w) for (int k = 0; k < 7; k++) x.at(O.q, k) = row[EGP_X_QPOS + k];
         __syncthreads();
-        t4_forward_only(x, l);
+        if (cw) t4_forward_only(x);
         for (int b = 1 + w; b < nb; b += T4_WARPS) {        // body quaternions of this thread's bodies
             const int qa = c_m.body_qposadr[b], nd = c_m.body_dofnum[b];
             quat_from_euler(x.at(O.q, qa), nd > 1 ? x.at(O.q, qa + 1) : 0.0, nd > 2 ? x.at(O.q, qa + 2) : 0.0, l.bqc[b]);
@@ -1559,10 +1198,11 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
             load_state_pred();
         }
         __syncthreads();
-        t4_forward_only(x, l);
+        if (cw) t4_forward_only(x);
     }
     make_state(raw, st);
-    T4_FOR_OWN_DOFS(i, b) l.ctrl[i] = 0.0;
+    T4_FOR_OWN_DOFS(i, b) tm_st1(x.a_ctrl(i), 0.0);
+    tm_wait_st();
     // state-LSTM h | c rows of this CTA, [2H][32] (s_net.initialize() at pre_episode, rnn.py:22-26)
     double *sn_g = SNET ? A.sn_state + (size_t)blockIdx.x * 2 * A.sn_H * 32 : nullptr;
     if (sn_g) for (int j = w; j < 2 * A.sn_H; j += T4_WARPS) sn_g[j * 32 + lane] = 0.0;
@@ -1651,7 +1291,7 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
         bool mean_flag = A.cfg.mean_action != 0;
         if (A.in.d_mean_flag) mean_flag = mean_flag || A.in.d_mean_flag[n] != 0;
         else if (A.cfg.noise_rate < 1.0) {
-            uint32_t c[4] = {(uint32_t)eid, (uint32_t)t, (uint32_t)A.cfg.iteration, 0x4d45414eu};
+            uint32_t c[4] = {(uint32_t)eid, (uint32_t)t, (uint32_t)A.cfg.iteration, 0x4d45414eu ^ (uint32_t)(A.cfg.iteration >> 32)};
             philox4x32(c, (uint32_t)A.cfg.seed, (uint32_t)(A.cfg.seed >> 32));
             mean_flag = mean_flag || (u01(c[0], c[1]) <= 1.0 - A.cfg.noise_rate);
         }
@@ -1668,7 +1308,7 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
                 }
             }
             const double act = h1s[a * 32 + lane] + exp(A.log_std[a]) * z;
-            l.ctrl[i] = c_m.a_ref[i] + act * c_m.a_scale[i];
+            tm_st1(x.a_ctrl(i), c_m.a_ref[i] + act * c_m.a_scale[i]);
             if (live) A.out.d_actions[n * nu + a] = act;
         }
         __syncthreads();
@@ -1683,7 +1323,10 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
         for (int k = 0; k < 7; k++) prev_root[k] = x.at(O.q, k);
         for (int b = 1 + w; b < nb; b += T4_WARPS) for (int k = 0; k < 4; k++) l.bqp[b][k] = l.bqc[b][k];
         __syncthreads();
-        for (int s = 0; s < c_m.frame_skip; s++) t4_substep(x, l);
+        if (cw) {
+            tm_wait_st();
+            for (int s = 0; s < c_m.frame_skip; s++) t4_substep(x);
+        }
         __syncthreads();
         cur_t += 1;
         const double head_z = x.at(O.xp, 3 * c_m.head_xp_slot + 2);
@@ -1722,8 +1365,9 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
         double rew = 0.0, info5[5] = {0, 0, 0, 0, 0};
         if (w0) {
             // sums in body order b = 1.. so the result does not depend on the warp split: re-add per warp share
-            pose2 = x.at(O.red, 0) + x.at(O.red, 2) + x.at(O.red, 4) + x.at(O.red, 6);
-            vd = x.at(O.red, 1) + x.at(O.red, 3) + x.at(O.red, 5) + x.at(O.red, 7);
+            pose2 = 0.0; vd = 0.0;
+#pragma unroll
+            for (int k = 0; k < T4_WARPS; k++) { pose2 += x.at(O.red, 2 * k); vd += x.at(O.red, 2 * k + 1); }
             double q7[7];
             for (int k = 0; k < 7; k++) q7[k] = x.at(O.q, k);
             double lin[3], qi[4], qrel[4], axis[3], ang, rv[3], fdl[3], fda[3];
@@ -1772,7 +1416,12 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
         __syncthreads();
         x.at(O.red, w) = bad ? 1.0 : 0.0;
         __syncthreads();
-        bad = (x.at(O.red, 0) + x.at(O.red, 1) + x.at(O.red, 2) + x.at(O.red, 3)) > 0.0;
+        {
+            double nbad = 0.0;
+#pragma unroll
+            for (int k = 0; k < T4_WARPS; k++) nbad += x.at(O.red, k);
+            bad = nbad > 0.0;
+        }
         if (bad) {
             rew = 0.0; fail = true;
             for (int k = 0; k < 5; k++) info5[k] = 0.0;
@@ -1842,7 +1491,7 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
                 if (c_m.chain_warp[0] == w) for (int k = 0; k < 7; k++) x.at(O.q, k) = r0[EGP_X_QPOS + k];
             }
             __syncthreads();
-            t4_forward_only(x, l);
+            if (cw) t4_forward_only(x);
             // restore parked lanes (uniform TMEM traffic, per-lane select of the value)
             T4_FOR_OWN_DOFS(i, b) {
                 const double cur = tm_ld1(x.a_c(i));
@@ -2055,78 +1704,6 @@ __global__ void build_input_kernel(const double *__restrict__ states, const int3
     }
 }
 
-static void build_chains(DevModel &d) {
-    // a chain is a maximal run of consecutive bodies b, b+1, ... with parent(b+1) == b where b has one child
-    int nb = d.nbody, nchild[MAXB] = {0};
-    for (int b = 0; b < nb; b++) if (d.body_parent[b] >= 0) nchild[d.body_parent[b]]++;
-    int nc = 0;
-    for (int b = 0; b < nb; b++) {
-        bool cont = b > 0 && d.body_parent[b] == b - 1 && nchild[b - 1] == 1;
-        if (!cont) {
-            d.chain_lo[nc] = b;
-            d.chain_parent[nc] = d.body_parent[b] >= 0 ? d.body_chain[d.body_parent[b]] : -1;
-            nc++;
-        }
-        d.chain_hi[nc - 1] = b;
-        d.body_chain[b] = nc - 1;
-    }
-    d.nchain = nc;
-    // ---- T4 schedule
-    int cchild[MAXC] = {0}, per_level_parents[MAXC] = {0}, per_level_count[MAXC] = {0};
-    d.nlevel = 0; d.nparent = 0; d.max_sib = 0; d.t4_ok = 1;
-    for (int c = 0; c < nc; c++) {
-        d.chain_level[c] = d.chain_parent[c] >= 0 ? d.chain_level[d.chain_parent[c]] + 1 : 0;
-        if (d.chain_level[c] + 1 > d.nlevel) d.nlevel = d.chain_level[c] + 1;
-        d.chain_cslot[c] = d.chain_parent[c] >= 0 ? cchild[d.chain_parent[c]]++ : -1;
-    }
-    for (int c = 0; c < nc; c++) {
-        d.chain_nchild[c] = cchild[c];
-        d.chain_pslot[c] = cchild[c] > 0 ? d.nparent++ : -1;
-        if (cchild[c] > d.max_sib) d.max_sib = cchild[c];
-        if (cchild[c] > 0) per_level_parents[d.chain_level[c]]++;
-    }
-    // per level: longest chain to warp 0, next to warp 1, ... (one chain per warp per level)
-    for (int L = 0; L < d.nlevel; L++) {
-        int order[MAXC], n = 0;
-        for (int c = 0; c < nc; c++) if (d.chain_level[c] == L) order[n++] = c;
-        auto ndof = [&](int c) { return d.body_dofadr[d.chain_hi[c]] + d.body_dofnum[d.chain_hi[c]] - d.body_dofadr[d.chain_lo[c]]; };
-        for (int a = 0; a < n; a++) for (int b2 = a + 1; b2 < n; b2++) {
-            // parents first (the trunk continues on warp 0), then by length
-            bool swap = (cchild[order[b2]] > 0 && cchild[order[a]] == 0) ||
-                        ((cchild[order[b2]] > 0) == (cchild[order[a]] > 0) && ndof(order[b2]) > ndof(order[a]));
-            if (swap) { int t = order[a]; order[a] = order[b2]; order[b2] = t; }
-        }
-        per_level_count[L] = n;
-        for (int a = 0; a < n; a++) d.chain_warp[order[a]] = a % 4;
-        if (n > 4 || per_level_parents[L] > 1) d.t4_ok = 0;
-    }
-    // every hinge of a body must share one anchor (the shared rows keep one anchor per body)
-    for (int b = 1; b < nb; b++)
-        for (int j = 1; j < d.body_dofnum[b]; j++)
-            for (int k = 0; k < 3; k++)
-                if (d.dof_anchor[d.body_dofadr[b] + j][k] != d.dof_anchor[d.body_dofadr[b]][k]) d.t4_ok = 0;
-    for (int b = 0; b < nb; b++) d.body_xp_slot[b] = -1;
-    int nslot = 0;
-    for (int k = 0; k < EGP_NEE; k++) {
-        if (d.body_xp_slot[d.ee_body[k]] < 0) d.body_xp_slot[d.ee_body[k]] = nslot++;
-        d.ee_xp_slot[k] = d.body_xp_slot[d.ee_body[k]];
-    }
-    if (d.body_xp_slot[d.head_body] < 0) d.body_xp_slot[d.head_body] = nslot++;
-    d.head_xp_slot = d.body_xp_slot[d.head_body];
-    // TMEM scratch slots: position of each dof / body among those owned by the same warp
-    int nd_w[4] = {0, 0, 0, 0}, nb_w[4] = {0, 0, 0, 0};
-    for (int b = 0; b < nb; b++) {
-        int w = d.chain_warp[d.body_chain[b]];
-        d.body_slot[b] = nb_w[w]++;
-        for (int i = d.body_dofadr[b]; i < d.body_dofadr[b] + d.body_dofnum[b]; i++) d.dof_slot[i] = nd_w[w]++;
-    }
-    int ND = 0, NB = 0;
-    for (int w = 0; w < 4; w++) { if (nd_w[w] > ND) ND = nd_w[w]; if (nb_w[w] > NB) NB = nb_w[w]; }
-    d.tm_dinv = 0; d.tm_u = 2 * ND; d.tm_tau = 4 * ND; d.tm_c = 6 * ND; d.tm_cin = 8 * ND; d.tm_fb = 8 * ND + 20 * NB;
-    d.tm_cols = 8 * ND + 32 * NB;
-    if (d.tm_cols > 512) d.t4_ok = 0;
-}
-
 }  // namespace egp
 
 using namespace egp;
@@ -2135,56 +1712,15 @@ extern "C" {
 
 int egp_model_create(const EgpModelDesc *s, int device, EgpModel **out) {
     if (!s || !out) { set_error("egp_model_create: null argument"); return EGP_EINVAL; }
-    if (s->nbody > MAXB || s->nv > MAXV || s->nbody < 1 || s->nv != s->nq - 1 || s->nu != s->nv - 6) {
-        set_error("egp_model_create: unsupported sizes nq=%d nv=%d nu=%d nbody=%d", s->nq, s->nv, s->nu, s->nbody);
-        return EGP_ESIZE;
-    }
-    if (s->body_dofnum[0] != 6 || s->body_parent[0] != -1) {
-        set_error("egp_model_create: body 0 must be the free-joint root");
-        return EGP_EINVAL;
-    }
     EgpModel *m = new EgpModel();
     memset(m, 0, sizeof(*m));
-    DevModel &d = m->host;
-    d.nq = s->nq; d.nv = s->nv; d.nu = s->nu; d.nbody = s->nbody;
-    d.frame_skip = s->frame_skip; d.head_body = s->head_body; d.v_ord = s->v_ord; d.decay = s->decay;
-    for (int k = 0; k < EGP_NEE; k++) d.ee_body[k] = s->ee_body[k];
-    d.h = s->timestep;
-    for (int k = 0; k < 3; k++) d.grav[k] = s->gravity[k];
-    for (int b = 0; b < s->nbody; b++) {
-        d.body_parent[b] = s->body_parent[b]; d.body_dofadr[b] = s->body_dofadr[b];
-        d.body_dofnum[b] = s->body_dofnum[b]; d.body_qposadr[b] = s->body_qposadr[b];
-        if (b > 0 && (s->body_parent[b] < 0 || s->body_parent[b] >= b || s->body_dofnum[b] < 1 || s->body_dofnum[b] > 3)) {
-            delete m;
-            set_error("egp_model_create: body %d: only 1-3 hinge joints on non-root bodies, parents before children", b);
-            return EGP_EINVAL;
-        }
-        d.body_mass[b] = s->body_mass[b];
-        for (int k = 0; k < 3; k++) { d.body_pos[b][k] = s->body_pos[3 * b + k]; d.body_ipos[b][k] = s->body_ipos[3 * b + k]; }
-        for (int k = 0; k < 6; k++) d.body_inertia[b][k] = s->body_inertia[6 * b + k];
-        d.b_diffw[b] = (b < s->nbody - 1 && s->b_diffw) ? s->b_diffw[b] : 1.0;
+    const char *why = nullptr;
+    const int frc = fill_dev_model(s, m->host, &why);
+    if (frc != EGP_OK) {
+        delete m;
+        set_error("egp_model_create: %s (nq=%d nv=%d nu=%d nbody=%d)", why ? why : "bad model", s->nq, s->nv, s->nu, s->nbody);
+        return frc;
     }
-    for (int i = 0; i < s->nv; i++) {
-        d.dof_arm[i] = s->dof_armature[i];
-        int aid = -1;
-        for (int k = 0; k < 3; k++) {
-            d.dof_axis[i][k] = s->dof_axis[3 * i + k];
-            d.dof_anchor[i][k] = s->dof_anchor[3 * i + k];
-        }
-        for (int k = 0; k < 3; k++)
-            if (d.dof_axis[i][k] == 1.0 && d.dof_axis[i][(k + 1) % 3] == 0.0 && d.dof_axis[i][(k + 2) % 3] == 0.0) aid = k;
-        d.dof_axis_id[i] = aid;
-        bool act = i >= 6;
-        d.kp[i] = act ? s->jkp[i - 6] : 0.0;
-        d.kd[i] = act ? s->jkd[i - 6] : 0.0;
-        d.a_ref[i] = act ? s->a_ref[i - 6] : 0.0;
-        d.a_scale[i] = act ? s->a_scale[i - 6] : 0.0;
-        d.tlim[i] = act ? s->torque_lim[i - 6] : 0.0;
-    }
-    d.w_p = s->w_p; d.w_v = s->w_v; d.w_e = s->w_e; d.w_rp = s->w_rp; d.w_rv = s->w_rv;
-    d.k_p = s->k_p; d.k_v = s->k_v; d.k_e = s->k_e; d.k_rh = s->k_rh; d.k_rq = s->k_rq; d.k_rl = s->k_rl; d.k_ra = s->k_ra;
-    build_chains(d);
-    if (d.nchain > MAXC) { delete m; set_error("egp_model_create: too many chains"); return EGP_ESIZE; }
     m->device = device;
     *out = m;
     return EGP_OK;
@@ -2327,19 +1863,16 @@ int egp_rollout_f64(EgpModel *m, const EgpPolicyWeights *pol, const EgpRolloutCf
     int blocks = (cfg->n_env + ENVS_PER_CTA - 1) / ENVS_PER_CTA;
     // variant selection: T4 (4 warps per 32 envs, tree data in shared memory) when the model and the policy
     // width fit, else the one-warp V1 kernel; EGP_ROLLOUT_VARIANT=1 forces V1 (A/B parity runs)
-    T4Off O;
-    O.q = 0; O.v = O.q + d.nq; O.ax = O.v + d.nv; O.anc = O.ax + 3 * d.nv; O.U = O.anc + 3 * d.nbody;
-    O.jf = O.U + 6 * d.nv; O.jb = O.jf + 24 * d.nparent; O.ja = O.jb + 33 * d.max_sib; O.xp = O.ja + 6 * d.nparent;
-    O.red = O.xp + 3 * (EGP_NEE + 1); O.total = O.red + 8;
+    T4Off O = t4_offsets(d);
     // MLP shared-memory plan inside the alias window [O.ax, limit): input / hidden / weight-stage rows.
     // Try (tile depth 64, full layers) -> (32, full) -> (32, chunked layer 2/3, second hidden layer never resident).
     const int limit_rows = 227 * 1024 / 256;
     const char *force = getenv("EGP_ROLLOUT_VARIANT");
     bool use_t4 = false;
     A.kc = 64; A.chunk23 = 0;
-    if (d.t4_ok && !(force && force[0] == '1') && A.Ap / JB <= 8) {
-        const int plans[3][2] = {{64, 0}, {32, 0}, {32, 1}};
-        for (int pi = 0; pi < 3 && !use_t4; pi++) {
+    if (d.t4_ok && !(force && force[0] == '1') && A.Ap / JB <= T4_WARPS) {
+        const int plans[4][2] = {{64, 0}, {32, 0}, {32, 1}, {16, 1}};
+        for (int pi = 0; pi < 4 && !use_t4; pi++) {
             int kc = plans[pi][0], ch = plans[pi][1];
             int h2r = ch ? MLP_C2 : A.H2p;
             int xr = A.D > h2r ? A.D : h2r;
@@ -2441,7 +1974,8 @@ int egp_rollout_f64(EgpModel *m, const EgpPolicyWeights *pol, const EgpRolloutCf
         if (vn) return A.kc == 64 ? launch(rollout_kernel_t4<64, false, false, true>) : launch(rollout_kernel_t4<32, false, false, true>);
         if (A.kc == 64) return launch(rollout_kernel_t4<64, false, false>);
         if (!A.chunk23) return launch(rollout_kernel_t4<32, false, false>);
-        return launch(rollout_kernel_t4<32, true, false>);
+        if (A.kc == 32) return launch(rollout_kernel_t4<32, true, false>);
+        return launch(rollout_kernel_t4<16, true, false>);
     }
     size_t smem = sizeof(double) * ENVS_PER_CTA * ((size_t)xrows + hrows);
     if (smem > 227 * 1024) { set_error("egp_rollout_f64: policy too wide for shared memory (%zu bytes)", smem); return EGP_ESIZE; }

@@ -31,17 +31,14 @@ def merge_moments_(stats):
         return stats
     gathered = [torch.empty_like(stats) for _ in range(d.get_world_size())]
     d.all_gather(gathered, stats.contiguous())
-    g = torch.stack(gathered).to('cpu', torch.float64).tolist()
-    n, mean, m2 = 0.0, 0.0, 0.0
-    for nb, mb, sb in g:
-        if nb == 0:
-            continue
-        tot = n + nb
-        delta = mb - mean
-        m2 = m2 + sb + delta * delta * n * nb / tot
-        mean = mean + delta * nb / tot
-        n = tot
-    stats.copy_(torch.tensor([n, mean, m2], dtype=stats.dtype))
+    # pooled form of the Chan merge, evaluated on the device (no host round trip) from the same gathered rows in
+    # the same order on every rank: n = sum n_i, mean = sum n_i mean_i / n, M2 = sum (M2_i + n_i (mean_i - mean)^2)
+    g = torch.stack(gathered).to(torch.float64)
+    nb, mb, sb = g[:, 0], g[:, 1], g[:, 2]
+    n = nb.sum()
+    mean = (nb * mb).sum() / torch.clamp(n, min=1.0)
+    m2 = (sb + nb * (mb - mean) ** 2).sum()
+    stats.copy_(torch.stack([n, mean, m2]).to(stats.dtype))
     return stats
 
 

@@ -42,6 +42,9 @@ class HumanoidEnv:
         else:
             self.md = load_builtin(getattr(cfg, 'mujoco_model', 'humanoid_1205_v1'))
         self.frame_skip = 15                                # humanoid_v1.py:16
+        if float(getattr(cfg, 'env_init_noise', 0.0) or 0.0) != 0.0:
+            # humanoid_v1.py:222 adds N(0, env_init_noise) to qpos[7:] at reset; every shipped yml leaves it at 0
+            raise lib.EgpError('env_init_noise != 0 is not implemented by the fused reset (humanoid_v1.py:222)')
         self.device = device
         self.kernel = lib.Model(self.md, cfg.jkp, cfg.jkd, cfg.a_ref, cfg.a_scale, cfg.torque_lim,
                                 getattr(cfg, 'b_diffw', np.ones(self.md.nbody - 1)), cfg.reward_weights,

@@ -188,6 +188,42 @@ def reward_weights(ws):
     return out
 
 
+def build_desc(md, jkp, jkd, a_ref, a_scale, torque_lim, b_diffw, reward_ws=None, frame_skip=15):
+    """EgpModelDesc (include/egopose_b200.h) of a compiled MJCF model + cfg constants; returns (desc, arrays kept alive)"""
+    keep = {}
+    d = ModelDesc()
+    d.nq, d.nv, d.nu, d.nbody, d.timestep = md.nq, md.nv, md.nu, md.nbody, md.timestep
+    d.gravity[:] = md.gravity
+    for name in ('body_parent', 'body_dofadr', 'body_dofnum', 'body_qposadr', 'dof_body', 'dof_parent'):
+        keep[name] = _np_i(getattr(md, name))
+        setattr(d, name, keep[name].ctypes.data_as(_ip))
+    for name in ('body_pos', 'body_mass', 'body_ipos', 'body_inertia', 'dof_armature', 'dof_axis', 'dof_anchor'):
+        keep[name] = _np_d(getattr(md, name))
+        setattr(d, name, keep[name].ctypes.data_as(_dp))
+    d.ee_body[:] = [md.body_names.index(n) for n in EE_NAMES]
+    d.head_body = md.body_names.index('Head')
+    d.frame_skip = frame_skip
+    for name, val in (('jkp', jkp), ('jkd', jkd), ('a_ref', a_ref), ('a_scale', a_scale), ('torque_lim', torque_lim),
+                      ('b_diffw', b_diffw)):
+        keep[name] = _np_d(val)
+        setattr(d, name, keep[name].ctypes.data_as(_dp))
+    for k, v in reward_weights(reward_ws).items():
+        setattr(d, k, v)
+    return d, keep
+
+
+def desc_from_cfg_dict(md, cfg, frame_skip=15):
+    """build_desc from the yml dict of config/egomimic/*.yml (egomimic_config.py:105-122 semantics)"""
+    jp = list(zip(*cfg['joint_params']))
+    mult = cfg.get('jkp_multiplier', 1.0)
+    jkp = np.array(jp[1], dtype=np.float64) * mult
+    jkd = np.array(jp[2], dtype=np.float64) * cfg.get('jkd_multiplier', mult)
+    a_ref = np.deg2rad(np.array(jp[3], dtype=np.float64))
+    b_diffw = np.array(list(zip(*cfg['body_params']))[1], dtype=np.float64)
+    return build_desc(md, jkp, jkd, a_ref, np.array(jp[4], dtype=np.float64), np.array(jp[5], dtype=np.float64), b_diffw,
+                      cfg.get('reward_weights'), frame_skip)
+
+
 class Model:
     """Owns an EgpModel handle: compiled MJCF constants + cfg constants + expert tables on one device."""
 
@@ -201,25 +237,8 @@ class Model:
         self.nq, self.nv, self.nu, self.nbody = md.nq, md.nv, md.nu, md.nbody
         self.S = self.nq - 2 + self.nv
         self.dt = md.timestep * frame_skip
-        keep = self._keep = {}
-        d = ModelDesc()
-        d.nq, d.nv, d.nu, d.nbody, d.timestep = md.nq, md.nv, md.nu, md.nbody, md.timestep
-        d.gravity[:] = md.gravity
-        for name in ('body_parent', 'body_dofadr', 'body_dofnum', 'body_qposadr', 'dof_body', 'dof_parent'):
-            keep[name] = _np_i(getattr(md, name))
-            setattr(d, name, keep[name].ctypes.data_as(_ip))
-        for name in ('body_pos', 'body_mass', 'body_ipos', 'body_inertia', 'dof_armature', 'dof_axis', 'dof_anchor'):
-            keep[name] = _np_d(getattr(md, name))
-            setattr(d, name, keep[name].ctypes.data_as(_dp))
-        d.ee_body[:] = [md.body_names.index(n) for n in EE_NAMES]
-        d.head_body = md.body_names.index('Head')
-        d.frame_skip = frame_skip
-        for name, val in (('jkp', jkp), ('jkd', jkd), ('a_ref', a_ref), ('a_scale', a_scale), ('torque_lim', torque_lim),
-                          ('b_diffw', b_diffw)):
-            keep[name] = _np_d(val)
-            setattr(d, name, keep[name].ctypes.data_as(_dp))
-        for k, v in reward_weights(reward_ws).items():
-            setattr(d, k, v)
+        d, keep = build_desc(md, jkp, jkd, a_ref, a_scale, torque_lim, b_diffw, reward_ws, frame_skip)
+        self._keep = keep
         self.desc = d
         h = _vp()
         torch.cuda.set_device(self.device)

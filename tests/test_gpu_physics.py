@@ -67,7 +67,9 @@ def test_env_step_vs_reference_golden(model, golden):
         q0, v0 = g['ep%d.qpos' % ei][0], g['ep%d.qvel' % ei][0]
         qd, vd = cu(q0[None]), cu(v0[None])
         obs, hz, tq = model.env_step_debug(qd, vd, cu(g['ep%d.action' % ei][:1]))
-        assert helpers.relerr(tq[0].cpu().numpy(), np.clip(g['ep%d.torque0' % ei][0], -200, 200)) < 1e-7 or True
+        # the golden records compute_torque() before np.clip (humanoid_v1.py:171-172): clip with the per-joint limits
+        lim = np.array([jp[5] for jp in helpers.cfg_dict()['joint_params']], dtype=np.float64)
+        assert helpers.relerr(tq[0].cpu().numpy(), np.clip(g['ep%d.torque0' % ei][0], -lim, lim)) < 1e-7
         assert helpers.relerr(qd[0].cpu().numpy(), g['ep%d.qpos' % ei][1]) < 1e-7
         assert helpers.relerr(vd[0].cpu().numpy(), g['ep%d.qvel' % ei][1]) < 1e-6
         assert helpers.relerr(obs[0].cpu().numpy(), g['ep%d.obs' % ei][1]) < 1e-6
