@@ -27,6 +27,10 @@
 
 #include "common.cuh"
 
+#ifdef EGP_T4_CLK
+namespace egp { __device__ unsigned long long g_t4_clk2[16]; __device__ long long g_t4_last; }
+#define EGP_CLK_MARK(slot) { long long _t = clock64(); if (blockIdx.x == 0 && threadIdx.x == 0) { egp::g_t4_clk2[slot] += _t - egp::g_t4_last; egp::g_t4_last = _t; } }
+#endif
 #include "tree.cuh"
 
 namespace egp {
@@ -530,7 +534,9 @@ struct RolloutArgs {
     const double *W1t, *b1, *W2t, *b2, *W3t, *b3, *log_std;
     int D, H1, H2, A, H1p, H2p, Ap;
     int K1p, K2p, K3p;      // T4: k padded to the tile depth (weights packed as tiles)
-    int kc, chunk23;        // T4: tile depth (64 | 32); 1 = chunked layer-2/3 path for wide policies
+    int chunk23;            // T4: 1 = chunked layer-2/3 path for wide policies
+    int xrows, hrows, xs;   // T4: rows of the activation buffers xs / h1s and their row stride in doubles
+    double *log_part;       // [CTAs][EGP_LOG_SIZE] per-CTA logger partials (merged by logger_merge_kernel)
     // value net of the 'valuefs' evaluation rule (same plan as the policy, head padded to vAp rows), its context table
     const double *vW1t, *vb1, *vW2t, *vb2, *vW3t, *vb3, *vctx;
     int vAp;
@@ -786,7 +792,7 @@ struct T4Local {
 // right-hand sides, bias forces, body inertias) live there instead of in L2-backed thread-local memory.
 // All accesses are warp-uniform (tcgen05.ld/st are .sync.aligned).
 __device__ __forceinline__ void tm_st1(uint32_t a, double v) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(a), "r"(__double2loint(v)), "r"(__double2hiint(v)) : "memory");
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(a), "r"(__double2loint(v)), "r"(__double2hiint(v)));
 }
 __device__ __forceinline__ double tm_ld1(uint32_t a) {
     int lo, hi;
@@ -796,7 +802,7 @@ __device__ __forceinline__ double tm_ld1(uint32_t a) {
 __device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tm_st2(uint32_t a, double v0, double v1) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(__double2loint(v0)), "r"(__double2hiint(v0)),
-                 "r"(__double2loint(v1)), "r"(__double2hiint(v1)) : "memory");
+                 "r"(__double2loint(v1)), "r"(__double2hiint(v1)));
 }
 __device__ __forceinline__ void tm_ld2(uint32_t a, double &v0, double &v1) {
     int r[4];
@@ -807,7 +813,7 @@ __device__ __forceinline__ void tm_ld2(uint32_t a, double &v0, double &v1) {
 __device__ __forceinline__ void tm_st4(uint32_t a, const double *v) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(a),
                  "r"(__double2loint(v[0])), "r"(__double2hiint(v[0])), "r"(__double2loint(v[1])), "r"(__double2hiint(v[1])),
-                 "r"(__double2loint(v[2])), "r"(__double2hiint(v[2])), "r"(__double2loint(v[3])), "r"(__double2hiint(v[3])) : "memory");
+                 "r"(__double2loint(v[2])), "r"(__double2hiint(v[2])), "r"(__double2loint(v[3])), "r"(__double2hiint(v[3])));
 }
 __device__ __forceinline__ void tm_ld4(uint32_t a, double *v) {
     int r[8];
@@ -821,7 +827,7 @@ __device__ __forceinline__ void tm_st8(uint32_t a, const double *v) {
                  "r"(__double2loint(v[0])), "r"(__double2hiint(v[0])), "r"(__double2loint(v[1])), "r"(__double2hiint(v[1])),
                  "r"(__double2loint(v[2])), "r"(__double2hiint(v[2])), "r"(__double2loint(v[3])), "r"(__double2hiint(v[3])),
                  "r"(__double2loint(v[4])), "r"(__double2hiint(v[4])), "r"(__double2loint(v[5])), "r"(__double2hiint(v[5])),
-                 "r"(__double2loint(v[6])), "r"(__double2hiint(v[6])), "r"(__double2loint(v[7])), "r"(__double2hiint(v[7])) : "memory");
+                 "r"(__double2loint(v[6])), "r"(__double2hiint(v[6])), "r"(__double2loint(v[7])), "r"(__double2hiint(v[7])));
 }
 __device__ __forceinline__ void tm_ld8(uint32_t a, double *v) {
     int r[16];
@@ -833,15 +839,46 @@ __device__ __forceinline__ void tm_ld8(uint32_t a, double *v) {
     for (int k = 0; k < 8; k++) v[k] = __hiloint2double(r[2 * k + 1], r[2 * k]);
 }
 
-// loads without the wait: issue several, then ONE tm_wait_ld over all destination registers (the operands make the
-// dependency visible to the compiler)
-__device__ __forceinline__ void tm_ld4_nowait(uint32_t a, int (&r)[8]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(a) : "memory");
-}
-__device__ __forceinline__ void tm_wait_ld8(int (&r)[8]) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]) :: "memory");
-}
+// ---- asynchronous scratch loads: tcgen05.ld is issued without the wait (no "memory" clobber either: these accesses do not
+// touch ordinary memory, and volatile asm statements keep their mutual order), the destination registers become valid
+// after tm_wait_ld, whose "+r" operands make that dependency visible to the compiler
+template <int NR> struct TmLd;
+template <> struct TmLd<8> {
+    static __device__ __forceinline__ void issue(uint32_t a, int (&r)[8]) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(a));
+    }
+    static __device__ __forceinline__ void wait(int (&r)[8]) {
+        asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]));
+    }
+};
+template <> struct TmLd<16> {
+    static __device__ __forceinline__ void issue(uint32_t a, int (&r)[16]) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                       "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(a));
+    }
+    static __device__ __forceinline__ void wait(int (&r)[16]) {
+        asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                     "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]));
+    }
+};
+template <> struct TmLd<32> {
+    static __device__ __forceinline__ void issue(uint32_t a, int (&r)[32]) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                     "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                       "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+                       "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+                       "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]) : "r"(a));
+    }
+    static __device__ __forceinline__ void wait(int (&r)[32]) {
+        asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                     "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]),
+                     "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]),
+                     "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31]));
+    }
+};
 
 // storage context of the tree sweeps (csrc/tree.cuh) on the device: shared rows [row][env] + Tensor Memory scratch
 extern __shared__ double t4_smem[];          // the CTA's dynamic shared memory (named here so that non-inlined sweeps
@@ -851,25 +888,24 @@ struct T4Ctx {
     uint32_t tm;        // TMEM base of this warp's lane quarter
     T4Off o;
     __device__ __forceinline__ double &at(int off, int idx) const { return t4_smem[(off + idx) * 32 + lane]; }
-    // TMEM column addresses
-    __device__ __forceinline__ uint32_t a_ctrl(int i) const { return tm + c_m.tm_ctrl + 2 * c_m.dof_slot[i]; }
-    __device__ __forceinline__ uint32_t a_tau(int i) const { return tm + c_m.tm_tau + 2 * c_m.dof_slot[i]; }
-    __device__ __forceinline__ uint32_t a_c(int i) const { return tm + c_m.tm_c + 2 * c_m.dof_slot[i]; }
-    __device__ __forceinline__ uint32_t a_cin(int b) const { return tm + c_m.tm_cin + 20 * c_m.body_slot[b]; }
-    __device__ __forceinline__ uint32_t a_fb(int b) const { return tm + c_m.tm_fb + 12 * c_m.body_slot[b]; }
+    // TMEM column addresses of a dof's ctrl / tau / C entry and of a body's record
+    __device__ __forceinline__ uint32_t a_ctrl(int i) const { return tm + c_m.dof_col_ctrl[i]; }
+    __device__ __forceinline__ uint32_t a_tau(int i) const { return tm + c_m.dof_col_tau[i]; }
+    __device__ __forceinline__ uint32_t a_c(int i) const { return tm + c_m.dof_col_c[i]; }
+    __device__ __forceinline__ uint32_t a_cin(int b) const { return tm + c_m.bk[b].rec + R_CIN; }
     __device__ __forceinline__ void st_cin(int b, const double *ci) const { tm_st8(a_cin(b), ci); tm_st2(a_cin(b) + 16, ci[8], ci[9]); }
     __device__ __forceinline__ void ld_cin(int b, double *ci) const { tm_ld8(a_cin(b), ci); tm_ld2(a_cin(b) + 16, ci[8], ci[9]); }
-    __device__ __forceinline__ void st_fb(int b, const double *f) const { tm_st4(a_fb(b), f); tm_st2(a_fb(b) + 8, f[4], f[5]); }
-    __device__ __forceinline__ void ld_fb(int b, double *f) const { tm_ld4(a_fb(b), f); tm_ld2(a_fb(b) + 8, f[4], f[5]); }
-    // N consecutive per-dof values (N = 1 or 3) at column `col` of this thread's scratch; a 3-wide load is issued as one
-    // 4-wide access (the extra double is the next slot / array, always inside the allocation)
-    template <int N> __device__ __forceinline__ void tld(int col, double *v) const {
-        if (N == 1) v[0] = tm_ld1(tm + col);
-        else { double t[4]; tm_ld4(tm + col, t); v[0] = t[0]; v[1] = t[1]; v[2] = t[2]; }
-    }
+    template <int NR> __device__ __forceinline__ void tld_issue(int col, int (&r)[NR]) const { TmLd<NR>::issue(tm + col, r); }
+    template <int NR> __device__ __forceinline__ void tld_wait(int (&r)[NR]) const { TmLd<NR>::wait(r); }
+    static __device__ __forceinline__ double unpack(const int *r, int k) { return __hiloint2double(r[2 * k + 1], r[2 * k]); }
     template <int N> __device__ __forceinline__ void tst(int col, const double *v) const {
-        if (N == 1) tm_st1(tm + col, v[0]);
-        else { tm_st2(tm + col, v[0], v[1]); tm_st1(tm + col + 4, v[2]); }
+        uint32_t a = tm + col;
+        int k = 0;
+        if (N >= 16) { tm_st8(a, v); tm_st8(a + 16, v + 8); k = 16; }
+        else if (N >= 8) { tm_st8(a, v); k = 8; }
+        if (N - k >= 4) { tm_st4(a + 2 * k, v + k); k += 4; }
+        if (N - k >= 2) { tm_st2(a + 2 * k, v[k], v[k + 1]); k += 2; }
+        if (N - k >= 1) tm_st1(a + 2 * k, v[k]);
     }
     __device__ __forceinline__ void twait_st() const { tm_wait_st(); }
 };
@@ -880,15 +916,19 @@ __device__ __forceinline__ void t4_bar() { asm volatile("bar.sync 1, 128;" ::: "
 // level-synchronous tree sweeps (root | spine, legs | arms, head): one chain per warp and level, junction records
 // cross warps through shared memory (csrc/tree.cuh holds the per-chain work)
 template <int MODE>
-__device__ __noinline__ void t4_forward(const T4Ctx x) {
+__device__ __forceinline__ void t4_forward(const T4Ctx &x) {
+#pragma unroll 1
     for (int L = 0; L < c_m.nlevel; L++) {
         const int c = c_m.lvl_chain[L][x.w];
         if (c >= 0) t5_fwd_chain<MODE>(x, c);
+        if (MODE == 0) { EGP_CLK_MARK(11) }
         t4_bar();
+        if (MODE == 0) { EGP_CLK_MARK(12) }
     }
 }
 
-__device__ __noinline__ void t4_backward(const T4Ctx x, const int MODE) {
+__device__ __forceinline__ void t4_backward(const T4Ctx &x, const int MODE) {
+#pragma unroll 1
     for (int L = c_m.nlevel - 1; L >= 0; L--) {
         const int c = c_m.lvl_chain[L][x.w];
         Bwd w;
@@ -906,19 +946,44 @@ __device__ __noinline__ void t4_backward(const T4Ctx x, const int MODE) {
             for (int b = c_m.chain_lo[_c]; b <= c_m.chain_hi[_c]; b++)                               \
                 for (int i = c_m.body_dofadr[b]; i < c_m.body_dofadr[b] + c_m.body_dofnum[b]; i++)
 
-__device__ void t4_forward_only(const T4Ctx &x) {      // sim.forward(); chain warps only
+__device__ __noinline__ void t4_forward_only(const T4Ctx x) {      // sim.forward(); chain warps only; own register allocation
     t4_forward<2>(x);
-    T4_FOR_OWN_DOFS(i, b) tm_st1(x.a_tau(i), 0.0);
+    T4_FOR_OWN_DOFS(i, b) if (i >= 6) tm_st1(x.a_tau(i), 0.0);
     tm_wait_st();
     t4_backward(x, 0);
 }
 
 // One iteration of do_simulation (humanoid_v1.py:166-174): stable-PD torque on the stale tree data, then mj_step.
-__device__ void t4_substep(const T4Ctx &x) {
+#ifdef EGP_T4_CLK
+__device__ unsigned long long g_t4_clk[8];      // build with -DEGP_T4_CLK: cycles of warp 0 of CTA 0 per sweep kind
+#endif
+__device__ __forceinline__ void t4_substep(const T4Ctx &x) {
+#ifdef EGP_T4_CLK
+    const bool pr = blockIdx.x == 0 && x.w == 0 && x.lane == 0;
+    long long t0 = clock64();
+#define T4_CLK(slot) { long long t1 = clock64(); if (pr) g_t4_clk[slot] += t1 - t0; t0 = t1; }
+#else
+#define T4_CLK(slot)
+#endif
     t4_backward(x, 1);          // (M_stale + Kd h) factor + reduce, rhs from the current q, v
+    T4_CLK(0)
     t4_forward<1>(x);           // desired accel -> clipped torque ; kinematics / velocities / body forces at (q, v)
+    T4_CLK(1)
     t4_backward(x, 0);          // bias C, M factor + reduce with rhs = torque - C
+    T4_CLK(2)
     t4_forward<0>(x);           // qacc, semi-implicit Euler
+    T4_CLK(3)
+#ifdef EGP_T4_CLK
+    if (pr) g_t4_clk[4] += 1;
+#endif
+}
+
+// do_simulation (humanoid_v1.py:158-177): all sub-steps of one env step.  NOT inlined into the kernel: the sweeps get a
+// register allocation of their own (the kernel's per-step state - filtered observation shares, logger sums - is
+// saved / restored once per env step at the call, not carried through every sweep)
+__device__ __forceinline__ void t4_do_simulation(const T4Ctx &x, const int n_sub) {
+#pragma unroll 1
+    for (int s = 0; s < n_sub; s++) t4_substep(x);
 }
 
 // observation entry k (humanoid_v1.py:73-96) from the shared q / v rows; hd* = de-headed root quaternion,
@@ -935,133 +1000,119 @@ __device__ __forceinline__ double t4_obs_entry(const T4Ctx &x, int k, double hd0
     return x.at(x.o.v, j);
 }
 
-constexpr int MLP_KC_MAX = 64;               // k rows per weight tile (64, or 32 for wide policies)
+// ---- policy MLP on the FP64 tensor cores --------------------------------------------------------------------------
+// One dense layer for the CTA's 32 environments = [32 x K] . [K x N]: mma.sync m8n8k4 f64 (DMMA) issues 256 FMAs per
+// instruction at the DFMA pipe's FLOP rate (measured: 16 cycles per DMMA and sub-partition, tools/micro/fp64_probe.cu),
+// i.e. 8x fewer issue slots than the SIMT loop it replaces, and - decisive here - its operands are distributed over the
+// lanes: an activation fragment is one conflict-free 256-byte shared load, a weight fragment one coalesced 256-byte
+// global load of weights pre-packed in fragment order, instead of four 2-wavefront broadcast loads per 8 FMAs.
+// Activations live feature-major with a row stride of XS = 36 doubles: the four k rows of a fragment then fall on
+// disjoint bank groups (stride 32 would be a 4-way conflict).  Work item = 16 environments x 16 neurons (2 x 2
+// fragments); 2 * N/16 items are dealt round-robin to the 8 warps.
+constexpr int XS_WIDE = 36;                  // default row stride; 32 (4-way conflicts on the fragment loads) when 36 does not fit
+constexpr int MLP_NT = 16;                   // neurons per work item; weights / biases are padded to multiples of 16
 
-// Computes output blocks [jb0, jb1) (8 neurons each, split over the warps) of one dense layer:
-// ys[(j - 8*jb0 + out_row0)][lane] = act(bias[j] + sum_k W[j][k] xs[k][lane]).
-template <bool RELU, int KC>
-__device__ __forceinline__ void t4_mlp_layer(const double *__restrict__ Wp, const double *__restrict__ bias, int K, int Kp,
-                                             int jb0, int jb1, int out_row0, const double *xs, double *ys, double *stage,
-                                             int lane, int w) {
-    constexpr int TILE = KC * JB;
-    const int nchunk = Kp / KC, njb = jb1 - jb0;
-    const int my_blocks = (njb - w + T4_WARPS - 1) / T4_WARPS;
-    const int ntile = my_blocks > 0 ? my_blocks * nchunk : 0;
-    if (ntile <= 0) return;
-    double2 pre[TILE / 64];                                          // this lane's share of the tile in flight
-    auto tile_ptr = [&](int t) {
-        const int jb = jb0 + w + T4_WARPS * (t / nchunk), c = t % nchunk;
-        return reinterpret_cast<const double2 *>(Wp + ((size_t)jb * Kp + (size_t)c * KC) * JB);
-    };
-    {
-        const double2 *src = tile_ptr(0);
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+// accumulates acc[mf][nf] += x[16 envs of half eh][k in 4 kc0 .. 4 kc1) . W[neuron tile nt][k]; Wf = [N/8][K4][32] fragments,
+// K4 (a multiple of 4) = padded K / 4; xs row r holds k = row_k0 + r
+__device__ __forceinline__ void t4_dmma_acc(double (&acc)[2][2][2], const double *__restrict__ Wf, int K4, int nt, int kc0, int kc1,
+                                            int row_k0, const double *xs, int XS, int eh, int lane) {
+    const double *w0 = Wf + ((size_t)(2 * nt) * K4) * 32 + lane, *w1 = w0 + (size_t)K4 * 32;
+    const double *xa = xs + (ptrdiff_t)((lane & 3) - row_k0) * XS + eh * 16 + (lane >> 2);
+    double bn[4][2];
 #pragma unroll
-        for (int m = 0; m < TILE / 64; m++) pre[m] = __ldg(src + lane + 32 * m);
-    }
-    double acc[JB];
-    double2 *st2 = reinterpret_cast<double2 *>(stage);
-    for (int t = 0; t < ntile; t++) {
-        const int jb = jb0 + w + T4_WARPS * (t / nchunk), c = t % nchunk;
-        if (c == 0) {
+    for (int u = 0; u < 4; u++) { bn[u][0] = __ldg(w0 + (size_t)(kc0 + u) * 32); bn[u][1] = __ldg(w1 + (size_t)(kc0 + u) * 32); }
+    for (int g = kc0; g < kc1; g += 4) {
+        double bc[4][2];
 #pragma unroll
-            for (int jj = 0; jj < JB; jj++) acc[jj] = bias[jb * JB + jj];
+        for (int u = 0; u < 4; u++) { bc[u][0] = bn[u][0]; bc[u][1] = bn[u][1]; }
+        if (g + 4 < kc1) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) { bn[u][0] = __ldg(w0 + (size_t)(g + 4 + u) * 32); bn[u][1] = __ldg(w1 + (size_t)(g + 4 + u) * 32); }
         }
-        __syncwarp();
 #pragma unroll
-        for (int m = 0; m < TILE / 64; m++) st2[lane + 32 * m] = pre[m];
-        __syncwarp();
-        if (t + 1 < ntile) {
-            const double2 *src = tile_ptr(t + 1);
-#pragma unroll
-            for (int m = 0; m < TILE / 64; m++) pre[m] = __ldg(src + lane + 32 * m);
-        }
-        const int k0 = c * KC;
-        const int kn = K - k0 < KC ? K - k0 : KC;
-        const double *xp = xs + (size_t)k0 * 32 + lane;
-#pragma unroll 4
-        for (int kk = 0; kk < kn; kk++) {
-            const double xv = xp[(size_t)kk * 32];
-#pragma unroll
-            for (int jj = 0; jj < JB / 2; jj++) {
-                const double2 ww = st2[kk * (JB / 2) + jj];
-                acc[2 * jj] += ww.x * xv;
-                acc[2 * jj + 1] += ww.y * xv;
-            }
-        }
-        if (c == nchunk - 1) {
-#pragma unroll
-            for (int jj = 0; jj < JB; jj++)
-                ys[((jb - jb0) * JB + jj + out_row0) * 32 + lane] = RELU ? fmax(acc[jj], 0.0) : acc[jj];
+        for (int u = 0; u < 4; u++) {
+            const double a0 = xa[(size_t)(4 * (g + u)) * XS], a1 = xa[(size_t)(4 * (g + u)) * XS + 8];
+            dmma884(acc[0][0], a0, bc[u][0]);
+            dmma884(acc[0][1], a0, bc[u][1]);
+            dmma884(acc[1][0], a1, bc[u][0]);
+            dmma884(acc[1][1], a1, bc[u][1]);
         }
     }
 }
 
-// acc[8] += W[block jb][k in tiles [t0, t1)] . xs rows (k - row_k0): partial product used by the chunked
-// layer-2/3 path of wide policies (the second hidden layer never exists in full)
-template <int KC>
-__device__ __forceinline__ void t4_mlp_partial(const double *__restrict__ Wp, int K, int Kp, int jb, int t0, int t1, int row_k0,
-                                               const double *xs, double *acc, double *stage, int lane) {
-    constexpr int TILE = KC * JB;
-    double2 *st2 = reinterpret_cast<double2 *>(stage);
-    for (int c = t0; c < t1; c++) {
-        const double2 *src = reinterpret_cast<const double2 *>(Wp + ((size_t)jb * Kp + (size_t)c * KC) * JB);
-        double2 pre[TILE / 64];
+__device__ __forceinline__ void t4_dmma_init(double (&acc)[2][2][2], const double *__restrict__ bias, int nt, int lane) {
 #pragma unroll
-        for (int m = 0; m < TILE / 64; m++) pre[m] = __ldg(src + lane + 32 * m);
-        __syncwarp();
+    for (int nf = 0; nf < 2; nf++)
 #pragma unroll
-        for (int m = 0; m < TILE / 64; m++) st2[lane + 32 * m] = pre[m];
-        __syncwarp();
-        const int k0 = c * KC;
-        const int kn = K - k0 < KC ? K - k0 : KC;
-        for (int kk = 0; kk < kn; kk++) {
-            const double xv = xs[(size_t)(k0 + kk - row_k0) * 32 + lane];
-#pragma unroll
-            for (int jj = 0; jj < JB / 2; jj++) {
-                const double2 ww = st2[kk * (JB / 2) + jj];
-                acc[2 * jj] += ww.x * xv;
-                acc[2 * jj + 1] += ww.y * xv;
-            }
+        for (int c = 0; c < 2; c++) {
+            const double bv = bias[nt * MLP_NT + nf * 8 + 2 * (lane & 3) + c];
+            acc[0][nf][c] = bv; acc[1][nf][c] = bv;
         }
+}
+
+template <bool RELU>
+__device__ __forceinline__ void t4_dmma_store(const double (&acc)[2][2][2], int row0, double *ys, int XS, int eh, int lane) {
+#pragma unroll
+    for (int mf = 0; mf < 2; mf++)
+#pragma unroll
+        for (int nf = 0; nf < 2; nf++)
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                const double v = acc[mf][nf][c];
+                ys[(size_t)(row0 + nf * 8 + 2 * (lane & 3) + c) * XS + eh * 16 + mf * 8 + (lane >> 2)] = RELU ? fmax(v, 0.0) : v;
+            }
+}
+
+// neuron tiles [nt0, nt1) of one dense layer: ys[(16 (nt - nt0) + j) + out_row0][env] = act(bias + W x)
+template <bool RELU>
+__device__ __forceinline__ void t4_mlp_layer(const double *__restrict__ Wf, const double *__restrict__ bias, int K4, int nt0, int nt1,
+                                             int out_row0, const double *xs, double *ys, int XS, int lane, int w) {
+    for (int t = w; t < 2 * (nt1 - nt0); t += T4_WARPS) {
+        const int eh = t & 1, nt = nt0 + (t >> 1);
+        double acc[2][2][2];
+        t4_dmma_init(acc, bias, nt, lane);
+        t4_dmma_acc(acc, Wf, K4, nt, 0, K4, 0, xs, XS, eh, lane);
+        t4_dmma_store<RELU>(acc, (nt - nt0) * MLP_NT + out_row0, ys, XS, eh, lane);
     }
 }
 
 // PolicyGaussian trunk + head for the CTA's 32 environments (policy_gaussian.py:19-24, mlp.py:22-25):
-// xs [D rows] -> action means in h1s rows [0, A).  Normal path: three full layers.  Chunked path (second hidden
-// layer too wide for shared memory): layer 2 is produced C2 neurons at a time into the (dead) input rows and
-// immediately folded into register accumulators of the head.
+// xs [D rows, zero rows up to the padded K] -> action means in h1s rows [0, A).  Normal path: three full layers.
+// Chunked path (second hidden layer too wide for shared memory): layer 2 is produced MLP_C2 neurons at a time into the
+// (dead) input rows and immediately folded into the head's accumulators (Ap / 16 tiles x 2 halves <= 8 items: one per warp).
 constexpr int MLP_C2 = 64;
-template <int KC, bool CHUNK>
-__device__ __forceinline__ void t4_policy_forward(const RolloutArgs &A, double *xs, double *h1s, double *stage, int lane, int w) {
-    t4_mlp_layer<true, KC>(A.W1t, A.b1, A.D, A.K1p, 0, A.H1p / JB, 0, xs, h1s, stage, lane, w);
+template <bool CHUNK>
+__device__ __forceinline__ void t4_policy_forward(const RolloutArgs &A, double *xs, double *h1s, int lane, int w) {
+    const int XS = A.xs;
+    t4_mlp_layer<true>(A.W1t, A.b1, A.K1p / 4, 0, A.H1p / MLP_NT, 0, xs, h1s, XS, lane, w);
     __syncthreads();
     if (!CHUNK) {
-        t4_mlp_layer<true, KC>(A.W2t, A.b2, A.H1, A.K2p, 0, A.H2p / JB, 0, h1s, xs, stage, lane, w);
+        t4_mlp_layer<true>(A.W2t, A.b2, A.K2p / 4, 0, A.H2p / MLP_NT, 0, h1s, xs, XS, lane, w);
         __syncthreads();
-        t4_mlp_layer<false, KC>(A.W3t, A.b3, A.H2, A.K3p, 0, A.Ap / JB, 0, xs, h1s, stage, lane, w);
+        t4_mlp_layer<false>(A.W3t, A.b3, A.K3p / 4, 0, A.Ap / MLP_NT, 0, xs, h1s, XS, lane, w);
         __syncthreads();
         return;
     }
-    double acc3[JB];
-    const int nob = A.Ap / JB;                              // head output blocks (<= T4_WARPS, checked on the host): warp w owns block w
-#pragma unroll
-    for (int jj = 0; jj < JB; jj++) acc3[jj] = w < nob ? A.b3[w * JB + jj] : 0.0;
+    const int nitem = 2 * (A.Ap / MLP_NT);                  // <= T4_WARPS, checked on the host
+    const int eh = w & 1, nt = w >> 1;
+    double acc3[2][2][2];
+    if (w < nitem) t4_dmma_init(acc3, A.b3, nt, lane);
     for (int c2 = 0; c2 < A.H2p; c2 += MLP_C2) {
         const int hi = c2 + MLP_C2 < A.H2p ? c2 + MLP_C2 : A.H2p;
-        t4_mlp_layer<true, KC>(A.W2t, A.b2, A.H1, A.K2p, c2 / JB, hi / JB, 0, h1s, xs, stage, lane, w);
+        t4_mlp_layer<true>(A.W2t, A.b2, A.K2p / 4, c2 / MLP_NT, hi / MLP_NT, 0, h1s, xs, XS, lane, w);
         __syncthreads();
-        const int khi = hi < A.H2 ? hi : A.H2;              // real neurons of this chunk
-        if (khi > c2 && w < nob)
-            t4_mlp_partial<KC>(A.W3t, khi, A.K3p, w, c2 / KC, (khi + KC - 1) / KC, c2, xs, acc3, stage, lane);
+        if (w < nitem) t4_dmma_acc(acc3, A.W3t, A.K3p / 4, nt, c2 / 4, hi / 4, c2, xs, XS, eh, lane);
         __syncthreads();
     }
-    if (w < nob)
-#pragma unroll
-        for (int jj = 0; jj < JB; jj++) h1s[(w * JB + jj) * 32 + lane] = acc3[jj];
+    if (w < nitem) t4_dmma_store<false>(acc3, nt * MLP_NT, h1s, XS, eh, lane);
     __syncthreads();
 }
 
-template <int KC, bool CHUNK, bool SNET, bool VALFS = false>
+template <bool CHUNK, bool SNET, bool VALFS = false>
 __global__ void __launch_bounds__(T4_THREADS, 1)
 rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
     extern __shared__ double smem[];
@@ -1081,17 +1132,10 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
     x.tm = tmem_base + ((uint32_t)((w & 3) * 32) << 16);     // warps w and w + 4 share a lane quarter
     const bool cw = w < T4_CW;                             // chain warp: owns tree sweeps (helper warps: MLP / obs / reward only)
     const int S = c_m.nq - 2 + c_m.nv, nu = c_m.nu, nv = c_m.nv, nb = c_m.nbody, nq = c_m.nq;
-    double *xs = smem + (size_t)O.ax * 32;               // MLP activations alias the axis / anchor / U rows
-    const int h2rows = CHUNK ? MLP_C2 : A.H2p;
-    int xrows = A.D > h2rows ? A.D : h2rows;
-    int hrows4 = A.H1p > A.Ap ? A.H1p : A.Ap;
-    if (SNET) {                                          // same plan as egp_rollout_f64: LSTM input / gate-chunk rows
-        const int sn_in = c_m.nq - 2 + c_m.nv + A.sn_H;
-        if (xrows < sn_in) xrows = sn_in;
-        if (hrows4 < 256) hrows4 = 256;
-    }
-    double *h1s = xs + (size_t)xrows * 32;
-    double *stage = h1s + (size_t)hrows4 * 32 + (size_t)w * KC * JB;    // per-warp weight tile
+    // MLP activations alias the axis / anchor / U rows: xs [A.xrows][XS], h1s [A.hrows][XS] (plan made on the host)
+    const int XS = A.xs;
+    double *xs = smem + (size_t)O.ax * 32;
+    double *h1s = xs + (size_t)A.xrows * XS;
     const int T = A.cfg.horizon, E = A.cfg.n_env;
     const double dt = c_m.h * c_m.frame_skip;
     const int env = blockIdx.x * 32 + lane;
@@ -1184,6 +1228,23 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
         }
     };
 
+    // Trajbatch rows are written row-contiguous: a [feature][env] tile in shared memory (the activation buffers, free at
+    // that point of the step) is read transposed, warp = environment, lane = feature, so every row of 115 / 52 doubles
+    // leaves as full 128-byte lines instead of one 8-byte store per environment 276 KB apart.
+    auto write_rows = [&](double *dst, const double *tile, int width, size_t step_n) {       // dst row of env e: (e_global * T + t) * width
+        if (!dst) return;
+        for (int e = w; e < 32; e += T4_WARPS) {
+            const long long ge = (long long)blockIdx.x * 32 + e;
+            if (ge >= E) break;
+            double *row = dst + ((size_t)ge * T + step_n) * width;
+            for (int k = lane; k < width; k += 32) row[k] = tile[(size_t)k * XS + e];
+        }
+    };
+    auto stage_share = [&](double *tile, const double *share) {     // this thread's strided share -> tile[k][env]
+        int s = 0;
+        for (int k = w; k < S; k += T4_WARPS, s++) tile[(size_t)k * XS + lane] = share[s];
+    };
+    double pend[(2 * MAXV + T4_WARPS - 1) / T4_WARPS];   // next_state of the previous step, written with the next step's rows
     draw_reset(0);
     do_reset();
     if (A.cfg.eval_mode || A.in.d_init_qpos) {
@@ -1201,7 +1262,7 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
         if (cw) t4_forward_only(x);
     }
     make_state(raw, st);
-    T4_FOR_OWN_DOFS(i, b) tm_st1(x.a_ctrl(i), 0.0);
+    T4_FOR_OWN_DOFS(i, b) if (i >= 6) tm_st1(x.a_ctrl(i), 0.0);
     tm_wait_st();
     // state-LSTM h | c rows of this CTA, [2H][32] (s_net.initialize() at pre_episode, rnn.py:22-26)
     double *sn_g = SNET ? A.sn_state + (size_t)blockIdx.x * 2 * A.sn_H * 32 : nullptr;
@@ -1220,38 +1281,45 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
                 for (int b = c_m.chain_lo[c]; b <= c_m.chain_hi[c]; b++)
                     for (int r = 0; r < 3; r++) l.sav_anc[b][r] = x.at(O.anc, 3 * b + r);
         __syncthreads();
-        // ---- policy input cat(ctx[frame], state), feature-major
+        // ---- trajbatch rows of this step (raw observation, previous step's next_state) through the hidden-layer tile
+        if (A.out.d_raw_obs) {
+            stage_share(h1s, raw);
+            __syncthreads();
+            write_rows(A.out.d_raw_obs, h1s, S, t);
+            __syncthreads();
+        }
+        if (A.out.d_next_states && t > 0) {
+            stage_share(h1s, pend);
+            __syncthreads();
+            write_rows(A.out.d_next_states, h1s, S, t - 1);
+            __syncthreads();
+        }
+        // ---- policy input cat(ctx[frame], state), feature-major; rows up to the padded K are zero
         int off = 0;
         if (A.ctx && !sn_g) {
             const double *cx = ctx_row(A, take, start, cur_t);
-            for (int k = w; k < A.ctx_dim; k += T4_WARPS) xs[k * 32 + lane] = cx[k];
+            for (int k = w; k < A.ctx_dim; k += T4_WARPS) xs[(size_t)k * XS + lane] = cx[k];
             off = A.ctx_dim;
         }
-        {
-            int s = 0;
-            for (int k = w; k < S; k += T4_WARPS, s++) {
-                xs[(off + k) * 32 + lane] = st[s];
-                if (live) {
-                    A.out.d_states[n * S + k] = st[s];
-                    if (A.out.d_raw_obs) A.out.d_raw_obs[n * S + k] = raw[s];
-                }
-            }
-        }
+        stage_share(xs + (size_t)off * XS, st);
+        for (int k = (sn_g ? S + A.sn_H : A.D) + w; k < A.xrows; k += T4_WARPS) xs[(size_t)k * XS + lane] = 0.0;
+        __syncthreads();
+        write_rows(A.out.d_states, xs + (size_t)off * XS, S, t);
         if (sn_g) {
             // ---- s_net LSTMCell step on the filtered state (video_forecast_net.py:89-93, rnn.py:36-43):
             // gates = W [state | h_prev] + b, 64 units (256 packed gate rows 4u + g) at a time through the dense-layer
             // routine, then c = sig(f) c + sig(i) tanh(g), h = sig(o) tanh(c); policy input = cat(ctx row, h)
             const int H = A.sn_H;
-            for (int j = w; j < H; j += T4_WARPS) xs[(S + j) * 32 + lane] = sn_g[j * 32 + lane];
+            for (int j = w; j < H; j += T4_WARPS) xs[(size_t)(S + j) * XS + lane] = sn_g[j * 32 + lane];
             __syncthreads();
             for (int c0 = 0; c0 < H; c0 += 64) {
                 const int hi = c0 + 64 < H ? c0 + 64 : H;
-                t4_mlp_layer<false, KC>(A.sn_Wp, A.sn_b, S + H, A.sn_Kp, c0 * 4 / JB, hi * 4 / JB, 0, xs, h1s, stage, lane, w);
+                t4_mlp_layer<false>(A.sn_Wp, A.sn_b, A.sn_Kp / 4, c0 * 4 / MLP_NT, (hi * 4 + MLP_NT - 1) / MLP_NT, 0, xs, h1s, XS, lane, w);
                 __syncthreads();
                 for (int u = c0 + w; u < hi; u += T4_WARPS) {
-                    const double *gr = h1s + (size_t)(u - c0) * 4 * 32 + lane;
-                    const double ig = 1.0 / (1.0 + exp(-gr[0])), fg = 1.0 / (1.0 + exp(-gr[32]));
-                    const double gg = tanh(gr[64]), og = 1.0 / (1.0 + exp(-gr[96]));
+                    const double *gr = h1s + (size_t)(u - c0) * 4 * XS + lane;
+                    const double ig = 1.0 / (1.0 + exp(-gr[0])), fg = 1.0 / (1.0 + exp(-gr[XS]));
+                    const double gg = tanh(gr[2 * XS]), og = 1.0 / (1.0 + exp(-gr[3 * XS]));
                     const double cn = fg * sn_g[(H + u) * 32 + lane] + ig * gg;
                     sn_g[(H + u) * 32 + lane] = cn;
                     sn_g[u * 32 + lane] = og * tanh(cn);
@@ -1260,21 +1328,22 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
             }
             if (A.ctx) {
                 const double *cx = ctx_row(A, take, start, cur_t);
-                for (int k = w; k < A.ctx_dim; k += T4_WARPS) xs[k * 32 + lane] = cx[k];
+                for (int k = w; k < A.ctx_dim; k += T4_WARPS) xs[(size_t)k * XS + lane] = cx[k];
             }
-            for (int j = w; j < H; j += T4_WARPS) xs[(A.ctx_dim + j) * 32 + lane] = sn_g[j * 32 + lane];
+            for (int j = w; j < H; j += T4_WARPS) xs[(size_t)(A.ctx_dim + j) * XS + lane] = sn_g[j * 32 + lane];
+            for (int k = A.D + w; k < A.xrows; k += T4_WARPS) xs[(size_t)k * XS + lane] = 0.0;
         }
         __syncthreads();
         if (VALFS) {
             // value = value_net(value_vs_net(state)) on cat(value context row, state); value_stat.push(value)
             if (A.vctx) {
                 const double *cx = A.vctx + (ctx_row(A, take, start, cur_t) - A.ctx);
-                for (int k = w; k < A.ctx_dim; k += T4_WARPS) xs[k * 32 + lane] = cx[k];
+                for (int k = w; k < A.ctx_dim; k += T4_WARPS) xs[(size_t)k * XS + lane] = cx[k];
                 __syncthreads();
             }
             RolloutArgs V = A;
             V.W1t = A.vW1t; V.b1 = A.vb1; V.W2t = A.vW2t; V.b2 = A.vb2; V.W3t = A.vW3t; V.b3 = A.vb3; V.Ap = A.vAp;
-            t4_policy_forward<KC, CHUNK>(V, xs, h1s, stage, lane, w);
+            t4_policy_forward<CHUNK>(V, xs, h1s, lane, w);
             value = h1s[lane];
             vs_n += 1.0;
             vs_mean += (value - vs_mean) / vs_n;
@@ -1282,12 +1351,12 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
             __syncthreads();
             // the dense layers overwrote the input rows: rebuild the policy input
             const double *cx = ctx_row(A, take, start, cur_t);
-            for (int k = w; k < A.ctx_dim; k += T4_WARPS) xs[k * 32 + lane] = cx[k];
-            int s = 0;
-            for (int k = w; k < S; k += T4_WARPS, s++) xs[(A.ctx_dim + k) * 32 + lane] = st[s];
+            for (int k = w; k < A.ctx_dim; k += T4_WARPS) xs[(size_t)k * XS + lane] = cx[k];
+            stage_share(xs + (size_t)A.ctx_dim * XS, st);
+            for (int k = A.D + w; k < A.xrows; k += T4_WARPS) xs[(size_t)k * XS + lane] = 0.0;
             __syncthreads();
         }
-        t4_policy_forward<KC, CHUNK>(A, xs, h1s, stage, lane, w);
+        t4_policy_forward<CHUNK>(A, xs, h1s, lane, w);
         bool mean_flag = A.cfg.mean_action != 0;
         if (A.in.d_mean_flag) mean_flag = mean_flag || A.in.d_mean_flag[n] != 0;
         else if (A.cfg.noise_rate < 1.0) {
@@ -1295,9 +1364,8 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
             philox4x32(c, (uint32_t)A.cfg.seed, (uint32_t)(A.cfg.seed >> 32));
             mean_flag = mean_flag || (u01(c[0], c[1]) <= 1.0 - A.cfg.noise_rate);
         }
-        T4_FOR_OWN_DOFS(i, b) {
-            if (i < 6) continue;
-            const int a = i - 6;
+        // ---- sample (distributions.py / policy.py:12-15): a = mu + exp(log_std) eps, in place in the mean rows, all warps
+        for (int a = w; a < nu; a += T4_WARPS) {
             double z = 0.0;
             if (!mean_flag) {
                 if (A.in.d_eps) z = A.in.d_eps[n * nu + a];
@@ -1307,9 +1375,13 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
                     z = (a & 1) ? z1 : z0;
                 }
             }
-            const double act = h1s[a * 32 + lane] + exp(A.log_std[a]) * z;
-            tm_st1(x.a_ctrl(i), c_m.a_ref[i] + act * c_m.a_scale[i]);
-            if (live) A.out.d_actions[n * nu + a] = act;
+            h1s[(size_t)a * XS + lane] += exp(A.log_std[a]) * z;
+        }
+        __syncthreads();
+        write_rows(A.out.d_actions, h1s, nu, t);
+        T4_FOR_OWN_DOFS(i, b) {
+            if (i < 6) continue;
+            tm_st1(x.a_ctrl(i), c_m.a_ref[i] + h1s[(size_t)(i - 6) * XS + lane] * c_m.a_scale[i]);
         }
         __syncthreads();
         // ---- restore the aliased tree rows
@@ -1325,7 +1397,7 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
         __syncthreads();
         if (cw) {
             tm_wait_st();
-            for (int s = 0; s < c_m.frame_skip; s++) t4_substep(x);
+            t4_do_simulation(x, c_m.frame_skip);
         }
         __syncthreads();
         cur_t += 1;
@@ -1430,8 +1502,8 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
             if (w0) log_acc[EGP_LOG_NUM_NAN_RESETS] += 1.0;
         }
         const bool done = fail || end;
+        if (A.out.d_next_states) { int s = 0; for (int k = w; k < S; k += T4_WARPS, s++) pend[s] = nst[s]; }
         if (live) {
-            if (A.out.d_next_states) { int s = 0; for (int k = w; k < S; k += T4_WARPS, s++) A.out.d_next_states[n * S + k] = nst[s]; }
             if (w0) {
                 A.out.d_rewards[n] = rew;
                 A.out.d_masks[n] = (done || t == T - 1) ? 0.0 : 1.0;
@@ -1531,34 +1603,67 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
     if (live) {
         if (A.out.d_final_qpos) for (int k = w; k < nq; k += T4_WARPS) A.out.d_final_qpos[(size_t)env * nq + k] = x.at(O.q, k);
         if (A.out.d_final_qvel) for (int k = w; k < nv; k += T4_WARPS) A.out.d_final_qvel[(size_t)env * nv + k] = x.at(O.v, k);
-        if (A.out.d_logger && w0) {
-            double *Lg = A.out.d_logger;
-            atomicAdd(Lg + EGP_LOG_NUM_STEPS, log_acc[EGP_LOG_NUM_STEPS]);
-            atomicAdd(Lg + EGP_LOG_NUM_EPISODES, log_acc[EGP_LOG_NUM_EPISODES]);
-            atomicAdd(Lg + EGP_LOG_TOTAL_REWARD, log_acc[EGP_LOG_TOTAL_REWARD]);
-            atomicAdd(Lg + EGP_LOG_TOTAL_C_REWARD, log_acc[EGP_LOG_TOTAL_C_REWARD]);
-            atomicAdd(Lg + EGP_LOG_NUM_NAN_RESETS, log_acc[EGP_LOG_NUM_NAN_RESETS]);
-            if (A.cfg.eval_mode) atomicAdd(Lg + EGP_LOG_NUM_FAILSAFE_RESETS, log_acc[EGP_LOG_NUM_FAILSAFE_RESETS]);
-            for (int k = 0; k < 5; k++) atomicAdd(Lg + EGP_LOG_C_INFO + k, log_acc[EGP_LOG_C_INFO + k]);
-            auto amin = [](double *addr, double v) {
-                unsigned long long *a = (unsigned long long *)addr, old = *a, assumed;
-                do { assumed = old; if (__longlong_as_double(assumed) <= v) break;
-                     old = atomicCAS(a, assumed, __double_as_longlong(v)); } while (assumed != old);
-            };
-            auto amax = [](double *addr, double v) {
-                unsigned long long *a = (unsigned long long *)addr, old = *a, assumed;
-                do { assumed = old; if (__longlong_as_double(assumed) >= v) break;
-                     old = atomicCAS(a, assumed, __double_as_longlong(v)); } while (assumed != old);
-            };
-            amin(Lg + EGP_LOG_MIN_C_REWARD, log_acc[EGP_LOG_MIN_C_REWARD]);
-            amax(Lg + EGP_LOG_MAX_C_REWARD, log_acc[EGP_LOG_MAX_C_REWARD]);
-            amin(Lg + EGP_LOG_MIN_EPISODE_REWARD, log_acc[EGP_LOG_MIN_EPISODE_REWARD]);
-            amax(Lg + EGP_LOG_MAX_EPISODE_REWARD, log_acc[EGP_LOG_MAX_EPISODE_REWARD]);
+    }
+    if (A.out.d_next_states) {                              // next_state of the last step (tree rows are dead now)
+        __syncthreads();
+        stage_share(h1s, pend);
+        __syncthreads();
+        write_rows(A.out.d_next_states, h1s, S, T - 1);
+    }
+    // LoggerRL sums / extrema: fixed-order butterfly over the CTA's environments, one partial row per CTA, merged in CTA
+    // order by logger_merge_kernel - the same bits on every run (no floating-point atomics)
+    if (A.log_part && w0) {
+        if (!live) {
+            for (int k = 0; k < EGP_LOG_SIZE; k++) log_acc[k] = 0.0;
+            log_acc[EGP_LOG_MIN_C_REWARD] = INFINITY; log_acc[EGP_LOG_MAX_C_REWARD] = -INFINITY;
+            log_acc[EGP_LOG_MIN_EPISODE_REWARD] = INFINITY; log_acc[EGP_LOG_MAX_EPISODE_REWARD] = -INFINITY;
+        }
+#pragma unroll
+        for (int k = 0; k < EGP_LOG_SIZE; k++) {
+            double v = log_acc[k];
+            const bool mn = k == EGP_LOG_MIN_C_REWARD || k == EGP_LOG_MIN_EPISODE_REWARD;
+            const bool mx = k == EGP_LOG_MAX_C_REWARD || k == EGP_LOG_MAX_EPISODE_REWARD;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double u = __shfl_xor_sync(0xffffffffu, v, o);
+                v = mn ? fmin(v, u) : (mx ? fmax(v, u) : v + u);
+            }
+            if (lane == 0) A.log_part[(size_t)blockIdx.x * EGP_LOG_SIZE + k] = v;
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (w == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+}
+
+// d_logger[k] = ordered reduction of the per-CTA partial rows (sum; min / max for the extrema slots)
+__global__ void logger_merge_kernel(const double *__restrict__ part, int nblk, double *__restrict__ out) {
+    const int k = threadIdx.x;
+    if (k >= EGP_LOG_SIZE) return;
+    const bool mn = k == EGP_LOG_MIN_C_REWARD || k == EGP_LOG_MIN_EPISODE_REWARD;
+    const bool mx = k == EGP_LOG_MAX_C_REWARD || k == EGP_LOG_MAX_EPISODE_REWARD;
+    double v = mn ? INFINITY : (mx ? -INFINITY : 0.0);
+    for (int b = 0; b < nblk; b++) {
+        const double u = part[(size_t)b * EGP_LOG_SIZE + k];
+        v = mn ? fmin(v, u) : (mx ? fmax(v, u) : v + u);
+    }
+    out[k] = v;
+}
+
+// packs W [out][in] -> DMMA fragments Wf[outp / 8][K4][32]: element (nf, kc, lane) = W[8 nf + lane / 4][4 kc + lane % 4]
+// (zero padded both ways; outp a multiple of 16, K4 a multiple of 4), biases padded (T4 policy MLP)
+__global__ void pack_frag_kernel(const double *__restrict__ W, const double *__restrict__ b, int out, int in, int outp, int K4,
+                                 double *__restrict__ Wf, double *__restrict__ bp) {
+    const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long total = (long long)(outp / 8) * K4 * 32;
+    if (idx < total) {
+        const int lane = (int)(idx & 31);
+        const long long t = idx >> 5;
+        const int kc = (int)(t % K4), nf = (int)(t / K4);
+        const int j = 8 * nf + (lane >> 2), k = 4 * kc + (lane & 3);
+        Wf[idx] = (j < out && k < in) ? W[(size_t)j * in + k] : 0.0;
+    }
+    if (idx < outp) bp[idx] = idx < out ? b[idx] : 0.0;
 }
 
 // transposes W [out][in] -> Wt [in][outp] (zero padded), biases padded
@@ -1568,17 +1673,6 @@ __global__ void transpose_pad_kernel(const double *__restrict__ W, const double 
     if (idx < in * outp) {
         int k = idx / outp, j = idx % outp;
         Wt[idx] = j < out ? W[(size_t)j * in + k] : 0.0;
-    }
-    if (idx < outp) bp[idx] = idx < out ? b[idx] : 0.0;
-}
-
-// packs W [out][in] -> tiles Wp[out/8][inp][8] (zero padded both ways), biases padded (T4 MLP)
-__global__ void pack_tiles_kernel(const double *__restrict__ W, const double *__restrict__ b, int out, int in, int outp,
-                                  int inp, double *__restrict__ Wp, double *__restrict__ bp) {
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx < inp * outp) {
-        int jb = idx / (inp * JB), rem = idx % (inp * JB), k = rem / JB, jj = rem % JB, j = jb * JB + jj;
-        Wp[idx] = (j < out && k < in) ? W[(size_t)j * in + k] : 0.0;
     }
     if (idx < outp) bp[idx] = idx < out ? b[idx] : 0.0;
 }
@@ -1838,7 +1932,6 @@ int egp_rollout_f64(EgpModel *m, const EgpPolicyWeights *pol, const EgpRolloutCf
     cudaStream_t st = (cudaStream_t)stream;
     int rc = bind_model(m);
     if (rc) return rc;
-    auto pad = [](int x) { return (x + JB - 1) / JB * JB; };
     RolloutArgs A;
     memset(&A, 0, sizeof A);
     A.cfg = *cfg;
@@ -1852,49 +1945,49 @@ int egp_rollout_f64(EgpModel *m, const EgpPolicyWeights *pol, const EgpRolloutCf
     A.ctx_T = ctx_override ? in->ctx_T : 0;
     A.win_off = ctx_override ? in->d_win_off : nullptr;
     A.D = pol->in_dim; A.H1 = pol->h1; A.H2 = pol->h2; A.A = pol->out_dim;
-    A.H1p = pad(A.H1); A.H2p = pad(A.H2); A.Ap = pad(A.A);
-    int xrows = A.D > A.H2p ? A.D : A.H2p;
-    int hrows = A.H1p > A.Ap ? A.H1p : A.Ap;
-    if (snH) {                      // LSTM input rows [S + H] and one 64-unit gate chunk (256 rows)
-        if (hrows < 256) hrows = 256;
-        A.sn_H = snH;
-    }
     const int sn_in = snH ? S + snH : 0;
+    A.sn_H = snH;
     int blocks = (cfg->n_env + ENVS_PER_CTA - 1) / ENVS_PER_CTA;
-    // variant selection: T4 (4 warps per 32 envs, tree data in shared memory) when the model and the policy
-    // width fit, else the one-warp V1 kernel; EGP_ROLLOUT_VARIANT=1 forces V1 (A/B parity runs)
+    // variant selection: T4 (8 warps per 32 envs, tree data in shared memory, policy MLP on the FP64 tensor cores) when
+    // the model and the policy width fit, else the one-warp V1 kernel; EGP_ROLLOUT_VARIANT=1 forces V1 (A/B parity runs)
     T4Off O = t4_offsets(d);
-    // MLP shared-memory plan inside the alias window [O.ax, limit): input / hidden / weight-stage rows.
-    // Try (tile depth 64, full layers) -> (32, full) -> (32, chunked layer 2/3, second hidden layer never resident).
+    // T4 MLP plan inside the alias window [O.ax, limit): input rows xs [xrows][XS] + hidden rows h1s [hrows][XS], every
+    // width padded to 16 (one work item = 16 neurons; K = 4 x a multiple of 4 fragments).  Full layers, else the chunked
+    // layer-2/3 path in which the second hidden layer never exists in full.
+    auto pad16 = [](int x) { return (x + 15) / 16 * 16; };
     const int limit_rows = 227 * 1024 / 256;
     const char *force = getenv("EGP_ROLLOUT_VARIANT");
     bool use_t4 = false;
-    A.kc = 64; A.chunk23 = 0;
-    if (d.t4_ok && !(force && force[0] == '1') && A.Ap / JB <= T4_WARPS) {
-        const int plans[4][2] = {{64, 0}, {32, 0}, {32, 1}, {16, 1}};
-        for (int pi = 0; pi < 4 && !use_t4; pi++) {
-            int kc = plans[pi][0], ch = plans[pi][1];
-            int h2r = ch ? MLP_C2 : A.H2p;
-            int xr = A.D > h2r ? A.D : h2r;
-            if (xr < sn_in) xr = sn_in;
-            int need_rows = xr + hrows + T4_WARPS * kc * JB / 32;
+    A.chunk23 = 0;
+    if (d.t4_ok && !(force && force[0] == '1') && 2 * (pad16(A.A) / MLP_NT) <= T4_WARPS) {
+        const int H1p = pad16(A.H1), H2p = pad16(A.H2), Ap = pad16(A.A), Dp = pad16(A.D);
+        for (int pi = 0; pi < 4 && !use_t4; pi++) {        // (stride 36 | 32) x (full | chunked layer 2/3)
+            const int ch = pi & 1, xs_stride = pi < 2 ? XS_WIDE : 32;
+            int xr = Dp > (ch ? MLP_C2 : H2p) ? Dp : (ch ? MLP_C2 : H2p);
+            int hr = H1p > Ap ? H1p : Ap;
+            if (snH) {                  // LSTM input rows [S + H] and one 64-unit gate chunk (256 rows)
+                if (xr < pad16(sn_in)) xr = pad16(sn_in);
+                if (hr < 256) hr = 256;
+            }
+            const int need_rows = ((xr + hr) * xs_stride + 31) / 32;
             if (O.ax + need_rows <= limit_rows) {
-                use_t4 = true; A.kc = kc; A.chunk23 = ch;
+                use_t4 = true; A.chunk23 = ch; A.xrows = xr; A.hrows = hr; A.xs = xs_stride;
                 if (O.total - O.ax < need_rows) O.total = O.ax + need_rows;
             }
         }
     }
+    auto pad = [use_t4](int x) { return use_t4 ? (x + 15) / 16 * 16 : (x + JB - 1) / JB * JB; };
+    A.H1p = pad(A.H1); A.H2p = pad(A.H2); A.Ap = pad(A.A);
+    A.K1p = use_t4 ? pad(A.D) : A.D; A.K2p = use_t4 ? pad(A.H1) : A.H1; A.K3p = use_t4 ? pad(A.H2) : A.H2;
     size_t smem4 = sizeof(double) * 32 * (size_t)O.total;
-    const int kcv = A.kc;
-    auto padk = [kcv](int x) { return (x + kcv - 1) / kcv * kcv; };
-    A.K1p = use_t4 ? padk(A.D) : A.D; A.K2p = use_t4 ? padk(A.H1) : A.H1; A.K3p = use_t4 ? padk(A.H2) : A.H2;
     if (snH && !use_t4) { set_error("egp_rollout_f64: the state LSTM needs the T4 rollout variant (policy too wide?)"); return EGP_ESIZE; }
     const bool ev = cfg->eval_mode || (in && (in->d_fix_len || in->d_init_qpos || in->d_init_qvel)) || out->d_qpos_traj || out->d_qvel_traj;
     if (in && ((in->d_init_qpos == nullptr) != (in->d_init_qvel == nullptr))) { set_error("egp_rollout_f64: d_init_qpos / d_init_qvel come in pairs"); return EGP_EINVAL; }
     if (ev && !use_t4) { set_error("egp_rollout_f64: evaluation roll-outs (eval_mode / fix_len / qpos_traj) need the T4 rollout variant"); return EGP_ESIZE; }
     if (cfg->eval_mode && !(in && in->d_state_pred)) { set_error("egp_rollout_f64: eval_mode needs d_state_pred"); return EGP_EINVAL; }
     if ((out->d_qpos_traj == nullptr) != (out->d_qvel_traj == nullptr)) { set_error("egp_rollout_f64: d_qpos_traj / d_qvel_traj come in pairs"); return EGP_EINVAL; }
-    A.sn_Kp = snH ? padk(sn_in) : 0;
+    A.sn_Kp = snH ? pad(sn_in) : 0;
+    const int snN = snH ? pad(4 * snH) : 0;             // gate rows, padded
     const EgpPolicyWeights *vn = in ? in->value_net : nullptr;
     if (cfg->eval_mode == 2 && !vn) { set_error("egp_rollout_f64: eval_mode 2 ('valuefs') needs value_net"); return EGP_EINVAL; }
     if (vn) {
@@ -1908,8 +2001,9 @@ int egp_rollout_f64(EgpModel *m, const EgpPolicyWeights *pol, const EgpRolloutCf
         A.vAp = pad(1);
         A.vctx = in->d_vctx;
     }
+    const size_t log_elems = (size_t)blocks * EGP_LOG_SIZE;
     size_t need = (size_t)A.K1p * A.H1p + A.H1p + (size_t)A.K2p * A.H2p + A.H2p + (size_t)A.K3p * A.Ap + A.Ap +
-                  (size_t)A.sn_Kp * 4 * snH + 4 * snH;
+                  (size_t)A.sn_Kp * snN + snN + log_elems;
     const size_t vneed = vn ? (size_t)A.K1p * A.H1p + A.H1p + (size_t)A.K2p * A.H2p + A.H2p + (size_t)A.K3p * A.vAp + A.vAp : 0;
     need += vneed;
     if (need > m->wbuf_elems) {
@@ -1925,8 +2019,13 @@ int egp_rollout_f64(EgpModel *m, const EgpPolicyWeights *pol, const EgpRolloutCf
     double *b2 = w; w += A.H2p;
     double *W3t = w; w += (size_t)A.K3p * A.Ap;
     double *b3 = w; w += A.Ap;
-    double *snW = w; w += (size_t)A.sn_Kp * 4 * snH;
-    double *snb = w; w += 4 * snH;
+    double *snW = w; w += (size_t)A.sn_Kp * snN;
+    double *snb = w; w += snN;
+    double *logp = w; w += log_elems;
+    auto pack = [&](const double *W, const double *bsrc, int out_n, int in_n, int outp, int Kp, double *Wf, double *bp) {
+        const long long total = (long long)outp * Kp;       // = (outp / 8) * (Kp / 4) * 32
+        pack_frag_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(W, bsrc, out_n, in_n, outp, Kp / 4, Wf, bp);
+    };
     if (vn) {
         double *v1 = w; w += (size_t)A.K1p * A.H1p;
         double *vb1 = w; w += A.H1p;
@@ -1934,19 +2033,19 @@ int egp_rollout_f64(EgpModel *m, const EgpPolicyWeights *pol, const EgpRolloutCf
         double *vb2 = w; w += A.H2p;
         double *v3 = w; w += (size_t)A.K3p * A.vAp;
         double *vb3 = w;
-        pack_tiles_kernel<<<(A.K1p * A.H1p + 255) / 256, 256, 0, st>>>(vn->d_W1, vn->d_b1, A.H1, A.D, A.H1p, A.K1p, v1, vb1);
-        pack_tiles_kernel<<<(A.K2p * A.H2p + 255) / 256, 256, 0, st>>>(vn->d_W2, vn->d_b2, A.H2, A.H1, A.H2p, A.K2p, v2, vb2);
-        pack_tiles_kernel<<<(A.K3p * A.vAp + 255) / 256, 256, 0, st>>>(vn->d_W3, vn->d_b3, 1, A.H2, A.vAp, A.K3p, v3, vb3);
+        pack(vn->d_W1, vn->d_b1, A.H1, A.D, A.H1p, A.K1p, v1, vb1);
+        pack(vn->d_W2, vn->d_b2, A.H2, A.H1, A.H2p, A.K2p, v2, vb2);
+        pack(vn->d_W3, vn->d_b3, 1, A.H2, A.vAp, A.K3p, v3, vb3);
         A.vW1t = v1; A.vb1 = vb1; A.vW2t = v2; A.vb2 = vb2; A.vW3t = v3; A.vb3 = vb3;
     }
     if (snH) {
-        pack_tiles_kernel<<<(A.sn_Kp * 4 * snH + 255) / 256, 256, 0, st>>>(in->d_snet_W, in->d_snet_b, 4 * snH, sn_in, 4 * snH, A.sn_Kp, snW, snb);
+        pack(in->d_snet_W, in->d_snet_b, 4 * snH, sn_in, snN, A.sn_Kp, snW, snb);
         A.sn_Wp = snW; A.sn_b = snb; A.sn_state = in->d_snet_state;
     }
     if (use_t4) {
-        pack_tiles_kernel<<<(A.K1p * A.H1p + 255) / 256, 256, 0, st>>>(pol->d_W1, pol->d_b1, A.H1, A.D, A.H1p, A.K1p, W1t, b1);
-        pack_tiles_kernel<<<(A.K2p * A.H2p + 255) / 256, 256, 0, st>>>(pol->d_W2, pol->d_b2, A.H2, A.H1, A.H2p, A.K2p, W2t, b2);
-        pack_tiles_kernel<<<(A.K3p * A.Ap + 255) / 256, 256, 0, st>>>(pol->d_W3, pol->d_b3, A.A, A.H2, A.Ap, A.K3p, W3t, b3);
+        pack(pol->d_W1, pol->d_b1, A.H1, A.D, A.H1p, A.K1p, W1t, b1);
+        pack(pol->d_W2, pol->d_b2, A.H2, A.H1, A.H2p, A.K2p, W2t, b2);
+        pack(pol->d_W3, pol->d_b3, A.A, A.H2, A.Ap, A.K3p, W3t, b3);
     } else {
         transpose_pad_kernel<<<(A.D * A.H1p + 255) / 256, 256, 0, st>>>(pol->d_W1, pol->d_b1, A.H1, A.D, A.H1p, W1t, b1);
         transpose_pad_kernel<<<(A.H1 * A.H2p + 255) / 256, 256, 0, st>>>(pol->d_W2, pol->d_b2, A.H2, A.H1, A.H2p, W2t, b2);
@@ -1954,12 +2053,8 @@ int egp_rollout_f64(EgpModel *m, const EgpPolicyWeights *pol, const EgpRolloutCf
     }
     EGP_CHECK_LAUNCH("weight packing");
     A.W1t = W1t; A.b1 = b1; A.W2t = W2t; A.b2 = b2; A.W3t = W3t; A.b3 = b3; A.log_std = pol->d_log_std;
-    if (out->d_logger) {
-        double init[EGP_LOG_SIZE] = {0};
-        init[EGP_LOG_MIN_C_REWARD] = INFINITY; init[EGP_LOG_MAX_C_REWARD] = -INFINITY;
-        init[EGP_LOG_MIN_EPISODE_REWARD] = INFINITY; init[EGP_LOG_MAX_EPISODE_REWARD] = -INFINITY;
-        EGP_CUDA(cudaMemcpyAsync(out->d_logger, init, sizeof init, cudaMemcpyHostToDevice, st));
-    }
+    A.log_part = out->d_logger ? logp : nullptr;
+    int rc2 = EGP_OK;
     if (use_t4) {
         auto launch = [&](auto kern) -> int {
             EGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
@@ -1969,20 +2064,43 @@ int egp_rollout_f64(EgpModel *m, const EgpPolicyWeights *pol, const EgpRolloutCf
         };
         if (snH) {
             if (A.chunk23) { set_error("egp_rollout_f64: state LSTM with the chunked wide-policy plan is not supported"); return EGP_ESIZE; }
-            return A.kc == 64 ? launch(rollout_kernel_t4<64, false, true>) : launch(rollout_kernel_t4<32, false, true>);
+            rc2 = launch(rollout_kernel_t4<false, true>);
+        } else if (vn) rc2 = launch(rollout_kernel_t4<false, false, true>);
+        else if (!A.chunk23) rc2 = launch(rollout_kernel_t4<false, false>);
+        else rc2 = launch(rollout_kernel_t4<true, false>);
+    } else {
+        const int xrows = A.D > A.H2p ? A.D : A.H2p, hrows = A.H1p > A.Ap ? A.H1p : A.Ap;
+        size_t smem = sizeof(double) * ENVS_PER_CTA * ((size_t)xrows + hrows);
+        if (smem > 227 * 1024) { set_error("egp_rollout_f64: policy too wide for shared memory (%zu bytes)", smem); return EGP_ESIZE; }
+        if (out->d_logger) {            // the one-warp kernel accumulates with atomics
+            double init[EGP_LOG_SIZE] = {0};
+            init[EGP_LOG_MIN_C_REWARD] = INFINITY; init[EGP_LOG_MAX_C_REWARD] = -INFINITY;
+            init[EGP_LOG_MIN_EPISODE_REWARD] = INFINITY; init[EGP_LOG_MAX_EPISODE_REWARD] = -INFINITY;
+            EGP_CUDA(cudaMemcpyAsync(out->d_logger, init, sizeof init, cudaMemcpyHostToDevice, st));
         }
-        if (vn) return A.kc == 64 ? launch(rollout_kernel_t4<64, false, false, true>) : launch(rollout_kernel_t4<32, false, false, true>);
-        if (A.kc == 64) return launch(rollout_kernel_t4<64, false, false>);
-        if (!A.chunk23) return launch(rollout_kernel_t4<32, false, false>);
-        if (A.kc == 32) return launch(rollout_kernel_t4<32, true, false>);
-        return launch(rollout_kernel_t4<16, true, false>);
+        EGP_CUDA(cudaFuncSetAttribute(rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rollout_kernel<<<blocks, ENVS_PER_CTA, smem, st>>>(A);
+        EGP_CHECK_LAUNCH("rollout_kernel");
     }
-    size_t smem = sizeof(double) * ENVS_PER_CTA * ((size_t)xrows + hrows);
-    if (smem > 227 * 1024) { set_error("egp_rollout_f64: policy too wide for shared memory (%zu bytes)", smem); return EGP_ESIZE; }
-    EGP_CUDA(cudaFuncSetAttribute(rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    rollout_kernel<<<blocks, ENVS_PER_CTA, smem, st>>>(A);
-    EGP_CHECK_LAUNCH("rollout_kernel");
+    if (rc2 != EGP_OK) return rc2;
+    if (out->d_logger && use_t4) {
+        logger_merge_kernel<<<1, 32, 0, st>>>(logp, blocks, out->d_logger);
+        EGP_CHECK_LAUNCH("logger_merge_kernel");
+    }
     return EGP_OK;
 }
+
+#ifdef EGP_T4_CLK
+int egp_debug_t4_clk(unsigned long long *out8) {
+    EGP_CUDA(cudaDeviceSynchronize());
+    EGP_CUDA(cudaMemcpyFromSymbol(out8, g_t4_clk, sizeof(unsigned long long) * 8));
+    EGP_CUDA(cudaMemcpyFromSymbol(out8 + 8, g_t4_clk2, sizeof(unsigned long long) * 16));
+    unsigned long long z2[16] = {0};
+    EGP_CUDA(cudaMemcpyToSymbol(g_t4_clk2, z2, sizeof z2));
+    unsigned long long z[8] = {0};
+    EGP_CUDA(cudaMemcpyToSymbol(g_t4_clk, z, sizeof z));
+    return EGP_OK;
+}
+#endif
 
 }  // extern "C"

@@ -33,6 +33,10 @@
 #define EGP_CONST_M egp::h_m
 #endif
 
+#ifndef EGP_CLK_MARK
+#define EGP_CLK_MARK(slot)
+#endif
+
 namespace egp {
 
 constexpr int MAXB = EGP_MAX_BODY;
@@ -40,8 +44,17 @@ constexpr int MAXV = EGP_MAX_DOF;
 constexpr int MAXC = EGP_MAX_CHAIN;
 constexpr int T4_CW = 4;                    // chain warps (own the tree sweeps)
 
+constexpr int R_COLS_HOST = 56;              // columns of one body's scratch record (see the sweeps below)
+
 // body kinds of the block sweeps
 enum { BK_ROOT = 0, BK_XYZ = 1, BK_X = 2, BK_Y = 3, BK_Z = 4, BK_OTHER = 5 };
+
+// per-body constants of the block sweeps, contiguous so that a body-step fetches them with a few wide constant loads
+struct BodyK {
+    int da, qa, nd, kind, rec, xp_slot, pad0, pad1;         // dof / qpos address, #dofs, BK_*, scratch-record column, xp row slot
+    double pos[3], anchor[3], ipos[3], inertia[6], mass;
+    double arm[3], armkd[3], kp[3], kd[3], tlim[3];         // per dof of the body: armature, armature + kd h, gains, torque limit
+};
 
 struct DevModel {
     int nq, nv, nu, nbody, nchain, frame_skip, head_body, v_ord, decay;
@@ -59,9 +72,10 @@ struct DevModel {
     int lvl_chain[MAXC][T4_CW];                                               // chain of (level, warp) or -1
     int nlevel, nparent, max_sib, t4_ok;
     int body_xp_slot[MAXB], ee_xp_slot[EGP_NEE], head_xp_slot;                // rows of the shared body-position record
-    // TMEM scratch layout (T4): index of a dof / body among those owned by the same warp, column bases (32-bit units)
-    int dof_slot[MAXV], body_slot[MAXB];
-    int tm_ctrl, tm_y, tm_tau, tm_c, tm_cin, tm_fb, tm_cols;
+    // scratch (Tensor Memory) layout: one 56-column record per body, numbered among the bodies owned by the same warp;
+    // column of a dof's ctrl / tau / C entry (-1 where the root has none)
+    int body_slot[MAXB], dof_col_ctrl[MAXV], dof_col_tau[MAXV], dof_col_c[MAXV], tm_cols;
+    BodyK bk[MAXB];
     double w_p, w_v, w_e, w_rp, w_rv, k_p, k_v, k_e, k_rh, k_rq, k_rl, k_ra;
 };
 
@@ -151,10 +165,11 @@ template <> struct SymInv<3> {
 //   rhs[j]    right-hand side of dof j (tau - C for forward dynamics, -C - kp e - kd v for stable PD)
 // Updates the carry (I^A -= W U^T, p^A += W u) and returns W = U D^-1 (for the forward sweep) and y = D^-1 u.
 // SKIND: 0 general S = [ax; lin], 1 angular only S = [ax; 0] (root rotation), 2 S = [0; e_j] (root translation).
-template <int ND, int SKIND, bool LAST>
-EGP_HD void blk_backward(Bwd &w, const double (&S)[ND][6], const double (&diag)[ND], const double (&rhs)[ND],
-                         double (&W)[ND][6], double (&y)[ND]) {
-    double U[ND][6], D[ND][ND], Di[ND][ND], u[ND];
+// phase A: U = I^A S, D = S^T U + diag, u = rhs - S^T p^A, D^-1
+template <int ND, int SKIND>
+EGP_HD void blk_backward_a(const Bwd &w, const double (&S)[ND][6], const double (&diag)[ND], const double (&rhs)[ND],
+                           double (&U)[ND][6], double (&Di)[ND][ND], double (&u)[ND]) {
+    double D[ND][ND];
 #pragma unroll
     for (int j = 0; j < ND; j++) {
 #pragma unroll
@@ -183,34 +198,45 @@ EGP_HD void blk_backward(Bwd &w, const double (&S)[ND][6], const double (&diag)[
         else u[j] = rhs[j] - dot6(S[j], w.pA);
     }
     SymInv<ND>::run(D, Di);
+}
+
+// phase B: W = U D^-1, y = D^-1 u, carry update I^A -= W U^T, p^A += W u (skipped at the root: nothing above it).
+// W is produced one row (r) at a time - stored through `put(j, r, value)` and folded into row r of the carry - so that
+// only ND of its 6 ND entries are live at any moment.
+template <int ND, bool LAST, class PUT>
+EGP_HD void blk_backward_b(Bwd &w, const double (&U)[ND][6], const double (&Di)[ND][ND], const double (&u)[ND],
+                           double (&y)[ND], PUT put) {
 #pragma unroll
     for (int j = 0; j < ND; j++) {
         double t = 0.0;
 #pragma unroll
         for (int k = 0; k < ND; k++) t += Di[j][k] * u[k];
         y[j] = t;
+    }
 #pragma unroll
-        for (int r = 0; r < 6; r++) {
+    for (int r = 0; r < 6; r++) {
+        double Wr[ND];
+#pragma unroll
+        for (int j = 0; j < ND; j++) {
             double s = 0.0;
 #pragma unroll
             for (int k = 0; k < ND; k++) s += U[k][r] * Di[k][j];
-            W[j][r] = s;
+            Wr[j] = s;
+            put(j, r, s);
         }
-    }
-    if (LAST) return;           // nothing above the root: the reduced carry is never read
+        if (!LAST) {
 #pragma unroll
-    for (int r = 0; r < 6; r++) {
+            for (int c = r; c < 6; c++) {
+                double t = w.IA[sx(r, c)];
 #pragma unroll
-        for (int c = r; c < 6; c++) {
-            double t = w.IA[sx(r, c)];
+                for (int j = 0; j < ND; j++) t -= Wr[j] * U[j][c];
+                w.IA[sx(r, c)] = t;
+            }
+            double t = w.pA[r];
 #pragma unroll
-            for (int j = 0; j < ND; j++) t -= W[j][r] * U[j][c];
-            w.IA[sx(r, c)] = t;
+            for (int j = 0; j < ND; j++) t += Wr[j] * u[j];
+            w.pA[r] = t;
         }
-        double t = w.pA[r];
-#pragma unroll
-        for (int j = 0; j < ND; j++) t += W[j][r] * u[j];
-        w.pA[r] = t;
     }
 }
 
@@ -226,13 +252,35 @@ EGP_HD void add_body_inertia(Bwd &w, const double *ci) {
 
 // ------------------------------------------------------------------------------------------------
 // Sweeps over one (level, warp) chain.  X is the storage context:
-//   double &at(int row_off, int idx)          shared row [row][env] of this lane's environment
-//   tld1/tld2/tld3 ... tst1/tst3 ...          per-thread scratch (Tensor Memory on the device), column = 32-bit unit
-//   o                                         T4Off row offsets
+//   double &at(int row_off, int idx)            shared row [row][env] of this lane's environment
+//   tld_issue<NR>(col, int (&r)[NR]) / tld_wait  per-thread scratch (Tensor Memory on the device): asynchronous load of NR
+//                                               32-bit columns, complete after the matching tld_wait; unpack(r, k) = double k
+//   tst<N>(col, const double *)                 scratch store of N doubles
+//   o                                           T4Off row offsets
 // MODE of the backward sweep: 0 forward dynamics (bias C = S.F stored, rhs = tau - C, pivots + armature),
 //                             1 stable PD (rhs = -C - kp e - kd v from the current q, v and the stored bias, pivots + kd h).
 // MODE of the forward sweep:  1 [PD accel -> clipped torque] on the OLD tree rows, then kinematics refresh;
 //                             0 forward-dynamics accel + semi-implicit Euler; 2 kinematics refresh only (sim.forward()).
+//
+// Scheduling: the only values that really recur along a chain are the carries (I^A, p^A, F backward; frame, velocity,
+// acceleration forward).  Everything else a body-step reads - its scratch record, its shared rows, its constants - does
+// not depend on the carry, so every sweep is software-pipelined BY HAND: the operands of body b+1 are requested before the
+// arithmetic of body b starts (one body ahead: what fits in registers next to the carry).  The compiler cannot do this
+// itself: the loads of b+1 would have to move above the stores of b into the same shared array.
+//
+// Scratch record of a body (56 columns = 28 doubles, contiguous so that one access fetches what a sweep needs):
+//   hinge body: fb 6 | cin 10 | ctrl 3 | C 3 | tau 3 | y 3        root: fb 6 | cin 10 | C 6 | y 6
+// cross-body operand prefetch per sweep (register pressure decides: see DESIGN.md)
+#ifndef EGP_PF_BWD
+#define EGP_PF_BWD 0
+#endif
+#ifndef EGP_PF_FWD1
+#define EGP_PF_FWD1 1
+#endif
+#ifndef EGP_PF_FWD0
+#define EGP_PF_FWD0 0
+#endif
+constexpr int R_FB = 0, R_CIN = 12, R_CTRL = 32, R_C = 38, R_TAU = 44, R_Y = 50, R_ROOT_C = 32, R_ROOT_Y = 44, R_COLS = 56;
 
 template <class X>
 EGP_HD void t5_bwd_gather(const X &x, int c, Bwd &w) {
@@ -252,117 +300,153 @@ EGP_HD void t5_bwd_gather(const X &x, int c, Bwd &w) {
     }
 }
 
-// hinge body with ND joints through one anchor
+// operands of one backward body-step (hinge body), requested while the previous body-step finishes
+struct BwdIn {
+    int da, nd, rec;
+    int b;
+    double kp[3], g[3];                 // stable PD: kp and g = kp q + kd v (rhs = kp ctrl - g - C)
+    double ax[3][3], anc[3];
+    int tm[32], tmt[8];                 // MODE 0: fb | cin, tau (+1).  MODE 1: cin | ctrl | C
+};
+
+// the scratch record (longest latency) is requested between the two phases of the previous body-step, the shared rows
+// (shorter latency, 30 more registers) when its carry update is done
+template <class X>
+EGP_HD void t5_bwd_load_tm(const X &x, int b, const int MODE, BwdIn &in) {
+    const BodyK &K = EGP_CONST_M.bk[b];
+    in.b = b; in.da = K.da; in.nd = K.nd; in.rec = K.rec;
+    if (MODE == 0) { x.template tld_issue<32>(K.rec + R_FB, in.tm); x.template tld_issue<8>(K.rec + R_TAU, in.tmt); }
+    else x.template tld_issue<32>(K.rec + R_CIN, in.tm);
+}
+
+template <class X>
+EGP_HD void t5_bwd_load_rows(const X &x, int b, const int MODE, BwdIn &in) {
+    const BodyK &K = EGP_CONST_M.bk[b];
+#pragma unroll
+    for (int r = 0; r < 3; r++) in.anc[r] = x.at(x.o.anc, 3 * b + r);
+    // branch-free: a 1-dof body re-reads its dof 0 for j = 1, 2 (never used); every field is written on every path, which
+    // keeps the operand record in registers (a partially written aggregate would be demoted to local memory)
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        const int jj = j < K.nd ? j : 0, i = K.da + jj;
+#pragma unroll
+        for (int r = 0; r < 3; r++) in.ax[j][r] = x.at(x.o.ax, 3 * i + r);
+        if (MODE == 1) { in.kp[j] = K.kp[jj]; in.g[j] = K.kp[jj] * x.at(x.o.q, i + 1) + K.kd[jj] * x.at(x.o.v, i); }
+    }
+}
+
+// one hinge body; `in` holds this body's operands on entry and (next >= 0) the next body's on exit: they are requested
+// between the two phases of the block elimination, when this body's own operands are dead and the carry update
+// (the longest stretch of arithmetic that needs no memory) is about to start
 template <int ND, class X>
-EGP_HD void t5_bwd_body(const X &x, Bwd &w, int b, const int MODE) {
-    const DevModel &M = EGP_CONST_M;
-    const int da = M.body_dofadr[b], sl = M.dof_slot[da];
-    double S[ND][6], diag[ND], rhs[ND], W[ND][6], y[ND];
-    const double an[3] = {x.at(x.o.anc, 3 * b), x.at(x.o.anc, 3 * b + 1), x.at(x.o.anc, 3 * b + 2)};
+EGP_HD void t5_bwd_body(const X &x, Bwd &w, BwdIn &in, const int MODE, const int next) {
+    const int da = in.da, rec = in.rec;
+    double ci[10], S[ND][6], diag[ND], rhs[ND], y[ND], U[ND][6], Di[ND][ND], u[ND];
+    if (MODE == 0) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) w.F[k] += X::unpack(in.tm, k);
+#pragma unroll
+        for (int k = 0; k < 10; k++) ci[k] = X::unpack(in.tm, 6 + k);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 10; k++) ci[k] = X::unpack(in.tm, k);
+    }
+    add_body_inertia(w, ci);
 #pragma unroll
     for (int j = 0; j < ND; j++) {
-        const int i = da + j;
-        S[j][0] = x.at(x.o.ax, 3 * i); S[j][1] = x.at(x.o.ax, 3 * i + 1); S[j][2] = x.at(x.o.ax, 3 * i + 2);
-        cross3(an, S[j], S[j] + 3);
-        diag[j] = M.dof_arm[i] + (MODE == 1 ? M.kd[i] * M.h : 0.0);
+        S[j][0] = in.ax[j][0]; S[j][1] = in.ax[j][1]; S[j][2] = in.ax[j][2];
+        cross3(in.anc, S[j], S[j] + 3);
+        diag[j] = MODE == 1 ? EGP_CONST_M.bk[in.b].armkd[j] : EGP_CONST_M.bk[in.b].arm[j];
     }
     if (MODE == 0) {
-        double tau[ND], C[ND];
-        x.template tld<ND>(M.tm_tau + 2 * sl, tau);
+        double C[ND];
 #pragma unroll
-        for (int j = 0; j < ND; j++) { C[j] = dot6(S[j], w.F); rhs[j] = tau[j] - C[j]; }
-        x.template tst<ND>(M.tm_c + 2 * sl, C);
+        for (int j = 0; j < ND; j++) { C[j] = dot6(S[j], w.F); rhs[j] = X::unpack(in.tmt, j) - C[j]; }
+        x.template tst<ND>(rec + R_C, C);
     } else {
-        double C[ND], ctrl[ND];
-        x.template tld<ND>(M.tm_c + 2 * sl, C);
-        x.template tld<ND>(M.tm_ctrl + 2 * sl, ctrl);
 #pragma unroll
-        for (int j = 0; j < ND; j++) {
-            const int i = da + j;
-            const double eq = x.at(x.o.q, i + 1) - ctrl[j];
-            rhs[j] = -C[j] - M.kp[i] * eq - M.kd[i] * x.at(x.o.v, i);
-        }
+        for (int j = 0; j < ND; j++) rhs[j] = in.kp[j] * X::unpack(in.tm, 10 + j) - in.g[j] - X::unpack(in.tm, 13 + j);
     }
-    blk_backward<ND, 0, false>(w, S, diag, rhs, W, y);
-    x.template tst<ND>(M.tm_y + 2 * sl, y);
-#pragma unroll
-    for (int j = 0; j < ND; j++)
-#pragma unroll
-        for (int r = 0; r < 6; r++) x.at(x.o.U, 6 * (da + j) + r) = W[j][r];
+    blk_backward_a<ND, 0>(w, S, diag, rhs, U, Di, u);
+    if (EGP_PF_BWD && next >= 0) t5_bwd_load_tm(x, next, MODE, in);
+    blk_backward_b<ND, false>(w, U, Di, u, y, [&](int j, int r, double v) { x.at(x.o.U, 6 * (da + j) + r) = v; });
+    x.template tst<ND>(rec + R_Y, y);
+    if (EGP_PF_BWD == 1 && next >= 0) t5_bwd_load_rows(x, next, MODE, in);
 }
 
 // free-joint root: rotational block (dofs 3..5, S = [R e_k; 0]) then translational block (dofs 0..2, S = [0; e_k]);
 // no gains, no armature, no actuation on the root (humanoid_v1.py:137-140)
 template <class X>
 EGP_HD void t5_bwd_root(const X &x, Bwd &w, int b, const int MODE) {
-    const DevModel &M = EGP_CONST_M;
-    const int da = M.body_dofadr[b], sl = M.dof_slot[da];
-    double W[3][6], y[3], rhs[3], diag[3] = {M.dof_arm[da + 3], M.dof_arm[da + 4], M.dof_arm[da + 5]};
+    const BodyK &K = EGP_CONST_M.bk[b];
+    const int da = K.da, rec = K.rec;
+    int tm[32], tmc[16];
+    x.template tld_issue<32>(rec + R_FB, tm);
+    if (MODE == 1) x.template tld_issue<16>(rec + R_ROOT_C, tmc);
+    double S[3][6];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        const int i = da + 3 + j;
+        S[j][0] = x.at(x.o.ax, 3 * i); S[j][1] = x.at(x.o.ax, 3 * i + 1); S[j][2] = x.at(x.o.ax, 3 * i + 2);
+        S[j][3] = S[j][4] = S[j][5] = 0.0;
+    }
+    x.template tld_wait<32>(tm);
+    if (MODE == 1) x.template tld_wait<16>(tmc);
+    double ci[10];
+#pragma unroll
+    for (int k = 0; k < 10; k++) ci[k] = X::unpack(tm, 6 + k);
+    add_body_inertia(w, ci);
+    if (MODE == 0) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) w.F[k] += X::unpack(tm, k);
+    }
+    double y[6], C[6], rhs[3], diag[3] = {K.arm[0], K.arm[1], K.arm[2]};   // free joint: armature of the 6 dofs is one value
     {
-        double S[3][6];
 #pragma unroll
         for (int j = 0; j < 3; j++) {
-            const int i = da + 3 + j;
-            S[j][0] = x.at(x.o.ax, 3 * i); S[j][1] = x.at(x.o.ax, 3 * i + 1); S[j][2] = x.at(x.o.ax, 3 * i + 2);
-            S[j][3] = S[j][4] = S[j][5] = 0.0;
+            C[3 + j] = MODE == 0 ? dot3(S[j], w.F) : X::unpack(tmc, 3 + j);
+            rhs[j] = -C[3 + j];
         }
-        double C[3];
-        if (MODE == 0) {
-#pragma unroll
-            for (int j = 0; j < 3; j++) { C[j] = dot3(S[j], w.F); rhs[j] = -C[j]; }
-            x.template tst<3>(M.tm_c + 2 * (sl + 3), C);
-        } else {
-            x.template tld<3>(M.tm_c + 2 * (sl + 3), C);
-#pragma unroll
-            for (int j = 0; j < 3; j++) rhs[j] = -C[j];
-        }
-        blk_backward<3, 1, false>(w, S, diag, rhs, W, y);
-        x.template tst<3>(M.tm_y + 2 * (sl + 3), y);
-#pragma unroll
-        for (int j = 0; j < 3; j++)
-#pragma unroll
-            for (int r = 0; r < 6; r++) x.at(x.o.U, 6 * (da + 3 + j) + r) = W[j][r];
+        double yb[3], U[3][6], Di[3][3], u[3];
+        blk_backward_a<3, 1>(w, S, diag, rhs, U, Di, u);
+        blk_backward_b<3, false>(w, U, Di, u, yb, [&](int j, int r, double v) { x.at(x.o.U, 6 * (da + 3 + j) + r) = v; });
+        y[3] = yb[0]; y[4] = yb[1]; y[5] = yb[2];
     }
     {
-        double S[3][6] = {};
-        double C[3];
-        diag[0] = M.dof_arm[da]; diag[1] = M.dof_arm[da + 1]; diag[2] = M.dof_arm[da + 2];
-        if (MODE == 0) {
+        double Sz[3][6] = {};
 #pragma unroll
-            for (int j = 0; j < 3; j++) { C[j] = w.F[3 + j]; rhs[j] = -C[j]; }
-            x.template tst<3>(M.tm_c + 2 * sl, C);
-        } else {
-            x.template tld<3>(M.tm_c + 2 * sl, C);
-#pragma unroll
-            for (int j = 0; j < 3; j++) rhs[j] = -C[j];
+        for (int j = 0; j < 3; j++) {
+            C[j] = MODE == 0 ? w.F[3 + j] : X::unpack(tmc, j);
+            rhs[j] = -C[j];
         }
-        blk_backward<3, 2, true>(w, S, diag, rhs, W, y);
-        x.template tst<3>(M.tm_y + 2 * sl, y);
-#pragma unroll
-        for (int j = 0; j < 3; j++)
-#pragma unroll
-            for (int r = 0; r < 6; r++) x.at(x.o.U, 6 * (da + j) + r) = W[j][r];
+        double yb[3], U[3][6], Di[3][3], u[3];
+        blk_backward_a<3, 2>(w, Sz, diag, rhs, U, Di, u);
+        blk_backward_b<3, true>(w, U, Di, u, yb, [&](int j, int r, double v) { x.at(x.o.U, 6 * (da + j) + r) = v; });
+        y[0] = yb[0]; y[1] = yb[1]; y[2] = yb[2];
     }
+    if (MODE == 0) x.template tst<6>(rec + R_ROOT_C, C);
+    x.template tst<6>(rec + R_ROOT_Y, y);
 }
 
 template <class X>
 EGP_HD void t5_bwd_chain(const X &x, int c, Bwd &w, const int MODE) {
     const DevModel &M = EGP_CONST_M;
-    for (int b = M.chain_hi[c]; b >= M.chain_lo[c]; b--) {
-        double ci[10];
-        x.ld_cin(b, ci);
-        add_body_inertia(w, ci);
-        if (MODE == 0) {
-            double fbv[6];
-            x.ld_fb(b, fbv);
-#pragma unroll
-            for (int k = 0; k < 6; k++) w.F[k] += fbv[k];
-        }
-        const int kind = M.body_kind[b];
-        if (kind == BK_XYZ) t5_bwd_body<3>(x, w, b, MODE);
-        else if (kind == BK_ROOT) t5_bwd_root(x, w, b, MODE);
-        else t5_bwd_body<1>(x, w, b, MODE);
+    const int hi = M.chain_hi[c], lo = M.chain_lo[c];
+    const bool has_root = M.bk[lo].kind == BK_ROOT;
+    const int lo_h = has_root ? lo + 1 : lo;            // hinge bodies [lo_h, hi]
+    BwdIn in;
+    if (EGP_PF_BWD && hi >= lo_h) { t5_bwd_load_tm(x, hi, MODE, in); if (EGP_PF_BWD == 1) t5_bwd_load_rows(x, hi, MODE, in); }
+#pragma unroll 1
+    for (int b = hi; b >= lo_h; b--) {
+        if (!EGP_PF_BWD) t5_bwd_load_tm(x, b, MODE, in);       // all operands of the body requested at once
+        if (EGP_PF_BWD != 1) t5_bwd_load_rows(x, b, MODE, in);
+        x.template tld_wait<32>(in.tm);
+        if (MODE == 0) x.template tld_wait<8>(in.tmt);
+        const int next = b > lo_h ? b - 1 : -1;
+        if (in.nd == 3) t5_bwd_body<3>(x, w, in, MODE, next);
+        else t5_bwd_body<1>(x, w, in, MODE, next);
     }
+    if (has_root) t5_bwd_root(x, w, lo, MODE);
     x.twait_st();
     if (M.chain_parent[c] >= 0) {
         const int base = x.o.jb + 33 * M.chain_cslot[c];
@@ -373,26 +457,59 @@ EGP_HD void t5_bwd_chain(const X &x, int c, Bwd &w, const int MODE) {
     }
 }
 
-// ---- forward sweep pieces ---------------------------------------------------------------------------
-// solve part of a hinge body on the rows currently in storage: x = y - W^T a, a += S x, then torque (MODE 1) or
-// semi-implicit Euler (MODE 0)
+// ---- forward sweep ---------------------------------------------------------------------------------
+// operands of one forward body-step (hinge body), requested while the previous body-step finishes
+template <int MODE>
+struct FwdIn {
+    int b, da, qa, nd, kind, rec, xp_slot;
+    double W[3][6], ax[3][3], anc[3];       // solve part: rows currently in storage (the OLD tree rows for MODE 1)
+    double q[3], v[3];
+    double sn[3], cs[3];                    // kinematics part: sin / cos of the joint angles
+    int tmy[8], tmc[8];                     // y (solve), ctrl (MODE 1)
+};
+
+template <int MODE, class X>
+EGP_HD void t5_fwd_load(const X &x, int b, FwdIn<MODE> &in) {
+    const BodyK &K = EGP_CONST_M.bk[b];
+    in.b = b; in.da = K.da; in.qa = K.qa; in.nd = K.nd; in.kind = K.kind; in.rec = K.rec; in.xp_slot = K.xp_slot;
+    if (MODE != 2) x.template tld_issue<8>(K.rec + R_Y - 2, in.tmy);         // tau[2] | y
+    if (MODE == 1) x.template tld_issue<8>(K.rec + R_CTRL, in.tmc);          // ctrl | C[0]
+    if (MODE != 2) {
+#pragma unroll
+        for (int r = 0; r < 3; r++) in.anc[r] = x.at(x.o.anc, 3 * b + r);
+    }
+    // branch-free (see t5_bwd_load): a 1-dof body re-reads its dof 0 for j = 1, 2
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        const int jj = j < K.nd ? j : 0, i = K.da + jj;
+        if (MODE != 2) {
+#pragma unroll
+            for (int r = 0; r < 6; r++) in.W[j][r] = x.at(x.o.U, 6 * i + r);
+#pragma unroll
+            for (int r = 0; r < 3; r++) in.ax[j][r] = x.at(x.o.ax, 3 * i + r);
+        }
+        in.v[j] = x.at(x.o.v, i);
+        in.q[j] = x.at(x.o.q, K.qa + jj);
+        if (MODE != 0) sincos(in.q[j], &in.sn[j], &in.cs[j]);
+    }
+}
+
+// what the kinematics part of a body-step keeps of its operands while the next body's are being requested
+struct KinIn {
+    int b, da, rec, xp_slot;
+    double v[3], sn[3], cs[3];
+};
+
+// solve part of a hinge body: x = y - W^T a, a += S x, then torque (MODE 1) or semi-implicit Euler (MODE 0)
 template <int ND, int MODE, class X>
-EGP_HD void t5_fwd_solve_body(const X &x, double *a, int b) {
-    const DevModel &M = EGP_CONST_M;
-    const int da = M.body_dofadr[b], sl = M.dof_slot[da];
-    const double h = M.h;
-    const double an[3] = {x.at(x.o.anc, 3 * b), x.at(x.o.anc, 3 * b + 1), x.at(x.o.anc, 3 * b + 2)};
-    double y[ND], xs[ND], S[ND][6];
-    x.template tld<ND>(M.tm_y + 2 * sl, y);
+EGP_HD void t5_fwd_solve_body(const X &x, double *a, const FwdIn<MODE> &in) {
+    const double h = EGP_CONST_M.h;
+    double xs[ND], S[ND][6];
 #pragma unroll
     for (int j = 0; j < ND; j++) {
-        const int i = da + j;
-        double Wj[6];
-#pragma unroll
-        for (int r = 0; r < 6; r++) Wj[r] = x.at(x.o.U, 6 * i + r);
-        xs[j] = y[j] - dot6(Wj, a);
-        S[j][0] = x.at(x.o.ax, 3 * i); S[j][1] = x.at(x.o.ax, 3 * i + 1); S[j][2] = x.at(x.o.ax, 3 * i + 2);
-        cross3(an, S[j], S[j] + 3);
+        xs[j] = X::unpack(in.tmy, 1 + j) - dot6(in.W[j], a);
+        S[j][0] = in.ax[j][0]; S[j][1] = in.ax[j][1]; S[j][2] = in.ax[j][2];
+        cross3(in.anc, S[j], S[j] + 3);
     }
 #pragma unroll
     for (int r = 0; r < 6; r++) {
@@ -402,59 +519,54 @@ EGP_HD void t5_fwd_solve_body(const X &x, double *a, int b) {
         a[r] = t;
     }
     if (MODE == 1) {                // torque = clip(-kp e - kd (v + x h))  (humanoid_v1.py:152-155,172)
-        double ctrl[ND], tq[ND];
-        x.template tld<ND>(M.tm_ctrl + 2 * sl, ctrl);
+        double tq[ND];
 #pragma unroll
         for (int j = 0; j < ND; j++) {
-            const int i = da + j;
-            const double eq = x.at(x.o.q, i + 1) - ctrl[j];
-            double t = -M.kp[i] * eq - M.kd[i] * (x.at(x.o.v, i) + xs[j] * h);
-            const double lim = M.tlim[i];
+            const double eq = in.q[j] - X::unpack(in.tmc, j);
+            const BodyK &K = EGP_CONST_M.bk[in.b];
+            const double t = -K.kp[j] * eq - K.kd[j] * (in.v[j] + xs[j] * h);
+            const double lim = K.tlim[j];
             tq[j] = t < -lim ? -lim : (t > lim ? lim : t);
         }
-        x.template tst<ND>(M.tm_tau + 2 * sl, tq);
+        x.template tst<ND>(in.rec + R_TAU, tq);
     } else {
 #pragma unroll
         for (int j = 0; j < ND; j++) {
-            const int i = da + j;
-            const double vn = x.at(x.o.v, i) + h * xs[j];
-            x.at(x.o.v, i) = vn;
-            x.at(x.o.q, i + 1) += h * vn;
+            const double vn = in.v[j] + h * xs[j];
+            x.at(x.o.v, in.da + j) = vn;
+            x.at(x.o.q, in.qa + j) = in.q[j] + h * vn;
         }
     }
 }
 
 template <int MODE, class X>
 EGP_HD void t5_fwd_solve_root(const X &x, double *a, int b) {
-    const DevModel &M = EGP_CONST_M;
-    const int da = M.body_dofadr[b], sl = M.dof_slot[da], qa = M.body_qposadr[b];
-    const double h = M.h;
-    double y[6], xs[6];
-    x.template tld<3>(M.tm_y + 2 * sl, y);
-    x.template tld<3>(M.tm_y + 2 * (sl + 3), y + 3);
+    const BodyK &K = EGP_CONST_M.bk[b];
+    const int da = K.da, qa = K.qa;
+    const double h = EGP_CONST_M.h;
+    int tmy[16];
+    x.template tld_issue<16>(K.rec + R_ROOT_Y - 4, tmy);       // C[4], C[5] | y 6
+    double y[6], xs[6], W[6][6], R3[3][3];
+#pragma unroll
+    for (int j = 0; j < 6; j++)
+#pragma unroll
+        for (int r = 0; r < 6; r++) W[j][r] = x.at(x.o.U, 6 * (da + j) + r);
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+        for (int r = 0; r < 3; r++) R3[j][r] = x.at(x.o.ax, 3 * (da + 3 + j) + r);
+    x.template tld_wait<16>(tmy);
+#pragma unroll
+    for (int j = 0; j < 6; j++) y[j] = X::unpack(tmy, 2 + j);
     // translational block first (the root has no parent: a = 0 on entry)
 #pragma unroll
-    for (int j = 0; j < 3; j++) {
-        double Wj[6];
-#pragma unroll
-        for (int r = 0; r < 6; r++) Wj[r] = x.at(x.o.U, 6 * (da + j) + r);
-        xs[j] = y[j] - dot6(Wj, a);
-    }
+    for (int j = 0; j < 3; j++) xs[j] = y[j] - dot6(W[j], a);
 #pragma unroll
     for (int j = 0; j < 3; j++) a[3 + j] += xs[j];
 #pragma unroll
-    for (int j = 0; j < 3; j++) {
-        double Wj[6];
+    for (int j = 0; j < 3; j++) xs[3 + j] = y[3 + j] - dot6(W[3 + j], a);
 #pragma unroll
-        for (int r = 0; r < 6; r++) Wj[r] = x.at(x.o.U, 6 * (da + 3 + j) + r);
-        xs[3 + j] = y[3 + j] - dot6(Wj, a);
-    }
-#pragma unroll
-    for (int j = 0; j < 3; j++) {
-        const int i = da + 3 + j;
-        const double xj = xs[3 + j];
-        a[0] += x.at(x.o.ax, 3 * i) * xj; a[1] += x.at(x.o.ax, 3 * i + 1) * xj; a[2] += x.at(x.o.ax, 3 * i + 2) * xj;
-    }
+    for (int j = 0; j < 3; j++) { a[0] += R3[j][0] * xs[3 + j]; a[1] += R3[j][1] * xs[3 + j]; a[2] += R3[j][2] * xs[3 + j]; }
     if (MODE == 0) {
         // semi-implicit Euler; root position + quaternion integration with the NEW velocity
         double vn[6];
@@ -479,19 +591,18 @@ EGP_HD void t5_fwd_solve_root(const X &x, double *a, int b) {
     }
 }
 
-// body done: world position record, spatial inertia about O in world axes, RNE body force
+// body done: world position record, spatial inertia about O in world axes, RNE body force -> scratch record
 template <class X>
-EGP_HD void t5_body_finish(const X &x, const Fwd &f, int b) {
-    const DevModel &M = EGP_CONST_M;
-    const int xs = M.body_xp_slot[b];
-    if (xs >= 0)
+EGP_HD void t5_body_finish(const X &x, const Fwd &f, int b, int rec, int xp_slot) {
+    const BodyK &K = EGP_CONST_M.bk[b];
+    if (xp_slot >= 0)
 #pragma unroll
-        for (int r = 0; r < 3; r++) x.at(x.o.xp, 3 * xs + r) = f.p[r] + x.at(x.o.q, r);
+        for (int r = 0; r < 3; r++) x.at(x.o.xp, 3 * xp_slot + r) = f.p[r] + x.at(x.o.q, r);
     double cpos[3];
-    const double ip0 = M.body_ipos[b][0], ip1 = M.body_ipos[b][1], ip2 = M.body_ipos[b][2];
+    const double ip0 = K.ipos[0], ip1 = K.ipos[1], ip2 = K.ipos[2];
 #pragma unroll
     for (int r = 0; r < 3; r++) cpos[r] = f.p[r] + f.R[3 * r] * ip0 + f.R[3 * r + 1] * ip1 + f.R[3 * r + 2] * ip2;
-    const double *in = M.body_inertia[b];
+    const double *in = K.inertia;
     const double Ib[9] = {in[0], in[3], in[4], in[3], in[1], in[5], in[4], in[5], in[2]};
     double Tm[9], Iw[6];
 #pragma unroll
@@ -505,8 +616,9 @@ EGP_HD void t5_body_finish(const X &x, const Fwd &f, int b) {
     Iw[3] = Tm[0] * f.R[3] + Tm[1] * f.R[4] + Tm[2] * f.R[5];
     Iw[4] = Tm[0] * f.R[6] + Tm[1] * f.R[7] + Tm[2] * f.R[8];
     Iw[5] = Tm[3] * f.R[6] + Tm[4] * f.R[7] + Tm[5] * f.R[8];
-    const double mass = M.body_mass[b], cc2 = dot3(cpos, cpos);
-    double ci[10];
+    const double mass = K.mass, cc2 = dot3(cpos, cpos);
+    double rc[16];                  // fb 6 | cin 10, the record's leading 32 columns
+    double *ci = rc + 6;
     ci[0] = mass;
     ci[1] = mass * cpos[0]; ci[2] = mass * cpos[1]; ci[3] = mass * cpos[2];
     ci[4] = Iw[0] + mass * (cc2 - cpos[0] * cpos[0]);
@@ -522,38 +634,33 @@ EGP_HD void t5_body_finish(const X &x, const Fwd &f, int b) {
     cross3(f.v, Iv, c0);            // v x* f = [w x n + v x f ; w x f]
     cross3(f.v + 3, Iv + 3, c1);
     cross3(f.v, Iv + 3, c2);
-    double fbv[6];
 #pragma unroll
     for (int r = 0; r < 3; r++) {
-        fbv[r] = Ia[r] + c0[r] + c1[r];
-        fbv[3 + r] = Ia[3 + r] + c2[r];
+        rc[r] = Ia[r] + c0[r] + c1[r];
+        rc[3 + r] = Ia[3 + r] + c2[r];
     }
-    x.st_cin(b, ci);
-    x.st_fb(b, fbv);
+    x.template tst<16>(rec + R_FB, rc);
 }
 
 // kinematics refresh of a hinge body: ND joints about coordinate axes (A0 + j) % 3 of the successively rotated
 // frame, all through one anchor (MuJoCo kinematics)
 template <int ND, int A0, class X>
-EGP_HD void t5_fwd_kin_body(const X &x, Fwd &f, int b) {
-    const DevModel &M = EGP_CONST_M;
-    const int da = M.body_dofadr[b], qa = M.body_qposadr[b];
-    const double bp0 = M.body_pos[b][0], bp1 = M.body_pos[b][1], bp2 = M.body_pos[b][2];
-    const double da0 = M.dof_anchor[da][0], da1 = M.dof_anchor[da][1], da2 = M.dof_anchor[da][2];
+EGP_HD void t5_fwd_kin_body(const X &x, Fwd &f, const KinIn &in) {
+    const BodyK &K = EGP_CONST_M.bk[in.b];
+    const double bp0 = K.pos[0], bp1 = K.pos[1], bp2 = K.pos[2];
+    const double da0 = K.anchor[0], da1 = K.anchor[1], da2 = K.anchor[2];
     double anc[3];
 #pragma unroll
     for (int r = 0; r < 3; r++) {
         f.p[r] += f.R[3 * r] * bp0 + f.R[3 * r + 1] * bp1 + f.R[3 * r + 2] * bp2;
         anc[r] = f.p[r] + f.R[3 * r] * da0 + f.R[3 * r + 1] * da1 + f.R[3 * r + 2] * da2;
-        x.at(x.o.anc, 3 * b + r) = anc[r];
+        x.at(x.o.anc, 3 * in.b + r) = anc[r];
     }
-    double sn[ND], cs[ND], qd[ND];
-#pragma unroll
-    for (int j = 0; j < ND; j++) { sincos(x.at(x.o.q, qa + j), &sn[j], &cs[j]); qd[j] = x.at(x.o.v, da + j); }
 #pragma unroll
     for (int j = 0; j < ND; j++) {
         const int aid = (A0 + j) % 3, c1 = (aid + 1) % 3, c2 = (aid + 2) % 3;
-        const int i = da + j;
+        const int i = in.da + j;
+        const double qd = in.v[j];
         double S[6];
         S[0] = f.R[aid]; S[1] = f.R[3 + aid]; S[2] = f.R[6 + aid];
 #pragma unroll
@@ -566,17 +673,17 @@ EGP_HD void t5_fwd_kin_body(const X &x, Fwd &f, int b) {
         cross3(f.v + 3, S, t2);
 #pragma unroll
         for (int r = 0; r < 3; r++) {
-            f.a[r] += t0[r] * qd[j];
-            f.a[3 + r] += (t1[r] + t2[r]) * qd[j];
+            f.a[r] += t0[r] * qd;
+            f.a[3 + r] += (t1[r] + t2[r]) * qd;
         }
 #pragma unroll
-        for (int r = 0; r < 6; r++) f.v[r] += S[r] * qd[j];
+        for (int r = 0; r < 6; r++) f.v[r] += S[r] * qd;
         // rotate the frame about the joint axis through the anchor
 #pragma unroll
         for (int r = 0; r < 3; r++) {
             const double a1 = f.R[3 * r + c1], a2 = f.R[3 * r + c2];
-            f.R[3 * r + c1] = cs[j] * a1 + sn[j] * a2;
-            f.R[3 * r + c2] = -sn[j] * a1 + cs[j] * a2;
+            f.R[3 * r + c1] = in.cs[j] * a1 + in.sn[j] * a2;
+            f.R[3 * r + c2] = -in.sn[j] * a1 + in.cs[j] * a2;
         }
     }
 #pragma unroll
@@ -587,7 +694,7 @@ EGP_HD void t5_fwd_kin_body(const X &x, Fwd &f, int b) {
 template <class X>
 EGP_HD void t5_fwd_kin_root(const X &x, Fwd &f, int b) {
     const DevModel &M = EGP_CONST_M;
-    const int da = M.body_dofadr[b], qa = M.body_qposadr[b];
+    const int da = M.bk[b].da, qa = M.bk[b].qa;
     double q4[4] = {x.at(x.o.q, qa + 3), x.at(x.o.q, qa + 4), x.at(x.o.q, qa + 5), x.at(x.o.q, qa + 6)};
     const double n = sqrt(q4[0] * q4[0] + q4[1] * q4[1] + q4[2] * q4[2] + q4[3] * q4[3]);
 #pragma unroll
@@ -636,22 +743,65 @@ EGP_HD void t5_fwd_chain(const X &x, int c) {
 #pragma unroll
         for (int k = 0; k < 6; k++) { f.v[k] = x.at(base, 12 + k); f.a[k] = x.at(base, 18 + k); }
     }
-    for (int b = M.chain_lo[c]; b <= M.chain_hi[c]; b++) {
-        const int kind = M.body_kind[b];
-        if (MODE != 2) {
-            if (kind == BK_XYZ) t5_fwd_solve_body<3, MODE>(x, a, b);
-            else if (kind == BK_ROOT) t5_fwd_solve_root<MODE>(x, a, b);
-            else t5_fwd_solve_body<1, MODE>(x, a, b);
-        }
+    const int lo = M.chain_lo[c], hi = M.chain_hi[c];
+    const bool has_root = M.bk[lo].kind == BK_ROOT;
+    const int lo_h = has_root ? lo + 1 : lo;
+    if (MODE == 0) { EGP_CLK_MARK(8) }
+    if (has_root) {
+        if (MODE != 2) t5_fwd_solve_root<MODE>(x, a, lo);
         if (MODE != 0) {
-            if (kind == BK_XYZ) t5_fwd_kin_body<3, 0>(x, f, b);
-            else if (kind == BK_ROOT) t5_fwd_kin_root(x, f, b);
-            else if (kind == BK_X) t5_fwd_kin_body<1, 0>(x, f, b);
-            else if (kind == BK_Y) t5_fwd_kin_body<1, 1>(x, f, b);
-            else t5_fwd_kin_body<1, 2>(x, f, b);
-            t5_body_finish(x, f, b);
+            t5_fwd_kin_root(x, f, lo);
+            t5_body_finish(x, f, lo, M.bk[lo].rec, M.bk[lo].xp_slot);
         }
     }
+    if (MODE == 0) { EGP_CLK_MARK(9) }
+    constexpr bool PF = (MODE == 0 && EGP_PF_FWD0) || (MODE == 1 && EGP_PF_FWD1);
+    FwdIn<MODE> in;
+    if (PF && hi >= lo_h) t5_fwd_load<MODE>(x, lo_h, in);
+#pragma unroll 1
+    for (int b = lo_h; b <= hi; b++) {
+        if (!PF) t5_fwd_load<MODE>(x, b, in);
+        if (MODE != 2) x.template tld_wait<8>(in.tmy);
+        if (MODE == 1) x.template tld_wait<8>(in.tmc);
+        const int kind = in.kind;
+        KinIn kin;
+        kin.b = in.b; kin.da = in.da; kin.rec = in.rec; kin.xp_slot = in.xp_slot;
+#pragma unroll
+        for (int j = 0; j < 3; j++) { kin.v[j] = in.v[j]; kin.sn[j] = in.sn[j]; kin.cs[j] = in.cs[j]; }
+        if (MODE == 0 && PF) {
+            // accel + Euler only: little arithmetic per body, so the next body's operands are requested a full body ahead
+            FwdIn<MODE> cur;
+            cur.da = in.da; cur.qa = in.qa; cur.nd = in.nd; cur.rec = in.rec;
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+#pragma unroll
+                for (int r = 0; r < 6; r++) cur.W[j][r] = in.W[j][r];
+#pragma unroll
+                for (int r = 0; r < 3; r++) cur.ax[j][r] = in.ax[j][r];
+                cur.anc[j] = in.anc[j]; cur.q[j] = in.q[j]; cur.v[j] = in.v[j];
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) cur.tmy[k] = in.tmy[k];
+            if (b < hi) t5_fwd_load<MODE>(x, b + 1, in);
+            if (cur.nd == 3) t5_fwd_solve_body<3, MODE>(x, a, cur);
+            else t5_fwd_solve_body<1, MODE>(x, a, cur);
+        } else {
+            if (MODE != 2) {
+                if (in.nd == 3) t5_fwd_solve_body<3, MODE>(x, a, in);
+                else t5_fwd_solve_body<1, MODE>(x, a, in);
+            }
+            // this body's solve operands are dead: request the next body's while the kinematics / body-force arithmetic runs
+            if (PF && b < hi) t5_fwd_load<MODE>(x, b + 1, in);
+        }
+        if (MODE != 0) {
+            if (kind == BK_XYZ) t5_fwd_kin_body<3, 0>(x, f, kin);
+            else if (kind == BK_X) t5_fwd_kin_body<1, 0>(x, f, kin);
+            else if (kind == BK_Y) t5_fwd_kin_body<1, 1>(x, f, kin);
+            else t5_fwd_kin_body<1, 2>(x, f, kin);
+            t5_body_finish(x, f, kin.b, kin.rec, kin.xp_slot);
+        }
+    }
+    if (MODE == 0) { EGP_CLK_MARK(10) }
     x.twait_st();
     if (M.chain_pslot[c] >= 0) {
         if (MODE != 2) {
@@ -743,19 +893,32 @@ inline void build_chains(DevModel &d) {
     }
     if (d.body_xp_slot[d.head_body] < 0) d.body_xp_slot[d.head_body] = nslot++;
     d.head_xp_slot = d.body_xp_slot[d.head_body];
-    // TMEM scratch slots: position of each dof / body among those owned by the same warp.  Per dof: ctrl, y, tau, C
-    // (2 columns each; one spare dof slot so that 3-wide block accesses may be issued as one 4-wide access)
-    int nd_w[T4_CW] = {0}, nb_w[T4_CW] = {0};
-    for (int b = 0; b < nb; b++) {
-        int w = d.chain_warp[d.body_chain[b]];
-        d.body_slot[b] = nb_w[w]++;
-        for (int i = d.body_dofadr[b]; i < d.body_dofadr[b] + d.body_dofnum[b]; i++) d.dof_slot[i] = nd_w[w]++;
-    }
-    int ND = 0, NB = 0;
-    for (int w = 0; w < T4_CW; w++) { if (nd_w[w] > ND) ND = nd_w[w]; if (nb_w[w] > NB) NB = nb_w[w]; }
-    d.tm_ctrl = 0; d.tm_y = 2 * ND; d.tm_tau = 4 * ND; d.tm_c = 6 * ND; d.tm_cin = 8 * ND; d.tm_fb = 8 * ND + 20 * NB;
-    d.tm_cols = 8 * ND + 32 * NB;
+    // scratch records: position of each body among those owned by the same warp
+    int nb_w[T4_CW] = {0};
+    for (int b = 0; b < nb; b++) d.body_slot[b] = nb_w[d.chain_warp[d.body_chain[b]]]++;
+    int NB = 0;
+    for (int w = 0; w < T4_CW; w++) if (nb_w[w] > NB) NB = nb_w[w];
+    d.tm_cols = R_COLS_HOST * NB;
     if (d.tm_cols > 512) d.t4_ok = 0;
+    for (int b = 0; b < nb; b++) {
+        BodyK &K = d.bk[b];
+        memset(&K, 0, sizeof K);
+        const int da = d.body_dofadr[b], nd = d.body_dofnum[b];
+        K.da = da; K.qa = d.body_qposadr[b]; K.nd = nd; K.kind = d.body_kind[b]; K.rec = R_COLS_HOST * d.body_slot[b];
+        K.xp_slot = d.body_xp_slot[b];
+        for (int k = 0; k < 3; k++) { K.pos[k] = d.body_pos[b][k]; K.ipos[k] = d.body_ipos[b][k]; K.anchor[k] = d.dof_anchor[da][k]; }
+        for (int k = 0; k < 6; k++) K.inertia[k] = d.body_inertia[b][k];
+        K.mass = d.body_mass[b];
+        for (int j = 0; j < 3 && j < nd; j++) {
+            const int i = da + j;
+            K.arm[j] = d.dof_arm[i]; K.armkd[j] = d.dof_arm[i] + d.kd[i] * d.h; K.kp[j] = d.kp[i]; K.kd[j] = d.kd[i]; K.tlim[j] = d.tlim[i];
+        }
+        for (int j = 0; j < nd; j++) {
+            const int i = da + j;
+            if (b == 0) { d.dof_col_ctrl[i] = -1; d.dof_col_tau[i] = -1; d.dof_col_c[i] = K.rec + 32 + 2 * j; }
+            else { d.dof_col_ctrl[i] = K.rec + 32 + 2 * j; d.dof_col_c[i] = K.rec + 38 + 2 * j; d.dof_col_tau[i] = K.rec + 44 + 2 * j; }
+        }
+    }
 }
 
 // EgpModelDesc -> DevModel (egp_model_create); returns 0 or a negative EGP_E* code with *why set

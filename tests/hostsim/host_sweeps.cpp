@@ -18,16 +18,14 @@ struct HostCtx {
     int w;
     T4Off o;
     double &at(int off, int idx) const { return sm[off + idx]; }
-    template <int N> void tld(int col, double *v) const { for (int k = 0; k < N; k++) v[k] = tmem[col / 2 + k]; }
+    template <int NR> void tld_issue(int col, int (&r)[NR]) const { memcpy(r, tmem + col / 2, 4 * NR); }
+    template <int NR> void tld_wait(int (&)[NR]) const {}
+    static double unpack(const int *r, int k) { double v; memcpy(&v, r + 2 * k, 8); return v; }
     template <int N> void tst(int col, const double *v) const { for (int k = 0; k < N; k++) tmem[col / 2 + k] = v[k]; }
-    void st_cin(int b, const double *ci) const { memcpy(tmem + (h_m.tm_cin + 20 * h_m.body_slot[b]) / 2, ci, 80); }
-    void ld_cin(int b, double *ci) const { memcpy(ci, tmem + (h_m.tm_cin + 20 * h_m.body_slot[b]) / 2, 80); }
-    void st_fb(int b, const double *f) const { memcpy(tmem + (h_m.tm_fb + 12 * h_m.body_slot[b]) / 2, f, 48); }
-    void ld_fb(int b, double *f) const { memcpy(f, tmem + (h_m.tm_fb + 12 * h_m.body_slot[b]) / 2, 48); }
     void twait_st() const {}
 };
 
-static double g_sm[4096], g_tm[T4_CW][256];
+static double g_sm[4096], g_tm[T4_CW][256 + 8];
 static HostCtx g_x[T4_CW];
 
 template <int MODE> static void fwd() {
@@ -82,16 +80,16 @@ void hs_env_step(double *qpos, double *qvel, const double *action, double *torqu
     for (int k = 0; k < h_m.nq; k++) g_sm[O.q + k] = qpos[k];
     for (int k = 0; k < h_m.nv; k++) g_sm[O.v + k] = qvel[k];
     fwd<2>();
-    for (int i = 0; i < h_m.nv; i++) g_tm[dof_warp(i)][(h_m.tm_tau + 2 * h_m.dof_slot[i]) / 2] = 0.0;
+    for (int i = 6; i < h_m.nv; i++) g_tm[dof_warp(i)][h_m.dof_col_tau[i] / 2] = 0.0;
     bwd(0);
-    if (bias0) for (int i = 0; i < h_m.nv; i++) bias0[i] = g_tm[dof_warp(i)][(h_m.tm_c + 2 * h_m.dof_slot[i]) / 2];
+    if (bias0) for (int i = 0; i < h_m.nv; i++) bias0[i] = g_tm[dof_warp(i)][h_m.dof_col_c[i] / 2];
     for (int i = 6; i < h_m.nv; i++)
-        g_tm[dof_warp(i)][(h_m.tm_ctrl + 2 * h_m.dof_slot[i]) / 2] = h_m.a_ref[i] + action[i - 6] * h_m.a_scale[i];
+        g_tm[dof_warp(i)][h_m.dof_col_ctrl[i] / 2] = h_m.a_ref[i] + action[i - 6] * h_m.a_scale[i];
     for (int s = 0; s < h_m.frame_skip; s++) {
         bwd(1);
         fwd<1>();
         if (s == 0 && torque0)
-            for (int i = 6; i < h_m.nv; i++) torque0[i - 6] = g_tm[dof_warp(i)][(h_m.tm_tau + 2 * h_m.dof_slot[i]) / 2];
+            for (int i = 6; i < h_m.nv; i++) torque0[i - 6] = g_tm[dof_warp(i)][h_m.dof_col_tau[i] / 2];
         bwd(0);
         fwd<0>();
     }
