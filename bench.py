@@ -31,6 +31,22 @@ sys.path.insert(0, os.path.join(ROOT, 'tests'))
 
 WORKLOAD = 'subject_03 egomimic humanoid PPO iteration: 4096 envs x 300 steps per GPU, 2x300 MLP policy/value, 10 epochs'
 
+# BASELINE.json configs (per-GPU shares; `--gpus N` weak-scales them).  2 is the default the driver measures; the others are
+# run explicitly (`--config K`) and their lines kept under profiles/.
+CONFIGS = {
+    2: dict(task='egomimic', cfg='subject_03', envs=4096, horizon=300, hidden=[300, 300], n_takes=8, minibatch=0,
+            workload=WORKLOAD),
+    3: dict(task='egomimic', cfg='cross_01', envs=8192, horizon=300, hidden=[512, 512], n_takes=32, minibatch=0,
+            workload='cross_01 egomimic humanoid PPO iteration: 8192 envs x 300 steps per GPU, 2x512 MLP policy/value, 10 epochs'),
+    4: dict(task='egoforecast', cfg='subject_03', envs=4096, horizon=90, hidden=[300, 200], n_takes=8, minibatch=0,
+            workload='subject_03 egoforecast humanoid PPO iteration: 4096 envs x 90 steps per GPU (16384 envs on 4 GPUs), '
+                     'VideoForecastNet context (causal LSTM over 30 past CNN-feature frames, precomputed features) + state LSTM '
+                     '115->128 stepped inside the rollout kernel, 2-layer [300, 200] MLP policy/value on the 256-wide input, 10 epochs'),
+    5: dict(task='egomimic', cfg='cross_01', envs=8192, horizon=300, hidden=[512, 512], n_takes=32, minibatch=65536,
+            workload='cross_01 egomimic humanoid PPO iteration: 8192 envs x 300 steps per GPU (65536 envs on 8 GPUs), 2x512 MLP, '
+                     'mini-batch PPO (opt_batch_size 65536, agents/agent_ppo.py:24-43), 10 epochs'),
+}
+
 
 def parse():
     ap = argparse.ArgumentParser()
@@ -38,16 +54,26 @@ def parse():
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--envs', type=int, default=4096)
-    ap.add_argument('--horizon', type=int, default=300)
-    ap.add_argument('--hidden', type=int, nargs=2, default=[300, 300])
+    ap.add_argument('--config', type=int, default=2, choices=sorted(CONFIGS), help='BASELINE.json config (2 = headline)')
+    ap.add_argument('--envs', type=int, default=None)
+    ap.add_argument('--horizon', type=int, default=None)
+    ap.add_argument('--hidden', type=int, nargs=2, default=None)
     ap.add_argument('--epochs', type=int, default=10)
+    ap.add_argument('--no-variants', action='store_true', help='skip the cuBLAS / 7-slice update timings')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-envs', type=int, default=0, help='envs in the CPU sample (0 = 2 per core)')
     ap.add_argument('--cpu-horizon', type=int, default=20)
     ap.add_argument('--cpu-update-rows', type=int, default=12288)
-    return ap.parse_args()
+    args = ap.parse_args()
+    c = CONFIGS[args.config]
+    args.envs = args.envs or c['envs']
+    args.horizon = args.horizon or c['horizon']
+    args.hidden = args.hidden or list(c['hidden'])
+    args.task, args.cfg_id, args.n_takes, args.minibatch, args.workload = c['task'], c['cfg'], c['n_takes'], c['minibatch'], c['workload']
+    if (args.envs, args.horizon, args.hidden) != (c['envs'], c['horizon'], list(c['hidden'])):
+        args.workload += ' [overridden: %d envs x %d steps, hidden %s]' % (args.envs, args.horizon, args.hidden)
+    return args
 
 
 def peaks():
@@ -101,39 +127,49 @@ class ClockSampler:
                 'reasons': reasons, 'samples': len(sm)}
 
 
-def synthetic_problem(args, n_takes=8):
+def synthetic_problem(args):
     """seeded synthetic experts: smooth in-range trajectories, N(0,1) CNN features"""
     from egopose_b200.mjcf import load_builtin
     from egopose_b200.synthetic import synthetic_cnn_feat, synthetic_takes
     md = load_builtin()
-    L = args.horizon + 2 * 10 + 64
-    return md, synthetic_takes(md, n_takes, L, seed=1), synthetic_cnn_feat(n_takes, L)
+    margin = 30 if args.task == 'egoforecast' else 10
+    L = args.horizon + 2 * margin + 64
+    return md, synthetic_takes(md, args.n_takes, L, seed=1), synthetic_cnn_feat(args.n_takes, L)
 
 
-def build_agent(args, device, takes, cnn):
+def build_agent(args, device, takes, cnn, gemm=None, oz_slices=None):
     import torch
     from egopose_b200.agent import AgentEgo
     from egopose_b200.config import Config
     from egopose_b200.env import HumanoidEnv
-    from egopose_b200.nets import MLP, FrameContext, PolicyGaussian, Value
+    from egopose_b200.nets import MLP, FrameContext, PolicyGaussian, Value, VideoForecastNet
     from egopose_b200.zfilter import ZFilter
     torch.set_default_dtype(torch.float64)
     torch.manual_seed(1)
-    cfg = Config('subject_03')
+    cfg = Config(args.cfg_id, task=args.task)
     cfg.env_episode_len = args.horizon
     env = HumanoidEnv(cfg, device=device.index)
     env.seed(cfg.seed)
     env.set_expert_qpos(['take_%d' % i for i in range(len(takes))], takes, cnn)
     sd, ad = env.observation_space.shape[0], env.action_space.shape[0]
-    policy = PolicyGaussian(MLP(sd + 128, args.hidden, 'relu'), ad, log_std=cfg.log_std, fix_std=cfg.fix_std).to(device)
-    value = Value(MLP(sd + 128, args.hidden, 'relu')).to(device)
-    opt_p = torch.optim.Adam(policy.parameters(), lr=cfg.policy_lr)
-    opt_v = torch.optim.Adam(value.parameters(), lr=cfg.value_lr)
+    if args.task == 'egoforecast':          # ego_forecast.py:53-58: forecast context nets (v_hdim 128, state LSTM 128)
+        mk = lambda: VideoForecastNet(128, sd, 128, cfg.fr_margin, 'lstm', None, 128, 'lstm').to(device)  # noqa: E731
+        pvs, vvs = mk(), mk()
+        in_dim = pvs.out_dim
+    else:
+        pvs, vvs, in_dim = FrameContext(128), FrameContext(128), sd + 128
+    policy = PolicyGaussian(MLP(in_dim, args.hidden, 'relu'), ad, log_std=cfg.log_std, fix_std=cfg.fix_std).to(device)
+    value = Value(MLP(in_dim, args.hidden, 'relu')).to(device)
+    pparams = list(policy.parameters()) + [p for p in pvs.parameters()]
+    vparams = list(value.parameters()) + [p for p in vvs.parameters()]
+    opt_p = torch.optim.Adam(pparams, lr=cfg.policy_lr)
+    opt_v = torch.optim.Adam(vparams, lr=cfg.value_lr)
     agent = AgentEgo(env=env, dtype=torch.float64, device=device, running_state=ZFilter((sd,), clip=5),
-                     custom_reward=None, num_threads=1, policy_net=policy, policy_vs_net=FrameContext(128),
-                     value_net=value, value_vs_net=FrameContext(128), optimizer_policy=opt_p, optimizer_value=opt_v,
+                     custom_reward=None, num_threads=1, policy_net=policy, policy_vs_net=pvs,
+                     value_net=value, value_vs_net=vvs, optimizer_policy=opt_p, optimizer_value=opt_v,
                      opt_num_epochs=args.epochs, gamma=cfg.gamma, tau=cfg.tau, clip_epsilon=cfg.clip_epsilon,
-                     policy_grad_clip=[(list(policy.parameters()), 40)], num_envs=args.envs, horizon=args.horizon)
+                     policy_grad_clip=[(pparams, 40)], num_envs=args.envs, horizon=args.horizon,
+                     use_mini_batch=args.minibatch > 0, opt_batch_size=args.minibatch or 64, gemm=gemm, oz_slices=oz_slices)
     return agent, cfg
 
 
@@ -205,7 +241,7 @@ def run_reference(args):
     line = {'impl': 'reference', 'metric': 'env-steps/sec (humanoid PPO rollout+update)', 'value': v, 'unit': 'env-steps/s',
             'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'envs_per_gpu': args.envs, 'horizon': args.horizon, 'hidden': args.hidden,
+            'config': {'workload': args.workload, 'baseline_config': args.config, 'envs_per_gpu': args.envs, 'horizon': args.horizon, 'hidden': args.hidden,
                        'epochs': args.epochs, 'parallelism': 'host threads (rank 0 only)'},
             'cpu_baseline': {'value': v, 'unit': 'env-steps/s', 'cores': detail['cores'], 'kind': 'port',
                              'sample': detail['sample'], 'rollout_steps_per_s': detail['rollout_steps_per_s'],
@@ -291,8 +327,9 @@ def main():
         flush.fill_(i)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
+        rctx, rwin = agent._rollout_context()
         agent.env.kernel.rollout(w, E, T, T, cfg.fr_margin, zf_mean=zm, zf_std=zs, zf_clip=clip, seed=7, iteration=900 + i,
-                                 want_next=False, want_raw=True, out=agent._out)
+                                 want_next=False, want_raw=True, out=agent._out, ctx=rctx, win_off=rwin, **agent._rollout_extra())
         b.record()
         b.synchronize()
         times.append(a.elapsed_time(b))
@@ -343,10 +380,21 @@ def main():
         del rb, ob, wb
     except Exception as e:        # noqa: BLE001
         gae_big = {'error': str(e)[:200]}
-    # `traffic`: dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the committed ncu --set full capture
-    # of this exact configuration (profiles/r1_rollout_t4_full.md / r1_gae_full.md); not re-measured live
-    default_cfg = (E, T, tuple(args.hidden)) == (4096, 300, (300, 300))
+    # `traffic` (dram__bytes_read.sum + dram__bytes_write.sum of ONE launch) and pipe utilisation cannot be measured outside a
+    # profiler: they are read from profiles/ncu_captures.json, written by tools/ncu_capture_summary.py from the ncu --set full
+    # captures of THIS build at this configuration (the file names its .ncu-rep, commit and date), else null
+    default_cfg = args.config == 2 and (E, T, tuple(args.hidden)) == (4096, 300, (300, 300))
+    cap = {}
+    try:
+        cap = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_captures.json'))) if default_cfg else {}
+    except Exception:
+        cap = {}
+    cap_of = lambda k, f: (cap.get(k) or {}).get(f)     # noqa: E731
     flops_env_step = 15 * 2 * 21e3 + 2 * (243 * 300 + 300 * 300 + 300 * 52)      # ABA sweeps + policy MLP, FMA = 2
+    # DFMA-pipe peak of the rollout kernel's arithmetic: 64 double-precision FMA lanes per SM and clock (measured:
+    # tools/micro/fp64_probe.cu, 2.13 cycles per warp-wide DFMA and sub-partition) x the SM clock sampled during this run
+    sm_mhz = clocks.get('sm_mhz') or 1965.0
+    dfma_peak = torch.cuda.get_device_properties(device).multi_processor_count * 64 * 2 * sm_mhz * 1e6 / 1e12
     fp64_peak = None
     try:        # live float64 GEMM peak of this box (MEASURED_PEAKS.json carries no FP64 figure)
         sq = torch.randn(6144, 6144, dtype=torch.float64, device=device)
@@ -363,19 +411,23 @@ def main():
         pass
     roofline = {'kernel': 'rollout_kernel_t4', 'bound': 'hbm', 'achieved': roll_bytes / (roll_ms / 1e3) / 1e9, 'peak': hbm,
                 'unit': 'GB/s', 'frac': roll_bytes / (roll_ms / 1e3) / 1e9 / hbm,
-                'traffic': 10.203e9 if default_cfg else None, 'peak_source': peak_src,
+                'traffic': cap_of('rollout_kernel_t4', 'dram_bytes'), 'traffic_source': cap_of('rollout_kernel_t4', 'source'),
+                'peak_source': peak_src,
                 'ms': roll_ms, 'share_of_step': roll_ms / ms, 'algorithmic_bytes_per_env_step': roll_bytes // N,
-                'note': 'the fused rollout keeps all state on chip (~200 FLOP/B): it is FP64-issue/latency bound, not HBM '
-                        'bound (SURVEY 7); fp64 utilisation below; traffic > algorithmic bytes is thread-local scratch '
-                        'write-back (180 MB footprint > L2)'}
-    extra = {'rollout_fp64': {'achieved': flops_env_step * N / (roll_ms / 1e3) / 1e12, 'peak': fp64_peak, 'unit': 'TFLOP/s',
-                              'frac': (flops_env_step * N / (roll_ms / 1e3) / 1e12 / fp64_peak) if fp64_peak else None,
-                              'peak_source': 'cuBLAS DGEMM 6144^3 measured live on this GPU',
+                'binding_resource': 'FP64 issue / dependent-issue latency of the tree sweeps (not HBM)',
+                'note': 'the contract asks for the HBM figure of the dominant kernel; the fused rollout keeps all state on chip '
+                        '(~200 FLOP/B), so its roofline is the DFMA pipe: see roofline_extra.rollout_fp64'}
+    extra = {'rollout_fp64': {'achieved': flops_env_step * N / (roll_ms / 1e3) / 1e12, 'peak': dfma_peak, 'unit': 'TFLOP/s',
+                              'frac': flops_env_step * N / (roll_ms / 1e3) / 1e12 / dfma_peak,
+                              'peak_source': '64 DFMA lanes/SM/clk (tools/micro/fp64_probe.cu) x %d SMs x %.0f MHz sampled in this run'
+                                             % (torch.cuda.get_device_properties(device).multi_processor_count, sm_mhz),
                               'flop_per_env_step': flops_env_step,
-                              'ncu_fp64_pipe_active_pct': 12.2 if default_cfg else None},
+                              'ncu_fp64_pipe_active_pct': cap_of('rollout_kernel_t4', 'fp64_pipe_active_pct'),
+                              'ncu_issue_active_pct': cap_of('rollout_kernel_t4', 'issue_active_pct'),
+                              'ncu_source': cap_of('rollout_kernel_t4', 'source')},
              'gae_kernel': {'bound': 'hbm', 'achieved': 5 * wbytes * N / (gae_ms / 1e3) / 1e9, 'peak': hbm, 'unit': 'GB/s',
                             'frac': 5 * wbytes * N / (gae_ms / 1e3) / 1e9 / hbm, 'ms': gae_ms, 'bytes_per_sample': 40,
-                            'traffic': 63.36e6 if default_cfg else None},
+                            'traffic': cap_of('gae', 'dram_bytes'), 'traffic_source': cap_of('gae', 'source')},
              'gae_kernel_config5': gae_big,
              'update_dgemm': {'bound': 'tensor(fp64)', 'achieved': None, 'peak': fp64_peak, 'unit': 'TFLOP/s'},
              'rollout_env_substeps_per_s': N * 15 / (roll_ms / 1e3)}
@@ -406,7 +458,8 @@ def main():
                                        'peak_source': '2 x dense bf16 ' + tp_src + ' (kind::i8 issues at twice the bf16 rate)',
                                        'f64_equivalent_tflops': 2.0 * N * args.hidden[0] * 243 / (g_ms / 1e3) / 1e12,
                                        'slices': S_oz, 'slice_pairs': pairs,
-                                       'traffic': 4.79e9 if default_cfg and S_oz == 6 else None,
+                                       'traffic': cap_of('oz_gemm_kernel', 'dram_bytes') if S_oz == 6 else None,
+                                       'traffic_source': cap_of('oz_gemm_kernel', 'source') if S_oz == 6 else None,
                                        'note': 'unpadded algorithmic work; the tiles pad N 300->320 and K 243->256'}
             del xg, wg, a_sl, b_sl, og
         except Exception as exc:        # the headline numbers above do not depend on this probe
@@ -422,6 +475,31 @@ def main():
                                      'whole update phase incl. slicing / loss / Adam, against the cuBLAS DGEMM peak' % agent.oz_slices
                                      if agent.gemm == 'ozaki' else
                                      'cuBLAS d884 DGEMMs + fused elementwise kernels; whole update phase incl. loss/Adam')
+
+    # ---- the same update on the other dense-layer back ends (cuBLAS DGEMM = the reference's arithmetic, 7 slices = DGEMM-level
+    # rounding), timed on the batch of the last rollout: one warm-up + one timed update each, fresh nets / optimizers
+    variants = None
+    if not args.no_variants and agent.gemm == 'ozaki' and world == 1 and args.task == 'egomimic':
+        variants = {}
+        for name, gm, sl in (('cublas', 'cublas', None), ('ozaki_7_slices', 'ozaki', 7)):
+            try:
+                ag2, _ = build_agent(args, device, takes, cnn, gemm=gm, oz_slices=sl)
+                ag2.running_state = agent.running_state
+                b2, _ = ag2.sample(N, to_host=False)
+                ag2.update_params(b2)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                ag2.update_params(b2)
+                b.record()
+                b.synchronize()
+                u_ms = a.elapsed_time(b)
+                variants[name] = {'ms_update': u_ms, 'value': N / ((ms_roll + u_ms) / 1e3), 'unit': 'env-steps/s',
+                                  'note': 'ms_rollout of the timed region + this update'}
+                ag2.env.close()
+                del ag2, b2
+                torch.cuda.empty_cache()
+            except Exception as exc:        # noqa: BLE001
+                variants[name] = {'error': str(exc)[:200]}
 
     # ---- e2e through the public API with host trajbatches
     e2e = None
@@ -453,13 +531,13 @@ def main():
         line = {'metric': 'env-steps/sec (humanoid PPO rollout+update)', 'value': value, 'unit': 'env-steps/s',
                 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
                 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-                'config': {'workload': WORKLOAD, 'envs_per_gpu': E, 'horizon': T, 'hidden': args.hidden,
+                'config': {'workload': args.workload, 'baseline_config': args.config, 'envs_per_gpu': E, 'horizon': T, 'hidden': args.hidden,
                            'epochs': args.epochs, 'parallelism': 'env-sharded dp%d' % world,
                            'update_gemm': ('float64 in/out on int8 tcgen05 (Ozaki, %d slices, error <= %.0e of row x column maxima)'
                                            % (agent.oz_slices, (agent.oz_slices + 2) * 2.0 ** (-7 * agent.oz_slices))
                                            if agent.gemm == 'ozaki' else 'cuBLAS DGEMM'),
                            'l2': 'inputs larger than L2 (trajbatch %.1f GB per step)' % (N * (2 * 115 + 52) * 8 / 1e9)},
-                'ms_rollout': ms_roll, 'ms_update': ms_upd, 'gpu_launches': launches, 'clocks': clocks,
+                'ms_rollout': ms_roll, 'ms_update': ms_upd, 'update_variants': variants, 'gpu_launches': launches, 'clocks': clocks,
                 'roofline': roofline, 'roofline_extra': extra, 'e2e': e2e, 'cpu_baseline': cpu,
                 'avg_c_reward': log.avg_c_reward, 'avg_episode_len': log.avg_episode_reward,
                 'nan_resets': log.num_nan_resets}

@@ -69,11 +69,26 @@ class _FlatNet:
                 st['exp_avg_sq'] = self.v[a:b].view(p.shape)
                 st['step'] = torch.tensor(float(self.step))
 
-    def realias(self):
-        """Re-establish parameter <-> flat-buffer aliasing after the caller moved the modules (utils/torch.py:13-27
-        to_cpu / to_device around checkpointing, ego_mimic.py:134: module.to() rebinds p.data to fresh tensors).  The
-        module tensors are the source of truth at that point (the caller may also have loaded a state dict)."""
+    def realias(self, named=None):
+        """Re-establish parameter <-> flat-buffer aliasing after the caller moved the modules (a stock module.to(cpu) /
+        .to(cuda) round trip around checkpointing, ego_mimic.py:134): current PyTorch then REPLACES the Parameter objects
+        (CPU and CUDA tensors are not shallow-copy compatible), older versions rebind p.data.  ``named`` is the current
+        (name, parameter) list of the modules; the module tensors are the source of truth at that point (the caller may
+        also have loaded a state dict).  The caller's optimizer is re-pointed to the new objects, its state follows."""
         moved = False
+        if named is not None:
+            cur = dict(named)
+            for i, (n, old) in enumerate(zip(self.names, self.params)):
+                new = cur.get(n)
+                if new is None or new is old:
+                    continue
+                self.params[i] = new
+                moved = True
+                if self.optimizer is not None:
+                    for g in self.optimizer.param_groups:
+                        g['params'] = [new if q is old else q for q in g['params']]
+                    if old in self.optimizer.state:
+                        self.optimizer.state[new] = self.optimizer.state.pop(old)
         for p, a, b in zip(self.params, self.offsets[:-1], self.offsets[1:]):
             if p.data.data_ptr() != self.flat[a:b].data_ptr() or p.data.device != self.flat.device:
                 self.flat[a:b].copy_(p.data.reshape(-1).to(self.flat.device, torch.float64))
@@ -244,6 +259,7 @@ class Agent:
         self.iteration = 0
         self._out = {}
         self._host_pool = {}        # pinned host staging buffers reused by sample(to_host=True)
+        self.keep_next_states = False
         if dtype != torch.float64:
             raise lib.EgpError('the fused path computes in float64 like the reference (ego_mimic.py:31-32)')
         if render:
@@ -305,9 +321,17 @@ class Agent:
         E = int(self.num_envs or math.ceil(min_batch_size / T))
         return E, T
 
-    def sample(self, min_batch_size, to_host=True, parity=None):
+    def sample(self, min_batch_size, to_host=None, parity=None):
         """agents/agent.py:87-111.  ``parity`` may carry pre-drawn eps / reset_take / reset_start / mean_flag
-        device tensors (SURVEY 7 'RNG parity'); otherwise noise and resets come from in-kernel Philox."""
+        device tensors (SURVEY 7 'RNG parity'); otherwise noise and resets come from in-kernel Philox.
+
+        The returned batch is DEVICE-RESIDENT and lazy (``to_host=None``, the default): ``batch.states`` etc. are numpy
+        arrays exactly as the reference's, materialised on first access; ``update_params(batch)`` reads the device tensors
+        directly, and re-uploads an array only if the caller touched it.  ``to_host=True`` copies every field eagerly into
+        pinned host buffers (asynchronous DMA, one synchronise).  ``next_states`` - never read by the update
+        (agent_ego.py:37-42) - is recorded only with ``to_host=True`` or ``agent.keep_next_states = True``.
+        The batch aliases buffers that the NEXT sample() overwrites (both the device tensors and the pinned host copies):
+        a batch kept across iterations must be copied by the caller; the reference returns independent arrays."""
         t_start = time.time()
         self.pre_sample()
         E, T = self.plan(min_batch_size)
@@ -329,12 +353,15 @@ class Agent:
             fix_head_lb=self.env.fix_head_lb, noise_rate=self.noise_rate, mean_action=self.mean_action,
             zf_mean=zm, zf_std=zs, zf_clip=clip, seed=self.env._seed, iteration=self.iteration,
             eps=p.get('eps'), reset_take=p.get('reset_take'), reset_start=p.get('reset_start'),
-            mean_flag=p.get('mean_flag'), want_next=to_host, want_raw=rs is not None, out=self._out,
+            mean_flag=p.get('mean_flag'), want_next=bool(to_host) or self.keep_next_states, want_raw=rs is not None, out=self._out,
             ctx=ctx, win_off=win_off, **self._rollout_extra())
         self.iteration += 1
         if rs is not None:
             self._merge_obs(out['raw_obs'])
-        batch = self.traj_cls(dev={k: out.get(k) for k in self.traj_cls.fields}, horizon=T)
+        dev = {k: out.get(k) for k in self.traj_cls.fields}
+        if not (to_host or self.keep_next_states):
+            dev['next_states'] = None       # a buffer left from an earlier to_host=True rollout would be stale
+        batch = self.traj_cls(dev=dev, horizon=T)
         lg = out['logger']
         lg = dist_utils.reduce_logger_(lg.clone(), (lib.LOG['MIN_C_REWARD'], lib.LOG['MIN_EPISODE_REWARD']),
                                        (lib.LOG['MAX_C_REWARD'], lib.LOG['MAX_EPISODE_REWARD']))
@@ -381,10 +408,21 @@ class AgentPG(Agent):
         self._xcaches = {}
 
     # ---- flat storage ------------------------------------------------------------------------------
+    def _named_params(self):
+        """(policy list, value list) of (name, parameter): the nets plus the video-context nets the optimizers also own
+        (ego_mimic.py:68-69); the grad-norm clip spans policy_net and policy_vs_net jointly"""
+        pol = [(n, p) for n, p in self.policy_net.named_parameters() if p.requires_grad]
+        val = [(n, p) for n, p in self.value_net.named_parameters() if p.requires_grad]
+        for lst, vs in ((pol, getattr(self, 'policy_vs_net', None)), (val, getattr(self, 'value_vs_net', None))):
+            if isinstance(vs, (VideoStateNet, VideoForecastNet)):
+                lst += [('vs.' + n, p) for n, p in vs.named_parameters() if p.requires_grad]
+        return pol, val
+
     def _setup(self):
         if self._nets is not None:
-            self._pf.realias()
-            self._vf.realias()
+            pol, val = self._named_params()
+            self._pf.realias(pol)
+            self._vf.realias(val)
             return
         for opt in (self.optimizer_policy, self.optimizer_value):
             if not isinstance(opt, torch.optim.Adam):
@@ -393,13 +431,7 @@ class AgentPG(Agent):
             if g.get('weight_decay', 0) or g.get('amsgrad', False):
                 raise lib.EgpError('weight_decay / amsgrad are not supported by the fused Adam')
         dev = self.policy_net.action_mean.weight.device
-        pol = [(n, p) for n, p in self.policy_net.named_parameters() if p.requires_grad]
-        val = [(n, p) for n, p in self.value_net.named_parameters() if p.requires_grad]
-        # the optimizers also own the video-context nets' parameters (ego_mimic.py:68-69); the grad-norm clip spans
-        # policy_net and policy_vs_net jointly
-        for lst, vs in ((pol, getattr(self, 'policy_vs_net', None)), (val, getattr(self, 'value_vs_net', None))):
-            if isinstance(vs, (VideoStateNet, VideoForecastNet)):
-                lst += [('vs.' + n, p) for n, p in vs.named_parameters() if p.requires_grad]
+        pol, val = self._named_params()
         if not (trunk_ok(self.policy_net.net) and trunk_ok(self.value_net.net)):
             raise lib.EgpError('fused path needs two-hidden-layer relu MLP trunks')
         self._pf = _FlatNet(pol, self.optimizer_policy, dev)

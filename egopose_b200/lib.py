@@ -420,7 +420,7 @@ class Model:
         pw.d_W3, pw.d_b3, pw.d_log_std = ptr(weights['W3']), ptr(weights['b3']), ptr(weights['log_std'])
         check(self.lib.egp_rollout_f64(self.handle, C.byref(pw), C.byref(cfg), C.byref(inp), C.byref(o), stream_ptr()),
               'egp_rollout_f64')
-        launches += 4
+        launches += 5               # 3 weight packs + rollout kernel + logger merge
         return out
 
     def build_input(self, states, v_metas, masks, horizon):

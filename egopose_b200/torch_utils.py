@@ -20,27 +20,40 @@ class _Restore:
 
 
 class to_cpu(_Restore):
-    """utils/torch.py:13-27.  The fused sampler reads the policy parameters where they are (GPU), so
-    callers no longer need this around sample(); kept for checkpointing (ego_mimic.py:134)."""
+    """utils/torch.py:13-27: inside the context the models' tensors live on the CPU (checkpointing, ego_mimic.py:134).
+    Implemented the way the PyTorch of the reference's era behaved - every parameter / buffer keeps its identity and only
+    its ``.data`` is swapped, the original tensors come back on exit - so the flat parameter buffers of the fused agents
+    (and the caller's optimizer) stay aliased.  The fused sampler reads the policy parameters where they are (GPU), so
+    callers no longer need this around sample()."""
 
     def __init__(self, *models):
         self.models = [x for x in models if x is not None]
-        self.prev = [_dev(x) if list(x.parameters()) else torch.device('cpu') for x in self.models]
-        for x in self.models:
-            x.to(torch.device('cpu'))
+        self.saved = []
+        for m in self.models:
+            for t in list(m.parameters()) + list(m.buffers()):
+                self.saved.append((t, t.data))
+                t.data = t.data.to(torch.device('cpu'))
 
     def __exit__(self, *args):
-        for x, d in zip(self.models, self.prev):
-            x.to(d)
+        for t, d in self.saved:
+            t.data = d
         return False
 
 
-class to_device(to_cpu):
+class to_device(_Restore):
+    """utils/torch.py:30-44.  ego_mimic.py:66 calls it as a plain statement to place the nets for good (the object is
+    dropped without leaving the context); as a context manager it moves them back on exit."""
+
     def __init__(self, device, *models):
         self.models = [x for x in models if x is not None]
         self.prev = [_dev(x) if list(x.parameters()) else device for x in self.models]
         for x in self.models:
             x.to(device)
+
+    def __exit__(self, *args):
+        for x, d in zip(self.models, self.prev):
+            x.to(d)
+        return False
 
 
 class to_test(_Restore):

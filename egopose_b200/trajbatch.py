@@ -25,7 +25,8 @@ class TrajBatch:
         if name in _FIELDS:
             if name not in self._host:
                 if name not in self.dev or self.dev[name] is None:
-                    raise AttributeError(name)
+                    raise AttributeError('%s was not recorded by this rollout%s' % (
+                        name, ' (set agent.keep_next_states = True or sample(to_host=True))' if name == 'next_states' else ''))
                 a = self.dev[name].cpu().numpy()
                 if name in ('masks', 'exps'):
                     a = a.astype(np.int64)          # reference stores python ints (agents/agent.py:60-61)

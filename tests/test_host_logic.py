@@ -186,3 +186,48 @@ def test_checkpoint_roundtrip_and_reference_names(tmp_path):
         import subprocess
         out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True)
         assert out.stdout.strip().endswith('ok'), out.stderr[-1500:]
+
+
+def test_checkpoint_optimizer_and_rng_state(tmp_path):
+    """optimizer / RNG state travel under keys the reference ignores; the base format is unchanged"""
+    import pickle
+    import types
+    import torch
+    from egopose_b200 import checkpoint, zfilter
+    from egopose_b200.nets import MLP, PolicyGaussian, Value
+    torch.set_default_dtype(torch.float64)
+    pol, val = PolicyGaussian(MLP(6, (8, 4), 'relu'), 3), Value(MLP(6, (8, 4), 'relu'))
+    opt_p, opt_v = torch.optim.Adam(pol.parameters(), lr=1e-3), torch.optim.Adam(val.parameters(), lr=1e-3)
+    for opt, net in ((opt_p, pol), (opt_v, val)):
+        out = net(torch.randn(5, 6))
+        (out.loc if hasattr(out, 'loc') else out).sum().backward()
+        opt.step()
+    agent = types.SimpleNamespace(env=types.SimpleNamespace(_seed=7), iteration=42)
+    path = str(tmp_path / 'iter_0001.p')
+    checkpoint.save_checkpoint(path, pol, None, val, None, zfilter.ZFilter((4,), clip=5), opt_p, opt_v, agent)
+    raw = checkpoint._Unpickler(open(path, 'rb')).load()
+    assert {'policy_dict', 'policy_vs_dict', 'value_dict', 'value_vs_dict', 'running_state'} <= set(raw)     # reference keys
+    assert raw['rng']['seed'] == 7 and raw['rng']['iteration'] == 42
+    pol2 = PolicyGaussian(MLP(6, (8, 4), 'relu'), 3)
+    opt_p2 = torch.optim.Adam(pol2.parameters(), lr=1e-3)
+    agent2 = types.SimpleNamespace(env=types.SimpleNamespace(_seed=0), iteration=0)
+    cp, _ = checkpoint.load_checkpoint(path, pol2, None, None, None)
+    checkpoint.restore_training_state(cp, optimizer_policy=opt_p2, agent=agent2)
+    st, st2 = opt_p.state[pol.action_mean.weight], opt_p2.state[pol2.action_mean.weight]
+    assert torch.equal(st['exp_avg'], st2['exp_avg']) and float(st2['step']) == 1.0
+    assert agent2.iteration == 42 and agent2.env._seed == 7
+
+
+def test_cnn_feature_file_roundtrip(tmp_path):
+    """gen_cnn_feature.py:68-70: pickle of (dict take -> [L, F], meta); HumanoidEnv.load_experts reads element 0"""
+    import pickle
+    import numpy as np
+    from egopose_b200 import dataset
+    feats = {'take_a': np.random.RandomState(0).randn(12, 128), 'take_b': np.random.RandomState(1).randn(9, 128)}
+    path = str(tmp_path / 'features' / 'cnn_feat_x.p')
+    dataset.write_cnn_feat_file(path, feats, cfg='subject_03', it=100, meta_id='meta_subject_03')
+    got, meta = pickle.load(open(path, 'rb'))       # exactly what humanoid_v1.py:49 does
+    assert set(got) == set(feats) and all(np.array_equal(got[k], feats[k]) for k in feats)
+    assert meta['cfg'] == 'subject_03' and meta['iter'] == 100 and meta['meta'] == 'meta_subject_03' and 'time' in meta
+    g2, _ = dataset.read_cnn_feat_file(path)
+    assert np.array_equal(g2['take_b'], feats['take_b'])

@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """SURVEY 8e test on real NCCL: a 2-rank data-parallel iteration (environments sharded, per-epoch gradient
 all-reduce, global advantage moments / exps count) must produce the same parameters as one rank processing the
-concatenated batch.  Launch:  torchrun --nproc-per-node 2 tools/check_multi_gpu.py   (prints PASS/FAIL on rank 0)."""
+concatenated batch.  Launch:  torchrun --nproc-per-node 2 tools/check_multi_gpu.py   (prints PASS/FAIL on rank 0).
+EGP_CHECK_BACKEND=gloo EGP_CHECK_SAME_DEVICE=1 lets all ranks share cuda:0 (tests/test_gpu_scale.py on a 1-GPU lease)."""
+import argparse
 import os
 import sys
 
@@ -40,11 +42,21 @@ def build(device, E, T, EPL, CD):
 
 
 def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--envs', type=int, default=32)
+    ap.add_argument('--horizon', type=int, default=12)
+    args = ap.parse_args()
     world, rank, local = int(os.environ['WORLD_SIZE']), int(os.environ['RANK']), int(os.environ['LOCAL_RANK'])
+    backend = os.environ.get('EGP_CHECK_BACKEND', 'nccl')
+    if os.environ.get('EGP_CHECK_SAME_DEVICE') == '1':
+        local = 0
     torch.cuda.set_device(local)
     device = torch.device('cuda', local)
-    dist.init_process_group('nccl', device_id=device)
-    E, T, EPL, CD = 32, 12, 10, 16
+    if backend == 'nccl':
+        dist.init_process_group('nccl', device_id=device)
+    else:
+        dist.init_process_group(backend)
+    E, T, EPL, CD = args.envs, args.horizon, 10, 16
     rng = np.random.RandomState(7)
     rt, rs = rng.randint(0, 3, size=(E, T)), rng.randint(10, 70 - EPL - 10, size=(E, T))
     eps = rng.randn(E * T, 52)
@@ -80,7 +92,7 @@ def main():
         ok = replicas_identical and perr < 1e-9 and lerr < 1e-10 and verr < 1e-10 and log.num_steps == E * T
         print('world %d: replicas bit-identical %s | params rel err vs 1-GPU %.2e | surr abs err %.2e | vloss rel err %.2e | '
               'logger steps %d avg_c_reward %.6f vs %.6f -> %s' % (world, replicas_identical, perr, lerr, verr, log.num_steps,
-                                                                   log.avg_c_reward, log1.avg_c_reward, 'PASS' if ok else 'FAIL'))
+                                                                   log.avg_c_reward, log1.avg_c_reward, 'PASS EQUIVALENT' if ok else 'FAIL'))
         sys.exit(0 if ok else 1)
 
 
