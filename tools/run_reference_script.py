@@ -26,6 +26,8 @@ def prepare(workdir, task, cfg_id, iters, batch, ckpt_every, episode_len=None, w
     from egopose_b200.config import Config
     src = json.load(open(os.path.join(ROOT, 'egopose_b200', 'assets', '%s_subject_03.cfg.json' % task)))
     src.update(max_iter_num=iters, min_batch_size=batch, save_model_interval=ckpt_every)
+    if task == 'egoforecast':       # warm start from the ego-mimic checkpoint of the same scratch directory (ego_forecast.py:60-69)
+        src.update(ego_mimic_cfg=cfg_id, ego_mimic_iter=iters)
     if episode_len:
         src['env_episode_len'] = episode_len
     os.makedirs(os.path.join(workdir, 'config', task), exist_ok=True)
