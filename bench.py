@@ -60,6 +60,8 @@ def parse():
     ap.add_argument('--hidden', type=int, nargs=2, default=None)
     ap.add_argument('--epochs', type=int, default=10)
     ap.add_argument('--no-variants', action='store_true', help='skip the cuBLAS / 7-slice update timings')
+    ap.add_argument('--vsnet', action='store_true', help='egomimic with the learned VideoStateNet (BiLSTM 128 -> 2 x 64 over T + 2 m '
+                    'CNN-feature frames) as policy / value context instead of the per-frame table; episodes run the full horizon')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-envs', type=int, default=0, help='envs in the CPU sample (0 = 2 per core)')
@@ -71,6 +73,8 @@ def parse():
     args.horizon = args.horizon or c['horizon']
     args.hidden = args.hidden or list(c['hidden'])
     args.task, args.cfg_id, args.n_takes, args.minibatch, args.workload = c['task'], c['cfg'], c['n_takes'], c['minibatch'], c['workload']
+    if args.vsnet:
+        args.workload += ' [VideoStateNet context nets in sample and update (video_state_net.py), head-height fail rule off]'
     if (args.envs, args.horizon, args.hidden) != (c['envs'], c['horizon'], list(c['hidden'])):
         args.workload += ' [overridden: %d envs x %d steps, hidden %s]' % (args.envs, args.horizon, args.hidden)
     return args
@@ -142,7 +146,7 @@ def build_agent(args, device, takes, cnn, gemm=None, oz_slices=None):
     from egopose_b200.agent import AgentEgo
     from egopose_b200.config import Config
     from egopose_b200.env import HumanoidEnv
-    from egopose_b200.nets import MLP, FrameContext, PolicyGaussian, Value, VideoForecastNet
+    from egopose_b200.nets import MLP, FrameContext, PolicyGaussian, Value, VideoForecastNet, VideoStateNet
     from egopose_b200.zfilter import ZFilter
     torch.set_default_dtype(torch.float64)
     torch.manual_seed(1)
@@ -156,6 +160,11 @@ def build_agent(args, device, takes, cnn, gemm=None, oz_slices=None):
         mk = lambda: VideoForecastNet(128, sd, 128, cfg.fr_margin, 'lstm', None, 128, 'lstm').to(device)  # noqa: E731
         pvs, vvs = mk(), mk()
         in_dim = pvs.out_dim
+    elif getattr(args, 'vsnet', False):     # ego_mimic.py:52-53: BiLSTM video context, re-run on every forward of the update
+        pvs = VideoStateNet(128, cfg.policy_v_hdim, cfg.fr_margin, 'lstm', None, False).to(device)
+        vvs = VideoStateNet(128, cfg.value_v_hdim, cfg.fr_margin, 'lstm', None, False).to(device)
+        in_dim = sd + cfg.policy_v_hdim
+        env.set_fix_head_lb(-10.0)          # full-length episodes, as in a trained run (contact-less bodies fall after ~9 steps)
     else:
         pvs, vvs, in_dim = FrameContext(128), FrameContext(128), sd + 128
     policy = PolicyGaussian(MLP(in_dim, args.hidden, 'relu'), ad, log_std=cfg.log_std, fix_std=cfg.fix_std).to(device)

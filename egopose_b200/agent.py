@@ -41,7 +41,7 @@ class _FlatNet:
     """Flat parameter / gradient / Adam-moment storage for one optimizer; the module parameters and the
     torch.optim.Adam state become views of it."""
 
-    def __init__(self, named, optimizer, device):
+    def __init__(self, named, optimizer, device, grad=None):
         self.names = [n for n, _ in named]
         self.params = [p for _, p in named]
         self.optimizer = optimizer
@@ -50,7 +50,7 @@ class _FlatNet:
         n = int(self.offsets[-1])
         f64 = dict(dtype=torch.float64, device=device)
         self.flat = torch.empty(n, **f64)
-        self.grad = torch.zeros(n, **f64)
+        self.grad = torch.zeros(n, **f64) if grad is None else grad     # may be a slice of a buffer shared with another net
         self.m = torch.zeros(n, **f64)
         self.v = torch.zeros(n, **f64)
         self.norm2 = torch.zeros(1, **f64)
@@ -434,8 +434,12 @@ class AgentPG(Agent):
         pol, val = self._named_params()
         if not (trunk_ok(self.policy_net.net) and trunk_ok(self.value_net.net)):
             raise lib.EgpError('fused path needs two-hidden-layer relu MLP trunks')
-        self._pf = _FlatNet(pol, self.optimizer_policy, dev)
-        self._vf = _FlatNet(val, self.optimizer_value, dev)
+        # ONE flat [value | policy] gradient buffer: with several ranks every PPO epoch all-reduces it once
+        nv = sum(p.numel() for _, p in val)
+        npol = sum(p.numel() for _, p in pol)
+        self._gflat = torch.zeros(nv + npol, dtype=torch.float64, device=dev)
+        self._pf = _FlatNet(pol, self.optimizer_policy, dev, grad=self._gflat[nv:])
+        self._vf = _FlatNet(val, self.optimizer_value, dev, grad=self._gflat[:nv])
         self._pt = _Trunk(self._pf, 'action_mean')
         self._vt = _Trunk(self._vf, 'value_head')
         self._learn_std = 'action_log_std' in self._pf.names
@@ -503,7 +507,7 @@ class AgentPG(Agent):
         ent['live'] = True
         return ent
 
-    def update_value(self, x, returns, inv_n, reuse_forward=False, cache=True):
+    def update_value(self, x, returns, inv_n, reuse_forward=False, cache=True, defer=False):
         """agents/agent_pg.py:19-26.  ``reuse_forward``: the activations of the value forward that produced the
         GAE inputs are still valid (no parameter step since), so the first epoch skips its forward GEMMs.
         ``x`` is a tensor or a _NetInput."""
@@ -519,6 +523,8 @@ class AgentPG(Agent):
                         loss=dict(kind='value', returns=returns, inv_n=inv_n, loss=self._scal[0:1]))
                 if inp.learned:
                     inp.backward(dx)
+                if defer:               # the caller all-reduces the flat [value | policy] gradient once and steps both nets
+                    continue
                 d = _dist()
                 if d is not None:
                     d.all_reduce(self._vf.grad)
@@ -535,10 +541,21 @@ class AgentPG(Agent):
             dx = self._vt.backward(dv, inp.cd if inp.learned else 0)
             if inp.learned:
                 inp.backward(dx)
+            if defer:
+                continue
             d = _dist()
             if d is not None:
                 d.all_reduce(self._vf.grad)
             self._vf.adam(0.0)
+
+    def _reduce_and_step(self, max_norm):
+        """one sum all-reduce of the flat [value | policy] gradient, then both optimizer steps (value first, agent_ppo.py:46-51;
+        the nets share no parameters, so stepping the value net after the policy backward changes nothing)"""
+        d = _dist()
+        if d is not None:
+            d.all_reduce(self._gflat)
+        self._vf.adam(0.0)
+        self._pf.adam(max_norm)
 
     def update_params(self, batch):
         t0 = time.time()
@@ -596,7 +613,8 @@ class AgentPPO(AgentPG):
             raise lib.EgpError('one (params, max_norm) clip group is supported (ego_mimic.py:90)')
         return float(self.policy_grad_clip[0][1])
 
-    def _policy_step(self, xp, actions, adv, logp0, exps, inv_count, log_std, max_norm, mu=None, cache=True, init_logp0=False):
+    def _policy_step(self, xp, actions, adv, logp0, exps, inv_count, log_std, max_norm, mu=None, cache=True, init_logp0=False,
+                     defer=False):
         """ppo_loss forward+backward, gradient all-reduce, clip + Adam (agent_ppo.py:47-51 / :38-43)"""
         inp = xp if isinstance(xp, _NetInput) else _NetInput(x_const=xp)
         oz = self._oz(self._pt, inp)
@@ -615,6 +633,8 @@ class AgentPPO(AgentPG):
                               init_logp0=init_logp0))
             if inp.learned:
                 inp.backward(dx)
+            if defer:
+                return self._scal[1:2].clone()
             if _dist() is not None:
                 _dist().all_reduce(self._pf.grad)
             self._pf.adam(max_norm)
@@ -632,6 +652,8 @@ class AgentPPO(AgentPG):
         dx = self._pt.backward(dmu, inp.cd if inp.learned else 0)
         if inp.learned:
             inp.backward(dx)
+        if defer:
+            return self._scal[1:2].clone()
         if _dist() is not None:
             _dist().all_reduce(self._pf.grad)
         self._pf.adam(max_norm)
@@ -671,10 +693,14 @@ class AgentPPO(AgentPG):
             ws = dist_utils.world_size()
             for i in range(nb):
                 lo, hi = i * B, min((i + 1) * B, n)
-                self.update_value(gxv[lo:hi], g['ret'][lo:hi], 1.0 / ((hi - lo) * ws), cache=False)
+                defer = _dist() is not None and self.value_opt_niter == 1
+                self.update_value(gxv[lo:hi], g['ret'][lo:hi], 1.0 / ((hi - lo) * ws), cache=False, defer=defer)
                 vloss.append(self._scal[0:1].clone())
                 surr.append(self._policy_step(g['xp'][lo:hi], g['ac'][lo:hi], g['adv'][lo:hi], g['lp'][lo:hi], g['ex'][lo:hi],
-                                              (1.0 / float(counts[i])) if counts[i] > 0 else 0.0, log_std, max_norm, cache=False))
+                                              (1.0 / float(counts[i])) if counts[i] > 0 else 0.0, log_std, max_norm, cache=False,
+                                              defer=defer))
+                if defer:
+                    self._reduce_and_step(max_norm)
         self.last_info = dict(surr_loss=surr, value_loss=vloss)
 
     def update_policy(self, xp, xv, actions, returns, adv, exps, inv_count, inv_n):
@@ -714,17 +740,26 @@ class AgentPPO(AgentPG):
             if getattr(self, '_vstream', None) is None:
                 self._vstream = torch.cuda.Stream()
             self._vstream.wait_stream(cur)
+        # several ranks: both backward passes of an epoch first, then ONE all-reduce of the flat [value | policy] gradient
+        # (SURVEY 8e collective C1) and both optimizer steps; the two streams join at that point
+        defer = d is not None and self.value_opt_niter == 1
         for ep in range(self.opt_num_epochs):
             if two:
                 with torch.cuda.stream(self._vstream):
-                    self.update_value(xv, returns, inv_n)
+                    self.update_value(xv, returns, inv_n, defer=defer)
                     vloss.append(self._scal[0:1].clone())
             else:
-                self.update_value(xv, returns, inv_n, reuse_forward=(ep == 0 and self._value_fresh))     # :46
+                self.update_value(xv, returns, inv_n, reuse_forward=(ep == 0 and self._value_fresh), defer=defer)     # :46
                 vloss.append(self._scal[0:1].clone())
             surr.append(self._policy_step(xp, actions, adv, logp0, exps, inv_count, log_std, max_norm,
                                           mu=mu if ep == 0 else None,       # epoch 0 reuses the fixed-log-prob forward
-                                          init_logp0=fuse0 and ep == 0))
+                                          init_logp0=fuse0 and ep == 0, defer=defer))
+            if defer:
+                if two:
+                    torch.cuda.current_stream().wait_stream(self._vstream)
+                self._reduce_and_step(max_norm)
+                if two:
+                    self._vstream.wait_stream(torch.cuda.current_stream())
         if two:
             torch.cuda.current_stream().wait_stream(self._vstream)
         self.last_info = dict(surr_loss=surr, value_loss=vloss)

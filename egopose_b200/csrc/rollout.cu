@@ -32,6 +32,7 @@ namespace egp { __device__ unsigned long long g_t4_clk2[16]; __device__ long lon
 #define EGP_CLK_MARK(slot) { long long _t = clock64(); if (blockIdx.x == 0 && threadIdx.x == 0) { egp::g_t4_clk2[slot] += _t - egp::g_t4_last; egp::g_t4_last = _t; } }
 #endif
 #include "tree.cuh"
+#include "dmma.cuh"
 
 namespace egp {
 
@@ -1000,86 +1001,7 @@ __device__ __forceinline__ double t4_obs_entry(const T4Ctx &x, int k, double hd0
     return x.at(x.o.v, j);
 }
 
-// ---- policy MLP on the FP64 tensor cores --------------------------------------------------------------------------
-// One dense layer for the CTA's 32 environments = [32 x K] . [K x N]: mma.sync m8n8k4 f64 (DMMA) issues 256 FMAs per
-// instruction at the DFMA pipe's FLOP rate (measured: 16 cycles per DMMA and sub-partition, tools/micro/fp64_probe.cu),
-// i.e. 8x fewer issue slots than the SIMT loop it replaces, and - decisive here - its operands are distributed over the
-// lanes: an activation fragment is one conflict-free 256-byte shared load, a weight fragment one coalesced 256-byte
-// global load of weights pre-packed in fragment order, instead of four 2-wavefront broadcast loads per 8 FMAs.
-// Activations live feature-major with a row stride of XS = 36 doubles: the four k rows of a fragment then fall on
-// disjoint bank groups (stride 32 would be a 4-way conflict).  Work item = 16 environments x 16 neurons (2 x 2
-// fragments); 2 * N/16 items are dealt round-robin to the 8 warps.
-constexpr int XS_WIDE = 36;                  // default row stride; 32 (4-way conflicts on the fragment loads) when 36 does not fit
-constexpr int MLP_NT = 16;                   // neurons per work item; weights / biases are padded to multiples of 16
-
-__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
-}
-
-// accumulates acc[mf][nf] += x[16 envs of half eh][k in 4 kc0 .. 4 kc1) . W[neuron tile nt][k]; Wf = [N/8][K4][32] fragments,
-// K4 (a multiple of 4) = padded K / 4; xs row r holds k = row_k0 + r
-__device__ __forceinline__ void t4_dmma_acc(double (&acc)[2][2][2], const double *__restrict__ Wf, int K4, int nt, int kc0, int kc1,
-                                            int row_k0, const double *xs, int XS, int eh, int lane) {
-    const double *w0 = Wf + ((size_t)(2 * nt) * K4) * 32 + lane, *w1 = w0 + (size_t)K4 * 32;
-    const double *xa = xs + (ptrdiff_t)((lane & 3) - row_k0) * XS + eh * 16 + (lane >> 2);
-    double bn[4][2];
-#pragma unroll
-    for (int u = 0; u < 4; u++) { bn[u][0] = __ldg(w0 + (size_t)(kc0 + u) * 32); bn[u][1] = __ldg(w1 + (size_t)(kc0 + u) * 32); }
-    for (int g = kc0; g < kc1; g += 4) {
-        double bc[4][2];
-#pragma unroll
-        for (int u = 0; u < 4; u++) { bc[u][0] = bn[u][0]; bc[u][1] = bn[u][1]; }
-        if (g + 4 < kc1) {
-#pragma unroll
-            for (int u = 0; u < 4; u++) { bn[u][0] = __ldg(w0 + (size_t)(g + 4 + u) * 32); bn[u][1] = __ldg(w1 + (size_t)(g + 4 + u) * 32); }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const double a0 = xa[(size_t)(4 * (g + u)) * XS], a1 = xa[(size_t)(4 * (g + u)) * XS + 8];
-            dmma884(acc[0][0], a0, bc[u][0]);
-            dmma884(acc[0][1], a0, bc[u][1]);
-            dmma884(acc[1][0], a1, bc[u][0]);
-            dmma884(acc[1][1], a1, bc[u][1]);
-        }
-    }
-}
-
-__device__ __forceinline__ void t4_dmma_init(double (&acc)[2][2][2], const double *__restrict__ bias, int nt, int lane) {
-#pragma unroll
-    for (int nf = 0; nf < 2; nf++)
-#pragma unroll
-        for (int c = 0; c < 2; c++) {
-            const double bv = bias[nt * MLP_NT + nf * 8 + 2 * (lane & 3) + c];
-            acc[0][nf][c] = bv; acc[1][nf][c] = bv;
-        }
-}
-
-template <bool RELU>
-__device__ __forceinline__ void t4_dmma_store(const double (&acc)[2][2][2], int row0, double *ys, int XS, int eh, int lane) {
-#pragma unroll
-    for (int mf = 0; mf < 2; mf++)
-#pragma unroll
-        for (int nf = 0; nf < 2; nf++)
-#pragma unroll
-            for (int c = 0; c < 2; c++) {
-                const double v = acc[mf][nf][c];
-                ys[(size_t)(row0 + nf * 8 + 2 * (lane & 3) + c) * XS + eh * 16 + mf * 8 + (lane >> 2)] = RELU ? fmax(v, 0.0) : v;
-            }
-}
-
-// neuron tiles [nt0, nt1) of one dense layer: ys[(16 (nt - nt0) + j) + out_row0][env] = act(bias + W x)
-template <bool RELU>
-__device__ __forceinline__ void t4_mlp_layer(const double *__restrict__ Wf, const double *__restrict__ bias, int K4, int nt0, int nt1,
-                                             int out_row0, const double *xs, double *ys, int XS, int lane, int w) {
-    for (int t = w; t < 2 * (nt1 - nt0); t += T4_WARPS) {
-        const int eh = t & 1, nt = nt0 + (t >> 1);
-        double acc[2][2][2];
-        t4_dmma_init(acc, bias, nt, lane);
-        t4_dmma_acc(acc, Wf, K4, nt, 0, K4, 0, xs, XS, eh, lane);
-        t4_dmma_store<RELU>(acc, (nt - nt0) * MLP_NT + out_row0, ys, XS, eh, lane);
-    }
-}
-
+// ---- policy MLP on the FP64 tensor cores (csrc/dmma.cuh) ------------------------------------------------------------
 // PolicyGaussian trunk + head for the CTA's 32 environments (policy_gaussian.py:19-24, mlp.py:22-25):
 // xs [D rows, zero rows up to the padded K] -> action means in h1s rows [0, A).  Normal path: three full layers.
 // Chunked path (second hidden layer too wide for shared memory): layer 2 is produced MLP_C2 neurons at a time into the
@@ -1650,23 +1572,7 @@ __global__ void logger_merge_kernel(const double *__restrict__ part, int nblk, d
     out[k] = v;
 }
 
-// packs W [out][in] -> DMMA fragments Wf[outp / 8][K4][32]: element (nf, kc, lane) = W[8 nf + lane / 4][4 kc + lane % 4]
-// (zero padded both ways; outp a multiple of 16, K4 a multiple of 4), biases padded (T4 policy MLP)
-__global__ void pack_frag_kernel(const double *__restrict__ W, const double *__restrict__ b, int out, int in, int outp, int K4,
-                                 double *__restrict__ Wf, double *__restrict__ bp) {
-    const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    const long long total = (long long)(outp / 8) * K4 * 32;
-    if (idx < total) {
-        const int lane = (int)(idx & 31);
-        const long long t = idx >> 5;
-        const int kc = (int)(t % K4), nf = (int)(t / K4);
-        const int j = 8 * nf + (lane >> 2), k = 4 * kc + (lane & 3);
-        Wf[idx] = (j < out && k < in) ? W[(size_t)j * in + k] : 0.0;
-    }
-    if (idx < outp) bp[idx] = idx < out ? b[idx] : 0.0;
-}
-
-// transposes W [out][in] -> Wt [in][outp] (zero padded), biases padded
+// transposes W [out][in] -> Wt [in][outp] (zero padded), biases padded (one-warp V1 kernel)
 __global__ void transpose_pad_kernel(const double *__restrict__ W, const double *__restrict__ b, int out, int in, int outp,
                                      double *__restrict__ Wt, double *__restrict__ bp) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -2024,7 +1930,7 @@ int egp_rollout_f64(EgpModel *m, const EgpPolicyWeights *pol, const EgpRolloutCf
     double *logp = w; w += log_elems;
     auto pack = [&](const double *W, const double *bsrc, int out_n, int in_n, int outp, int Kp, double *Wf, double *bp) {
         const long long total = (long long)outp * Kp;       // = (outp / 8) * (Kp / 4) * 32
-        pack_frag_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(W, bsrc, out_n, in_n, outp, Kp / 4, Wf, bp);
+        pack_frag_kernel_t<false><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(W, bsrc, out_n, in_n, outp, Kp / 4, Wf, bp);
     };
     if (vn) {
         double *v1 = w; w += (size_t)A.K1p * A.H1p;

@@ -123,6 +123,10 @@ SYMBOLS = {
     'egp_oz_mlp_chunk_rows': (_i64, []),
     'egp_oz_mlp_work_bytes': (_i64, [_int, _int, _int, _int, _i64, _int]),
     'egp_oz_mlp_xcache_bytes': (_i64, [_int, _i64, _i64, _int]),
+    'egp_lstm_wfrag_elems': (_i64, [_int]),
+    'egp_lstm_pack_whh_f64': (_int, [_vp, _int, _vp, _vp, _vp]),
+    'egp_lstm_seq_fwd_f64': (_int, [_vp, _vp, _int, _i64, _int, _vp, _vp, _vp, _vp, _vp]),
+    'egp_lstm_seq_bwd_f64': (_int, [_vp, _vp, _vp, _vp, _int, _i64, _int, _vp, _vp, _vp]),
     'egp_oz_mlp_step_f64': (_int, [C.POINTER(MlpNet), _vp, _i64, _i64, C.POINTER(MlpLoss), _vp, _int, _i64, _vp, _int, _vp, _i64,
                                    _vp]),
 }
@@ -714,3 +718,44 @@ class OzMlp:
         if cache is not None:
             cache['valid'] = True
         return y
+
+
+# ---- fused LSTM sequence recurrence (csrc/lstm.cu) -----------------------------------------------
+LSTM_FUSED_H = (64, 128)
+
+
+def lstm_pack_whh(weight_hh):
+    """torch weight_hh [4H, H] -> (forward fragments, backward fragments) for lstm_seq_fwd / lstm_seq_bwd"""
+    global launches
+    import torch
+    H = weight_hh.shape[1]
+    n = load().egp_lstm_wfrag_elems(H)
+    wf = torch.empty(n, dtype=torch.float64, device=weight_hh.device)
+    wb = torch.empty(n, dtype=torch.float64, device=weight_hh.device)
+    check(load().egp_lstm_pack_whh_f64(ptr(weight_hh.contiguous()), H, ptr(wf), ptr(wb), stream_ptr()), 'egp_lstm_pack_whh_f64')
+    launches += 2
+    return wf, wb
+
+
+def lstm_seq_fwd(xi, off, L, B, H, wf):
+    """xi [Np, 4H] packed input projections, off int64 [L + 1] on the device -> (h [Np, H], gates [Np, 4H], c [Np, H])"""
+    global launches
+    import torch
+    Np = xi.shape[0]
+    h = torch.zeros((Np, H), dtype=torch.float64, device=xi.device)
+    gates = torch.empty((Np, 4 * H), dtype=torch.float64, device=xi.device)
+    c = torch.empty((Np, H), dtype=torch.float64, device=xi.device)
+    check(load().egp_lstm_seq_fwd_f64(ptr(xi), ptr(off), L, B, H, ptr(wf), ptr(h), ptr(gates), ptr(c), stream_ptr()),
+          'egp_lstm_seq_fwd_f64')
+    launches += 1
+    return h, gates, c
+
+
+def lstm_seq_bwd(dh, gates, c, off, L, B, H, wb):
+    global launches
+    import torch
+    dxi = torch.zeros_like(gates)
+    check(load().egp_lstm_seq_bwd_f64(ptr(dh), ptr(gates), ptr(c), ptr(off), L, B, H, ptr(wb), ptr(dxi), stream_ptr()),
+          'egp_lstm_seq_bwd_f64')
+    launches += 1
+    return dxi

@@ -12,6 +12,7 @@ the rollout and the PPO update read the parameter storage directly from the CUDA
 (egopose_b200/agent.py) and never call forward().
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -133,6 +134,38 @@ class FrameContext(nn.Module):
         raise RuntimeError('FrameContext is consumed inside the fused kernels (egp_rollout / egp_build_input)')
 
 
+class _LstmRecurrence(torch.autograd.Function):
+    """Sequential half of an LSTM sweep on the fused kernels (csrc/lstm.cu, egp_lstm_seq_fwd / bwd_f64): packed gate
+    pre-activations xi [Np, 4H] (= x W_ih^T + biases, a plain GEMM of the caller) -> hidden states [Np, H].  Rows are time-major
+    packed, step s owns rows [off[s], off[s+1]); ``prev`` maps a row to the row of the same batch element one step earlier
+    (-1 at its first step).  backward returns d xi and dW_hh = d xi^T H_prev (GEMM)."""
+
+    @staticmethod
+    def forward(ctx, xi, weight_hh, off, prev, L, B):
+        from . import lib
+        H = weight_hh.shape[1]
+        wf, wb = lib.lstm_pack_whh(weight_hh.detach())
+        h, gates, c = lib.lstm_seq_fwd(xi.detach().contiguous(), off, L, B, H, wf)
+        ctx.save_for_backward(h, gates, c, off, prev, wb)
+        ctx.dims = (L, B, H)
+        return h
+
+    @staticmethod
+    def backward(ctx, dh):
+        from . import lib
+        h, gates, c, off, prev, wb = ctx.saved_tensors
+        L, B, H = ctx.dims
+        dxi = lib.lstm_seq_bwd(dh.contiguous(), gates, c, off, L, B, H, wb)
+        # dW_hh = sum over rows of dxi_row^T h_prev_row: rows at their first step have h_prev = 0
+        hp = h.index_select(0, prev.clamp(min=0)) * (prev >= 0).to(h.dtype).unsqueeze(1)
+        return dxi, dxi.t() @ hp, None, None, None, None
+
+
+def _fused_lstm_ok(cell, x):
+    from . import lib
+    return x.is_cuda and x.dtype == torch.float64 and cell.hidden_size in lib.LSTM_FUSED_H and os.environ.get('EGP_LSTM', 'fused') == 'fused'
+
+
 class RNN(nn.Module):
     """models/rnn.py:5-61 mirror (LSTM cells only): parameters live in nn.LSTMCell modules named rnn_f / rnn_b so
     the state-dict keys match the reference; batch mode runs the whole sequence.  The input projection of all
@@ -165,6 +198,14 @@ class RNN(nn.Module):
         L, B, _ = x.shape
         H = cell.hidden_size
         xi = torch.addmm(cell.bias_ih + cell.bias_hh, x.reshape(L * B, -1), cell.weight_ih.t()).view(L, B, 4 * H)
+        if _fused_lstm_ok(cell, x):
+            # fused recurrence (one launch per sweep): iteration order = time order, reversed for the backward direction
+            xs = xi.flip(0) if reverse else xi
+            off = torch.arange(L + 1, device=x.device, dtype=torch.int64) * B
+            rows = torch.arange(L * B, device=x.device, dtype=torch.int64)
+            prev = torch.where(rows >= B, rows - B, torch.full_like(rows, -1))
+            hs = _LstmRecurrence.apply(xs.reshape(L * B, 4 * H), cell.weight_hh, off, prev, L, B).view(L, B, H)
+            return hs.flip(0) if reverse else hs
         h = x.new_zeros((B, H))
         c = x.new_zeros((B, H))
         whh_t = cell.weight_hh.t()
@@ -379,6 +420,20 @@ class VideoForecastNet(nn.Module):
         cell = self.s_net.rnn_f
         H = cell.hidden_size
         xi = torch.addmm(cell.bias_ih + cell.bias_hh, states, cell.weight_ih.t())    # input projection of every row
+        if _fused_lstm_ok(cell, states):
+            # fused recurrence over the ragged episodes: rows gathered time-major (episodes sorted longest first)
+            if 'packed' not in e:
+                alive = np.asarray(e['alive'][:e['tmax']], dtype=np.int64)
+                off = np.concatenate([[0], np.cumsum(alive)])
+                prev = np.full(int(off[-1]), -1, dtype=np.int64)
+                for t in range(1, e['tmax']):
+                    prev[off[t]:off[t + 1]] = off[t - 1] + np.arange(alive[t])
+                e['packed'] = dict(order=torch.cat(e['rows']), off=torch.as_tensor(off, device=states.device),
+                                   prev=torch.as_tensor(prev, device=states.device), B=int(alive[0]))
+            pk = e['packed']
+            hs = _LstmRecurrence.apply(xi.index_select(0, pk['order']), cell.weight_hh, pk['off'], pk['prev'], e['tmax'], pk['B'])
+            s_out = states.new_zeros((e['n'], H)).index_copy(0, pk['order'], hs)
+            return torch.cat((v_out, s_out), dim=1)
         whh_t = cell.weight_hh.t()
         h = states.new_zeros((int(e['alive'][0]), H))
         c = torch.zeros_like(h)

@@ -325,6 +325,23 @@ int egp_oz_mlp_step_f64(const EgpMlpNet *net, const double *d_x, int64_t ldx, in
                         int n_slices, int64_t chunk_rows, void *d_xcache, int xcache_state, void *d_work, int64_t work_bytes,
                         void *stream);
 
+/* --- fused LSTM sequence recurrence (csrc/lstm.cu) ------------------------------------------------------------------
+ * Replaces the per-step LSTMCell loops of models/rnn.py:45-61 (RNN.batch_forward: both directions of the BiLSTM of
+ * models/video_state_net.py:36-70) and the state-LSTM unroll of models/video_forecast_net.py:95-111 in the PPO update.  The
+ * non-recurrent GEMMs (input projection, weight gradients) stay with the caller.  Rows are "time-major packed": step s owns
+ * rows [off[s], off[s+1]) = the batch elements alive at step s (counts non-increasing; dense [L, B]: off[s] = s B); d_off is a
+ * DEVICE array of L + 1 int64.  Gate order i | f | g | o (torch.nn.LSTMCell).  hidden size H = 64 or 128. */
+int64_t egp_lstm_wfrag_elems(int H);    /* doubles per packed W_hh operand (4 H H) */
+/* d_Whh [4H][H] (torch weight_hh) -> tensor-core fragment order for the forward (h W_hh^T) and backward (dG W_hh) products */
+int egp_lstm_pack_whh_f64(const double *d_Whh, int H, double *d_Wf_fwd, double *d_Wf_bwd, void *stream);
+/* d_xi [Np][4H] = x W_ih^T + b_ih + b_hh  ->  d_h [Np][H], d_gates [Np][4H] (post-activation, saved for backward), d_c [Np][H] */
+int egp_lstm_seq_fwd_f64(const double *d_xi, const int64_t *d_off, int L, int64_t B, int H, const double *d_Wf_fwd, double *d_h,
+                         double *d_gates, double *d_c, void *stream);
+/* d_dh [Np][H] upstream gradient of every h  ->  d_dxi [Np][4H] gradient of the gate pre-activations (dW_hh = d_dxi^T H_prev,
+ * dW_ih = d_dxi^T X, db = column sums of d_dxi are GEMMs of the caller) */
+int egp_lstm_seq_bwd_f64(const double *d_dh, const double *d_gates, const double *d_c, const int64_t *d_off, int L, int64_t B, int H,
+                         const double *d_Wf_bwd, double *d_dxi, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
