@@ -383,9 +383,22 @@ def main():
             b.synchronize()
             bt.append(a.elapsed_time(b))
         bms = float(np.median(bt[1:]))
+        old_min = lib.gae_set_onepass_min(1 << 62)        # the small-batch (two-pass) kernels at this size, for comparison
+        bt2 = []
+        for rep in range(4):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            lib.gae(rb[0], rb[1], rb[2], cfg.gamma, cfg.tau, work=wb, out=ob)
+            b.record()
+            b.synchronize()
+            bt2.append(a.elapsed_time(b))
+        lib.gae_set_onepass_min(old_min)
         gae_big = {'bound': 'hbm', 'samples': NB, 'ms': bms, 'achieved': 5 * wbytes * NB / (bms / 1e3) / 1e9, 'peak': hbm,
                    'unit': 'GB/s', 'frac': 5 * wbytes * NB / (bms / 1e3) / 1e9 / hbm, 'bytes_per_sample': 40,
-                   'note': 'BASELINE config 5 batch (19.66 M samples, inputs + outputs 786 MB > L2), one call = 3 launches'}
+                   'ms_two_pass_kernels': float(np.median(bt2[1:])),
+                   'note': 'BASELINE config 5 batch (19.66 M samples, inputs + outputs 786 MB > L2), one call = one ticketed '
+                           'one-pass launch (+ a memset of its flags); the two-pass kernels used below %d samples are timed beside it'
+                           % old_min}
         del rb, ob, wb
     except Exception as e:        # noqa: BLE001
         gae_big = {'error': str(e)[:200]}

@@ -1159,7 +1159,7 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
             const long long ge = (long long)blockIdx.x * 32 + e;
             if (ge >= E) break;
             double *row = dst + ((size_t)ge * T + step_n) * width;
-            for (int k = lane; k < width; k += 32) row[k] = tile[(size_t)k * XS + e];
+            for (int k = lane; k < width; k += 32) __stcs(row + k, tile[(size_t)k * XS + e]);   // streaming: must not evict the CTAs' L2-resident scratch
         }
     };
     auto stage_share = [&](double *tile, const double *share) {     // this thread's strided share -> tile[k][env]

@@ -43,8 +43,17 @@ int num_sms(int device) {
 // No atomics, fences or spinning.  The second read of (r, m, V) comes out of L2 (inputs << 126 MB), so DRAM
 // traffic stays at the algorithmic 5 doubles / sample (3 in, 2 out).
 constexpr int GAE_THREADS = 256;
-constexpr int GAE_ITEMS = 8;
+#ifndef GAE_ITEMS_N
+#define GAE_ITEMS_N 8
+#endif
+constexpr int GAE_ITEMS = GAE_ITEMS_N;
 constexpr int GAE_TILE = GAE_THREADS * GAE_ITEMS;
+#ifndef GAE_EXP
+#define GAE_EXP 0
+#endif
+#ifndef GAE_ONEPASS_CTAS
+#define GAE_ONEPASS_CTAS 4
+#endif
 
 struct Moments { double n, mean, m2; };
 
@@ -54,6 +63,11 @@ __device__ __forceinline__ Moments merge(Moments a, Moments b) {
     Moments r;
     r.n = a.n + b.n;
     double d = b.mean - a.mean;
+    if (a.n == b.n) {                               // equal counts (every merge inside a full tile): the same arithmetic as
+        r.mean = a.mean + d * 0.5;                  // below with b.n / r.n = 1/2 and a.n b.n / r.n = a.n / 2, no division
+        r.m2 = a.m2 + b.m2 + d * d * (0.5 * a.n);
+        return r;
+    }
     r.mean = a.mean + d * (b.n / r.n);
     r.m2 = a.m2 + b.m2 + d * d * (a.n * b.n / r.n);
     return r;
@@ -74,9 +88,9 @@ __device__ __forceinline__ void gae_load_compose(const double *__restrict__ rew,
     if (vec && lo + GAE_ITEMS < n) {    // interior, 16-byte aligned arrays: 128-bit loads
 #pragma unroll
         for (int k = 0; k < GAE_ITEMS; k += 2) {
-            double2 r2 = *reinterpret_cast<const double2 *>(rew + lo + k);
-            double2 m2 = *reinterpret_cast<const double2 *>(msk + lo + k);
-            double2 v2 = *reinterpret_cast<const double2 *>(val + lo + k);
+            double2 r2 = __ldcs(reinterpret_cast<const double2 *>(rew + lo + k));       // read once: streaming
+            double2 m2 = __ldcs(reinterpret_cast<const double2 *>(msk + lo + k));
+            double2 v2 = __ldcs(reinterpret_cast<const double2 *>(val + lo + k));
             dl[k] = r2.x; dl[k + 1] = r2.y; c[k] = m2.x; c[k + 1] = m2.y; v[k] = v2.x; v[k + 1] = v2.y;
         }
         v[GAE_ITEMS] = val[lo + GAE_ITEMS];
@@ -98,6 +112,45 @@ __device__ __forceinline__ void gae_load_compose(const double *__restrict__ rew,
         D = dl[k] + c[k] * D;
         C = c[k] * C;
     }
+}
+
+// (n, mean, M2) of this thread's GAE_ITEMS advantages: two short sums instead of a Chan merge (with its divisions) per sample
+__device__ __forceinline__ Moments gae_thread_moments(const double *out_a, long long lo, long long n) {
+    Moments mom = {0.0, 0.0, 0.0};
+    if (lo + GAE_ITEMS <= n) {
+        double sum = 0.0;
+#pragma unroll
+        for (int k = 0; k < GAE_ITEMS; k++) sum += out_a[k];
+        mom.n = GAE_ITEMS; mom.mean = sum * (1.0 / GAE_ITEMS);
+#pragma unroll
+        for (int k = 0; k < GAE_ITEMS; k++) { const double d = out_a[k] - mom.mean; mom.m2 = fma(d, d, mom.m2); }
+    } else if (lo < n) {
+        double sum = 0.0;
+        for (int k = 0; k < GAE_ITEMS; k++) if (lo + k < n) { sum += out_a[k]; mom.n += 1.0; }
+        mom.mean = sum / mom.n;
+        for (int k = 0; k < GAE_ITEMS; k++) if (lo + k < n) { const double d = out_a[k] - mom.mean; mom.m2 = fma(d, d, mom.m2); }
+    }
+    return mom;
+}
+
+// (n, mean, M2) of a tile from the per-thread moments: shuffle tree per warp, then an ordered tree over the 8 warps
+// (equal counts at every level of a full tile: no divisions); valid in thread 0.  Contains one __syncthreads.
+__device__ __forceinline__ Moments gae_tile_moments(Moments mom, Moments *s_mom) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mom = merge(mom, shfl_down(mom, o));
+    if (lane == 0) s_mom[warp] = mom;
+    __syncthreads();
+    Moments t = {0.0, 0.0, 0.0};
+    if (warp == 0) {
+        if (lane < GAE_THREADS / 32) t = s_mom[lane];
+#pragma unroll
+        for (int o = 1; o < GAE_THREADS / 32; o <<= 1) {
+            Moments nb = shfl_down(t, o);
+            if ((lane & (2 * o - 1)) == 0) t = merge(t, nb);
+        }
+    }
+    return t;
 }
 
 // inclusive scan of the per-thread maps over the block in thread order (descending sample index);
@@ -139,7 +192,7 @@ gae_apply_kernel(const double *__restrict__ rew, const double *__restrict__ msk,
                  double tau, long long n, bool vec, unsigned int ntiles, const double *__restrict__ agg, double *__restrict__ adv,
                  double *__restrict__ ret, double *__restrict__ partial /* [ntiles][3] */) {
     __shared__ Moments s_mom[GAE_THREADS / 32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     const long long lo = (long long)blockIdx.x * GAE_TILE + (long long)(GAE_THREADS - 1 - tid) * GAE_ITEMS;
     double dl[GAE_ITEMS], c[GAE_ITEMS], v[GAE_ITEMS + 1], C, D, eC, eD, tC, tD;
     gae_load_compose(rew, msk, val, gamma, tau, n, lo, vec, dl, c, v, C, D);
@@ -151,17 +204,13 @@ gae_apply_kernel(const double *__restrict__ rew, const double *__restrict__ msk,
     }
     gae_block_scan(C, D, eC, eD, tC, tD);
     double a = eD + eC * ain;                       // advantage just above this thread's highest sample
-    Moments mom = {0.0, 0.0, 0.0};
     double out_a[GAE_ITEMS];
 #pragma unroll
     for (int k = GAE_ITEMS - 1; k >= 0; k--) {
         a = dl[k] + c[k] * a;
         out_a[k] = a;
-        if (lo + k < n) {
-            Moments one = {1.0, a, 0.0};
-            mom = merge(mom, one);
-        }
     }
+    Moments mom = gae_thread_moments(out_a, lo, n);
     if (vec && lo + GAE_ITEMS <= n) {
 #pragma unroll
         for (int k = 0; k < GAE_ITEMS; k += 2) {
@@ -173,27 +222,38 @@ gae_apply_kernel(const double *__restrict__ rew, const double *__restrict__ msk,
         for (int k = 0; k < GAE_ITEMS; k++)
             if (lo + k < n) { adv[lo + k] = out_a[k]; ret[lo + k] = v[k] + out_a[k]; }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mom = merge(mom, shfl_down(mom, o));
-    if (lane == 0) s_mom[warp] = mom;
-    __syncthreads();
+    const Moments t = gae_tile_moments(mom, s_mom);
     if (tid == 0) {
-        Moments t = s_mom[0];
-        for (int w = 1; w < GAE_THREADS / 32; w++) t = merge(t, s_mom[w]);
         partial[3 * (size_t)blockIdx.x + 0] = t.n; partial[3 * (size_t)blockIdx.x + 1] = t.mean; partial[3 * (size_t)blockIdx.x + 2] = t.m2;
     }
 }
 
-__global__ void __launch_bounds__(256)
-gae_moments_kernel(const double *__restrict__ partial, unsigned int ntiles, double *__restrict__ stats) {
+// ordered merge of the per-tile partials by one 256-thread block (deterministic: contiguous slices per thread in tile
+// order, ordered shuffle tree, warps in order)
+__device__ __forceinline__ void gae_merge_partials(const double *partial, unsigned int ntiles, double *__restrict__ stats) {
     __shared__ Moments s_mom[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // contiguous slices per thread, merged in tile order
     const unsigned int per = (ntiles + 255) / 256, k0 = threadIdx.x * per;
-    Moments t = {0.0, 0.0, 0.0};
-    for (unsigned int k = k0; k < k0 + per && k < ntiles; k++) {
-        Moments o = {partial[3 * (size_t)k], partial[3 * (size_t)k + 1], partial[3 * (size_t)k + 2]};
-        t = merge(t, o);
+    // this thread's contiguous slice, in tile order.  Partials with the count of the slice's first one (all full tiles)
+    // combine without a division each: mean of the means, M2 = sum of M2 + count * sum of squared mean deviations
+    // (second read of the slice: L2); the others (the ragged last tile) go through the general merge.
+    Moments t = {0.0, 0.0, 0.0}, odd = {0.0, 0.0, 0.0};
+    if (k0 < ntiles) {
+        const unsigned int k1 = min(k0 + per, ntiles);
+        const double n0 = __ldcg(partial + 3 * (size_t)k0);
+        double cnt = 0.0, sum = 0.0, m2 = 0.0;
+        for (unsigned int k = k0; k < k1; k++) {
+            Moments o = {__ldcg(partial + 3 * (size_t)k), __ldcg(partial + 3 * (size_t)k + 1), __ldcg(partial + 3 * (size_t)k + 2)};
+            if (o.n == n0) { cnt += 1.0; sum += o.mean; m2 += o.m2; }
+            else odd = merge(odd, o);
+        }
+        const double mean = sum / cnt;
+        double dev = 0.0;
+        for (unsigned int k = k0; k < k1; k++)
+            if (__ldcg(partial + 3 * (size_t)k) == n0) { const double d = __ldcg(partial + 3 * (size_t)k + 1) - mean; dev = fma(d, d, dev); }
+        t.n = cnt * n0; t.mean = mean; t.m2 = m2 + n0 * dev;
+        if (n0 == 0.0) t = Moments{0.0, 0.0, 0.0};
+        t = merge(t, odd);
     }
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {              // ordered tree: lane l absorbs lane l + o
@@ -206,6 +266,100 @@ gae_moments_kernel(const double *__restrict__ partial, unsigned int ntiles, doub
         Moments r = s_mom[0];
         for (int w = 1; w < 8; w++) r = merge(r, s_mom[w]);
         stats[0] = r.n; stats[1] = r.mean; stats[2] = r.m2;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+gae_moments_kernel(const double *__restrict__ partial, unsigned int ntiles, double *__restrict__ stats) {
+    gae_merge_partials(partial, ntiles, stats);
+}
+
+// Large batches (inputs beyond what L2 keeps between two passes): ONE pass by a persistent grid (every CTA resident, so
+// waiting on another CTA cannot deadlock).  CTA b takes the tiles ntiles-1-b, ntiles-1-b-G, ... (from the END of the
+// batch: the direction of the recurrence).  A tile publishes its affine map (C, D) right after its block scan as ONE
+// 16-byte store into a slot the caller filled with an all-ones bit pattern, then folds the maps of the tiles after it
+// until C hits 0 (the first episode boundary: normally inside the very next tile, which the neighbouring CTA is
+// processing at the same moment), re-reading (one 16-byte load) only slots that still hold the pattern: no flags and no
+// fences.  The last CTA to finish merges the moment partials in tile order.  5 doubles of traffic per sample (3 in,
+// 2 out), the algorithmic minimum; results are bit-identical to the two-pass kernels (same per-tile arithmetic, same
+// merge order).  `done` starts at 2^32 - 1 (the caller's one memset fills slots and counter with ones).
+constexpr unsigned long long GAE_EMPTY = 0xffffffffffffffffull;
+
+__device__ __forceinline__ void gae_publish(double *slot, double C, double D) {
+    unsigned long long c = (unsigned long long)__double_as_longlong(C), d = (unsigned long long)__double_as_longlong(D);
+    if (c == GAE_EMPTY) c = 0x7ff8000000000000ull;          // a NaN carrying the reserved payload stays a NaN
+    if (d == GAE_EMPTY) d = 0x7ff8000000000000ull;
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"(c), "l"(d) : "memory");
+}
+__device__ __forceinline__ void gae_fetch(const double *slot, double &C, double &D) {
+    unsigned long long c, d;
+    for (;;) {
+        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(c), "=l"(d) : "l"(slot) : "memory");
+        if (c != GAE_EMPTY && d != GAE_EMPTY) break;
+        __nanosleep(20);
+    }
+    C = __longlong_as_double((long long)c); D = __longlong_as_double((long long)d);
+}
+
+__global__ void __launch_bounds__(GAE_THREADS, GAE_ONEPASS_CTAS)
+gae_onepass_kernel(const double *__restrict__ rew, const double *__restrict__ msk, const double *__restrict__ val, double gamma,
+                   double tau, long long n, bool vec, unsigned int ntiles, double *agg, unsigned int *done,
+                   double *__restrict__ adv, double *__restrict__ ret, double *partial, double *__restrict__ stats) {
+    __shared__ Moments s_mom[GAE_THREADS / 32];
+    __shared__ unsigned int s_last;
+    __shared__ double s_ain;
+    const int tid = threadIdx.x;
+    for (long long tl = (long long)ntiles - 1 - blockIdx.x; tl >= 0; tl -= gridDim.x) {
+        const unsigned int tile = (unsigned int)tl;
+        const long long lo = (long long)tile * GAE_TILE + (long long)(GAE_THREADS - 1 - tid) * GAE_ITEMS;
+        double dl[GAE_ITEMS], c[GAE_ITEMS], v[GAE_ITEMS + 1], C, D, eC, eD, tC, tD;
+        gae_load_compose(rew, msk, val, gamma, tau, n, lo, vec, dl, c, v, C, D);
+        gae_block_scan(C, D, eC, eD, tC, tD);
+        if (tid == 0) {
+            gae_publish(agg + 2 * (size_t)tile, tC, tD);
+            double aC = 1.0, ain = 0.0;
+            for (unsigned int q = tile + 1; q < ntiles && aC != 0.0; q++) {
+                double qC, qD;
+                gae_fetch(agg + 2 * (size_t)q, qC, qD);
+                ain += aC * qD;
+                aC *= qC;
+            }
+            s_ain = ain;
+        }
+        __syncthreads();
+        double a = eD + eC * s_ain;
+        double out_a[GAE_ITEMS];
+#pragma unroll
+        for (int k = GAE_ITEMS - 1; k >= 0; k--) {
+            a = dl[k] + c[k] * a;
+            out_a[k] = a;
+        }
+        Moments mom = gae_thread_moments(out_a, lo, n);
+        if (vec && lo + GAE_ITEMS <= n) {
+#pragma unroll
+            for (int k = 0; k < GAE_ITEMS; k += 2) {
+                __stcs(reinterpret_cast<double2 *>(adv + lo + k), make_double2(out_a[k], out_a[k + 1]));
+                __stcs(reinterpret_cast<double2 *>(ret + lo + k), make_double2(v[k] + out_a[k], v[k + 1] + out_a[k + 1]));
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < GAE_ITEMS; k++)
+                if (lo + k < n) { adv[lo + k] = out_a[k]; ret[lo + k] = v[k] + out_a[k]; }
+        }
+        const Moments t = gae_tile_moments(mom, s_mom);
+        if (tid == 0) {
+            __stcg(partial + 3 * (size_t)tile + 0, t.n); __stcg(partial + 3 * (size_t)tile + 1, t.mean); __stcg(partial + 3 * (size_t)tile + 2, t.m2);
+        }
+        // the next iteration's block scan has a barrier between these shared-memory reads and its own writes of s_mom / s_ain
+    }
+    if (tid == 0) {
+        __threadfence();
+        s_last = atomicAdd(done, 1u) + 1u == gridDim.x - 1u ? 1u : 0u;     // counts up from 2^32 - 1 (one memset fills slots and counter)
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        gae_merge_partials(partial, ntiles, stats);
     }
 }
 
@@ -517,20 +671,51 @@ int egp_version(void) { return 100; }
 int64_t egp_gae_work_bytes(int64_t n) {
     int64_t nt = (n + GAE_TILE - 1) / GAE_TILE;
     if (nt < 1) nt = 1;
-    return nt * (int64_t)(5 * sizeof(double)) + 64;
+    return nt * (int64_t)(5 * sizeof(double)) + 64;      /* agg[nt][2] (16-byte aligned), partial[nt][3], done */
+}
+
+static int64_t g_gae_onepass_min = 1ll << 16;   // samples (32 tiles); measured faster from config 2's 1.2 M samples (43 vs 48 us) upwards
+
+int64_t egp_gae_set_onepass_min(int64_t n) {
+    const int64_t old = g_gae_onepass_min;
+    if (n >= 0) g_gae_onepass_min = n;
+    return old;
 }
 
 int egp_gae_f64(const double *d_rewards, const double *d_masks, const double *d_values, double gamma, double tau,
                 int64_t n, double *d_adv, double *d_ret, double *d_stats, void *d_work, void *stream) {
-    if (n <= 0 || !d_rewards || !d_masks || !d_values || !d_adv || !d_ret || !d_stats || !d_work) {
-        set_error("egp_gae_f64: bad argument");
+    if (n <= 0 || !d_rewards || !d_masks || !d_values || !d_adv || !d_ret || !d_stats || !d_work || ((uintptr_t)d_work & 15)) {
+        set_error("egp_gae_f64: bad argument (null pointer, n <= 0 or d_work not 16-byte aligned)");
         return EGP_EINVAL;
     }
     cudaStream_t st = (cudaStream_t)stream;
     unsigned int nt = (unsigned int)((n + GAE_TILE - 1) / GAE_TILE);
-    double *agg = (double *)d_work;
-    double *partial = agg + 2 * (size_t)nt;
+    double *agg = (double *)d_work;                                  // [nt][2], then 16 bytes for `done`, then partial [nt][3]
+    unsigned int *done = (unsigned int *)(agg + 2 * (size_t)nt);
+    double *partial = agg + 2 * (size_t)nt + 2;
     const bool vec = (((uintptr_t)d_rewards | (uintptr_t)d_masks | (uintptr_t)d_values | (uintptr_t)d_adv | (uintptr_t)d_ret) & 15) == 0;
+    if (n >= g_gae_onepass_min) {
+        if (cudaMemsetAsync(agg, 0xff, (2 * (size_t)nt + 2) * sizeof(double), st) != cudaSuccess) {     // empty slots; done = 2^32 - 1
+            set_error("egp_gae_f64: cudaMemsetAsync failed");
+            return EGP_ECUDA;
+        }
+        static int ctas_per_sm = 0;
+        if (!ctas_per_sm) {
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, gae_onepass_kernel, GAE_THREADS, 0) != cudaSuccess || ctas_per_sm < 1) {
+                ctas_per_sm = 0;
+                set_error("egp_gae_f64: occupancy query failed");
+                return EGP_ECUDA;
+            }
+        }
+        int dev = 0;
+        cudaGetDevice(&dev);
+        unsigned int grid = (unsigned int)(num_sms(dev) * ctas_per_sm);        // every CTA resident: spinning on a neighbour is safe
+        if (grid > nt) grid = nt;
+        gae_onepass_kernel<<<grid, GAE_THREADS, 0, st>>>(d_rewards, d_masks, d_values, gamma, tau, (long long)n, vec, nt, agg, done,
+                                                       d_adv, d_ret, partial, d_stats);
+        EGP_CHECK_LAUNCH("gae_onepass_kernel");
+        return EGP_OK;
+    }
     gae_agg_kernel<<<nt, GAE_THREADS, 0, st>>>(d_rewards, d_masks, d_values, gamma, tau, (long long)n, vec, agg);
     gae_apply_kernel<<<nt, GAE_THREADS, 0, st>>>(d_rewards, d_masks, d_values, gamma, tau, (long long)n, vec, nt, agg, d_adv,
                                                  d_ret, partial);

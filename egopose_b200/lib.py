@@ -101,6 +101,7 @@ SYMBOLS = {
                                C.POINTER(TrajOut), _vp]),
     'egp_gae_work_bytes': (_i64, [_i64]),
     'egp_gae_f64': (_int, [_vp, _vp, _vp, _d, _d, _i64, _vp, _vp, _vp, _vp, _vp]),
+    'egp_gae_set_onepass_min': (_i64, [_i64]),
     'egp_standardize_f64': (_int, [_vp, _i64, _vp, _vp]),
     'egp_gauss_logp_f64': (_int, [_vp, _vp, _vp, _i64, _int, _vp, _vp]),
     'egp_ppo_loss_grad_f64': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _i64, _int, _vp, _vp, _vp, _vp]),
@@ -457,8 +458,13 @@ def gae(rewards, masks, values, gamma, tau, work=None, out=None):
         work = torch.empty(nbytes, dtype=torch.uint8, device=rewards.device)
     check(lib.egp_gae_f64(ptr(rewards), ptr(masks), ptr(values), gamma, tau, n, ptr(adv), ptr(ret), ptr(stats),
                           ptr(work), stream_ptr()), 'egp_gae_f64')
-    launches += 3
+    launches += 1 if n >= lib.egp_gae_set_onepass_min(-1) else 3
     return adv, ret, stats
+
+
+def gae_set_onepass_min(n):
+    """batch size from which egp_gae_f64 takes the one-pass scan (returns the previous value; n < 0 only queries)"""
+    return int(load().egp_gae_set_onepass_min(int(n)))
 
 
 def standardize_(x, stats):

@@ -214,10 +214,14 @@ int egp_rollout_f64(EgpModel *m, const EgpPolicyWeights *pol, const EgpRolloutCf
 /* K4: core/common.py:5-21 estimate_advantages reverse scan over the flat batch.  d_adv gets the
  * UN-normalised advantages, d_ret = values + adv, d_stats[0..2] = (n, mean, M2) of adv so that
  * (adv - mean) / sqrt(M2 / (n - 1)) is the reference's standardisation (:22).
- * d_work: egp_gae_work_bytes(n) bytes of scratch. */
+ * d_work: egp_gae_work_bytes(n) bytes of scratch, 16-byte aligned. */
 int64_t egp_gae_work_bytes(int64_t n);
 int egp_gae_f64(const double *d_rewards, const double *d_masks, const double *d_values, double gamma, double tau,
                 int64_t n, double *d_adv, double *d_ret, double *d_stats, void *d_work, void *stream);
+/* Batches of at least this many samples take the one-pass scan (tiles handed out by ticket from the end of the batch,
+ * each folds the published maps of the tiles after it: 5 doubles of HBM traffic per sample); smaller ones the two-pass
+ * scan whose second read is an L2 hit.  Results are bit-identical.  Returns the previous value; n < 0 only queries. */
+int64_t egp_gae_set_onepass_min(int64_t n);
 /* (x - stats.mean) / std in place (materialises the reference's normalised advantages) */
 int egp_standardize_f64(double *d_x, int64_t n, const double *d_stats, void *stream);
 

@@ -45,6 +45,33 @@ def test_gae_no_episode_boundaries_long_chain():
     assert np.allclose(lib.standardize_(adv, stats).cpu().numpy(), adv_n, rtol=1e-9, atol=1e-10)
 
 
+@pytest.mark.parametrize('n,mask', [(1, 'rand'), (2049, 'rand'), (300 * 700, 'episodes'), (2048 * 40 + 3, 'ones'),
+                                    (2048 * 700 + 11, 'rand'), (6_000_001, 'episodes')])
+def test_gae_one_pass_is_bit_identical_to_two_pass(n, mask):
+    """the ticketed one-pass scan (large batches) and the two-pass scan do the same per-tile arithmetic in the same merge
+    order: advantages, returns and moments must agree bit for bit; also against the oracle"""
+    from egopose_b200 import lib
+    rng = np.random.RandomState(7)
+    r, v = rng.rand(n), rng.randn(n)
+    m = np.ones(n) if mask == 'ones' else (rng.rand(n) > 0.02).astype(np.float64)
+    if mask == 'episodes':
+        m[149::150] = 0.0
+    m[-1] = 0.0
+    old = lib.gae_set_onepass_min(1 << 62)
+    try:
+        a2, r2, s2 = lib.gae(cu(r), cu(m), cu(v), 0.95, 0.95)
+        lib.gae_set_onepass_min(0)
+        for _ in range(3):                              # repeated calls reuse nothing between launches
+            a1, r1, s1 = lib.gae(cu(r), cu(m), cu(v), 0.95, 0.95)
+            assert torch.equal(a1, a2) and torch.equal(r1, r2) and torch.equal(s1, s2)
+    finally:
+        lib.gae_set_onepass_min(old)
+    if 1 < n < 1_000_000:
+        adv_n, ret_o = oppo.gae(r, m, v, 0.95, 0.95)
+        assert np.allclose(r1.cpu().numpy(), ret_o, rtol=1e-11, atol=1e-11)
+        assert np.allclose(lib.standardize_(a1, s1).cpu().numpy(), adv_n, rtol=1e-9, atol=1e-10)
+
+
 def test_gae_unaligned_views():
     """8-byte-offset tensor views take the scalar load path"""
     from egopose_b200 import lib
