@@ -128,6 +128,7 @@ struct EnvData {
     double q[MAXV + 1], v[MAXV];
     double S[MAXV][6], U[MAXV][6], Dinv[MAXV], u[MAXV];
     double C[MAXV], tau[MAXV], qacc[MAXV];
+    double dadd[MAXV];                  // joint limits: extra pivot weight of the active rows (0 otherwise)
     double cin[MAXB][10], fb[MAXB][6];
     double xp[MAXB][3];                 // body positions (world) from the last kinematics refresh
     Fwd jf[MAXC];
@@ -293,7 +294,8 @@ __device__ void pass_backward(EnvData &e) {
                     double Ci = dot6(S, w.F);
                     e.C[i] = Ci;
                     rhs = e.tau[i] - Ci;
-                } else rhs = e.tau[i];
+                } else if (MODE == 2) rhs = e.qacc[i] - e.C[i];      // limit re-solve: qacc holds tau + the rows' D s aref
+                else rhs = e.tau[i];
 #pragma unroll
                 for (int r = 0; r < 6; r++) {
                     double t = 0.0;
@@ -303,6 +305,7 @@ __device__ void pass_backward(EnvData &e) {
                 }
                 double D = dot6(S, U) + c_m.dof_arm[i];
                 if (MODE == 1) D += c_m.kd[i] * c_m.h;
+                if (MODE == 2) D += e.dadd[i];
                 const double Dinv = 1.0 / D;
                 const double ui = rhs - dot6(S, w.pA);
                 e.Dinv[i] = Dinv;
@@ -345,6 +348,68 @@ __device__ void pass_accel(EnvData &e, double *out) {
     }
 }
 
+// ---- joint limits (MuJoCo soft constraints; DevModel.limits, egp_model_set_joint_limits) -------------------------
+// One limit row of hinge dof i at penetration dist < 0 and row velocity vel = s v_i: impedance d(dist) from solimp,
+// weight D = 1/R with R = (1 - d)/d * dof_invweight0, reference acceleration aref = -b vel - k d dist.
+__device__ void limit_row(int i, double dist, double vel, double &Dc, double &aref) {
+    double imp;
+    if (c_m.lim_d0 == c_m.lim_dw || c_m.lim_width <= 1e-15) imp = 0.5 * (c_m.lim_d0 + c_m.lim_dw);
+    else {
+        const double xx = fabs(dist) / c_m.lim_width, pw = c_m.lim_pow, mid = c_m.lim_mid;
+        double y;
+        if (xx >= 1.0) y = 1.0;
+        else if (xx <= 0.0) y = 0.0;
+        else if (pw == 1.0) y = xx;
+        else if (xx <= mid) y = pow(xx, pw) / pow(mid, pw - 1.0);
+        else y = 1.0 - pow(1.0 - xx, pw) / pow(1.0 - mid, pw - 1.0);
+        imp = c_m.lim_d0 + y * (c_m.lim_dw - c_m.lim_d0);
+    }
+    double R = (1.0 - imp) / imp * c_m.lim_iw[i];
+    if (R < 1e-15) R = 1e-15;
+    Dc = 1.0 / R;
+    aref = -c_m.lim_b * vel - c_m.lim_k * imp * dist;
+}
+
+// After pass_backward<0> + pass_accel gave the smooth qacc: if any range is violated, the solver's optimum is
+// (M + diag(D_active)) a = tau - C + sum_active D s aref  (every row's Jacobian is a unit vector, so the rows only add to
+// the pivots and the right-hand side of the same articulated-body sweeps); the active set {rows with s a - aref < 0} is
+// iterated to its fixed point.  The smooth bias C and the smooth tree data stay as they are (compute_torque reads them).
+__device__ void limit_solve(EnvData &e) {
+    const int nv = c_m.nv;
+    unsigned long long inst = 0ull, act;
+    double Dc[MAXV], ar[MAXV];                  // per row: D, s * aref ... kept only for instantiated rows
+    double sg[MAXV];
+    for (int i = 6; i < nv; i++) {
+        const double lo = c_m.lim_lo[i], hi = c_m.lim_hi[i], q = e.q[i + 1];
+        if (!(lo < hi)) continue;
+        double dist, s;
+        if (q - lo < 0.0) { dist = q - lo; s = 1.0; }
+        else if (hi - q < 0.0) { dist = hi - q; s = -1.0; }
+        else continue;
+        limit_row(i, dist, s * e.v[i], Dc[i], ar[i]);
+        sg[i] = s;
+        inst |= 1ull << i;
+    }
+    if (!inst) return;
+    act = inst;
+    double tau0[MAXV];
+    for (int i = 0; i < nv; i++) tau0[i] = e.tau[i];
+    for (int it = 0; it < 64; it++) {
+        for (int i = 0; i < nv; i++) {
+            const bool on = (act >> i) & 1ull;
+            e.dadd[i] = on ? Dc[i] : 0.0;
+            e.qacc[i] = tau0[i] + (on ? Dc[i] * sg[i] * ar[i] : 0.0);
+        }
+        pass_backward<2>(e);
+        pass_accel(e, e.qacc);
+        unsigned long long nact = 0ull;
+        for (int i = 6; i < nv; i++)
+            if (((inst >> i) & 1ull) && sg[i] * e.qacc[i] - ar[i] < 0.0) nact |= 1ull << i;
+        if (nact == act) break;
+        act = nact;
+    }
+}
+
 // sim.forward() at the current state (envs/common/mujoco_env.py:100-101): refresh tree data + bias
 __device__ void env_forward(EnvData &e) {
     pass_kinematics(e);
@@ -378,6 +443,7 @@ __device__ void env_substep(EnvData &e, const double *ctrl /* per dof, [nv] */, 
     pass_kinematics(e);
     pass_backward<0>(e);
     pass_accel(e, e.qacc);
+    if (c_m.limits) limit_solve(e);
     for (int i = 0; i < nv; i++) e.v[i] += h * e.qacc[i];
     for (int k = 0; k < 3; k++) e.q[k] += h * e.v[k];
     {
@@ -1596,6 +1662,7 @@ __global__ void forward_debug_kernel(int n, const double *qpos, const double *qv
     for (int k = 0; k < nv; k++) e.tau[k] = (k >= 6 && ctrl) ? ctrl[(size_t)i * c_m.nu + k - 6] : 0.0;
     pass_backward<0>(e);
     pass_accel(e, e.qacc);
+    if (c_m.limits) limit_solve(e);
     for (int k = 0; k < nv; k++) { bias[(size_t)i * nv + k] = e.C[k]; qacc[(size_t)i * nv + k] = e.qacc[k]; }
     for (int b = 0; b < nb; b++) for (int r = 0; r < 3; r++) xpos[((size_t)i * nb + b) * 3 + r] = e.xp[b][r];
 }
@@ -1723,6 +1790,32 @@ int egp_model_create(const EgpModelDesc *s, int device, EgpModel **out) {
     }
     m->device = device;
     *out = m;
+    return EGP_OK;
+}
+
+int egp_model_set_joint_limits(EgpModel *m, const double *range, const double *invweight0, const double *solref,
+                               const double *solimp) {
+    if (!m) { set_error("egp_model_set_joint_limits: null model"); return EGP_EINVAL; }
+    DevModel &d = m->host;
+    if (m->device >= 0 && m->device < 64 && g_bound_model[m->device] == m) g_bound_model[m->device] = nullptr;   // re-upload on next use
+    if (!range) { d.limits = 0; return EGP_OK; }
+    if (!invweight0) { set_error("egp_model_set_joint_limits: invweight0 is required with a range table"); return EGP_EINVAL; }
+    const double sr[2] = {solref ? solref[0] : 0.02, solref ? solref[1] : 1.0};
+    const double si[5] = {solimp ? solimp[0] : 0.9, solimp ? solimp[1] : 0.95, solimp ? solimp[2] : 0.001, solimp ? solimp[3] : 0.5,
+                          solimp ? solimp[4] : 2.0};
+    if (!(sr[0] > 0.0) || !(sr[1] > 0.0)) { set_error("egp_model_set_joint_limits: only the (timeconst, dampratio) form of solref is supported"); return EGP_EINVAL; }
+    auto clampi = [](double x) { return x < 1e-4 ? 1e-4 : (x > 0.9999 ? 0.9999 : x); };
+    for (int i = 0; i < d.nv; i++) {
+        d.lim_lo[i] = range[2 * i]; d.lim_hi[i] = range[2 * i + 1]; d.lim_iw[i] = invweight0[i];
+        if (i < 6 && d.body_dofnum[0] == 6) { d.lim_lo[i] = 0.0; d.lim_hi[i] = 0.0; }      // the free root has no range
+        if (d.lim_lo[i] < d.lim_hi[i] && !(invweight0[i] > 0.0)) { set_error("egp_model_set_joint_limits: invweight0[%d] must be positive", i); return EGP_EINVAL; }
+    }
+    const double tc = sr[0] < 2.0 * d.h ? 2.0 * d.h : sr[0];                                 // refsafe
+    d.lim_d0 = clampi(si[0]); d.lim_dw = clampi(si[1]); d.lim_width = si[2] < 0.0 ? 0.0 : si[2]; d.lim_mid = clampi(si[3]);
+    d.lim_pow = si[4] < 1.0 ? 1.0 : si[4];
+    d.lim_k = 1.0 / (d.lim_dw * d.lim_dw * tc * tc * sr[1] * sr[1]);
+    d.lim_b = 2.0 / (d.lim_dw * tc);
+    d.limits = 1;
     return EGP_OK;
 }
 
@@ -1865,7 +1958,7 @@ int egp_rollout_f64(EgpModel *m, const EgpPolicyWeights *pol, const EgpRolloutCf
     const char *force = getenv("EGP_ROLLOUT_VARIANT");
     bool use_t4 = false;
     A.chunk23 = 0;
-    if (d.t4_ok && !(force && force[0] == '1') && 2 * (pad16(A.A) / MLP_NT) <= T4_WARPS) {
+    if (d.t4_ok && !d.limits && !(force && force[0] == '1') && 2 * (pad16(A.A) / MLP_NT) <= T4_WARPS) {      // joint limits: V1 sweeps only (so far)
         const int H1p = pad16(A.H1), H2p = pad16(A.H2), Ap = pad16(A.A), Dp = pad16(A.D);
         for (int pi = 0; pi < 4 && !use_t4; pi++) {        // (stride 36 | 32) x (full | chunked layer 2/3)
             const int ch = pi & 1, xs_stride = pi < 2 ? XS_WIDE : 32;

@@ -77,6 +77,10 @@ struct DevModel {
     int body_slot[MAXB], dof_col_ctrl[MAXV], dof_col_tau[MAXV], dof_col_c[MAXV], tm_cols;
     BodyK bk[MAXB];
     double w_p, w_v, w_e, w_rp, w_rv, k_p, k_v, k_e, k_rh, k_rq, k_rl, k_ra;
+    // joint limits as MuJoCo soft constraints (egp_model_set_joint_limits; off = smooth dynamics, the north star)
+    int limits;
+    double lim_lo[MAXV], lim_hi[MAXV], lim_iw[MAXV];       // range per dof (lo >= hi: none), diag(M^-1) at qpos0
+    double lim_k, lim_b, lim_d0, lim_dw, lim_width, lim_mid, lim_pow;
 };
 
 #if defined(__CUDACC__)
@@ -490,7 +494,11 @@ EGP_HD void t5_fwd_load(const X &x, int b, FwdIn<MODE> &in) {
         }
         in.v[j] = x.at(x.o.v, i);
         in.q[j] = x.at(x.o.q, K.qa + jj);
-        if (MODE != 0) sincos(in.q[j], &in.sn[j], &in.cs[j]);
+        if (MODE != 0) {            // through temporaries: handing sincos() addresses of `in` members forces the whole record into local memory
+            double sn_j, cs_j;
+            sincos(in.q[j], &sn_j, &cs_j);
+            in.sn[j] = sn_j; in.cs[j] = cs_j;
+        }
     }
 }
 

@@ -49,6 +49,11 @@ class HumanoidEnv:
         self.kernel = lib.Model(self.md, cfg.jkp, cfg.jkd, cfg.a_ref, cfg.a_scale, cfg.torque_lim,
                                 getattr(cfg, 'b_diffw', np.ones(self.md.nbody - 1)), cfg.reward_weights,
                                 frame_skip=self.frame_skip, device=device)
+        # joint ranges of the XML as MuJoCo soft constraints: off by default (the fused kernels' scope is the smooth dynamics);
+        # cfg.joint_limits = True (or EGP_JOINT_LIMITS=1) switches them on for every roll-out of this environment
+        import os
+        if bool(getattr(cfg, 'joint_limits', False)) or os.environ.get('EGP_JOINT_LIMITS', '0') == '1':
+            self.kernel.set_joint_limits(True)
         self.model = _ModelView(self.md)
         self.obs_dim = self.md.nq - 2 + self.md.nv
         self.observation_space = _Space(self.obs_dim)

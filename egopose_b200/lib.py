@@ -99,6 +99,7 @@ SYMBOLS = {
     'egp_env_step_debug_f64': (_int, [_vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'egp_rollout_f64': (_int, [_vp, C.POINTER(PolicyWeights), C.POINTER(RolloutCfg), C.POINTER(RolloutIn),
                                C.POINTER(TrajOut), _vp]),
+    'egp_model_set_joint_limits': (_int, [_vp, _vp, _vp, _vp, _vp]),
     'egp_gae_work_bytes': (_i64, [_i64]),
     'egp_gae_f64': (_int, [_vp, _vp, _vp, _d, _d, _i64, _vp, _vp, _vp, _vp, _vp]),
     'egp_gae_set_onepass_min': (_i64, [_i64]),
@@ -308,6 +309,52 @@ class Model:
         if extras:
             return rows, float(hz.min().item()), ex
         return rows, float(hz.min().item())
+
+    # ---- joint limits -------------------------------------------------------------------------
+    def dof_ranges(self):
+        """[nv][2] radians: the XML's hinge ranges per dof (free root: 0, 0 = none)"""
+        md = self.md
+        rng = np.zeros((self.nv, 2))
+        free = md.body_dofnum[0] == 6
+        for j, r in enumerate(md.jnt_range):
+            if free and j == 0:
+                continue
+            rng[j + 5 if free else j] = r
+        return rng
+
+    def invweight0(self):
+        """mjModel.dof_invweight0 of the actuated hinges: diag(M^-1) at qpos0, from the articulated-body solver itself
+        (qacc with a unit torque on dof i minus qacc without actuation; limits off while measuring)"""
+        import torch
+        dev = torch.device('cuda', self.device)
+        n = self.nu + 1
+        q = torch.as_tensor(np.tile(np.asarray(self.md.qpos0, dtype=np.float64), (n, 1)), device=dev)
+        v = torch.zeros((n, self.nv), dtype=torch.float64, device=dev)
+        ctrl = torch.zeros((n, self.nu), dtype=torch.float64, device=dev)
+        ctrl[1:] = torch.eye(self.nu, dtype=torch.float64, device=dev)
+        check(self.lib.egp_model_set_joint_limits(self.handle, None, None, None, None), 'egp_model_set_joint_limits')
+        _, _, qacc = self.forward_debug(q, v, ctrl)
+        qacc = qacc.cpu().numpy()
+        iw = np.ones(self.nv)
+        first = self.nv - self.nu
+        for k in range(self.nu):
+            iw[first + k] = qacc[1 + k, first + k] - qacc[0, first + k]
+        return iw
+
+    def set_joint_limits(self, on=True, solref=None, solimp=None):
+        """sim.step() with the XML's joint ranges as MuJoCo soft constraints (include/egopose_b200.h:
+        egp_model_set_joint_limits); off = smooth dynamics, the default"""
+        if not on:
+            check(self.lib.egp_model_set_joint_limits(self.handle, None, None, None, None), 'egp_model_set_joint_limits')
+            self.joint_limits = False
+            return
+        keep = [np.ascontiguousarray(self.dof_ranges()), np.ascontiguousarray(self.invweight0())]
+        sr = np.ascontiguousarray(solref, dtype=np.float64) if solref is not None else None
+        si = np.ascontiguousarray(solimp, dtype=np.float64) if solimp is not None else None
+        hp = lambda a: a.ctypes.data if a is not None else None      # noqa: E731
+        check(self.lib.egp_model_set_joint_limits(self.handle, hp(keep[0]), hp(keep[1]), hp(sr), hp(si)),
+              'egp_model_set_joint_limits')
+        self.joint_limits = True
 
     # ---- debug / parity -----------------------------------------------------------------------
     def forward_debug(self, qpos, qvel, ctrl=None):

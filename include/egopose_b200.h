@@ -178,6 +178,16 @@ int egp_version(void);
 int egp_model_create(const EgpModelDesc *desc, int device, EgpModel **out);
 void egp_model_destroy(EgpModel *m);
 
+/* Joint limits (humanoid_1205_v1.xml:10 limited="true", :28-30 range=...) as MuJoCo soft constraints inside mj_step
+ * (what sim.step() adds to the smooth dynamics when a hinge leaves its range): range [nv][2] radians per dof (lower >=
+ * upper: none; the free root is ignored), invweight0 [nv] = diag(M^-1) at qpos0 (mjModel.dof_invweight0), solref
+ * (timeconst, dampratio) and solimp (d0, dwidth, width, midpoint, power), NULL = MuJoCo's defaults 0.02 1 /
+ * 0.9 0.95 0.001 0.5 2.  Host pointers.  range = NULL switches the limits off again (smooth dynamics: the default).
+ * With limits on, roll-outs run on the one-warp-per-32-environments kernel (the block sweeps do not carry them yet);
+ * evaluation roll-outs and the state LSTM are then unavailable (EGP_ESIZE).  Floor contact is not modelled. */
+int egp_model_set_joint_limits(EgpModel *m, const double *range, const double *invweight0, const double *solref,
+                               const double *solimp);
+
 /* replaces HumanoidEnv.load_experts (humanoid_v1.py:45-54): packed rows [total_frames][EGP_X_STRIDE],
  * take offsets [n_takes+1], per-take head_height_lb, optional per-frame context rows (host pointers) */
 int egp_expert_upload(EgpModel *m, int n_takes, const int32_t *take_off, const double *rows,

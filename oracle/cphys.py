@@ -28,7 +28,8 @@ class EoModel(C.Structure):
                 ('body_pos', _dp), ('body_mass', _dp), ('body_ipos', _dp), ('body_inertia', _dp),
                 ('dof_body', _ip), ('dof_parent', _ip),
                 ('dof_armature', _dp), ('dof_axis', _dp), ('dof_anchor', _dp),
-                ('ee_body', C.c_int * NEE), ('head_body', C.c_int)]
+                ('ee_body', C.c_int * NEE), ('head_body', C.c_int),
+                ('dof_range', _dp), ('dof_invweight0', _dp), ('solref', C.c_double * 2), ('solimp', C.c_double * 5)]
 
 
 class EoData(C.Structure):
@@ -107,7 +108,7 @@ def default_cfg_dict(task='egomimic', cfg_id='subject_03'):
 class Oracle:
     """Model + cfg bound to the C oracle.  ``cfg`` is the yml dict (config/egomimic/*.yml)."""
 
-    def __init__(self, cfg=None, model_json=None, episode_len=None, fix_head_lb=None):
+    def __init__(self, cfg=None, model_json=None, episode_len=None, fix_head_lb=None, joint_limits=False):
         self.L = lib()
         md = json.load(open(model_json or os.path.join(ASSETS, 'humanoid_1205_v1.model.json')))
         self.md = md
@@ -153,6 +154,36 @@ class Oracle:
         c.fix_head_lb = float('nan') if fix_head_lb is None else float(fix_head_lb)
         self.cfg = c
         self.dt = md['timestep'] * 15
+        if joint_limits:
+            self.enable_joint_limits()
+
+    def dof_ranges(self):
+        """[nv][2] (radians): the hinge ranges of the XML per dof; the free root has none (0, 0)"""
+        rng = np.zeros((self.nv, 2))
+        free = self.md['body_dofnum'][0] == 6
+        for j, r in enumerate(self.md['jnt_range']):
+            if free and j == 0:
+                continue
+            rng[j + 5 if free else j] = r
+        return rng
+
+    def invweight0(self):
+        """mjModel.dof_invweight0 of the hinges: diag(M^-1) at qpos0"""
+        d = self.new_data(self.md['qpos0'], np.zeros(self.nv))
+        keep, self.model.dof_range = self.model.dof_range, None
+        self.forward(d)
+        self.model.dof_range = keep
+        return np.ascontiguousarray(np.diag(np.linalg.inv(self.qM(d))))
+
+    def enable_joint_limits(self, solref=(0.02, 1.0), solimp=(0.9, 0.95, 0.001, 0.5, 2.0)):
+        """MuJoCo's defaults (the XML sets none)"""
+        k = self._keep
+        k['dof_invweight0'] = self.invweight0()
+        k['dof_range'] = np.ascontiguousarray(self.dof_ranges())
+        self.model.solref[:] = solref
+        self.model.solimp[:] = solimp
+        self.model.dof_invweight0 = _p(k['dof_invweight0'])
+        self.model.dof_range = _p(k['dof_range'])
 
     # ---- physics ---------------------------------------------------------------------------
     def new_data(self, qpos, qvel, ctrl=None):

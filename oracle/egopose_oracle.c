@@ -276,6 +276,35 @@ int eo_chol_solve(int n, double *A, double *b) {
 /* mj_forward, smooth part: kinematics -> subtree COM -> CRBA (qM + armature)
  * -> RNE bias (gravity + Coriolis/centrifugal) -> qacc = M^-1 (ctrl - bias).  No collision, joint
  * limits or constraint solver (north-star scope). */
+/* one limit row: impedance d(dist) (solimp: d0, dwidth, width, midpoint, power), R = (1 - d)/d * invweight, D = 1/R,
+ * aref = -b vel - k d dist with k = 1/(dmax^2 tc^2 dr^2), b = 2/(dmax tc), tc >= 2 dt (solref: timeconst, dampratio) */
+void eo_limit_row(const EoModel *m, double dist, double vel, double invweight, double *Dout, double *aref) {
+    const double MINVAL = 1e-15, MINIMP = 1e-4, MAXIMP = 0.9999;
+    double d0 = m->solimp[0], dw = m->solimp[1], width = m->solimp[2], mid = m->solimp[3], power = m->solimp[4];
+    d0 = d0 < MINIMP ? MINIMP : (d0 > MAXIMP ? MAXIMP : d0);
+    dw = dw < MINIMP ? MINIMP : (dw > MAXIMP ? MAXIMP : dw);
+    mid = mid < MINIMP ? MINIMP : (mid > MAXIMP ? MAXIMP : mid);
+    if (power < 1.0) power = 1.0;
+    double imp;
+    if (d0 == dw || width <= MINVAL) imp = 0.5 * (d0 + dw);
+    else {
+        double x = fabs(dist) / width, y;
+        if (x >= 1.0) y = 1.0;
+        else if (x <= 0.0) y = 0.0;
+        else if (power == 1.0) y = x;
+        else if (x <= mid) y = pow(x, power) / pow(mid, power - 1.0);
+        else y = 1.0 - pow(1.0 - x, power) / pow(1.0 - mid, power - 1.0);
+        imp = d0 + y * (dw - d0);
+    }
+    double tc = m->solref[0], dr = m->solref[1];
+    if (tc < 2.0 * m->timestep) tc = 2.0 * m->timestep;
+    double k = 1.0 / (dw * dw * tc * tc * dr * dr), bb = 2.0 / (dw * tc);
+    double R = (1.0 - imp) / imp * invweight;
+    if (R < MINVAL) R = MINVAL;
+    *Dout = 1.0 / R;
+    *aref = -bb * vel - k * imp * dist;
+}
+
 void eo_forward(const EoModel *m, EoData *d) {
     int nv = m->nv, nb = m->nbody;
     double axis_w[EO_MAXV * 3], anchor_w[EO_MAXV * 3];
@@ -396,11 +425,53 @@ void eo_forward(const EoModel *m, EoData *d) {
     for (int i = 0; i < nv; i++) d->qfrc_bias[i] = dot6(d->cdof[i], cfrc[m->dof_body[i]]);
 
     /* qacc = M^-1 (qfrc_actuator - qfrc_bias); unit-gear motors on dofs 6.. (xml:139-192) */
-    double A[EO_MAXV * EO_MAXV], rhs[EO_MAXV];
-    memcpy(A, d->qM, sizeof(double) * nv * nv);
+    double A[EO_MAXV * EO_MAXV], rhs[EO_MAXV], smooth[EO_MAXV];
     int first = nv - m->nu;
-    for (int i = 0; i < nv; i++) rhs[i] = (i >= first ? d->ctrl[i - first] : 0.0) - d->qfrc_bias[i];
-    eo_chol_solve(nv, A, rhs);
+    for (int i = 0; i < nv; i++) smooth[i] = (i >= first ? d->ctrl[i - first] : 0.0) - d->qfrc_bias[i];
+    if (!m->dof_range) {
+        memcpy(A, d->qM, sizeof(double) * nv * nv);
+        memcpy(rhs, smooth, sizeof(double) * nv);
+        eo_chol_solve(nv, A, rhs);
+        memcpy(d->qacc, rhs, sizeof(double) * nv);
+        return;
+    }
+    /* Joint limits (see EoModel).  A violated range (dist = q - lower or upper - q < margin = 0) instantiates one
+     * unilateral row J = +-e_i with reference acceleration aref = -b (J v) - k d(dist) dist and weight D = 1/R,
+     * R = (1 - d)/d * dof_invweight0_i.  MuJoCo's solver minimises 1/2 (a - a0)^T M (a - a0) + sum_i s_i(J_i a - aref_i),
+     * s(r) = 1/2 D r^2 for r < 0, else 0.  Because every J_i is a unit vector the stationarity condition of a fixed
+     * active set is  (M + diag(D_active)) a = qfrc_smooth + sum_active D_i J_i aref_i:  the active set is iterated
+     * to its fixed point (Newton on the piecewise-quadratic cost with unit steps). */
+    int inst[EO_MAXV], act[EO_MAXV];
+    double sgn[EO_MAXV], Dc[EO_MAXV], aref[EO_MAXV];
+    int any = 0;
+    for (int i = 0; i < nv; i++) {
+        inst[i] = 0;
+        int b = m->dof_body[i];
+        if (m->body_dofnum[b] == 6) continue;
+        double lo = m->dof_range[2 * i], hi = m->dof_range[2 * i + 1];
+        if (!(lo < hi)) continue;
+        double q = d->qpos[i + 1], dist, s;                 /* hinge dof i reads qpos[i + 1] (free root: 7 qpos, 6 dofs) */
+        if (q - lo < 0.0) { dist = q - lo; s = 1.0; }
+        else if (hi - q < 0.0) { dist = hi - q; s = -1.0; }
+        else continue;
+        eo_limit_row(m, dist, s * d->qvel[i], m->dof_invweight0[i], &Dc[i], &aref[i]);
+        inst[i] = 1; sgn[i] = s; any = 1;
+    }
+    for (int i = 0; i < nv; i++) act[i] = inst[i];
+    for (int it = 0; it < 64; it++) {
+        memcpy(A, d->qM, sizeof(double) * nv * nv);
+        for (int i = 0; i < nv; i++) {
+            rhs[i] = smooth[i];
+            if (act[i]) { A[i * nv + i] += Dc[i]; rhs[i] += Dc[i] * sgn[i] * aref[i]; }
+        }
+        eo_chol_solve(nv, A, rhs);
+        int changed = 0;
+        for (int i = 0; i < nv && any; i++) {
+            int a1 = inst[i] && (sgn[i] * rhs[i] - aref[i] < 0.0);
+            if (a1 != act[i]) { act[i] = a1; changed = 1; }
+        }
+        if (!changed) break;
+    }
     memcpy(d->qacc, rhs, sizeof(double) * nv);
 }
 

@@ -40,6 +40,14 @@ typedef struct {
     const double *dof_armature, *dof_axis, *dof_anchor;             /* [nv],[nv][3],[nv][3] */
     int ee_body[EO_NEE];
     int head_body;
+    /* joint limits as MuJoCo soft constraints (humanoid_1205_v1.xml:10 limited="true", :28-30 range=...; MuJoCo defaults
+     * solref 0.02 1, solimp 0.9 0.95 0.001 0.5 2, margin 0).  dof_range NULL = smooth dynamics only (the north star).
+     * UNPINNED like the rest of the MuJoCo arithmetic (no MuJoCo binary here): restated from MuJoCo's documented
+     * constraint model (engine_core_constraint.c: mj_instantiateLimit, mj_makeImpedance, mj_referenceConstraint; the
+     * solver's optimum instead of its iterates). */
+    const double *dof_range;        /* [nv][2] lower, upper in radians; lower >= upper: no limit on that dof */
+    const double *dof_invweight0;   /* [nv] diag(M^-1) at qpos0 (mjModel.dof_invweight0 of a hinge) */
+    double solref[2], solimp[5];
 } EoModel;
 
 typedef struct {            /* mjData subset the reference reads */
@@ -87,6 +95,7 @@ void eo_forward(const EoModel *m, EoData *d);                   /* mj_forward (s
 void eo_step(const EoModel *m, EoData *d);                      /* mj_step: forward then Euler */
 void eo_kinematics(const EoModel *m, EoData *d, double *dof_axis_w, double *dof_anchor_w);
 int eo_chol_solve(int n, double *A, double *b);                 /* in-place dense Cholesky solve */
+void eo_limit_row(const EoModel *m, double dist, double vel, double invweight, double *D, double *aref);
 
 /* env (ego_pose/envs/humanoid_v1.py) */
 void eo_compute_torque(const EoModel *m, const EoCfg *c, const EoData *d, const double *ctrl, double *torque);
