@@ -51,7 +51,6 @@ class HumanoidEnv:
                                 frame_skip=self.frame_skip, device=device)
         # joint ranges of the XML as MuJoCo soft constraints: off by default (the fused kernels' scope is the smooth dynamics);
         # cfg.joint_limits = True (or EGP_JOINT_LIMITS=1) switches them on for every roll-out of this environment
-        import os
         if bool(getattr(cfg, 'joint_limits', False)) or os.environ.get('EGP_JOINT_LIMITS', '0') == '1':
             self.kernel.set_joint_limits(True)
         self.model = _ModelView(self.md)
