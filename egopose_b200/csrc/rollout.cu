@@ -124,11 +124,18 @@ __device__ __forceinline__ void quat_from_euler(double ai, double aj, double ak,
 
 // per-environment scratch (thread-local)
 
+constexpr int MAXCON = 40;             // floor contacts per environment (21 geoms: 15 capsules x 2, 4 spheres, 2 boxes x 4)
+
 struct EnvData {
     double q[MAXV + 1], v[MAXV];
     double S[MAXV][6], U[MAXV][6], Dinv[MAXV], u[MAXV];
     double C[MAXV], tau[MAXV], qacc[MAXV];
     double dadd[MAXV];                  // joint limits: extra pivot weight of the active rows (0 otherwise)
+    // floor contacts of the last kinematics refresh: body, spatial directions [c x d; d] (about O) of the normal and the two
+    // tangents, and per pyramid edge (n + mu t1, n - mu t1, n + mu t2, n - mu t2) the weight D, aref and the active flag
+    int ncon, con_body[MAXCON];
+    double con_p[MAXCON][3][6], row_D[4 * MAXCON], row_aref[4 * MAXCON];
+    unsigned char row_act[4 * MAXCON], row_new[4 * MAXCON];
     double cin[MAXB][10], fb[MAXB][6];
     double xp[MAXB][3];                 // body positions (world) from the last kinematics refresh
     Fwd jf[MAXC];
@@ -136,9 +143,34 @@ struct EnvData {
     double ja[MAXC][6];
 };
 
+__device__ void limit_row(double invweight, double dist, double vel, double &Dc, double &aref);
+
+// one floor contact of body b at point c (relative to O) with penetration distance dist: the three spatial directions
+// and the four pyramid-edge rows (condim 3, friction mu; mj_instantiateContact, mj_diagApprox, mj_makeImpedance)
+__device__ void add_contact(EnvData &e, int b, const double *c, double dist, const double *vb /* body velocity [w; v_O] */) {
+    if (e.ncon >= MAXCON) return;
+    const int k = e.ncon++;
+    e.con_body[k] = b;
+    const double dirs[3][3] = {{0.0, 0.0, 1.0}, {0.0, 1.0, 0.0}, {-1.0, 0.0, 0.0}};     // normal, tangents (mju_makeFrame)
+    for (int a = 0; a < 3; a++) {
+        cross3(c, dirs[a], e.con_p[k][a]);
+        e.con_p[k][a][3] = dirs[a][0]; e.con_p[k][a][4] = dirs[a][1]; e.con_p[k][a][5] = dirs[a][2];
+    }
+    const double mu = c_m.con_mu, tran = c_m.body_iw[b];
+    const double vn = dot6(e.con_p[k][0], vb), v1 = dot6(e.con_p[k][1], vb), v2 = dot6(e.con_p[k][2], vb);
+    for (int ed = 0; ed < 4; ed++) {
+        const double vel = vn + ((ed & 1) ? -mu : mu) * (ed < 2 ? v1 : v2);
+        double D0, aref;
+        limit_row(tran + mu * mu * tran, dist - c_m.con_margin, vel, D0, aref);
+        e.row_D[4 * k + ed] = D0 / (2.0 * mu * mu);                                    // pyramidal: R = 2 mu^2 R_0
+        e.row_aref[4 * k + ed] = aref;
+    }
+}
+
 // F1: kinematics + velocities + bias accelerations + body inertias/forces at (q, v); refreshes S, cin, fb, xp.
 __device__ void pass_kinematics(EnvData &e) {
     const int nchain = c_m.nchain;
+    e.ncon = 0;
     for (int c = 0; c < nchain; c++) {
         Fwd f;
         const int pc = c_m.chain_parent[c];
@@ -223,6 +255,41 @@ __device__ void pass_kinematics(EnvData &e) {
             }
             // body done: world position, spatial inertia about O in world axes, RNE body force
             for (int r = 0; r < 3; r++) e.xp[b][r] = f.p[r] + e.q[r];
+            if (c_m.contacts) {
+                // geom against the floor plane z = 0 (mjc_PlaneSphere / PlaneCapsule / PlaneBox); heights are world heights,
+                // contact points are kept relative to O = root position like every other spatial quantity
+                const double margin = c_m.con_margin, zO = e.q[2];
+                const double *sz = c_m.geom_size[b];
+                double c0[3];
+                for (int r = 0; r < 3; r++)
+                    c0[r] = f.p[r] + f.R[3 * r] * c_m.geom_p0[b][0] + f.R[3 * r + 1] * c_m.geom_p0[b][1] + f.R[3 * r + 2] * c_m.geom_p0[b][2];
+                if (c_m.geom_type[b] == 2) {
+                    int cnt = 0;
+                    for (int vtx = 0; vtx < 8 && cnt < 4; vtx++) {
+                        const double l0 = (vtx & 1) ? sz[0] : -sz[0], l1 = (vtx & 2) ? sz[1] : -sz[1], l2 = (vtx & 4) ? sz[2] : -sz[2];
+                        double wv[3];
+                        for (int r = 0; r < 3; r++) wv[r] = c0[r] + f.R[3 * r] * l0 + f.R[3 * r + 1] * l1 + f.R[3 * r + 2] * l2;
+                        const double dist = wv[2] + zO;
+                        if (dist > margin) continue;
+                        wv[2] -= 0.5 * dist;
+                        add_contact(e, b, wv, dist, f.v);
+                        cnt++;
+                    }
+                } else {
+                    const int ne = c_m.geom_type[b] == 1 ? 2 : 1;
+                    for (int en = 0; en < ne; en++) {
+                        double cc[3];
+                        if (ne == 2 && en == 0) {
+                            for (int r = 0; r < 3; r++)
+                                cc[r] = f.p[r] + f.R[3 * r] * c_m.geom_p1[b][0] + f.R[3 * r + 1] * c_m.geom_p1[b][1] + f.R[3 * r + 2] * c_m.geom_p1[b][2];
+                        } else for (int r = 0; r < 3; r++) cc[r] = c0[r];
+                        const double dist = cc[2] + zO - sz[0];
+                        if (dist >= margin) continue;
+                        cc[2] -= sz[0] + 0.5 * dist;
+                        add_contact(e, b, cc, dist, f.v);
+                    }
+                }
+            }
             double cpos[3];
             for (int r = 0; r < 3; r++)
                 cpos[r] = f.p[r] + f.R[3 * r] * c_m.body_ipos[b][0] + f.R[3 * r + 1] * c_m.body_ipos[b][1] + f.R[3 * r + 2] * c_m.body_ipos[b][2];
@@ -284,6 +351,22 @@ __device__ void pass_backward(EnvData &e) {
             w.IA[sx(2, 3)] += -ci[2]; w.IA[sx(2, 4)] += ci[1];
             w.IA[sx(3, 3)] += ci[0]; w.IA[sx(4, 4)] += ci[0]; w.IA[sx(5, 5)] += ci[0];
             if (MODE == 0) for (int k = 0; k < 6; k++) w.F[k] += e.fb[b][k];
+            if (MODE == 2) {
+                // active contact rows of this body: D p p^T joins the articulated inertia, D aref p acts as an external force
+                for (int k = 0; k < e.ncon; k++) {
+                    if (e.con_body[k] != b) continue;
+                    for (int ed = 0; ed < 4; ed++) {
+                        if (!e.row_act[4 * k + ed]) continue;
+                        const double sg = (ed & 1) ? -c_m.con_mu : c_m.con_mu, D = e.row_D[4 * k + ed], fa = D * e.row_aref[4 * k + ed];
+                        double p[6];
+                        for (int r = 0; r < 6; r++) p[r] = e.con_p[k][0][r] + sg * e.con_p[k][ed < 2 ? 1 : 2][r];
+                        for (int r = 0; r < 6; r++) {
+                            for (int cc = r; cc < 6; cc++) w.IA[sx(r, cc)] += D * p[r] * p[cc];
+                            w.pA[r] -= fa * p[r];
+                        }
+                    }
+                }
+            }
             const int da = c_m.body_dofadr[b], nd = c_m.body_dofnum[b];
             for (int i = da + nd - 1; i >= da; i--) {
                 double S[6], U[6];
@@ -348,10 +431,10 @@ __device__ void pass_accel(EnvData &e, double *out) {
     }
 }
 
-// ---- joint limits (MuJoCo soft constraints; DevModel.limits, egp_model_set_joint_limits) -------------------------
-// One limit row of hinge dof i at penetration dist < 0 and row velocity vel = s v_i: impedance d(dist) from solimp,
-// weight D = 1/R with R = (1 - d)/d * dof_invweight0, reference acceleration aref = -b vel - k d dist.
-__device__ void limit_row(int i, double dist, double vel, double &Dc, double &aref) {
+// ---- constraint rows: joint limits and floor contacts (MuJoCo soft constraints; egp_model_set_joint_limits / _contacts) ---
+// One row at signed distance dist (already minus its margin) and row velocity vel: impedance d(dist) from solimp, weight
+// D = 1/R with R = (1 - d)/d * invweight, reference acceleration aref = -b vel - k d dist.
+__device__ void limit_row(double invweight, double dist, double vel, double &Dc, double &aref) {
     double imp;
     if (c_m.lim_d0 == c_m.lim_dw || c_m.lim_width <= 1e-15) imp = 0.5 * (c_m.lim_d0 + c_m.lim_dw);
     else {
@@ -364,49 +447,84 @@ __device__ void limit_row(int i, double dist, double vel, double &Dc, double &ar
         else y = 1.0 - pow(1.0 - xx, pw) / pow(1.0 - mid, pw - 1.0);
         imp = c_m.lim_d0 + y * (c_m.lim_dw - c_m.lim_d0);
     }
-    double R = (1.0 - imp) / imp * c_m.lim_iw[i];
+    double R = (1.0 - imp) / imp * invweight;
     if (R < 1e-15) R = 1e-15;
     Dc = 1.0 / R;
     aref = -c_m.lim_b * vel - c_m.lim_k * imp * dist;
 }
 
-// After pass_backward<0> + pass_accel gave the smooth qacc: if any range is violated, the solver's optimum is
-// (M + diag(D_active)) a = tau - C + sum_active D s aref  (every row's Jacobian is a unit vector, so the rows only add to
-// the pivots and the right-hand side of the same articulated-body sweeps); the active set {rows with s a - aref < 0} is
-// iterated to its fixed point.  The smooth bias C and the smooth tree data stay as they are (compute_torque reads them).
-__device__ void limit_solve(EnvData &e) {
+// forward acceleration sweep that also evaluates the contact rows: row_new = (p . a_body - aref < 0)
+__device__ void pass_accel_rows(EnvData &e, double *out) {
+    const int nchain = c_m.nchain;
+    for (int c = 0; c < nchain; c++) {
+        double a[6];
+        const int pc = c_m.chain_parent[c];
+        for (int k = 0; k < 6; k++) a[k] = pc >= 0 ? e.ja[pc][k] : 0.0;
+        for (int b = c_m.chain_lo[c]; b <= c_m.chain_hi[c]; b++) {
+            const int da = c_m.body_dofadr[b], nd = c_m.body_dofnum[b];
+            for (int i = da; i < da + nd; i++) {
+                double x = e.Dinv[i] * (e.u[i] - dot6(e.U[i], a));
+                out[i] = x;
+#pragma unroll
+                for (int r = 0; r < 6; r++) a[r] += e.S[i][r] * x;
+            }
+            for (int k = 0; k < e.ncon; k++) {
+                if (e.con_body[k] != b) continue;
+                const double an = dot6(e.con_p[k][0], a), a1 = dot6(e.con_p[k][1], a), a2 = dot6(e.con_p[k][2], a);
+                for (int ed = 0; ed < 4; ed++) {
+                    const double r = an + ((ed & 1) ? -c_m.con_mu : c_m.con_mu) * (ed < 2 ? a1 : a2) - e.row_aref[4 * k + ed];
+                    e.row_new[4 * k + ed] = r < 0.0;
+                }
+            }
+        }
+        for (int k = 0; k < 6; k++) e.ja[c][k] = a[k];
+    }
+}
+
+// After pass_backward<0> + pass_accel gave the smooth qacc: with rows present the solver's optimum is
+//   (M + sum_act D_i J_i^T J_i) a = tau - C + sum_act D_i aref_i J_i^T.
+// A limit row's Jacobian is a unit vector (adds D to a pivot), a contact row's is p^T J_body (adds D p p^T to that body's
+// articulated inertia and D aref p to its external force): the same articulated-body sweeps solve it in O(n).  The
+// active set {rows with J a - aref < 0} is iterated to its fixed point.  The smooth bias C and the smooth tree data
+// stay as they are (compute_torque reads them).
+__device__ void constraint_solve(EnvData &e) {
     const int nv = c_m.nv;
     unsigned long long inst = 0ull, act;
-    double Dc[MAXV], ar[MAXV];                  // per row: D, s * aref ... kept only for instantiated rows
-    double sg[MAXV];
-    for (int i = 6; i < nv; i++) {
-        const double lo = c_m.lim_lo[i], hi = c_m.lim_hi[i], q = e.q[i + 1];
-        if (!(lo < hi)) continue;
-        double dist, s;
-        if (q - lo < 0.0) { dist = q - lo; s = 1.0; }
-        else if (hi - q < 0.0) { dist = hi - q; s = -1.0; }
-        else continue;
-        limit_row(i, dist, s * e.v[i], Dc[i], ar[i]);
-        sg[i] = s;
-        inst |= 1ull << i;
+    double Dc[MAXV], ar[MAXV], sg[MAXV];
+    if (c_m.limits) {
+        for (int i = 6; i < nv; i++) {
+            const double lo = c_m.lim_lo[i], hi = c_m.lim_hi[i], q = e.q[i + 1];
+            if (!(lo < hi)) continue;
+            double dist, s;
+            if (q - lo < 0.0) { dist = q - lo; s = 1.0; }
+            else if (hi - q < 0.0) { dist = hi - q; s = -1.0; }
+            else continue;
+            limit_row(c_m.lim_iw[i], dist, s * e.v[i], Dc[i], ar[i]);
+            sg[i] = s;
+            inst |= 1ull << i;
+        }
     }
-    if (!inst) return;
+    const int nrow = 4 * e.ncon;
+    if (!inst && !nrow) return;
     act = inst;
+    for (int k = 0; k < nrow; k++) e.row_act[k] = 1;
     double tau0[MAXV];
     for (int i = 0; i < nv; i++) tau0[i] = e.tau[i];
-    for (int it = 0; it < 64; it++) {
+    for (int it = 0; it < 100; it++) {
         for (int i = 0; i < nv; i++) {
             const bool on = (act >> i) & 1ull;
             e.dadd[i] = on ? Dc[i] : 0.0;
             e.qacc[i] = tau0[i] + (on ? Dc[i] * sg[i] * ar[i] : 0.0);
         }
         pass_backward<2>(e);
-        pass_accel(e, e.qacc);
+        pass_accel_rows(e, e.qacc);
         unsigned long long nact = 0ull;
         for (int i = 6; i < nv; i++)
             if (((inst >> i) & 1ull) && sg[i] * e.qacc[i] - ar[i] < 0.0) nact |= 1ull << i;
-        if (nact == act) break;
+        bool same = nact == act;
+        for (int k = 0; k < nrow; k++) { same = same && e.row_new[k] == e.row_act[k]; e.row_act[k] = e.row_new[k]; }
         act = nact;
+        if (same) break;
     }
 }
 
@@ -443,7 +561,7 @@ __device__ void env_substep(EnvData &e, const double *ctrl /* per dof, [nv] */, 
     pass_kinematics(e);
     pass_backward<0>(e);
     pass_accel(e, e.qacc);
-    if (c_m.limits) limit_solve(e);
+    if (c_m.limits || c_m.contacts) constraint_solve(e);
     for (int i = 0; i < nv; i++) e.v[i] += h * e.qacc[i];
     for (int k = 0; k < 3; k++) e.q[k] += h * e.v[k];
     {
@@ -1662,7 +1780,7 @@ __global__ void forward_debug_kernel(int n, const double *qpos, const double *qv
     for (int k = 0; k < nv; k++) e.tau[k] = (k >= 6 && ctrl) ? ctrl[(size_t)i * c_m.nu + k - 6] : 0.0;
     pass_backward<0>(e);
     pass_accel(e, e.qacc);
-    if (c_m.limits) limit_solve(e);
+    if (c_m.limits || c_m.contacts) constraint_solve(e);
     for (int k = 0; k < nv; k++) { bias[(size_t)i * nv + k] = e.C[k]; qacc[(size_t)i * nv + k] = e.qacc[k]; }
     for (int b = 0; b < nb; b++) for (int r = 0; r < 3; r++) xpos[((size_t)i * nb + b) * 3 + r] = e.xp[b][r];
 }
@@ -1793,29 +1911,65 @@ int egp_model_create(const EgpModelDesc *s, int device, EgpModel **out) {
     return EGP_OK;
 }
 
-int egp_model_set_joint_limits(EgpModel *m, const double *range, const double *invweight0, const double *solref,
-                               const double *solimp) {
-    if (!m) { set_error("egp_model_set_joint_limits: null model"); return EGP_EINVAL; }
-    DevModel &d = m->host;
-    if (m->device >= 0 && m->device < 64 && g_bound_model[m->device] == m) g_bound_model[m->device] = nullptr;   // re-upload on next use
-    if (!range) { d.limits = 0; return EGP_OK; }
-    if (!invweight0) { set_error("egp_model_set_joint_limits: invweight0 is required with a range table"); return EGP_EINVAL; }
+// solref (timeconst, dampratio) / solimp (d0, dwidth, width, midpoint, power) -> the constants of limit_row; one set shared
+// by limit and contact rows (the XML sets neither: MuJoCo's defaults)
+static int set_solparams(DevModel &d, const double *solref, const double *solimp, const char *who) {
     const double sr[2] = {solref ? solref[0] : 0.02, solref ? solref[1] : 1.0};
     const double si[5] = {solimp ? solimp[0] : 0.9, solimp ? solimp[1] : 0.95, solimp ? solimp[2] : 0.001, solimp ? solimp[3] : 0.5,
                           solimp ? solimp[4] : 2.0};
-    if (!(sr[0] > 0.0) || !(sr[1] > 0.0)) { set_error("egp_model_set_joint_limits: only the (timeconst, dampratio) form of solref is supported"); return EGP_EINVAL; }
+    if (!(sr[0] > 0.0) || !(sr[1] > 0.0)) { set_error("%s: only the (timeconst, dampratio) form of solref is supported", who); return EGP_EINVAL; }
     auto clampi = [](double x) { return x < 1e-4 ? 1e-4 : (x > 0.9999 ? 0.9999 : x); };
-    for (int i = 0; i < d.nv; i++) {
-        d.lim_lo[i] = range[2 * i]; d.lim_hi[i] = range[2 * i + 1]; d.lim_iw[i] = invweight0[i];
-        if (i < 6 && d.body_dofnum[0] == 6) { d.lim_lo[i] = 0.0; d.lim_hi[i] = 0.0; }      // the free root has no range
-        if (d.lim_lo[i] < d.lim_hi[i] && !(invweight0[i] > 0.0)) { set_error("egp_model_set_joint_limits: invweight0[%d] must be positive", i); return EGP_EINVAL; }
-    }
     const double tc = sr[0] < 2.0 * d.h ? 2.0 * d.h : sr[0];                                 // refsafe
     d.lim_d0 = clampi(si[0]); d.lim_dw = clampi(si[1]); d.lim_width = si[2] < 0.0 ? 0.0 : si[2]; d.lim_mid = clampi(si[3]);
     d.lim_pow = si[4] < 1.0 ? 1.0 : si[4];
     d.lim_k = 1.0 / (d.lim_dw * d.lim_dw * tc * tc * sr[1] * sr[1]);
     d.lim_b = 2.0 / (d.lim_dw * tc);
+    return EGP_OK;
+}
+
+static void unbind(EgpModel *m) {
+    if (m->device >= 0 && m->device < 64 && g_bound_model[m->device] == m) g_bound_model[m->device] = nullptr;   // re-upload on next use
+}
+
+int egp_model_set_joint_limits(EgpModel *m, const double *range, const double *invweight0, const double *solref,
+                               const double *solimp) {
+    if (!m) { set_error("egp_model_set_joint_limits: null model"); return EGP_EINVAL; }
+    DevModel &d = m->host;
+    unbind(m);
+    if (!range) { d.limits = 0; return EGP_OK; }
+    if (!invweight0) { set_error("egp_model_set_joint_limits: invweight0 is required with a range table"); return EGP_EINVAL; }
+    for (int i = 0; i < d.nv; i++) {
+        d.lim_lo[i] = range[2 * i]; d.lim_hi[i] = range[2 * i + 1]; d.lim_iw[i] = invweight0[i];
+        if (i < 6 && d.body_dofnum[0] == 6) { d.lim_lo[i] = 0.0; d.lim_hi[i] = 0.0; }      // the free root has no range
+        if (d.lim_lo[i] < d.lim_hi[i] && !(invweight0[i] > 0.0)) { set_error("egp_model_set_joint_limits: invweight0[%d] must be positive", i); return EGP_EINVAL; }
+    }
+    const int rc = set_solparams(d, solref, solimp, "egp_model_set_joint_limits");
+    if (rc != EGP_OK) return rc;
     d.limits = 1;
+    return EGP_OK;
+}
+
+int egp_model_set_contacts(EgpModel *m, const int32_t *geom_type, const double *geom_size, const double *geom_p0,
+                           const double *geom_p1, const double *body_invweight0, double margin, double friction,
+                           const double *solref, const double *solimp) {
+    if (!m) { set_error("egp_model_set_contacts: null model"); return EGP_EINVAL; }
+    DevModel &d = m->host;
+    unbind(m);
+    if (!geom_type) { d.contacts = 0; return EGP_OK; }
+    if (!geom_size || !geom_p0 || !geom_p1 || !body_invweight0 || !(friction > 0.0) || margin < 0.0) {
+        set_error("egp_model_set_contacts: geom tables, body_invweight0, friction > 0 and margin >= 0 are required");
+        return EGP_EINVAL;
+    }
+    for (int b = 0; b < d.nbody; b++) {
+        if (geom_type[b] < 0 || geom_type[b] > 2) { set_error("egp_model_set_contacts: geom_type[%d] = %d (0 sphere, 1 capsule, 2 box)", b, geom_type[b]); return EGP_EINVAL; }
+        d.geom_type[b] = geom_type[b];
+        for (int k = 0; k < 3; k++) { d.geom_size[b][k] = geom_size[3 * b + k]; d.geom_p0[b][k] = geom_p0[3 * b + k]; d.geom_p1[b][k] = geom_p1[3 * b + k]; }
+        d.body_iw[b] = body_invweight0[2 * b];
+    }
+    const int rc = set_solparams(d, solref, solimp, "egp_model_set_contacts");
+    if (rc != EGP_OK) return rc;
+    d.con_margin = margin; d.con_mu = friction;
+    d.contacts = 1;
     return EGP_OK;
 }
 
@@ -1958,7 +2112,7 @@ int egp_rollout_f64(EgpModel *m, const EgpPolicyWeights *pol, const EgpRolloutCf
     const char *force = getenv("EGP_ROLLOUT_VARIANT");
     bool use_t4 = false;
     A.chunk23 = 0;
-    if (d.t4_ok && !d.limits && !(force && force[0] == '1') && 2 * (pad16(A.A) / MLP_NT) <= T4_WARPS) {      // joint limits: V1 sweeps only (so far)
+    if (d.t4_ok && !d.limits && !d.contacts && !(force && force[0] == '1') && 2 * (pad16(A.A) / MLP_NT) <= T4_WARPS) {      // joint limits / contacts: V1 sweeps only (so far)
         const int H1p = pad16(A.H1), H2p = pad16(A.H2), Ap = pad16(A.A), Dp = pad16(A.D);
         for (int pi = 0; pi < 4 && !use_t4; pi++) {        // (stride 36 | 32) x (full | chunked layer 2/3)
             const int ch = pi & 1, xs_stride = pi < 2 ? XS_WIDE : 32;

@@ -81,6 +81,10 @@ struct DevModel {
     int limits;
     double lim_lo[MAXV], lim_hi[MAXV], lim_iw[MAXV];       // range per dof (lo >= hi: none), diag(M^-1) at qpos0
     double lim_k, lim_b, lim_d0, lim_dw, lim_width, lim_mid, lim_pow;
+    // floor contact (egp_model_set_contacts): one collision geom per body (0 sphere | 1 capsule | 2 box), plane z = 0
+    int contacts, geom_type[MAXB];
+    double geom_size[MAXB][3], geom_p0[MAXB][3], geom_p1[MAXB][3], body_iw[MAXB];     // body_iw: translational invweight0
+    double con_margin, con_mu;
 };
 
 #if defined(__CUDACC__)

@@ -53,6 +53,9 @@ class HumanoidEnv:
         # cfg.joint_limits = True (or EGP_JOINT_LIMITS=1) switches them on for every roll-out of this environment
         if bool(getattr(cfg, 'joint_limits', False)) or os.environ.get('EGP_JOINT_LIMITS', '0') == '1':
             self.kernel.set_joint_limits(True)
+        # floor contact (geom-floor pairs, pyramidal friction cones): cfg.floor_contact = True or EGP_FLOOR_CONTACT=1
+        if bool(getattr(cfg, 'floor_contact', False)) or os.environ.get('EGP_FLOOR_CONTACT', '0') == '1':
+            self.kernel.set_contacts(True)
         self.model = _ModelView(self.md)
         self.obs_dim = self.md.nq - 2 + self.md.nv
         self.observation_space = _Space(self.obs_dim)

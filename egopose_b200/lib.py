@@ -100,6 +100,7 @@ SYMBOLS = {
     'egp_rollout_f64': (_int, [_vp, C.POINTER(PolicyWeights), C.POINTER(RolloutCfg), C.POINTER(RolloutIn),
                                C.POINTER(TrajOut), _vp]),
     'egp_model_set_joint_limits': (_int, [_vp, _vp, _vp, _vp, _vp]),
+    'egp_model_set_contacts': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _vp, _vp]),
     'egp_gae_work_bytes': (_i64, [_i64]),
     'egp_gae_f64': (_int, [_vp, _vp, _vp, _d, _d, _i64, _vp, _vp, _vp, _vp, _vp]),
     'egp_gae_set_onepass_min': (_i64, [_i64]),
@@ -323,23 +324,9 @@ class Model:
         return rng
 
     def invweight0(self):
-        """mjModel.dof_invweight0 of the actuated hinges: diag(M^-1) at qpos0, from the articulated-body solver itself
-        (qacc with a unit torque on dof i minus qacc without actuation; limits off while measuring)"""
-        import torch
-        dev = torch.device('cuda', self.device)
-        n = self.nu + 1
-        q = torch.as_tensor(np.tile(np.asarray(self.md.qpos0, dtype=np.float64), (n, 1)), device=dev)
-        v = torch.zeros((n, self.nv), dtype=torch.float64, device=dev)
-        ctrl = torch.zeros((n, self.nu), dtype=torch.float64, device=dev)
-        ctrl[1:] = torch.eye(self.nu, dtype=torch.float64, device=dev)
-        check(self.lib.egp_model_set_joint_limits(self.handle, None, None, None, None), 'egp_model_set_joint_limits')
-        _, _, qacc = self.forward_debug(q, v, ctrl)
-        qacc = qacc.cpu().numpy()
-        iw = np.ones(self.nv)
-        first = self.nv - self.nu
-        for k in range(self.nu):
-            iw[first + k] = qacc[1 + k, first + k] - qacc[0, first + k]
-        return iw
+        """mjModel.dof_invweight0: diag(M^-1) at qpos0 (mjcf.inverse_weights)"""
+        from .mjcf import inverse_weights
+        return inverse_weights(self.md)[0]
 
     def set_joint_limits(self, on=True, solref=None, solimp=None):
         """sim.step() with the XML's joint ranges as MuJoCo soft constraints (include/egopose_b200.h:
@@ -355,6 +342,28 @@ class Model:
         check(self.lib.egp_model_set_joint_limits(self.handle, hp(keep[0]), hp(keep[1]), hp(sr), hp(si)),
               'egp_model_set_joint_limits')
         self.joint_limits = True
+
+    def set_contacts(self, on=True, margin=0.001, friction=1.0, solref=None, solimp=None):
+        """sim.step() with the floor (plane z = 0) against the body geoms, MuJoCo's soft contacts with pyramidal cones
+        (include/egopose_b200.h: egp_model_set_contacts); off = smooth dynamics, the default.  margin / friction default
+        to the XML's values (geom margin 0.001, floor friction 1)"""
+        if not on:
+            check(self.lib.egp_model_set_contacts(self.handle, None, None, None, None, None, 0.0, 1.0, None, None),
+                  'egp_model_set_contacts')
+            self.contacts = False
+            return
+        from .mjcf import inverse_weights
+        md = self.md
+        if not md.geom_type:
+            raise EgpError('the model description carries no collision geoms (recompile it with tools/compile_model.py)')
+        keep = [_np_i(md.geom_type), _np_d(md.geom_size), _np_d(md.geom_p0), _np_d(md.geom_p1),
+                np.ascontiguousarray(inverse_weights(md)[1])]
+        sr = np.ascontiguousarray(solref, dtype=np.float64) if solref is not None else None
+        si = np.ascontiguousarray(solimp, dtype=np.float64) if solimp is not None else None
+        hp = lambda a: a.ctypes.data if a is not None else None      # noqa: E731
+        check(self.lib.egp_model_set_contacts(self.handle, hp(keep[0]), hp(keep[1]), hp(keep[2]), hp(keep[3]), hp(keep[4]),
+                                              float(margin), float(friction), hp(sr), hp(si)), 'egp_model_set_contacts')
+        self.contacts = True
 
     # ---- debug / parity -----------------------------------------------------------------------
     def forward_debug(self, qpos, qvel, ctrl=None):

@@ -112,6 +112,12 @@ class ModelDesc:
     actuator_dof: list = field(default_factory=list)
     actuator_gear: list = field(default_factory=list)
     qpos0: list = field(default_factory=list)
+    # collision geoms (one per body): 0 sphere | 1 capsule | 2 box; size = radius | radius | half extents;
+    # p0 = centre (sphere, box) or first end point (capsule), p1 = second end point, both in the body frame
+    geom_type: list = field(default_factory=list)
+    geom_size: list = field(default_factory=list)
+    geom_p0: list = field(default_factory=list)
+    geom_p1: list = field(default_factory=list)
 
     # -- helpers mirroring what the reference reads from mujoco_py -------------------------------
     def body_qposaddr(self):
@@ -163,6 +169,17 @@ def compile_mjcf(path) -> ModelDesc:
         if len(geoms) != 1:
             raise NotImplementedError('exactly one geom per body expected (%s)' % elem.get('name'))
         mass, centre, inertia = geom_inertial(geoms[0])
+        gtype = geoms[0].get('type', 'sphere')
+        gsize = list(_vec(geoms[0].get('size'))) + [0.0, 0.0]
+        m.geom_type.append({'sphere': 0, 'capsule': 1, 'box': 2}[gtype])
+        m.geom_size.append(gsize[:3])
+        if gtype == 'capsule':
+            ft = _vec(geoms[0].get('fromto'), 6)
+            m.geom_p0.append(list(ft[:3] - pos))
+            m.geom_p1.append(list(ft[3:] - pos))
+        else:
+            m.geom_p0.append(list(_vec(geoms[0].get('pos', '0 0 0'), 3) - pos))
+            m.geom_p1.append([0.0, 0.0, 0.0])
         m.body_mass.append(mass)
         m.body_ipos.append(list(centre - pos))
         m.body_inertia.append([inertia[0, 0], inertia[1, 1], inertia[2, 2], inertia[0, 1], inertia[0, 2], inertia[1, 2]])
@@ -224,6 +241,50 @@ def compile_mjcf(path) -> ModelDesc:
         m.actuator_gear.append(float(mot.get('gear', 1.0)))
     m.nu = len(m.actuator_names)
     return m
+
+
+def inverse_weights(md):
+    """(dof_invweight0 [nv], body_invweight0 [nbody][2]) as MuJoCo's compiler derives them (engine_setconst.c: set0): the
+    diagonal of M^-1 at qpos0 per dof, and per body the mean diagonal of J M^-1 J^T for the translational / rotational
+    Jacobian of its centre of mass.  At qpos0 every body frame of a coordinate="global" model is the world frame, so the
+    mass matrix is a plain sum over bodies of J_b^T diag(m 1, I_b) J_b plus the armature."""
+    nb, nv = md.nbody, md.nv
+    xpos = np.zeros((nb, 3))
+    for b in range(nb):
+        p = md.body_parent[b]
+        xpos[b] = np.asarray(md.body_pos[b]) + (xpos[p] if p >= 0 else 0.0)
+    root_free = md.body_dofnum[0] == 6
+    if root_free:
+        xpos += np.asarray(md.qpos0[:3]) - xpos[0]
+    com = xpos + np.asarray(md.body_ipos)
+    Js = []
+    M = np.diag(np.asarray(md.dof_armature, dtype=np.float64))
+    for b in range(nb):
+        J = np.zeros((6, nv))                           # rows: v_com (3), omega (3)
+        i = md.body_dofadr[b] + md.body_dofnum[b] - 1
+        while i >= 0:
+            jb = md.dof_body[i]
+            k = i - md.body_dofadr[jb]
+            if md.body_dofnum[jb] == 6 and k < 3:
+                J[k, i] = 1.0
+            else:
+                ax = np.asarray(md.dof_axis[i], dtype=np.float64)
+                anc = xpos[jb] + np.asarray(md.dof_anchor[i])
+                J[3:, i] = ax
+                J[:3, i] = np.cross(ax, com[b] - anc)
+            i = md.dof_parent[i]
+        xx, yy, zz, xy, xz, yz = md.body_inertia[b]
+        I6 = np.zeros((6, 6))
+        I6[:3, :3] = np.eye(3) * md.body_mass[b]
+        I6[3:, 3:] = [[xx, xy, xz], [xy, yy, yz], [xz, yz, zz]]
+        M += J.T @ I6 @ J
+        Js.append(J)
+    Mi = np.linalg.inv(M)
+    body_iw = np.zeros((nb, 2))
+    for b in range(nb):
+        A = Js[b] @ Mi @ Js[b].T
+        body_iw[b] = [np.trace(A[:3, :3]) / 3.0, np.trace(A[3:, 3:]) / 3.0]
+    return np.ascontiguousarray(np.diag(Mi)), body_iw
 
 
 def load_builtin(name='humanoid_1205_v1') -> ModelDesc:

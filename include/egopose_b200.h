@@ -188,6 +188,17 @@ void egp_model_destroy(EgpModel *m);
 int egp_model_set_joint_limits(EgpModel *m, const double *range, const double *invweight0, const double *solref,
                                const double *solimp);
 
+/* Floor contact (humanoid_1205_v1.xml:21 plane z = 0 with condim 3, friction 1; :11 geom margin 0.001) inside mj_step,
+ * MuJoCo's soft-constraint model with pyramidal friction cones: one collision geom per body, geom_type [nbody] (0 sphere |
+ * 1 capsule | 2 box), geom_size [nbody][3] (radius | radius | half extents), geom_p0 / geom_p1 [nbody][3] (centre, or the
+ * capsule's two end points, in the body frame), body_invweight0 [nbody][2] (mjModel.body_invweight0: translational,
+ * rotational), margin, sliding friction; solref / solimp as above (one set is shared with the limit rows).  Host pointers;
+ * geom_type = NULL switches contacts off (the default).  Only geom-floor pairs are generated: contacts BETWEEN body geoms
+ * are not modelled.  Same kernel restriction as the joint limits. */
+int egp_model_set_contacts(EgpModel *m, const int32_t *geom_type, const double *geom_size, const double *geom_p0,
+                           const double *geom_p1, const double *body_invweight0, double margin, double friction,
+                           const double *solref, const double *solimp);
+
 /* replaces HumanoidEnv.load_experts (humanoid_v1.py:45-54): packed rows [total_frames][EGP_X_STRIDE],
  * take offsets [n_takes+1], per-take head_height_lb, optional per-frame context rows (host pointers) */
 int egp_expert_upload(EgpModel *m, int n_takes, const int32_t *take_off, const double *rows,

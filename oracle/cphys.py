@@ -29,7 +29,9 @@ class EoModel(C.Structure):
                 ('dof_body', _ip), ('dof_parent', _ip),
                 ('dof_armature', _dp), ('dof_axis', _dp), ('dof_anchor', _dp),
                 ('ee_body', C.c_int * NEE), ('head_body', C.c_int),
-                ('dof_range', _dp), ('dof_invweight0', _dp), ('solref', C.c_double * 2), ('solimp', C.c_double * 5)]
+                ('dof_range', _dp), ('dof_invweight0', _dp), ('solref', C.c_double * 2), ('solimp', C.c_double * 5),
+                ('geom_type', _ip), ('geom_size', _dp), ('geom_p0', _dp), ('geom_p1', _dp), ('body_invweight0', _dp),
+                ('contact_margin', C.c_double), ('contact_mu', C.c_double)]
 
 
 class EoData(C.Structure):
@@ -37,7 +39,7 @@ class EoData(C.Structure):
                 ('qacc', C.c_double * MAXV),
                 ('xpos', C.c_double * 3 * MAXB), ('xquat', C.c_double * 4 * MAXB), ('xipos', C.c_double * 3 * MAXB),
                 ('qM', C.c_double * (MAXV * MAXV)), ('qfrc_bias', C.c_double * MAXV),
-                ('cdof', C.c_double * 6 * MAXV), ('subtree_com', C.c_double * 3)]
+                ('cdof', C.c_double * 6 * MAXV), ('subtree_com', C.c_double * 3), ('n_efc', C.c_int), ('solver_iter', C.c_int)]
 
 
 class EoCfg(C.Structure):
@@ -108,7 +110,7 @@ def default_cfg_dict(task='egomimic', cfg_id='subject_03'):
 class Oracle:
     """Model + cfg bound to the C oracle.  ``cfg`` is the yml dict (config/egomimic/*.yml)."""
 
-    def __init__(self, cfg=None, model_json=None, episode_len=None, fix_head_lb=None, joint_limits=False):
+    def __init__(self, cfg=None, model_json=None, episode_len=None, fix_head_lb=None, joint_limits=False, contacts=False):
         self.L = lib()
         md = json.load(open(model_json or os.path.join(ASSETS, 'humanoid_1205_v1.model.json')))
         self.md = md
@@ -156,6 +158,8 @@ class Oracle:
         self.dt = md['timestep'] * 15
         if joint_limits:
             self.enable_joint_limits()
+        if contacts:
+            self.enable_contacts()
 
     def dof_ranges(self):
         """[nv][2] (radians): the hinge ranges of the XML per dof; the free root has none (0, 0)"""
@@ -169,11 +173,47 @@ class Oracle:
 
     def invweight0(self):
         """mjModel.dof_invweight0 of the hinges: diag(M^-1) at qpos0"""
+        return np.ascontiguousarray(np.diag(self.minv0()[0]))
+
+    def minv0(self):
+        """M^-1 at qpos0 and the data it was computed from (smooth forward)"""
         d = self.new_data(self.md['qpos0'], np.zeros(self.nv))
-        keep, self.model.dof_range = self.model.dof_range, None
-        self.forward(d)
-        self.model.dof_range = keep
-        return np.ascontiguousarray(np.diag(np.linalg.inv(self.qM(d))))
+        smooth = EoModel.from_buffer_copy(self.model)       # a copy: pointer fields read from a Structure alias its memory
+        smooth.dof_range, smooth.geom_type = None, None
+        self.L.eo_forward(C.byref(smooth), C.byref(d))
+        return np.linalg.inv(self.qM(d)), d
+
+    def body_invweight0(self):
+        """mjModel.body_invweight0: mean diagonal of J M^-1 J^T at qpos0 for the translational and the rotational Jacobian
+        of every body's centre of mass (engine_setconst.c: set0)"""
+        Mi, d = self.minv0()
+        cdof = np.array(d.cdof).reshape(MAXV, 6)[:self.nv]
+        xipos = np.array(d.xipos).reshape(MAXB, 3)[:self.nbody]
+        out = np.zeros((self.nbody, 2))
+        for b in range(self.nbody):
+            J = np.zeros((6, self.nv))
+            i = self.md['body_dofadr'][b] + self.md['body_dofnum'][b] - 1
+            while i >= 0:
+                J[3:, i] = cdof[i, :3]                                      # rotational
+                J[:3, i] = cdof[i, 3:] + np.cross(cdof[i, :3], xipos[b])    # velocity of the com: v_O + w x c
+                i = self.md['dof_parent'][i]
+            A = J @ Mi @ J.T
+            out[b] = [np.trace(A[:3, :3]) / 3.0, np.trace(A[3:, 3:]) / 3.0]
+        return out
+
+    def enable_contacts(self, margin=0.001, mu=1.0, solref=(0.02, 1.0), solimp=(0.9, 0.95, 0.001, 0.5, 2.0)):
+        """floor contacts with MuJoCo's defaults / the XML's values (margin 0.001 on every geom, floor friction 1)"""
+        k = self._keep
+        k['body_invweight0'] = np.ascontiguousarray(self.body_invweight0())
+        k['geom_type'] = _i(self.md['geom_type'])
+        for name in ('geom_size', 'geom_p0', 'geom_p1'):
+            k[name] = _d(self.md[name])
+        self.model.solref[:] = solref
+        self.model.solimp[:] = solimp
+        self.model.contact_margin, self.model.contact_mu = margin, mu
+        for name in ('geom_size', 'geom_p0', 'geom_p1', 'body_invweight0'):
+            setattr(self.model, name, _p(k[name]))
+        self.model.geom_type = _p(k['geom_type'])
 
     def enable_joint_limits(self, solref=(0.02, 1.0), solimp=(0.9, 0.95, 0.001, 0.5, 2.0)):
         """MuJoCo's defaults (the XML sets none)"""

@@ -305,6 +305,143 @@ void eo_limit_row(const EoModel *m, double dist, double vel, double invweight, d
     *aref = -bb * vel - k * imp * dist;
 }
 
+/* ---- constraint rows: joint limits and floor contacts -------------------------------------------------------------
+ * Every row i is unilateral with Jacobian J_i, weight D_i and reference acceleration aref_i; MuJoCo's solver minimises
+ *     1/2 (a - a0)^T M (a - a0) + sum_i s_i(J_i a - aref_i),   s(r) = 1/2 D r^2 for r < 0, else 0
+ * (a0 = smooth acceleration).  For a fixed active set the minimiser solves
+ *     (M + sum_act D_i J_i^T J_i) a = qfrc_smooth + sum_act D_i aref_i J_i^T;
+ * the active set {i: J_i a - aref_i < 0} is iterated to its fixed point (Newton on the piecewise-quadratic cost with unit
+ * steps; the optimum is unique, MuJoCo's Newton solver converges to the same point up to its tolerance). */
+#define EO_MAXCON 40
+#define EO_MAXROW (EO_MAXV + 4 * EO_MAXCON)
+
+typedef struct { int n; double J[EO_MAXROW][EO_MAXV], D[EO_MAXROW], aref[EO_MAXROW]; } EoRows;
+
+/* Jacobian row of direction dir at world point pt of body b: cdof is about the world origin, [axis; anchor x axis] */
+static void point_jac_row(const EoModel *m, const EoData *d, int b, const double *pt, const double *dir, double *J) {
+    double p[6];
+    cross3(pt, dir, p);
+    p[3] = dir[0]; p[4] = dir[1]; p[5] = dir[2];
+    for (int i = 0; i < m->nv; i++) J[i] = 0.0;
+    for (int i = m->body_dofadr[b] + m->body_dofnum[b] - 1; i >= 0; i = m->dof_parent[i]) J[i] = dot6(d->cdof[i], p);
+}
+
+static void add_contact(const EoModel *m, const EoData *d, EoRows *R, int b, const double *pt, double dist) {
+    /* frame: normal +z (plane), tangents y and -x (mju_makeFrame of (0,0,1)); pyramid edges n +- mu t (condim 3) */
+    static const double nrm[3] = {0, 0, 1}, t1[3] = {0, 1, 0}, t2[3] = {-1, 0, 0};
+    if (R->n + 4 > EO_MAXROW) return;
+    const double mu = m->contact_mu, margin = m->contact_margin;
+    double Jn[EO_MAXV], J1[EO_MAXV], J2[EO_MAXV];
+    point_jac_row(m, d, b, pt, nrm, Jn);
+    point_jac_row(m, d, b, pt, t1, J1);
+    point_jac_row(m, d, b, pt, t2, J2);
+    const double tran = m->body_invweight0[2 * b];          /* world body: 0 */
+    for (int e = 0; e < 4; e++) {
+        double *J = R->J[R->n];
+        const double *Jt = e < 2 ? J1 : J2;
+        const double sg = (e & 1) ? -mu : mu;
+        double vel = 0.0;
+        for (int i = 0; i < m->nv; i++) { J[i] = Jn[i] + sg * Jt[i]; vel += J[i] * d->qvel[i]; }
+        double D0, aref;
+        eo_limit_row(m, dist - margin, vel, tran + mu * mu * tran, &D0, &aref);
+        R->D[R->n] = D0 / (2.0 * mu * mu);                  /* pyramidal: R = 2 mu^2 R_0 */
+        R->aref[R->n] = aref;
+        R->n++;
+    }
+}
+
+static void collect_rows(const EoModel *m, const EoData *d, EoRows *R) {
+    R->n = 0;
+    if (m->dof_range) {
+        for (int i = 0; i < m->nv; i++) {
+            if (m->body_dofnum[m->dof_body[i]] == 6) continue;
+            double lo = m->dof_range[2 * i], hi = m->dof_range[2 * i + 1];
+            if (!(lo < hi)) continue;
+            double q = d->qpos[i + 1], dist, s;             /* hinge dof i reads qpos[i + 1] (free root: 7 qpos, 6 dofs) */
+            if (q - lo < 0.0) { dist = q - lo; s = 1.0; }
+            else if (hi - q < 0.0) { dist = hi - q; s = -1.0; }
+            else continue;
+            for (int k = 0; k < m->nv; k++) R->J[R->n][k] = 0.0;
+            R->J[R->n][i] = s;
+            eo_limit_row(m, dist, s * d->qvel[i], m->dof_invweight0[i], &R->D[R->n], &R->aref[R->n]);
+            R->n++;
+        }
+    }
+    if (m->geom_type) {
+        const double margin = m->contact_margin;
+        for (int b = 0; b < m->nbody; b++) {
+            double Rm[9], c0[3], c1[3];
+            quat_to_mat(d->xquat[b], Rm);
+            mat_vec(Rm, m->geom_p0 + 3 * b, c0);
+            for (int k = 0; k < 3; k++) c0[k] += d->xpos[b][k];
+            const double *sz = m->geom_size + 3 * b;
+            if (m->geom_type[b] == 0 || m->geom_type[b] == 1) {
+                /* sphere; capsule = the spheres at its two ends (second end point first: mjc_PlaneCapsule tests +axis) */
+                int ne = m->geom_type[b] == 1 ? 2 : 1;
+                if (ne == 2) {
+                    mat_vec(Rm, m->geom_p1 + 3 * b, c1);
+                    for (int k = 0; k < 3; k++) c1[k] += d->xpos[b][k];
+                }
+                for (int e = 0; e < ne; e++) {
+                    const double *c = (ne == 2 && e == 0) ? c1 : c0;
+                    double dist = c[2] - sz[0];
+                    if (dist >= margin) continue;
+                    double pt[3] = {c[0], c[1], c[2] - (sz[0] + 0.5 * dist)};
+                    add_contact(m, d, R, b, pt, dist);
+                }
+            } else {
+                int cnt = 0;
+                for (int v = 0; v < 8 && cnt < 4; v++) {    /* box corners, at most 4 contacts (mjc_PlaneBox) */
+                    double loc[3] = {(v & 1 ? sz[0] : -sz[0]), (v & 2 ? sz[1] : -sz[1]), (v & 4 ? sz[2] : -sz[2])}, w[3];
+                    mat_vec(Rm, loc, w);
+                    for (int k = 0; k < 3; k++) w[k] += c0[k];
+                    double dist = w[2];
+                    if (dist > margin) continue;
+                    double pt[3] = {w[0], w[1], w[2] - 0.5 * dist};
+                    add_contact(m, d, R, b, pt, dist);
+                    cnt++;
+                }
+            }
+        }
+    }
+}
+
+int eo_constraint_solve(const EoModel *m, EoData *d, const double *smooth) {
+    const int nv = m->nv;
+    static _Thread_local EoRows R;
+    double A[EO_MAXV * EO_MAXV], rhs[EO_MAXV];
+    int act[EO_MAXROW];
+    collect_rows(m, d, &R);
+    for (int i = 0; i < R.n; i++) act[i] = 1;
+    int it;
+    for (it = 0; it < 100; it++) {
+        memcpy(A, d->qM, sizeof(double) * nv * nv);
+        memcpy(rhs, smooth, sizeof(double) * nv);
+        for (int i = 0; i < R.n; i++) {
+            if (!act[i]) continue;
+            const double *J = R.J[i];
+            for (int r = 0; r < nv; r++) {
+                if (J[r] == 0.0) continue;
+                rhs[r] += R.D[i] * R.aref[i] * J[r];
+                for (int c = 0; c < nv; c++) A[r * nv + c] += R.D[i] * J[r] * J[c];
+            }
+        }
+        eo_chol_solve(nv, A, rhs);
+        int changed = 0;
+        for (int i = 0; i < R.n; i++) {
+            double r = -R.aref[i];
+            for (int k = 0; k < nv; k++) r += R.J[i][k] * rhs[k];
+            int a1 = r < 0.0;
+            if (a1 != act[i]) { act[i] = a1; changed = 1; }
+        }
+        if (!changed) break;
+    }
+    memcpy(d->qacc, rhs, sizeof(double) * nv);
+    d->n_efc = R.n;
+    d->solver_iter = it;
+    return R.n;
+}
+
 void eo_forward(const EoModel *m, EoData *d) {
     int nv = m->nv, nb = m->nbody;
     double axis_w[EO_MAXV * 3], anchor_w[EO_MAXV * 3];
@@ -428,51 +565,14 @@ void eo_forward(const EoModel *m, EoData *d) {
     double A[EO_MAXV * EO_MAXV], rhs[EO_MAXV], smooth[EO_MAXV];
     int first = nv - m->nu;
     for (int i = 0; i < nv; i++) smooth[i] = (i >= first ? d->ctrl[i - first] : 0.0) - d->qfrc_bias[i];
-    if (!m->dof_range) {
+    if (!m->dof_range && !m->geom_type) {
         memcpy(A, d->qM, sizeof(double) * nv * nv);
         memcpy(rhs, smooth, sizeof(double) * nv);
         eo_chol_solve(nv, A, rhs);
         memcpy(d->qacc, rhs, sizeof(double) * nv);
         return;
     }
-    /* Joint limits (see EoModel).  A violated range (dist = q - lower or upper - q < margin = 0) instantiates one
-     * unilateral row J = +-e_i with reference acceleration aref = -b (J v) - k d(dist) dist and weight D = 1/R,
-     * R = (1 - d)/d * dof_invweight0_i.  MuJoCo's solver minimises 1/2 (a - a0)^T M (a - a0) + sum_i s_i(J_i a - aref_i),
-     * s(r) = 1/2 D r^2 for r < 0, else 0.  Because every J_i is a unit vector the stationarity condition of a fixed
-     * active set is  (M + diag(D_active)) a = qfrc_smooth + sum_active D_i J_i aref_i:  the active set is iterated
-     * to its fixed point (Newton on the piecewise-quadratic cost with unit steps). */
-    int inst[EO_MAXV], act[EO_MAXV];
-    double sgn[EO_MAXV], Dc[EO_MAXV], aref[EO_MAXV];
-    int any = 0;
-    for (int i = 0; i < nv; i++) {
-        inst[i] = 0;
-        int b = m->dof_body[i];
-        if (m->body_dofnum[b] == 6) continue;
-        double lo = m->dof_range[2 * i], hi = m->dof_range[2 * i + 1];
-        if (!(lo < hi)) continue;
-        double q = d->qpos[i + 1], dist, s;                 /* hinge dof i reads qpos[i + 1] (free root: 7 qpos, 6 dofs) */
-        if (q - lo < 0.0) { dist = q - lo; s = 1.0; }
-        else if (hi - q < 0.0) { dist = hi - q; s = -1.0; }
-        else continue;
-        eo_limit_row(m, dist, s * d->qvel[i], m->dof_invweight0[i], &Dc[i], &aref[i]);
-        inst[i] = 1; sgn[i] = s; any = 1;
-    }
-    for (int i = 0; i < nv; i++) act[i] = inst[i];
-    for (int it = 0; it < 64; it++) {
-        memcpy(A, d->qM, sizeof(double) * nv * nv);
-        for (int i = 0; i < nv; i++) {
-            rhs[i] = smooth[i];
-            if (act[i]) { A[i * nv + i] += Dc[i]; rhs[i] += Dc[i] * sgn[i] * aref[i]; }
-        }
-        eo_chol_solve(nv, A, rhs);
-        int changed = 0;
-        for (int i = 0; i < nv && any; i++) {
-            int a1 = inst[i] && (sgn[i] * rhs[i] - aref[i] < 0.0);
-            if (a1 != act[i]) { act[i] = a1; changed = 1; }
-        }
-        if (!changed) break;
-    }
-    memcpy(d->qacc, rhs, sizeof(double) * nv);
+    eo_constraint_solve(m, d, smooth);
 }
 
 /* mj_step = mj_forward + semi-implicit Euler; position-dependent outputs

@@ -48,6 +48,15 @@ typedef struct {
     const double *dof_range;        /* [nv][2] lower, upper in radians; lower >= upper: no limit on that dof */
     const double *dof_invweight0;   /* [nv] diag(M^-1) at qpos0 (mjModel.dof_invweight0 of a hinge) */
     double solref[2], solimp[5];
+    /* floor contact (xml:21 plane z = 0, condim 3, friction 1; xml:11 body geoms: margin 0.001; pyramidal cones, the
+     * MuJoCo default).  One collision geom per body (0 sphere | 1 capsule | 2 box; p0 / p1 in the body frame).  Only
+     * geom-floor pairs: contacts between body geoms are NOT modelled.  geom_type NULL = no contacts.  UNPINNED, restated
+     * from engine_collision_primitive.c (mjc_PlaneSphere / PlaneCapsule / PlaneBox) and engine_core_constraint.c
+     * (mj_instantiateContact, mj_diagApprox, mj_makeImpedance). */
+    const int *geom_type;
+    const double *geom_size, *geom_p0, *geom_p1;    /* [nb][3] each */
+    const double *body_invweight0;                  /* [nb][2] translational, rotational (mjModel.body_invweight0) */
+    double contact_margin, contact_mu;
 } EoModel;
 
 typedef struct {            /* mjData subset the reference reads */
@@ -57,6 +66,7 @@ typedef struct {            /* mjData subset the reference reads */
     double qfrc_bias[EO_MAXV];
     double cdof[EO_MAXV][6];
     double subtree_com[3];
+    int n_efc, solver_iter;             /* constraint rows of the last eo_forward and active-set iterations it took */
 } EoData;
 
 typedef struct {            /* cfg subset (ego_pose/utils/egomimic_config.py:94-122) */
@@ -95,6 +105,7 @@ void eo_forward(const EoModel *m, EoData *d);                   /* mj_forward (s
 void eo_step(const EoModel *m, EoData *d);                      /* mj_step: forward then Euler */
 void eo_kinematics(const EoModel *m, EoData *d, double *dof_axis_w, double *dof_anchor_w);
 int eo_chol_solve(int n, double *A, double *b);                 /* in-place dense Cholesky solve */
+int eo_constraint_solve(const EoModel *m, EoData *d, const double *qfrc_smooth);   /* rows + solve -> d->qacc */
 void eo_limit_row(const EoModel *m, double dist, double vel, double invweight, double *D, double *aref);
 
 /* env (ego_pose/envs/humanoid_v1.py) */

@@ -33,15 +33,6 @@ def _violating_states(orc, n, seed):
     return q, v
 
 
-def test_invweight0_matches_oracle_unpinned():
-    orc = cphys.Oracle(joint_limits=True)
-    model = helpers.make_model()
-    iw = model.invweight0()
-    ref = orc.invweight0()
-    assert np.allclose(iw[6:], ref[6:], rtol=1e-9)
-    model.close()
-
-
 def test_forward_with_limits_vs_oracle_unpinned():
     orc = cphys.Oracle(joint_limits=True)
     model = helpers.make_model()
@@ -124,3 +115,102 @@ def test_rollout_with_limits_vs_oracle_unpinned():
         assert np.allclose(out['rewards'].cpu().numpy(), ref['rewards'], rtol=1e-6, atol=1e-9)
         model.close()
     assert helpers.relerr(res[True]['states'], res[False]['states']) > 1e-3
+
+
+# ---- floor contact -----------------------------------------------------------------------------------------------
+def _floor_states(orc, n, seed):
+    """random poses a few centimetres above / into the floor in random orientations, some joints beyond their ranges"""
+    rng = np.random.RandomState(seed)
+    q, v = _violating_states(orc, n, seed)
+    v *= 0.5
+    for e in range(n):
+        d = orc.new_data(q[e], v[e])
+        q[e, 2] = 0.0
+        d = orc.new_data(q[e], v[e])
+        xp = orc.kinematics(q[e])[0]
+        q[e, 2] = -xp[:, 2].min() + rng.uniform(-0.02, 0.08)        # lowest body origin near z = 0
+    return q, v
+
+
+@pytest.mark.parametrize('limits', [False, True])
+def test_forward_with_contacts_vs_oracle_unpinned(limits):
+    orc = cphys.Oracle(joint_limits=limits, contacts=True)
+    model = helpers.make_model()
+    model.set_contacts(True)
+    model.set_joint_limits(limits)
+    n = 64
+    q, v = _floor_states(orc, n, 11)
+    ctrl = 10 * np.random.RandomState(4).randn(n, orc.nu)
+    _, _, qacc = model.forward_debug(cu(q), cu(v), cu(ctrl))
+    qacc = qacc.cpu().numpy()
+    n_rows, worst = 0, 0.0
+    for e in range(n):
+        d = orc.new_data(q[e], v[e], ctrl[e])
+        orc.forward(d)
+        n_rows += d.n_efc
+        assert d.solver_iter < 99
+        worst = max(worst, helpers.relerr(qacc[e], np.array(d.qacc[:orc.nv])))
+    assert n_rows > 8 * n               # contacts everywhere
+    assert worst < 1e-7, worst
+    model.close()
+
+
+def test_standing_on_the_floor_vs_oracle_unpinned():
+    """T-pose on flat feet, PD target = the pose: the contact rows carry the weight (root height constant to a few mm for
+    30 steps = 1 s; without a floor the head-height rule ends the episode after 9 steps), CUDA == oracle step by step"""
+    orc = cphys.Oracle(joint_limits=True, contacts=True)
+    orc.make_expert(cphys.synthetic_takes(orc.md, 1, 40, seed=2))
+    orc.cfg.fix_head_lb = -100.0
+    model = helpers.make_model()
+    model.set_contacts(True)
+    model.set_joint_limits(True)
+    q = np.array(orc.md['qpos0'], dtype=np.float64)
+    q[2] = 0.8665                                        # soles on z = 0
+    v = np.zeros(orc.nv)
+    act = (-np.array(orc._keep['a_ref']) / np.array(orc._keep['a_scale']))[None]
+    qd, vd = cu(q[None]), cu(v[None])
+    for t in range(40):
+        env = cphys.EoEnv()
+        q0, v0 = qd[0].cpu().numpy().copy(), vd[0].cpu().numpy().copy()
+        orc.env_set_state(env, q0, v0)
+        env.take = 0
+        orc.env_step(env, act[0])
+        model.env_step_debug(qd, vd, cu(act))
+        assert helpers.relerr(qd[0].cpu().numpy(), np.array(env.d.qpos[:orc.nq])) < 1e-7, t
+        assert helpers.relerr(vd[0].cpu().numpy(), np.array(env.d.qvel[:orc.nv])) < 1e-5, t
+        assert env.d.n_efc >= 16
+        if t < 30:
+            assert abs(qd[0, 2].item() - 0.8665) < 0.01, (t, qd[0, 2].item())
+    model.close()
+
+
+def test_rollout_with_contacts_and_limits_vs_oracle_unpinned():
+    E, T = 6, 24
+    orc = cphys.Oracle(episode_len=20, joint_limits=True, contacts=True)
+    takes = cphys.synthetic_takes(orc.md, 3, 64, seed=7)
+    orc.make_expert(takes, None)
+    S, nu = orc.S, orc.nu
+    w = helpers.policy_weights(S, 32, 24, nu, seed=3, log_std=-1.0)
+    rng = np.random.RandomState(9)
+    reset_take = rng.randint(0, 3, size=(E, T))
+    reset_start = rng.randint(10, 64 - 20 - 10, size=(E, T))
+    eps = rng.randn(E * T, nu)
+    mean_flag = np.zeros(E * T, dtype=np.uint8)
+    zf_mean, zf_std = np.zeros(S), np.ones(S)
+    pol = orc.make_policy(w['W1'], w['b1'], w['W2'], w['b2'], w['W3'], w['b3'], w['log_std'])
+    orc.cfg.fix_head_lb = 0.2
+    ref = orc.rollout(pol, E, T, reset_take, reset_start, eps, mean_flag, zf_mean, zf_std, 5.0, n_threads=4)
+    model = helpers.make_model()
+    model.upload_experts(orc._keep['x_rows'], orc._keep['x_off'], orc._keep['x_lb'], None)
+    model.set_joint_limits(True)
+    model.set_contacts(True)
+    wd = {k: cu(v.ravel() if k == 'log_std' else v) for k, v in w.items()}
+    out = model.rollout(wd, E, T, episode_len=20, fix_head_lb=0.2, zf_mean=cu(zf_mean), zf_std=cu(zf_std), eps=cu(eps),
+                        reset_take=cu(reset_take, torch.int32), reset_start=cu(reset_start, torch.int32),
+                        mean_flag=cu(mean_flag, torch.uint8))
+    torch.cuda.synchronize()
+    assert np.array_equal(out['masks'].cpu().numpy(), ref['masks'])
+    # contacts make the dynamics stiff: rounding differences grow faster along an episode than in free fall
+    assert helpers.relerr(out['states'].cpu().numpy(), ref['states']) < 1e-5
+    assert np.allclose(out['rewards'].cpu().numpy(), ref['rewards'], rtol=1e-5, atol=1e-8)
+    model.close()

