@@ -60,6 +60,9 @@ def parse():
     ap.add_argument('--hidden', type=int, nargs=2, default=None)
     ap.add_argument('--epochs', type=int, default=10)
     ap.add_argument('--no-variants', action='store_true', help='skip the cuBLAS / 7-slice update timings')
+    ap.add_argument('--physics', choices=['smooth', 'full'], default='smooth',
+                    help='smooth = the north-star scope (no constraints); full = + the 52 joint ranges and floor contact '
+                         '(MuJoCo soft constraints; runs on the one-warp rollout kernel)')
     ap.add_argument('--vsnet', action='store_true', help='egomimic with the learned VideoStateNet (BiLSTM 128 -> 2 x 64 over T + 2 m '
                     'CNN-feature frames) as policy / value context instead of the per-frame table; episodes run the full horizon')
     ap.add_argument('--no-e2e', action='store_true')
@@ -153,6 +156,9 @@ def build_agent(args, device, takes, cnn, gemm=None, oz_slices=None):
     cfg = Config(args.cfg_id, task=args.task)
     cfg.env_episode_len = args.horizon
     env = HumanoidEnv(cfg, device=device.index)
+    if args.physics == 'full':
+        env.kernel.set_joint_limits(True)
+        env.kernel.set_contacts(True)
     env.seed(cfg.seed)
     env.set_expert_qpos(['take_%d' % i for i in range(len(takes))], takes, cnn)
     sd, ad = env.observation_space.shape[0], env.action_space.shape[0]
@@ -405,7 +411,7 @@ def main():
     # `traffic` (dram__bytes_read.sum + dram__bytes_write.sum of ONE launch) and pipe utilisation cannot be measured outside a
     # profiler: they are read from profiles/ncu_captures.json, written by tools/ncu_capture_summary.py from the ncu --set full
     # captures of THIS build at this configuration (the file names its .ncu-rep, commit and date), else null
-    default_cfg = args.config == 2 and (E, T, tuple(args.hidden)) == (4096, 300, (300, 300))
+    default_cfg = args.config == 2 and (E, T, tuple(args.hidden)) == (4096, 300, (300, 300)) and args.physics == 'smooth'
     cap = {}
     try:
         cap = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_captures.json'))) if default_cfg else {}
@@ -431,7 +437,7 @@ def main():
         del sq
     except Exception:
         pass
-    roofline = {'kernel': 'rollout_kernel_t4', 'bound': 'hbm', 'achieved': roll_bytes / (roll_ms / 1e3) / 1e9, 'peak': hbm,
+    roofline = {'kernel': 'rollout_kernel_t4' if args.physics == 'smooth' else 'rollout_kernel (one warp per 32 environments)', 'bound': 'hbm', 'achieved': roll_bytes / (roll_ms / 1e3) / 1e9, 'peak': hbm,
                 'unit': 'GB/s', 'frac': roll_bytes / (roll_ms / 1e3) / 1e9 / hbm,
                 'traffic': cap_of('rollout_kernel_t4', 'dram_bytes'), 'traffic_source': cap_of('rollout_kernel_t4', 'source'),
                 'peak_source': peak_src,
@@ -555,13 +561,16 @@ def main():
                 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
                 'config': {'workload': args.workload, 'baseline_config': args.config, 'envs_per_gpu': E, 'horizon': T, 'hidden': args.hidden,
                            'epochs': args.epochs, 'parallelism': 'env-sharded dp%d' % world,
+                           'physics': ('smooth dynamics (north star)' if args.physics == 'smooth' else
+                                       'smooth dynamics + joint limits + floor contact (one-warp rollout kernel)'),
                            'update_gemm': ('float64 in/out on int8 tcgen05 (Ozaki, %d slices, error <= %.0e of row x column maxima)'
                                            % (agent.oz_slices, (agent.oz_slices + 2) * 2.0 ** (-7 * agent.oz_slices))
                                            if agent.gemm == 'ozaki' else 'cuBLAS DGEMM'),
                            'l2': 'inputs larger than L2 (trajbatch %.1f GB per step)' % (N * (2 * 115 + 52) * 8 / 1e9)},
                 'ms_rollout': ms_roll, 'ms_update': ms_upd, 'update_variants': variants, 'gpu_launches': launches, 'clocks': clocks,
                 'roofline': roofline, 'roofline_extra': extra, 'e2e': e2e, 'cpu_baseline': cpu,
-                'avg_c_reward': log.avg_c_reward, 'avg_episode_len': log.avg_episode_reward,
+                'avg_c_reward': log.avg_c_reward, 'avg_episode_reward': log.avg_episode_reward,
+                'avg_episode_len': log.num_steps / max(1, log.num_episodes),
                 'nan_resets': log.num_nan_resets}
         print(json.dumps(line))
     if world > 1:

@@ -743,12 +743,13 @@ __device__ __forceinline__ const double *ctx_row(const RolloutArgs &A, int take,
 template <bool RELU>
 __device__ __forceinline__ void mlp_layer(const double *__restrict__ Wt, const double *__restrict__ bias, int K, int Np,
                                           const double *xs, double *ys, int lane) {
+    const int EP = blockDim.x;                  // environments of this CTA = row stride of the activation tiles
     for (int j0 = 0; j0 < Np; j0 += JB) {
         double acc[JB];
 #pragma unroll
         for (int jj = 0; jj < JB; jj++) acc[jj] = bias[j0 + jj];
         for (int k = 0; k < K; k++) {
-            const double xv = xs[k * ENVS_PER_CTA + lane];
+            const double xv = xs[k * EP + lane];
             const double2 *w = reinterpret_cast<const double2 *>(Wt + (size_t)k * Np + j0);
 #pragma unroll
             for (int jj = 0; jj < JB / 2; jj++) {
@@ -758,7 +759,7 @@ __device__ __forceinline__ void mlp_layer(const double *__restrict__ Wt, const d
             }
         }
 #pragma unroll
-        for (int jj = 0; jj < JB; jj++) ys[(j0 + jj) * ENVS_PER_CTA + lane] = RELU ? fmax(acc[jj], 0.0) : acc[jj];
+        for (int jj = 0; jj < JB; jj++) ys[(j0 + jj) * EP + lane] = RELU ? fmax(acc[jj], 0.0) : acc[jj];
     }
 }
 
@@ -785,12 +786,14 @@ rollout_kernel(const RolloutArgs A) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x;
     const int S = c_m.nq - 2 + c_m.nv, nu = c_m.nu, nv = c_m.nv, nb = c_m.nbody;
-    double *xs = smem;                                  // [max(D, H2p)][32]
+    // The CTA is one (possibly partial) warp of EP <= 32 environments (32 unless EGP_V1_ENVS_PER_CTA says otherwise)
+    const int EP = blockDim.x;
+    double *xs = smem;                                  // [max(D, H2p)][EP]
     const int xrows = A.D > A.H2p ? A.D : A.H2p;
-    double *h1s = smem + (size_t)xrows * ENVS_PER_CTA;  // [max(H1p, Ap)][32] (also receives the action means)
+    double *h1s = smem + (size_t)xrows * EP;            // [max(H1p, Ap)][EP] (also receives the action means)
     const int T = A.cfg.horizon, E = A.cfg.n_env;
     const double dt = c_m.h * c_m.frame_skip;
-    const int env = blockIdx.x * ENVS_PER_CTA + lane;
+    const int env = blockIdx.x * EP + lane;
     const bool live = env < E;
     const int eid = live ? env : E - 1;                 // idle lanes shadow the last env and write nothing
 
@@ -832,11 +835,11 @@ rollout_kernel(const RolloutArgs A) {
         int off = 0;
         if (A.ctx) {
             const double *cx = ctx_row(A, take, start, cur_t);
-            for (int k = 0; k < A.ctx_dim; k++) xs[k * ENVS_PER_CTA + lane] = cx[k];
+            for (int k = 0; k < A.ctx_dim; k++) xs[k * EP + lane] = cx[k];
             off = A.ctx_dim;
         }
-        for (int k = 0; k < S; k++) xs[(off + k) * ENVS_PER_CTA + lane] = state[k];
-        __syncwarp();
+        for (int k = 0; k < S; k++) xs[(off + k) * EP + lane] = state[k];
+        __syncthreads();
         // ---- PolicyGaussian forward (policy_gaussian.py:19-24, mlp.py:22-25)
         mlp_layer<true>(A.W1t, A.b1, A.D, A.H1p, xs, h1s, lane);
         mlp_layer<true>(A.W2t, A.b2, A.H1, A.H2p, h1s, xs, lane);
@@ -855,8 +858,8 @@ rollout_kernel(const RolloutArgs A) {
                 if (A.in.d_eps) { z0 = A.in.d_eps[n * nu + a]; z1 = a + 1 < nu ? A.in.d_eps[n * nu + a + 1] : 0.0; }
                 else normal2(A.cfg.seed, A.cfg.iteration, (uint32_t)eid, (uint32_t)(t * 64 + a), &z0, &z1);
             }
-            act[a] = h1s[a * ENVS_PER_CTA + lane] + exp(A.log_std[a]) * z0;
-            if (a + 1 < nu) act[a + 1] = h1s[(a + 1) * ENVS_PER_CTA + lane] + exp(A.log_std[a + 1]) * z1;
+            act[a] = h1s[a * EP + lane] + exp(A.log_std[a]) * z0;
+            if (a + 1 < nu) act[a + 1] = h1s[(a + 1) * EP + lane] + exp(A.log_std[a + 1]) * z1;
         }
         if (live) {
             for (int k = 0; k < S; k++) A.out.d_states[n * S + k] = state[k];
@@ -923,7 +926,7 @@ rollout_kernel(const RolloutArgs A) {
         } else {
             for (int k = 0; k < S; k++) state[k] = nstate[k];
         }
-        __syncwarp();
+        __syncthreads();
     }
     if (live) {
         if (A.out.d_final_qpos) for (int k = 0; k < c_m.nq; k++) A.out.d_final_qpos[(size_t)env * c_m.nq + k] = e.q[k];
@@ -2223,7 +2226,14 @@ int egp_rollout_f64(EgpModel *m, const EgpPolicyWeights *pol, const EgpRolloutCf
         else rc2 = launch(rollout_kernel_t4<true, false>);
     } else {
         const int xrows = A.D > A.H2p ? A.D : A.H2p, hrows = A.H1p > A.Ap ? A.H1p : A.Ap;
-        size_t smem = sizeof(double) * ENVS_PER_CTA * ((size_t)xrows + hrows);
+        // environments per CTA: 32.  Narrower CTAs (more warps per SM at 4096 environments) were measured SLOWER on B200
+        // (full-physics rollout 4.28 s at 32, 5.18 s at 16, 6.06 s at 8, 6.73 s at 4): the kernel is bound by its thread-local
+        // tree data moving through L1 / L2, where a partial warp wastes most of every line; EGP_V1_ENVS_PER_CTA keeps the A/B
+        int ep = ENVS_PER_CTA;
+        const char *epf = getenv("EGP_V1_ENVS_PER_CTA");
+        if (epf && atoi(epf) >= 1 && atoi(epf) <= 32) ep = atoi(epf);
+        blocks = (cfg->n_env + ep - 1) / ep;
+        size_t smem = sizeof(double) * ep * ((size_t)xrows + hrows);
         if (smem > 227 * 1024) { set_error("egp_rollout_f64: policy too wide for shared memory (%zu bytes)", smem); return EGP_ESIZE; }
         if (out->d_logger) {            // the one-warp kernel accumulates with atomics
             double init[EGP_LOG_SIZE] = {0};
@@ -2232,7 +2242,7 @@ int egp_rollout_f64(EgpModel *m, const EgpPolicyWeights *pol, const EgpRolloutCf
             EGP_CUDA(cudaMemcpyAsync(out->d_logger, init, sizeof init, cudaMemcpyHostToDevice, st));
         }
         EGP_CUDA(cudaFuncSetAttribute(rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        rollout_kernel<<<blocks, ENVS_PER_CTA, smem, st>>>(A);
+        rollout_kernel<<<blocks, ep, smem, st>>>(A);
         EGP_CHECK_LAUNCH("rollout_kernel");
     }
     if (rc2 != EGP_OK) return rc2;
