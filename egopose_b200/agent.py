@@ -438,6 +438,25 @@ class AgentPG(Agent):
         nv = sum(p.numel() for _, p in val)
         npol = sum(p.numel() for _, p in pol)
         self._gflat = torch.zeros(nv + npol, dtype=torch.float64, device=dev)
+        # With several ranks the flat gradient lives in this rank's peer-memory exchange block (csrc/p2p.cu): the
+        # per-epoch sum is one kernel that reads the peers' blocks over NVLink, no NCCL call.  EGP_GRAD_EXCHANGE=nccl
+        # keeps torch.distributed's all-reduce; the choice is collective (every rank must have mapped every peer).
+        self._peer = None
+        d = _dist()
+        if d is not None and d.get_world_size() > 1 and os.environ.get('EGP_GRAD_EXCHANGE', 'p2p') != 'nccl':
+            ok, peer = 1, None
+            try:
+                peer = lib.PeerComm(nv + npol, dev, d)
+            except Exception as exc:        # noqa: BLE001  (no peer access / IPC refused: decided together below)
+                ok, self._peer_error = 0, str(exc)
+            flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+            d.all_reduce(flag, op=d.ReduceOp.MIN)
+            if int(flag.item()) == 1:
+                self._peer = peer
+                self._gflat = peer.src
+                self._gflat.zero_()
+            elif peer is not None:
+                peer.close()
         self._pf = _FlatNet(pol, self.optimizer_policy, dev, grad=self._gflat[nv:])
         self._vf = _FlatNet(val, self.optimizer_value, dev, grad=self._gflat[:nv])
         self._pt = _Trunk(self._pf, 'action_mean')
@@ -552,7 +571,9 @@ class AgentPG(Agent):
         """one sum all-reduce of the flat [value | policy] gradient, then both optimizer steps (value first, agent_ppo.py:46-51;
         the nets share no parameters, so stepping the value net after the policy backward changes nothing)"""
         d = _dist()
-        if d is not None:
+        if self._peer is not None:
+            self._gflat.copy_(self._peer.allreduce())     # the kernel has completed before the copy: no peer reads src any more
+        elif d is not None:
             d.all_reduce(self._gflat)
         self._vf.adam(0.0)
         self._pf.adam(max_norm)
@@ -560,6 +581,12 @@ class AgentPG(Agent):
     def update_params(self, batch):
         t0 = time.time()
         self._setup()
+        if self._peer is not None:
+            # a rank that never arrived at a gradient exchange of the previous update (barrier timeout inside the kernel)
+            # leaves garbage in the sum: fail loudly instead of training on it
+            err = self._peer.error()
+            if err:
+                raise lib.EgpError('peer-memory gradient exchange: barrier %d timed out in the previous update' % err)
         states, actions, rewards, masks, exps, v_metas, horizon = self._device_batch(batch)
         xp, xv = self._inputs(states, v_metas, masks, horizon)
         # values + GAE (agent_pg.py:48-53, core/common.py:5-25)

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libegopose_b200.so')
-SOURCES = ['update_kernels.cu', 'rollout.cu', 'ozaki.cu', 'oz_mlp.cu', 'lstm.cu']
+SOURCES = ['update_kernels.cu', 'rollout.cu', 'ozaki.cu', 'oz_mlp.cu', 'lstm.cu', 'p2p.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '--shared', '-Xptxas', '-v']
 

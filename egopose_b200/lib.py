@@ -130,6 +130,14 @@ SYMBOLS = {
     'egp_lstm_pack_whh_f64': (_int, [_vp, _int, _vp, _vp, _vp]),
     'egp_lstm_seq_fwd_f64': (_int, [_vp, _vp, _int, _i64, _int, _vp, _vp, _vp, _vp, _vp]),
     'egp_lstm_seq_bwd_f64': (_int, [_vp, _vp, _vp, _vp, _int, _i64, _int, _vp, _vp, _vp]),
+    'egp_comm_handle_bytes': (_i64, []),
+    'egp_comm_create': (_int, [_int, _int, _int, _i64, _vp, _vp]),
+    'egp_comm_connect': (_int, [_vp, _vp]),
+    'egp_comm_src': (_vp, [_vp]),
+    'egp_comm_out': (_vp, [_vp]),
+    'egp_allreduce_grads_f64': (_int, [_vp, _i64, _vp]),
+    'egp_comm_error': (_int, [_vp]),
+    'egp_comm_destroy': (None, [_vp]),
     'egp_oz_mlp_step_f64': (_int, [C.POINTER(MlpNet), _vp, _i64, _i64, C.POINTER(MlpLoss), _vp, _int, _i64, _vp, _int, _vp, _i64,
                                    _vp]),
 }
@@ -821,3 +829,53 @@ def lstm_seq_bwd(dh, gates, c, off, L, B, H, wb):
           'egp_lstm_seq_bwd_f64')
     launches += 1
     return dxi
+
+
+# ---- gradient exchange over NVLink peer memory (csrc/p2p.cu) -------------------------------------
+class _DevMem:
+    """raw device pointer as a __cuda_array_interface__ object (float64 vector) so that torch can wrap it"""
+
+    def __init__(self, ptr_, n, owner):
+        self.__cuda_array_interface__ = {'shape': (int(n),), 'typestr': '<f8', 'data': (int(ptr_), False), 'version': 2}
+        self._owner = owner
+
+
+class PeerComm:
+    """One exchange block per rank, mapped by every peer of the node (include/egopose_b200.h: egp_comm_*).  ``src`` is
+    the tensor to write the local gradient into, ``allreduce()`` leaves the rank-ordered sum in ``out`` (one kernel
+    launch, no NCCL).  The IPC handles travel through ``torch.distributed`` (any backend) once, at construction."""
+
+    def __init__(self, n, device, dist):
+        import torch
+        self.lib = load()
+        self.n = int(n)
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        hb = int(self.lib.egp_comm_handle_bytes())
+        mine = C.create_string_buffer(hb)
+        h = C.c_void_p()
+        dev = torch.device(device)
+        check(self.lib.egp_comm_create(self.rank, self.world, dev.index if dev.index is not None else torch.cuda.current_device(),
+                                       self.n, C.byref(h), mine), 'egp_comm_create')
+        self.handle = h
+        blobs = [None] * self.world
+        dist.all_gather_object(blobs, bytes(mine.raw))
+        allh = C.create_string_buffer(b''.join(blobs), hb * self.world)
+        check(self.lib.egp_comm_connect(self.handle, allh), 'egp_comm_connect')
+        self.src = torch.as_tensor(_DevMem(self.lib.egp_comm_src(self.handle), self.n, self), device=dev)
+        self.out = torch.as_tensor(_DevMem(self.lib.egp_comm_out(self.handle), self.n, self), device=dev)
+
+    def allreduce(self, n=None):
+        global launches
+        check(self.lib.egp_allreduce_grads_f64(self.handle, int(n if n is not None else self.n), stream_ptr()),
+              'egp_allreduce_grads_f64')
+        launches += 1
+        return self.out
+
+    def error(self):
+        return int(self.lib.egp_comm_error(self.handle))
+
+    def close(self):
+        if getattr(self, 'handle', None):
+            self.src = self.out = None
+            self.lib.egp_comm_destroy(self.handle)
+            self.handle = None

@@ -184,7 +184,7 @@ void egp_model_destroy(EgpModel *m);
  * (timeconst, dampratio) and solimp (d0, dwidth, width, midpoint, power), NULL = MuJoCo's defaults 0.02 1 /
  * 0.9 0.95 0.001 0.5 2.  Host pointers.  range = NULL switches the limits off again (smooth dynamics: the default).
  * With limits on, roll-outs run on the one-warp-per-32-environments kernel (the block sweeps do not carry them yet);
- * evaluation roll-outs and the state LSTM are then unavailable (EGP_ESIZE).  Floor contact is not modelled. */
+ * evaluation roll-outs and the state LSTM are then unavailable (EGP_ESIZE).  Floor contact: egp_model_set_contacts. */
 int egp_model_set_joint_limits(EgpModel *m, const double *range, const double *invweight0, const double *solref,
                                const double *solimp);
 
@@ -366,6 +366,26 @@ int egp_lstm_seq_fwd_f64(const double *d_xi, const int64_t *d_off, int L, int64_
  * dW_ih = d_dxi^T X, db = column sums of d_dxi are GEMMs of the caller) */
 int egp_lstm_seq_bwd_f64(const double *d_dh, const double *d_gates, const double *d_c, const int64_t *d_off, int L, int64_t B, int H,
                          const double *d_Wf_bwd, double *d_dxi, void *stream);
+
+/* --- gradient exchange over NVLink peer memory ------------------------------------------------------
+ * The data-parallel update differentiates one global batch (agents/agent_ppo.py:44-56): rank-local gradients of the flat
+ * [value | policy] buffer are summed once per PPO epoch.  One process per GPU of a node; every rank owns an exchange block
+ * (cudaMalloc, shared through CUDA IPC): src [n] (write the local gradient here), out [n] (the sum, bit-identical on every
+ * rank: every rank adds the peers' src in rank order, reading them over NVLink).  egp_allreduce_grads_f64 is ONE kernel
+ * launch per rank and call: cross-GPU flag barrier, peer-to-peer sum, flag barrier (after completion nobody reads this
+ * rank's src any more).  All ranks must make the same sequence of calls.
+ *   egp_comm_create  : allocates the block, returns the IPC handle (egp_comm_handle_bytes() bytes) to hand to the peers
+ *   egp_comm_connect : all_handles = the world handles in rank order (exchanged by the caller, e.g. all_gather)
+ *   egp_comm_error   : 0, or which barrier timed out (a rank never arrived within ~4 s); synchronises the device */
+typedef struct EgpComm EgpComm;
+int64_t egp_comm_handle_bytes(void);
+int egp_comm_create(int rank, int world, int device, int64_t n, EgpComm **out, void *handle_out);
+int egp_comm_connect(EgpComm *c, const void *all_handles);
+double *egp_comm_src(EgpComm *c);
+double *egp_comm_out(EgpComm *c);
+int egp_allreduce_grads_f64(EgpComm *c, int64_t n, void *stream);
+int egp_comm_error(EgpComm *c);
+void egp_comm_destroy(EgpComm *c);
 
 #ifdef __cplusplus
 }

@@ -244,9 +244,11 @@ def _free_port():
 
 
 def test_two_ranks_on_one_gpu_equal_single_rank():
-    """G ranks on the global batch == 1 rank on the same batch.  Two processes share cuda:0 and exchange through
-    gloo (device tensors are staged by torch.distributed), so this runs on the 1-GPU test lease; NCCL at 2 - 8 GPUs is
-    exercised by bench.py --gpus N and tools/check_multi_gpu.py."""
+    """G ranks on the global batch == 1 rank on the same batch.  Two processes share cuda:0, so this runs on the
+    1-GPU test lease: the small collectives go through gloo (device tensors staged by torch.distributed), the per-epoch
+    gradient sum through the peer-memory kernel (csrc/p2p.cu: CUDA IPC works between processes on one device; the two
+    kernels time-slice); the same path over NVLink at 2 - 8 GPUs is exercised by bench.py --gpus N / tools/check_multi_gpu.py.
+    EGP_GRAD_EXCHANGE=nccl (torch.distributed all_reduce instead of the kernel) must give the same parameters."""
     script = os.path.join(ROOT, 'tools', 'check_multi_gpu.py')
     env = dict(os.environ, MASTER_ADDR='127.0.0.1', MASTER_PORT=str(_free_port()), EGP_CHECK_BACKEND='gloo',
                EGP_CHECK_SAME_DEVICE='1')
@@ -255,3 +257,10 @@ def test_two_ranks_on_one_gpu_equal_single_rank():
     res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert 'EQUIVALENT' in res.stdout, res.stdout[-3000:]
+    assert 'peer memory (csrc/p2p.cu), barrier status 0' in res.stdout, res.stdout[-3000:]
+    env['EGP_GRAD_EXCHANGE'] = 'nccl'
+    env['MASTER_PORT'] = str(_free_port())
+    cmd[cmd.index('--master-port') + 1] = env['MASTER_PORT']
+    res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert 'EQUIVALENT' in res.stdout and 'torch.distributed all_reduce' in res.stdout, res.stdout[-3000:]

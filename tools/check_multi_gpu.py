@@ -71,6 +71,7 @@ def main():
     batch, log = agent.sample(E // world * T, to_host=False, parity=par)
     agent.update_params(batch)
     dp_losses = agent.losses()
+    exchange = 'peer memory (csrc/p2p.cu), barrier status %d' % agent._peer.error() if agent._peer is not None else 'torch.distributed all_reduce'
     dp_params = torch.cat([p.detach().reshape(-1) for p in list(pol.parameters()) + list(val.parameters())]).clone()
     gathered = [torch.empty_like(dp_params) for _ in range(world)]
     dist.all_gather(gathered, dp_params)
@@ -91,8 +92,9 @@ def main():
         verr = float(np.abs(dp_losses['value_loss'] - l1['value_loss']).max() / np.abs(l1['value_loss']).max())
         ok = replicas_identical and perr < 1e-9 and lerr < 1e-10 and verr < 1e-10 and log.num_steps == E * T
         print('world %d: replicas bit-identical %s | params rel err vs 1-GPU %.2e | surr abs err %.2e | vloss rel err %.2e | '
-              'logger steps %d avg_c_reward %.6f vs %.6f -> %s' % (world, replicas_identical, perr, lerr, verr, log.num_steps,
-                                                                   log.avg_c_reward, log1.avg_c_reward, 'PASS EQUIVALENT' if ok else 'FAIL'))
+              'logger steps %d avg_c_reward %.6f vs %.6f | gradient exchange: %s -> %s'
+              % (world, replicas_identical, perr, lerr, verr, log.num_steps, log.avg_c_reward, log1.avg_c_reward, exchange,
+                 'PASS EQUIVALENT' if ok else 'FAIL'))
         sys.exit(0 if ok else 1)
 
 
