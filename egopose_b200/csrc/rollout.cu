@@ -130,7 +130,7 @@ struct EnvData {
     double q[MAXV + 1], v[MAXV];
     double S[MAXV][6], U[MAXV][6], Dinv[MAXV], u[MAXV];
     double C[MAXV], tau[MAXV], qacc[MAXV];
-    double dadd[MAXV];                  // joint limits: extra pivot weight of the active rows (0 otherwise)
+    double dadd[MAXV], radd[MAXV];      // joint limits: extra pivot weight / right-hand side of the active rows (0 otherwise)
     // floor contacts of the last kinematics refresh: body, spatial directions [c x d; d] (about O) of the normal and the two
     // tangents, and per pyramid edge (n + mu t1, n - mu t1, n + mu t2, n - mu t2) the weight D, aref and the active flag
     int ncon, con_body[MAXCON];
@@ -330,7 +330,8 @@ __device__ void pass_kinematics(EnvData &e) {
     }
 }
 
-// Backward articulated-body sweep.  MODE 0: bias C_i = S_i . F and factor/solve with rhs = tau - C,
+// Backward articulated-body sweep (MODE 2 / 3: with the active constraint rows, 2 re-uses the bias C, 3 computes it like 0).
+// MODE 0: bias C_i = S_i . F and factor/solve with rhs = tau - C,
 // pivots S.U + armature (forward dynamics).  MODE 1: rhs = e.tau (pre-filled), pivots + kd h (stable PD).
 template <int MODE>
 __device__ void pass_backward(EnvData &e) {
@@ -350,8 +351,8 @@ __device__ void pass_backward(EnvData &e) {
             w.IA[sx(1, 3)] += ci[3];  w.IA[sx(1, 5)] += -ci[1];
             w.IA[sx(2, 3)] += -ci[2]; w.IA[sx(2, 4)] += ci[1];
             w.IA[sx(3, 3)] += ci[0]; w.IA[sx(4, 4)] += ci[0]; w.IA[sx(5, 5)] += ci[0];
-            if (MODE == 0) for (int k = 0; k < 6; k++) w.F[k] += e.fb[b][k];
-            if (MODE == 2) {
+            if (MODE == 0 || MODE == 3) for (int k = 0; k < 6; k++) w.F[k] += e.fb[b][k];
+            if (MODE >= 2) {
                 // active contact rows of this body: D p p^T joins the articulated inertia, D aref p acts as an external force
                 for (int k = 0; k < e.ncon; k++) {
                     if (e.con_body[k] != b) continue;
@@ -373,11 +374,12 @@ __device__ void pass_backward(EnvData &e) {
 #pragma unroll
                 for (int r = 0; r < 6; r++) S[r] = e.S[i][r];
                 double rhs;
-                if (MODE == 0) {
+                if (MODE == 0 || MODE == 3) {
                     double Ci = dot6(S, w.F);
                     e.C[i] = Ci;
                     rhs = e.tau[i] - Ci;
-                } else if (MODE == 2) rhs = e.qacc[i] - e.C[i];      // limit re-solve: qacc holds tau + the rows' D s aref
+                    if (MODE == 3) rhs += e.radd[i];
+                } else if (MODE == 2) rhs = e.tau[i] + e.radd[i] - e.C[i];     // constrained re-solve: radd = the limit rows' D s aref
                 else rhs = e.tau[i];
 #pragma unroll
                 for (int r = 0; r < 6; r++) {
@@ -388,7 +390,7 @@ __device__ void pass_backward(EnvData &e) {
                 }
                 double D = dot6(S, U) + c_m.dof_arm[i];
                 if (MODE == 1) D += c_m.kd[i] * c_m.h;
-                if (MODE == 2) D += e.dadd[i];
+                if (MODE >= 2) D += e.dadd[i];
                 const double Dinv = 1.0 / D;
                 const double ui = rhs - dot6(S, w.pA);
                 e.Dinv[i] = Dinv;
@@ -481,13 +483,15 @@ __device__ void pass_accel_rows(EnvData &e, double *out) {
     }
 }
 
-// After pass_backward<0> + pass_accel gave the smooth qacc: with rows present the solver's optimum is
+// mj_forward's acceleration stage after pass_kinematics, with e.tau = actuation: bias C + qacc.  Without constraint rows
+// the plain bias / factor sweep and acceleration sweep.  With rows the solver's optimum is
 //   (M + sum_act D_i J_i^T J_i) a = tau - C + sum_act D_i aref_i J_i^T.
 // A limit row's Jacobian is a unit vector (adds D to a pivot), a contact row's is p^T J_body (adds D p p^T to that body's
 // articulated inertia and D aref p to its external force): the same articulated-body sweeps solve it in O(n).  The
-// active set {rows with J a - aref < 0} is iterated to its fixed point.  The smooth bias C and the smooth tree data
-// stay as they are (compute_torque reads them).
-__device__ void constraint_solve(EnvData &e) {
+// active set {rows with J a - aref < 0} is iterated to its fixed point, starting from all rows active; that first
+// iterate shares its backward sweep with the bias computation (MODE 3), later ones re-use the bias (MODE 2).  The
+// smooth bias C and the smooth tree data stay as they are (compute_torque reads them).
+__device__ void forward_dynamics(EnvData &e) {
     const int nv = c_m.nv;
     unsigned long long inst = 0ull, act;
     double Dc[MAXV], ar[MAXV], sg[MAXV];
@@ -505,18 +509,21 @@ __device__ void constraint_solve(EnvData &e) {
         }
     }
     const int nrow = 4 * e.ncon;
-    if (!inst && !nrow) return;
+    if (!inst && !nrow) {
+        pass_backward<0>(e);
+        pass_accel(e, e.qacc);
+        return;
+    }
     act = inst;
     for (int k = 0; k < nrow; k++) e.row_act[k] = 1;
-    double tau0[MAXV];
-    for (int i = 0; i < nv; i++) tau0[i] = e.tau[i];
     for (int it = 0; it < 100; it++) {
         for (int i = 0; i < nv; i++) {
             const bool on = (act >> i) & 1ull;
             e.dadd[i] = on ? Dc[i] : 0.0;
-            e.qacc[i] = tau0[i] + (on ? Dc[i] * sg[i] * ar[i] : 0.0);
+            e.radd[i] = on ? Dc[i] * sg[i] * ar[i] : 0.0;
         }
-        pass_backward<2>(e);
+        if (it == 0) pass_backward<3>(e);
+        else pass_backward<2>(e);
         pass_accel_rows(e, e.qacc);
         unsigned long long nact = 0ull;
         for (int i = 6; i < nv; i++)
@@ -559,9 +566,7 @@ __device__ void env_substep(EnvData &e, const double *ctrl /* per dof, [nv] */, 
     }
     // mj_step: forward at (q, v) then semi-implicit Euler
     pass_kinematics(e);
-    pass_backward<0>(e);
-    pass_accel(e, e.qacc);
-    if (c_m.limits || c_m.contacts) constraint_solve(e);
+    forward_dynamics(e);
     for (int i = 0; i < nv; i++) e.v[i] += h * e.qacc[i];
     for (int k = 0; k < 3; k++) e.q[k] += h * e.v[k];
     {
@@ -1781,9 +1786,7 @@ __global__ void forward_debug_kernel(int n, const double *qpos, const double *qv
     for (int k = 0; k < nv; k++) e.v[k] = qvel[(size_t)i * nv + k];
     pass_kinematics(e);
     for (int k = 0; k < nv; k++) e.tau[k] = (k >= 6 && ctrl) ? ctrl[(size_t)i * c_m.nu + k - 6] : 0.0;
-    pass_backward<0>(e);
-    pass_accel(e, e.qacc);
-    if (c_m.limits || c_m.contacts) constraint_solve(e);
+    forward_dynamics(e);
     for (int k = 0; k < nv; k++) { bias[(size_t)i * nv + k] = e.C[k]; qacc[(size_t)i * nv + k] = e.qacc[k]; }
     for (int b = 0; b < nb; b++) for (int r = 0; r < 3; r++) xpos[((size_t)i * nb + b) * 3 + r] = e.xp[b][r];
 }

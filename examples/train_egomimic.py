@@ -35,6 +35,12 @@ def main():
     ap.add_argument('--horizon', type=int, default=50)
     ap.add_argument('--takes', type=int, default=8)
     ap.add_argument('--save', default='')
+    ap.add_argument('--physics', choices=['smooth', 'full'], default='smooth',
+                    help='full = joint limits + floor contact (MuJoCo soft constraints, one-warp rollout kernel)')
+    ap.add_argument('--standing', action='store_true',
+                    help='expert = standing still on the floor (T-pose, soles on z = 0, random heading per take): a physically '
+                         'consistent target for --physics full, where the policy has to learn to keep the balance')
+    ap.add_argument('--policy-lr', type=float, default=0.0, help='override cfg.policy_lr')
     args = ap.parse_args()
     world, rank, local = (int(os.environ.get(k, d)) for k, d in (('WORLD_SIZE', 1), ('RANK', 0), ('LOCAL_RANK', 0)))
     torch.cuda.set_device(local)
@@ -51,8 +57,18 @@ def main():
     env = HumanoidEnv(cfg, device=local)
     env.seed(cfg.seed + 1000 * rank)
     L = args.horizon + 2 * cfg.fr_margin + 64
-    env.set_expert_qpos(['take_%d' % i for i in range(args.takes)], synthetic_takes(env.md, args.takes, L, seed=1),
-                        synthetic_cnn_feat(args.takes, L))
+    if args.physics == 'full':
+        env.kernel.set_joint_limits(True)
+        env.kernel.set_contacts(True)
+    takes = synthetic_takes(env.md, args.takes, L, seed=1)
+    if args.standing:
+        rng = np.random.RandomState(3)
+        for q in takes:
+            yaw = rng.uniform(-np.pi, np.pi)
+            q[:] = np.asarray(env.md.qpos0)
+            q[:, 2] = 0.8665                                            # soles of the foot boxes on the floor
+            q[:, 3:7] = [np.cos(yaw / 2), 0.0, 0.0, np.sin(yaw / 2)]
+    env.set_expert_qpos(['take_%d' % i for i in range(args.takes)], takes, synthetic_cnn_feat(args.takes, L))
     state_dim, action_dim = env.observation_space.shape[0], env.action_space.shape[0]
     running_state = ZFilter((state_dim,), clip=5)
     policy_vs_net, value_vs_net = FrameContext(128, cfg.policy_v_hdim, cfg.fr_margin), FrameContext(128, cfg.value_v_hdim, cfg.fr_margin)
@@ -70,6 +86,8 @@ def main():
     for i_iter in range(args.iters):
         cfg.update_adaptive_params(i_iter)                              # ego_mimic.py:93-99
         agent.set_noise_rate(cfg.adp_noise_rate)
+        if args.policy_lr > 0:
+            cfg.adp_policy_lr = args.policy_lr
         set_optimizer_lr(optimizer_policy, cfg.adp_policy_lr)
         if cfg.fix_std:
             policy_net.action_log_std.fill_(cfg.adp_log_std)
@@ -82,7 +100,7 @@ def main():
                   'surr {:+.5f}->{:+.5f}\tvloss {:.4f}->{:.4f}'.format(
                       i_iter, log.sample_time, t_update, log.avg_c_reward,
                       np.array2string(log.avg_c_info, formatter={'all': lambda v: '%.4f' % v}, separator=','),
-                      log.min_c_reward, log.max_c_reward, log.avg_episode_reward, losses['surr_loss'][0],
+                      log.min_c_reward, log.max_c_reward, log.num_steps / max(1, log.num_episodes), losses['surr_loss'][0],
                       losses['surr_loss'][-1], losses['value_loss'][0], losses['value_loss'][-1]), flush=True)
     if args.save and rank == 0:
         checkpoint.save_checkpoint(args.save, policy_net, policy_vs_net, value_net, value_vs_net, running_state)
