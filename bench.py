@@ -456,7 +456,8 @@ def main():
              'gae_kernel': {'bound': 'hbm', 'achieved': 5 * wbytes * N / (gae_ms / 1e3) / 1e9, 'peak': hbm, 'unit': 'GB/s',
                             'frac': 5 * wbytes * N / (gae_ms / 1e3) / 1e9 / hbm, 'ms': gae_ms, 'bytes_per_sample': 40,
                             'traffic': cap_of('gae', 'dram_bytes'), 'traffic_source': cap_of('gae', 'source')},
-             'gae_kernel_config5': gae_big,
+             'gae_kernel_config5': (dict(gae_big, traffic=cap_of('gae_config5', 'dram_bytes'), traffic_source=cap_of('gae_config5', 'source'))
+                                    if isinstance(gae_big, dict) and 'error' not in gae_big else gae_big),
              'update_dgemm': {'bound': 'tensor(fp64)', 'achieved': None, 'peak': fp64_peak, 'unit': 'TFLOP/s'},
              'rollout_env_substeps_per_s': N * 15 / (roll_ms / 1e3)}
     # the update's dominant kernel alone: [N, 243] x [300, 243]^T float64 product on the int8 tensor cores (first policy /
