@@ -173,3 +173,25 @@ def test_statue_stands_on_the_floor_unpinned():
         if t < 30:
             assert abs(env.d.qpos[2] - 0.8665) < 0.01
     assert steps >= 50          # without a floor: 9
+
+
+def test_active_set_iteration_converges_quickly_unpinned():
+    """300 random poses on / in the floor with violated ranges, random velocities and actuation: the fixed point of the
+    active set is reached in a handful of sweeps (the kernels cap the loop at 100)"""
+    o = cphys.Oracle(joint_limits=True, contacts=True)
+    rng = np.random.RandomState(0)
+    iters, rows = [], []
+    for _ in range(300):
+        viol = [(int(i), float(rng.choice([-1, 1]) * rng.uniform(1e-4, 0.3)))
+                for i in rng.choice(np.arange(6, o.nv), rng.randint(0, 8), replace=False)]
+        q, _v = _state(o, rng, viol)
+        quat = rng.randn(4)
+        q[3:7] = quat / np.linalg.norm(quat)
+        q[2] = 0.0
+        q[2] = -o.kinematics(q)[0][:, 2].min() + rng.uniform(-0.05, 0.1)
+        d = o.new_data(q, rng.randn(o.nv) * rng.choice([0.1, 1.0, 3.0]), 20 * rng.randn(o.nu))
+        o.forward(d)
+        iters.append(d.solver_iter)
+        rows.append(d.n_efc)
+    assert max(iters) <= 20, max(iters)
+    assert max(rows) > 30 and np.mean(rows) > 8
