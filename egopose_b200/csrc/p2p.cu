@@ -44,12 +44,14 @@ __device__ __forceinline__ unsigned long long ld_sys(const unsigned long long *p
     return v;
 }
 
+__device__ long long c_p2p_timeout = 8000000000ll;              // cycles a barrier waits for a peer: ~4 s at 2 GHz
+
 // all ranks have written `epoch` into my flags[phase]; false on timeout
 __device__ bool p2p_wait(const P2pBlock *mine, int phase, int world, unsigned long long epoch) {
     const long long t0 = clock64();
     for (int p = 0; p < world; p++) {
         while (ld_sys(&mine->flags[phase][p]) < epoch) {
-            if (clock64() - t0 > 8000000000ll) return false;       // ~4 s at 2 GHz
+            if (clock64() - t0 > c_p2p_timeout) return false;
             __nanosleep(100);
         }
     }
@@ -83,7 +85,7 @@ p2p_allreduce_kernel(P2pPeers peers, int rank, int world, long long n, unsigned 
             for (int p = 1; p < world; p++) acc += __ldcg(peers.src[p] + n - 1);
             out[n - 1] = acc;
         }
-    } else if (threadIdx.x == 0) mine->error = 1u;
+    } else if (threadIdx.x == 0) atomicOr(&mine->error, 1u);
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
@@ -91,7 +93,7 @@ p2p_allreduce_kernel(P2pPeers peers, int rank, int world, long long n, unsigned 
             mine->done = 0u;
             __threadfence_system();
             for (int p = 0; p < world; p++) st_sys(&peers.blk[p]->flags[1][rank], epoch);
-            if (!p2p_wait(mine, 1, world, epoch)) mine->error = 2u;
+            if (!p2p_wait(mine, 1, world, epoch)) atomicOr(&mine->error, 2u);
         }
     }
 }
@@ -155,6 +157,28 @@ int egp_comm_connect(EgpComm *c, const void *all_handles) {
     return EGP_OK;
 }
 
+/* Same wiring for several communicators that live in ONE process (one process driving several GPUs, or the in-process
+ * tests): CUDA IPC handles cannot be opened by the process that exported them, the raw pointers are used instead. */
+int egp_comm_connect_local(EgpComm *c, EgpComm *const *all) {
+    if (!c || !all) { set_error("egp_comm_connect_local: null argument"); return EGP_EINVAL; }
+    for (int p = 0; p < c->world; p++) {
+        if (!all[p] || all[p]->world != c->world || all[p]->rank != p || all[p]->n != c->n) {
+            set_error("egp_comm_connect_local: entry %d is not rank %d of the same exchange", p, p);
+            return EGP_EINVAL;
+        }
+        if (all[p]->device != c->device) {
+            EGP_CUDA(cudaSetDevice(c->device));
+            cudaError_t e = cudaDeviceEnablePeerAccess(all[p]->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cuda_fail(e, "cudaDeviceEnablePeerAccess");
+            cudaGetLastError();
+        }
+        c->peer_base[p] = p == c->rank ? c->base : nullptr;         // nothing to close for local peers
+        c->peers.blk[p] = (P2pBlock *)all[p]->base;
+        c->peers.src[p] = (double *)((char *)all[p]->base + sizeof(P2pBlock));
+    }
+    return EGP_OK;
+}
+
 double *egp_comm_src(EgpComm *c) { return c ? (double *)((char *)c->base + sizeof(P2pBlock)) : nullptr; }
 double *egp_comm_out(EgpComm *c) { return c ? c->out : nullptr; }
 
@@ -171,7 +195,19 @@ int egp_allreduce_grads_f64(EgpComm *c, int64_t n, void *stream) {
     return EGP_OK;
 }
 
-/* 0 = no rank timed out so far (reads the error word: synchronises the device) */
+/* barrier timeout in SM cycles (default 8e9, about 4 s); returns the previous value; cycles <= 0 only queries */
+int64_t egp_comm_set_timeout_cycles(int64_t cycles) {
+    long long old = 0;
+    if (cudaMemcpyFromSymbol(&old, c_p2p_timeout, sizeof old) != cudaSuccess) return -1;
+    if (cycles > 0) {
+        long long v = cycles;
+        if (cudaMemcpyToSymbol(c_p2p_timeout, &v, sizeof v) != cudaSuccess) return -1;
+    }
+    return old;
+}
+
+/* 0 = no rank timed out so far; bit 0: a peer's gradient never became ready, bit 1: a peer never finished reading
+ * (reads the error word: synchronises the device) */
 int egp_comm_error(EgpComm *c) {
     if (!c) return -1;
     P2pBlock b;

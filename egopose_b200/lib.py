@@ -133,6 +133,8 @@ SYMBOLS = {
     'egp_comm_handle_bytes': (_i64, []),
     'egp_comm_create': (_int, [_int, _int, _int, _i64, _vp, _vp]),
     'egp_comm_connect': (_int, [_vp, _vp]),
+    'egp_comm_connect_local': (_int, [_vp, _vp]),
+    'egp_comm_set_timeout_cycles': (_i64, [_i64]),
     'egp_comm_src': (_vp, [_vp]),
     'egp_comm_out': (_vp, [_vp]),
     'egp_allreduce_grads_f64': (_int, [_vp, _i64, _vp]),
@@ -844,6 +846,29 @@ class PeerComm:
     """One exchange block per rank, mapped by every peer of the node (include/egopose_b200.h: egp_comm_*).  ``src`` is
     the tensor to write the local gradient into, ``allreduce()`` leaves the rank-ordered sum in ``out`` (one kernel
     launch, no NCCL).  The IPC handles travel through ``torch.distributed`` (any backend) once, at construction."""
+
+    @classmethod
+    def local_group(cls, n, devices):
+        """the communicators of len(devices) ranks that all live in this process (rank r on devices[r])"""
+        import torch
+        L = load()
+        world = len(devices)
+        hb = int(L.egp_comm_handle_bytes())
+        comms = []
+        for r, dev in enumerate(devices):
+            c = cls.__new__(cls)
+            c.lib, c.n, c.rank, c.world = L, int(n), r, world
+            c.device = torch.device(dev)
+            h = C.c_void_p()
+            check(L.egp_comm_create(r, world, c.device.index or 0, c.n, C.byref(h), C.create_string_buffer(hb)), 'egp_comm_create')
+            c.handle = h
+            comms.append(c)
+        arr = (C.c_void_p * world)(*[c.handle for c in comms])
+        for c in comms:
+            check(L.egp_comm_connect_local(c.handle, arr), 'egp_comm_connect_local')
+            c.src = torch.as_tensor(_DevMem(L.egp_comm_src(c.handle), c.n, c), device=c.device)
+            c.out = torch.as_tensor(_DevMem(L.egp_comm_out(c.handle), c.n, c), device=c.device)
+        return comms
 
     def __init__(self, n, device, dist):
         import torch

@@ -376,11 +376,14 @@ int egp_lstm_seq_bwd_f64(const double *d_dh, const double *d_gates, const double
  * rank's src any more).  All ranks must make the same sequence of calls.
  *   egp_comm_create  : allocates the block, returns the IPC handle (egp_comm_handle_bytes() bytes) to hand to the peers
  *   egp_comm_connect : all_handles = the world handles in rank order (exchanged by the caller, e.g. all_gather)
- *   egp_comm_error   : 0, or which barrier timed out (a rank never arrived within ~4 s); synchronises the device */
+ *   egp_comm_error   : 0, or which barriers timed out (bit 0: a peer's gradient never became ready, bit 1: a peer never
+ *                      finished reading; a rank did not arrive within ~4 s); synchronises the device */
 typedef struct EgpComm EgpComm;
 int64_t egp_comm_handle_bytes(void);
 int egp_comm_create(int rank, int world, int device, int64_t n, EgpComm **out, void *handle_out);
 int egp_comm_connect(EgpComm *c, const void *all_handles);
+int egp_comm_connect_local(EgpComm *c, EgpComm *const *all);   /* ranks that live in this process: all = the world communicators in rank order */
+int64_t egp_comm_set_timeout_cycles(int64_t cycles);            /* barrier timeout (SM cycles, default 8e9); returns the previous value; <= 0 only queries; per device */
 double *egp_comm_src(EgpComm *c);
 double *egp_comm_out(EgpComm *c);
 int egp_allreduce_grads_f64(EgpComm *c, int64_t n, void *stream);
