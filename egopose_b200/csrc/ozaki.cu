@@ -41,6 +41,9 @@ constexpr int EPI_WARPS = 8;
 constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;   // warp 0: TMA producer, warp 1: MMA issuer, warps 2-9: epilogue
 constexpr int SMEM_LIMIT = 227 * 1024 - 2048;   // dynamic shared memory: 227 KB minus the static barriers
 constexpr int MAX_STAGES = 12;
+#ifndef OZ_WIDE_N
+#define OZ_WIDE_N 0      // 1: merge the B slices of consecutive accumulators into one wide instruction (measured: no change)
+#endif
 
 // ---------------------------------------------------------------------------------------------------------------
 // slicing
@@ -601,6 +604,27 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int k2 = 0; k2 < BK / UMMA_K; k2++) {
 #pragma unroll
                         for (int t = 0; t < S; t++) {
+#if OZ_WIDE_N
+                            // A slice t pairs with B slices u = 0 .. S-t-1 into accumulators t+u = CONSECUTIVE column blocks
+                            // of Tensor Memory, and the B slices of a stage are consecutive 8-row groups of shared memory:
+                            // up to 256 / BN of them go into ONE instruction of N = g BN columns (same products, same exact
+                            // integer sums).  21 -> 9 instructions per K step at S = 6, BN = 80.  Bit-exact, but NOT faster on
+                            // B200 (1.998 vs 1.94 ms for the [1.2M, 243] x [300, 243]^T product): the time goes with the
+                            // accumulator columns written, not with the instruction count.
+                            constexpr int G = RB == 8 ? 1 : 256 / BN;
+#pragma unroll
+                            for (int u = 0; u < S - t; u += G) {
+                                const int g = S - t - u < G ? S - t - u : G;
+                                const uint32_t td = tmem + (uint32_t)((t + u) * BN), al = sa4 + ((t * A_SLICE + k2 * UMMA_K) >> 4),
+                                               bl = sb4 + ((u * B_SLICE + k2 * UMMA_K) >> 4), acc_flag = (t > 0 || k2 > 0) ? 1u : first;
+                                const uint32_t id = idesc_i8(g * BN, RB != 8 || t == 0, RB != 8 || u == 0);
+                                const bool first_u = u == 0, last_u = u + G >= S - t;
+                                if (first_u && last_u) umma_i8<0>(td, al, bl, DESC_HI, id, acc_flag);
+                                else if (first_u) umma_i8<1>(td, al, bl, DESC_HI, id, acc_flag);
+                                else if (last_u) umma_i8<3>(td, al, bl, DESC_HI, id, acc_flag);
+                                else umma_i8<2>(td, al, bl, DESC_HI, id, acc_flag);
+                            }
+#else
 #pragma unroll
                             for (int u = 0; u < S - t; u++) {
                                 const uint32_t td = tmem + (uint32_t)((t + u) * BN), al = sa4 + ((t * A_SLICE + k2 * UMMA_K) >> 4),
@@ -612,6 +636,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 else if (u == n_u - 1) umma_i8<3>(td, al, bl, DESC_HI, id, acc_flag);
                                 else umma_i8<2>(td, al, bl, DESC_HI, id, acc_flag);
                             }
+#endif
                         }
                     }
                     umma_commit(smem_u32(&empty_bar[s]));            // frees the smem stage when these MMAs retire
