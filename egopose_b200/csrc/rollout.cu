@@ -23,6 +23,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -51,6 +52,8 @@ struct EgpModel {
     // transposed / padded policy weights (scratch owned by the model)
     double *d_wbuf;
     size_t wbuf_elems;
+    double *d_cons;             // constraint scratch of the block-sweep kernel (joint limits / floor contact)
+    size_t cons_elems;
 };
 
 namespace egp {
@@ -727,6 +730,7 @@ struct RolloutArgs {
     int chunk23;            // T4: 1 = chunked layer-2/3 path for wide policies
     int xrows, hrows, xs;   // T4: rows of the activation buffers xs / h1s and their row stride in doubles
     double *log_part;       // [CTAs][EGP_LOG_SIZE] per-CTA logger partials (merged by logger_merge_kernel)
+    double *cons;           // T4 with joint limits / floor contact: [CTAs][CS_PER_BODY * nbody][32] constraint scratch
     // value net of the 'valuefs' evaluation rule (same plan as the policy, head padded to vAp rows), its context table
     const double *vW1t, *vb1, *vW2t, *vb2, *vW3t, *vb3, *vctx;
     int vAp;
@@ -1077,6 +1081,7 @@ template <> struct TmLd<32> {
 extern __shared__ double t4_smem[];          // the CTA's dynamic shared memory (named here so that non-inlined sweeps
                                              // address it as shared memory, not through a generic pointer)
 struct T4Ctx {
+    static constexpr bool CONS = false;
     int lane, w;
     uint32_t tm;        // TMEM base of this warp's lane quarter
     T4Off o;
@@ -1103,13 +1108,24 @@ struct T4Ctx {
     __device__ __forceinline__ void twait_st() const { tm_wait_st(); }
 };
 
+// the same context with the constraint rows of joint limits / floor contact (csrc/tree.cuh, cons_*): scratch in L2-resident
+// global memory ([slot][lane] per CTA) + the per-thread state of the active-set iteration
+struct T4CtxC : T4Ctx {
+    static constexpr bool CONS = true;
+    double *csb;
+    mutable unsigned ccnt, lim_inst, lim_act;
+    mutable int cchg;
+    int cit;
+    __device__ __forceinline__ double &cs(int slot) const { return csb[(size_t)slot * 32 + lane]; }
+};
+
 // barrier of the four chain warps (the helper warps never enter the sweeps)
 __device__ __forceinline__ void t4_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // level-synchronous tree sweeps (root | spine, legs | arms, head): one chain per warp and level, junction records
 // cross warps through shared memory (csrc/tree.cuh holds the per-chain work)
-template <int MODE>
-__device__ __forceinline__ void t4_forward(const T4Ctx &x) {
+template <int MODE, class X>
+__device__ __forceinline__ void t4_forward(const X &x) {
 #pragma unroll 1
     for (int L = 0; L < c_m.nlevel; L++) {
         const int c = c_m.lvl_chain[L][x.w];
@@ -1120,7 +1136,8 @@ __device__ __forceinline__ void t4_forward(const T4Ctx &x) {
     }
 }
 
-__device__ __forceinline__ void t4_backward(const T4Ctx &x, const int MODE) {
+template <class X>
+__device__ __forceinline__ void t4_backward(const X &x, const int MODE) {
 #pragma unroll 1
     for (int L = c_m.nlevel - 1; L >= 0; L--) {
         const int c = c_m.lvl_chain[L][x.w];
@@ -1139,7 +1156,10 @@ __device__ __forceinline__ void t4_backward(const T4Ctx &x, const int MODE) {
             for (int b = c_m.chain_lo[_c]; b <= c_m.chain_hi[_c]; b++)                               \
                 for (int i = c_m.body_dofadr[b]; i < c_m.body_dofadr[b] + c_m.body_dofnum[b]; i++)
 
-__device__ __noinline__ void t4_forward_only(const T4Ctx x) {      // sim.forward(); chain warps only; own register allocation
+template <class X>
+__device__ __noinline__ void t4_forward_only(const X x0) {     // sim.forward(); chain warps only; own register allocation
+    X x = x0;
+    if constexpr (X::CONS) { x.ccnt = 0u; x.lim_act = 0u; x.cit = 1; }      // no constraint rows: only the tree data and the bias are used
     t4_forward<2>(x);
     T4_FOR_OWN_DOFS(i, b) if (i >= 6) tm_st1(x.a_tau(i), 0.0);
     tm_wait_st();
@@ -1150,7 +1170,8 @@ __device__ __noinline__ void t4_forward_only(const T4Ctx x) {      // sim.forwar
 #ifdef EGP_T4_CLK
 __device__ unsigned long long g_t4_clk[8];      // build with -DEGP_T4_CLK: cycles of warp 0 of CTA 0 per sweep kind
 #endif
-__device__ __forceinline__ void t4_substep(const T4Ctx &x) {
+template <class X>
+__device__ __forceinline__ void t4_substep(const X &x) {
 #ifdef EGP_T4_CLK
     const bool pr = blockIdx.x == 0 && x.w == 0 && x.lane == 0;
     long long t0 = clock64();
@@ -1160,12 +1181,41 @@ __device__ __forceinline__ void t4_substep(const T4Ctx &x) {
 #endif
     t4_backward(x, 1);          // (M_stale + Kd h) factor + reduce, rhs from the current q, v
     T4_CLK(0)
+    if constexpr (X::CONS) x.ccnt = 0u;
     t4_forward<1>(x);           // desired accel -> clipped torque ; kinematics / velocities / body forces at (q, v)
     T4_CLK(1)
-    t4_backward(x, 0);          // bias C, M factor + reduce with rhs = torque - C
-    T4_CLK(2)
-    t4_forward<0>(x);           // qacc, semi-implicit Euler
-    T4_CLK(3)
+    if constexpr (X::CONS) {
+        // mj_step with constraint rows: the kinematics pass above has collected the floor contacts; the
+        // factor / solve sweeps carry the active rows (pivots, articulated inertias, bias forces), the solve-only forward
+        // sweep re-evaluates them, and the pair is repeated until the active set of every environment of the CTA is at its
+        // fixed point (first pass: every row active; bias C and factor share that pass); then the Euler step.
+        X &xm = const_cast<X &>(x);
+        x.lim_inst = 0u; x.lim_act = 0u;
+#pragma unroll 1
+        for (xm.cit = 0; xm.cit < 100; xm.cit++) {
+            x.cchg = 0;
+            t4_backward(x, 0);
+            t4_forward<3>(x);
+            const bool any = __any_sync(0xffffffffu, x.cchg != 0);
+            if (x.lane == 0) t4_smem[(x.o.red + x.w) * 32] = any ? 1.0 : 0.0;
+            t4_bar();
+            const double tot = t4_smem[x.o.red * 32] + t4_smem[(x.o.red + 1) * 32] + t4_smem[(x.o.red + 2) * 32] + t4_smem[(x.o.red + 3) * 32];
+            if (tot == 0.0) break;
+        }
+        T4_CLK(2)
+#pragma unroll 1
+        for (int L = 0; L < c_m.nlevel; L++) {
+            const int c = c_m.lvl_chain[L][x.w];
+            if (c >= 0) t5_integrate_chain(x, c);
+        }
+        t4_bar();
+        T4_CLK(3)
+    } else {
+        t4_backward(x, 0);          // bias C, M factor + reduce with rhs = torque - C
+        T4_CLK(2)
+        t4_forward<0>(x);           // qacc, semi-implicit Euler
+        T4_CLK(3)
+    }
 #ifdef EGP_T4_CLK
     if (pr) g_t4_clk[4] += 1;
 #endif
@@ -1174,7 +1224,8 @@ __device__ __forceinline__ void t4_substep(const T4Ctx &x) {
 // do_simulation (humanoid_v1.py:158-177): all sub-steps of one env step.  NOT inlined into the kernel: the sweeps get a
 // register allocation of their own (the kernel's per-step state - filtered observation shares, logger sums - is
 // saved / restored once per env step at the call, not carried through every sweep)
-__device__ __forceinline__ void t4_do_simulation(const T4Ctx &x, const int n_sub) {
+template <class X>
+__device__ __forceinline__ void t4_do_simulation(const X &x, const int n_sub) {
 #pragma unroll 1
     for (int s = 0; s < n_sub; s++) t4_substep(x);
 }
@@ -1226,12 +1277,16 @@ __device__ __forceinline__ void t4_policy_forward(const RolloutArgs &A, double *
     __syncthreads();
 }
 
-template <bool CHUNK, bool SNET, bool VALFS = false>
+template <bool CHUNK, bool SNET, bool VALFS = false, bool CONS = false>
 __global__ void __launch_bounds__(T4_THREADS, 1)
 rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
     extern __shared__ double smem[];
-    T4Ctx x;
+    typename std::conditional<CONS, T4CtxC, T4Ctx>::type x;
     x.lane = threadIdx.x & 31; x.w = threadIdx.x >> 5; x.o = O;
+    if constexpr (CONS) {
+        x.csb = A.cons + (size_t)blockIdx.x * CS_PER_BODY * c_m.nbody * 32;
+        x.ccnt = 0u; x.lim_inst = 0u; x.lim_act = 0u; x.cchg = 0; x.cit = 0;
+    }
     const int lane = x.lane, w = x.w;
     // allocate the whole Tensor Memory of this SM (1 CTA per SM) as scratch; base address comes back via smem
     __shared__ uint32_t s_tmem_base;
@@ -1983,7 +2038,7 @@ void egp_model_destroy(EgpModel *m) {
     if (!m) return;
     cudaSetDevice(m->device);
     if (m->device >= 0 && m->device < 64 && g_bound_model[m->device] == m) g_bound_model[m->device] = nullptr;
-    cudaFree(m->d_take_off); cudaFree(m->d_rows); cudaFree(m->d_head_lb); cudaFree(m->d_ctx); cudaFree(m->d_wbuf);
+    cudaFree(m->d_take_off); cudaFree(m->d_rows); cudaFree(m->d_head_lb); cudaFree(m->d_ctx); cudaFree(m->d_wbuf); cudaFree(m->d_cons);
     delete m;
 }
 
@@ -2118,7 +2173,7 @@ int egp_rollout_f64(EgpModel *m, const EgpPolicyWeights *pol, const EgpRolloutCf
     const char *force = getenv("EGP_ROLLOUT_VARIANT");
     bool use_t4 = false;
     A.chunk23 = 0;
-    if (d.t4_ok && !d.limits && !d.contacts && !(force && force[0] == '1') && 2 * (pad16(A.A) / MLP_NT) <= T4_WARPS) {      // joint limits / contacts: V1 sweeps only (so far)
+    if (d.t4_ok && !(force && force[0] == '1') && 2 * (pad16(A.A) / MLP_NT) <= T4_WARPS) {
         const int H1p = pad16(A.H1), H2p = pad16(A.H2), Ap = pad16(A.A), Dp = pad16(A.D);
         for (int pi = 0; pi < 4 && !use_t4; pi++) {        // (stride 36 | 32) x (full | chunked layer 2/3)
             const int ch = pi & 1, xs_stride = pi < 2 ? XS_WIDE : 32;
@@ -2134,6 +2189,14 @@ int egp_rollout_f64(EgpModel *m, const EgpPolicyWeights *pol, const EgpRolloutCf
                 if (O.total - O.ax < need_rows) O.total = O.ax + need_rows;
             }
         }
+    }
+    // joint limits / floor contact: the block sweeps carry the rows (kernel instantiation CONS) for the plain policy plan; the
+    // state LSTM, the value rule and the chunked wide-policy plan fall back to the one-warp kernel (EGP_CONS_VARIANT=1 forces it)
+    bool cons = false;
+    if (d.limits || d.contacts) {
+        const char *cforce = getenv("EGP_CONS_VARIANT");
+        if (use_t4 && !snH && !(in && in->value_net) && !A.chunk23 && !(cforce && cforce[0] == '1')) cons = true;
+        else { use_t4 = false; A.chunk23 = 0; }
     }
     auto pad = [use_t4](int x) { return use_t4 ? (x + 15) / 16 * 16 : (x + JB - 1) / JB * JB; };
     A.H1p = pad(A.H1); A.H2p = pad(A.H2); A.Ap = pad(A.A);
@@ -2221,7 +2284,18 @@ int egp_rollout_f64(EgpModel *m, const EgpPolicyWeights *pol, const EgpRolloutCf
             EGP_CHECK_LAUNCH("rollout_kernel_t4");
             return EGP_OK;
         };
-        if (snH) {
+        if (cons) {
+            // joint limits / floor contact: the block sweeps with constraint rows (plain policy plan only)
+            const size_t need = (size_t)blocks * CS_PER_BODY * d.nbody * 32;
+            if (m->cons_elems < need) {
+                cudaFree(m->d_cons);
+                m->d_cons = nullptr; m->cons_elems = 0;
+                EGP_CUDA(cudaMalloc(&m->d_cons, need * sizeof(double)));
+                m->cons_elems = need;
+            }
+            A.cons = m->d_cons;
+            rc2 = launch(rollout_kernel_t4<false, false, false, true>);
+        } else if (snH) {
             if (A.chunk23) { set_error("egp_rollout_f64: state LSTM with the chunked wide-policy plan is not supported"); return EGP_ESIZE; }
             rc2 = launch(rollout_kernel_t4<false, true>);
         } else if (vn) rc2 = launch(rollout_kernel_t4<false, false, true>);

@@ -290,6 +290,177 @@ EGP_HD void add_body_inertia(Bwd &w, const double *ci) {
 #endif
 constexpr int R_FB = 0, R_CIN = 12, R_CTRL = 32, R_C = 38, R_TAU = 44, R_Y = 50, R_ROOT_C = 32, R_ROOT_Y = 44, R_COLS = 56;
 
+// ---- constraint rows in the block sweeps (contexts with X::CONS) -----------------------------
+// A context with CONS = true adds:  double &cs(int slot)  this environment's constraint scratch (L2-resident global memory,
+// [slot][lane] per CTA), and the per-thread state  ccnt (3 bits per body slot: floor contacts of that body), lim_inst / lim_act
+// (1 bit per (body slot, joint): range violated / row active), cchg (the active set changed in this pass), cit (active-set
+// iteration).  Scratch record of body b at slot CS_PER_BODY * b:  flags (as a double: bit 4 k + e = edge e of contact k active) |
+// per contact: point c (relative to O) 3, weight D, aref of the four pyramid edges.
+constexpr int CS_PER_BODY = 33;
+
+// one row at signed distance dist (already minus its margin) and row velocity vel -> weight D = 1/R, reference acceleration
+EGP_HD void cons_row(double invweight, double dist, double vel, double &Dc, double &aref) {
+    const DevModel &M = EGP_CONST_M;
+    double imp;
+    if (M.lim_d0 == M.lim_dw || M.lim_width <= 1e-15) imp = 0.5 * (M.lim_d0 + M.lim_dw);
+    else {
+        const double xx = fabs(dist) / M.lim_width, pw = M.lim_pow, mid = M.lim_mid;
+        double y;
+        if (xx >= 1.0) y = 1.0;
+        else if (xx <= 0.0) y = 0.0;
+        else if (pw == 1.0) y = xx;
+        else if (xx <= mid) y = pow(xx, pw) / pow(mid, pw - 1.0);
+        else y = 1.0 - pow(1.0 - xx, pw) / pow(1.0 - mid, pw - 1.0);
+        imp = M.lim_d0 + y * (M.lim_dw - M.lim_d0);
+    }
+    double R = (1.0 - imp) / imp * invweight;
+    if (R < 1e-15) R = 1e-15;
+    Dc = 1.0 / R;
+    aref = -M.lim_b * vel - M.lim_k * imp * dist;
+}
+
+// range row of dof i at position q, velocity v: instantiated?, side s, weight, aref
+EGP_HD bool cons_limit(int i, double q, double v, double &s, double &Dc, double &aref) {
+    const DevModel &M = EGP_CONST_M;
+    const double lo = M.lim_lo[i], hi = M.lim_hi[i];
+    if (!M.limits || !(lo < hi)) return false;
+    double dist;
+    if (q - lo < 0.0) { dist = q - lo; s = 1.0; }
+    else if (hi - q < 0.0) { dist = hi - q; s = -1.0; }
+    else return false;
+    cons_row(M.lim_iw[i], dist, s * v, Dc, aref);
+    return true;
+}
+
+// spatial directions [c x d; d] of the contact normal (0,0,1) and the tangents (0,1,0), (-1,0,0) at point c
+EGP_HD void cons_dirs(const double *c, double *pn, double *p1, double *p2) {
+    pn[0] = c[1]; pn[1] = -c[0]; pn[2] = 0.0; pn[3] = 0.0; pn[4] = 0.0; pn[5] = 1.0;
+    p1[0] = -c[2]; p1[1] = 0.0; p1[2] = c[0]; p1[3] = 0.0; p1[4] = 1.0; p1[5] = 0.0;
+    p2[0] = 0.0; p2[1] = -c[2]; p2[2] = c[1]; p2[3] = -1.0; p2[4] = 0.0; p2[5] = 0.0;
+}
+
+// one contact of body b at point c (relative to O), distance dist: record k of the body's scratch, all four edges
+template <class X>
+EGP_HD void cons_emit(const X &x, const Fwd &f, int b, int k, const double *c, double dist) {
+    const DevModel &M = EGP_CONST_M;
+    const double mu = M.con_mu, tran = M.body_iw[b];
+    double pn[6], p1[6], p2[6];
+    cons_dirs(c, pn, p1, p2);
+    const double vn = dot6(pn, f.v), v1 = dot6(p1, f.v), v2 = dot6(p2, f.v);
+    const int r0 = CS_PER_BODY * b + 1 + 8 * k;
+    x.cs(r0) = c[0]; x.cs(r0 + 1) = c[1]; x.cs(r0 + 2) = c[2];
+    double D0 = 0.0;
+#pragma unroll
+    for (int ed = 0; ed < 4; ed++) {
+        double ar;
+        cons_row(tran + mu * mu * tran, dist - M.con_margin, vn + ((ed & 1) ? -mu : mu) * (ed < 2 ? v1 : v2), D0, ar);
+        x.cs(r0 + 4 + ed) = ar;
+    }
+    x.cs(r0 + 3) = D0 / (2.0 * mu * mu);
+}
+
+// kinematics pass: body b's geom against the floor plane z = 0 (mjc_PlaneSphere / PlaneCapsule / PlaneBox) -> scratch record,
+// all edges active
+template <class X>
+EGP_HD void cons_collide(const X &x, const Fwd &f, int b) {
+    const DevModel &M = EGP_CONST_M;
+    const int slot = M.body_slot[b];
+    int cnt = 0;
+    if (M.contacts) {
+        const double margin = M.con_margin, zO = x.at(x.o.q, 2);
+        const double *sz = M.geom_size[b];
+        double c0[3];
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+            c0[r] = f.p[r] + f.R[3 * r] * M.geom_p0[b][0] + f.R[3 * r + 1] * M.geom_p0[b][1] + f.R[3 * r + 2] * M.geom_p0[b][2];
+        if (M.geom_type[b] == 2) {
+            for (int vtx = 0; vtx < 8 && cnt < 4; vtx++) {
+                const double l0 = (vtx & 1) ? sz[0] : -sz[0], l1 = (vtx & 2) ? sz[1] : -sz[1], l2 = (vtx & 4) ? sz[2] : -sz[2];
+                double wv[3];
+#pragma unroll
+                for (int r = 0; r < 3; r++) wv[r] = c0[r] + f.R[3 * r] * l0 + f.R[3 * r + 1] * l1 + f.R[3 * r + 2] * l2;
+                const double dist = wv[2] + zO;
+                if (dist > margin) continue;
+                wv[2] -= 0.5 * dist;
+                cons_emit(x, f, b, cnt, wv, dist);
+                cnt++;
+            }
+        } else {
+            const int ne = M.geom_type[b] == 1 ? 2 : 1;
+            for (int en = 0; en < ne; en++) {
+                double cc[3];
+                if (ne == 2 && en == 0) {
+#pragma unroll
+                    for (int r = 0; r < 3; r++)
+                        cc[r] = f.p[r] + f.R[3 * r] * M.geom_p1[b][0] + f.R[3 * r + 1] * M.geom_p1[b][1] + f.R[3 * r + 2] * M.geom_p1[b][2];
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 3; r++) cc[r] = c0[r];
+                }
+                const double dist = cc[2] + zO - sz[0];
+                if (dist >= margin) continue;
+                cc[2] -= sz[0] + 0.5 * dist;
+                cons_emit(x, f, b, cnt, cc, dist);
+                cnt++;
+            }
+        }
+        if (cnt) x.cs(CS_PER_BODY * b) = (double)((1 << (4 * cnt)) - 1);
+    }
+    x.ccnt = (x.ccnt & ~(7u << (3 * slot))) | ((unsigned)cnt << (3 * slot));
+}
+
+// backward sweep: the active contact rows of body b join its articulated inertia (D p p^T) and its bias force (- D aref p)
+template <class X>
+EGP_HD void cons_bwd_contacts(const X &x, Bwd &w, int b) {
+    const int slot = EGP_CONST_M.body_slot[b], cnt = (x.ccnt >> (3 * slot)) & 7u, base = CS_PER_BODY * b;
+    if (!cnt) return;
+    const unsigned flags = (unsigned)x.cs(base);
+    const double mu = EGP_CONST_M.con_mu;
+    for (int k = 0; k < cnt; k++) {
+        const unsigned eb = (flags >> (4 * k)) & 15u;
+        if (!eb) continue;
+        const int r0 = base + 1 + 8 * k;
+        const double c[3] = {x.cs(r0), x.cs(r0 + 1), x.cs(r0 + 2)}, D = x.cs(r0 + 3);
+        double pn[6], p1[6], p2[6];
+        cons_dirs(c, pn, p1, p2);
+#pragma unroll
+        for (int ed = 0; ed < 4; ed++) {
+            if (!((eb >> ed) & 1u)) continue;
+            const double sg = (ed & 1) ? -mu : mu, fa = D * x.cs(r0 + 4 + ed);
+            double p[6];
+#pragma unroll
+            for (int r = 0; r < 6; r++) p[r] = pn[r] + sg * (ed < 2 ? p1[r] : p2[r]);
+#pragma unroll
+            for (int r = 0; r < 6; r++) {
+#pragma unroll
+                for (int cc = r; cc < 6; cc++) w.IA[sx(r, cc)] += D * p[r] * p[cc];
+                w.pA[r] -= fa * p[r];
+            }
+        }
+    }
+}
+
+// forward (solve-only) sweep: re-evaluate the contact rows of body b at its acceleration a = J_body qacc
+template <class X>
+EGP_HD void cons_fwd_contacts(const X &x, const double *a, int b) {
+    const int slot = EGP_CONST_M.body_slot[b], cnt = (x.ccnt >> (3 * slot)) & 7u, base = CS_PER_BODY * b;
+    if (!cnt) return;
+    const unsigned flags = (unsigned)x.cs(base);
+    const double mu = EGP_CONST_M.con_mu;
+    unsigned nf = 0;
+    for (int k = 0; k < cnt; k++) {
+        const int r0 = base + 1 + 8 * k;
+        const double c[3] = {x.cs(r0), x.cs(r0 + 1), x.cs(r0 + 2)};
+        double pn[6], p1[6], p2[6];
+        cons_dirs(c, pn, p1, p2);
+        const double an = dot6(pn, a), a1 = dot6(p1, a), a2 = dot6(p2, a);
+#pragma unroll
+        for (int ed = 0; ed < 4; ed++)
+            if (an + ((ed & 1) ? -mu : mu) * (ed < 2 ? a1 : a2) - x.cs(r0 + 4 + ed) < 0.0) nf |= 1u << (4 * k + ed);
+    }
+    if (nf != flags) { x.cs(base) = (double)nf; x.cchg = 1; }
+}
+
 template <class X>
 EGP_HD void t5_bwd_gather(const X &x, int c, Bwd &w) {
 #pragma unroll
@@ -360,6 +531,7 @@ EGP_HD void t5_bwd_body(const X &x, Bwd &w, BwdIn &in, const int MODE, const int
         for (int k = 0; k < 10; k++) ci[k] = X::unpack(in.tm, k);
     }
     add_body_inertia(w, ci);
+    if constexpr (X::CONS) { if (MODE == 0) cons_bwd_contacts(x, w, in.b); }
 #pragma unroll
     for (int j = 0; j < ND; j++) {
         S[j][0] = in.ax[j][0]; S[j][1] = in.ax[j][1]; S[j][2] = in.ax[j][2];
@@ -371,6 +543,18 @@ EGP_HD void t5_bwd_body(const X &x, Bwd &w, BwdIn &in, const int MODE, const int
 #pragma unroll
         for (int j = 0; j < ND; j++) { C[j] = dot6(S[j], w.F); rhs[j] = X::unpack(in.tmt, j) - C[j]; }
         x.template tst<ND>(rec + R_C, C);
+        if constexpr (X::CONS) {
+            // range rows of this body's joints: a violated range adds its weight to the pivot and D s aref to the right-hand side
+            const int slot = EGP_CONST_M.body_slot[in.b];
+#pragma unroll
+            for (int j = 0; j < ND; j++) {
+                const unsigned bit = 1u << (3 * slot + j);
+                double sgn, Dc, ar;
+                if (!cons_limit(da + j, x.at(x.o.q, da + j + 1), x.at(x.o.v, da + j), sgn, Dc, ar)) continue;
+                if (x.cit == 0) { x.lim_inst |= bit; x.lim_act |= bit; }
+                if (x.lim_act & bit) { diag[j] += Dc; rhs[j] += Dc * sgn * ar; }
+            }
+        }
     } else {
 #pragma unroll
         for (int j = 0; j < ND; j++) rhs[j] = in.kp[j] * X::unpack(in.tm, 10 + j) - in.g[j] - X::unpack(in.tm, 13 + j);
@@ -404,6 +588,7 @@ EGP_HD void t5_bwd_root(const X &x, Bwd &w, int b, const int MODE) {
 #pragma unroll
     for (int k = 0; k < 10; k++) ci[k] = X::unpack(tm, 6 + k);
     add_body_inertia(w, ci);
+    if constexpr (X::CONS) { if (MODE == 0) cons_bwd_contacts(x, w, b); }
     if (MODE == 0) {
 #pragma unroll
         for (int k = 0; k < 6; k++) w.F[k] += X::unpack(tm, k);
@@ -480,7 +665,7 @@ template <int MODE, class X>
 EGP_HD void t5_fwd_load(const X &x, int b, FwdIn<MODE> &in) {
     const BodyK &K = EGP_CONST_M.bk[b];
     in.b = b; in.da = K.da; in.qa = K.qa; in.nd = K.nd; in.kind = K.kind; in.rec = K.rec; in.xp_slot = K.xp_slot;
-    if (MODE != 2) x.template tld_issue<8>(K.rec + R_Y - 2, in.tmy);         // tau[2] | y
+    if (MODE != 2) x.template tld_issue<8>(K.rec + R_Y - 2, in.tmy);         // tau[2] | y      (MODE 3: solve only, like 0 without Euler)
     if (MODE == 1) x.template tld_issue<8>(K.rec + R_CTRL, in.tmc);          // ctrl | C[0]
     if (MODE != 2) {
 #pragma unroll
@@ -498,7 +683,7 @@ EGP_HD void t5_fwd_load(const X &x, int b, FwdIn<MODE> &in) {
         }
         in.v[j] = x.at(x.o.v, i);
         in.q[j] = x.at(x.o.q, K.qa + jj);
-        if (MODE != 0) {            // through temporaries: handing sincos() addresses of `in` members forces the whole record into local memory
+        if (MODE == 1 || MODE == 2) {            // through temporaries: handing sincos() addresses of `in` members forces the whole record into local memory
             double sn_j, cs_j;
             sincos(in.q[j], &sn_j, &cs_j);
             in.sn[j] = sn_j; in.cs[j] = cs_j;
@@ -541,6 +726,22 @@ EGP_HD void t5_fwd_solve_body(const X &x, double *a, const FwdIn<MODE> &in) {
             tq[j] = t < -lim ? -lim : (t > lim ? lim : t);
         }
         x.template tst<ND>(in.rec + R_TAU, tq);
+    } else if (MODE == 3) {
+        // constrained solve: keep qacc in the record's y slot (this body has consumed y), re-evaluate the rows of this body
+        x.template tst<ND>(in.rec + R_Y, xs);
+        if constexpr (X::CONS) {
+            const int slot = EGP_CONST_M.body_slot[in.b];
+#pragma unroll
+            for (int j = 0; j < ND; j++) {
+                const unsigned bit = 1u << (3 * slot + j);
+                if (!(x.lim_inst & bit)) continue;
+                double sgn, Dc, ar;
+                cons_limit(in.da + j, in.q[j], in.v[j], sgn, Dc, ar);
+                const bool on = sgn * xs[j] - ar < 0.0;
+                if (on != ((x.lim_act & bit) != 0)) { x.lim_act ^= bit; x.cchg = 1; }
+            }
+            cons_fwd_contacts(x, a, in.b);
+        }
     } else {
 #pragma unroll
         for (int j = 0; j < ND; j++) {
@@ -579,6 +780,10 @@ EGP_HD void t5_fwd_solve_root(const X &x, double *a, int b) {
     for (int j = 0; j < 3; j++) xs[3 + j] = y[3 + j] - dot6(W[3 + j], a);
 #pragma unroll
     for (int j = 0; j < 3; j++) { a[0] += R3[j][0] * xs[3 + j]; a[1] += R3[j][1] * xs[3 + j]; a[2] += R3[j][2] * xs[3 + j]; }
+    if (MODE == 3) {
+        x.template tst<6>(K.rec + R_ROOT_Y, xs);
+        if constexpr (X::CONS) cons_fwd_contacts(x, a, b);
+    }
     if (MODE == 0) {
         // semi-implicit Euler; root position + quaternion integration with the NEW velocity
         double vn[6];
@@ -746,7 +951,8 @@ EGP_HD void t5_fwd_chain(const X &x, int c) {
 #pragma unroll
         for (int k = 0; k < 6; k++) a[k] = pc >= 0 ? x.at(x.o.ja + 6 * M.chain_pslot[pc], k) : 0.0;
     }
-    if (MODE != 0 && pc >= 0) {
+    constexpr bool KIN = MODE == 1 || MODE == 2;      // kinematics refresh; 0 / 1 / 3 solve
+    if (KIN && pc >= 0) {
         const int base = x.o.jf + 24 * M.chain_pslot[pc];
 #pragma unroll
         for (int k = 0; k < 3; k++) f.p[k] = x.at(base, k);
@@ -761,9 +967,10 @@ EGP_HD void t5_fwd_chain(const X &x, int c) {
     if (MODE == 0) { EGP_CLK_MARK(8) }
     if (has_root) {
         if (MODE != 2) t5_fwd_solve_root<MODE>(x, a, lo);
-        if (MODE != 0) {
+        if (KIN) {
             t5_fwd_kin_root(x, f, lo);
             t5_body_finish(x, f, lo, M.bk[lo].rec, M.bk[lo].xp_slot);
+            if constexpr (X::CONS) { if (MODE == 1) cons_collide(x, f, lo); }
         }
     }
     if (MODE == 0) { EGP_CLK_MARK(9) }
@@ -805,12 +1012,13 @@ EGP_HD void t5_fwd_chain(const X &x, int c) {
             // this body's solve operands are dead: request the next body's while the kinematics / body-force arithmetic runs
             if (PF && b < hi) t5_fwd_load<MODE>(x, b + 1, in);
         }
-        if (MODE != 0) {
+        if (KIN) {
             if (kind == BK_XYZ) t5_fwd_kin_body<3, 0>(x, f, kin);
             else if (kind == BK_X) t5_fwd_kin_body<1, 0>(x, f, kin);
             else if (kind == BK_Y) t5_fwd_kin_body<1, 1>(x, f, kin);
             else t5_fwd_kin_body<1, 2>(x, f, kin);
             t5_body_finish(x, f, kin.b, kin.rec, kin.xp_slot);
+            if constexpr (X::CONS) { if (MODE == 1) cons_collide(x, f, kin.b); }
         }
     }
     if (MODE == 0) { EGP_CLK_MARK(10) }
@@ -820,7 +1028,7 @@ EGP_HD void t5_fwd_chain(const X &x, int c) {
 #pragma unroll
             for (int k = 0; k < 6; k++) x.at(x.o.ja + 6 * M.chain_pslot[c], k) = a[k];
         }
-        if (MODE != 0) {
+        if (KIN) {
             const int base = x.o.jf + 24 * M.chain_pslot[c];
 #pragma unroll
             for (int k = 0; k < 3; k++) x.at(base, k) = f.p[k];
@@ -828,6 +1036,50 @@ EGP_HD void t5_fwd_chain(const X &x, int c) {
             for (int k = 0; k < 9; k++) x.at(base, 3 + k) = f.R[k];
 #pragma unroll
             for (int k = 0; k < 6; k++) { x.at(base, 12 + k) = f.v[k]; x.at(base, 18 + k) = f.a[k]; }
+        }
+    }
+}
+
+// semi-implicit Euler of one chain from the accelerations a solve-only forward sweep (MODE 3) left in the y slots
+template <class X>
+EGP_HD void t5_integrate_chain(const X &x, int c) {
+    const DevModel &M = EGP_CONST_M;
+    const double h = M.h;
+    for (int b = M.chain_lo[c]; b <= M.chain_hi[c]; b++) {
+        const BodyK &K = M.bk[b];
+        if (K.kind == BK_ROOT) {
+            const int da = K.da, qa = K.qa;
+            int tmy[16];
+            x.template tld_issue<16>(K.rec + R_ROOT_Y - 4, tmy);
+            x.template tld_wait<16>(tmy);
+            double vn[6];
+#pragma unroll
+            for (int j = 0; j < 6; j++) { vn[j] = x.at(x.o.v, da + j) + h * X::unpack(tmy, 2 + j); x.at(x.o.v, da + j) = vn[j]; }
+#pragma unroll
+            for (int k = 0; k < 3; k++) x.at(x.o.q, qa + k) += h * vn[k];
+            const double *wv = vn + 3;
+            double n = sqrt(dot3(wv, wv)), ax[3] = {1.0, 0.0, 0.0};
+            if (n > 1e-15) { ax[0] = wv[0] / n; ax[1] = wv[1] / n; ax[2] = wv[2] / n; }
+            double sn, cs;
+            sincos(0.5 * h * n, &sn, &cs);
+            double qr[4] = {cs, ax[0] * sn, ax[1] * sn, ax[2] * sn};
+            double q4[4] = {x.at(x.o.q, qa + 3), x.at(x.o.q, qa + 4), x.at(x.o.q, qa + 5), x.at(x.o.q, qa + 6)};
+            double qn = sqrt(q4[0] * q4[0] + q4[1] * q4[1] + q4[2] * q4[2] + q4[3] * q4[3]);
+#pragma unroll
+            for (int k = 0; k < 4; k++) q4[k] /= qn;
+            double o4[4];
+            quat_mul(q4, qr, o4);
+#pragma unroll
+            for (int k = 0; k < 4; k++) x.at(x.o.q, qa + 3 + k) = o4[k];
+        } else {
+            int tmy[8];
+            x.template tld_issue<8>(K.rec + R_Y - 2, tmy);
+            x.template tld_wait<8>(tmy);
+            for (int j = 0; j < K.nd; j++) {
+                const double vn = x.at(x.o.v, K.da + j) + h * (j == 0 ? X::unpack(tmy, 1) : (j == 1 ? X::unpack(tmy, 2) : X::unpack(tmy, 3)));
+                x.at(x.o.v, K.da + j) = vn;
+                x.at(x.o.q, K.qa + j) += h * vn;
+            }
         }
     }
 }

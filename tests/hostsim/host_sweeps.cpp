@@ -13,6 +13,7 @@
 namespace egp {
 
 struct HostCtx {
+    static constexpr bool CONS = false;
     double *sm;         // [rows]
     double *tmem;       // this warp's per-thread scratch, 256 doubles
     int w;

@@ -214,3 +214,35 @@ def test_rollout_with_contacts_and_limits_vs_oracle_unpinned():
     assert helpers.relerr(out['states'].cpu().numpy(), ref['states']) < 1e-5
     assert np.allclose(out['rewards'].cpu().numpy(), ref['rewards'], rtol=1e-5, atol=1e-8)
     model.close()
+
+
+def test_block_sweep_kernel_with_rows_matches_the_one_warp_kernel(monkeypatch):
+    """joint limits + floor contact: the 8-warp block-sweep kernel (rows folded into its articulated-body sweeps, active
+    set iterated per CTA) against the one-warp kernel (per-thread active-set loop) on a perf-mode roll-out: same Philox
+    streams, so the trajectories must agree to rounding; and both must differ from the smooth roll-out"""
+    orc = cphys.Oracle(episode_len=20)
+    takes = cphys.synthetic_takes(orc.md, 3, 64, seed=7)
+    orc.make_expert(takes, None)
+    S, nu = orc.S, orc.nu
+    w = helpers.policy_weights(S, 64, 48, nu, seed=3, log_std=-1.0)
+    wd = {k: cu(v.ravel() if k == 'log_std' else v) for k, v in w.items()}
+    E, T = 96, 25
+    outs = {}
+    for name, lim, force in (('smooth', False, None), ('block', True, None), ('one_warp', True, '1')):
+        if force is None:
+            monkeypatch.delenv('EGP_CONS_VARIANT', raising=False)
+        else:
+            monkeypatch.setenv('EGP_CONS_VARIANT', force)
+        model = helpers.make_model()
+        model.upload_experts(orc._keep['x_rows'], orc._keep['x_off'], orc._keep['x_lb'], None)
+        model.set_joint_limits(lim)
+        model.set_contacts(lim)
+        out = model.rollout(wd, E, T, episode_len=20, fix_head_lb=0.2, seed=11, iteration=3)
+        torch.cuda.synchronize()
+        outs[name] = {k: out[k].clone() for k in ('states', 'rewards', 'masks', 'logger')}
+        model.close()
+    a, b = outs['block'], outs['one_warp']
+    assert torch.equal(a['masks'], b['masks'])
+    assert helpers.relerr(a['states'].cpu().numpy(), b['states'].cpu().numpy()) < 1e-6
+    assert np.allclose(a['rewards'].cpu().numpy(), b['rewards'].cpu().numpy(), rtol=1e-6, atol=1e-9)
+    assert helpers.relerr(a['states'].cpu().numpy(), outs['smooth']['states'].cpu().numpy()) > 1e-3
