@@ -183,8 +183,9 @@ void egp_model_destroy(EgpModel *m);
  * upper: none; the free root is ignored), invweight0 [nv] = diag(M^-1) at qpos0 (mjModel.dof_invweight0), solref
  * (timeconst, dampratio) and solimp (d0, dwidth, width, midpoint, power), NULL = MuJoCo's defaults 0.02 1 /
  * 0.9 0.95 0.001 0.5 2.  Host pointers.  range = NULL switches the limits off again (smooth dynamics: the default).
- * With limits on, roll-outs run on the one-warp-per-32-environments kernel (the block sweeps do not carry them yet);
- * evaluation roll-outs and the state LSTM are then unavailable (EGP_ESIZE).  Floor contact: egp_model_set_contacts. */
+ * The block-sweep rollout kernel carries the rows for the plain policy plan (training and evaluation roll-outs); the
+ * state LSTM, the value rule and the chunked wide-policy plan fall back to the one-warp kernel or return EGP_ESIZE.
+ * Floor contact: egp_model_set_contacts. */
 int egp_model_set_joint_limits(EgpModel *m, const double *range, const double *invweight0, const double *solref,
                                const double *solimp);
 
