@@ -572,7 +572,8 @@ def main():
                 'roofline': roofline, 'roofline_extra': extra, 'e2e': e2e, 'cpu_baseline': cpu,
                 'avg_c_reward': log.avg_c_reward, 'avg_episode_reward': log.avg_episode_reward,
                 'avg_episode_len': log.num_steps / max(1, log.num_episodes),
-                'nan_resets': log.num_nan_resets}
+                'nan_resets': log.num_nan_resets,
+                'cons_cap_hits': (int(lib.load().egp_cons_cap_hits(0)) if args.physics == 'full' else None)}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

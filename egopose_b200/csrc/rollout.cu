@@ -486,6 +486,9 @@ __device__ void pass_accel_rows(EnvData &e, double *out) {
     }
 }
 
+// constrained solves that left the active-set loop at its cap without a fixed point (egp_cons_cap_hits)
+__device__ unsigned long long g_cons_cap_hits;
+
 // mj_forward's acceleration stage after pass_kinematics, with e.tau = actuation: bias C + qacc.  Without constraint rows
 // the plain bias / factor sweep and acceleration sweep.  With rows the solver's optimum is
 //   (M + sum_act D_i J_i^T J_i) a = tau - C + sum_act D_i aref_i J_i^T.
@@ -528,13 +531,26 @@ __device__ void forward_dynamics(EnvData &e) {
         if (it == 0) pass_backward<3>(e);
         else pass_backward<2>(e);
         pass_accel_rows(e, e.qacc);
-        unsigned long long nact = 0ull;
-        for (int i = 6; i < nv; i++)
-            if (((inst >> i) & 1ull) && sg[i] * e.qacc[i] - ar[i] < 0.0) nact |= 1ull << i;
-        bool same = nact == act;
-        for (int k = 0; k < nrow; k++) { same = same && e.row_new[k] == e.row_act[k]; e.row_act[k] = e.row_new[k]; }
-        act = nact;
+        // all rows that disagree flip at once; if that has not settled after CONS_CAREFUL passes (coupled rows can flip back and
+        // forth: about 1 of 20 000 solves), only the first disagreeing row flips per pass
+        const bool careful = it >= CONS_CAREFUL;
+        bool same = true;
+        for (int i = 6; i < nv; i++) {
+            if (!((inst >> i) & 1ull)) continue;
+            const bool on = sg[i] * e.qacc[i] - ar[i] < 0.0;
+            if (on != (bool)((act >> i) & 1ull)) {
+                if (!careful || same) act ^= 1ull << i;
+                same = false;
+            }
+        }
+        for (int k = 0; k < nrow; k++) {
+            if (e.row_new[k] != e.row_act[k]) {
+                if (!careful || same) e.row_act[k] = e.row_new[k];
+                same = false;
+            }
+        }
         if (same) break;
+        if (it == 99) atomicAdd(&g_cons_cap_hits, 1ull);
     }
 }
 
@@ -1113,8 +1129,8 @@ struct T4Ctx {
 struct T4CtxC : T4Ctx {
     static constexpr bool CONS = true;
     double *csb;
-    mutable unsigned ccnt, lim_inst, lim_act;
-    mutable int cchg;
+    mutable unsigned ccnt, lim_inst, lim_act, lim_pinst, lim_pact;
+    mutable int cchg, cflip;
     int cit;
     __device__ __forceinline__ double &cs(int slot) const { return csb[(size_t)slot * 32 + lane]; }
 };
@@ -1159,7 +1175,7 @@ __device__ __forceinline__ void t4_backward(const X &x, const int MODE) {
 template <class X>
 __device__ __noinline__ void t4_forward_only(const X x0) {     // sim.forward(); chain warps only; own register allocation
     X x = x0;
-    if constexpr (X::CONS) { x.ccnt = 0u; x.lim_act = 0u; x.cit = 1; }      // no constraint rows: only the tree data and the bias are used
+    if constexpr (X::CONS) { x.ccnt = 0u; x.lim_act = 0u; x.lim_pinst = 0u; x.lim_pact = 0u; x.cit = 1; }      // no constraint rows: only the tree data and the bias are used
     t4_forward<2>(x);
     T4_FOR_OWN_DOFS(i, b) if (i >= 6) tm_st1(x.a_tau(i), 0.0);
     tm_wait_st();
@@ -1181,7 +1197,6 @@ __device__ __forceinline__ void t4_substep(const X &x) {
 #endif
     t4_backward(x, 1);          // (M_stale + Kd h) factor + reduce, rhs from the current q, v
     T4_CLK(0)
-    if constexpr (X::CONS) x.ccnt = 0u;
     t4_forward<1>(x);           // desired accel -> clipped torque ; kinematics / velocities / body forces at (q, v)
     T4_CLK(1)
     if constexpr (X::CONS) {
@@ -1190,10 +1205,11 @@ __device__ __forceinline__ void t4_substep(const X &x) {
         // sweep re-evaluates them, and the pair is repeated until the active set of every environment of the CTA is at its
         // fixed point (first pass: every row active; bias C and factor share that pass); then the Euler step.
         X &xm = const_cast<X &>(x);
+        x.lim_pinst = x.lim_inst; x.lim_pact = x.lim_act;
         x.lim_inst = 0u; x.lim_act = 0u;
 #pragma unroll 1
         for (xm.cit = 0; xm.cit < 100; xm.cit++) {
-            x.cchg = 0;
+            x.cchg = 0; x.cflip = 0;
             t4_backward(x, 0);
             t4_forward<3>(x);
             const bool any = __any_sync(0xffffffffu, x.cchg != 0);
@@ -1201,6 +1217,7 @@ __device__ __forceinline__ void t4_substep(const X &x) {
             t4_bar();
             const double tot = t4_smem[x.o.red * 32] + t4_smem[(x.o.red + 1) * 32] + t4_smem[(x.o.red + 2) * 32] + t4_smem[(x.o.red + 3) * 32];
             if (tot == 0.0) break;
+            if (xm.cit == 99 && x.cchg) atomicAdd(&g_cons_cap_hits, 1ull);
         }
         T4_CLK(2)
 #pragma unroll 1
@@ -1285,7 +1302,7 @@ rollout_kernel_t4(const RolloutArgs A, const T4Off O) {
     x.lane = threadIdx.x & 31; x.w = threadIdx.x >> 5; x.o = O;
     if constexpr (CONS) {
         x.csb = A.cons + (size_t)blockIdx.x * CS_PER_BODY * c_m.nbody * 32;
-        x.ccnt = 0u; x.lim_inst = 0u; x.lim_act = 0u; x.cchg = 0; x.cit = 0;
+        x.ccnt = 0u; x.lim_inst = 0u; x.lim_act = 0u; x.lim_pinst = 0u; x.lim_pact = 0u; x.cchg = 0; x.cflip = 0; x.cit = 0;
     }
     const int lane = x.lane, w = x.w;
     // allocate the whole Tensor Memory of this SM (1 CTA per SM) as scratch; base address comes back via smem
@@ -2032,6 +2049,15 @@ int egp_model_set_contacts(EgpModel *m, const int32_t *geom_type, const double *
     d.con_margin = margin; d.con_mu = friction;
     d.contacts = 1;
     return EGP_OK;
+}
+
+/* number of constrained solves (per environment and sub-step) since the last reset that ran into the iteration cap (100) of
+ * the active-set loop without reaching its fixed point; synchronises the device */
+int64_t egp_cons_cap_hits(int reset) {
+    unsigned long long v = 0, z = 0;
+    if (cudaMemcpyFromSymbol(&v, g_cons_cap_hits, sizeof v) != cudaSuccess) return -1;
+    if (reset && cudaMemcpyToSymbol(g_cons_cap_hits, &z, sizeof z) != cudaSuccess) return -1;
+    return (int64_t)v;
 }
 
 void egp_model_destroy(EgpModel *m) {

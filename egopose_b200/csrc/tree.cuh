@@ -294,9 +294,21 @@ constexpr int R_FB = 0, R_CIN = 12, R_CTRL = 32, R_C = 38, R_TAU = 44, R_Y = 50,
 // A context with CONS = true adds:  double &cs(int slot)  this environment's constraint scratch (L2-resident global memory,
 // [slot][lane] per CTA), and the per-thread state  ccnt (3 bits per body slot: floor contacts of that body), lim_inst / lim_act
 // (1 bit per (body slot, joint): range violated / row active), cchg (the active set changed in this pass), cit (active-set
-// iteration).  Scratch record of body b at slot CS_PER_BODY * b:  flags (as a double: bit 4 k + e = edge e of contact k active) |
+// iteration), cflip (a row of this thread has flipped in this pass), lim_pinst / lim_pact (the same at the end of the
+// previous sub-step).  Scratch record of body b at slot CS_PER_BODY * b:  flags (as a double: bit 4 k + e = edge e of contact k active) |
 // per contact: point c (relative to O) 3, weight D, aref of the four pyramid edges.
 constexpr int CS_PER_BODY = 33;
+constexpr int CONS_CAREFUL = 12;     // passes after which only one disagreeing row flips per pass (coupled rows can flip back and forth)
+
+// may a disagreeing row of this thread flip in this pass?  Always in the first CONS_CAREFUL passes; afterwards one row per pass
+// and environment: only in the chain warp whose turn it is (round robin), and only the first one it meets
+template <class X>
+EGP_HD bool cons_may_flip(const X &x) {
+    if (x.cit < CONS_CAREFUL) return true;
+    if ((x.cit & 3) != x.w || x.cflip) return false;
+    x.cflip = 1;
+    return true;
+}
 
 // one row at signed distance dist (already minus its margin) and row velocity vel -> weight D = 1/R, reference acceleration
 EGP_HD void cons_row(double invweight, double dist, double vel, double &Dc, double &aref) {
@@ -365,6 +377,7 @@ template <class X>
 EGP_HD void cons_collide(const X &x, const Fwd &f, int b) {
     const DevModel &M = EGP_CONST_M;
     const int slot = M.body_slot[b];
+    const int old_cnt = (x.ccnt >> (3 * slot)) & 7u;
     int cnt = 0;
     if (M.contacts) {
         const double margin = M.con_margin, zO = x.at(x.o.q, 2);
@@ -404,7 +417,9 @@ EGP_HD void cons_collide(const X &x, const Fwd &f, int b) {
                 cnt++;
             }
         }
-        if (cnt) x.cs(CS_PER_BODY * b) = (double)((1 << (4 * cnt)) - 1);
+        // first guess of the active set: what the previous sub-step ended with if the body still has the same number of contacts
+        // (a body at rest keeps its rows; the fixed point of the iteration does not depend on the guess), else every edge
+        if (cnt && cnt != old_cnt) x.cs(CS_PER_BODY * b) = (double)((1 << (4 * cnt)) - 1);
     }
     x.ccnt = (x.ccnt & ~(7u << (3 * slot))) | ((unsigned)cnt << (3 * slot));
 }
@@ -458,7 +473,14 @@ EGP_HD void cons_fwd_contacts(const X &x, const double *a, int b) {
         for (int ed = 0; ed < 4; ed++)
             if (an + ((ed & 1) ? -mu : mu) * (ed < 2 ? a1 : a2) - x.cs(r0 + 4 + ed) < 0.0) nf |= 1u << (4 * k + ed);
     }
-    if (nf != flags) { x.cs(base) = (double)nf; x.cchg = 1; }
+    if (nf != flags) {
+        x.cchg = 1;
+        if (x.cit < CONS_CAREFUL) x.cs(base) = (double)nf;
+        else if (cons_may_flip(x)) {            // one edge only: the lowest disagreeing bit
+            const unsigned df = nf ^ flags;
+            x.cs(base) = (double)(flags ^ (df & (0u - df)));
+        }
+    }
 }
 
 template <class X>
@@ -551,7 +573,10 @@ EGP_HD void t5_bwd_body(const X &x, Bwd &w, BwdIn &in, const int MODE, const int
                 const unsigned bit = 1u << (3 * slot + j);
                 double sgn, Dc, ar;
                 if (!cons_limit(da + j, x.at(x.o.q, da + j + 1), x.at(x.o.v, da + j), sgn, Dc, ar)) continue;
-                if (x.cit == 0) { x.lim_inst |= bit; x.lim_act |= bit; }
+                if (x.cit == 0) {           // first guess: the row's state at the end of the previous sub-step, active if it is new
+                    x.lim_inst |= bit;
+                    if (!(x.lim_pinst & bit) || (x.lim_pact & bit)) x.lim_act |= bit;
+                }
                 if (x.lim_act & bit) { diag[j] += Dc; rhs[j] += Dc * sgn * ar; }
             }
         }
@@ -738,7 +763,7 @@ EGP_HD void t5_fwd_solve_body(const X &x, double *a, const FwdIn<MODE> &in) {
                 double sgn, Dc, ar;
                 cons_limit(in.da + j, in.q[j], in.v[j], sgn, Dc, ar);
                 const bool on = sgn * xs[j] - ar < 0.0;
-                if (on != ((x.lim_act & bit) != 0)) { x.lim_act ^= bit; x.cchg = 1; }
+                if (on != ((x.lim_act & bit) != 0)) { x.cchg = 1; if (cons_may_flip(x)) x.lim_act ^= bit; }
             }
             cons_fwd_contacts(x, a, in.b);
         }

@@ -100,6 +100,7 @@ SYMBOLS = {
     'egp_rollout_f64': (_int, [_vp, C.POINTER(PolicyWeights), C.POINTER(RolloutCfg), C.POINTER(RolloutIn),
                                C.POINTER(TrajOut), _vp]),
     'egp_model_set_joint_limits': (_int, [_vp, _vp, _vp, _vp, _vp]),
+    'egp_cons_cap_hits': (_i64, [_int]),
     'egp_model_set_contacts': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _vp, _vp]),
     'egp_gae_work_bytes': (_i64, [_i64]),
     'egp_gae_f64': (_int, [_vp, _vp, _vp, _d, _d, _i64, _vp, _vp, _vp, _vp, _vp]),

@@ -196,6 +196,9 @@ int egp_model_set_joint_limits(EgpModel *m, const double *range, const double *i
  * rotational), margin, sliding friction; solref / solimp as above (one set is shared with the limit rows).  Host pointers;
  * geom_type = NULL switches contacts off (the default).  Only geom-floor pairs are generated: contacts BETWEEN body geoms
  * are not modelled.  Same kernel restriction as the joint limits. */
+/* diagnostics: constrained solves (one environment, one sub-step) since the last reset that left the active-set loop at its
+ * cap of 100 passes without a fixed point; synchronises the device */
+int64_t egp_cons_cap_hits(int reset);
 int egp_model_set_contacts(EgpModel *m, const int32_t *geom_type, const double *geom_size, const double *geom_p0,
                            const double *geom_p1, const double *body_invweight0, double margin, double friction,
                            const double *solref, const double *solimp);

@@ -313,6 +313,7 @@ void eo_limit_row(const EoModel *m, double dist, double vel, double invweight, d
  * the active set {i: J_i a - aref_i < 0} is iterated to its fixed point (Newton on the piecewise-quadratic cost with unit
  * steps; the optimum is unique, MuJoCo's Newton solver converges to the same point up to its tolerance). */
 #define EO_MAXCON 40
+#define EO_CAREFUL 12
 #define EO_MAXROW (EO_MAXV + 4 * EO_MAXCON)
 
 typedef struct { int n; double J[EO_MAXROW][EO_MAXV], D[EO_MAXROW], aref[EO_MAXROW]; } EoRows;
@@ -406,6 +407,13 @@ static void collect_rows(const EoModel *m, const EoData *d, EoRows *R) {
     }
 }
 
+/* diagnostics of the active-set iteration over all solves since the last reset: [0] solves with rows, [1] largest number of
+ * passes, [2] solves that hit the cap without reaching a fixed point (not thread-safe counters: test use only) */
+static long g_solver_stats[3];
+void eo_solver_stats(long *out3, int reset) {
+    for (int k = 0; k < 3; k++) { out3[k] = g_solver_stats[k]; if (reset) g_solver_stats[k] = 0; }
+}
+
 int eo_constraint_solve(const EoModel *m, EoData *d, const double *smooth) {
     const int nv = m->nv;
     static _Thread_local EoRows R;
@@ -427,18 +435,24 @@ int eo_constraint_solve(const EoModel *m, EoData *d, const double *smooth) {
             }
         }
         eo_chol_solve(nv, A, rhs);
+        /* all rows that disagree flip at once; if that has not settled after EO_CAREFUL passes (coupled rows can flip back and
+         * forth: seen in about 1 of 20 000 solves), only the first disagreeing row flips per pass */
         int changed = 0;
         for (int i = 0; i < R.n; i++) {
             double r = -R.aref[i];
             for (int k = 0; k < nv; k++) r += R.J[i][k] * rhs[k];
             int a1 = r < 0.0;
-            if (a1 != act[i]) { act[i] = a1; changed = 1; }
+            if (a1 != act[i]) {
+                if (it < EO_CAREFUL || !changed) act[i] = a1;
+                changed = 1;
+            }
         }
         if (!changed) break;
     }
     memcpy(d->qacc, rhs, sizeof(double) * nv);
     d->n_efc = R.n;
     d->solver_iter = it;
+    if (R.n) { g_solver_stats[0]++; if (it + 1 > g_solver_stats[1]) g_solver_stats[1] = it + 1; if (it >= 100) g_solver_stats[2]++; }
     return R.n;
 }
 

@@ -106,6 +106,7 @@ void eo_step(const EoModel *m, EoData *d);                      /* mj_step: forw
 void eo_kinematics(const EoModel *m, EoData *d, double *dof_axis_w, double *dof_anchor_w);
 int eo_chol_solve(int n, double *A, double *b);                 /* in-place dense Cholesky solve */
 int eo_constraint_solve(const EoModel *m, EoData *d, const double *qfrc_smooth);   /* rows + solve -> d->qacc */
+void eo_solver_stats(long *out3, int reset);
 void eo_limit_row(const EoModel *m, double dist, double vel, double invweight, double *D, double *aref);
 
 /* env (ego_pose/envs/humanoid_v1.py) */

@@ -220,6 +220,7 @@ def test_block_sweep_kernel_with_rows_matches_the_one_warp_kernel(monkeypatch):
     """joint limits + floor contact: the 8-warp block-sweep kernel (rows folded into its articulated-body sweeps, active
     set iterated per CTA) against the one-warp kernel (per-thread active-set loop) on a perf-mode roll-out: same Philox
     streams, so the trajectories must agree to rounding; and both must differ from the smooth roll-out"""
+    from egopose_b200 import lib
     orc = cphys.Oracle(episode_len=20)
     takes = cphys.synthetic_takes(orc.md, 3, 64, seed=7)
     orc.make_expert(takes, None)
@@ -237,8 +238,12 @@ def test_block_sweep_kernel_with_rows_matches_the_one_warp_kernel(monkeypatch):
         model.upload_experts(orc._keep['x_rows'], orc._keep['x_off'], orc._keep['x_lb'], None)
         model.set_joint_limits(lim)
         model.set_contacts(lim)
+        lib.load().egp_cons_cap_hits(1)
         out = model.rollout(wd, E, T, episode_len=20, fix_head_lb=0.2, seed=11, iteration=3)
         torch.cuda.synchronize()
+        # every constrained solve reached the fixed point of its active set (this roll-out contains two solves in which the
+        # all-rows-at-once iteration flips two coupled rows back and forth: the one-row-per-pass rule settles them)
+        assert lib.load().egp_cons_cap_hits(0) == 0
         outs[name] = {k: out[k].clone() for k in ('states', 'rewards', 'masks', 'logger')}
         model.close()
     a, b = outs['block'], outs['one_warp']
