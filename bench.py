@@ -239,6 +239,15 @@ def cpu_reference(args, takes, cnn, hidden, threads):
     return 1.0 / per_step, detail
 
 
+def cons_passes(lib):
+    """average number of (backward, forward) passes of the active-set iteration per sub-step in the block-sweep kernel"""
+    import ctypes
+    out = (ctypes.c_int64 * 2)()
+    if lib.load().egp_cons_passes(out, 0) != 0 or out[0] == 0:
+        return None
+    return out[1] / out[0]
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -573,7 +582,8 @@ def main():
                 'avg_c_reward': log.avg_c_reward, 'avg_episode_reward': log.avg_episode_reward,
                 'avg_episode_len': log.num_steps / max(1, log.num_episodes),
                 'nan_resets': log.num_nan_resets,
-                'cons_cap_hits': (int(lib.load().egp_cons_cap_hits(0)) if args.physics == 'full' else None)}
+                'cons_cap_hits': (int(lib.load().egp_cons_cap_hits(0)) if args.physics == 'full' else None),
+                'cons_passes_per_substep': cons_passes(lib) if args.physics == 'full' else None}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -488,6 +488,7 @@ __device__ void pass_accel_rows(EnvData &e, double *out) {
 
 // constrained solves that left the active-set loop at its cap without a fixed point (egp_cons_cap_hits)
 __device__ unsigned long long g_cons_cap_hits;
+__device__ unsigned long long g_cons_passes[2];     // block-sweep kernel, CTA 0 only: sub-steps, active-set passes
 
 // mj_forward's acceleration stage after pass_kinematics, with e.tau = actuation: bias C + qacc.  Without constraint rows
 // the plain bias / factor sweep and acceleration sweep.  With rows the solver's optimum is
@@ -1219,6 +1220,7 @@ __device__ __forceinline__ void t4_substep(const X &x) {
             if (tot == 0.0) break;
             if (xm.cit == 99 && x.cchg) atomicAdd(&g_cons_cap_hits, 1ull);
         }
+        if (blockIdx.x == 0 && threadIdx.x == 0) { g_cons_passes[0] += 1; g_cons_passes[1] += (unsigned long long)(xm.cit < 100 ? xm.cit + 1 : 100); }
         T4_CLK(2)
 #pragma unroll 1
         for (int L = 0; L < c_m.nlevel; L++) {
@@ -2053,6 +2055,15 @@ int egp_model_set_contacts(EgpModel *m, const int32_t *geom_type, const double *
 
 /* number of constrained solves (per environment and sub-step) since the last reset that ran into the iteration cap (100) of
  * the active-set loop without reaching its fixed point; synchronises the device */
+/* block-sweep kernel: out[0] = sub-steps, out[1] = active-set passes they took (first CTA of every launch); synchronises */
+int egp_cons_passes(int64_t *out2, int reset) {
+    unsigned long long v[2] = {0, 0}, z[2] = {0, 0};
+    if (!out2 || cudaMemcpyFromSymbol(v, g_cons_passes, sizeof v) != cudaSuccess) return EGP_ECUDA;
+    if (reset && cudaMemcpyToSymbol(g_cons_passes, z, sizeof z) != cudaSuccess) return EGP_ECUDA;
+    out2[0] = (int64_t)v[0]; out2[1] = (int64_t)v[1];
+    return EGP_OK;
+}
+
 int64_t egp_cons_cap_hits(int reset) {
     unsigned long long v = 0, z = 0;
     if (cudaMemcpyFromSymbol(&v, g_cons_cap_hits, sizeof v) != cudaSuccess) return -1;

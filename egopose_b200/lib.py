@@ -101,6 +101,7 @@ SYMBOLS = {
                                C.POINTER(TrajOut), _vp]),
     'egp_model_set_joint_limits': (_int, [_vp, _vp, _vp, _vp, _vp]),
     'egp_cons_cap_hits': (_i64, [_int]),
+    'egp_cons_passes': (_int, [_vp, _int]),
     'egp_model_set_contacts': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _vp, _vp]),
     'egp_gae_work_bytes': (_i64, [_i64]),
     'egp_gae_f64': (_int, [_vp, _vp, _vp, _d, _d, _i64, _vp, _vp, _vp, _vp, _vp]),

@@ -199,6 +199,9 @@ int egp_model_set_joint_limits(EgpModel *m, const double *range, const double *i
 /* diagnostics: constrained solves (one environment, one sub-step) since the last reset that left the active-set loop at its
  * cap of 100 passes without a fixed point; synchronises the device */
 int64_t egp_cons_cap_hits(int reset);
+/* diagnostics of the block-sweep kernel: out2[0] = sub-steps, out2[1] = backward + forward passes of the active-set iteration
+ * they took (counted by the first CTA of every launch) */
+int egp_cons_passes(int64_t *out2, int reset);
 int egp_model_set_contacts(EgpModel *m, const int32_t *geom_type, const double *geom_size, const double *geom_p0,
                            const double *geom_p1, const double *body_invweight0, double margin, double friction,
                            const double *solref, const double *solimp);
