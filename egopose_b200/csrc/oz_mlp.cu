@@ -22,6 +22,10 @@ namespace oz {
 
 static inline long long al(long long v) { return (v + 1023) & ~1023LL; }
 static inline int pad16(long long k) { return (int)((k + 15) / 16 * 16); }
+// Row pitch of slice tensors whose contraction runs along the FEATURES: a multiple of the 32-byte k block, so that every
+// 32-byte row segment a TMA box fetches is one aligned sector (pitch 304 for a 300-wide layer put every other row across
+// two sectors: the 300-wide forward / data-gradient GEMMs ran 25 % slower than the 243 -> 256 wide first layer per k block).
+static inline int padk(long long k) { return (int)((k + 31) / 32 * 32); }
 
 // gW[o][i] (+)= 2^(ea_i + eb_o + EOFF) * sum_z part[z][i][o] for i < in; gb[o] (+)= the same for i == in (ones row)
 __global__ void __launch_bounds__(256)
@@ -66,50 +70,91 @@ head1_fwd_kernel(const double *__restrict__ a2, long long m, int h2, const doubl
 }
 
 // d2[n][k] = a2[n][k] > 0 ? dy[n] w[k] : 0 ; part[block][k] = sum over the block's rows of dy[n] a2[n][k], part[block][h2] = sum dy[n]
-__global__ void __launch_bounds__(32 * HEAD_WARPS)
+// J = ceil(h2 / 32) column groups per lane (compile-time: weights and partial sums stay in registers, 3 blocks per SM).
+// Optionally records what the slicers of d2 need: rowmax[n] = high word of max_k |d2[n][k]|, colmax[k] = bit pattern of
+// max_n |d2[n][k]| (atomicMax, buffer zeroed by the caller) - so d2 is read ONCE afterwards (oz_slice_both).
+template <int J>
+__global__ void __launch_bounds__(32 * HEAD_WARPS, J <= 10 ? 3 : 2)
 head1_bwd_kernel(const double *__restrict__ a2, const double *__restrict__ dy, long long m, int h2, const double *__restrict__ w,
-                 double *__restrict__ d2, double *__restrict__ part) {
-    __shared__ double red[HEAD_WARPS][32 * HEAD_MAXJ + 1];
+                 double *__restrict__ d2, double *__restrict__ part, uint32_t *__restrict__ rowmax,
+                 unsigned long long *__restrict__ colmax) {
+    __shared__ double red[HEAD_WARPS][32 * J + 1];
     const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
     const long long per = (m + gridDim.x - 1) / gridDim.x, r0 = (long long)blockIdx.x * per, r1 = r0 + per < m ? r0 + per : m;
-    double wl[HEAD_MAXJ], acc[HEAD_MAXJ], sdy = 0.0;
+    double wl[J], acc[J], sdy = 0.0;
+    uint32_t cm[J];
 #pragma unroll
-    for (int j = 0; j < HEAD_MAXJ; j++) { wl[j] = lane + 32 * j < h2 ? w[lane + 32 * j] : 0.0; acc[j] = 0.0; }
+    for (int j = 0; j < J; j++) { wl[j] = lane + 32 * j < h2 ? w[lane + 32 * j] : 0.0; acc[j] = 0.0; cm[j] = 0u; }
     for (long long r = r0 + wp; r < r1; r += HEAD_WARPS) {
         const double g = dy[r];
         const double *row = a2 + r * h2;
         double *out = d2 + r * h2;
-        sdy += g;
+        double a[J];
 #pragma unroll
-        for (int j = 0; j < HEAD_MAXJ; j++)
+        for (int j = 0; j < J; j++) a[j] = lane + 32 * j < h2 ? __ldcs(row + lane + 32 * j) : 0.0;
+        sdy += g;
+        uint32_t hm = 0u;
+#pragma unroll
+        for (int j = 0; j < J; j++)
             if (lane + 32 * j < h2) {
-                const double a = row[lane + 32 * j];
-                out[lane + 32 * j] = a > 0.0 ? g * wl[j] : 0.0;
-                acc[j] += g * a;
+                const double v = a[j] > 0.0 ? g * wl[j] : 0.0;
+                out[lane + 32 * j] = v;
+                acc[j] += g * a[j];
+                const uint32_t h = (uint32_t)__double2hiint(v) & 0x7fffffffu;
+                hm = max(hm, h);
+                cm[j] = max(cm[j], h);
             }
+        if (rowmax) {
+            hm = __reduce_max_sync(0xffffffffu, hm);
+            if (lane == 0) rowmax[r] = hm;
+        }
     }
 #pragma unroll
-    for (int j = 0; j < HEAD_MAXJ; j++) red[wp][lane + 32 * j] = acc[j];
-    if (lane == 0) red[wp][32 * HEAD_MAXJ] = sdy;
+    for (int j = 0; j < J; j++) red[wp][lane + 32 * j] = acc[j];
+    if (lane == 0) red[wp][32 * J] = sdy;
     __syncthreads();
     for (int k = threadIdx.x; k <= h2; k += blockDim.x) {
-        const int src = k < h2 ? k : 32 * HEAD_MAXJ;
+        const int src = k < h2 ? k : 32 * J;
         double t = 0.0;
 #pragma unroll
         for (int q = 0; q < HEAD_WARPS; q++) t += red[q][src];
         part[(size_t)blockIdx.x * (h2 + 1) + k] = t;
     }
+    if (colmax) {
+        __syncthreads();
+        uint32_t *redu = reinterpret_cast<uint32_t *>(&red[0][0]);
+#pragma unroll
+        for (int j = 0; j < J; j++) redu[wp * (32 * J) + lane + 32 * j] = cm[j];
+        __syncthreads();
+        for (int k = threadIdx.x; k < h2; k += blockDim.x) {
+            uint32_t t = redu[k];
+#pragma unroll
+            for (int q = 1; q < HEAD_WARPS; q++) t = max(t, redu[q * (32 * J) + k]);
+            if (t > 0u) atomicMax(colmax + k, (unsigned long long)t << 32);
+        }
+    }
 }
 
-// gW[k] (+)= sum_blocks part[block][k] in block order ; gb (+)= part[.][h2]
-__global__ void head1_reduce_kernel(const double *__restrict__ part, int nblocks, int h2, double *__restrict__ gW, double *__restrict__ gb,
-                                    int accumulate) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k > h2) return;
+// gW[k] (+)= sum_blocks part[block][k] in a fixed order ; gb (+)= part[.][h2].  One block per k: thread t sums blocks
+// t, t + 128, ... then a fixed shared-memory tree (deterministic).
+__global__ void __launch_bounds__(128)
+head1_reduce_kernel(const double *__restrict__ part, int nblocks, int h2, double *__restrict__ gW, double *__restrict__ gb,
+                    int accumulate) {
+    __shared__ double red[128];
+    const int k = blockIdx.x;
     double t = 0.0;
-    for (int b = 0; b < nblocks; b++) t += part[(size_t)b * (h2 + 1) + k];
-    double *dst = k < h2 ? gW + k : gb;
-    *dst = accumulate ? *dst + t : t;
+    for (int b = threadIdx.x; b < nblocks; b += 128) t += part[(size_t)b * (h2 + 1) + k];
+    red[threadIdx.x] = t;
+    __syncthreads();
+#pragma unroll
+    for (int o = 64; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        double *dst = k < h2 ? gW + k : gb;
+        *dst = accumulate ? *dst + red[0] : red[0];
+    }
 }
 
 struct Buf {
@@ -139,7 +184,7 @@ int64_t egp_oz_mlp_chunk_rows(void) { return (int64_t)num_sms() * BM; }
 
 /* bytes of the input-slice cache for n rows of width in_dim (row slices + transposed slices with the ones row, per chunk) */
 static long long xcache_chunk_bytes(int in_dim, long long chunk, int S) {
-    const int kp = pad16(in_dim);
+    const int kp = padk(in_dim);
     const long long cp = pad16(chunk);
     return al((long long)S * chunk * kp) + al(chunk * 4) + al((long long)S * (in_dim + 1) * cp) + al((in_dim + 1) * 4LL);
 }
@@ -161,7 +206,7 @@ struct MlpPlan {
 static MlpPlan mlp_plan(char *base, int in, int h1, int h2, int od, long long M, int S, int dx_cols = 0) {
     MlpPlan P;
     const long long MP = pad16(M);
-    const int kin = pad16(in), kh1 = pad16(h1), kh2 = pad16(h2), kod = pad16(od);
+    const int kin = padk(in), kh1 = padk(h1), kh2 = padk(h2), kod = padk(od);
     const int hmax = h1 > h2 ? h1 : h2;
     Buf B{base, 0, 0};
     P.W1s = Sl{B.take<int8_t>((long long)S * h1 * kin), B.take<int32_t>(h1 + 16)};
@@ -220,7 +265,7 @@ int egp_oz_mlp_step_f64(const EgpMlpNet *net, const double *d_x, int64_t ldx, in
     if (xcache_state && !d_xcache) { set_error("egp_oz_mlp_step_f64: cache state without cache"); return EGP_EINVAL; }
     cudaStream_t st = (cudaStream_t)stream;
     const long long M = chunk_rows, MP = pad16(M);
-    const int kin = pad16(in), kh1 = pad16(h1), kh2 = pad16(h2), kod = pad16(od);
+    const int kin = padk(in), kh1 = padk(h1), kh2 = padk(h2), kod = padk(od);
     const int hmax = h1 > h2 ? h1 : h2;
     const MlpPlan P = mlp_plan((char *)d_work, in, h1, h2, od, M, S, dxc);
     const Sl &W1s = P.W1s, &W2s = P.W2s, &W3s = P.W3s, &W3T = P.W3T, &W2T = P.W2T, &a1s = P.a1s, &a2s = P.a2s, &d2s = P.d2s, &dys = P.dys,
@@ -237,7 +282,7 @@ int egp_oz_mlp_step_f64(const EgpMlpNet *net, const double *d_x, int64_t ldx, in
     OZ_TRY(slice_rows(net->d_W2, h2, h1, h1, S, W2s.q, kh1, W2s.e, nullptr, st));
     // scalar head (the critic): streamed in plain float64 instead of padding a 1-wide GEMM to a tensor-core tile
     const bool head1 = od == 1 && h2 <= 32 * HEAD_MAXJ;
-    const int head_blocks = num_sms() * 4;
+    const int head_blocks = num_sms() * 3;
     if (!head1) OZ_TRY(slice_rows(net->d_W3, od, h2, h2, S, W3s.q, kh2, W3s.e, nullptr, st));
     if (bwd) {
         EGP_CUDA(cudaMemsetAsync(cmax[0], 0, cmax_bytes, st));
@@ -319,9 +364,15 @@ int egp_oz_mlp_step_f64(const EgpMlpNet *net, const double *d_x, int64_t ldx, in
         };
         if (head1) {
             if ((long long)head_blocks * (h2 + 1) * 8 > part_bytes) { set_error("egp_oz_mlp_step_f64: head workspace"); return EGP_EINVAL; }
-            head1_bwd_kernel<<<head_blocks, 32 * HEAD_WARPS, 0, st>>>(a2, dy, m, h2, net->d_W3, d2, part);
+            uint32_t *rmx = nullptr;
+            unsigned long long *cmx = nullptr;
+            const int jn = (h2 + 31) / 32;
+            if (jn <= 4) head1_bwd_kernel<4><<<head_blocks, 32 * HEAD_WARPS, 0, st>>>(a2, dy, m, h2, net->d_W3, d2, part, rmx, cmx);
+            else if (jn <= 8) head1_bwd_kernel<8><<<head_blocks, 32 * HEAD_WARPS, 0, st>>>(a2, dy, m, h2, net->d_W3, d2, part, rmx, cmx);
+            else if (jn <= 10) head1_bwd_kernel<10><<<head_blocks, 32 * HEAD_WARPS, 0, st>>>(a2, dy, m, h2, net->d_W3, d2, part, rmx, cmx);
+            else head1_bwd_kernel<HEAD_MAXJ><<<head_blocks, 32 * HEAD_WARPS, 0, st>>>(a2, dy, m, h2, net->d_W3, d2, part, rmx, cmx);
             EGP_CHECK_LAUNCH("head1_bwd_kernel");
-            head1_reduce_kernel<<<(h2 + 1 + 127) / 128, 128, 0, st>>>(part, head_blocks, h2, net->d_gW3, net->d_gb3, acc);
+            head1_reduce_kernel<<<h2 + 1, 128, 0, st>>>(part, head_blocks, h2, net->d_gW3, net->d_gb3, acc);
             EGP_CHECK_LAUNCH("head1_reduce_kernel");
         } else {
             EGP_CUDA(cudaMemsetAsync(cmax[5], 0, cmax_bytes, st));
