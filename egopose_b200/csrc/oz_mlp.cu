@@ -182,6 +182,16 @@ extern "C" {
 
 int64_t egp_oz_mlp_chunk_rows(void) { return (int64_t)num_sms() * BM; }
 
+/* 1 (default; EGP_OZ_FUSED_SLICE=0 in the environment starts with 0): producers record row / column abs-maxima and every
+ * intermediate is sliced in both orientations from one read; 0: separate row / column-maximum / transposed passes.
+ * Negative: query only.  Returns the setting in force (before the call's change when querying). */
+int egp_oz_mlp_set_fused_slicing(int on) {
+    static int state = -1;
+    if (state < 0) { const char *e = getenv("EGP_OZ_FUSED_SLICE"); state = (e && atoi(e) == 0) ? 0 : 1; }
+    if (on >= 0) state = on ? 1 : 0;
+    return state;
+}
+
 /* bytes of the input-slice cache for n rows of width in_dim (row slices + transposed slices with the ones row, per chunk) */
 static long long xcache_chunk_bytes(int in_dim, long long chunk, int S) {
     const int kp = padk(in_dim);
@@ -198,6 +208,7 @@ struct MlpPlan {
     Sl W1s, W2s, W3s, W3T, W2T, a1s, a2s, d2s, dys, a1T, a2T, d2T, d1T, dyT, d1s, W1Tc;
     unsigned long long *cmax[8];
     double *a1, *a2, *d1, *d2, *ybuf, *dy, *part;
+    uint32_t *rmax;
     long long part_bytes;
     char *xlocal;
     long long total;
@@ -217,6 +228,7 @@ static MlpPlan mlp_plan(char *base, int in, int h1, int h2, int od, long long M,
     for (int i = 0; i < 8; i++) P.cmax[i] = B.take<unsigned long long>(hmax + in + od + 16);
     P.a1 = B.take<double>(M * h1); P.a2 = B.take<double>(M * h2); P.d1 = B.take<double>(M * h1); P.d2 = B.take<double>(M * h2);
     P.ybuf = B.take<double>(M * od); P.dy = B.take<double>(M * od);
+    P.rmax = B.take<uint32_t>(M);
     P.a1s = Sl{B.take<int8_t>(S * M * kh1), B.take<int32_t>(M)}; P.a2s = Sl{B.take<int8_t>(S * M * kh2), B.take<int32_t>(M)};
     P.d2s = Sl{B.take<int8_t>(S * M * kh2), B.take<int32_t>(M)}; P.dys = Sl{B.take<int8_t>(S * M * kod), B.take<int32_t>(M)};
     P.a1T = Sl{B.take<int8_t>(S * (h1 + 1) * MP), B.take<int32_t>(h1 + 16)}; P.a2T = Sl{B.take<int8_t>(S * (h2 + 1) * MP), B.take<int32_t>(h2 + 16)};
@@ -272,6 +284,11 @@ int egp_oz_mlp_step_f64(const EgpMlpNet *net, const double *d_x, int64_t ldx, in
              &a1T = P.a1T, &a2T = P.a2T, &d2T = P.d2T, &d1T = P.d1T, &dyT = P.dyT, &d1s = P.d1s, &W1Tc = P.W1Tc;
     unsigned long long *const *cmax = P.cmax;
     double *a1 = P.a1, *a2 = P.a2, *d1 = P.d1, *d2 = P.d2, *ybuf = P.ybuf, *dy = P.dy, *part = P.part;
+    uint32_t *rmax = P.rmax;
+    // Row / column abs-maxima of every GEMM output come from the producing kernel's epilogue, so each intermediate is read
+    // ONCE by oz_slice_both instead of by a row slicer, (a column-maximum pass,) and a transposed slicer.
+    // EGP_OZ_FUSED_SLICE=0 keeps the separate passes (bit-identical results; tests compare the two).
+    const bool fused = egp_oz_mlp_set_fused_slicing(-1) != 0;
     const long long part_bytes = P.part_bytes;
     char *xlocal = P.xlocal;
     const long long cmax_bytes = (hmax + in + od + 16) * 8LL;
@@ -316,20 +333,35 @@ int egp_oz_mlp_step_f64(const EgpMlpNet *net, const double *d_x, int64_t ldx, in
         GemmOut o;
         // ---- forward
         o = GemmOut(); o.C = a1; o.ldc = h1; o.bias = net->d_b1; o.relu = 1;
-        OZ_TRY(gemm(xs.q, xs.e, m, W1s.q, W1s.e, h1, kin, S, o, st));
         if (bwd) EGP_CUDA(cudaMemsetAsync(cmax[3], 0, cmax_bytes, st));
-        OZ_TRY(slice_rows(a1, m, h1, h1, S, a1s.q, kh1, a1s.e, bwd ? cmax[3] : nullptr, st));
-        if (bwd) OZ_TRY(slice_colsT(a1, m, h1, h1, S, cmax[3], a1T.q, mp, a1T.e, 1, st));
+        if (bwd && fused) { EGP_CUDA(cudaMemsetAsync(rmax, 0, m * 4, st)); o.rowmax = rmax; o.colmax = cmax[3]; }
+        OZ_TRY(gemm(xs.q, xs.e, m, W1s.q, W1s.e, h1, kin, S, o, st));
+        if (bwd && fused) {
+            OZ_TRY(slice_both(a1, m, h1, h1, S, rmax, cmax[3], a1s.q, kh1, a1s.e, a1T.q, mp, a1T.e, 1, st));
+        } else {
+            OZ_TRY(slice_rows(a1, m, h1, h1, S, a1s.q, kh1, a1s.e, bwd ? cmax[3] : nullptr, st));
+            if (bwd) OZ_TRY(slice_colsT(a1, m, h1, h1, S, cmax[3], a1T.q, mp, a1T.e, 1, st));
+        }
         o = GemmOut(); o.C = a2; o.ldc = h2; o.bias = net->d_b2; o.relu = 1;
+        const bool a2_fused = bwd && fused && !head1;
+        if (a2_fused) {
+            EGP_CUDA(cudaMemsetAsync(cmax[4], 0, cmax_bytes, st));
+            EGP_CUDA(cudaMemsetAsync(rmax, 0, m * 4, st));
+            o.rowmax = rmax; o.colmax = cmax[4];
+        }
         OZ_TRY(gemm(a1s.q, a1s.e, m, W2s.q, W2s.e, h2, kh1, S, o, st));
         double *yc = d_y ? d_y + r0 * od : ybuf;
         if (head1) {
             head1_fwd_kernel<<<head_blocks, 32 * HEAD_WARPS, 0, st>>>(a2, m, h2, net->d_W3, net->d_b3, yc);
             EGP_CHECK_LAUNCH("head1_fwd_kernel");
         } else {
-            if (bwd) EGP_CUDA(cudaMemsetAsync(cmax[4], 0, cmax_bytes, st));
-            OZ_TRY(slice_rows(a2, m, h2, h2, S, a2s.q, kh2, a2s.e, bwd ? cmax[4] : nullptr, st));
-            if (bwd) OZ_TRY(slice_colsT(a2, m, h2, h2, S, cmax[4], a2T.q, mp, a2T.e, 1, st));
+            if (a2_fused) {
+                OZ_TRY(slice_both(a2, m, h2, h2, S, rmax, cmax[4], a2s.q, kh2, a2s.e, a2T.q, mp, a2T.e, 1, st));
+            } else {
+                if (bwd) EGP_CUDA(cudaMemsetAsync(cmax[4], 0, cmax_bytes, st));
+                OZ_TRY(slice_rows(a2, m, h2, h2, S, a2s.q, kh2, a2s.e, bwd ? cmax[4] : nullptr, st));
+                if (bwd) OZ_TRY(slice_colsT(a2, m, h2, h2, S, cmax[4], a2T.q, mp, a2T.e, 1, st));
+            }
             o = GemmOut(); o.C = yc; o.ldc = od; o.bias = net->d_b3;
             OZ_TRY(gemm(a2s.q, a2s.e, m, W3s.q, W3s.e, od, kh2, S, o, st));
         }
@@ -364,8 +396,9 @@ int egp_oz_mlp_step_f64(const EgpMlpNet *net, const double *d_x, int64_t ldx, in
         };
         if (head1) {
             if ((long long)head_blocks * (h2 + 1) * 8 > part_bytes) { set_error("egp_oz_mlp_step_f64: head workspace"); return EGP_EINVAL; }
-            uint32_t *rmx = nullptr;
-            unsigned long long *cmx = nullptr;
+            EGP_CUDA(cudaMemsetAsync(cmax[6], 0, cmax_bytes, st));
+            uint32_t *rmx = fused ? rmax : nullptr;
+            unsigned long long *cmx = fused ? cmax[6] : nullptr;
             const int jn = (h2 + 31) / 32;
             if (jn <= 4) head1_bwd_kernel<4><<<head_blocks, 32 * HEAD_WARPS, 0, st>>>(a2, dy, m, h2, net->d_W3, d2, part, rmx, cmx);
             else if (jn <= 8) head1_bwd_kernel<8><<<head_blocks, 32 * HEAD_WARPS, 0, st>>>(a2, dy, m, h2, net->d_W3, d2, part, rmx, cmx);
@@ -379,24 +412,38 @@ int egp_oz_mlp_step_f64(const EgpMlpNet *net, const double *d_x, int64_t ldx, in
             OZ_TRY(slice_rows(dy, m, od, od, S, dys.q, kod, dys.e, cmax[5], st));
             OZ_TRY(slice_colsT(dy, m, od, od, S, cmax[5], dyT.q, mp, dyT.e, 0, st));
             OZ_TRY(wgrad(a2T, h2, dyT, od, net->d_gW3, net->d_gb3));
+            EGP_CUDA(cudaMemsetAsync(cmax[6], 0, cmax_bytes, st));
             o = GemmOut(); o.C = d2; o.ldc = h2; o.mask = a2; o.ldm = h2;
+            if (fused) { EGP_CUDA(cudaMemsetAsync(rmax, 0, m * 4, st)); o.rowmax = rmax; o.colmax = cmax[6]; }
             OZ_TRY(gemm(dys.q, dys.e, m, W3T.q, W3T.e, h2, kod, S, o, st));
         }
-        EGP_CUDA(cudaMemsetAsync(cmax[6], 0, cmax_bytes, st));
-        OZ_TRY(slice_rows(d2, m, h2, h2, S, d2s.q, kh2, d2s.e, cmax[6], st));
-        OZ_TRY(slice_colsT(d2, m, h2, h2, S, cmax[6], d2T.q, mp, d2T.e, 0, st));
+        if (fused) {
+            OZ_TRY(slice_both(d2, m, h2, h2, S, rmax, cmax[6], d2s.q, kh2, d2s.e, d2T.q, mp, d2T.e, 0, st));
+        } else {
+            OZ_TRY(slice_rows(d2, m, h2, h2, S, d2s.q, kh2, d2s.e, cmax[6], st));
+            OZ_TRY(slice_colsT(d2, m, h2, h2, S, cmax[6], d2T.q, mp, d2T.e, 0, st));
+        }
         OZ_TRY(wgrad(a1T, h1, d2T, h2, net->d_gW2, net->d_gb2));
-        o = GemmOut(); o.C = d1; o.ldc = h1; o.mask = a1; o.ldm = h1;
-        OZ_TRY(gemm(d2s.q, d2s.e, m, W2T.q, W2T.e, h1, kh2, S, o, st));
         EGP_CUDA(cudaMemsetAsync(cmax[7], 0, cmax_bytes, st));
+        o = GemmOut(); o.C = d1; o.ldc = h1; o.mask = a1; o.ldm = h1;
+        if (fused) {
+            o.colmax = cmax[7];
+            if (dxc > 0) { EGP_CUDA(cudaMemsetAsync(rmax, 0, m * 4, st)); o.rowmax = rmax; }
+        }
+        OZ_TRY(gemm(d2s.q, d2s.e, m, W2T.q, W2T.e, h1, kh2, S, o, st));
         if (dxc > 0) {
-            OZ_TRY(slice_rows(d1, m, h1, h1, S, d1s.q, kh1, d1s.e, cmax[7], st));
+            if (fused) {
+                OZ_TRY(slice_both(d1, m, h1, h1, S, rmax, cmax[7], d1s.q, kh1, d1s.e, d1T.q, mp, d1T.e, 0, st));
+            } else {
+                OZ_TRY(slice_rows(d1, m, h1, h1, S, d1s.q, kh1, d1s.e, cmax[7], st));
+                OZ_TRY(slice_colsT(d1, m, h1, h1, S, cmax[7], d1T.q, mp, d1T.e, 0, st));
+            }
             o = GemmOut(); o.C = net->d_dx + r0 * dxc; o.ldc = dxc;
             OZ_TRY(gemm(d1s.q, d1s.e, m, W1Tc.q, W1Tc.e, dxc, kh1, S, o, st));
         } else {
-            OZ_TRY(col_absmax(d1, m, h1, h1, cmax[7], st));
+            if (!fused) OZ_TRY(col_absmax(d1, m, h1, h1, cmax[7], st));
+            OZ_TRY(slice_colsT(d1, m, h1, h1, S, cmax[7], d1T.q, mp, d1T.e, 0, st));
         }
-        OZ_TRY(slice_colsT(d1, m, h1, h1, S, cmax[7], d1T.q, mp, d1T.e, 0, st));
         OZ_TRY(wgrad(xT, in, d1T, h1, net->d_gW1, net->d_gb1));
     }
 #undef OZ_TRY

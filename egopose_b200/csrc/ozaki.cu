@@ -378,6 +378,124 @@ oz_slice_colsT_kernel(const double *__restrict__ x, long long N, int F, long lon
     }
 }
 
+
+// packed int8 digits of four elements for all S slices
+template <int S>
+__device__ __forceinline__ void oz_slice4(const double (&v)[4], double scale, uint32_t (&pk)[S]) {
+    if constexpr (RB == 7) {
+        unsigned ylo[4], yhi[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) oz_y<S>(v[j], scale, ylo[j], yhi[j]);
+#pragma unroll
+        for (int t = 0; t < S; t++) pk[t] = oz_pack4<S>(ylo, yhi, t);
+    } else {
+#pragma unroll
+        for (int t = 0; t < S; t++) pk[t] = 0u;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int q[S];
+            oz_digits<S>(v[j], scale, q);
+#pragma unroll
+            for (int t = 0; t < S; t++) pk[t] |= (uint32_t)(q[t] & 255) << (8 * j);
+        }
+    }
+}
+
+// BOTH slice orientations of x [N][F] from ONE read: the transposed column-scaled slices of oz_slice_colsT_kernel and the
+// row-scaled slices of oz_slice_rows_kernel, when the row and column abs-maxima are already known (the producing GEMM's
+// epilogue or the value head's backward kernel recorded them).  Same tiles, loader and column rotation as the transposed
+// slicer; after the transposed pass over a 128 x 32 tile, warp w re-reads rows 16 w .. 16 w + 15 of the tile (lane ->
+// row l / 8, features 4 (l % 8) ..) and writes 4 bytes per slice: 8 lanes fill one 32-byte sector of a slice row (the row
+// pitch Kp is a multiple of 32).  Columns F .. Kp - 1 come out as zero digits (zero-filled loads).  The results are
+// bit-identical to the two separate kernels (same exponents, same digit arithmetic).
+template <int S>
+__global__ void __launch_bounds__(256)
+oz_slice_both_kernel(const double *__restrict__ x, long long N, int F, long long ldx, const int32_t *__restrict__ exps,
+                     int8_t *__restrict__ out, long long Np, int ones_row, const uint32_t *__restrict__ rowmax,
+                     int8_t *__restrict__ outR, int Kp, int32_t *__restrict__ expsR) {
+    extern __shared__ __align__(16) double colst_tile[];           // [2][128][32], columns rotated by 2 per 16-row group
+    const int f0 = blockIdx.x * 32;         // panels vary fastest: the blocks that fill the sectors of one slice row run together
+    const int FT = F + (ones_row ? 1 : 0);
+    const long long ntile = (Np + 127) / 128;
+    const long long t0 = (long long)blockIdx.y * COLST_TPB;
+    const long long t1 = t0 + COLST_TPB < ntile ? t0 + COLST_TPB : ntile;
+    const int lfl = threadIdx.x & 31, lrl = threadIdx.x >> 5;       // loader: feature lane, 8 rows per pass
+    auto issue = [&](long long tile_idx, int buf) {
+        double *tb = colst_tile + buf * (128 * 32);
+        const long long n0 = tile_idx * 128;
+        const int f = f0 + lfl;
+#pragma unroll 4
+        for (int r = lrl; r < 128; r += 8) {
+            const long long n = n0 + r;
+            double *dst = tb + r * 32 + ((lfl + 2 * (r >> 4)) & 31);
+            const bool ok = n < N && f < F;
+            cp_async8(dst, ok ? x + n * ldx + f : x, ok);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    const int g = threadIdx.x & 7, fl = threadIdx.x >> 3;
+    const int f = f0 + fl;
+    const int fc = (fl + 2 * g) & 31;
+    const double scale = f < FT ? pow2(RB * S - 1 - exps[f]) : 0.0;
+    const bool ones = ones_row && f == F;
+    // row pass: warp lrl owns tile rows 16 lrl .., lane -> (row lfl / 8 of a 4-row step, feature group lfl % 8)
+    const int rfg = lfl & 7, rc0 = f0 + 4 * rfg;
+    const int rp0 = (4 * rfg + 2 * lrl) & 31, rp1 = (4 * rfg + 2 + 2 * lrl) & 31;
+    if (t0 < t1) issue(t0, 0);
+    for (long long ti = t0; ti < t1; ti++) {
+        const int buf = (int)((ti - t0) & 1);
+        if (ti + 1 < t1) {
+            issue(ti + 1, buf ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        const double *tb = colst_tile + buf * (128 * 32);
+        const long long nb = ti * 128 + g * 16;
+        if (f < FT && nb < Np) {
+            uint32_t pk[S][4];
+#pragma unroll
+            for (int jq = 0; jq < 4; jq++) {
+                double v[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    v[j] = tb[(g * 16 + jq * 4 + j) * 32 + fc];
+                    if (ones) v[j] = (nb + jq * 4 + j < N) ? 1.0 : 0.0;
+                }
+                uint32_t p4[S];
+                oz_slice4<S>(v, scale, p4);
+#pragma unroll
+                for (int t = 0; t < S; t++) pk[t][jq] = p4[t];
+            }
+#pragma unroll
+            for (int t = 0; t < S; t++)
+                *reinterpret_cast<uint4 *>(out + ((size_t)t * FT + f) * Np + nb) = make_uint4(pk[t][0], pk[t][1], pk[t][2], pk[t][3]);
+        }
+        if (rc0 < Kp) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int r = lrl * 16 + i * 4 + (lfl >> 3);
+                const long long n = ti * 128 + r;
+                if (n < N) {
+                    const int e = oz_exponent_hi(rowmax[n]);
+                    if (blockIdx.x == 0 && rfg == 0) expsR[n] = e;
+                    const double rscale = pow2(RB * S - 1 - e);
+                    const double2 a0 = *reinterpret_cast<const double2 *>(tb + r * 32 + rp0);
+                    const double2 a1 = *reinterpret_cast<const double2 *>(tb + r * 32 + rp1);
+                    const double v[4] = {a0.x, a0.y, a1.x, a1.y};
+                    uint32_t p4[S];
+                    oz_slice4<S>(v, rscale, p4);
+#pragma unroll
+                    for (int t = 0; t < S; t++)
+                        *reinterpret_cast<uint32_t *>(outR + ((size_t)t * N + n) * Kp + rc0) = p4[t];
+                }
+            }
+        }
+        __syncthreads();                                            // the buffer is refilled two iterations later
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // PTX wrappers (sm_100a)
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -511,6 +629,8 @@ struct GemmArgs {
     int smallk;                 // contraction per split <= 448: int32 pre-merge of neighbouring accumulators is exact
     int mask_vec;               // mask rows can be read with 16-byte loads
     int tma_store;              // output through shared memory + TMA (needs even ldc and a 16-byte aligned base)
+    uint32_t *rowmax;           // optional [M]: high word of max_n |C[m][n]| (atomicMax, zeroed by the caller)
+    unsigned long long *colmax; // optional [N]: bit pattern (high word << 32) of max_m |C[m][n]| (atomicMax, zeroed by the caller)
 };
 
 template <int S, int BN>
@@ -697,6 +817,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #endif
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             double hv[HC];
+            uint32_t hrow = 0u;                                        // running |.| maximum of this thread's row (high words)
 #pragma unroll
             for (int c0 = 0; c0 < HC; c0 += 8) {
                 int acc[S][8];
@@ -755,6 +876,22 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                 }
+                if (g.rowmax || g.colmax) {
+                    // abs-max of the FINAL values for the slicers of this output (high words order like the doubles): the
+                    // consumer reads C once instead of once per orientation plus a reduction pass
+                    uint32_t hcol = 0u;
+#pragma unroll
+                    for (int jj = 0; jj < 8; jj++) {
+                        const uint32_t h = row_ok ? ((uint32_t)__double2hiint(v[jj]) & 0x7fffffffu) : 0u;
+                        hrow = max(hrow, h);
+                        if (g.colmax) {
+                            const uint32_t cm = __reduce_max_sync(0xffffffffu, h);
+                            if (lane == jj) hcol = cm;
+                        }
+                    }
+                    if (g.colmax && lane < 8 && colb + lane < g.N && hcol > 0u)
+                        atomicMax(g.colmax + colb + lane, (unsigned long long)hcol << 32);
+                }
                 if (g.tma_store) {
                     uint8_t *buf = obuf + (nstore & 1) * 2048;
                     if (nstore >= 2) {                                  // the store that last read this buffer has drained it
@@ -779,6 +916,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (colb + jj < g.N) crow[colb + jj] = v[jj];
                 }
             }
+            if (g.rowmax && row_ok && hrow > 0u) atomicMax(g.rowmax + row, hrow);
 #ifdef OZ_PROFILE
             e_post += clock64() - e0;
 #endif
@@ -934,6 +1072,7 @@ int gemm(const int8_t *a, const int32_t *ea, long long m, const int8_t *b, const
     } else {
         if (!o.C || !ea || !eb || o.ldc < n) { set_error("egp_oz_gemm_f64: bad output argument"); return EGP_EINVAL; }
         g.partial = 0; g.C = o.C; g.ldc = o.ldc;
+        g.rowmax = o.rowmax; g.colmax = o.colmax;
     }
     o.splits_used = splits;
     g.smallk = RB == 7 && (long long)g.kb_per_split * BK <= 448;
@@ -1079,6 +1218,39 @@ int slice_colsT(const double *x, long long n, int f, long long ldx, int S, const
     return EGP_OK;
 }
 
+
+template <int S>
+static int launch_both(dim3 grid, int smem, const double *x, long long n, int f, long long ldx, const int32_t *exps, int8_t *out,
+                       long long np, int ones_row, const uint32_t *rowmax, int8_t *outR, int kp, int32_t *expsR, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        EGP_CUDA(cudaFuncSetAttribute(oz_slice_both_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr = true;
+    }
+    oz_slice_both_kernel<S><<<grid, 256, smem, st>>>(x, n, f, ldx, exps, out, np, ones_row, rowmax, outR, kp, expsR);
+    return EGP_OK;
+}
+
+int slice_both(const double *x, long long n, int f, long long ldx, int S, const uint32_t *rowmax, const unsigned long long *colmax,
+               int8_t *outR, int kp, int32_t *expsR, int8_t *outT, long long np, int32_t *expsT, int ones_row, cudaStream_t st) {
+    if (!x || !outR || !expsR || !outT || !expsT || !rowmax || !colmax || n < 1 || f < 1 || ldx < f || np < n || (np & 15) || kp < f ||
+        (kp & 31) || kp > 768) {
+        set_error("egp_oz_slice_both_f64: bad argument (np %lld >= n multiple of 16, kp %d >= f multiple of 32)", np, kp);
+        return EGP_EINVAL;
+    }
+    const int ft = f + (ones_row ? 1 : 0);
+    oz_col_exps_kernel<<<(ft + 127) / 128, 128, 0, st>>>(colmax, f, ones_row, expsT);
+    const long long ntile = (np + 127) / 128;
+    dim3 grid((unsigned)((ft + 31) / 32), (unsigned)((ntile + COLST_TPB - 1) / COLST_TPB));
+    if (grid.y > 65535u) { set_error("egp_oz_slice_both_f64: more than %d rows", 65535 * COLST_TPB * 128); return EGP_ESIZE; }
+    const int smem = 2 * 128 * 32 * 8;
+    int rc = EGP_OK;
+    OZ_DISPATCH_S(S, rc = launch_both<S_>(grid, smem, x, n, f, ldx, expsT, outT, np, ones_row, rowmax, outR, kp, expsR, st));
+    if (rc) return rc;
+    EGP_CHECK_LAUNCH("oz_slice_both_kernel");
+    return EGP_OK;
+}
+
 }  // namespace oz
 }  // namespace egp
 
@@ -1111,6 +1283,20 @@ int64_t egp_oz_gemm_work_bytes(int64_t m, int n, int64_t kp, int n_slices) {
 int egp_oz_gemm_f64(const int8_t *d_a, const int32_t *d_ea, int64_t m, const int8_t *d_b, const int32_t *d_eb, int n, int64_t kp,
                     int n_slices, const double *d_bias, int relu, const double *d_mask, int64_t ldm, double *d_c, int64_t ldc,
                     void *d_work, int64_t work_bytes, void *stream) {
+    return egp_oz_gemm_max_f64(d_a, d_ea, m, d_b, d_eb, n, kp, n_slices, d_bias, relu, d_mask, ldm, d_c, ldc, nullptr, nullptr, d_work,
+                               work_bytes, stream);
+}
+
+int egp_oz_slice_both_f64(const double *d_x, int64_t n, int f, int64_t ldx, int n_slices, const uint32_t *d_rowmax,
+                          const double *d_colmax, int8_t *d_out_rows, int kp, int32_t *d_exps_rows, int8_t *d_out_t, int64_t np,
+                          int32_t *d_exps_t, int ones_row, void *stream) {
+    return slice_both(d_x, n, f, ldx, n_slices, d_rowmax, (const unsigned long long *)d_colmax, d_out_rows, kp, d_exps_rows, d_out_t,
+                      np, d_exps_t, ones_row, (cudaStream_t)stream);
+}
+
+int egp_oz_gemm_max_f64(const int8_t *d_a, const int32_t *d_ea, int64_t m, const int8_t *d_b, const int32_t *d_eb, int n, int64_t kp,
+                        int n_slices, const double *d_bias, int relu, const double *d_mask, int64_t ldm, double *d_c, int64_t ldc,
+                        uint32_t *d_rowmax, double *d_colmax, void *d_work, int64_t work_bytes, void *stream) {
     if (!d_a || !d_b || !d_ea || !d_eb || !d_c || m < 1 || n < 1 || ldc < n) {
         set_error("egp_oz_gemm_f64: bad argument (m %lld n %d kp %lld ldc %lld)", (long long)m, n, (long long)kp, (long long)ldc);
         return EGP_EINVAL;
@@ -1120,8 +1306,10 @@ int egp_oz_gemm_f64(const int8_t *d_a, const int32_t *d_ea, int64_t m, const int
     o.C = d_c; o.ldc = ldc; o.bias = d_bias; o.relu = relu; o.mask = d_mask; o.ldm = ldm;
     const int splits = choose_splits(m, n, kp, n_slices);
     if (splits > 1) {
+        if (d_rowmax || d_colmax) { set_error("egp_oz_gemm_max_f64: abs-maxima are not recorded on the split-K path"); return EGP_EINVAL; }
         o.force_splits = splits; o.work = (double *)d_work; o.work_bytes = work_bytes;
     }
+    o.rowmax = d_rowmax; o.colmax = (unsigned long long *)d_colmax;
     int rc = gemm(d_a, d_ea, m, d_b, d_eb, n, kp, n_slices, o, st);
     if (rc) return rc;
     if (splits > 1) {

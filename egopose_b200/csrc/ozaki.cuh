@@ -35,6 +35,11 @@ int col_absmax(const double *x, long long n, int f, long long ldx, unsigned long
 int slice_colsT(const double *x, long long n, int f, long long ldx, int S, const unsigned long long *colmax, int8_t *out,
                 long long np, int32_t *exps, int ones_row, cudaStream_t st);
 
+// both orientations from one read of x, given the row abs-max high words (rowmax [n]) and the column abs-max bit patterns:
+// row slices int8 [S][n][kp] + expsR[n] (kp multiple of 32), transposed slices int8 [S][f (+1)][np] + expsT[f (+1)]
+int slice_both(const double *x, long long n, int f, long long ldx, int S, const uint32_t *rowmax, const unsigned long long *colmax,
+               int8_t *outR, int kp, int32_t *expsR, int8_t *outT, long long np, int32_t *expsT, int ones_row, cudaStream_t st);
+
 struct GemmOut {
     double *C = nullptr;            // [m][ldc]
     long long ldc = 0;
@@ -46,6 +51,9 @@ struct GemmOut {
     double *work = nullptr;
     long long work_bytes = 0;
     int force_splits = 0;           // > 0: use exactly this many splits (and write partials even when 1)
+    // abs-maxima of the final output for its slicers (optional; zeroed by the caller; not on the split-K path):
+    uint32_t *rowmax = nullptr;            // [m] high words (atomicMax)
+    unsigned long long *colmax = nullptr;  // [n] bit patterns, high word << 32 (atomicMax) - same encoding as slice_rows' colmax
     int splits_used = 0;            // out
     long long ldp = 0;              // out
 };

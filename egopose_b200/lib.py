@@ -106,6 +106,7 @@ SYMBOLS = {
     'egp_gae_work_bytes': (_i64, [_i64]),
     'egp_gae_f64': (_int, [_vp, _vp, _vp, _d, _d, _i64, _vp, _vp, _vp, _vp, _vp]),
     'egp_gae_set_onepass_min': (_i64, [_i64]),
+    'egp_oz_mlp_set_fused_slicing': (_int, [_int]),
     'egp_standardize_f64': (_int, [_vp, _i64, _vp, _vp]),
     'egp_gauss_logp_f64': (_int, [_vp, _vp, _vp, _i64, _int, _vp, _vp]),
     'egp_ppo_loss_grad_f64': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _i64, _int, _vp, _vp, _vp, _vp]),
@@ -125,6 +126,8 @@ SYMBOLS = {
     'egp_oz_slice_cols_t_f64': (_int, [_vp, _i64, _int, _i64, _int, _vp, _vp, _i64, _vp, _int, _vp]),
     'egp_oz_gemm_work_bytes': (_i64, [_i64, _int, _i64, _int]),
     'egp_oz_gemm_f64': (_int, [_vp, _vp, _i64, _vp, _vp, _int, _i64, _int, _vp, _int, _vp, _i64, _vp, _i64, _vp, _i64, _vp]),
+    'egp_oz_gemm_max_f64': (_int, [_vp, _vp, _i64, _vp, _vp, _int, _i64, _int, _vp, _int, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _vp]),
+    'egp_oz_slice_both_f64': (_int, [_vp, _i64, _int, _i64, _int, _vp, _vp, _vp, _int, _vp, _vp, _i64, _vp, _int, _vp]),
     'egp_oz_mlp_chunk_rows': (_i64, []),
     'egp_oz_mlp_work_bytes': (_i64, [_int, _int, _int, _int, _i64, _int]),
     'egp_oz_mlp_xcache_bytes': (_i64, [_int, _i64, _i64, _int]),
@@ -689,9 +692,28 @@ def oz_slice_colsT(x, n_slices, colmax, out=None, ones_row=False):
 _oz_work = {}
 
 
-def oz_gemm(a, ea, b, eb, bias=None, relu=False, out=None, mask=None):
+def oz_slice_both(x, n_slices, rowmax, colmax, ones_row=False):
+    """x [N, F] float64 -> ((row slices [S, N, Kp32], exps [N]), (transposed slices [S, F (+1), Np], exps [F (+1)])) from ONE read,
+    given rowmax ([N] int32/uint32 high words of the row abs-maxima) and colmax ([F] float64 bit patterns)"""
+    global launches
+    import torch
+    N, F = x.shape
+    if x.stride(1) != 1:
+        raise EgpError('oz_slice_both: x must be row-major')
+    kp = (F + 31) // 32 * 32
+    npad = _pad16(N)
+    ft = F + (1 if ones_row else 0)
+    r = (torch.empty((n_slices, N, kp), dtype=torch.int8, device=x.device), torch.empty((N,), dtype=torch.int32, device=x.device))
+    t = (torch.empty((n_slices, ft, npad), dtype=torch.int8, device=x.device), torch.empty((ft,), dtype=torch.int32, device=x.device))
+    check(load().egp_oz_slice_both_f64(ptr(x), N, F, x.stride(0), n_slices, ptr(rowmax), ptr(colmax), ptr(r[0]), kp, ptr(r[1]),
+                                       ptr(t[0]), npad, ptr(t[1]), int(bool(ones_row)), stream_ptr()), 'egp_oz_slice_both_f64')
+    launches += 2
+    return r, t
+
+
+def oz_gemm(a, ea, b, eb, bias=None, relu=False, out=None, mask=None, rowmax=None, colmax=None):
     """C [M, N] = A B^T (+ bias, relu; * (mask > 0)) from row-scaled slices a [S, M, Kp], b [S, N, Kp] and exponents
-    ea [M], eb [N]"""
+    ea [M], eb [N]; rowmax ([M] int32, zeroed) / colmax ([N] float64, zeroed) optionally receive the abs-maxima of C"""
     global launches
     import torch
     S, M, kp = a.shape
@@ -708,9 +730,9 @@ def oz_gemm(a, ea, b, eb, bias=None, relu=False, out=None, mask=None):
         if work is None or work.numel() < need:
             work = torch.empty(need, dtype=torch.uint8, device=a.device)
             _oz_work[a.device] = work
-    check(lib.egp_oz_gemm_f64(ptr(a), ptr(ea), M, ptr(b), ptr(eb), N, kp, S, ptr(bias), int(bool(relu)), ptr(mask),
-                              mask.stride(0) if mask is not None else 0, ptr(out), out.stride(0), ptr(work), need, stream_ptr()),
-          'egp_oz_gemm_f64')
+    check(lib.egp_oz_gemm_max_f64(ptr(a), ptr(ea), M, ptr(b), ptr(eb), N, kp, S, ptr(bias), int(bool(relu)), ptr(mask),
+                                  mask.stride(0) if mask is not None else 0, ptr(out), out.stride(0), ptr(rowmax), ptr(colmax),
+                                  ptr(work), need, stream_ptr()), 'egp_oz_gemm_max_f64')
     launches += 2 if need else 1
     return out
 

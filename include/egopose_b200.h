@@ -317,6 +317,20 @@ int64_t egp_oz_gemm_work_bytes(int64_t m, int n, int64_t kp, int n_slices);
 int egp_oz_gemm_f64(const int8_t *d_a, const int32_t *d_ea, int64_t m, const int8_t *d_b, const int32_t *d_eb, int n,
                     int64_t kp, int n_slices, const double *d_bias, int relu, const double *d_mask, int64_t ldm,
                     double *d_c, int64_t ldc, void *d_work, int64_t work_bytes, void *stream);
+/* The same product; additionally the epilogue records the abs-maxima of the FINAL output (after bias / relu / mask) for
+ * the slicers of C: d_rowmax [m] = high 32 bits of max_n |C[m][n]|, d_colmax [n] = bit pattern (high word << 32) of
+ * max_m |C[m][n]| - both optional, combined with atomicMax, so the caller zeroes them; not available with split-K. */
+int egp_oz_gemm_max_f64(const int8_t *d_a, const int32_t *d_ea, int64_t m, const int8_t *d_b, const int32_t *d_eb, int n,
+                        int64_t kp, int n_slices, const double *d_bias, int relu, const double *d_mask, int64_t ldm,
+                        double *d_c, int64_t ldc, uint32_t *d_rowmax, double *d_colmax, void *d_work, int64_t work_bytes,
+                        void *stream);
+/* BOTH orientations from one read of d_x [n][f], given its recorded maxima (egp_oz_gemm_max_f64, or d_colmax from
+ * egp_oz_slice_rows_f64 / egp_oz_colmax_f64 and d_rowmax = high words of the row maxima): row slices d_out_rows [S][n][kp]
+ * (kp >= f, multiple of 32) + d_exps_rows [n] exactly as egp_oz_slice_rows_f64 writes them, transposed slices
+ * d_out_t [S][f + ones_row][np] + d_exps_t [f + ones_row] exactly as egp_oz_slice_cols_t_f64 writes them. */
+int egp_oz_slice_both_f64(const double *d_x, int64_t n, int f, int64_t ldx, int n_slices, const uint32_t *d_rowmax,
+                          const double *d_colmax, int8_t *d_out_rows, int kp, int32_t *d_exps_rows, int8_t *d_out_t, int64_t np,
+                          int32_t *d_exps_t, int ones_row, void *stream);
 
 /* --- chunked MLP forward / loss / backward on the int8 tensor cores (egopose_b200/csrc/oz_mlp.cu) ------------
  * One optimisation step's forward + loss + backward of a two-hidden-layer relu MLP (models/mlp.py:22-25 trunk,
@@ -348,6 +362,10 @@ typedef struct {
 } EgpMlpLoss;
 
 int64_t egp_oz_mlp_chunk_rows(void);   /* 128 rows x number of SMs */
+/* on = 1 (default): the GEMM epilogues / the value head's backward kernel record the row and column abs-maxima of their
+ * outputs, and every intermediate of egp_oz_mlp_step_f64 is sliced in BOTH orientations from one read; 0: separate row,
+ * column-maximum and transposed passes (bit-identical results); negative: query.  Returns the setting in force. */
+int egp_oz_mlp_set_fused_slicing(int on);
 int64_t egp_oz_mlp_work_bytes(int in_dim, int h1, int h2, int out_dim, int64_t chunk_rows, int n_slices);
 int64_t egp_oz_mlp_xcache_bytes(int in_dim, int64_t n, int64_t chunk_rows, int n_slices);
 /* d_x [n][in_dim] (leading dimension ldx).  kind 0 writes y [n][out_dim] to d_y; kinds 1 / 2 write the six gradients

@@ -221,3 +221,82 @@ def test_mlp_step_input_gradient_matches_autograd(dxc):
     assert torch.allclose(dx, ref, rtol=1e-8, atol=1e-10 * ref.abs().max().item())
     for g, wt in zip(grads, Wt):
         assert torch.allclose(g, wt.grad, rtol=1e-8, atol=1e-10 * wt.grad.abs().max().item())
+
+
+@pytest.mark.parametrize('dims,n,chunk,dxc', [((243, 300, 300, 52), 3000, 1024, 0), ((243, 300, 300, 1), 2900, 1024, 0),
+                                              ((40, 64, 48, 1), 700, 256, 16), ((243, 512, 512, 52), 1500, 640, 24),
+                                              ((37, 50, 70, 3), 333, 128, 37)])
+def test_mlp_step_fused_slicing_is_bit_identical(dims, n, chunk, dxc):
+    """Producer-recorded abs-maxima + one-read two-orientation slicing (default) against the separate row / column-maximum /
+    transposed passes: the same exponents and digits, so every gradient must agree BIT FOR BIT."""
+    W = _weights(dims, 3)
+    torch.manual_seed(17)
+    x = torch.randn(n, dims[0], device=DEV, dtype=torch.float64)
+    x[5] = 0.0                                           # an all-zero sample row
+    od = dims[3]
+    if od == 1:
+        ls = dict(kind='value', returns=torch.randn(n, device=DEV, dtype=torch.float64), inv_n=1.0 / n)
+    else:
+        log_std = torch.full((od,), -2.3, device=DEV, dtype=torch.float64)
+        mu0 = _torch_mlp(W, x)
+        actions = mu0 + torch.exp(log_std) * torch.randn(n, od, device=DEV, dtype=torch.float64)
+        adv = torch.randn(n, device=DEV, dtype=torch.float64)
+        exps = (torch.rand(n, device=DEV) > 0.3).double()                # rows with zero gradient
+        ls = dict(kind='ppo', actions=actions, log_std=log_std, adv=adv,
+                  stats=torch.tensor([float(n), adv.mean().item(), ((adv - adv.mean()) ** 2).sum().item()], device=DEV, dtype=torch.float64),
+                  logp0=lib.gauss_logp(mu0 + 0.02 * torch.randn_like(mu0), actions, log_std), exps=exps, clip_eps=0.2,
+                  inv_count=1.0 / exps.sum().item(), dlogstd=None)
+    out = {}
+    L = lib.load()
+    prev = L.egp_oz_mlp_set_fused_slicing(-1)
+    try:
+        for mode in (0, 1):
+            assert L.egp_oz_mlp_set_fused_slicing(mode) == mode
+            oz = lib.OzMlp(*dims, n_slices=6, chunk_rows=chunk, device=DEV)
+            grads = [torch.full_like(w, float('nan')) for w in W]
+            loss = torch.zeros(1, device=DEV, dtype=torch.float64)
+            dx = torch.full((n, dxc), float('nan'), device=DEV, dtype=torch.float64) if dxc else None
+            oz.step(W, x, grads=grads, loss=dict(ls, loss=loss), dx=dx)
+            torch.cuda.synchronize()
+            out[mode] = (grads, loss.clone(), dx)
+    finally:
+        L.egp_oz_mlp_set_fused_slicing(prev)
+    assert abs(out[0][1].item() - out[1][1].item()) <= 1e-13 * abs(out[0][1].item())    # the loss is summed with atomics: order-dependent
+    for a, b in zip(out[0][0], out[1][0]):
+        assert torch.isfinite(a).all() and torch.equal(a, b)
+    if dxc:
+        assert torch.equal(out[0][2], out[1][2])
+
+
+@pytest.mark.parametrize('M,N,K,relu,mask', [(300, 300, 243, True, False), (1000, 512, 300, True, False), (129, 52, 64, False, False),
+                                             (700, 300, 52, False, True), (5, 7, 20, False, False), (2048, 512, 512, False, True)])
+def test_gemm_records_maxima_and_slice_both_matches_separate_slicers(M, N, K, relu, mask):
+    """egp_oz_gemm_max_f64 records the row / column abs-maxima of its FINAL output; egp_oz_slice_both_f64 then writes exactly the
+    bytes of egp_oz_slice_rows_f64 + egp_oz_slice_cols_t_f64 from one read."""
+    S = 6
+    torch.manual_seed(M + N)
+    a = torch.randn(M, K, device=DEV, dtype=torch.float64) * torch.exp(2 * torch.randn(M, 1, device=DEV, dtype=torch.float64))
+    b = torch.randn(N, K, device=DEV, dtype=torch.float64)
+    a[M // 2] = 0.0
+    bias = torch.randn(N, device=DEV, dtype=torch.float64) if relu else None
+    mk = torch.randn(M, N, device=DEV, dtype=torch.float64) if mask else None
+    sa, ea = lib.oz_slice_rows(a, S)
+    sb, eb = lib.oz_slice_rows(b, S)
+    ref = lib.oz_gemm(sa, ea, sb, eb, bias=bias, relu=relu, mask=mk)
+    rowmax = torch.zeros(M, dtype=torch.int32, device=DEV)
+    colmax = torch.zeros(N, dtype=torch.float64, device=DEV)
+    c = lib.oz_gemm(sa, ea, sb, eb, bias=bias, relu=relu, mask=mk, rowmax=rowmax, colmax=colmax)
+    assert torch.equal(c, ref)
+    hi = lambda t: (t.contiguous().view(torch.int64) >> 32).to(torch.int32)          # noqa: E731
+    assert torch.equal(rowmax, hi(c.abs().max(1).values))
+    assert torch.equal(hi(colmax), hi(c.abs().max(0).values))
+    assert (colmax.view(torch.int64) & 0xffffffff).eq(0).all()
+    for ones in (False, True):
+        cm = torch.zeros(N, dtype=torch.float64, device=DEV)
+        r_ref = lib.oz_slice_rows(c, S, colmax=cm)
+        t_ref = lib.oz_slice_colsT(c, S, cm, ones_row=ones)
+        (r, er), (t, et) = lib.oz_slice_both(c, S, rowmax, colmax, ones_row=ones)
+        assert torch.equal(er, r_ref[1]) and torch.equal(et, t_ref[1])
+        assert torch.equal(t, t_ref[0])
+        kp16 = r_ref[0].shape[2]
+        assert torch.equal(r[:, :, :kp16], r_ref[0]) and r[:, :, N:].eq(0).all()
