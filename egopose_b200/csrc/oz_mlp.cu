@@ -209,6 +209,7 @@ struct MlpPlan {
     unsigned long long *cmax[8];
     double *a1, *a2, *d1, *d2, *ybuf, *dy, *part;
     uint32_t *rmax;
+    unsigned long long *a1b, *a2b;      // relu sign bits of a1 / a2 (one word per row and half n-tile)
     long long part_bytes;
     char *xlocal;
     long long total;
@@ -229,6 +230,7 @@ static MlpPlan mlp_plan(char *base, int in, int h1, int h2, int od, long long M,
     P.a1 = B.take<double>(M * h1); P.a2 = B.take<double>(M * h2); P.d1 = B.take<double>(M * h1); P.d2 = B.take<double>(M * h2);
     P.ybuf = B.take<double>(M * od); P.dy = B.take<double>(M * od);
     P.rmax = B.take<uint32_t>(M);
+    P.a1b = B.take<unsigned long long>(M * 2 * gemm_ntiles(h1, S)); P.a2b = B.take<unsigned long long>(M * 2 * gemm_ntiles(h2, S));
     P.a1s = Sl{B.take<int8_t>(S * M * kh1), B.take<int32_t>(M)}; P.a2s = Sl{B.take<int8_t>(S * M * kh2), B.take<int32_t>(M)};
     P.d2s = Sl{B.take<int8_t>(S * M * kh2), B.take<int32_t>(M)}; P.dys = Sl{B.take<int8_t>(S * M * kod), B.take<int32_t>(M)};
     P.a1T = Sl{B.take<int8_t>(S * (h1 + 1) * MP), B.take<int32_t>(h1 + 16)}; P.a2T = Sl{B.take<int8_t>(S * (h2 + 1) * MP), B.take<int32_t>(h2 + 16)};
@@ -285,6 +287,7 @@ int egp_oz_mlp_step_f64(const EgpMlpNet *net, const double *d_x, int64_t ldx, in
     unsigned long long *const *cmax = P.cmax;
     double *a1 = P.a1, *a2 = P.a2, *d1 = P.d1, *d2 = P.d2, *ybuf = P.ybuf, *dy = P.dy, *part = P.part;
     uint32_t *rmax = P.rmax;
+    unsigned long long *a1b = P.a1b, *a2b = P.a2b;
     // Row / column abs-maxima of every GEMM output come from the producing kernel's epilogue, so each intermediate is read
     // ONCE by oz_slice_both instead of by a row slicer, (a column-maximum pass,) and a transposed slicer.
     // EGP_OZ_FUSED_SLICE=0 keeps the separate passes (bit-identical results; tests compare the two).
@@ -334,7 +337,7 @@ int egp_oz_mlp_step_f64(const EgpMlpNet *net, const double *d_x, int64_t ldx, in
         // ---- forward
         o = GemmOut(); o.C = a1; o.ldc = h1; o.bias = net->d_b1; o.relu = 1;
         if (bwd) EGP_CUDA(cudaMemsetAsync(cmax[3], 0, cmax_bytes, st));
-        if (bwd && fused) { EGP_CUDA(cudaMemsetAsync(rmax, 0, m * 4, st)); o.rowmax = rmax; o.colmax = cmax[3]; }
+        if (bwd && fused) { EGP_CUDA(cudaMemsetAsync(rmax, 0, m * 4, st)); o.rowmax = rmax; o.colmax = cmax[3]; o.relu_bits = a1b; }
         OZ_TRY(gemm(xs.q, xs.e, m, W1s.q, W1s.e, h1, kin, S, o, st));
         if (bwd && fused) {
             OZ_TRY(slice_both(a1, m, h1, h1, S, rmax, cmax[3], a1s.q, kh1, a1s.e, a1T.q, mp, a1T.e, 1, st));
@@ -347,7 +350,7 @@ int egp_oz_mlp_step_f64(const EgpMlpNet *net, const double *d_x, int64_t ldx, in
         if (a2_fused) {
             EGP_CUDA(cudaMemsetAsync(cmax[4], 0, cmax_bytes, st));
             EGP_CUDA(cudaMemsetAsync(rmax, 0, m * 4, st));
-            o.rowmax = rmax; o.colmax = cmax[4];
+            o.rowmax = rmax; o.colmax = cmax[4]; o.relu_bits = a2b;
         }
         OZ_TRY(gemm(a1s.q, a1s.e, m, W2s.q, W2s.e, h2, kh1, S, o, st));
         double *yc = d_y ? d_y + r0 * od : ybuf;
@@ -414,7 +417,7 @@ int egp_oz_mlp_step_f64(const EgpMlpNet *net, const double *d_x, int64_t ldx, in
             OZ_TRY(wgrad(a2T, h2, dyT, od, net->d_gW3, net->d_gb3));
             EGP_CUDA(cudaMemsetAsync(cmax[6], 0, cmax_bytes, st));
             o = GemmOut(); o.C = d2; o.ldc = h2; o.mask = a2; o.ldm = h2;
-            if (fused) { EGP_CUDA(cudaMemsetAsync(rmax, 0, m * 4, st)); o.rowmax = rmax; o.colmax = cmax[6]; }
+            if (fused) { EGP_CUDA(cudaMemsetAsync(rmax, 0, m * 4, st)); o.rowmax = rmax; o.colmax = cmax[6]; o.mask_bits = a2b; }
             OZ_TRY(gemm(dys.q, dys.e, m, W3T.q, W3T.e, h2, kod, S, o, st));
         }
         if (fused) {
@@ -427,7 +430,7 @@ int egp_oz_mlp_step_f64(const EgpMlpNet *net, const double *d_x, int64_t ldx, in
         EGP_CUDA(cudaMemsetAsync(cmax[7], 0, cmax_bytes, st));
         o = GemmOut(); o.C = d1; o.ldc = h1; o.mask = a1; o.ldm = h1;
         if (fused) {
-            o.colmax = cmax[7];
+            o.colmax = cmax[7]; o.mask_bits = a1b;
             if (dxc > 0) { EGP_CUDA(cudaMemsetAsync(rmax, 0, m * 4, st)); o.rowmax = rmax; }
         }
         OZ_TRY(gemm(d2s.q, d2s.e, m, W2T.q, W2T.e, h1, kh2, S, o, st));

@@ -38,6 +38,10 @@ namespace oz {
 
 constexpr int UMMA_K = 32;                      // K per tcgen05.mma for 8-bit operands
 constexpr int EPI_WARPS = 8;
+#ifndef OZ_OUT_BUFS
+#define OZ_OUT_BUFS 2
+#endif
+constexpr int OUT_BUFS = OZ_OUT_BUFS;               // 32 x 64 B output staging buffers per epilogue warp (TMA stores in flight)
 constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;   // warp 0: TMA producer, warp 1: MMA issuer, warps 2-9: epilogue
 constexpr int SMEM_LIMIT = 227 * 1024 - 2048;   // dynamic shared memory: 227 KB minus the static barriers
 constexpr int MAX_STAGES = 12;
@@ -629,6 +633,8 @@ struct GemmArgs {
     int smallk;                 // contraction per split <= 448: int32 pre-merge of neighbouring accumulators is exact
     int mask_vec;               // mask rows can be read with 16-byte loads
     int tma_store;              // output through shared memory + TMA (needs even ldc and a 16-byte aligned base)
+    unsigned long long *relu_bits;      // optional out [M][2 nt]: bit c of word 2 n_blk + half = (C[m][n_blk BN + half BN/2 + c] > 0)
+    const unsigned long long *mask_bits;  // optional in, same layout: replaces the float64 mask (one 8-byte load per thread and tile)
     uint32_t *rowmax;           // optional [M]: high word of max_n |C[m][n]| (atomicMax, zeroed by the caller)
     unsigned long long *colmax; // optional [N]: bit pattern (high word << 32) of max_m |C[m][n]| (atomicMax, zeroed by the caller)
 };
@@ -776,8 +782,8 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // (full sectors, clipped at the matrix edge by the tensor map); overlaps the next tile's MMAs.
         const int q = warp & 3, half = (warp - 2) >> 2;
         constexpr int HC = BN / 2;                                     // columns per warp
-        uint8_t *obuf = smem + (size_t)stages * STAGE + (size_t)(warp - 2) * 4096;
-        double *colc = reinterpret_cast<double *>(smem + (size_t)stages * STAGE + EPI_WARPS * 4096) + (warp - 2) * 2 * HC;
+        uint8_t *obuf = smem + (size_t)stages * STAGE + (size_t)(warp - 2) * (OUT_BUFS * 2048);
+        double *colc = reinterpret_cast<double *>(smem + (size_t)stages * STAGE + EPI_WARPS * (OUT_BUFS * 2048)) + (warp - 2) * 2 * HC;
         uint32_t tc = 0, nstore = 0;
 #ifdef OZ_PROFILE
         long long e_wait = 0, e_drain = 0, e_post = 0, e_tot = clock64(), e0;
@@ -808,6 +814,11 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 __syncwarp();
             }
+            uint32_t mb_lo = ~0u, mb_hi = ~0u, rb_lo = 0u, rb_hi = 0u;       // columns 0-31 | 32.. of this thread's half tile
+            if (g.mask_bits && row_ok) {
+                const unsigned long long mb = __ldcs(g.mask_bits + row * (2 * g.nt) + 2 * n_blk + half);
+                mb_lo = (uint32_t)mb; mb_hi = (uint32_t)(mb >> 32);
+            }
 #ifdef OZ_PROFILE
             e0 = clock64();
 #endif
@@ -818,6 +829,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             double hv[HC];
             uint32_t hrow = 0u;                                        // running |.| maximum of this thread's row (high words)
+            const uint32_t hmask = row_ok ? 0x7fffffffu : 0u;         // rows outside the matrix hold the bias only
 #pragma unroll
             for (int c0 = 0; c0 < HC; c0 += 8) {
                 int acc[S][8];
@@ -861,7 +873,19 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             v[jj] = __longlong_as_double(b);
                         }
                     }
-                    if (mrow) {
+                    if (g.relu_bits) {                                 // after the relu v >= +0: (v > 0) <=> any bit set
+#pragma unroll
+                        for (int jj = 0; jj < 8; jj++) {
+                            const uint32_t nz = ((uint32_t)__double2hiint(v[jj]) | (uint32_t)__double2loint(v[jj])) != 0u ? 1u : 0u;
+                            if (c0 + jj < 32) rb_lo |= nz << ((c0 + jj) & 31);
+                            else rb_hi |= nz << ((c0 + jj) & 31);
+                        }
+                    }
+                    if (g.mask_bits) {
+#pragma unroll
+                        for (int jj = 0; jj < 8; jj++)
+                            if (!(((c0 + jj < 32 ? mb_lo : mb_hi) >> ((c0 + jj) & 31)) & 1u)) v[jj] = 0.0;
+                    } else if (mrow) {
                         if (g.mask_vec && colb + 8 <= g.N) {
 #pragma unroll
                             for (int jj = 0; jj < 8; jj += 2) {
@@ -882,7 +906,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     uint32_t hcol = 0u;
 #pragma unroll
                     for (int jj = 0; jj < 8; jj++) {
-                        const uint32_t h = row_ok ? ((uint32_t)__double2hiint(v[jj]) & 0x7fffffffu) : 0u;
+                        const uint32_t h = (uint32_t)__double2hiint(v[jj]) & hmask;
                         hrow = max(hrow, h);
                         if (g.colmax) {
                             const uint32_t cm = __reduce_max_sync(0xffffffffu, h);
@@ -893,9 +917,9 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         atomicMax(g.colmax + colb + lane, (unsigned long long)hcol << 32);
                 }
                 if (g.tma_store) {
-                    uint8_t *buf = obuf + (nstore & 1) * 2048;
-                    if (nstore >= 2) {                                  // the store that last read this buffer has drained it
-                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    uint8_t *buf = obuf + (nstore % OUT_BUFS) * 2048;
+                    if (nstore >= OUT_BUFS) {                           // the store that last read this buffer has drained it
+                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(OUT_BUFS - 1) : "memory");
                         __syncwarp();
                     }
                     const uint32_t rb = smem_u32(buf) + lane * 64, sw = (lane >> 1) & 3;
@@ -917,6 +941,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             }
             if (g.rowmax && row_ok && hrow > 0u) atomicMax(g.rowmax + row, hrow);
+            if (g.relu_bits && row_ok) g.relu_bits[row * (2 * g.nt) + 2 * n_blk + half] = ((unsigned long long)rb_hi << 32) | rb_lo;
 #ifdef OZ_PROFILE
             e_post += clock64() - e0;
 #endif
@@ -975,7 +1000,7 @@ static int make_map_out(CUtensorMap *tm, const double *base, long long rows, int
     return EGP_OK;
 }
 
-constexpr int OUT_STAGE_BYTES = EPI_WARPS * 4096 + EPI_WARPS * 2 * 40 * 8;   // per epilogue warp: two 32 x 64 B staging buffers + (2^eb, bias) per column
+constexpr int OUT_STAGE_BYTES = EPI_WARPS * OUT_BUFS * 2048 + EPI_WARPS * 2 * 40 * 8;   // per epilogue warp: two 32 x 64 B staging buffers + (2^eb, bias) per column
 
 template <int S, int BN>
 static int launch_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC, GemmArgs g, cudaStream_t st) {
@@ -1009,6 +1034,11 @@ static inline int pick_bn(int n, int S) {
     if (force && atoi(force) == 80) return 80;
     const int t64 = (n + 63) / 64, t80 = (n + 79) / 80;
     return (t80 * 80 <= t64 * 64 || t80 < t64) ? 80 : 64;
+}
+
+int gemm_ntiles(int n, int S) {
+    const int bn = pick_bn(n, S);
+    return (n + bn - 1) / bn;
 }
 
 long long gemm_tiles(long long m, int n, int S) {
@@ -1073,6 +1103,9 @@ int gemm(const int8_t *a, const int32_t *ea, long long m, const int8_t *b, const
         if (!o.C || !ea || !eb || o.ldc < n) { set_error("egp_oz_gemm_f64: bad output argument"); return EGP_EINVAL; }
         g.partial = 0; g.C = o.C; g.ldc = o.ldc;
         g.rowmax = o.rowmax; g.colmax = o.colmax;
+        if (o.relu_bits && !o.relu) { set_error("egp_oz_gemm_f64: relu_bits needs relu"); return EGP_EINVAL; }
+        g.relu_bits = o.relu_bits; g.mask_bits = o.mask_bits;
+        if (g.mask_bits) g.mask = nullptr;
     }
     o.splits_used = splits;
     g.smallk = RB == 7 && (long long)g.kb_per_split * BK <= 448;

@@ -54,12 +54,18 @@ struct GemmOut {
     // abs-maxima of the final output for its slicers (optional; zeroed by the caller; not on the split-K path):
     uint32_t *rowmax = nullptr;            // [m] high words (atomicMax)
     unsigned long long *colmax = nullptr;  // [n] bit patterns, high word << 32 (atomicMax) - same encoding as slice_rows' colmax
+    // relu sign bits, one 64-bit word per (row, half n-tile): written by a relu GEMM (relu_bits), consumed INSTEAD of the
+    // float64 mask by the relu-backward GEMM over the same [m][n] shape (mask_bits): 8 bytes per thread and tile in place of
+    // BN / 2 doubles.  Both [m][2 * gemm_ntiles(n, S)] words.
+    unsigned long long *relu_bits = nullptr;
+    const unsigned long long *mask_bits = nullptr;
     int splits_used = 0;            // out
     long long ldp = 0;              // out
 };
 long long gemm_work_bytes(long long m, int n, long long kp, int force_splits);
 int choose_splits(long long m, int n, long long kp, int S);
 long long gemm_tiles(long long m, int n, int S);      // output tiles of one split
+int gemm_ntiles(int n, int S);                        // n-tiles (columns of tiles) of an [m][n] output
 // C = A B^T from slices A [S][m][kp], B [S][n][kp]
 int gemm(const int8_t *a, const int32_t *ea, long long m, const int8_t *b, const int32_t *eb, int n, long long kp, int S,
          GemmOut &o, cudaStream_t st);
