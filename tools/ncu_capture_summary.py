@@ -3,7 +3,7 @@
 extracted from `ncu --set full --clock-control none` captures of the CURRENT build at the headline configuration.  bench.py
 reads this file instead of carrying literals; every entry names its .ncu-rep, the commit and the date.
 
-   python tools/ncu_capture_summary.py key=path.ncu-rep [key=path ...]      keys: rollout_kernel_t4, gae, oz_gemm_kernel
+   python tools/ncu_capture_summary.py key=path.ncu-rep[:launch] [key=path ...]      keys: rollout_kernel_t4, gae, oz_gemm_kernel
 """
 import csv
 import datetime
@@ -37,7 +37,12 @@ def main():
     cur = json.load(open(OUT)) if os.path.exists(OUT) else {}
     for arg in sys.argv[1:]:
         key, rep = arg.split('=', 1)
+        sel = None
+        if ':' in rep:                  # path.ncu-rep:i  -> launch i of the capture only
+            rep, sel = rep.rsplit(':', 1)
         launches = raw(rep)
+        if sel is not None:
+            launches = [launches[int(sel)]]
         # several launches of one logical call (the GAE scan = 3 kernels) are summed
         ent = {'source': os.path.relpath(rep, ROOT), 'commit': commit, 'date': datetime.date.today().isoformat(),
                'kernels': [l['Kernel Name'][0] for l in launches],
