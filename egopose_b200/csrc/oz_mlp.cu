@@ -230,7 +230,7 @@ static MlpPlan mlp_plan(char *base, int in, int h1, int h2, int od, long long M,
     P.a1 = B.take<double>(M * h1); P.a2 = B.take<double>(M * h2); P.d1 = B.take<double>(M * h1); P.d2 = B.take<double>(M * h2);
     P.ybuf = B.take<double>(M * od); P.dy = B.take<double>(M * od);
     P.rmax = B.take<uint32_t>(M);
-    P.a1b = B.take<unsigned long long>(M * 2 * gemm_ntiles(h1, S)); P.a2b = B.take<unsigned long long>(M * 2 * gemm_ntiles(h2, S));
+    P.a1b = B.take<unsigned long long>(M * gemm_bits_words(h1, S)); P.a2b = B.take<unsigned long long>(M * gemm_bits_words(h2, S));
     P.a1s = Sl{B.take<int8_t>(S * M * kh1), B.take<int32_t>(M)}; P.a2s = Sl{B.take<int8_t>(S * M * kh2), B.take<int32_t>(M)};
     P.d2s = Sl{B.take<int8_t>(S * M * kh2), B.take<int32_t>(M)}; P.dys = Sl{B.take<int8_t>(S * M * kod), B.take<int32_t>(M)};
     P.a1T = Sl{B.take<int8_t>(S * (h1 + 1) * MP), B.take<int32_t>(h1 + 16)}; P.a2T = Sl{B.take<int8_t>(S * (h2 + 1) * MP), B.take<int32_t>(h2 + 16)};

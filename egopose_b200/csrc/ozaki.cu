@@ -37,12 +37,19 @@ namespace egp {
 namespace oz {
 
 constexpr int UMMA_K = 32;                      // K per tcgen05.mma for 8-bit operands
-constexpr int EPI_WARPS = 8;
+#ifndef OZ_EPI_WARPS
+#define OZ_EPI_WARPS 16
+#endif
+constexpr int EPI_WARPS = OZ_EPI_WARPS;             // 8: two warps per lane quadrant (half a tile's columns each); 16: four (a quarter each)
+constexpr int EPI_PARTS = EPI_WARPS / 4;            // column parts of a tile
+constexpr int CW = EPI_PARTS == 2 ? 8 : 4;          // columns per drain / post chunk (registers: 576 threads leave 96 per thread)
+constexpr int OUT_BUF_BYTES = 32 * CW * 8;          // one output staging buffer: 32 rows x CW doubles
+static_assert(EPI_WARPS == 8 || EPI_WARPS == 16, "epilogue warps");
 #ifndef OZ_OUT_BUFS
 #define OZ_OUT_BUFS 2
 #endif
 constexpr int OUT_BUFS = OZ_OUT_BUFS;               // 32 x 64 B output staging buffers per epilogue warp (TMA stores in flight)
-constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;   // warp 0: TMA producer, warp 1: MMA issuer, warps 2-9: epilogue
+constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;   // warp 0: TMA producer, warp 1: MMA issuer, the others: epilogue
 constexpr int SMEM_LIMIT = 227 * 1024 - 2048;   // dynamic shared memory: 227 KB minus the static barriers
 constexpr int MAX_STAGES = 12;
 #ifndef OZ_WIDE_N
@@ -576,6 +583,10 @@ __host__ __device__ constexpr uint32_t idesc_i8(int bn, bool a_signed = true, bo
     return (2u << 4) | ((a_signed ? 1u : 0u) << 7) | ((b_signed ? 1u : 0u) << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, int *r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, int *r) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr) : "memory");
@@ -585,7 +596,7 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, int *r) {
 // Radix 128: G = 4; SMALLK (contraction <= 448): neighbours are first merged in int32 (|acc_d| <= (d + 1) K 2^12).
 // Radix 256: G = 3 (|acc_d| < 2^31 -> every group stays below 2^53).
 template <int S, bool SMALLK>
-__device__ __forceinline__ double oz_horner(const int (&acc)[S][8], int j, double rs_hi, double rs_lo) {
+__device__ __forceinline__ double oz_horner(const int (&acc)[S][CW], int j, double rs_hi, double rs_lo) {
     constexpr int GMAX = RB == 8 ? 3 : 4;
     constexpr int G = S < GMAX ? S : GMAX, L = S - G;
     long long hi, lo = 0;
@@ -781,9 +792,9 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // MMA warp.  Post: scale / bias / relu / mask, 32 x 8 blocks through a 64-byte-swizzled shared buffer -> TMA store
         // (full sectors, clipped at the matrix edge by the tensor map); overlaps the next tile's MMAs.
         const int q = warp & 3, half = (warp - 2) >> 2;
-        constexpr int HC = BN / 2;                                     // columns per warp
-        uint8_t *obuf = smem + (size_t)stages * STAGE + (size_t)(warp - 2) * (OUT_BUFS * 2048);
-        double *colc = reinterpret_cast<double *>(smem + (size_t)stages * STAGE + EPI_WARPS * (OUT_BUFS * 2048)) + (warp - 2) * 2 * HC;
+        constexpr int HC = BN / EPI_PARTS;                                     // columns per warp
+        uint8_t *obuf = smem + (size_t)stages * STAGE + (size_t)(warp - 2) * (OUT_BUFS * OUT_BUF_BYTES);
+        double *colc = reinterpret_cast<double *>(smem + (size_t)stages * STAGE + EPI_WARPS * (OUT_BUFS * OUT_BUF_BYTES)) + (warp - 2) * 2 * HC;
         uint32_t tc = 0, nstore = 0;
 #ifdef OZ_PROFILE
         long long e_wait = 0, e_drain = 0, e_post = 0, e_tot = clock64(), e0;
@@ -816,7 +827,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             uint32_t mb_lo = ~0u, mb_hi = ~0u, rb_lo = 0u, rb_hi = 0u;       // columns 0-31 | 32.. of this thread's half tile
             if (g.mask_bits && row_ok) {
-                const unsigned long long mb = __ldcs(g.mask_bits + row * (2 * g.nt) + 2 * n_blk + half);
+                const unsigned long long mb = __ldcs(g.mask_bits + row * (EPI_PARTS * g.nt) + EPI_PARTS * n_blk + half);
                 mb_lo = (uint32_t)mb; mb_hi = (uint32_t)(mb >> 32);
             }
 #ifdef OZ_PROFILE
@@ -831,43 +842,46 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint32_t hrow = 0u;                                        // running |.| maximum of this thread's row (high words)
             const uint32_t hmask = row_ok ? 0x7fffffffu : 0u;         // rows outside the matrix hold the bias only
 #pragma unroll
-            for (int c0 = 0; c0 < HC; c0 += 8) {
-                int acc[S][8];
+            for (int c0 = 0; c0 < HC; c0 += CW) {
+                int acc[S][CW];
 #pragma unroll
-                for (int d = 0; d < S; d++) tmem_ld8(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(d * BN + half * HC + c0), acc[d]);
+                for (int d = 0; d < S; d++) {
+                    const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(d * BN + half * HC + c0);
+                    if constexpr (CW == 8) tmem_ld8(ta, acc[d]); else tmem_ld4(ta, acc[d]);
+                }
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (c0 + 8 >= HC) {                                    // last chunk is in registers: release TMEM
+                if (c0 + CW >= HC) {                                    // last chunk is in registers: release TMEM
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) mbar_arrive(smem_u32(&tempty_bar));
                 }
                 if (g.smallk) {
 #pragma unroll
-                    for (int jj = 0; jj < 8; jj++) hv[c0 + jj] = oz_horner<S, true>(acc, jj, rs_hi, rs_lo);
+                    for (int jj = 0; jj < CW; jj++) hv[c0 + jj] = oz_horner<S, true>(acc, jj, rs_hi, rs_lo);
                 } else {
 #pragma unroll
-                    for (int jj = 0; jj < 8; jj++) hv[c0 + jj] = oz_horner<S, false>(acc, jj, rs_hi, rs_lo);
+                    for (int jj = 0; jj < CW; jj++) hv[c0 + jj] = oz_horner<S, false>(acc, jj, rs_hi, rs_lo);
                 }
             }
 #ifdef OZ_PROFILE
             e_drain += clock64() - e0; e0 = clock64();
 #endif
 #pragma unroll
-            for (int c0 = 0; c0 < HC; c0 += 8) {
+            for (int c0 = 0; c0 < HC; c0 += CW) {
                 const int colb = col0 + c0;
-                double v[8];
+                double v[CW];
 #pragma unroll
-                for (int jj = 0; jj < 8; jj++) v[jj] = hv[c0 + jj];
+                for (int jj = 0; jj < CW; jj++) v[jj] = hv[c0 + jj];
                 if (!g.partial) {
 #pragma unroll
-                    for (int jj = 0; jj < 8; jj += 2) {
+                    for (int jj = 0; jj < CW; jj += 2) {
                         const double4 cb = *reinterpret_cast<const double4 *>(colc + 2 * (c0 + jj));    // broadcast LDS.128 x2
                         v[jj] = fma(v[jj], cb.x, cb.y);
                         v[jj + 1] = fma(v[jj + 1], cb.z, cb.w);
                     }
                     if (g.relu) {
 #pragma unroll
-                        for (int jj = 0; jj < 8; jj++) {               // max(v, 0) on the integer pipe
+                        for (int jj = 0; jj < CW; jj++) {               // max(v, 0) on the integer pipe
                             long long b = __double_as_longlong(v[jj]);
                             b &= ~(b >> 63);
                             v[jj] = __longlong_as_double(b);
@@ -875,7 +889,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                     if (g.relu_bits) {                                 // after the relu v >= +0: (v > 0) <=> any bit set
 #pragma unroll
-                        for (int jj = 0; jj < 8; jj++) {
+                        for (int jj = 0; jj < CW; jj++) {
                             const uint32_t nz = ((uint32_t)__double2hiint(v[jj]) | (uint32_t)__double2loint(v[jj])) != 0u ? 1u : 0u;
                             if (c0 + jj < 32) rb_lo |= nz << ((c0 + jj) & 31);
                             else rb_hi |= nz << ((c0 + jj) & 31);
@@ -883,19 +897,19 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                     if (g.mask_bits) {
 #pragma unroll
-                        for (int jj = 0; jj < 8; jj++)
+                        for (int jj = 0; jj < CW; jj++)
                             if (!(((c0 + jj < 32 ? mb_lo : mb_hi) >> ((c0 + jj) & 31)) & 1u)) v[jj] = 0.0;
                     } else if (mrow) {
-                        if (g.mask_vec && colb + 8 <= g.N) {
+                        if (g.mask_vec && colb + CW <= g.N) {
 #pragma unroll
-                            for (int jj = 0; jj < 8; jj += 2) {
+                            for (int jj = 0; jj < CW; jj += 2) {
                                 const longlong2 mk = *reinterpret_cast<const longlong2 *>(mrow + colb + jj);
                                 if (!(mk.x > 0)) v[jj] = 0.0;           // bit pattern > 0  <=>  value > +0
                                 if (!(mk.y > 0)) v[jj + 1] = 0.0;
                             }
                         } else {
 #pragma unroll
-                            for (int jj = 0; jj < 8; jj++)
+                            for (int jj = 0; jj < CW; jj++)
                                 if (colb + jj < g.N && !(mrow[colb + jj] > 0.0)) v[jj] = 0.0;
                         }
                     }
@@ -905,7 +919,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     // consumer reads C once instead of once per orientation plus a reduction pass
                     uint32_t hcol = 0u;
 #pragma unroll
-                    for (int jj = 0; jj < 8; jj++) {
+                    for (int jj = 0; jj < CW; jj++) {
                         const uint32_t h = (uint32_t)__double2hiint(v[jj]) & hmask;
                         hrow = max(hrow, h);
                         if (g.colmax) {
@@ -913,18 +927,19 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             if (lane == jj) hcol = cm;
                         }
                     }
-                    if (g.colmax && lane < 8 && colb + lane < g.N && hcol > 0u)
+                    if (g.colmax && lane < CW && colb + lane < g.N && hcol > 0u)
                         atomicMax(g.colmax + colb + lane, (unsigned long long)hcol << 32);
                 }
                 if (g.tma_store) {
-                    uint8_t *buf = obuf + (nstore % OUT_BUFS) * 2048;
+                    uint8_t *buf = obuf + (nstore % OUT_BUFS) * OUT_BUF_BYTES;
                     if (nstore >= OUT_BUFS) {                           // the store that last read this buffer has drained it
                         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(OUT_BUFS - 1) : "memory");
                         __syncwarp();
                     }
-                    const uint32_t rb = smem_u32(buf) + lane * 64, sw = (lane >> 1) & 3;
+                    // row = lane, CW * 8 bytes per row, 16-byte chunks swizzled as the output tensor map expects (64 B / 32 B swizzle)
+                    const uint32_t rb = smem_u32(buf) + lane * (CW * 8), sw = CW == 8 ? ((lane >> 1) & 3) : ((lane >> 2) & 1);
 #pragma unroll
-                    for (int c = 0; c < 4; c++)
+                    for (int c = 0; c < CW / 2; c++)
                         asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(rb + ((c ^ sw) << 4)), "d"(v[2 * c]), "d"(v[2 * c + 1]) : "memory");
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
@@ -936,12 +951,12 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     nstore++;
                 } else if (row_ok) {
 #pragma unroll
-                    for (int jj = 0; jj < 8; jj++)
+                    for (int jj = 0; jj < CW; jj++)
                         if (colb + jj < g.N) crow[colb + jj] = v[jj];
                 }
             }
             if (g.rowmax && row_ok && hrow > 0u) atomicMax(g.rowmax + row, hrow);
-            if (g.relu_bits && row_ok) g.relu_bits[row * (2 * g.nt) + 2 * n_blk + half] = ((unsigned long long)rb_hi << 32) | rb_lo;
+            if (g.relu_bits && row_ok) g.relu_bits[row * (EPI_PARTS * g.nt) + EPI_PARTS * n_blk + half] = ((unsigned long long)rb_hi << 32) | rb_lo;
 #ifdef OZ_PROFILE
             e_post += clock64() - e0;
 #endif
@@ -992,15 +1007,15 @@ static int make_map_out(CUtensorMap *tm, const double *base, long long rows, int
     if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return EGP_ECUDA; }
     cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)splits};
     cuuint64_t strides[2] = {(cuuint64_t)ld * 8, (cuuint64_t)ld * 8 * (cuuint64_t)rows};
-    cuuint32_t box[3] = {8, 32, 1};
+    cuuint32_t box[3] = {(cuuint32_t)CW, 32, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    CW == 8 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (output) failed with %d (rows %lld cols %d ld %lld)", (int)r, rows, cols, ld); return EGP_ECUDA; }
     return EGP_OK;
 }
 
-constexpr int OUT_STAGE_BYTES = EPI_WARPS * OUT_BUFS * 2048 + EPI_WARPS * 2 * 40 * 8;   // per epilogue warp: two 32 x 64 B staging buffers + (2^eb, bias) per column
+constexpr int OUT_STAGE_BYTES = EPI_WARPS * OUT_BUFS * OUT_BUF_BYTES + EPI_WARPS * 2 * (80 / EPI_PARTS) * 8;   // per epilogue warp: two 32 x 64 B staging buffers + (2^eb, bias) per column
 
 template <int S, int BN>
 static int launch_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC, GemmArgs g, cudaStream_t st) {
@@ -1040,6 +1055,7 @@ int gemm_ntiles(int n, int S) {
     const int bn = pick_bn(n, S);
     return (n + bn - 1) / bn;
 }
+int gemm_bits_words(int n, int S) { return EPI_PARTS * gemm_ntiles(n, S); }
 
 long long gemm_tiles(long long m, int n, int S) {
     const int bn = pick_bn(n, S);

@@ -7,9 +7,14 @@ namespace oz {
 
 constexpr int BM = 128;             // output rows per tile (tcgen05 M)
 #ifndef OZ_BK
-#define OZ_BK 32
+#define OZ_BK 64
 #endif
-constexpr int BK = OZ_BK;           // contraction bytes per stage row (32: one tcgen05.mma.kind::i8 K step, 32-byte swizzle; 64: two, 64-byte swizzle)
+// Contraction bytes per stage row (32: one tcgen05.mma.kind::i8 K step, 32-byte swizzle; 64: two, 64-byte swizzle).  The TMA
+// unit serves about one box ROW per clock whatever its width, and a 128 x 80 x K tile asks for (128 + 80) S K / BK operand rows:
+// at BK = 32 that is 12.5 k requests per 17 k-clock tile (K = 320) and the producer's AND the epilogue's store requests queue
+// behind each other (the store instruction itself stalled ~700 clocks); 64-byte rows halve the request count (two stages of
+// 80 KB instead of four of 40 KB: same bytes in flight).
+constexpr int BK = OZ_BK;
 #ifndef OZ_RADIX_BITS
 #define OZ_RADIX_BITS 7
 #endif
@@ -20,7 +25,7 @@ constexpr int BK = OZ_BK;           // contraction bytes per stage row (32: one 
 // is ~200x LESS accurate than the centred radix-128 digits despite the extra bit per slice (err / max|C| 6.8e-10 at S = 5
 // vs 3.1e-10 for radix 128 at S = 5 and 3.8e-12 at S = 6) - no gain, kept only as a documented negative result.
 constexpr int RB = OZ_RADIX_BITS;
-constexpr int MAX_S = RB == 8 ? 6 : 8;
+constexpr int MAX_S = RB == 8 ? 6 : (BK == 64 ? 7 : 8);     // 8 slices x two 64-byte stages do not fit shared memory (7 = DGEMM rounding level)
 constexpr int EOFF = 2 - 2 * RB;    // C = 2^(ea + eb + EOFF) * sum_d acc_d 2^(-RB d)
 // k blocks of one int32 accumulation: S pairs x K x max |digit product| < 2^31
 inline long long max_kblocks(int S) { return RB == 8 ? (((1LL << 31) / (65025LL * S * BK)) & ~1LL) : ((16384 / S * 32 / BK) & ~1LL); }
@@ -56,7 +61,7 @@ struct GemmOut {
     unsigned long long *colmax = nullptr;  // [n] bit patterns, high word << 32 (atomicMax) - same encoding as slice_rows' colmax
     // relu sign bits, one 64-bit word per (row, half n-tile): written by a relu GEMM (relu_bits), consumed INSTEAD of the
     // float64 mask by the relu-backward GEMM over the same [m][n] shape (mask_bits): 8 bytes per thread and tile in place of
-    // BN / 2 doubles.  Both [m][2 * gemm_ntiles(n, S)] words.
+    // its columns as doubles.  Both [m][gemm_bits_words(n, S)] words (one per epilogue warp of the row).
     unsigned long long *relu_bits = nullptr;
     const unsigned long long *mask_bits = nullptr;
     int splits_used = 0;            // out
@@ -66,6 +71,7 @@ long long gemm_work_bytes(long long m, int n, long long kp, int force_splits);
 int choose_splits(long long m, int n, long long kp, int S);
 long long gemm_tiles(long long m, int n, int S);      // output tiles of one split
 int gemm_ntiles(int n, int S);                        // n-tiles (columns of tiles) of an [m][n] output
+int gemm_bits_words(int n, int S);                    // 64-bit words per row of the relu sign bits of an [m][n] output
 // C = A B^T from slices A [S][m][kp], B [S][n][kp]
 int gemm(const int8_t *a, const int32_t *ea, long long m, const int8_t *b, const int32_t *eb, int n, long long kp, int S,
          GemmOut &o, cudaStream_t st);
