@@ -797,7 +797,12 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         double *colc = reinterpret_cast<double *>(smem + (size_t)stages * STAGE + EPI_WARPS * (OUT_BUFS * OUT_BUF_BYTES)) + (warp - 2) * 2 * HC;
         uint32_t tc = 0, nstore = 0;
 #ifdef OZ_PROFILE
-        long long e_wait = 0, e_drain = 0, e_post = 0, e_tot = clock64(), e0;
+        long long e_wait = 0, e_drain = 0, e_post = 0, e_tot = clock64(), e0, e1, e_wg = 0, e_st = 0, e_fence = 0, e_issue = 0, e_math = 0;
+#define OZ_E1 e1 = clock64()
+#define OZ_EACC(v) v += clock64() - e1
+#else
+#define OZ_E1
+#define OZ_EACC(v)
 #endif
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tc++) {
             const int n_blk = (int)(tile % g.nt);
@@ -870,6 +875,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int c0 = 0; c0 < HC; c0 += CW) {
                 const int colb = col0 + c0;
                 double v[CW];
+                OZ_E1;
 #pragma unroll
                 for (int jj = 0; jj < CW; jj++) v[jj] = hv[c0 + jj];
                 if (!g.partial) {
@@ -927,27 +933,35 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             if (lane == jj) hcol = cm;
                         }
                     }
+                    // (combining these in shared memory first was tried: slower, 255 -> 303 us - shared-memory atomics queue behind the
+                    // tensor cores' operand reads; the global reductions are fire-and-forget)
                     if (g.colmax && lane < CW && colb + lane < g.N && hcol > 0u)
                         atomicMax(g.colmax + colb + lane, (unsigned long long)hcol << 32);
                 }
+                OZ_EACC(e_math);
                 if (g.tma_store) {
                     uint8_t *buf = obuf + (nstore % OUT_BUFS) * OUT_BUF_BYTES;
+                    OZ_E1;
                     if (nstore >= OUT_BUFS) {                           // the store that last read this buffer has drained it
                         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(OUT_BUFS - 1) : "memory");
                         __syncwarp();
                     }
+                    OZ_EACC(e_wg); OZ_E1;
                     // row = lane, CW * 8 bytes per row, 16-byte chunks swizzled as the output tensor map expects (64 B / 32 B swizzle)
                     const uint32_t rb = smem_u32(buf) + lane * (CW * 8), sw = CW == 8 ? ((lane >> 1) & 3) : ((lane >> 2) & 1);
 #pragma unroll
                     for (int c = 0; c < CW / 2; c++)
                         asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(rb + ((c ^ sw) << 4)), "d"(v[2 * c]), "d"(v[2 * c + 1]) : "memory");
+                    OZ_EACC(e_st); OZ_E1;
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
+                    OZ_EACC(e_fence); OZ_E1;
                     if (lane == 0) {
                         asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
                                      ::"l"((uint64_t)&tmC), "r"(smem_u32(buf)), "r"(colb), "r"(m_blk * BM + q * 32), "r"(z) : "memory");
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
+                    OZ_EACC(e_issue);
                     nstore++;
                 } else if (row_ok) {
 #pragma unroll
@@ -962,7 +976,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #endif
         }
 #ifdef OZ_PROFILE
-        if (blockIdx.x == 0 && warp == 2 && lane == 0) printf("epi warp: total %lld  wait tfull %lld  drain %lld  post %lld\n", clock64() - e_tot, e_wait, e_drain, e_post);
+        if (blockIdx.x == 0 && warp == 2 && lane == 0) printf("epi warp: total %lld  wait tfull %lld  drain %lld  post %lld (math %lld  wait_group %lld  st.shared %lld  fence %lld  tma issue %lld)\n", clock64() - e_tot, e_wait, e_drain, e_post, e_math, e_wg, e_st, e_fence, e_issue);
 #endif
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
