@@ -40,6 +40,9 @@ constexpr int UMMA_K = 32;                      // K per tcgen05.mma for 8-bit o
 #ifndef OZ_EPI_WARPS
 #define OZ_EPI_WARPS 16
 #endif
+#ifndef OZ_COLC_SHFL
+#define OZ_COLC_SHFL 0
+#endif
 constexpr int EPI_WARPS = OZ_EPI_WARPS;             // 8: two warps per lane quadrant (half a tile's columns each); 16: four (a quarter each)
 constexpr int EPI_PARTS = EPI_WARPS / 4;            // column parts of a tile
 constexpr int CW = EPI_PARTS == 2 ? 8 : 4;          // columns per drain / post chunk (registers: 576 threads leave 96 per thread)
@@ -819,6 +822,19 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const double rs_hi = pow2(ea - RB * (GH - 1)), rs_lo = pow2(ea - RB * (S - 1));
             double *crow = g.C + ((size_t)z * (g.partial ? g.M : 0) + (row_ok ? row : 0)) * g.ldc;
             const double *mrow = (g.mask && row_ok) ? g.mask + row * g.ldm : nullptr;
+#if OZ_COLC_SHFL
+            // column constants of this warp's columns kept in lane c's registers (2^eb as its exponent, the bias) and broadcast
+            // by shuffles in the post phase instead of staged in shared memory
+            static_assert(!OZ_COLC_SHFL || BN / EPI_PARTS <= 32, "one column per lane");
+            int c_eb = 0;
+            double c_bias = 0.0;
+            if (!g.partial && lane < HC) {
+                const int col = col0 + lane;
+                int eb = col < g.N ? g.eb[col] : 0;
+                c_eb = eb < -1022 ? -1022 : (eb > 1023 ? 1023 : eb);
+                if (g.bias && col < g.N) c_bias = g.bias[col];
+            }
+#else
             if (!g.partial) {
                 __syncwarp();
                 for (int c = lane; c < HC; c += 32) {
@@ -830,6 +846,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 __syncwarp();
             }
+#endif
             uint32_t mb_lo = ~0u, mb_hi = ~0u, rb_lo = 0u, rb_hi = 0u;       // columns 0-31 | 32.. of this thread's half tile
             if (g.mask_bits && row_ok) {
                 const unsigned long long mb = __ldcs(g.mask_bits + row * (EPI_PARTS * g.nt) + EPI_PARTS * n_blk + half);
@@ -879,12 +896,21 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                 for (int jj = 0; jj < CW; jj++) v[jj] = hv[c0 + jj];
                 if (!g.partial) {
+#if OZ_COLC_SHFL
+#pragma unroll
+                    for (int jj = 0; jj < CW; jj++) {
+                        const double sc = pow2(__shfl_sync(0xffffffffu, c_eb, c0 + jj));
+                        const double bi = g.bias ? __shfl_sync(0xffffffffu, c_bias, c0 + jj) : 0.0;
+                        v[jj] = fma(v[jj], sc, bi);
+                    }
+#else
 #pragma unroll
                     for (int jj = 0; jj < CW; jj += 2) {
                         const double4 cb = *reinterpret_cast<const double4 *>(colc + 2 * (c0 + jj));    // broadcast LDS.128 x2
                         v[jj] = fma(v[jj], cb.x, cb.y);
                         v[jj + 1] = fma(v[jj + 1], cb.z, cb.w);
                     }
+#endif
                     if (g.relu) {
 #pragma unroll
                         for (int jj = 0; jj < CW; jj++) {               // max(v, 0) on the integer pipe
