@@ -306,8 +306,10 @@ def main():
         batch, log = agent.sample(N, to_host=host)
         agent.env.end_reward = log.avg_c_reward * cfg.gamma / (1 - cfg.gamma)       # ego_mimic.py:112
         if host:        # reference-format call: a batch object that only carries host (numpy) arrays
-            batch = TrajBatchEgo(host={k: getattr(batch, k) for k in batch.fields}, horizon=T, pinned=batch._pinned)
+            batch = batch.host_only()
         agent.update_params(batch)
+        if host:
+            batch.wait_host()           # the step ends when every downloaded array has landed (next_states comes down last)
         return log
 
     for _ in range(args.warmup):

@@ -334,6 +334,9 @@ class Agent:
         a batch kept across iterations must be copied by the caller; the reference returns independent arrays."""
         t_start = time.time()
         self.pre_sample()
+        if getattr(self, '_d2h_done', None) is not None:
+            torch.cuda.current_stream().wait_event(self._d2h_done)     # the last batch's downloads read the buffers this rollout overwrites
+            self._d2h_done = None
         E, T = self.plan(min_batch_size)
         w = self._policy_weights()
         rs = self.running_state
@@ -367,7 +370,16 @@ class Agent:
                                        (lib.LOG['MAX_C_REWARD'], lib.LOG['MAX_EPISODE_REWARD']))
         logger = self.logger_cls.from_device(lg.cpu().numpy())     # D2H of 16 doubles: the rollout's sync point
         if to_host:
-            batch.to_host(self._host_pool)
+            # downloads on a side stream, one event per field (TrajBatch.to_host): update_params() re-uploads field k while
+            # field k + 1 is still coming down, numpy readers wait for the array they touch; EGP_D2H_STREAM=0: one blocking pass
+            if os.environ.get('EGP_D2H_STREAM', '1') != '0':
+                if getattr(self, '_copy_stream', None) is None:
+                    self._copy_stream = torch.cuda.Stream(device=lg.device)
+                batch.to_host(self._host_pool, stream=self._copy_stream)
+                self._d2h_done = torch.cuda.Event()
+                self._d2h_done.record(self._copy_stream)
+            else:
+                batch.to_host(self._host_pool)
         logger.sample_time = time.time() - t_start
         return batch, logger
 
@@ -483,6 +495,9 @@ class AgentPG(Agent):
                     self._host_pool['up.' + name] = stage
                 stage.numpy()[...] = a
                 src = stage
+            ev = batch.host_event(name) if hasattr(batch, 'host_event') else None
+            if ev is not None:
+                torch.cuda.current_stream().wait_event(ev)      # the download of this field is still in flight: wait on the device
             return src.to(dev, non_blocking=True).to(dtype)
         has_vm = 'v_metas' in getattr(batch, '_host', {}) or (not hasattr(batch, '_host') and hasattr(batch, 'v_metas'))
         vm = up('v_metas', torch.int32) if has_vm else None

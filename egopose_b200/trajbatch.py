@@ -8,6 +8,14 @@ import numpy as np
 _FIELDS = ('states', 'actions', 'masks', 'next_states', 'rewards', 'exps', 'v_metas')
 
 
+class _null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
 class TrajBatch:
     fields = _FIELDS[:6]
 
@@ -16,6 +24,7 @@ class TrajBatch:
         self.horizon = horizon          # rows per environment (None for reference-format batches)
         self._host = dict(host or {})
         self._pinned = dict(pinned or {})   # name -> pinned CPU tensor backing the numpy view in _host
+        self._events = {}               # name -> CUDA event of a device-to-host copy still in flight (to_host(stream=...))
 
     @classmethod
     def from_numpy(cls, **arrays):
@@ -23,6 +32,9 @@ class TrajBatch:
 
     def __getattr__(self, name):
         if name in _FIELDS:
+            ev = self.__dict__.get('_events', {}).pop(name, None)
+            if ev is not None:
+                ev.synchronize()        # the copy behind this array was issued asynchronously: wait for it (only it)
             if name not in self._host:
                 if name not in self.dev or self.dev[name] is None:
                     raise AttributeError('%s was not recorded by this rollout%s' % (
@@ -34,33 +46,67 @@ class TrajBatch:
             return self._host[name]
         raise AttributeError(name)
 
-    def to_host(self, pool=None):
+    def to_host(self, pool=None, stream=None):
         """materialise every field on the host.  With ``pool`` (dict name -> pinned CPU tensor, reused across
         iterations) the copies are asynchronous DMA into page-locked memory with one synchronise at the end;
-        the numpy attributes are views of those buffers (valid until the next sample())."""
+        the numpy attributes are views of those buffers (valid until the next sample()).
+        With ``stream`` (a CUDA side stream) nothing is synchronised here: the copies run on that stream in the order the
+        update consumes the fields (``next_states``, which it never reads, last), every field gets its own event, a numpy
+        attribute waits for its event on first access, and ``host_event(name)`` lets a consumer on another stream wait on
+        the device instead (the re-upload of field k then overlaps the download of field k + 1: PCIe is full duplex)."""
         import torch
         if pool is None:
             for f in self.fields:
                 if f in self.dev and self.dev[f] is not None:
                     getattr(self, f)
             return self
-        for f in self.fields:
-            t = self.dev.get(f)
-            if t is None:
-                continue
-            want = torch.int64 if f in ('masks', 'exps') else t.dtype
-            buf = pool.get(f)
-            if buf is None or buf.shape != t.shape or buf.dtype != want:
-                buf = torch.empty(t.shape, dtype=want, pin_memory=True)
-                pool[f] = buf
-            if want != t.dtype:
-                t = t.to(want)              # device-side cast, then DMA
-            buf.copy_(t, non_blocking=True)
-            self._pinned[f] = buf
-        torch.cuda.current_stream().synchronize()
+        order = [f for f in ('v_metas', 'states', 'actions', 'rewards', 'masks', 'exps', 'next_states') if f in self.fields]
+        if stream is not None:
+            stream.wait_stream(torch.cuda.current_stream())     # the rollout, and earlier uploads out of these pinned buffers
+        with torch.cuda.stream(stream) if stream is not None else _null():
+            for f in order:
+                t = self.dev.get(f)
+                if t is None:
+                    continue
+                want = torch.int64 if f in ('masks', 'exps') else t.dtype
+                buf = pool.get(f)
+                if buf is None or buf.shape != t.shape or buf.dtype != want:
+                    buf = torch.empty(t.shape, dtype=want, pin_memory=True)
+                    pool[f] = buf
+                if want != t.dtype:
+                    t = t.to(want)              # device-side cast, then DMA
+                buf.copy_(t, non_blocking=True)
+                self._pinned[f] = buf
+                if stream is not None:
+                    ev = torch.cuda.Event()
+                    ev.record(stream)
+                    self._events[f] = ev
+        if stream is None:
+            torch.cuda.current_stream().synchronize()
         for f, buf in self._pinned.items():
             self._host[f] = buf.numpy()
         return self
+
+    def host_event(self, name):
+        """CUDA event of the still pending device-to-host copy behind ``name`` (None when the array is complete)"""
+        return self._events.get(name)
+
+    def wait_host(self):
+        """block until every asynchronous device-to-host copy of this batch has landed"""
+        for ev in list(self._events.values()):
+            ev.synchronize()
+        self._events.clear()
+        return self
+
+    def host_only(self):
+        """the same batch as a reference-format object: numpy arrays only (views of the pinned buffers, pending copies and
+        their events carried over), no device tensors - what a caller that built the batch from host data would pass"""
+        b = type(self)(host=dict(self._host), horizon=self.horizon, pinned=dict(self._pinned))
+        b._events = self._events            # shared: whoever waits first clears the entry for both
+        for f in self.fields:
+            if f not in b._host and self.dev.get(f) is not None:
+                b._host[f] = getattr(self, f)
+        return b
 
     def pinned(self, name):
         """the pinned tensor behind attribute ``name`` if it is one of ours and still the exposed array"""

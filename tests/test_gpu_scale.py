@@ -264,3 +264,36 @@ def test_two_ranks_on_one_gpu_equal_single_rank():
     res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert 'EQUIVALENT' in res.stdout and 'torch.distributed all_reduce' in res.stdout, res.stdout[-3000:]
+
+
+def test_streamed_host_batch_updates_like_the_device_batch():
+    """sample(to_host=True) downloads on a side stream with one event per field (TrajBatch.to_host(stream=...)): the update
+    from the host-only batch waits for the downloads ON THE DEVICE and re-uploads field by field; a numpy reader waits for
+    the array it touches.  Same parameters as the update from the device batch; arrays identical to the device tensors."""
+    from egopose_b200.trajbatch import TrajBatch
+    N, D, H, A = 300000, 40, (48, 32), 7
+    bufs = _synthetic_batch(N, D, A, seed=3)
+    mk = lambda: TrajBatch(dev=dict(states=bufs[0], actions=bufs[1], rewards=bufs[2], masks=bufs[3], exps=bufs[4]), horizon=None)  # noqa: E731
+    a_dev, a_host = _agent('cublas', D, H, A, seed=9, epochs=2), _agent('cublas', D, H, A, seed=9, epochs=2)
+    side, pool = torch.cuda.Stream(), {}
+    for it in range(2):
+        a_dev.update_params(mk())
+        b = mk().to_host(pool, stream=side)
+        assert b.host_event('states') is not None            # nothing was synchronised
+        hb = b.host_only()
+        assert not hb.dev and hb.pinned('states') is not None
+        a_host.update_params(hb)
+        hb.wait_host()
+        assert b.host_event('states') is None and np.array_equal(b.states, bufs[0].cpu().numpy())
+        assert b.masks.dtype == np.int64 and np.array_equal(b.masks, bufs[3].cpu().numpy().astype(np.int64))
+        for dst, src in zip(bufs, _synthetic_batch(N, D, A, seed=20 + it)):
+            side.synchronize()
+            dst.copy_(src)
+    for p1, p2 in zip(list(a_dev.policy_net.parameters()) + list(a_dev.value_net.parameters()),
+                      list(a_host.policy_net.parameters()) + list(a_host.value_net.parameters())):
+        assert torch.allclose(p1.data, p2.data, rtol=1e-9, atol=1e-12)
+    # a reader that touches one array waits for that array only
+    b = mk().to_host(pool, stream=side)
+    r = b.rewards
+    assert np.array_equal(r, bufs[2].cpu().numpy()) and b.host_event('rewards') is None
+    b.wait_host()
