@@ -495,9 +495,16 @@ class AgentPG(Agent):
                     self._host_pool['up.' + name] = stage
                 stage.numpy()[...] = a
                 src = stage
-            ev = batch.host_event(name) if hasattr(batch, 'host_event') else None
-            if ev is not None:
-                torch.cuda.current_stream().wait_event(ev)      # the download of this field is still in flight: wait on the device
+            chunks = batch.host_chunks(name) if hasattr(batch, 'host_chunks') else []
+            if chunks:
+                # the download of this field is still in flight: wait for it on the device, chunk by chunk, and send every chunk
+                # back up as soon as it has landed (the two directions of the link run at the same time)
+                out = torch.empty(src.shape, dtype=src.dtype, device=dev)
+                cur = torch.cuda.current_stream()
+                for r0, r1, ev in chunks:
+                    cur.wait_event(ev)
+                    out[r0:r1].copy_(src[r0:r1], non_blocking=True)
+                return out.to(dtype)
             return src.to(dev, non_blocking=True).to(dtype)
         has_vm = 'v_metas' in getattr(batch, '_host', {}) or (not hasattr(batch, '_host') and hasattr(batch, 'v_metas'))
         vm = up('v_metas', torch.int32) if has_vm else None

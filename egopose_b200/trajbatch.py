@@ -6,6 +6,7 @@ first access so that the fused update path, which reads ``.dev`` directly, pays 
 import numpy as np
 
 _FIELDS = ('states', 'actions', 'masks', 'next_states', 'rewards', 'exps', 'v_metas')
+_CHUNK_BYTES = 128 << 20
 
 
 class _null:
@@ -25,6 +26,7 @@ class TrajBatch:
         self._host = dict(host or {})
         self._pinned = dict(pinned or {})   # name -> pinned CPU tensor backing the numpy view in _host
         self._events = {}               # name -> CUDA event of a device-to-host copy still in flight (to_host(stream=...))
+        self._chunks = {}               # name -> [(row0, row1, event)] of that copy
 
     @classmethod
     def from_numpy(cls, **arrays):
@@ -75,17 +77,32 @@ class TrajBatch:
                     pool[f] = buf
                 if want != t.dtype:
                     t = t.to(want)              # device-side cast, then DMA
-                buf.copy_(t, non_blocking=True)
                 self._pinned[f] = buf
-                if stream is not None:
+                if stream is None:
+                    buf.copy_(t, non_blocking=True)
+                    continue
+                # large fields go down in row chunks with an event each, so that a consumer can start uploading the head of
+                # the array while its tail is still on the way
+                rows = int(t.shape[0])
+                per = max(1, rows // max(1, (t.numel() * t.element_size()) // _CHUNK_BYTES)) if rows else 1
+                chunks = []
+                for r0 in range(0, max(rows, 1), per):
+                    r1 = min(rows, r0 + per)
+                    buf[r0:r1].copy_(t[r0:r1], non_blocking=True)
                     ev = torch.cuda.Event()
                     ev.record(stream)
-                    self._events[f] = ev
+                    chunks.append((r0, r1, ev))
+                self._chunks[f] = chunks
+                self._events[f] = chunks[-1][2]
         if stream is None:
             torch.cuda.current_stream().synchronize()
         for f, buf in self._pinned.items():
             self._host[f] = buf.numpy()
         return self
+
+    def host_chunks(self, name):
+        """[(row0, row1, event)] of the pending download behind ``name`` (empty when complete or never streamed)"""
+        return self._chunks.get(name, []) if name in self._events else []
 
     def host_event(self, name):
         """CUDA event of the still pending device-to-host copy behind ``name`` (None when the array is complete)"""
@@ -103,6 +120,7 @@ class TrajBatch:
         their events carried over), no device tensors - what a caller that built the batch from host data would pass"""
         b = type(self)(host=dict(self._host), horizon=self.horizon, pinned=dict(self._pinned))
         b._events = self._events            # shared: whoever waits first clears the entry for both
+        b._chunks = self._chunks
         for f in self.fields:
             if f not in b._host and self.dev.get(f) is not None:
                 b._host[f] = getattr(self, f)
