@@ -762,6 +762,14 @@ class OzMlp:
         (unless cached), 3 GEMMs + 2 row / 2 transposed slicings forward, loss, 5 GEMMs + 3 reductions + slicings backward"""
         prep = 3 + (6 if bwd else 0) + (3 if dx else 0)
         x = (3 if (bwd or fill_cache) else 1) if slice_x else 0
+        fused = bwd and load().egp_oz_mlp_set_fused_slicing(-1) != 0
+        if fused:
+            # one-read two-orientation slicing (exponent kernel + slicer per intermediate), no column-maximum passes:
+            # 8 GEMMs, 3 x 2 slice_both, dy rows + 2 x 2 transposed, loss, 3 reductions | scalar head: 5 GEMMs, 2 x 2 + 2, 4 head / loss, 2
+            per_chunk = x + (17 if head1 else 23) + (1 if dx else 0)
+            if head1:
+                prep -= 1 + 3
+            return prep + n_chunks * per_chunk
         per_chunk = x + (9 + 1 + 17 if bwd else 5) + (1 if dx else 0)
         if head1:       # scalar head streamed in float64: no slices of the last hidden layer, head forward / backward + reduce
             prep -= 1 + (3 if bwd else 0)
