@@ -76,6 +76,11 @@ def test_trajbatch_contract():
         b.next_states
     h = TrajBatchEgo.from_numpy(states=np.zeros((2, 115)), rewards=np.zeros(2))
     assert h.states.shape == (2, 115) and len(h) == 2
+    # reference-format copy: host arrays only, nothing pending when no side stream was involved
+    ho = b.host_only()
+    assert not ho.dev and ho.horizon == 3 and np.array_equal(ho.states, b.states) and np.array_equal(ho.masks, b.masks)
+    assert ho.host_event('states') is None and ho.host_chunks('states') == [] and ho.wait_host() is ho
+    assert 'next_states' not in ho._host
 
 
 def test_flat_storage_aliases_modules_and_adam_state():
